@@ -1,0 +1,396 @@
+"""ctypes loader for the CPU oracle (oracle/ring_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; never by the product package.
+Polynomials are numpy uint64 arrays of shape [nlimbs, N] (C-contiguous).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libring_oracle.so")
+
+u64 = C.c_uint64
+p64 = C.POINTER(C.c_uint64)
+vp = C.c_void_p
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "ring_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    def f(name, res, *args):
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+
+    f("orc_bred_params", None, u64, p64)
+    f("orc_mred_params", u64, u64)
+    f("orc_mform", u64, u64, u64, p64)
+    f("orc_mform_constant", u64, u64, u64, p64)
+    f("orc_invmform", u64, u64, u64, u64)
+    f("orc_invmform_constant", u64, u64, u64, u64)
+    f("orc_mred", u64, u64, u64, u64, u64)
+    f("orc_mred_constant", u64, u64, u64, u64, u64)
+    f("orc_bred_add", u64, u64, u64, p64)
+    f("orc_bred_add_constant", u64, u64, u64, p64)
+    f("orc_bred", u64, u64, u64, u64, p64)
+    f("orc_bred_constant", u64, u64, u64, u64, p64)
+    f("orc_cred", u64, u64, u64)
+    f("orc_power_of_2", u64, u64, u64, u64, u64)
+    f("orc_modexp", u64, u64, u64, u64)
+    f("orc_bitreverse64", u64, u64, u64)
+    f("orc_small_prime", u64, C.c_int)
+    f("orc_is_prime", C.c_int, u64)
+    f("orc_generate_ntt_primes", C.c_int, u64, u64, u64, p64)
+    f("orc_primitive_root", u64, u64)
+    f("orc_ctx_new", vp, u64, C.c_int, p64)
+    f("orc_ctx_free", None, vp)
+    f("orc_ctx_scalars", None, vp, p64, p64, p64, p64, p64, p64)
+    f("orc_ctx_tables", None, vp, C.c_int, p64, p64)
+    f("orc_ctx_rescale_param", u64, vp, C.c_int, C.c_int)
+    f("orc_ntt_limb", None, p64, p64, u64, p64, u64, u64, p64)
+    f("orc_invntt_limb", None, p64, p64, u64, p64, u64, u64, u64)
+    f("orc_ntt", None, vp, C.c_int, p64, p64)
+    f("orc_invntt", None, vp, C.c_int, p64, p64)
+    f("orc_ntt_one", None, vp, C.c_int, p64, p64)
+    f("orc_invntt_one", None, vp, C.c_int, p64, p64)
+    for name in ("add", "add_nomod", "sub", "sub_nomod", "mulcoeffs", "mulcoeffs_and_add", "mulcoeffs_and_add_nomod",
+                 "mulcoeffs_constant", "mulcoeffs_montgomery", "mulcoeffs_montgomery_and_add",
+                 "mulcoeffs_montgomery_and_add_nomod", "mulcoeffs_montgomery_constant_and_add_nomod",
+                 "mulcoeffs_montgomery_and_sub", "mulcoeffs_montgomery_and_sub_nomod",
+                 "mulcoeffs_montgomery_constant"):
+        f("orc_" + name, None, vp, C.c_int, p64, p64, p64)
+    for name in ("neg", "reduce", "mform_poly", "invmform_poly", "bitreverse_poly"):
+        f("orc_" + name, None, vp, C.c_int, p64, p64)
+    f("orc_add_scalar", None, vp, C.c_int, p64, p64)
+    f("orc_sub_scalar", None, vp, C.c_int, p64, p64)
+    f("orc_mul_scalar", None, vp, C.c_int, p64, p64, p64)
+    f("orc_mul_by_pow2", None, vp, C.c_int, p64, u64, p64)
+    f("orc_mult_by_monomial", None, vp, C.c_int, p64, u64, p64)
+    f("orc_mul_by_vector_montgomery", None, vp, C.c_int, p64, p64, p64)
+    f("orc_mul_by_vector_montgomery_and_add_nomod", None, vp, C.c_int, p64, p64, p64)
+    f("orc_gen_galois_params", None, u64, u64, p64)
+    f("orc_permute_ntt_index", None, u64, u64, u64, p64)
+    f("orc_permute_ntt_with_index", None, u64, C.c_int, p64, p64, p64)
+    f("orc_permute_ntt", None, u64, C.c_int, p64, u64, p64)
+    f("orc_permute", None, vp, C.c_int, p64, u64, p64)
+    f("orc_extender_new", vp, vp, vp)
+    f("orc_extender_free", None, vp)
+    f("orc_extender_params", None, vp, p64, p64)
+    f("orc_modup_split_qp", None, vp, C.c_int, p64, p64)
+    f("orc_modup_split_pq", None, vp, C.c_int, p64, p64)
+    f("orc_moddown_ntt_pq", None, vp, C.c_int, p64, p64)
+    f("orc_moddown_splited_ntt_pq", None, vp, C.c_int, p64, p64, p64)
+    f("orc_moddown_pq", None, vp, C.c_int, p64, p64)
+    f("orc_moddown_splited_pq", None, vp, C.c_int, p64, p64, p64)
+    f("orc_moddown_splited_qp", None, vp, C.c_int, C.c_int, p64, p64, p64)
+    f("orc_decomposer_new", vp, p64, C.c_int, p64, C.c_int)
+    f("orc_decomposer_free", None, vp)
+    f("orc_decomposer_beta", C.c_int, vp)
+    f("orc_decomposer_xalpha", C.c_int, vp, C.c_int)
+    f("orc_decompose_and_split", None, vp, u64, C.c_int, C.c_int, p64, p64, p64)
+    f("orc_decompose", None, vp, u64, C.c_int, C.c_int, p64, p64)
+    for name in ("div_floor_by_last_modulus_ntt", "div_floor_by_last_modulus", "div_round_by_last_modulus_ntt",
+                 "div_round_by_last_modulus"):
+        f("orc_" + name, None, vp, C.c_int, p64)
+    for name in ("div_floor_by_last_modulus_many", "div_floor_by_last_modulus_many_ntt",
+                 "div_round_by_last_modulus_many", "div_round_by_last_modulus_many_ntt"):
+        f("orc_" + name, None, vp, C.c_int, p64, C.c_int)
+    f("orc_ckks_eval_new", vp, vp, vp)
+    f("orc_ckks_eval_free", None, vp)
+    f("orc_ckks_switch_keys_in_place", None, vp, C.c_int, p64, p64, p64, p64)
+    f("orc_ckks_mul_relin", None, vp, C.c_int, p64, p64, p64, p64)
+    f("orc_ckks_rescale", None, vp, C.c_int, p64, C.c_int)
+    f("orc_ckks_permute_ntt", None, vp, C.c_int, p64, p64, p64, p64)
+    f("orc_ckks_switch_keys", None, vp, C.c_int, p64, p64, p64)
+
+
+def ptr(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"], (a.dtype, a.flags)
+    return a.ctypes.data_as(p64)
+
+
+def arr(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+
+
+def bred_params(q):
+    u = (u64 * 2)()
+    lib().orc_bred_params(q, u)
+    return [int(u[0]), int(u[1])]
+
+
+def generate_ntt_primes(logq, logn, levels):
+    out = np.zeros(levels, dtype=np.uint64)
+    n = lib().orc_generate_ntt_primes(logq, logn, levels, ptr(out))
+    assert n == levels
+    return [int(x) for x in out]
+
+
+def gen_moduli(logn, log_qi, log_pi, log_extra=()):
+    """ckks/utils.go:150-193 GenModuli (also bfv/utils.go:26-85 with a third
+    QiMul list): primes are generated per bit size, then dealt in order to Q,
+    then P (then QMul)."""
+    need = {}
+    for b in list(log_qi) + list(log_pi) + list(log_extra):
+        assert b <= 60
+        need[b] = need.get(b, 0) + 1
+    primes = {b: generate_ntt_primes(b, logn, n) for b, n in need.items()}
+    out = []
+    for group in (log_qi, log_pi, log_extra):
+        lst = []
+        for b in group:
+            lst.append(primes[b][0])
+            primes[b] = primes[b][1:]
+        out.append(lst)
+    return out
+
+
+class Context:
+    """ring.Context restated (ring/ring_context.go:18-209)."""
+
+    def __init__(self, N, moduli):
+        self.N = int(N)
+        self.moduli = [int(q) for q in moduli]
+        self.nl = len(self.moduli)
+        m = arr(self.moduli)
+        self.h = lib().orc_ctx_new(self.N, self.nl, ptr(m))
+        if not self.h:
+            raise ValueError("moduli do not allow NTT / invalid N")
+        self.bred = np.zeros((self.nl, 2), dtype=np.uint64)
+        self.mred = np.zeros(self.nl, dtype=np.uint64)
+        self.ninv = np.zeros(self.nl, dtype=np.uint64)
+        self.psi_mont = np.zeros(self.nl, dtype=np.uint64)
+        self.psi_inv_mont = np.zeros(self.nl, dtype=np.uint64)
+        lib().orc_ctx_scalars(self.h, None, ptr(self.bred), ptr(self.mred), ptr(self.ninv), ptr(self.psi_mont),
+                              ptr(self.psi_inv_mont))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_ctx_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def tables(self, limb):
+        psi = np.zeros(self.N, dtype=np.uint64)
+        psi_inv = np.zeros(self.N, dtype=np.uint64)
+        lib().orc_ctx_tables(self.h, limb, ptr(psi), ptr(psi_inv))
+        return psi, psi_inv
+
+    def all_tables(self):
+        psi = np.zeros((self.nl, self.N), dtype=np.uint64)
+        psi_inv = np.zeros((self.nl, self.N), dtype=np.uint64)
+        for i in range(self.nl):
+            lib().orc_ctx_tables(self.h, i, ptr(psi[i]), ptr(psi_inv[i]))
+        return psi, psi_inv
+
+    def rescale_params(self):
+        """flat triangular list rescaleParams[j-1][i], i<j (ring_context.go:148-158)"""
+        return [[int(lib().orc_ctx_rescale_param(self.h, j, i)) for i in range(j)] for j in range(1, self.nl)]
+
+    def new_poly(self, nl=None):
+        return np.zeros((self.nl if nl is None else nl, self.N), dtype=np.uint64)
+
+    # --- generic dispatch helpers -------------------------------------------------
+    def _nl(self, a, nl):
+        return a.shape[0] if nl is None else nl
+
+    def op3(self, name, p1, p2, p3=None, nl=None):
+        nl = self._nl(p1, nl)
+        if p3 is None:
+            p3 = np.zeros((nl, self.N), dtype=np.uint64)
+        getattr(lib(), "orc_" + name)(self.h, nl, ptr(p1), ptr(p2), ptr(p3))
+        return p3
+
+    def op2(self, name, p1, p2=None, nl=None):
+        nl = self._nl(p1, nl)
+        if p2 is None:
+            p2 = np.zeros((nl, self.N), dtype=np.uint64)
+        getattr(lib(), "orc_" + name)(self.h, nl, ptr(p1), ptr(p2))
+        return p2
+
+    def ntt(self, p, out=None, nl=None):
+        nl = self._nl(p, nl)
+        if out is None:
+            out = np.zeros((nl, self.N), dtype=np.uint64)
+        lib().orc_ntt(self.h, nl, ptr(p), ptr(out))
+        return out
+
+    def invntt(self, p, out=None, nl=None):
+        nl = self._nl(p, nl)
+        if out is None:
+            out = np.zeros((nl, self.N), dtype=np.uint64)
+        lib().orc_invntt(self.h, nl, ptr(p), ptr(out))
+        return out
+
+    def permute(self, p, gen, nl=None):
+        nl = self._nl(p, nl)
+        out = np.zeros((nl, self.N), dtype=np.uint64)
+        lib().orc_permute(self.h, nl, ptr(p), gen, ptr(out))
+        return out
+
+    def mul_scalar(self, p, scalars, nl=None):
+        nl = self._nl(p, nl)
+        out = np.zeros((nl, self.N), dtype=np.uint64)
+        s = arr(scalars)
+        lib().orc_mul_scalar(self.h, nl, ptr(p), ptr(s), ptr(out))
+        return out
+
+    def div_round_ntt(self, p):
+        """DivRoundByLastModulusNTT; returns the nl-1 limb result (input not modified)."""
+        q = p.copy()
+        lib().orc_div_round_by_last_modulus_ntt(self.h, q.shape[0], ptr(q))
+        return q[:-1].copy()
+
+
+def permute_ntt_index(gen, power, N):
+    idx = np.zeros(N, dtype=np.uint64)
+    lib().orc_permute_ntt_index(gen, power, N, ptr(idx))
+    return idx
+
+
+def permute_ntt_with_index(p, index):
+    out = np.zeros_like(p)
+    lib().orc_permute_ntt_with_index(p.shape[1], p.shape[0], ptr(p), ptr(index), ptr(out))
+    return out
+
+
+class Extender:
+    """ring.FastBasisExtender restated (ring/ring_basis_extension.go:9-350)."""
+
+    def __init__(self, ctxQ, ctxP):
+        self.Q, self.P = ctxQ, ctxP
+        self.h = lib().orc_extender_new(ctxQ.h, ctxP.h)
+
+    def __del__(self):
+        try:
+            lib().orc_extender_free(self.h)
+        except Exception:
+            pass
+
+    def modup_split_qp(self, level, p1):
+        out = self.P.new_poly()
+        lib().orc_modup_split_qp(self.h, level, ptr(p1), ptr(out))
+        return out
+
+    def modup_split_pq(self, level, p1):
+        out = self.Q.new_poly()
+        lib().orc_modup_split_pq(self.h, level, ptr(p1), ptr(out))
+        return out
+
+    def moddown_ntt_pq(self, level, p1):
+        p1 = p1.copy()
+        out = self.Q.new_poly(level + 1)
+        lib().orc_moddown_ntt_pq(self.h, level, ptr(p1), ptr(out))
+        return out
+
+    def moddown_splited_ntt_pq(self, level, p1Q, p1P):
+        p1P = p1P.copy()
+        out = self.Q.new_poly(level + 1)
+        lib().orc_moddown_splited_ntt_pq(self.h, level, ptr(p1Q), ptr(p1P), ptr(out))
+        return out
+
+    def moddown_pq(self, level, p1):
+        out = self.Q.new_poly(level + 1)
+        lib().orc_moddown_pq(self.h, level, ptr(p1), ptr(out))
+        return out
+
+    def moddown_splited_pq(self, level, p1Q, p1P):
+        out = self.Q.new_poly(level + 1)
+        lib().orc_moddown_splited_pq(self.h, level, ptr(p1Q), ptr(p1P), ptr(out))
+        return out
+
+    def moddown_splited_qp(self, levelQ, levelP, p1Q, p1P):
+        out = self.P.new_poly(levelP + 1)
+        lib().orc_moddown_splited_qp(self.h, levelQ, levelP, ptr(p1Q), ptr(p1P), ptr(out))
+        return out
+
+
+class Decomposer:
+    """ring.Decomposer restated (ring/ring_basis_extension.go:398-713)."""
+
+    def __init__(self, Q, P, N):
+        self.Qm, self.Pm, self.N = list(Q), list(P), N
+        q, p = arr(Q), arr(P)
+        self.h = lib().orc_decomposer_new(ptr(q), len(Q), ptr(p), len(P))
+        self.beta = lib().orc_decomposer_beta(self.h)
+
+    def __del__(self):
+        try:
+            lib().orc_decomposer_free(self.h)
+        except Exception:
+            pass
+
+    def decompose_and_split(self, level, crt, p0):
+        outQ = np.zeros((level + 1, self.N), dtype=np.uint64)
+        outP = np.zeros((len(self.Pm), self.N), dtype=np.uint64)
+        lib().orc_decompose_and_split(self.h, self.N, level, crt, ptr(p0), ptr(outQ), ptr(outP))
+        return outQ, outP
+
+    def decompose(self, level, crt, p0):
+        out = np.zeros((level + 1 + len(self.Pm), self.N), dtype=np.uint64)
+        lib().orc_decompose(self.h, self.N, level, crt, ptr(p0), ptr(out))
+        return out
+
+
+class CkksEvaluator:
+    """Hot ops of ckks.evaluator restated (ckks/evaluator.go:933-1591)."""
+
+    def __init__(self, ctxQ, ctxP):
+        self.Q, self.P = ctxQ, ctxP
+        self.h = lib().orc_ckks_eval_new(ctxQ.h, ctxP.h)
+
+    def __del__(self):
+        try:
+            lib().orc_ckks_eval_free(self.h)
+        except Exception:
+            pass
+
+    def switch_keys_in_place(self, level, cx, evk):
+        p0 = np.zeros((level + 1, self.Q.N), dtype=np.uint64)
+        p1 = np.zeros((level + 1, self.Q.N), dtype=np.uint64)
+        lib().orc_ckks_switch_keys_in_place(self.h, level, ptr(cx), ptr(evk), ptr(p0), ptr(p1))
+        return p0, p1
+
+    def mul_relin(self, level, ct0, ct1, evk):
+        out = np.zeros((2, level + 1, self.Q.N), dtype=np.uint64)
+        lib().orc_ckks_mul_relin(self.h, level, ptr(ct0), ptr(ct1), ptr(evk), ptr(out))
+        return out
+
+    def rescale(self, ct, nb=1):
+        nl = ct.shape[1]
+        buf = ct.copy()
+        lib().orc_ckks_rescale(self.h, nl, ptr(buf), nb)
+        return buf.reshape(-1)[: 2 * (nl - nb) * self.Q.N].reshape(2, nl - nb, self.Q.N).copy()
+
+    def permute_ntt(self, level, ct, index, evk):
+        out = np.zeros((2, level + 1, self.Q.N), dtype=np.uint64)
+        lib().orc_ckks_permute_ntt(self.h, level, ptr(ct), ptr(index), ptr(evk), ptr(out))
+        return out
+
+    def switch_keys(self, level, ct, evk):
+        out = np.zeros((2, level + 1, self.Q.N), dtype=np.uint64)
+        lib().orc_ckks_switch_keys(self.h, level, ptr(ct), ptr(evk), ptr(out))
+        return out
