@@ -1,0 +1,290 @@
+"""The reference's big-integer property tests (ring/ring_test.go) restated
+against the oracle, so that the parts of the path that have no golden vectors
+(basis extension, rescaling, Galois permutations, decomposition, key switching)
+are anchored the same way the reference anchors them: against math/big.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ring_oracle as orc
+
+QI60 = [1152921504066306049, 1152921504057917441, 1152921504053723137, 1152921504050839553]  # ring/params.go:50-69 tail
+PI60 = [576460752568975361, 576460752573431809, 576460752580902913, 576460752585490433]  # ring/params.go:28-47 tail
+M64 = (1 << 64) - 1
+
+
+def prod(xs):
+    r = 1
+    for x in xs:
+        r *= x
+    return r
+
+
+def crt_poly(values, moduli):
+    return np.array([[v % q for v in values] for q in moduli], dtype=np.uint64)
+
+
+def crt_reconstruct(poly, moduli):
+    Q = prod(moduli)
+    out = []
+    for j in range(poly.shape[1]):
+        x = 0
+        for i, q in enumerate(moduli):
+            Qi = Q // q
+            x += int(poly[i, j]) * Qi * pow(Qi, -1, q)
+        out.append(x % Q)
+    return out
+
+
+def div_round(a, b):
+    """ring/int.go:40-52 for a >= 0, b > 0"""
+    q, r = divmod(a, b)
+    return q + 1 if 2 * r >= b else q
+
+
+def test_bred_mred_vs_bigint():
+    # ring/ring_test.go:352-420
+    rng = random.Random(1)
+    L = orc.lib()
+    for q in QI60 + PI60 + [0x200000008001, 0x400018001]:
+        u = (orc.u64 * 2)(*orc.bred_params(q))
+        assert (int(u[0]) << 64) + int(u[1]) == (1 << 128) // q
+        qinv = L.orc_mred_params(q)
+        assert (qinv * q) & M64 == 1
+        for _ in range(500):
+            x, y = rng.randrange(q), rng.randrange(q)
+            assert L.orc_bred(x, y, q, u) == x * y % q
+            # MRed(x, MForm(y)) == x*y mod q
+            ym = L.orc_mform(y, q, u)
+            assert ym == (y << 64) % q
+            assert L.orc_mred(x, ym, q, qinv) == x * y % q
+            assert L.orc_invmform(ym, q, qinv) == y
+            w = rng.getrandbits(64)
+            assert L.orc_bred_add(w, q, u) == w % q
+            assert L.orc_modexp(x, y, q) == pow(x, y, q)
+
+
+def test_generate_ntt_primes_and_ckks_moduli():
+    # SURVEY.md Appendix B values, ckks/params.go:59-66,79-86
+    Q, P, _ = orc.gen_moduli(14, [45] + [34] * 9, [43, 43])
+    assert Q[:3] == [0x200000008001, 0x400018001, 0x400060001] and len(Q) == 10
+    assert P == [0x80000050001, 0x800000B8001]
+    assert sum(q.bit_length() for q in Q + P) - 0 >= 438
+    Q, P, _ = orc.gen_moduli(16, [55] + [45] * 33, [55] * 4)
+    assert Q[:3] == [0x80000000080001, 0x2000000A0001, 0x2000000E0001]
+    assert P[:3] == [0x80000000440001, 0x80000000500001, 0x800000005E0001]
+    for q in Q + P:
+        assert q % (2 << 16) == 1
+
+
+@pytest.mark.parametrize("N", [16, 64])
+def test_mulpoly_vs_naive(N):
+    # ring/ring_test.go:503-548: NTT-based product == schoolbook negacyclic product
+    rng = random.Random(2)
+    moduli = QI60[:2]
+    ctx = orc.Context(N, moduli)
+    a = np.array([[rng.randrange(q) for _ in range(N)] for q in moduli], dtype=np.uint64)
+    b = np.array([[rng.randrange(q) for _ in range(N)] for q in moduli], dtype=np.uint64)
+    na, nb = ctx.ntt(a), ctx.ntt(b)
+    c = ctx.invntt(ctx.op3("mulcoeffs", na, nb))
+    nam = ctx.op2("mform_poly", na)
+    c2 = ctx.invntt(ctx.op3("mulcoeffs_montgomery", nam, nb))
+    for i, q in enumerate(moduli):
+        want = [0] * N
+        for x in range(N):
+            for y in range(N):
+                k = x + y
+                v = int(a[i, x]) * int(b[i, y])
+                if k >= N:
+                    want[k - N] = (want[k - N] - v) % q
+                else:
+                    want[k] = (want[k] + v) % q
+        assert [int(v) for v in c[i]] == want
+        assert [int(v) for v in c2[i]] == want
+
+
+@pytest.mark.parametrize("srcdst", [(QI60, PI60), (QI60[:2], QI60[:2]), (PI60[:3], QI60)])
+def test_extend_basis_vs_crt(srcdst):
+    # ring/ring_test.go:550-585 (ModUpSplitQP equals reduction of the big integer)
+    src, dst = srcdst
+    N = 32
+    rng = random.Random(3)
+    ctxQ, ctxP = orc.Context(N, src), orc.Context(N, dst)
+    ext = orc.Extender(ctxQ, ctxP)
+    vals = [rng.randrange(prod(src)) for _ in range(N)]
+    vals[0] = 0  # (x = Q-1 is outside the float64 correction's exact range: the reference's v rounds up there)
+    pol = crt_poly(vals, src)
+    got = ext.modup_split_qp(len(src) - 1, pol)
+    assert np.array_equal(got, crt_poly(vals, dst))
+
+
+def test_div_round_floor_vs_bigint():
+    # ring/ring_test.go:134-220
+    N = 32
+    rng = random.Random(4)
+    moduli = QI60
+    ctx = orc.Context(N, moduli)
+    vals = [rng.randrange(prod(moduli)) // 10 for _ in range(N)]
+    pol = crt_poly(vals, moduli)
+    nb = len(moduli) - 1
+    want_r, want_f = list(vals), list(vals)
+    for j in range(nb):
+        want_r = [div_round(v, moduli[-1 - j]) for v in want_r]
+        want_f = [v // moduli[-1 - j] for v in want_f]
+    p = pol.copy()
+    orc.lib().orc_div_round_by_last_modulus_many(ctx.h, len(moduli), orc.ptr(p), nb)
+    assert np.array_equal(p[:1], crt_poly(want_r, moduli[:1]))
+    p = pol.copy()
+    orc.lib().orc_div_floor_by_last_modulus_many(ctx.h, len(moduli), orc.ptr(p), nb)
+    assert np.array_equal(p[:1], crt_poly(want_f, moduli[:1]))
+    # NTT-domain variants agree with the coefficient-domain ones
+    for name in ("div_round_by_last_modulus", "div_floor_by_last_modulus"):
+        p = pol.copy()
+        getattr(orc.lib(), "orc_" + name)(ctx.h, len(moduli), orc.ptr(p))
+        pn = ctx.ntt(pol)
+        getattr(orc.lib(), "orc_" + name + "_ntt")(ctx.h, len(moduli), orc.ptr(pn))
+        back = ctx.invntt(np.ascontiguousarray(pn[:-1]))
+        assert np.array_equal(back, p[:-1])
+
+
+def test_galois_shift():
+    # ring/ring_test.go:422-460: NTT(Permute(a, g)) == PermuteNTT(NTT(a), g), and
+    # the automorphism is X -> X^g on big-int coefficients
+    N = 64
+    rng = random.Random(5)
+    moduli = QI60[:2]
+    ctx = orc.Context(N, moduli)
+    a = np.array([[rng.randrange(q) for _ in range(N)] for q in moduli], dtype=np.uint64)
+    for g in (5, 25, 2 * N - 1, pow(5, 7, 2 * N)):
+        perm = ctx.permute(a, g)
+        out = np.zeros_like(a)
+        orc.lib().orc_permute_ntt(N, 2, orc.ptr(ctx.ntt(a)), g, orc.ptr(out))
+        assert np.array_equal(ctx.ntt(perm), out)
+        for i, q in enumerate(moduli):
+            want = [0] * N
+            for k in range(N):
+                e = (k * g) % (2 * N)
+                want[e % N] = (q - int(a[i, k])) if e >= N else int(a[i, k])
+            assert [int(v) for v in perm[i]] == want
+    idx = orc.permute_ntt_index(5, 3, N)
+    out = np.zeros_like(a)
+    orc.lib().orc_permute_ntt(N, 2, orc.ptr(a), pow(5, 3, 2 * N), orc.ptr(out))
+    assert np.array_equal(orc.permute_ntt_with_index(a, idx), out)
+
+
+def _ckks_small(N=32, nQ=5, nP=2, logq=40, logp=50):
+    logn = N.bit_length() - 1
+    Q, P, _ = orc.gen_moduli(logn, [logq + 5] + [logq] * (nQ - 1), [logp] * nP)
+    return Q, P
+
+
+@pytest.mark.parametrize("level", [4, 3, 2, 0])
+def test_decompose_digits_reconstruct(level):
+    """Each digit of DecomposeAndSplit is the integer D_i = [x]_{digit basis}
+    (in [0, prod digit)) reduced modulo every target prime: the exactness claim
+    of modUpExact (ring_basis_extension.go:352-393)."""
+    N = 32
+    Q, P = _ckks_small(N)
+    alpha = len(P)
+    rng = random.Random(6)
+    dec = orc.Decomposer(Q, P, N)
+    nl = level + 1
+    vals = [rng.randrange(prod(Q[:nl])) for _ in range(N)]
+    pol = crt_poly(vals, Q[:nl])
+    full = np.zeros((len(Q), N), dtype=np.uint64)
+    full[:nl] = pol
+    beta = -(-nl // alpha)
+    for crt in range(beta):
+        lo, hi = crt * alpha, min(crt * alpha + alpha, nl)
+        digit_mod = Q[lo:hi]
+        dvals = [v % prod(digit_mod) for v in vals]
+        gotQ, gotP = dec.decompose_and_split(level, crt, full)
+        assert np.array_equal(gotQ, crt_poly(dvals, Q[:nl])), (level, crt)
+        assert np.array_equal(gotP, crt_poly(dvals, P)), (level, crt)
+        got = dec.decompose(level, crt, full)
+        assert np.array_equal(got, np.concatenate([gotQ, gotP]))
+
+
+def _keygen(rng, ctxQP, Q, P, N, sk_in, sk_out):
+    """ckks/keygen.go:282-340 newSwitchingKey with a toy error (|e| <= 1) --
+    returns evk [beta][2][nQP][N] in NTT + Montgomery form."""
+    nQ, nP = len(Q), len(P)
+    alpha = nP
+    beta = -(-nQ // alpha)
+    QP = Q + P
+    Pprod = prod(P)
+    # P * skIn (coefficient ints -> NTT)
+    s_in_ntt = ctxQP.op2("mform_poly", ctxQP.ntt(crt_poly([Pprod * s for s in sk_in], QP)))
+    s_out_ntt = ctxQP.op2("mform_poly", ctxQP.ntt(crt_poly(sk_out, QP)))
+    evk = np.zeros((beta, 2, nQ + nP, N), dtype=np.uint64)
+    for i in range(beta):
+        e = [rng.choice([-1, 0, 1]) for _ in range(N)]
+        k0 = ctxQP.op2("mform_poly", ctxQP.ntt(crt_poly(e, QP)))
+        a = np.array([[rng.randrange(q) for _ in range(N)] for q in QP], dtype=np.uint64)
+        for j in range(alpha):
+            index = i * alpha + j
+            qi = QP[index]
+            k0[index] = (k0[index].astype(object) + s_in_ntt[index].astype(object)) % qi  # CRed(p1+p0) on reduced inputs
+            if index >= nQ - 1:
+                break
+        k0 = np.ascontiguousarray(k0.astype(np.uint64))
+        ctxQP.op3("mulcoeffs_montgomery_and_sub", a, s_out_ntt, k0)
+        evk[i, 0], evk[i, 1] = k0, a
+    return evk
+
+
+@pytest.mark.parametrize("level", [4, 3, 1])
+def test_ckks_keyswitch_semantics(level):
+    """switchKeysInPlace (ckks/evaluator.go:1475-1558) with a key built as
+    newSwitchingKey does: p0 + p1*s_out must equal cx*s_in up to a small error
+    relative to Q (the decryption check of ckks_test.go, at ring level)."""
+    N = 32
+    Q, P = _ckks_small(N)
+    rng = random.Random(7 + level)
+    ctxQ, ctxP, ctxQP = orc.Context(N, Q), orc.Context(N, P), orc.Context(N, Q + P)
+    ev = orc.CkksEvaluator(ctxQ, ctxP)
+    sk_in = [rng.choice([-1, 0, 1]) for _ in range(N)]
+    sk_out = [rng.choice([-1, 0, 1]) for _ in range(N)]
+    evk = _keygen(rng, ctxQP, Q, P, N, sk_in, sk_out)
+    nl = level + 1
+    Ql = Q[:nl]
+    cx_vals = [rng.randrange(prod(Ql)) for _ in range(N)]
+    cx = np.zeros((len(Q), N), dtype=np.uint64)
+    cx[:nl] = ctxQ.ntt(crt_poly(cx_vals, Ql), nl=nl)
+    p0, p1 = ev.switch_keys_in_place(level, cx, evk)
+
+    def negacyclic(a, b, mod):
+        out = [0] * N
+        for x in range(N):
+            for y in range(N):
+                k = x + y
+                if k >= N:
+                    out[k - N] = (out[k - N] - a[x] * b[y]) % mod
+                else:
+                    out[k] = (out[k] + a[x] * b[y]) % mod
+        return out
+
+    Qp = prod(Ql)
+    ctxl = orc.Context(N, Ql)
+    p0c = crt_reconstruct(ctxl.invntt(p0), Ql)
+    p1c = crt_reconstruct(ctxl.invntt(p1), Ql)
+    lhs = [(u + v) % Qp for u, v in zip(p0c, negacyclic(p1c, sk_out, Qp))]
+    rhs = negacyclic(cx_vals, sk_in, Qp)
+    err = max(min((l - r) % Qp, (r - l) % Qp) for l, r in zip(lhs, rhs))
+    # noise ~ beta * N * q_digit^alpha / P plus rounding: tiny next to Q
+    assert err.bit_length() < 30, err.bit_length()
+
+
+def test_unreduced_inputs_are_defined():
+    """NewPolyUniform feeds full 64-bit words (ring_object.go:26-46); the oracle
+    must be total on them (used later as a formula-exactness probe for CUDA)."""
+    N = 64
+    rng = np.random.default_rng(8)
+    ctx = orc.Context(N, QI60)
+    a = rng.integers(0, 1 << 64, size=(4, N), dtype=np.uint64)
+    out = ctx.ntt(a)
+    assert all((out[i] < QI60[i]).all() for i in range(4))
+    out = ctx.invntt(a)
+    assert all((out[i] < QI60[i]).all() for i in range(4))
