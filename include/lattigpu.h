@@ -1,0 +1,215 @@
+/*
+ * lattigpu.h -- C ABI of the B200-native RNS polynomial-ring engine.
+ *
+ * This is the drop-in boundary for the ring hot path of Lattigo v1.3.1
+ * (Eleven-Z/lattigo-FHE-by-go).  The reference has no FFI layer: ring.Context
+ * is a Go struct whose methods the ckks/bfv/dckks/dbfv packages call directly.
+ * Each entry point below replaces one of those methods (cited as
+ * reference-file:line); the Go side keeps its types and calls these through
+ * cgo.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *  - every function returns 0 (LG_OK) or a negative status; lg_last_error()
+ *    gives the message for the calling thread.  The Go shim turns a non-zero
+ *    status into panic(), matching the reference's misuse behaviour
+ *    (ring/ring_context.go:72,136).
+ *  - `nl` is the number of ACTIVE limbs an op touches (= level+1 of the
+ *    reference's *Lvl variants; pass the ring's limb count for the plain ones).
+ *  - a polynomial handle owns (or wraps) a device buffer laid out
+ *    [batch][nlimbs][N] of uint64; every op is applied to all `batch` entries
+ *    (batch = 1 reproduces the reference's one-poly call).
+ *  - `stream` is a cudaStream_t (NULL = the default stream).  Ops are
+ *    asynchronous; lg_stream_sync / lg_poly_download order them.
+ *  - like the reference, ops do not range-check limb counts beyond what is
+ *    needed for memory safety; out-of-range arguments return LG_ERR_ARG.
+ */
+#ifndef LATTIGPU_H
+#define LATTIGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LG_OK 0
+#define LG_ERR_ARG (-1)      /* invalid argument (the reference panics or indexes out of range) */
+#define LG_ERR_NTT (-2)      /* moduli do not allow the NTT (ring_context.go:142-145) */
+#define LG_ERR_CUDA (-3)     /* CUDA runtime error */
+#define LG_ERR_NOMEM (-4)
+#define LG_ERR_NODEVICE (-5) /* no CUDA device: there is no CPU fallback */
+
+typedef struct lg_ring lg_ring;             /* ring.Context            ring/ring_context.go:18-51 */
+typedef struct lg_poly lg_poly;             /* ring.Poly (device)      ring/ring_object.go:11-13 */
+typedef struct lg_extender lg_extender;     /* ring.FastBasisExtender  ring/ring_basis_extension.go:9-18 */
+typedef struct lg_decomposer lg_decomposer; /* ring.Decomposer         ring/ring_basis_extension.go:398-407 */
+typedef struct lg_galois lg_galois;         /* []uint64 index of PermuteNTTIndex, ring/ring_galois.go:29-50 */
+typedef struct lg_ckks_eval lg_ckks_eval;   /* hot ops of ckks.evaluator, ckks/evaluator.go:64-76 */
+typedef struct lg_bfv_eval lg_bfv_eval;     /* hot ops of bfv.evaluator,  bfv/evaluator.go:41-60 */
+typedef struct lg_swk lg_swk;               /* ckks/bfv SwitchingKey.evakey [beta][2] QP polys, ckks/keygen.go:282-340 */
+typedef void* lg_stream_t;                  /* cudaStream_t */
+
+/* ---- library / device ---------------------------------------------------- */
+const char* lg_last_error(void);
+const char* lg_version(void);
+int lg_device_count(int* count);
+int lg_set_device(int device);
+int lg_stream_create(lg_stream_t* stream);
+int lg_stream_destroy(lg_stream_t stream);
+int lg_stream_sync(lg_stream_t stream);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t lg_launch_count(void);
+
+/* ---- ring.Context -------------------------------------------------------- */
+/* NewContextWithParams = SetParameters + GenNTTParams, ring_context.go:60-209:
+ * tables are generated natively (same primitive-root search as ring/utils.go:182-288). */
+int lg_ring_create(uint64_t N, int nlimbs, const uint64_t* moduli, lg_ring** out);
+/* Same context from tables computed by the Go side (so that psi is literally the
+ * reference's): bred = nlimbs x {hi,lo} (bredParams), mred = mredParams, psi /
+ * psi_inv = nlimbs x N (nttPsi / nttPsiInv), ninv = nttNInv, rescale = the
+ * triangular rescaleParams[j-1][i] flattened j-major (j=1..nlimbs-1, i<j); may be NULL. */
+int lg_ring_create_from_tables(uint64_t N, int nlimbs, const uint64_t* moduli, const uint64_t* bred,
+                               const uint64_t* mred, const uint64_t* psi, const uint64_t* psi_inv,
+                               const uint64_t* ninv, const uint64_t* rescale, lg_ring** out);
+int lg_ring_destroy(lg_ring* ring);
+uint64_t lg_ring_n(const lg_ring* ring);
+int lg_ring_nlimbs(const lg_ring* ring);
+/* host copies of the tables (any pointer may be NULL); sizes as in create_from_tables */
+int lg_ring_get_tables(const lg_ring* ring, uint64_t* moduli, uint64_t* bred, uint64_t* mred, uint64_t* psi,
+                       uint64_t* psi_inv, uint64_t* ninv, uint64_t* rescale);
+
+/* ---- ring.Poly ------------------------------------------------------------ */
+int lg_poly_create(uint64_t N, int nlimbs, int batch, lg_poly** out);            /* ring.NewPoly, ring_object.go:16-23 */
+int lg_poly_wrap(void* device_ptr, uint64_t N, int nlimbs, int batch, lg_poly** out); /* non-owning */
+/* non-owning view of limbs [limb0, limb0+nlimbs) of every batch entry (Go: p.Coeffs[a:b]) */
+int lg_poly_view(const lg_poly* parent, int limb0, int nlimbs, lg_poly** out);
+int lg_poly_destroy(lg_poly* p);
+uint64_t lg_poly_n(const lg_poly* p);
+int lg_poly_nlimbs(const lg_poly* p);
+int lg_poly_batch(const lg_poly* p);
+void* lg_poly_device_ptr(const lg_poly* p);
+size_t lg_poly_batch_stride(const lg_poly* p); /* in words */
+/* host <-> device; host layout [nbatch][nl][N]; synchronous with respect to the host buffer */
+int lg_poly_upload(lg_poly* p, int batch0, int nbatch, int limb0, int nl, const uint64_t* host, lg_stream_t stream);
+int lg_poly_download(const lg_poly* p, int batch0, int nbatch, int limb0, int nl, uint64_t* host, lg_stream_t stream);
+int lg_poly_zero(lg_poly* p, lg_stream_t stream);                                /* Poly.Zero, ring_object.go:60-67 */
+int lg_poly_copy(const lg_poly* src, int nl, lg_poly* dst, lg_stream_t stream);  /* Copy/CopyLvl, ring_object.go:85-121 */
+
+/* ---- NTT, ring/ntt.go ------------------------------------------------------ */
+int lg_ring_ntt(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, lg_stream_t s);    /* NTT/NTTLvl :4-15 */
+int lg_ring_invntt(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, lg_stream_t s); /* InvNTT/InvNTTLvl :18-29 */
+/* free functions ring.NTT / ring.InvNTT (:53,:89) on ONE limb with the tables of `table_limb` */
+int lg_ring_ntt_limb(const lg_ring* r, int table_limb, const lg_poly* p1, int limb1, lg_poly* p2, int limb2,
+                     lg_stream_t s);
+int lg_ring_invntt_limb(const lg_ring* r, int table_limb, const lg_poly* p1, int limb1, lg_poly* p2, int limb2,
+                        lg_stream_t s);
+
+/* ---- coefficient-wise ops, ring/ring.go ------------------------------------ */
+int lg_ring_add(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);        /* :10-29 */
+int lg_ring_add_nomod(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);  /* :32-51 */
+int lg_ring_sub(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);        /* :54-73 */
+int lg_ring_sub_nomod(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);  /* :76-97 */
+int lg_ring_neg(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, lg_stream_t s);                          /* :100-119 */
+int lg_ring_reduce(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, lg_stream_t s);                       /* :122-143 */
+int lg_ring_mod(const lg_ring* r, int nl, const lg_poly* p1, uint64_t m, lg_poly* p2, lg_stream_t s);              /* :146-154 */
+int lg_ring_and(const lg_ring* r, int nl, const lg_poly* p1, uint64_t m, lg_poly* p2, lg_stream_t s);              /* :157-164 */
+int lg_ring_or(const lg_ring* r, int nl, const lg_poly* p1, uint64_t m, lg_poly* p2, lg_stream_t s);               /* :167-174 */
+int lg_ring_xor(const lg_ring* r, int nl, const lg_poly* p1, uint64_t m, lg_poly* p2, lg_stream_t s);              /* :177-184 */
+int lg_ring_mul_coeffs(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);               /* :187-195 */
+int lg_ring_mul_coeffs_and_add(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);       /* :198-206 */
+int lg_ring_mul_coeffs_and_add_nomod(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s); /* :209-217 */
+int lg_ring_mul_coeffs_constant(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);      /* :335-343 */
+int lg_ring_mul_coeffs_montgomery(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);               /* :221-243 */
+int lg_ring_mul_coeffs_montgomery_and_add(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);       /* :247-269 */
+int lg_ring_mul_coeffs_montgomery_and_add_nomod(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s); /* :273-295 */
+int lg_ring_mul_coeffs_montgomery_constant_and_add_nomod(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s); /* :298-308 */
+int lg_ring_mul_coeffs_montgomery_and_sub(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);       /* :311-319 */
+int lg_ring_mul_coeffs_montgomery_and_sub_nomod(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s); /* :323-331 */
+int lg_ring_mul_coeffs_montgomery_constant(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, lg_stream_t s);      /* :346-355 */
+int lg_ring_mform(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, lg_stream_t s);    /* MForm/MFormLvl :583-607 */
+int lg_ring_invmform(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, lg_stream_t s); /* InvMForm :610-619 */
+/* scalar ops: `scalar` has one word per active limb -- the same word repeated for
+ * AddScalar/SubScalar/MulScalar (:467,:490,:513), scalar mod q_i for the *Bigint
+ * variants (:477,:500,:539,:556; the big.Int reduction stays on the Go side).
+ * As in the reference (:482,:505) Add/SubScalar write into p1 itself. */
+int lg_ring_add_scalar(const lg_ring* r, int nl, lg_poly* p1, const uint64_t* scalar, lg_stream_t s);
+int lg_ring_sub_scalar(const lg_ring* r, int nl, lg_poly* p1, const uint64_t* scalar, lg_stream_t s);
+int lg_ring_mul_scalar(const lg_ring* r, int nl, const lg_poly* p1, const uint64_t* scalar, lg_poly* p2, lg_stream_t s);
+int lg_ring_mul_by_pow2(const lg_ring* r, int nl, const lg_poly* p1, uint64_t pow2, lg_poly* p2, lg_stream_t s);          /* :629-653 */
+int lg_ring_mult_by_monomial(const lg_ring* r, int nl, const lg_poly* p1, uint64_t deg, lg_poly* p2, lg_stream_t s);      /* :663-723 */
+/* vector = device poly with one limb of N words */
+int lg_ring_mul_by_vector_montgomery(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* vec, lg_poly* p2, lg_stream_t s);               /* :726-734 */
+int lg_ring_mul_by_vector_montgomery_and_add_nomod(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* vec, lg_poly* p2, lg_stream_t s); /* :737-745 */
+int lg_ring_bitreverse(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, lg_stream_t s);                          /* :749-772 (p1 != p2) */
+
+/* ---- Galois automorphisms, ring/ring_galois.go ----------------------------- */
+int lg_galois_create(uint64_t gen, uint64_t power, uint64_t N, lg_galois** out);           /* PermuteNTTIndex :29-50 */
+int lg_galois_create_from_index(const uint64_t* index, uint64_t N, lg_galois** out);      /* index computed by Go */
+int lg_galois_get_index(const lg_galois* g, uint64_t* index);
+int lg_galois_destroy(lg_galois* g);
+int lg_ring_permute_ntt_with_index(int nl, const lg_poly* in, const lg_galois* g, lg_poly* out, lg_stream_t s); /* :89-101 */
+int lg_ring_permute_ntt(int nl, const lg_poly* in, uint64_t gen, lg_poly* out, lg_stream_t s);                  /* :55-84 */
+int lg_ring_permute(const lg_ring* r, int nl, const lg_poly* in, uint64_t gen, lg_poly* out, lg_stream_t s);    /* Context.Permute :106-127 */
+
+/* ---- RNS rescaling, ring/ring_scaling.go ----------------------------------- */
+/* p0 has nl active limbs on entry; the result is in its first nl-1 (or nl-nb)
+ * limbs -- the Go side re-slices Coeffs exactly as ring_scaling.go:33,53,113,147. */
+int lg_ring_div_floor_by_last_modulus_ntt(const lg_ring* r, int nl, lg_poly* p0, lg_stream_t s);  /* :9-34 */
+int lg_ring_div_floor_by_last_modulus(const lg_ring* r, int nl, lg_poly* p0, lg_stream_t s);      /* :37-54 */
+int lg_ring_div_floor_by_last_modulus_many_ntt(const lg_ring* r, int nl, lg_poly* p0, int nb, lg_stream_t s); /* :57-61 */
+int lg_ring_div_floor_by_last_modulus_many(const lg_ring* r, int nl, lg_poly* p0, int nb, lg_stream_t s);     /* :64-69 */
+int lg_ring_div_round_by_last_modulus_ntt(const lg_ring* r, int nl, lg_poly* p0, lg_stream_t s);  /* :72-114 */
+int lg_ring_div_round_by_last_modulus(const lg_ring* r, int nl, lg_poly* p0, lg_stream_t s);      /* :117-148 */
+int lg_ring_div_round_by_last_modulus_many_ntt(const lg_ring* r, int nl, lg_poly* p0, int nb, lg_stream_t s); /* :152-156 */
+int lg_ring_div_round_by_last_modulus_many(const lg_ring* r, int nl, lg_poly* p0, int nb, lg_stream_t s);     /* :159-164 */
+
+/* ---- FastBasisExtender, ring/ring_basis_extension.go ------------------------ */
+int lg_extender_create(const lg_ring* ringQ, const lg_ring* ringP, lg_extender** out);  /* NewFastBasisExtender :55-74 */
+int lg_extender_destroy(lg_extender* e);
+int lg_extender_modup_split_qp(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s);  /* :147-149 */
+int lg_extender_modup_split_pq(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s);  /* :154-156 */
+/* p1 holds all Q limbs then all P limbs; its P part is destroyed (as :172) */
+int lg_extender_moddown_ntt_pq(const lg_extender* e, int level, lg_poly* p1, lg_poly* p2, lg_stream_t s);        /* :163-200 */
+/* p1P is destroyed (as :215) */
+int lg_extender_moddown_splited_ntt_pq(const lg_extender* e, int level, const lg_poly* p1Q, lg_poly* p1P, lg_poly* p2, lg_stream_t s); /* :207-242 */
+int lg_extender_moddown_pq(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s);      /* :248-275 */
+int lg_extender_moddown_splited_pq(const lg_extender* e, int level, const lg_poly* p1Q, const lg_poly* p1P, lg_poly* p2, lg_stream_t s); /* :281-308 */
+int lg_extender_moddown_splited_qp(const lg_extender* e, int levelQ, int levelP, const lg_poly* p1Q, const lg_poly* p1P, lg_poly* p2, lg_stream_t s); /* :314-350 */
+
+/* ---- Decomposer, ring/ring_basis_extension.go:398-713 ----------------------- */
+int lg_decomposer_create(uint64_t N, const uint64_t* Q, int nQ, const uint64_t* P, int nP, lg_decomposer** out); /* NewDecomposer :413-472 */
+int lg_decomposer_destroy(lg_decomposer* d);
+int lg_decomposer_beta(const lg_decomposer* d);
+int lg_decomposer_xalpha(const lg_decomposer* d, int i);                               /* Xalpha :408-410 */
+int lg_decomposer_decompose(const lg_decomposer* d, int level, int crt, const lg_poly* p0, lg_poly* p1, lg_stream_t s); /* :476-597 */
+int lg_decomposer_decompose_and_split(const lg_decomposer* d, int level, int crt, const lg_poly* p0, lg_poly* p1Q, lg_poly* p1P, lg_stream_t s); /* :601-713 */
+
+/* ---- evaluator key-switch path, ckks/evaluator.go ---------------------------- */
+int lg_ckks_eval_create(const lg_ring* ringQ, const lg_ring* ringP, lg_ckks_eval** out); /* NewEvaluator :81-112 (ring part) */
+int lg_ckks_eval_destroy(lg_ckks_eval* e);
+/* host layout [beta][2][nQ+nP][N], NTT + Montgomery form (ckks/keygen.go:282-340) */
+int lg_swk_create(uint64_t N, int beta, int nQP, const uint64_t* host, lg_swk** out);
+int lg_swk_wrap(void* device_ptr, uint64_t N, int beta, int nQP, lg_swk** out);
+int lg_swk_destroy(lg_swk* k);
+/* switchKeysInPlace :1475-1558: p0,p1 receive the level+1 limb results */
+int lg_ckks_switch_keys_in_place(lg_ckks_eval* e, int level, const lg_poly* cx, const lg_swk* evk, lg_poly* p0, lg_poly* p1, lg_stream_t s);
+/* MulRelin :1016-1133, ciphertext x ciphertext with relinearisation key.  Passing
+ * the same handles for (a0,a1) and (b0,b1) selects the squaring branch (:1080-1085). */
+int lg_ckks_mul_relin(lg_ckks_eval* e, int level, const lg_poly* a0, const lg_poly* a1, const lg_poly* b0, const lg_poly* b1,
+                      const lg_swk* rlk, lg_poly* out0, lg_poly* out1, lg_stream_t s);
+/* Relinearize :1144-1162 */
+int lg_ckks_relinearize(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_poly* c2, const lg_swk* rlk,
+                        lg_poly* out0, lg_poly* out1, lg_stream_t s);
+/* Rescale loop body :955-960 applied nb times: DivRoundByLastModulusNTT on both polys */
+int lg_ckks_rescale(lg_ckks_eval* e, int nl, lg_poly* c0, lg_poly* c1, int nb, lg_stream_t s);
+/* SwitchKeys :1176-1189 */
+int lg_ckks_switch_keys(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_swk* k, lg_poly* out0, lg_poly* out1, lg_stream_t s);
+/* permuteNTT :1452-1472 = RotateColumns with a direct key (:1220) / Conjugate (:1449) */
+int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_galois* g, const lg_swk* k,
+                        lg_poly* out0, lg_poly* out1, lg_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATTIGPU_H */

@@ -1,0 +1,652 @@
+// capi_ext.cu -- C-ABI host layer, part 2: FastBasisExtender, Decomposer and the
+// CKKS evaluator key-switch path.  Host-side mirror of
+// ring/ring_basis_extension.go and ckks/evaluator.go:933-1591 (hot ops only).
+#include <string.h>
+
+#include "capi_internal.hpp"
+
+static inline cudaStream_t cs(lg_stream_t s) { return (cudaStream_t)s; }
+
+// ---------------------------------------------------------------------------
+// basisextenderparameters, ring_basis_extension.go:76-142.  The reference uses
+// math/big for Q/q_i, its inverse mod q_i and the residues mod p_j; they are
+// canonical residues and are computed here with 128-bit modular products.
+// ---------------------------------------------------------------------------
+int ModUpDev::build(const u64* Q, int nq, const u64* P, int np) {
+    using namespace lgh;
+    nsrc = nq;
+    ndst = np;
+    std::vector<u64> sQ(Q, Q + nq), sQinv(nq), vqib(nq), vqispj((size_t)nq * np), vqpj((size_t)np * (nq + 1));
+    std::vector<u64> dQ(P, P + np), dQinv(np), dU0(np);
+    for (int i = 0; i < nq; ++i) sQinv[i] = mred_params(Q[i]);
+    for (int j = 0; j < np; ++j) {
+        dQinv[j] = mred_params(P[j]);
+        u64 lo;
+        bred_params(P[j], dU0[j], lo);
+    }
+    for (int i = 0; i < nq; ++i) {
+        const u64 qi = Q[i];
+        u64 star = 1 % qi;
+        for (int k = 0; k < nq; ++k)
+            if (k != i) star = mulmod(star, Q[k] % qi, qi);
+        vqib[i] = mform(powmod(star, qi - 2, qi), qi);  // :115-118 (QiBarre = QiStar^-1 mod qi)
+        for (int j = 0; j < np; ++j) {
+            const u64 pj = P[j];
+            u64 s = 1 % pj;
+            for (int k = 0; k < nq; ++k)
+                if (k != i) s = mulmod(s, Q[k] % pj, pj);
+            vqispj[(size_t)i * np + j] = mform(s, pj);  // :121-123
+        }
+    }
+    for (int j = 0; j < np; ++j) {  // :128-138
+        const u64 pj = P[j];
+        u64 qm = 1 % pj;
+        for (int k = 0; k < nq; ++k) qm = mulmod(qm, Q[k] % pj, pj);
+        const u64 v = pj - qm;
+        u64* row = vqpj.data() + (size_t)j * (nq + 1);
+        row[0] = 0;
+        for (int i = 1; i <= nq; ++i) {
+            const u64 t = row[i - 1] + v;
+            row[i] = t >= pj ? t - pj : t;
+        }
+    }
+    LG_TRY(srcQ.upload(sQ));
+    LG_TRY(srcQinv.upload(sQinv));
+    LG_TRY(qib.upload(vqib));
+    LG_TRY(qispj.upload(vqispj));
+    LG_TRY(qpjinv.upload(vqpj));
+    LG_TRY(dstQ.upload(dQ));
+    LG_TRY(dstQinv.upload(dQinv));
+    LG_TRY(dstU0.upload(dU0));
+    M.srcQ = srcQ.d;
+    M.srcQinv = srcQinv.d;
+    M.qib = qib.d;
+    M.qispj = qispj.d;
+    M.qpjinv = qpjinv.d;
+    M.dstQ = dstQ.d;
+    M.dstQinv = dstQinv.d;
+    M.dstU0 = dstU0.d;
+    M.src_total = nq;
+    M.dst_total = np;
+    return LG_OK;
+}
+
+// modUpExact (:352-393) on `nsrc` source limbs into `ndst` target limbs tgt0..
+static int modup_launch(const ModUpDev& m, u64 N, int batch, const u64* in, size_t in_bs, int nsrc, u64* out,
+                        size_t out_bs, int ndst, int tgt0, cudaStream_t st) {
+    LG_REQUIRE(nsrc >= 1 && nsrc <= m.nsrc && ndst >= 0 && tgt0 + ndst <= m.ndst, "modUpExact: basis out of range");
+    ModUpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = m.M;
+    a.N = (u32)N;
+    a.nsrc = nsrc;
+    a.in = in;
+    a.in_bs = in_bs;
+    a.nruns = 1;
+    a.out[0] = out;
+    a.out_bs[0] = out_bs;
+    a.ndst[0] = ndst;
+    a.tgt0[0] = tgt0;
+    a.copy_out = nullptr;
+    if (lg_launch_modup(a, batch, st) != 0) {
+        lg_set_error("modUpExact: too many source limbs (%d)", nsrc);
+        return LG_ERR_ARG;
+    }
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+// genModDownParams, ring_basis_extension.go:39-53
+static std::vector<u64> gen_moddown(const lg_ring* a, const lg_ring* b) {
+    std::vector<u64> out(a->nl);
+    for (int i = 0; i < a->nl; ++i) {
+        const u64 qi = a->q[i];
+        u64 m = 1 % qi;
+        for (int k = 0; k < b->nl; ++k) m = lgh::mulmod(m, b->q[k] % qi, qi);
+        out[i] = lgh::mform(lgh::powmod(m, qi - 2, qi), qi);
+    }
+    return out;
+}
+
+static int check_p(const lg_poly* p, u64 N, int nl, int batch, const char* what) {
+    LG_REQUIRE(p, "%s: null polynomial", what);
+    LG_REQUIRE(p->N == N, "%s: degree mismatch", what);
+    LG_REQUIRE(p->nlimbs >= nl, "%s: polynomial has %d limbs, %d needed", what, p->nlimbs, nl);
+    LG_REQUIRE(batch < 0 || p->batch == batch, "%s: batch mismatch", what);
+    return LG_OK;
+}
+
+// Shared tail of every ModDown*: tmp = modUp(P part -> Q[:level+1]); optionally
+// NTT(tmp); p2 = MRed(p1Q + (q - tmp), P^-1)   (:219-240, :254-273, :287-306)
+int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* p1Q, size_t p1Q_bs, u64* p1P,
+                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st) {
+    const lg_ring* Q = e->Q;
+    const lg_ring* P = e->P;
+    const u64 N = Q->N;
+    const int nl = level + 1;
+    LG_REQUIRE(level >= 0 && nl <= Q->nl, "ModDown: level %d out of range", level);
+    if (ntt)  // :172 / :215 -- destroys the P part of the input, like the reference
+        LG_TRY(lgi_ntt(P, limb_map_identity(), P->nl, batch, p1P, p1P_bs, p1P, p1P_bs, true, 0, 0, st));
+    Scratch tmp(st);
+    LG_TRY(tmp.alloc((size_t)batch * nl * N));
+    const size_t tbs = (size_t)nl * N;
+    LG_TRY(modup_launch(e->pq, N, batch, p1P, p1P_bs, P->nl, tmp.d, tbs, nl, 0, st));
+    if (ntt) LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
+    return lgi_ew(EW_SUB_MULMONT_SCALAR, Q, limb_map_identity(), nl, batch, p1Q, p1Q_bs, tmp.d, tbs, p2, p2_bs,
+                  e->moddown_pq.data(), nl, st);
+}
+
+extern "C" {
+
+int lg_extender_create(const lg_ring* ringQ, const lg_ring* ringP, lg_extender** out) {
+    LG_REQUIRE(ringQ && ringP && out, "NewFastBasisExtender: null argument");
+    LG_REQUIRE(ringQ->N == ringP->N, "NewFastBasisExtender: ring degrees differ");
+    std::unique_ptr<lg_extender> e(new lg_extender);
+    e->Q = ringQ;
+    e->P = ringP;
+    LG_TRY(e->qp.build(ringQ->q.data(), ringQ->nl, ringP->q.data(), ringP->nl));
+    LG_TRY(e->pq.build(ringP->q.data(), ringP->nl, ringQ->q.data(), ringQ->nl));
+    e->moddown_pq = gen_moddown(ringQ, ringP);
+    e->moddown_qp = gen_moddown(ringP, ringQ);
+    *out = e.release();
+    return LG_OK;
+}
+int lg_extender_destroy(lg_extender* e) {
+    delete e;
+    return LG_OK;
+}
+
+int lg_extender_modup_split_qp(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s) {
+    LG_REQUIRE(e, "ModUpSplitQP: null extender");
+    LG_TRY(check_p(p1, e->Q->N, level + 1, -1, "ModUpSplitQP"));
+    LG_TRY(check_p(p2, e->Q->N, e->P->nl, p1->batch, "ModUpSplitQP"));
+    return modup_launch(e->qp, e->Q->N, p1->batch, p1->d, p1->bstride, level + 1, p2->d, p2->bstride, e->P->nl, 0, cs(s));
+}
+int lg_extender_modup_split_pq(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s) {
+    LG_REQUIRE(e, "ModUpSplitPQ: null extender");
+    LG_TRY(check_p(p1, e->Q->N, level + 1, -1, "ModUpSplitPQ"));
+    LG_TRY(check_p(p2, e->Q->N, e->Q->nl, p1->batch, "ModUpSplitPQ"));
+    return modup_launch(e->pq, e->Q->N, p1->batch, p1->d, p1->bstride, level + 1, p2->d, p2->bstride, e->Q->nl, 0, cs(s));
+}
+int lg_extender_moddown_ntt_pq(const lg_extender* e, int level, lg_poly* p1, lg_poly* p2, lg_stream_t s) {
+    LG_REQUIRE(e, "ModDownNTTPQ: null extender");
+    const int nQ = e->Q->nl, nP = e->P->nl;
+    LG_TRY(check_p(p1, e->Q->N, nQ + nP, -1, "ModDownNTTPQ"));
+    LG_TRY(check_p(p2, e->Q->N, level + 1, p1->batch, "ModDownNTTPQ"));
+    return lgi_moddown_tail_ntt(e, level, p1->batch, p1->d, p1->bstride, p1->d + (size_t)nQ * p1->N, p1->bstride, p2->d,
+                                p2->bstride, true, cs(s));
+}
+int lg_extender_moddown_splited_ntt_pq(const lg_extender* e, int level, const lg_poly* p1Q, lg_poly* p1P, lg_poly* p2,
+                                       lg_stream_t s) {
+    LG_REQUIRE(e, "ModDownSplitedNTTPQ: null extender");
+    LG_TRY(check_p(p1Q, e->Q->N, level + 1, -1, "ModDownSplitedNTTPQ"));
+    LG_TRY(check_p(p1P, e->Q->N, e->P->nl, p1Q->batch, "ModDownSplitedNTTPQ"));
+    LG_TRY(check_p(p2, e->Q->N, level + 1, p1Q->batch, "ModDownSplitedNTTPQ"));
+    return lgi_moddown_tail_ntt(e, level, p1Q->batch, p1Q->d, p1Q->bstride, p1P->d, p1P->bstride, p2->d, p2->bstride, true,
+                                cs(s));
+}
+int lg_extender_moddown_pq(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s) {
+    LG_REQUIRE(e, "ModDownPQ: null extender");
+    const int nP = e->P->nl;
+    LG_TRY(check_p(p1, e->Q->N, level + 1 + nP, -1, "ModDownPQ"));
+    LG_TRY(check_p(p2, e->Q->N, level + 1, p1->batch, "ModDownPQ"));
+    // :254 the P limbs follow the level+1 active Q limbs
+    return lgi_moddown_tail_ntt(e, level, p1->batch, p1->d, p1->bstride, p1->d + (size_t)(level + 1) * p1->N, p1->bstride,
+                                p2->d, p2->bstride, false, cs(s));
+}
+int lg_extender_moddown_splited_pq(const lg_extender* e, int level, const lg_poly* p1Q, const lg_poly* p1P, lg_poly* p2,
+                                   lg_stream_t s) {
+    LG_REQUIRE(e, "ModDownSplitedPQ: null extender");
+    LG_TRY(check_p(p1Q, e->Q->N, level + 1, -1, "ModDownSplitedPQ"));
+    LG_TRY(check_p(p1P, e->Q->N, e->P->nl, p1Q->batch, "ModDownSplitedPQ"));
+    LG_TRY(check_p(p2, e->Q->N, level + 1, p1Q->batch, "ModDownSplitedPQ"));
+    return lgi_moddown_tail_ntt(e, level, p1Q->batch, p1Q->d, p1Q->bstride, p1P->d, p1P->bstride, p2->d, p2->bstride,
+                                false, cs(s));
+}
+int lg_extender_moddown_splited_qp(const lg_extender* e, int levelQ, int levelP, const lg_poly* p1Q, const lg_poly* p1P,
+                                   lg_poly* p2, lg_stream_t s) {
+    // :314-350: polypoolP = ModUpSplitQP(levelQ, p1Q); p2 = MRed(p1P + (p - pool), Q^-1)
+    LG_REQUIRE(e, "ModDownSplitedQP: null extender");
+    const lg_ring* P = e->P;
+    const u64 N = P->N;
+    LG_REQUIRE(levelP >= 0 && levelP < P->nl && levelQ >= 0 && levelQ < e->Q->nl, "ModDownSplitedQP: level out of range");
+    LG_TRY(check_p(p1Q, N, levelQ + 1, -1, "ModDownSplitedQP"));
+    LG_TRY(check_p(p1P, N, levelP + 1, p1Q->batch, "ModDownSplitedQP"));
+    LG_TRY(check_p(p2, N, levelP + 1, p1Q->batch, "ModDownSplitedQP"));
+    const int batch = p1Q->batch;
+    Scratch tmp(cs(s));
+    LG_TRY(tmp.alloc((size_t)batch * P->nl * N));
+    const size_t tbs = (size_t)P->nl * N;
+    LG_TRY(modup_launch(e->qp, N, batch, p1Q->d, p1Q->bstride, levelQ + 1, tmp.d, tbs, P->nl, 0, cs(s)));
+    return lgi_ew(EW_SUB_MULMONT_SCALAR, P, limb_map_identity(), levelP + 1, batch, p1P->d, p1P->bstride, tmp.d, tbs, p2->d,
+                  p2->bstride, e->moddown_qp.data(), levelP + 1, cs(s));
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Decomposer
+// ---------------------------------------------------------------------------
+
+// Decompose / DecomposeAndSplit (:476-713).  outQ receives limbs 0..level, outP
+// the nP special-prime limbs.  In the non-trivial case the reference first copies
+// the digit's own limbs and then overwrites them with the converted value (the
+// second target loop starts at alpha*crt, :548 / :664), so only the conversion
+// is materialised.
+int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u64* p0, size_t p0_bs, u64* outQ,
+                  size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st) {
+    LG_REQUIRE(level >= 0 && level < d->nQ, "Decompose: level %d out of range", level);
+    LG_REQUIRE(crt >= 0 && crt < d->beta, "Decompose: digit %d out of range", crt);
+    const int alphai = d->xalpha[crt];
+    const int p0idxst = crt * d->alpha;
+    const int p0idxed = p0idxst + alphai;
+    LG_REQUIRE(p0idxst <= level, "Decompose: digit %d is not active at level %d", crt, level);
+    const u64 N = d->N;
+    if ((p0idxed > level + 1 && (level + 1) % d->nP == 1) || alphai == 1) {  // :489 / :613
+        FanoutArgs f;
+        f.N = (u32)N;
+        f.in = p0 + (size_t)p0idxst * N;
+        f.in_bs = p0_bs;
+        f.nruns = 2;
+        f.out[0] = outQ;
+        f.out_bs[0] = outQ_bs;
+        f.ndst[0] = level + 1;
+        f.out[1] = outP;
+        f.out_bs[1] = outP_bs;
+        f.ndst[1] = d->nP;
+        f.mode = 0;
+        f.phalf = f.plast = 0;
+        lg_launch_fanout(f, batch, st);
+        LG_LAUNCH_CHECK();
+        return LG_OK;
+    }
+    int index;  // :503-507 / :631-635
+    if (level >= alphai + crt * d->alpha)
+        index = d->xalpha[crt] - 2;
+    else
+        index = (level - 1) % d->alpha;
+    LG_REQUIRE(index >= 0 && index < (int)d->modup[crt].size(), "Decompose: no parameters for digit %d index %d", crt, index);
+    const ModUpDev& m = *d->modup[crt][index];
+    ModUpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = m.M;
+    a.N = (u32)N;
+    a.nsrc = index + 2;
+    a.in = p0 + (size_t)p0idxst * N;
+    a.in_bs = p0_bs;
+    a.nruns = 2;
+    a.out[0] = outQ;  // targets 0..level (:528-563 / :662-692)
+    a.out_bs[0] = outQ_bs;
+    a.ndst[0] = level + 1;
+    a.tgt0[0] = 0;
+    a.out[1] = outP;  // special primes live at table index nQ.. (:565-577 / :694-709)
+    a.out_bs[1] = outP_bs;
+    a.ndst[1] = d->nP;
+    a.tgt0[1] = d->nQ;
+    a.copy_out = nullptr;
+    if (lg_launch_modup(a, batch, st) != 0) {
+        lg_set_error("Decompose: too many source limbs");
+        return LG_ERR_ARG;
+    }
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+static int decomposer_build(lg_decomposer* d, u64 N, const u64* Q, int nQ, const u64* P, int nP) {
+    d->N = N;
+    d->nQ = nQ;
+    d->nP = nP;
+    d->alpha = nP;
+    d->beta = (nQ + nP - 1) / nP;  // :431 ceil(len(Q)/alpha)
+    d->xalpha.assign(d->beta, d->alpha);
+    if (nQ % d->alpha != 0) d->xalpha[d->beta - 1] = nQ % d->alpha;
+    std::vector<u64> Pi(Q, Q + nQ);
+    Pi.insert(Pi.end(), P, P + nP);
+    d->modup.resize(d->beta);
+    for (int i = 0; i < d->beta; ++i)
+        for (int j = 0; j + 1 < d->xalpha[i]; ++j) {
+            std::unique_ptr<ModUpDev> m(new ModUpDev);
+            LG_TRY(m->build(Q + (size_t)i * d->alpha, j + 2, Pi.data(), nQ + nP));
+            d->modup[i].push_back(std::move(m));
+        }
+    return LG_OK;
+}
+
+extern "C" {
+
+int lg_decomposer_create(uint64_t N, const uint64_t* Q, int nQ, const uint64_t* P, int nP, lg_decomposer** out) {
+    LG_REQUIRE(Q && P && out && nQ >= 1 && nP >= 1, "NewDecomposer: invalid argument");
+    LG_REQUIRE(nQ + nP <= LG_MAX_LIMBS, "NewDecomposer: too many moduli");
+    std::unique_ptr<lg_decomposer> d(new lg_decomposer);
+    LG_TRY(decomposer_build(d.get(), N, Q, nQ, P, nP));
+    *out = d.release();
+    return LG_OK;
+}
+int lg_decomposer_destroy(lg_decomposer* d) {
+    delete d;
+    return LG_OK;
+}
+int lg_decomposer_beta(const lg_decomposer* d) { return d ? d->beta : 0; }
+int lg_decomposer_xalpha(const lg_decomposer* d, int i) { return (d && i >= 0 && i < d->beta) ? d->xalpha[i] : 0; }
+
+int lg_decomposer_decompose(const lg_decomposer* d, int level, int crt, const lg_poly* p0, lg_poly* p1, lg_stream_t s) {
+    LG_REQUIRE(d, "Decompose: null decomposer");
+    LG_TRY(check_p(p0, d->N, level + 1, -1, "Decompose"));
+    LG_TRY(check_p(p1, d->N, level + 1 + d->nP, p0->batch, "Decompose"));
+    return lgi_decompose(d, level, crt, p0->batch, p0->d, p0->bstride, p1->d, p1->bstride,
+                         p1->d + (size_t)(level + 1) * d->N, p1->bstride, cs(s));
+}
+int lg_decomposer_decompose_and_split(const lg_decomposer* d, int level, int crt, const lg_poly* p0, lg_poly* p1Q,
+                                      lg_poly* p1P, lg_stream_t s) {
+    LG_REQUIRE(d, "DecomposeAndSplit: null decomposer");
+    LG_TRY(check_p(p0, d->N, level + 1, -1, "DecomposeAndSplit"));
+    LG_TRY(check_p(p1Q, d->N, level + 1, p0->batch, "DecomposeAndSplit"));
+    LG_TRY(check_p(p1P, d->N, d->nP, p0->batch, "DecomposeAndSplit"));
+    return lgi_decompose(d, level, crt, p0->batch, p0->d, p0->bstride, p1Q->d, p1Q->bstride, p1P->d, p1P->bstride, cs(s));
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// CKKS evaluator hot ops
+// ---------------------------------------------------------------------------
+
+// switchKeysInPlace, ckks/evaluator.go:1475-1558, on raw device buffers.
+// cx: [batch][>=level+1][N] NTT domain.  out0/out1: level+1 limbs each.
+static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx, size_t cx_bs, const lg_swk* evk,
+                            u64* out0, size_t out0_bs, u64* out1, size_t out1_bs, cudaStream_t st) {
+    const lg_ring* Q = e->Q;
+    const lg_ring* P = e->P;
+    const lg_ring* QP = e->QP.get();
+    const u64 N = Q->N;
+    const int nQ = Q->nl, nP = P->nl, nl = level + 1, nd = nl + nP;
+    LG_REQUIRE(level >= 0 && level < nQ, "switchKeys: level %d out of range", level);
+    LG_REQUIRE(evk && evk->N == N && evk->nQP == nQ + nP, "switchKeys: switching key shape mismatch");
+    const int alpha = e->alpha;
+    const int beta = (nl + alpha - 1) / alpha;  // :1508
+    LG_REQUIRE(beta <= evk->beta, "switchKeys: key has %d digits, %d needed", evk->beta, beta);
+
+    Scratch c2(st), d(st), acc(st);
+    LG_TRY(c2.alloc((size_t)batch * nl * N));
+    LG_TRY(d.alloc((size_t)batch * nd * N));
+    LG_TRY(acc.alloc((size_t)2 * batch * nd * N));
+    const size_t c2_bs = (size_t)nl * N, d_bs = (size_t)nd * N;
+    u64* acc0 = acc.d;
+    u64* acc1 = acc.d + (size_t)batch * d_bs;
+    const LimbMap qp_map{nl, 0, nQ};  // Q limbs 0..level, then the special primes at #Q.. (:1519-1525)
+
+    // :1503  c2 = InvNTT(cx)
+    LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, cx, cx_bs, c2.d, c2_bs, true, 0, 0, st));
+    for (int i = 0; i < beta; ++i) {
+        // decomposeAndSplitNTT :1561-1591
+        LG_TRY(lgi_decompose(e->dec.get(), level, i, batch, c2.d, c2_bs, d.d, d_bs, d.d + (size_t)nl * N, d_bs, st));
+        const int p0idxst = i * alpha;
+        int p0idxed = p0idxst + e->dec->xalpha[i];
+        if (p0idxed > nl) p0idxed = nl;
+        // :1579-1584 the digit's own limbs are the NTT-domain input limbs
+        LG_TRY(lgi_ew(EW_COPY, Q, limb_map_identity(), p0idxed - p0idxst, batch, cx + (size_t)p0idxst * N, cx_bs, nullptr, 0,
+                      d.d + (size_t)p0idxst * N, d_bs, nullptr, 0, st));
+        // :1586, :1590 NTT of every other Q limb and of the P limbs
+        LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d.d, d_bs, d.d, d_bs, false, p0idxst, p0idxed, st));
+        // :1515-1541
+        KsMacArgs m;
+        m.T = QP->T;
+        m.map = qp_map;
+        m.d = d.d;
+        m.d_bs = d_bs;
+        m.evk0 = evk->key(i, 0);
+        m.evk1 = evk->key(i, 1);
+        m.acc0 = acc0;
+        m.acc1 = acc1;
+        m.acc_bs = d_bs;
+        m.first = (i == 0);
+        m.reduce = ((i & 7) == 1) || (i == beta - 1);  // :1536, :1547
+        lg_launch_ks_mac(m, nd, batch, st);
+        LG_LAUNCH_CHECK();
+    }
+    // :1556-1557
+    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc0, d_bs, acc0 + (size_t)nl * N, d_bs, out0, out0_bs, true, st));
+    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc1, d_bs, acc1 + (size_t)nl * N, d_bs, out1, out1_bs, true, st));
+    return LG_OK;
+}
+
+static int concat_ring(const lg_ring* Q, const lg_ring* P, std::unique_ptr<lg_ring>& out) {
+    std::unique_ptr<lg_ring> r(new lg_ring);
+    r->N = Q->N;
+    r->logN = Q->logN;
+    r->nl = Q->nl + P->nl;
+    auto cat = [](const std::vector<u64>& a, const std::vector<u64>& b) {
+        std::vector<u64> c(a);
+        c.insert(c.end(), b.begin(), b.end());
+        return c;
+    };
+    r->q = cat(Q->q, P->q);
+    r->bred = cat(Q->bred, P->bred);
+    r->mred = cat(Q->mred, P->mred);
+    r->ninv = cat(Q->ninv, P->ninv);
+    r->psi = cat(Q->psi, P->psi);
+    r->psi_inv = cat(Q->psi_inv, P->psi_inv);
+    LG_TRY(lgi_ring_build_device(r.get()));
+    out = std::move(r);
+    return LG_OK;
+}
+
+extern "C" {
+
+int lg_ckks_eval_create(const lg_ring* ringQ, const lg_ring* ringP, lg_ckks_eval** out) {
+    LG_REQUIRE(ringQ && ringP && out, "NewEvaluator: null argument");
+    LG_REQUIRE(ringQ->N == ringP->N, "NewEvaluator: ring degrees differ");
+    LG_REQUIRE(ringQ->nl + ringP->nl <= LG_MAX_LIMBS, "NewEvaluator: too many moduli");
+    std::unique_ptr<lg_ckks_eval> e(new lg_ckks_eval);
+    e->Q = ringQ;
+    e->P = ringP;
+    e->alpha = ringP->nl;
+    LG_TRY(concat_ring(ringQ, ringP, e->QP));
+    lg_extender* ext = nullptr;
+    LG_TRY(lg_extender_create(ringQ, ringP, &ext));
+    e->ext.reset(ext);
+    lg_decomposer* dec = nullptr;
+    LG_TRY(lg_decomposer_create(ringQ->N, ringQ->q.data(), ringQ->nl, ringP->q.data(), ringP->nl, &dec));
+    e->dec.reset(dec);
+    *out = e.release();
+    return LG_OK;
+}
+int lg_ckks_eval_destroy(lg_ckks_eval* e) {
+    delete e;
+    return LG_OK;
+}
+
+int lg_swk_create(uint64_t N, int beta, int nQP, const uint64_t* host, lg_swk** out) {
+    LG_REQUIRE(host && out && beta >= 1 && nQP >= 1, "SwitchingKey: invalid argument");
+    std::unique_ptr<lg_swk> k(new lg_swk);
+    k->N = N;
+    k->beta = beta;
+    k->nQP = nQP;
+    k->owns = true;
+    const size_t bytes = (size_t)beta * 2 * nQP * N * sizeof(u64);
+    LG_CUDA_CHECK(cudaMalloc((void**)&k->d, bytes));
+    LG_CUDA_CHECK(cudaMemcpy(k->d, host, bytes, cudaMemcpyHostToDevice));
+    *out = k.release();
+    return LG_OK;
+}
+int lg_swk_wrap(void* device_ptr, uint64_t N, int beta, int nQP, lg_swk** out) {
+    LG_REQUIRE(device_ptr && out && beta >= 1 && nQP >= 1, "SwitchingKey: invalid argument");
+    LG_REQUIRE(((uintptr_t)device_ptr & 15) == 0, "device pointer must be 16-byte aligned");
+    lg_swk* k = new lg_swk;
+    k->d = (u64*)device_ptr;
+    k->N = N;
+    k->beta = beta;
+    k->nQP = nQP;
+    k->owns = false;
+    *out = k;
+    return LG_OK;
+}
+int lg_swk_destroy(lg_swk* k) {
+    if (k && k->owns && k->d) cudaFree(k->d);
+    delete k;
+    return LG_OK;
+}
+
+int lg_ckks_switch_keys_in_place(lg_ckks_eval* e, int level, const lg_poly* cx, const lg_swk* evk, lg_poly* p0, lg_poly* p1,
+                                 lg_stream_t s) {
+    LG_REQUIRE(e, "switchKeysInPlace: null evaluator");
+    const u64 N = e->Q->N;
+    LG_TRY(check_p(cx, N, level + 1, -1, "switchKeysInPlace"));
+    LG_TRY(check_p(p0, N, level + 1, cx->batch, "switchKeysInPlace"));
+    LG_TRY(check_p(p1, N, level + 1, cx->batch, "switchKeysInPlace"));
+    return ckks_switch_keys(e, level, cx->batch, cx->d, cx->bstride, evk, p0->d, p0->bstride, p1->d, p1->bstride, cs(s));
+}
+
+int lg_ckks_mul_relin(lg_ckks_eval* e, int level, const lg_poly* a0, const lg_poly* a1, const lg_poly* b0, const lg_poly* b1,
+                      const lg_swk* rlk, lg_poly* out0, lg_poly* out1, lg_stream_t s) {
+    LG_REQUIRE(e, "MulRelin: null evaluator");
+    const lg_ring* Q = e->Q;
+    const u64 N = Q->N;
+    const int nl = level + 1;
+    LG_REQUIRE(level >= 0 && nl <= Q->nl, "MulRelin: level %d out of range", level);
+    LG_TRY(check_p(a0, N, nl, -1, "MulRelin"));
+    const int batch = a0->batch;
+    LG_TRY(check_p(a1, N, nl, batch, "MulRelin"));
+    LG_TRY(check_p(b0, N, nl, batch, "MulRelin"));
+    LG_TRY(check_p(b1, N, nl, batch, "MulRelin"));
+    LG_TRY(check_p(out0, N, nl, batch, "MulRelin"));
+    LG_TRY(check_p(out1, N, nl, batch, "MulRelin"));
+    cudaStream_t st = cs(s);
+    const bool square = (a0->d == b0->d && a1->d == b1->d);  // el0 == el1, :1080
+    const size_t bs = (size_t)nl * N;
+    Scratch w(st);
+    LG_TRY(w.alloc((size_t)7 * batch * bs));
+    u64* c00 = w.d;
+    u64* c01 = c00 + batch * bs;
+    u64* c0 = c01 + batch * bs;
+    u64* c1 = c0 + batch * bs;
+    u64* c2 = c1 + batch * bs;
+    u64* k0 = c2 + batch * bs;
+    u64* k1 = k0 + batch * bs;
+    const LimbMap id = limb_map_identity();
+    // :1076-1077
+    LG_TRY(lgi_ew(EW_MFORM, Q, id, nl, batch, a0->d, a0->bstride, nullptr, 0, c00, bs, nullptr, 0, st));
+    LG_TRY(lgi_ew(EW_MFORM, Q, id, nl, batch, a1->d, a1->bstride, nullptr, 0, c01, bs, nullptr, 0, st));
+    LG_TRY(lgi_ew(EW_MULMONT, Q, id, nl, batch, c00, bs, b0->d, b0->bstride, c0, bs, nullptr, 0, st));
+    LG_TRY(lgi_ew(EW_MULMONT, Q, id, nl, batch, c00, bs, b1->d, b1->bstride, c1, bs, nullptr, 0, st));
+    if (square)  // :1083
+        LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c1, bs, c1, bs, c1, bs, nullptr, 0, st));
+    else  // :1091
+        LG_TRY(lgi_ew(EW_MULMONT_ADD, Q, id, nl, batch, c01, bs, b0->d, b0->bstride, c1, bs, nullptr, 0, st));
+    LG_TRY(lgi_ew(EW_MULMONT, Q, id, nl, batch, c01, bs, b1->d, b1->bstride, c2, bs, nullptr, 0, st));
+    // :1098-1101
+    LG_TRY(ckks_switch_keys(e, level, batch, c2, bs, rlk, k0, bs, k1, bs, st));
+    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c0, bs, k0, bs, out0->d, out0->bstride, nullptr, 0, st));
+    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c1, bs, k1, bs, out1->d, out1->bstride, nullptr, 0, st));
+    return LG_OK;
+}
+
+int lg_ckks_relinearize(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_poly* c2, const lg_swk* rlk,
+                        lg_poly* out0, lg_poly* out1, lg_stream_t s) {
+    LG_REQUIRE(e, "Relinearize: null evaluator");
+    const lg_ring* Q = e->Q;
+    const u64 N = Q->N;
+    const int nl = level + 1;
+    LG_REQUIRE(level >= 0 && nl <= Q->nl, "Relinearize: level %d out of range", level);
+    LG_TRY(check_p(c0, N, nl, -1, "Relinearize"));
+    const int batch = c0->batch;
+    LG_TRY(check_p(c1, N, nl, batch, "Relinearize"));
+    LG_TRY(check_p(c2, N, nl, batch, "Relinearize"));
+    LG_TRY(check_p(out0, N, nl, batch, "Relinearize"));
+    LG_TRY(check_p(out1, N, nl, batch, "Relinearize"));
+    cudaStream_t st = cs(s);
+    const size_t bs = (size_t)nl * N;
+    Scratch w(st);
+    LG_TRY(w.alloc((size_t)2 * batch * bs));
+    u64* k0 = w.d;
+    u64* k1 = k0 + batch * bs;
+    LG_TRY(ckks_switch_keys(e, level, batch, c2->d, c2->bstride, rlk, k0, bs, k1, bs, st));
+    const LimbMap id = limb_map_identity();
+    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c0->d, c0->bstride, k0, bs, out0->d, out0->bstride, nullptr, 0, st));
+    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c1->d, c1->bstride, k1, bs, out1->d, out1->bstride, nullptr, 0, st));
+    return LG_OK;
+}
+
+int lg_ckks_rescale(lg_ckks_eval* e, int nl, lg_poly* c0, lg_poly* c1, int nb, lg_stream_t s) {
+    LG_REQUIRE(e, "Rescale: null evaluator");
+    LG_TRY(check_p(c0, e->Q->N, nl, -1, "Rescale"));
+    LG_TRY(check_p(c1, e->Q->N, nl, c0->batch, "Rescale"));
+    LG_REQUIRE(nb >= 1 && nb < nl, "cannot Rescale: input Ciphertext already at level 0");  // ckks/evaluator.go:938
+    for (int k = 0; k < nb; ++k) {  // :955-960
+        LG_TRY(lgi_div_by_last_modulus(e->Q, nl - k, c0->batch, c0->d, c0->bstride, true, true, cs(s)));
+        LG_TRY(lgi_div_by_last_modulus(e->Q, nl - k, c1->batch, c1->d, c1->bstride, true, true, cs(s)));
+    }
+    return LG_OK;
+}
+
+int lg_ckks_switch_keys(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_swk* k, lg_poly* out0,
+                        lg_poly* out1, lg_stream_t s) {
+    LG_REQUIRE(e, "SwitchKeys: null evaluator");
+    const lg_ring* Q = e->Q;
+    const u64 N = Q->N;
+    const int nl = level + 1;
+    LG_REQUIRE(level >= 0 && nl <= Q->nl, "SwitchKeys: level %d out of range", level);
+    LG_TRY(check_p(c0, N, nl, -1, "SwitchKeys"));
+    const int batch = c0->batch;
+    LG_TRY(check_p(c1, N, nl, batch, "SwitchKeys"));
+    LG_TRY(check_p(out0, N, nl, batch, "SwitchKeys"));
+    LG_TRY(check_p(out1, N, nl, batch, "SwitchKeys"));
+    cudaStream_t st = cs(s);
+    const size_t bs = (size_t)nl * N;
+    Scratch w(st);
+    LG_TRY(w.alloc((size_t)2 * batch * bs));
+    u64* k0 = w.d;
+    u64* k1 = k0 + batch * bs;
+    LG_TRY(ckks_switch_keys(e, level, batch, c1->d, c1->bstride, k, k0, bs, k1, bs, st));
+    const LimbMap id = limb_map_identity();
+    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c0->d, c0->bstride, k0, bs, out0->d, out0->bstride, nullptr, 0, st));
+    LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, k1, bs, nullptr, 0, out1->d, out1->bstride, nullptr, 0, st));
+    return LG_OK;
+}
+
+int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_galois* g, const lg_swk* k,
+                        lg_poly* out0, lg_poly* out1, lg_stream_t s) {
+    LG_REQUIRE(e && g, "permuteNTT: null argument");
+    const lg_ring* Q = e->Q;
+    const u64 N = Q->N;
+    const int nl = level + 1;
+    LG_REQUIRE(level >= 0 && nl <= Q->nl, "permuteNTT: level %d out of range", level);
+    LG_REQUIRE(g->N == N, "permuteNTT: index length mismatch");
+    LG_TRY(check_p(c0, N, nl, -1, "permuteNTT"));
+    const int batch = c0->batch;
+    LG_TRY(check_p(c1, N, nl, batch, "permuteNTT"));
+    LG_TRY(check_p(out0, N, nl, batch, "permuteNTT"));
+    LG_TRY(check_p(out1, N, nl, batch, "permuteNTT"));
+    cudaStream_t st = cs(s);
+    const size_t bs = (size_t)nl * N;
+    Scratch w(st);
+    LG_TRY(w.alloc((size_t)4 * batch * bs));
+    u64* el0 = w.d;
+    u64* el1 = el0 + batch * bs;
+    u64* k0 = el1 + batch * bs;
+    u64* k1 = k0 + batch * bs;
+    PermArgs a;
+    memset(&a.T, 0, sizeof(a.T));
+    a.T.N = (u32)N;
+    a.T.logN = Q->logN;
+    a.map = limb_map_identity();
+    a.index = g->d_index.d;
+    a.gen = 0;
+    a.in = c0->d;  // :1462-1463
+    a.in_bs = c0->bstride;
+    a.out = el0;
+    a.out_bs = bs;
+    lg_launch_permute_ntt(a, nl, batch, st);
+    a.in = c1->d;
+    a.in_bs = c1->bstride;
+    a.out = el1;
+    lg_launch_permute_ntt(a, nl, batch, st);
+    LG_LAUNCH_CHECK();
+    LG_TRY(ckks_switch_keys(e, level, batch, el1, bs, k, k0, bs, k1, bs, st));  // :1468
+    const LimbMap id = limb_map_identity();
+    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, el0, bs, k0, bs, out0->d, out0->bstride, nullptr, 0, st));  // :1470
+    LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, k1, bs, nullptr, 0, out1->d, out1->bstride, nullptr, 0, st));  // :1471
+    return LG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// capi_internal.hpp -- host-side objects behind the opaque C-ABI handles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <memory>
+#include <vector>
+
+#include "../../include/lattigpu.h"
+#include "hostmath.hpp"
+#include "kernels.h"
+
+void lg_set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> lg_g_launches;
+
+#define LG_REQUIRE(cond, ...)          \
+    do {                               \
+        if (!(cond)) {                 \
+            lg_set_error(__VA_ARGS__); \
+            return LG_ERR_ARG;         \
+        }                              \
+    } while (0)
+
+#define LG_TRY(expr)              \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != LG_OK) return _rc; \
+    } while (0)
+
+#define LG_LAUNCH_CHECK()                                                               \
+    do {                                                                                \
+        cudaError_t _e = cudaPeekAtLastError();                                         \
+        if (_e != cudaSuccess) {                                                        \
+            lg_set_error("%s:%d: kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return LG_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+// device array owned by a handle
+template <class T>
+struct DevArray {
+    T* d = nullptr;
+    size_t n = 0;
+    DevArray() {}
+    DevArray(const DevArray&) = delete;
+    DevArray& operator=(const DevArray&) = delete;
+    ~DevArray() {
+        if (d) cudaFree(d);
+    }
+    int upload(const std::vector<T>& h) {
+        n = h.size();
+        if (n == 0) return LG_OK;
+        LG_CUDA_CHECK(cudaMalloc(&d, n * sizeof(T)));
+        LG_CUDA_CHECK(cudaMemcpy(d, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+        return LG_OK;
+    }
+};
+
+// stream-ordered scratch (cudaMallocAsync): safe for concurrent evaluators that
+// share read-only ring handles, as the reference's goroutine pattern requires.
+struct Scratch {
+    u64* d = nullptr;
+    cudaStream_t st;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    Scratch(const Scratch&) = delete;
+    int alloc(size_t words) {
+        LG_CUDA_CHECK(cudaMallocAsync((void**)&d, words * sizeof(u64), st));
+        return LG_OK;
+    }
+    ~Scratch() {
+        if (d) cudaFreeAsync(d, st);
+    }
+};
+
+struct lg_ring {
+    u64 N = 0;
+    u32 logN = 0;
+    int nl = 0;
+    std::vector<u64> q, bred, mred, ninv, psi, psi_inv, rescale;  // host copies
+    DevArray<u64> d_q, d_qinv, d_bred, d_psi, d_psi_inv, d_ninv;
+    RingTables T;
+    u64 rescale_param(int j, int i) const { return rescale[(size_t)j * (j - 1) / 2 + i]; }  // rescaleParams[j-1][i]
+};
+
+struct lg_poly {
+    u64* d = nullptr;
+    u64 N = 0;
+    int nlimbs = 0;
+    int batch = 1;
+    size_t bstride = 0;  // words
+    bool owns = false;
+};
+
+struct lg_galois {
+    u64 N = 0;
+    std::vector<u64> index;
+    DevArray<u32> d_index;
+};
+
+// device modupParams (ring_basis_extension.go:20-37)
+struct ModUpDev {
+    int nsrc = 0, ndst = 0;
+    DevArray<u64> srcQ, srcQinv, qib, qispj, qpjinv, dstQ, dstQinv, dstU0;
+    ModUpTables M;
+    int build(const u64* Q, int nq, const u64* P, int np);
+};
+
+struct lg_extender {
+    const lg_ring* Q = nullptr;
+    const lg_ring* P = nullptr;
+    ModUpDev qp, pq;
+    std::vector<u64> moddown_pq;  // per Q limb: MForm(P^-1 mod q_i)
+    std::vector<u64> moddown_qp;  // per P limb: MForm(Q^-1 mod p_j)
+};
+
+struct lg_decomposer {
+    u64 N = 0;
+    int nQ = 0, nP = 0, alpha = 0, beta = 0;
+    std::vector<int> xalpha;
+    std::vector<std::vector<std::unique_ptr<ModUpDev>>> modup;  // [beta][xalpha-1]
+};
+
+struct lg_swk {
+    u64* d = nullptr;
+    u64 N = 0;
+    int beta = 0, nQP = 0;
+    bool owns = false;
+    const u64* key(int digit, int half) const { return d + ((size_t)(digit * 2 + half) * nQP) * N; }
+};
+
+struct lg_ckks_eval {
+    const lg_ring* Q = nullptr;
+    const lg_ring* P = nullptr;
+    std::unique_ptr<lg_ring> QP;  // concatenated tables (ckks.go:73 contextQP)
+    std::unique_ptr<lg_extender> ext;
+    std::unique_ptr<lg_decomposer> dec;
+    int alpha = 0;
+};
+
+// internal (non-ABI) helpers shared between translation units
+int lgi_ring_build_device(lg_ring* r);
+int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, size_t in_bs, u64* out, size_t out_bs,
+            bool inverse, int skip0, int skip1, cudaStream_t st);
+int lgi_ew(int op, const lg_ring* r, LimbMap map, int nl, int batch, const u64* a, size_t a_bs, const u64* b,
+           size_t b_bs, u64* c, size_t c_bs, const u64* scalars, int nscalars, cudaStream_t st);
+int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* p1Q, size_t p1Q_bs, u64* p1P,
+                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st);
+int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u64* p0, size_t p0_bs, u64* outQ,
+                  size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st);
+int lgi_div_by_last_modulus(const lg_ring* r, int nl, int batch, u64* p0, size_t bs, bool round, bool ntt,
+                            cudaStream_t st);

@@ -1,0 +1,48 @@
+// common.cuh -- shared device-side views used by every kernel family.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "modarith.cuh"
+
+// Device-resident tables of one ring.Context (ring/ring_context.go:18-51),
+// indexed by "table limb" = position of the prime in the context's modulus list.
+struct RingTables {
+    const u64* q;        // [nl]            Modulus
+    const u64* qinv;     // [nl]            mredParams
+    const u64* bred;     // [nl][2]         bredParams {hi, lo}
+    const u64* psi;      // [nl][N]         nttPsi     (Montgomery, bit-reversed)
+    const u64* psi_inv;  // [nl][N]         nttPsiInv
+    const u64* ninv;     // [nl]            nttNInv
+    u32 N;
+    u32 logN;
+    int nl;
+};
+
+// Maps the j-th data limb of a launch to a table limb: the first n0 data limbs
+// use table limbs l0.., the rest use l1...  (Q limbs 0..level followed by the
+// special primes at #Q.., as in ckks/evaluator.go:1519-1525.)
+struct LimbMap {
+    int n0, l0, l1;
+    __host__ __device__ int operator()(int j) const { return j < n0 ? l0 + j : l1 + (j - n0); }
+};
+static inline LimbMap limb_map_identity() { return LimbMap{1 << 30, 0, 0}; }
+
+__device__ __forceinline__ LimbConst load_limb_const(const RingTables& T, int tl) {
+    LimbConst c;
+    c.q = T.q[tl];
+    c.qinv = T.qinv[tl];
+    c.u0 = T.bred[2 * tl];
+    c.u1 = T.bred[2 * tl + 1];
+    return c;
+}
+
+#define LG_CUDA_CHECK(expr)                                                         \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            lg_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return LG_ERR_CUDA;                                                     \
+        }                                                                           \
+    } while (0)

@@ -1,0 +1,154 @@
+// kernels.h -- internal launcher interface between the C-ABI host layer
+// (capi.cu) and the kernel families.  Not part of the public boundary.
+#pragma once
+#include <atomic>
+
+#include "common.cuh"
+
+extern std::atomic<uint64_t> lg_g_launches;  // kernels launched by this library
+
+#define LG_MAX_LIMBS 64
+
+// ---- K1: NTT ----------------------------------------------------------------
+struct NttArgs {
+    RingTables T;
+    LimbMap map;
+    const u64* in;
+    u64* out;
+    size_t in_bstride, out_bstride;  // words between consecutive batch entries
+    int skip0, skip1;                // data limbs in [skip0, skip1) are left untouched
+};
+int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cudaStream_t st);
+
+// ---- K3a: coefficient-wise ops (ring/ring.go) --------------------------------
+enum EwOp {
+    EW_ADD = 0,
+    EW_ADD_NOMOD,
+    EW_SUB,
+    EW_SUB_NOMOD,
+    EW_NEG,
+    EW_REDUCE,
+    EW_MUL_BARRETT,
+    EW_MUL_BARRETT_ADD,
+    EW_MUL_BARRETT_ADD_NOMOD,
+    EW_MUL_BARRETT_CONSTANT,
+    EW_MULMONT,
+    EW_MULMONT_ADD,
+    EW_MULMONT_ADD_NOMOD,
+    EW_MULMONT_CONSTANT_ADD_NOMOD,
+    EW_MULMONT_SUB,
+    EW_MULMONT_SUB_NOMOD,
+    EW_MULMONT_CONSTANT,
+    EW_MFORM,
+    EW_INVMFORM,
+    EW_ADD_SCALAR,       // c = CRed(a + s_j)
+    EW_SUB_SCALAR,       // c = CRed(a + (q - s_j))
+    EW_MUL_SCALAR,       // c = MRed(a, MForm(BRedAdd(s_j)))
+    EW_MUL_SCALAR_MONT,  // c = MRed(a, s_j)             (s_j already Montgomery)
+    EW_MUL_POW2,         // c = PowerOf2(a, s_0)
+    EW_AND,
+    EW_OR,
+    EW_XOR,
+    EW_MOD,              // c = BRedAdd(a, m) for a foreign modulus m: s = {m, u0}
+    EW_MULVEC,           // c = MRed(a, vec)   (vec = one limb of N words, shared by all limbs)
+    EW_MULVEC_ADD_NOMOD, // c += MRed(a, vec)
+    EW_SUB_MULMONT_SCALAR,  // c = MRed(a + (q - b), s_j)   (ModDown / rescale tail)
+    EW_COPY,
+    EW_NUM_OPS
+};
+
+struct EwArgs {
+    RingTables T;
+    LimbMap map;
+    const u64* a;
+    const u64* b;
+    u64* c;
+    size_t a_bs, b_bs, c_bs;  // batch strides (words); 0 broadcasts one entry over the batch
+    size_t a_ls, b_ls, c_ls;  // limb strides (words); normally N, 0 broadcasts one limb
+    u64 s[LG_MAX_LIMBS];      // per-data-limb scalars
+};
+int lg_launch_ew(int op, const EwArgs& args, int nlimbs, int batch, cudaStream_t st);
+
+// ---- K4: permutations (ring/ring_galois.go, ring/ring.go) -------------------
+struct PermArgs {
+    RingTables T;
+    LimbMap map;
+    const u64* in;
+    u64* out;
+    size_t in_bs, out_bs;
+    const u32* index;  // gather table (PermuteNTTWithIndex)
+    u64 gen;           // Galois element (Permute) / monomial degree (MultByMonomial)
+};
+int lg_launch_permute_ntt(const PermArgs& a, int nlimbs, int batch, cudaStream_t st);
+int lg_launch_permute_coeff(const PermArgs& a, int nlimbs, int batch, cudaStream_t st);
+int lg_launch_mult_by_monomial(const PermArgs& a, int nlimbs, int batch, cudaStream_t st);
+int lg_launch_bitreverse(const PermArgs& a, int nlimbs, int batch, cudaStream_t st);
+
+// ---- K3b: exact basis extension (ring/ring_basis_extension.go:352-393) ------
+// Device-resident modupParams.  Source basis = nsrc primes, target basis = ndst
+// primes; tables are laid out for the FULL basis the params were built for
+// (src_total sources, dst_total targets) so that a prefix of the sources and an
+// arbitrary list of targets can be used, as the reference does with slices.
+struct ModUpTables {
+    const u64* srcQ;     // [src_total]
+    const u64* srcQinv;  // [src_total]
+    const u64* qib;      // [src_total]              qibMont
+    const u64* qispj;    // [src_total][dst_total]   qispjMont
+    const u64* qpjinv;   // [dst_total][src_total+1] qpjInv
+    const u64* dstQ;     // [dst_total]
+    const u64* dstQinv;  // [dst_total]
+    const u64* dstU0;    // [dst_total]  bredParams[0]
+    int src_total, dst_total;
+};
+struct ModUpArgs {
+    ModUpTables M;
+    u32 N;
+    int nsrc;            // active sources: tables rows 0..nsrc-1
+    const u64* in;       // source limb i at in + b*in_bs + i*N
+    size_t in_bs;
+    // targets are described by up to 3 runs: run k writes ndst_k limbs starting at
+    // out_k (limb stride N) using table targets tgt0_k, tgt0_k+1, ...
+    int nruns;
+    u64* out[3];
+    size_t out_bs[3];
+    int ndst[3];
+    int tgt0[3];
+    // optional pass-through: copy the nsrc source limbs to copy_out (Decompose*'s
+    // "p1.Coeffs[i+p0idxst][x] = p0.Coeffs[i+p0idxst][x]")
+    u64* copy_out;
+    size_t copy_bs;
+};
+int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st);
+
+// broadcast of one limb to many (trivial decomposition case) and the rescale
+// "last limb + pHalf" fan-out
+struct FanoutArgs {
+    u32 N;
+    const u64* in;  // one limb per batch entry
+    size_t in_bs;
+    int nruns;
+    u64* out[2];
+    size_t out_bs[2];
+    int ndst[2];
+    // mode 0: plain copy.  mode 1: out_i = CRed(in + phalf, plast) + add[i]
+    int mode;
+    u64 phalf, plast;
+    u64 add[LG_MAX_LIMBS];
+};
+int lg_launch_fanout(const FanoutArgs& a, int batch, cudaStream_t st);
+
+// ---- K3e: key-switch multiply-accumulate -------------------------------------
+struct KsMacArgs {
+    RingTables T;       // QP tables
+    LimbMap map;        // data limb -> table limb (also the evk limb)
+    const u64* d;       // decomposed digit, NTT domain: limb j at d + b*d_bs + j*N
+    size_t d_bs;
+    const u64* evk0;    // evk[i][0], limb tl at evk0 + tl*N   (shared by the batch)
+    const u64* evk1;
+    u64* acc0;          // accumulators, limb j at acc + b*acc_bs + j*N
+    u64* acc1;
+    size_t acc_bs;
+    int first;          // 1: acc = MRed(..) (no read), 0: acc += MRed(..)
+    int reduce;         // 1: acc = BRedAdd(acc + MRed(..))
+};
+int lg_launch_ks_mac(const KsMacArgs& a, int nlimbs, int batch, cudaStream_t st);

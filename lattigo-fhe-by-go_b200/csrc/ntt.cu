@@ -1,0 +1,322 @@
+// ntt.cu -- kernel family K1: batched per-limb negacyclic NTT / InvNTT.
+//
+// Replaces ring/ntt.go:53-139 of the reference (Cooley-Tukey forward with lazy
+// butterflies and a final BRedAdd; Gentleman-Sande inverse with a final
+// MRed by N^-1).  Every radix-2 butterfly keeps the reference's exact formula
+// (modarith.cuh) and twiddle, so outputs are bit-identical for ANY 64-bit
+// input, including the unreduced words the reference's own benchmarks feed.
+//
+// Schedule (N = 2^logN, one limb = N words, grid = tiles x limbs x batch):
+//   logN <= 11 : one CTA per limb, radix-2 stages in shared memory.
+//   logN >= 12 : two phases of register-resident radix-16 blocks
+//     "strided" phase : the top L = logN-8 stages; a CTA owns all 2^L rows of
+//                       W = 4096/2^L adjacent columns (coalesced 8*W-byte rows),
+//     "contig"  phase : the low 8 stages on 16 contiguous 256-word segments.
+//   Each thread keeps 16 coefficients in registers for 4 stages, then the CTA
+//   re-distributes them through (padded, conflict-free) shared memory.
+//   Twiddle index for the butterfly on (j, j+2^s): (N >> (s+1)) + (j >> (s+1))
+//   in both directions (ring/ntt.go:74 and :120).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+// ---- register blocks --------------------------------------------------------
+// x[r] holds the coefficient at global index j0 + r*2^s (bits [s,s+4) of j0 are
+// zero); twbase = (N + j0) >> s.  Stage u pairs r and r + 2^u (stride 2^(s+u)).
+
+template <int UHI, int ULO, bool VEC>
+LG_DEV void fwd_stages(u64 (&x)[16], const u64* __restrict__ tw, u32 twbase, u64 q, u64 qinv, u64 twoq) {
+#pragma unroll
+    for (int it = 0; it <= UHI - ULO; ++it) {
+        const int u = UHI - it;
+        const u32 base = twbase >> (u + 1);
+        const int ngroups = 16 >> (u + 1);
+        u64 w[8];
+        if (VEC && ngroups >= 2) {
+#pragma unroll
+            for (int g = 0; g < ngroups; g += 2) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tw + base + g));
+                w[g] = v.x;
+                w[g + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < ngroups; ++g) w[g] = __ldg(tw + base + g);
+        }
+#pragma unroll
+        for (int g = 0; g < ngroups; ++g) {
+#pragma unroll
+            for (int k = 0; k < (1 << u); ++k) {
+                const int r = (g << (u + 1)) + k;
+                butterfly_fwd(x[r], x[r + (1 << u)], w[g], q, qinv, twoq);
+            }
+        }
+    }
+}
+
+template <int ULO, int UHI, bool VEC>
+LG_DEV void inv_stages(u64 (&x)[16], const u64* __restrict__ tw, u32 twbase, u64 q, u64 qinv, u64 twoq) {
+#pragma unroll
+    for (int u = ULO; u <= UHI; ++u) {
+        const u32 base = twbase >> (u + 1);
+        const int ngroups = 16 >> (u + 1);
+        u64 w[8];
+        if (VEC && ngroups >= 2) {
+#pragma unroll
+            for (int g = 0; g < ngroups; g += 2) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tw + base + g));
+                w[g] = v.x;
+                w[g + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < ngroups; ++g) w[g] = __ldg(tw + base + g);
+        }
+#pragma unroll
+        for (int g = 0; g < ngroups; ++g) {
+#pragma unroll
+            for (int k = 0; k < (1 << u); ++k) {
+                const int r = (g << (u + 1)) + k;
+                butterfly_inv(x[r], x[r + (1 << u)], w[g], q, qinv, twoq);
+            }
+        }
+    }
+}
+
+LG_DEV u32 pad16(u32 e) { return e + (e >> 4); }
+
+struct LimbSetup {
+    LimbConst c;
+    const u64* in;
+    u64* out;
+    const u64* tw;
+    u64 ninv;
+    bool skip;
+};
+
+template <bool FWD>
+LG_DEV LimbSetup setup_limb(const NttArgs& a) {
+    LimbSetup s;
+    const int j = blockIdx.y, b = blockIdx.z;
+    s.skip = (j >= a.skip0 && j < a.skip1);
+    const int tl = a.map(j);
+    s.c = load_limb_const(a.T, tl);
+    s.tw = (FWD ? a.T.psi : a.T.psi_inv) + (size_t)tl * a.T.N;
+    s.ninv = FWD ? 0 : a.T.ninv[tl];
+    s.in = a.in + (size_t)b * a.in_bstride + (size_t)j * a.T.N;
+    s.out = a.out + (size_t)b * a.out_bstride + (size_t)j * a.T.N;
+    return s;
+}
+
+// ---- forward, strided phase: stages 1..L -----------------------------------
+template <int L>
+__global__ void __launch_bounds__(256) ntt_fwd_strided(const NttArgs a) {
+    constexpr int G = 1 << (L - 4);  // threads per column
+    constexpr int W = 256 / G;       // columns per CTA
+    constexpr int N2 = L - 4;        // stages of the second register block
+    __shared__ u64 sm[N2 > 0 ? 4096 : 1];
+    const LimbSetup s = setup_limb<true>(a);
+    if (s.skip) return;
+    const u32 LB = a.T.logN - L;
+    const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
+    const int t = threadIdx.x, col = t % W, g = t / W;
+    const size_t colg = (size_t)blockIdx.x * W + col;
+    u64 x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(g + r * G) << LB) + colg];
+    fwd_stages<3, 0, false>(x, s.tw, 16u, q, qinv, twoq);
+    if (N2 > 0) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sm[(g + r * G) * W + col] = x[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = sm[(16 * g + r) * W + col];
+        fwd_stages<(N2 > 0 ? N2 - 1 : 0), 0, false>(x, s.tw, (1u << L) + 16u * g, q, qinv, twoq);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) s.out[((size_t)(16 * g + r) << LB) + colg] = x[r];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) s.out[((size_t)(g + r * G) << LB) + colg] = x[r];
+    }
+}
+
+// ---- forward, contiguous phase: last 8 stages + BRedAdd ---------------------
+__global__ void __launch_bounds__(256) ntt_fwd_contig(const NttArgs a) {
+    __shared__ u64 sm[4096 + 256];
+    const LimbSetup s = setup_limb<true>(a);
+    if (s.skip) return;
+    const u32 N = a.T.N;
+    const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
+    const u32 t = threadIdx.x, seg = t >> 4, c = t & 15;
+    const u32 base = blockIdx.x * 4096u;
+    const u32 j0 = base + seg * 256u + c;
+    u64 x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = s.in[j0 + 16 * r];
+    fwd_stages<3, 0, false>(x, s.tw, (N + j0) >> 4, q, qinv, twoq);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + c + 16 * r)] = x[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + 16 * c + r)];
+    const u32 j1 = base + seg * 256u + 16 * c;
+    fwd_stages<3, 0, true>(x, s.tw, N + j1, q, qinv, twoq);
+    // ring/ntt.go:83-85
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + 16 * c + r)] = bred_add(x[r], q, s.c.u0);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s.out[base + t + 256u * k] = sm[pad16(t + 256u * k)];
+}
+
+// ---- inverse, contiguous phase: first 8 stages -------------------------------
+__global__ void __launch_bounds__(256) ntt_inv_contig(const NttArgs a) {
+    __shared__ u64 sm[4096 + 256];
+    const LimbSetup s = setup_limb<false>(a);
+    if (s.skip) return;
+    const u32 N = a.T.N;
+    const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
+    const u32 t = threadIdx.x, seg = t >> 4, c = t & 15;
+    const u32 base = blockIdx.x * 4096u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sm[pad16(t + 256u * k)] = s.in[base + t + 256u * k];
+    __syncthreads();
+    u64 x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + 16 * c + r)];
+    const u32 j1 = base + seg * 256u + 16 * c;
+    inv_stages<0, 3, true>(x, s.tw, N + j1, q, qinv, twoq);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + 16 * c + r)] = x[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + c + 16 * r)];
+    const u32 j0 = base + seg * 256u + c;
+    inv_stages<0, 3, false>(x, s.tw, (N + j0) >> 4, q, qinv, twoq);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s.out[j0 + 16 * r] = x[r];
+}
+
+// ---- inverse, strided phase: last L stages + MRed by N^-1 --------------------
+template <int L>
+__global__ void __launch_bounds__(256) ntt_inv_strided(const NttArgs a) {
+    constexpr int G = 1 << (L - 4);
+    constexpr int W = 256 / G;
+    constexpr int N2 = L - 4;
+    __shared__ u64 sm[N2 > 0 ? 4096 : 1];
+    const LimbSetup s = setup_limb<false>(a);
+    if (s.skip) return;
+    const u32 LB = a.T.logN - L;
+    const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
+    const int t = threadIdx.x, col = t % W, g = t / W;
+    const size_t colg = (size_t)blockIdx.x * W + col;
+    u64 x[16];
+    if (N2 > 0) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(16 * g + r) << LB) + colg];
+        inv_stages<0, (N2 > 0 ? N2 - 1 : 0), false>(x, s.tw, (1u << L) + 16u * g, q, qinv, twoq);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sm[(16 * g + r) * W + col] = x[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = sm[(g + r * G) * W + col];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(g + r * G) << LB) + colg];
+    }
+    inv_stages<0, 3, false>(x, s.tw, 16u, q, qinv, twoq);
+    // ring/ntt.go:136-138
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s.out[((size_t)(g + r * G) << LB) + colg] = mred(x[r], s.ninv, q, qinv);
+}
+
+// ---- small rings (logN <= 11): one CTA per limb, radix-2 in shared memory ----
+template <bool FWD>
+__global__ void ntt_small(const NttArgs a) {
+    extern __shared__ u64 dsm[];
+    const LimbSetup s = setup_limb<FWD>(a);
+    if (s.skip) return;
+    const u32 N = a.T.N;
+    const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
+    for (u32 i = threadIdx.x; i < N; i += blockDim.x) dsm[i] = s.in[i];
+    __syncthreads();
+    if (FWD) {
+        u32 sh = a.T.logN - 1;  // log2(t)
+        for (u32 m = 1; m < N; m <<= 1, --sh) {
+            for (u32 k = threadIdx.x; k < (N >> 1); k += blockDim.x) {
+                const u32 i = k >> sh, jj = k & ((1u << sh) - 1);
+                const u32 j = (i << (sh + 1)) + jj;
+                u64 U = dsm[j], V = dsm[j + (1u << sh)];
+                butterfly_fwd(U, V, s.tw[m + i], q, qinv, twoq);
+                dsm[j] = U;
+                dsm[j + (1u << sh)] = V;
+            }
+            __syncthreads();
+        }
+        for (u32 i = threadIdx.x; i < N; i += blockDim.x) s.out[i] = bred_add(dsm[i], q, s.c.u0);
+    } else {
+        u32 sh = 0;
+        for (u32 h = N >> 1; h >= 1; h >>= 1, ++sh) {
+            for (u32 k = threadIdx.x; k < (N >> 1); k += blockDim.x) {
+                const u32 i = k >> sh, jj = k & ((1u << sh) - 1);
+                const u32 j = (i << (sh + 1)) + jj;
+                u64 U = dsm[j], V = dsm[j + (1u << sh)];
+                butterfly_inv(U, V, s.tw[h + i], q, qinv, twoq);
+                dsm[j] = U;
+                dsm[j + (1u << sh)] = V;
+            }
+            __syncthreads();
+        }
+        for (u32 i = threadIdx.x; i < N; i += blockDim.x) s.out[i] = mred(dsm[i], s.ninv, q, qinv);
+    }
+}
+
+template <int L>
+void launch_strided(bool fwd, const NttArgs& a, dim3 grid, cudaStream_t st) {
+    if (fwd)
+        ntt_fwd_strided<L><<<grid, 256, 0, st>>>(a);
+    else
+        ntt_inv_strided<L><<<grid, 256, 0, st>>>(a);
+}
+
+}  // namespace
+
+int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cudaStream_t st) {
+    if (nlimbs <= 0 || batch <= 0) return 0;
+    const u32 logN = args.T.logN, N = args.T.N;
+    if (logN < 1 || logN > 16) return 1;
+    if (logN <= 11) {
+        const u32 threads = (N >> 1) < 32 ? 32 : ((N >> 1) > 512 ? 512 : (N >> 1));
+        dim3 grid(1, nlimbs, batch);
+        if (inverse)
+            ntt_small<false><<<grid, threads, N * sizeof(u64), st>>>(args);
+        else
+            ntt_small<true><<<grid, threads, N * sizeof(u64), st>>>(args);
+        lg_g_launches += 1;
+        return 0;
+    }
+    const int L = (int)logN - 8;
+    dim3 grid(N / 4096, nlimbs, batch);
+    NttArgs second = args;  // the second phase runs in place on the output
+    second.in = args.out;
+    second.in_bstride = args.out_bstride;
+    auto strided = [&](const NttArgs& a) {
+        switch (L) {
+            case 4: launch_strided<4>(!inverse, a, grid, st); break;
+            case 5: launch_strided<5>(!inverse, a, grid, st); break;
+            case 6: launch_strided<6>(!inverse, a, grid, st); break;
+            case 7: launch_strided<7>(!inverse, a, grid, st); break;
+            default: launch_strided<8>(!inverse, a, grid, st); break;
+        }
+    };
+    if (!inverse) {
+        strided(args);
+        ntt_fwd_contig<<<grid, 256, 0, st>>>(second);
+    } else {
+        ntt_inv_contig<<<grid, 256, 0, st>>>(args);
+        strided(second);
+    }
+    lg_g_launches += 2;
+    return 0;
+}

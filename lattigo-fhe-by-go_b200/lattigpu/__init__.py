@@ -1,0 +1,10 @@
+"""lattigpu -- B200-native RNS polynomial-ring engine behind Lattigo's ring.Context API.
+
+Python mirror of the reference's Go interface, bound to the C ABI in
+include/lattigpu.h.  GPU only: importing works anywhere, calling any op
+without the built library or without a CUDA device raises.
+"""
+from . import ckks, ring  # noqa: F401
+from ._lib import LIB_PATH, LattigpuError, lib  # noqa: F401
+
+__all__ = ["ring", "ckks", "lib", "LattigpuError", "LIB_PATH"]

@@ -1,0 +1,82 @@
+"""Host-side mirror of the hot ops of the reference's ckks.evaluator
+(ckks/evaluator.go:933-1591) over the C ABI: MulRelin, Relinearize, Rescale,
+SwitchKeys, RotateColumns/Conjugate with a direct key, and the key-switch core.
+
+A ciphertext is the pair (value[0], value[1]) of device Polys over Q (NTT
+domain); scale / isNTT metadata stay with the caller as in ckks/operand.go.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib, vp
+from .ring import Poly, _arr, _ptr, _s
+
+
+class SwitchingKey:
+    """ckks.SwitchingKey.evakey: [beta][2] polys over QP, NTT + Montgomery form
+    (ckks/keygen.go:282-340), uploaded once and shared by every ciphertext of a batch."""
+
+    def __init__(self, evakey=None, N=None, device_ptr=None, beta=None, nQP=None, keep=None):
+        h = vp()
+        if evakey is not None:
+            a = _arr(evakey)
+            assert a.ndim == 4 and a.shape[1] == 2, "evakey must be [beta][2][nQ+nP][N]"
+            self.beta, self.nQP, self.N = a.shape[0], a.shape[2], a.shape[3]
+            check(lib().lg_swk_create(self.N, self.beta, self.nQP, _ptr(a), C.byref(h)))
+        else:
+            self.beta, self.nQP, self.N = beta, nQP, N
+            check(lib().lg_swk_wrap(vp(device_ptr), N, beta, nQP, C.byref(h)))
+        self.h = h
+        self._keep = keep
+
+    def __del__(self):
+        try:
+            lib().lg_swk_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Evaluator:
+    """ring part of ckks.NewEvaluator (ckks/evaluator.go:81-112): contexts Q and P,
+    the FastBasisExtender and the Decomposer; scratch is stream-ordered."""
+
+    def __init__(self, contextQ, contextP):
+        self.contextQ, self.contextP = contextQ, contextP
+        h = vp()
+        check(lib().lg_ckks_eval_create(contextQ.h, contextP.h, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            lib().lg_ckks_eval_destroy(self.h)
+        except Exception:
+            pass
+
+    def switchKeysInPlace(self, level, cx, evakey, p0, p1, stream=None):
+        check(lib().lg_ckks_switch_keys_in_place(self.h, level, cx.h, evakey.h, p0.h, p1.h, _s(stream)))
+
+    def MulRelin(self, level, ct0, ct1, evakey, ctOut, stream=None):
+        """ct = (value0, value1).  ct0 is ct1 selects the squaring branch."""
+        check(lib().lg_ckks_mul_relin(self.h, level, ct0[0].h, ct0[1].h, ct1[0].h, ct1[1].h, evakey.h, ctOut[0].h, ctOut[1].h,
+                                      _s(stream)))
+
+    def Relinearize(self, level, ct0, evakey, ctOut, stream=None):
+        check(lib().lg_ckks_relinearize(self.h, level, ct0[0].h, ct0[1].h, ct0[2].h, evakey.h, ctOut[0].h, ctOut[1].h,
+                                        _s(stream)))
+
+    def Rescale(self, nl, ct, nb=1, stream=None):
+        """ckks/evaluator.go:955-960 applied nb times; the result lives in the first nl-nb limbs."""
+        check(lib().lg_ckks_rescale(self.h, nl, ct[0].h, ct[1].h, nb, _s(stream)))
+
+    def SwitchKeys(self, level, ct0, switchingKey, ctOut, stream=None):
+        check(lib().lg_ckks_switch_keys(self.h, level, ct0[0].h, ct0[1].h, switchingKey.h, ctOut[0].h, ctOut[1].h, _s(stream)))
+
+    def permuteNTT(self, level, ct0, index, evakey, ctOut, stream=None):
+        """RotateColumns with a direct key (:1220) / Conjugate (:1449)"""
+        check(lib().lg_ckks_permute_ntt(self.h, level, ct0[0].h, ct0[1].h, index.h, evakey.h, ctOut[0].h, ctOut[1].h,
+                                        _s(stream)))
+
+
+def NewEvaluator(contextQ, contextP):
+    return Evaluator(contextQ, contextP)

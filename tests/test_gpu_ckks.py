@@ -1,0 +1,172 @@
+"""GPU parity tests for the CKKS evaluator key-switch path (ckks/evaluator.go
+:933-1591) against the CPU oracle: switchKeysInPlace, MulRelin (+ squaring
+branch), Relinearize, Rescale, SwitchKeys and RotateColumns/Conjugate via
+permuteNTT.  Shapes follow ckks/params.go DefaultParams (PN12..PN14 bit-exact
+against the oracle; the largest sets through size-independent properties in
+test_gpu_fullsize.py).  Inputs are NewCiphertextRandom-style (ckks/ciphertext.go
+:33-49: full 64-bit words) as in the reference's benchmarks, and in-range.
+"""
+import numpy as np
+import pytest
+
+from oracle import ring_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+# (logN, LogQi, LogPi) -- ckks/params.go:36-87
+PN12 = (12, [37, 32], [38])
+PN13 = (13, [33, 30, 30, 30, 30, 30], [35])
+PN14 = (14, [45] + [34] * 9, [43, 43])
+SMALL3 = (12, [50, 40, 40, 40, 40, 40, 40], [50, 50, 50])  # alpha=3, beta=3 with a partial last digit
+
+
+@pytest.fixture(scope="module")
+def lg():
+    import lattigpu
+    from lattigpu import ring
+
+    ring.set_device(0)
+    return lattigpu
+
+
+class Setup:
+    def __init__(self, lg, params):
+        logN, lq, lp = params
+        self.N = 1 << logN
+        self.Q, self.P, _ = orc.gen_moduli(logN, lq, lp)
+        self.nQ, self.nP = len(self.Q), len(self.P)
+        self.oQ, self.oP = orc.Context(self.N, self.Q), orc.Context(self.N, self.P)
+        self.oev = orc.CkksEvaluator(self.oQ, self.oP)
+        self.cQ = lg.ring.NewContextWithParams(self.N, self.Q)
+        self.cP = lg.ring.NewContextWithParams(self.N, self.P)
+        self.ev = lg.ckks.NewEvaluator(self.cQ, self.cP)
+        self.beta = -(-self.nQ // self.nP)
+
+    def evk(self, rng):
+        """uniform key over QP in [0,q): statistically what newSwitchingKey produces (keygen.go:299-335)"""
+        k = np.stack([rng.integers(0, q, size=(self.beta, 2, self.N), dtype=np.uint64) for q in self.Q + self.P], axis=2)
+        return np.ascontiguousarray(k)
+
+    def ct(self, rng, kind, batch):
+        if kind == "words":
+            return rng.integers(0, 1 << 64, size=(batch, 2, self.nQ, self.N), dtype=np.uint64)
+        return np.ascontiguousarray(np.stack(
+            [rng.integers(0, q, size=(batch, 2, self.N), dtype=np.uint64) for q in self.Q], axis=2))
+
+
+def polys(lg, ct):
+    """[batch][2][nl][N] -> (value0, value1) device polys"""
+    return (lg.ring.Poly.from_numpy(np.ascontiguousarray(ct[:, 0])), lg.ring.Poly.from_numpy(np.ascontiguousarray(ct[:, 1])))
+
+
+def new_ct(lg, s, batch):
+    return (lg.ring.Poly(s.N, s.nQ, batch), lg.ring.Poly(s.N, s.nQ, batch))
+
+
+def host(ct, nl):
+    return np.stack([ct[0].numpy(nl=nl, squeeze=False), ct[1].numpy(nl=nl, squeeze=False)], axis=1)
+
+
+@pytest.mark.parametrize("params", [PN12, PN13, SMALL3, PN14], ids=["PN12", "PN13", "alpha3", "PN14"])
+@pytest.mark.parametrize("kind", ["reduced", "words"])
+def test_switch_keys_in_place_all_levels(lg, params, kind):
+    s = Setup(lg, params)
+    rng = np.random.default_rng(21)
+    evk = s.evk(rng)
+    dk = lg.ckks.SwitchingKey(evk)
+    cx = s.ct(rng, kind, 2)[:, 0]
+    pcx = lg.ring.Poly.from_numpy(np.ascontiguousarray(cx))
+    levels = range(s.nQ - 1, -1, -1) if params is not PN14 else [9, 8, 5, 0]
+    for level in levels:
+        p0, p1 = lg.ring.Poly(s.N, s.nQ, 2), lg.ring.Poly(s.N, s.nQ, 2)
+        s.ev.switchKeysInPlace(level, pcx, dk, p0, p1)
+        g0, g1 = p0.numpy(nl=level + 1), p1.numpy(nl=level + 1)
+        for b in range(2):
+            w0, w1 = s.oev.switch_keys_in_place(level, np.ascontiguousarray(cx[b]), evk)
+            assert np.array_equal(g0[b], w0) and np.array_equal(g1[b], w1), level
+
+
+@pytest.mark.parametrize("params", [PN12, PN13, SMALL3, PN14], ids=["PN12", "PN13", "alpha3", "PN14"])
+@pytest.mark.parametrize("kind", ["reduced", "words"])
+def test_mul_relin_rescale(lg, params, kind):
+    """the north-star sequence: MulRelin (ckks/evaluator.go:1016) then Rescale (:933)"""
+    s = Setup(lg, params)
+    rng = np.random.default_rng(22)
+    evk = s.evk(rng)
+    rlk = lg.ckks.SwitchingKey(evk)
+    batch = 3
+    a, b = s.ct(rng, kind, batch), s.ct(rng, kind, batch)
+    for level in sorted({s.nQ - 1, max(s.nQ - 2, 1)}, reverse=True):
+        nl = level + 1
+        pa, pb, out = polys(lg, a), polys(lg, b), new_ct(lg, s, batch)
+        s.ev.MulRelin(level, pa, pb, rlk, out)
+        got = host(out, nl)
+        want = np.stack([s.oev.mul_relin(level, np.ascontiguousarray(a[i, :, :nl]), np.ascontiguousarray(b[i, :, :nl]), evk)
+                         for i in range(batch)])
+        assert np.array_equal(got, want), level
+        if level >= 1:
+            s.ev.Rescale(nl, out)
+            got = host(out, nl - 1)
+            wr = np.stack([s.oev.rescale(want[i]) for i in range(batch)])
+            assert np.array_equal(got, wr), level
+    # squaring branch (el0 == el1, :1080-1085) and output aliasing an input
+    level = s.nQ - 1
+    pa = polys(lg, a)
+    s.ev.MulRelin(level, pa, pa, rlk, pa)
+    for i in range(batch):
+        x = np.ascontiguousarray(a[i])
+        assert np.array_equal(host(pa, s.nQ)[i], s.oev.mul_relin(level, x, x, evk))
+    if s.nQ >= 3:  # RescaleMany-style double drop
+        out = polys(lg, a)
+        s.ev.Rescale(s.nQ, out, nb=2)
+        for i in range(batch):
+            assert np.array_equal(host(out, s.nQ - 2)[i], s.oev.rescale(np.ascontiguousarray(a[i]), nb=2))
+
+
+@pytest.mark.parametrize("params", [PN13, SMALL3], ids=["PN13", "alpha3"])
+def test_rotate_conjugate_switchkeys_relinearize(lg, params):
+    s = Setup(lg, params)
+    rng = np.random.default_rng(23)
+    evk = s.evk(rng)
+    key = lg.ckks.SwitchingKey(evk)
+    batch = 2
+    a = s.ct(rng, "reduced", batch)
+    pa = polys(lg, a)
+    GaloisGen = 5  # ckks/ckks.go
+    for level in (s.nQ - 1, 1):
+        nl = level + 1
+        for gen, power in [(GaloisGen, 1), (GaloisGen, 5), (2 * s.N - 1, 1)]:  # rotations by 1, 5; conjugation
+            idx = lg.ring.PermuteNTTIndex(gen, power, s.N)
+            out = new_ct(lg, s, batch)
+            s.ev.permuteNTT(level, pa, idx, key, out)
+            widx = orc.permute_ntt_index(gen, power, s.N)
+            for i in range(batch):
+                want = s.oev.permute_ntt(level, np.ascontiguousarray(a[i, :, :nl]), widx, evk)
+                assert np.array_equal(host(out, nl)[i], want), (level, gen, power)
+        out = new_ct(lg, s, batch)
+        s.ev.SwitchKeys(level, pa, key, out)
+        for i in range(batch):
+            assert np.array_equal(host(out, nl)[i], s.oev.switch_keys(level, np.ascontiguousarray(a[i, :, :nl]), evk))
+        # Relinearize (:1144-1162) of a degree-2 ciphertext = switch keys on value[2]
+        c2 = s.ct(rng, "reduced", batch)[:, 0]
+        p2 = lg.ring.Poly.from_numpy(np.ascontiguousarray(c2))
+        out = new_ct(lg, s, batch)
+        s.ev.Relinearize(level, (pa[0], pa[1], p2), key, out)
+        for i in range(batch):
+            k0, k1 = s.oev.switch_keys_in_place(level, np.ascontiguousarray(c2[i]), evk)
+            assert np.array_equal(out[0].numpy(nl=nl, squeeze=False)[i], s.oQ.op3("add", np.ascontiguousarray(a[i, 0, :nl]), k0))
+            assert np.array_equal(out[1].numpy(nl=nl, squeeze=False)[i], s.oQ.op3("add", np.ascontiguousarray(a[i, 1, :nl]), k1))
+
+
+def test_error_paths(lg):
+    s = Setup(lg, PN12)
+    rng = np.random.default_rng(24)
+    key = lg.ckks.SwitchingKey(s.evk(rng))
+    a = polys(lg, s.ct(rng, "reduced", 1))
+    with pytest.raises(lg.LattigpuError, match="level 0"):  # ckks/evaluator.go:938
+        s.ev.Rescale(1, a)
+    with pytest.raises(lg.LattigpuError, match="out of range"):
+        s.ev.MulRelin(5, a, a, key, a)
+    short = lg.ckks.SwitchingKey(s.evk(rng)[:1])
+    with pytest.raises(lg.LattigpuError, match="digits"):
+        s.ev.MulRelin(1, a, a, short, a)
