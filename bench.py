@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ring hot path on B200.
+
+Metric (BASELINE.json): batched NTT/s and CKKS MulRelin+Rescale ops/s at logN=16.
+Workload at every N: CKKS PN16QP1761 (ckks/params.go:79-86: N=2^16, 34 Q limbs,
+4 P limbs, alpha=4, beta=9), level 33 -> 32; one "step" = MulRelin (with a
+relinearisation key) followed by Rescale on a batch of independent synthetic
+ciphertexts (ckks/evaluator.go:1016 and :933).  `value` is MulRelin+Rescale ops
+per second over all ranks with inputs resident in HBM; `ntt` carries the batched
+limb-NTT rates; `e2e` is the same step through the C ABI with HOST buffers
+(pinned upload of both operands, download of the result, inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU); ciphertexts are independent, so
+ranks shard the batch with no data-path collective ("weak" scaling: B per GPU).
+--impl reference times the CPU restatement of the reference (oracle/, no Go
+toolchain exists in the image) with one evaluator per host thread.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "lattigo-fhe-by-go_b200"))
+
+SEED = 0x1A771C0 + 4  # fixed seed + config id
+PARAMS_ID = 4  # ckks.PN16QP1761
+WORKLOAD = "CKKS PN16QP1761 (N=2^16, 34+4 limbs, level 33): MulRelin+Rescale, batch of independent ciphertexts"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="ciphertexts per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="ops in the cpu_baseline sample (0 = one per host thread)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--params", type=int, default=PARAMS_ID, help="index into ckks.DefaultParams (default PN16QP1761)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle (a literal C restatement of the reference) on host threads,
+# one evaluator per thread as in examples/dbfv/psi/psi.go:214-233
+# ----------------------------------------------------------------------------
+def cpu_mulrelin_rescale(params_id, nops, nthreads, seed=SEED):
+    import numpy as np
+
+    from lattigpu import ckks as gckks
+    from oracle import ring_oracle as orc
+
+    p = gckks.DefaultParams[params_id]
+    N = 1 << p["LogN"]
+    Q, P, _ = orc.gen_moduli(p["LogN"], p["LogQi"], p["LogPi"])
+    nQ, nP = len(Q), len(P)
+    beta = -(-nQ // nP)
+    rng = np.random.default_rng(seed)
+    oQ, oP = orc.Context(N, Q), orc.Context(N, P)
+    evk = np.ascontiguousarray(
+        np.stack([rng.integers(0, q, size=(beta, 2, N), dtype=np.uint64) for q in Q + P], axis=2))
+    cts = [np.ascontiguousarray(np.stack([rng.integers(0, q, size=(2, N), dtype=np.uint64) for q in Q], axis=1))
+           for _ in range(2)]
+    evs = [orc.CkksEvaluator(oQ, oP) for _ in range(nthreads)]
+    level = nQ - 1
+    counter = {"next": 0}
+    lock = threading.Lock()
+
+    def worker(ev):
+        while True:
+            with lock:
+                i = counter["next"]
+                if i >= nops:
+                    return
+                counter["next"] = i + 1
+            out = ev.mul_relin(level, cts[0], cts[1], evk)  # ctypes releases the GIL
+            ev.rescale(out)
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=worker, args=(ev,)) for ev in evs]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return nops / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nops = args.cpu_sample or cores
+    vals = []
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_mulrelin_rescale(args.params, min(nops, cores), cores)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, _ = cpu_mulrelin_rescale(args.params, nops, cores)
+        vals.append(v)
+        if time.perf_counter() - t_all > 240:
+            break
+    vals.sort()
+    value = vals[len(vals) // 2]
+    sample = "%d MulRelin+Rescale ops per step (one oracle evaluator per host thread), median of %d steps" % (nops, len(vals))
+    line = {
+        "impl": "reference", "metric": "CKKS MulRelin+Rescale ops/s at logN=16 (batched)", "value": value,
+        "unit": "ops/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 1, "ms_per_step": 1e3 * nops / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": nops},
+        "cpu_baseline": {"value": value, "unit": "ops/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import lattigpu
+    from lattigpu import ckks as gckks
+    from lattigpu import ring as gring
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    gring.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    p = gckks.DefaultParams[args.params]
+    N = 1 << p["LogN"]
+    Q, P = gckks.GenModuli(p)
+    nQ, nP = len(Q), len(P)
+    alpha = nP
+    beta = -(-nQ // alpha)
+    level = nQ - 1
+    B = args.batch
+    ctxQ, ctxP = gring.NewContextWithParams(N, Q), gring.NewContextWithParams(N, P)
+    ev = gckks.NewEvaluator(ctxQ, ctxP)
+    st = torch.cuda.current_stream()
+    sp = st.cuda_stream
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + rank)
+
+    def uniform(shape_prefix, moduli):
+        """uniform in [0, q_i) per limb, generated on the device: [*prefix][limb][N] int64"""
+        t = torch.empty(*shape_prefix, len(moduli), N, dtype=torch.int64, device=dev)
+        for i, q in enumerate(moduli):
+            t[..., i, :] = torch.randint(0, q, (*shape_prefix, N), dtype=torch.int64, device=dev, generator=g)
+        return t
+
+    def wrap(t, nl, batch):
+        return gring.Poly.wrap(t.data_ptr(), N, nl, batch, keep=t)
+
+    evk_t = uniform((beta, 2), Q + P)
+    rlk = gckks.SwitchingKey(N=N, device_ptr=evk_t.data_ptr(), beta=beta, nQP=nQ + nP, keep=evk_t)
+    a_t = [uniform((B,), Q) for _ in range(2)]
+    b_t = [uniform((B,), Q) for _ in range(2)]
+    o_t = [torch.empty(B, nQ, N, dtype=torch.int64, device=dev) for _ in range(2)]
+    ct_a = tuple(wrap(t, nQ, B) for t in a_t)
+    ct_b = tuple(wrap(t, nQ, B) for t in b_t)
+    ct_o = tuple(wrap(t, nQ, B) for t in o_t)
+
+    def step():
+        ev.MulRelin(level, ct_a, ct_b, rlk, ct_o, stream=sp)
+        ev.Rescale(nQ, ct_o, 1, stream=sp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = gring.launch_count()
+        e0.record(st)
+        for _ in range(steps):
+            fn()
+        e1.record(st)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = gring.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    # ---- headline: MulRelin + Rescale, inputs resident in HBM -------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, launches = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms / args.steps
+    value = world * B * 1e3 / ms_per_step
+
+    # ---- batched limb-NTT rates (the dominant kernel family, timed alone) -------
+    ntt_in, ntt_out = ct_a[0], ct_o[0]
+    nlimbs_launch = B * nQ
+
+    def fwd():
+        ctxQ.NTT(ntt_in, ntt_out, stream=sp)
+
+    def inv():
+        ctxQ.InvNTT(ntt_in, ntt_out, stream=sp)
+
+    reps = max(20, args.steps)
+    fwd_ms, _ = timed(fwd, reps, 3)
+    inv_ms, _ = timed(inv, reps, 3)
+    fwd_us = 1e3 * fwd_ms / reps
+    inv_us = 1e3 * inv_ms / reps
+    ntt_fwd_rate = world * nlimbs_launch / (fwd_us * 1e-6)
+    ntt_inv_rate = world * nlimbs_launch / (inv_us * 1e-6)
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    alg_bytes = 16.0 * N * nlimbs_launch  # one limb-NTT reads and writes N words once
+    achieved = alg_bytes / (fwd_us * 1e-6) / 1e9
+    butterflies = (N // 2) * p["LogN"] * nlimbs_launch
+    roofline = {
+        "bound": "hbm", "kernel": "ntt_fwd (strided + contiguous phase, one batched limb-NTT launch pair)",
+        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "limb_ntts_per_launch": nlimbs_launch,
+        "launch_us": fwd_us,
+        # the kernel is INT-pipe bound before it is HBM bound: 11 32x32 multiplies per butterfly
+        "int_pipe": {"butterflies_per_s": butterflies / (fwd_us * 1e-6), "imad_per_butterfly_min": 11,
+                     "gimad_per_s": 11 * butterflies / (fwd_us * 1e-6) / 1e9},
+    }
+
+    # ---- e2e: host buffers through the C ABI ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_a = [torch.empty(B, nQ, N, dtype=torch.int64).pin_memory() for _ in range(2)]
+        h_b = [torch.empty(B, nQ, N, dtype=torch.int64).pin_memory() for _ in range(2)]
+        h_o = [torch.empty(B, nQ - 1, N, dtype=torch.int64).pin_memory() for _ in range(2)]
+        for h, d in zip(h_a + h_b, a_t + b_t):
+            h.copy_(d)
+        L = lattigpu.lib()
+        u64p = ctypes.POINTER(ctypes.c_uint64)
+
+        def hp(t):
+            return ctypes.cast(t.data_ptr(), u64p)
+
+        def e2e_step():
+            for poly, h in zip(ct_a + ct_b, h_a + h_b):
+                lattigpu._lib.check(L.lg_poly_upload(poly.h, 0, B, 0, nQ, hp(h), ctypes.c_void_p(sp)))
+            step()
+            for poly, h in zip(ct_o, h_o):
+                lattigpu._lib.check(L.lg_poly_download(poly.h, 0, B, 0, nQ - 1, hp(h), ctypes.c_void_p(sp)))
+
+        e2e_steps = max(3, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * B * e2e_steps / dt, "unit": "ops/s", "h2d_bytes_per_step": 4 * B * nQ * N * 8,
+               "d2h_bytes_per_step": 2 * B * (nQ - 1) * N * 8, "ms_per_step": 1e3 * dt / e2e_steps,
+               "note": "pinned host buffers; lg_poly_upload x4, MulRelin, Rescale, lg_poly_download x2 per step"}
+
+    # ---- cpu baseline (rank 0, N=1 only) -----------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        nops = args.cpu_sample or cores
+        v, dt = cpu_mulrelin_rescale(args.params, nops, cores)
+        cpu = {"value": v, "unit": "ops/s", "cores": cores, "kind": "port",
+               "sample": "%d MulRelin+Rescale ops, one oracle evaluator per host thread, %.1f s wall" % (nops, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": "CKKS MulRelin+Rescale ops/s at logN=16 (batched)", "value": value, "unit": "ops/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "level": level,
+                       "l2_policy": "inputs+key larger than L2 (%.0f MiB per step per GPU), no flush" %
+                                    ((4 * B * nQ + 2 * beta * (nQ + nP)) * N * 8 / 2**20),
+                       "parallelism": "batch-sharded x%d, no collective" % world, "seed": SEED},
+            "ntt": {"fwd_limb_ntt_per_s": ntt_fwd_rate, "inv_limb_ntt_per_s": ntt_inv_rate, "N": N,
+                    "limbs_per_launch": nlimbs_launch, "fwd_us_per_launch": fwd_us, "inv_us_per_launch": inv_us},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

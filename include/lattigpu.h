@@ -79,6 +79,11 @@ int lg_ring_nlimbs(const lg_ring* ring);
 int lg_ring_get_tables(const lg_ring* ring, uint64_t* moduli, uint64_t* bred, uint64_t* mred, uint64_t* psi,
                        uint64_t* psi_inv, uint64_t* ninv, uint64_t* rescale);
 
+/* host-only number theory of the ring package (no device work) */
+int lg_is_prime(uint64_t num);                                                    /* IsPrime, ring/utils.go:75-128 */
+int lg_generate_ntt_primes(uint64_t logQ, uint64_t logN, uint64_t levels, uint64_t* primes); /* GenerateNTTPrimes :133-175 */
+uint64_t lg_primitive_root(uint64_t q);                                           /* primitiveRoot :182-205 */
+
 /* ---- ring.Poly ------------------------------------------------------------ */
 int lg_poly_create(uint64_t N, int nlimbs, int batch, lg_poly** out);            /* ring.NewPoly, ring_object.go:16-23 */
 int lg_poly_wrap(void* device_ptr, uint64_t N, int nlimbs, int batch, lg_poly** out); /* non-owning */

@@ -202,6 +202,26 @@ int lg_ring_get_tables(const lg_ring* r, uint64_t* moduli, uint64_t* bred, uint6
     return LG_OK;
 }
 
+// host-only helpers of ring/utils.go
+int lg_is_prime(uint64_t num) { return lgh::is_prime(num) ? 1 : 0; }
+uint64_t lg_primitive_root(uint64_t q) { return lgh::primitive_root(q); }
+int lg_generate_ntt_primes(uint64_t logQ, uint64_t logN, uint64_t levels, uint64_t* primes) {
+    // ring/utils.go:133-175 ("logQ must be between 1 and 60" panics there)
+    LG_REQUIRE(logQ >= 1 && logQ <= 60, "logQ must be between 1 and 60");
+    LG_REQUIRE(primes || levels == 0, "null output");
+    const u64 two_n = (u64)2 << logN;
+    u64 x = ((u64)1 << logQ) + 1, y = x, n = 0;
+    while (n < levels) {
+        if (lgh::is_prime(x)) primes[n++] = x;
+        x += two_n;
+        if (n < levels && two_n > y) {  // :161-170 (unreachable for logQ > logN+1, kept for fidelity)
+            y -= two_n;
+            if (lgh::is_prime(y)) primes[n++] = y;
+        }
+    }
+    return LG_OK;
+}
+
 // ---------------------------------------------------------------------------
 // ring.Poly
 // ---------------------------------------------------------------------------

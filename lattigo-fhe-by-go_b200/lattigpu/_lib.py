@@ -59,6 +59,9 @@ SIGNATURES = {
     "lg_ring_n": (u64, [_R]),
     "lg_ring_nlimbs": (ci, [_R]),
     "lg_ring_get_tables": (ci, [_R, p64, p64, p64, p64, p64, p64, p64]),
+    "lg_is_prime": (ci, [u64]),
+    "lg_generate_ntt_primes": (ci, [u64, u64, u64, p64]),
+    "lg_primitive_root": (u64, [u64]),
     "lg_poly_create": (ci, [u64, ci, ci, C.POINTER(vp)]),
     "lg_poly_wrap": (ci, [vp, u64, ci, ci, C.POINTER(vp)]),
     "lg_poly_view": (ci, [_P, ci, ci, C.POINTER(vp)]),

@@ -13,6 +13,36 @@ from ._lib import check, lib, vp
 from .ring import Poly, _arr, _ptr, _s
 
 
+# ckks/params.go:36-87 DefaultParams: (LogN, LogQi, LogPi, Scale)
+PN12QP109, PN13QP218, PN14QP438, PN15QP880, PN16QP1761 = range(5)
+DefaultParams = [
+    dict(LogN=12, LogQi=[37, 32], LogPi=[38], Scale=float(1 << 32)),
+    dict(LogN=13, LogQi=[33, 30, 30, 30, 30, 30], LogPi=[35], Scale=float(1 << 30)),
+    dict(LogN=14, LogQi=[45] + [34] * 9, LogPi=[43, 43], Scale=float(1 << 34)),
+    dict(LogN=15, LogQi=[50] + [40] * 17, LogPi=[50, 50, 50], Scale=float(1 << 40)),
+    dict(LogN=16, LogQi=[55] + [45] * 33, LogPi=[55, 55, 55, 55], Scale=float(1 << 45)),
+]
+
+
+def GenModuli(params):
+    """ckks/utils.go:150-193: primes are generated per bit size (GenerateNTTPrimes) and
+    dealt in order to Q, then P, so that all moduli are distinct.  Host only."""
+    from .ring import GenerateNTTPrimes
+
+    need = {}
+    for b in list(params["LogQi"]) + list(params["LogPi"]):
+        if b > 60:
+            raise ValueError("cannot GenModuli: the provided LogQi/LogPi must be smaller than 61")
+        need[b] = need.get(b, 0) + 1
+    primes = {b: GenerateNTTPrimes(b, params["LogN"], n) for b, n in need.items()}
+    Q, P = [], []
+    for b in params["LogQi"]:
+        Q.append(primes[b].pop(0))
+    for b in params["LogPi"]:
+        P.append(primes[b].pop(0))
+    return Q, P
+
+
 class SwitchingKey:
     """ckks.SwitchingKey.evakey: [beta][2] polys over QP, NTT + Montgomery form
     (ckks/keygen.go:282-340), uploaded once and shared by every ciphertext of a batch."""

@@ -37,6 +37,17 @@ def launch_count():
     return int(lib().lg_launch_count())
 
 
+def GenerateNTTPrimes(logQ, logN, levels):
+    """ring/utils.go:133-175 (host only)"""
+    out = np.zeros(levels, dtype=np.uint64)
+    check(lib().lg_generate_ntt_primes(logQ, logN, levels, _ptr(out)))
+    return [int(x) for x in out]
+
+
+def IsPrime(num):
+    return bool(lib().lg_is_prime(num))
+
+
 class Stream:
     def __init__(self, handle=None):
         if handle is None:
