@@ -40,16 +40,30 @@ __global__ void __launch_bounds__(256) modup_kernel(const ModUpArgs a) {
 #pragma unroll 1
         for (int t = 0; t < a.ndst[k]; ++t) {
             const int tg = a.tgt0[k] + t;
-            const u64 pj = __ldg(M.dstQ + tg), pinv = __ldg(M.dstQinv + tg), pu0 = __ldg(M.dstU0 + tg);
-            u64 acc = 0;
+            const u64 pj = __ldg(M.dstQ + tg), pinv = __ldg(M.dstQinv + tg);
+            // The reference sums canonical MRed(y_i, qispjMont[i][j]) terms (BRedAdd when i&7==6) and
+            // canonicalises with a final BRedAdd (:379-389), i.e. it returns
+            // (sum_i y_i*C_ij + qpjInv[j][v]) mod p_j in [0,p_j).  The same residue is obtained with
+            // one Montgomery reduction per 8 sources of the 128-bit sum of y_i * qispjMont[i][j]
+            // (< 8 * 2^61 * p_j, so REDC lands in [0,2p_j)) followed by conditional subtractions.
+            u64 total = 0;
 #pragma unroll
-            for (int i = 0; i < MAXSRC; ++i) {
-                if (i < a.nsrc) {
-                    acc += mred(y[i], __ldg(M.qispj + (size_t)i * M.dst_total + tg), pj, pinv);
-                    if ((i & 7) == 6) acc = bred_add(acc, pj, pu0);
+            for (int c0 = 0; c0 < MAXSRC; c0 += 8) {
+                if (c0 < a.nsrc) {
+                    unsigned __int128 S = 0;
+#pragma unroll
+                    for (int i = c0; i < c0 + 8 && i < MAXSRC; ++i)
+                        if (i < a.nsrc) S += (unsigned __int128)y[i] * __ldg(M.qispj + (size_t)i * M.dst_total + tg);
+                    const u64 shi = (u64)(S >> 64), slo = (u64)S;
+                    const u64 r = shi - mul_hi(mul_lo(slo, pinv), pj) + pj;  // in [0, 2p_j]
+                    total += cred(cred(r, pj), pj);
                 }
             }
-            out[(size_t)t * a.N] = bred_add(acc + __ldg(M.qpjinv + (size_t)tg * (M.src_total + 1) + v), pj, pu0);
+            total += __ldg(M.qpjinv + (size_t)tg * (M.src_total + 1) + v);
+            if (MAXSRC <= 8)
+                out[(size_t)t * a.N] = cred(total, pj);  // total < 2 p_j
+            else
+                out[(size_t)t * a.N] = bred_add(total, pj, __ldg(M.dstU0 + tg));
         }
     }
 }

@@ -118,8 +118,9 @@ static int check_p(const lg_poly* p, u64 N, int nl, int batch, const char* what)
 
 // Shared tail of every ModDown*: tmp = modUp(P part -> Q[:level+1]); optionally
 // NTT(tmp); p2 = MRed(p1Q + (q - tmp), P^-1)   (:219-240, :254-273, :287-306)
+// accumulate = true adds the result into p2 with CRed (the AddLvl the evaluators apply right after).
 int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* p1Q, size_t p1Q_bs, u64* p1P,
-                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st) {
+                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st, bool accumulate) {
     const lg_ring* Q = e->Q;
     const lg_ring* P = e->P;
     const u64 N = Q->N;
@@ -132,8 +133,8 @@ int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* 
     const size_t tbs = (size_t)nl * N;
     LG_TRY(modup_launch(e->pq, N, batch, p1P, p1P_bs, P->nl, tmp.d, tbs, nl, 0, st));
     if (ntt) LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
-    return lgi_ew(EW_SUB_MULMONT_SCALAR, Q, limb_map_identity(), nl, batch, p1Q, p1Q_bs, tmp.d, tbs, p2, p2_bs,
-                  e->moddown_pq.data(), nl, st);
+    return lgi_ew(accumulate ? EW_SUB_MULMONT_SCALAR_ADD : EW_SUB_MULMONT_SCALAR, Q, limb_map_identity(), nl, batch, p1Q,
+                  p1Q_bs, tmp.d, tbs, p2, p2_bs, e->moddown_pq.data(), nl, st);
 }
 
 extern "C" {
@@ -352,9 +353,12 @@ int lg_decomposer_decompose_and_split(const lg_decomposer* d, int level, int crt
 // ---------------------------------------------------------------------------
 
 // switchKeysInPlace, ckks/evaluator.go:1475-1558, on raw device buffers.
-// cx: [batch][>=level+1][N] NTT domain.  out0/out1: level+1 limbs each.
+// cx: [batch][>=level+1][N] NTT domain.  out0/out1: level+1 limbs each; with add0/add1 the result is
+// added (CRed) into what out0/out1 already hold -- the AddLvl every caller applies next (:1103-1104,
+// :1158-1159, :1187, :1470).
 static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx, size_t cx_bs, const lg_swk* evk,
-                            u64* out0, size_t out0_bs, u64* out1, size_t out1_bs, cudaStream_t st) {
+                            u64* out0, size_t out0_bs, u64* out1, size_t out1_bs, cudaStream_t st, bool add0 = false,
+                            bool add1 = false) {
     const lg_ring* Q = e->Q;
     const lg_ring* P = e->P;
     const lg_ring* QP = e->QP.get();
@@ -383,30 +387,49 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
         const int p0idxst = i * alpha;
         int p0idxed = p0idxst + e->dec->xalpha[i];
         if (p0idxed > nl) p0idxed = nl;
-        // :1579-1584 the digit's own limbs are the NTT-domain input limbs
-        LG_TRY(lgi_ew(EW_COPY, Q, limb_map_identity(), p0idxed - p0idxst, batch, cx + (size_t)p0idxst * N, cx_bs, nullptr, 0,
-                      d.d + (size_t)p0idxst * N, d_bs, nullptr, 0, st));
-        // :1586, :1590 NTT of every other Q limb and of the P limbs
-        LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d.d, d_bs, d.d, d_bs, false, p0idxst, p0idxed, st));
-        // :1515-1541
-        KsMacArgs m;
-        m.T = QP->T;
-        m.map = qp_map;
-        m.d = d.d;
-        m.d_bs = d_bs;
-        m.evk0 = evk->key(i, 0);
-        m.evk1 = evk->key(i, 1);
-        m.acc0 = acc0;
-        m.acc1 = acc1;
-        m.acc_bs = d_bs;
-        m.first = (i == 0);
-        m.reduce = ((i & 7) == 1) || (i == beta - 1);  // :1536, :1547
-        lg_launch_ks_mac(m, nd, batch, st);
-        LG_LAUNCH_CHECK();
+        const int first = (i == 0);
+        const int reduce = ((i & 7) == 1) || (i == beta - 1);  // :1536, :1547
+        if (Q->logN >= 12) {
+            // :1586, :1590 NTT of every Q limb outside the digit and of the P limbs, with the
+            // multiply-accumulate of :1515-1534 fused into the last NTT phase; the digit's own limbs
+            // are the NTT-domain input limbs (:1579-1584), read straight from cx.
+            NttMac mac;
+            mac.enabled = 1;
+            mac.evk0 = evk->key(i, 0);
+            mac.evk1 = evk->key(i, 1);
+            mac.acc0 = acc0;
+            mac.acc1 = acc1;
+            mac.acc_bs = d_bs;
+            mac.cx = cx;
+            mac.cx_bs = cx_bs;
+            mac.first = first;
+            mac.reduce = reduce;
+            LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d.d, d_bs, d.d, d_bs, false, p0idxst, p0idxed, st, &mac));
+        } else {
+            LG_TRY(lgi_ew(EW_COPY, Q, limb_map_identity(), p0idxed - p0idxst, batch, cx + (size_t)p0idxst * N, cx_bs, nullptr,
+                          0, d.d + (size_t)p0idxst * N, d_bs, nullptr, 0, st));
+            LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d.d, d_bs, d.d, d_bs, false, p0idxst, p0idxed, st));
+            KsMacArgs m;
+            m.T = QP->T;
+            m.map = qp_map;
+            m.d = d.d;
+            m.d_bs = d_bs;
+            m.evk0 = evk->key(i, 0);
+            m.evk1 = evk->key(i, 1);
+            m.acc0 = acc0;
+            m.acc1 = acc1;
+            m.acc_bs = d_bs;
+            m.first = first;
+            m.reduce = reduce;
+            lg_launch_ks_mac(m, nd, batch, st);
+            LG_LAUNCH_CHECK();
+        }
     }
     // :1556-1557
-    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc0, d_bs, acc0 + (size_t)nl * N, d_bs, out0, out0_bs, true, st));
-    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc1, d_bs, acc1 + (size_t)nl * N, d_bs, out1, out1_bs, true, st));
+    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc0, d_bs, acc0 + (size_t)nl * N, d_bs, out0, out0_bs, true, st,
+                                add0));
+    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc1, d_bs, acc1 + (size_t)nl * N, d_bs, out1, out1_bs, true, st,
+                                add1));
     return LG_OK;
 }
 
@@ -515,30 +538,31 @@ int lg_ckks_mul_relin(lg_ckks_eval* e, int level, const lg_poly* a0, const lg_po
     const bool square = (a0->d == b0->d && a1->d == b1->d);  // el0 == el1, :1080
     const size_t bs = (size_t)nl * N;
     Scratch w(st);
-    LG_TRY(w.alloc((size_t)7 * batch * bs));
-    u64* c00 = w.d;
-    u64* c01 = c00 + batch * bs;
-    u64* c0 = c01 + batch * bs;
-    u64* c1 = c0 + batch * bs;
-    u64* c2 = c1 + batch * bs;
-    u64* k0 = c2 + batch * bs;
-    u64* k1 = k0 + batch * bs;
-    const LimbMap id = limb_map_identity();
-    // :1076-1077
-    LG_TRY(lgi_ew(EW_MFORM, Q, id, nl, batch, a0->d, a0->bstride, nullptr, 0, c00, bs, nullptr, 0, st));
-    LG_TRY(lgi_ew(EW_MFORM, Q, id, nl, batch, a1->d, a1->bstride, nullptr, 0, c01, bs, nullptr, 0, st));
-    LG_TRY(lgi_ew(EW_MULMONT, Q, id, nl, batch, c00, bs, b0->d, b0->bstride, c0, bs, nullptr, 0, st));
-    LG_TRY(lgi_ew(EW_MULMONT, Q, id, nl, batch, c00, bs, b1->d, b1->bstride, c1, bs, nullptr, 0, st));
-    if (square)  // :1083
-        LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c1, bs, c1, bs, c1, bs, nullptr, 0, st));
-    else  // :1091
-        LG_TRY(lgi_ew(EW_MULMONT_ADD, Q, id, nl, batch, c01, bs, b0->d, b0->bstride, c1, bs, nullptr, 0, st));
-    LG_TRY(lgi_ew(EW_MULMONT, Q, id, nl, batch, c01, bs, b1->d, b1->bstride, c2, bs, nullptr, 0, st));
-    // :1098-1101
-    LG_TRY(ckks_switch_keys(e, level, batch, c2, bs, rlk, k0, bs, k1, bs, st));
-    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c0, bs, k0, bs, out0->d, out0->bstride, nullptr, 0, st));
-    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c1, bs, k1, bs, out1->d, out1->bstride, nullptr, 0, st));
-    return LG_OK;
+    LG_TRY(w.alloc((size_t)batch * bs));
+    u64* c2 = w.d;
+    // :1076-1095 tensor product in one pass; c0, c1 land directly in the outputs (same-index aliasing
+    // with the inputs is safe), c2 in scratch
+    TensorArgs t;
+    t.T = Q->T;
+    t.a0 = a0->d;
+    t.a1 = a1->d;
+    t.b0 = b0->d;
+    t.b1 = b1->d;
+    t.c0 = out0->d;
+    t.c1 = out1->d;
+    t.c2 = c2;
+    t.a_bs[0] = a0->bstride;
+    t.a_bs[1] = a1->bstride;
+    t.b_bs[0] = b0->bstride;
+    t.b_bs[1] = b1->bstride;
+    t.c_bs[0] = out0->bstride;
+    t.c_bs[1] = out1->bstride;
+    t.c_bs[2] = bs;
+    t.square = square ? 1 : 0;
+    lg_launch_tensor(t, nl, batch, st);
+    LG_LAUNCH_CHECK();
+    // :1098-1104 relinearise c2 and add: out0 = CRed(c0 + pool1), out1 = CRed(c1 + pool2)
+    return ckks_switch_keys(e, level, batch, c2, bs, rlk, out0->d, out0->bstride, out1->d, out1->bstride, st, true, true);
 }
 
 int lg_ckks_relinearize(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_poly* c2, const lg_swk* rlk,
@@ -556,15 +580,14 @@ int lg_ckks_relinearize(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
     LG_TRY(check_p(out1, N, nl, batch, "Relinearize"));
     cudaStream_t st = cs(s);
     const size_t bs = (size_t)nl * N;
-    Scratch w(st);
-    LG_TRY(w.alloc((size_t)2 * batch * bs));
-    u64* k0 = w.d;
-    u64* k1 = k0 + batch * bs;
-    LG_TRY(ckks_switch_keys(e, level, batch, c2->d, c2->bstride, rlk, k0, bs, k1, bs, st));
+    (void)bs;
     const LimbMap id = limb_map_identity();
-    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c0->d, c0->bstride, k0, bs, out0->d, out0->bstride, nullptr, 0, st));
-    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c1->d, c1->bstride, k1, bs, out1->d, out1->bstride, nullptr, 0, st));
-    return LG_OK;
+    LG_REQUIRE(c2->d != out0->d && c2->d != out1->d, "Relinearize: value[2] must not alias the receiver");
+    if (c0->d != out0->d) LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, c0->d, c0->bstride, nullptr, 0, out0->d, out0->bstride, nullptr, 0, st));
+    if (c1->d != out1->d) LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, c1->d, c1->bstride, nullptr, 0, out1->d, out1->bstride, nullptr, 0, st));
+    // :1156-1159
+    return ckks_switch_keys(e, level, batch, c2->d, c2->bstride, rlk, out0->d, out0->bstride, out1->d, out1->bstride, st, true,
+                            true);
 }
 
 int lg_ckks_rescale(lg_ckks_eval* e, int nl, lg_poly* c0, lg_poly* c1, int nb, lg_stream_t s) {
@@ -597,11 +620,14 @@ int lg_ckks_switch_keys(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
     LG_TRY(w.alloc((size_t)2 * batch * bs));
     u64* k0 = w.d;
     u64* k1 = k0 + batch * bs;
-    LG_TRY(ckks_switch_keys(e, level, batch, c1->d, c1->bstride, k, k0, bs, k1, bs, st));
+    (void)k0;
+    (void)k1;
     const LimbMap id = limb_map_identity();
-    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, c0->d, c0->bstride, k0, bs, out0->d, out0->bstride, nullptr, 0, st));
-    LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, k1, bs, nullptr, 0, out1->d, out1->bstride, nullptr, 0, st));
-    return LG_OK;
+    LG_REQUIRE(out0->d != c1->d, "SwitchKeys: receiver value[0] must not alias input value[1]");
+    if (c0->d != out0->d) LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, c0->d, c0->bstride, nullptr, 0, out0->d, out0->bstride, nullptr, 0, st));
+    // :1184-1188: value[0] += pool1, value[1] = pool2
+    return ckks_switch_keys(e, level, batch, c1->d, c1->bstride, k, out0->d, out0->bstride, out1->d, out1->bstride, st, true,
+                            false);
 }
 
 int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_galois* g, const lg_swk* k,
@@ -642,11 +668,12 @@ int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
     a.out = el1;
     lg_launch_permute_ntt(a, nl, batch, st);
     LG_LAUNCH_CHECK();
-    LG_TRY(ckks_switch_keys(e, level, batch, el1, bs, k, k0, bs, k1, bs, st));  // :1468
+    (void)k0;
+    (void)k1;
     const LimbMap id = limb_map_identity();
-    LG_TRY(lgi_ew(EW_ADD, Q, id, nl, batch, el0, bs, k0, bs, out0->d, out0->bstride, nullptr, 0, st));  // :1470
-    LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, k1, bs, nullptr, 0, out1->d, out1->bstride, nullptr, 0, st));  // :1471
-    return LG_OK;
+    // :1468-1471: value[0] = el0 + pool1, value[1] = pool2
+    LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, el0, bs, nullptr, 0, out0->d, out0->bstride, nullptr, 0, st));
+    return ckks_switch_keys(e, level, batch, el1, bs, k, out0->d, out0->bstride, out1->d, out1->bstride, st, true, false);
 }
 
 }  // extern "C"

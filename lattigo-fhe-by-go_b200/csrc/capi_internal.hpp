@@ -142,11 +142,11 @@ struct lg_ckks_eval {
 // internal (non-ABI) helpers shared between translation units
 int lgi_ring_build_device(lg_ring* r);
 int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, size_t in_bs, u64* out, size_t out_bs,
-            bool inverse, int skip0, int skip1, cudaStream_t st);
+            bool inverse, int skip0, int skip1, cudaStream_t st, const NttMac* mac = nullptr);
 int lgi_ew(int op, const lg_ring* r, LimbMap map, int nl, int batch, const u64* a, size_t a_bs, const u64* b,
            size_t b_bs, u64* c, size_t c_bs, const u64* scalars, int nscalars, cudaStream_t st);
 int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* p1Q, size_t p1Q_bs, u64* p1P,
-                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st);
+                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st, bool accumulate = false);
 int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u64* p0, size_t p0_bs, u64* outQ,
                   size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st);
 int lgi_div_by_last_modulus(const lg_ring* r, int nl, int batch, u64* p0, size_t bs, bool round, bool ntt,

@@ -44,6 +44,7 @@ LG_DEV u64 ew_apply(u64 a, u64 b, u64 c, const LimbConst& k, u64 s, u64 s2) {
         case EW_MULVEC: return mred(a, b, q, k.qinv);                         // :726-734
         case EW_MULVEC_ADD_NOMOD: return c + mred(a, b, q, k.qinv);           // :737-745
         case EW_SUB_MULMONT_SCALAR: return mred(a + (q - b), s, q, k.qinv);   // ring_basis_extension.go:236-238
+        case EW_SUB_MULMONT_SCALAR_ADD: return cred(c + mred(a + (q - b), s, q, k.qinv), q);  // + ckks/evaluator.go:1103
         case EW_COPY: return a;
     }
     return 0;
@@ -52,12 +53,12 @@ LG_DEV u64 ew_apply(u64 a, u64 b, u64 c, const LimbConst& k, u64 s, u64 s2) {
 __host__ __device__ constexpr bool ew_reads_b(int op) {
     return op == EW_ADD || op == EW_ADD_NOMOD || op == EW_SUB || op == EW_SUB_NOMOD ||
            (op >= EW_MUL_BARRETT && op <= EW_MULMONT_CONSTANT) || op == EW_MULVEC || op == EW_MULVEC_ADD_NOMOD ||
-           op == EW_SUB_MULMONT_SCALAR;
+           op == EW_SUB_MULMONT_SCALAR || op == EW_SUB_MULMONT_SCALAR_ADD;
 }
 __host__ __device__ constexpr bool ew_reads_c(int op) {
     return op == EW_MUL_BARRETT_ADD || op == EW_MUL_BARRETT_ADD_NOMOD || op == EW_MULMONT_ADD ||
            op == EW_MULMONT_ADD_NOMOD || op == EW_MULMONT_CONSTANT_ADD_NOMOD || op == EW_MULMONT_SUB ||
-           op == EW_MULMONT_SUB_NOMOD || op == EW_MULVEC_ADD_NOMOD;
+           op == EW_MULMONT_SUB_NOMOD || op == EW_MULVEC_ADD_NOMOD || op == EW_SUB_MULMONT_SCALAR_ADD;
 }
 
 template <int OP>

@@ -10,6 +10,21 @@ extern std::atomic<uint64_t> lg_g_launches;  // kernels launched by this library
 #define LG_MAX_LIMBS 64
 
 // ---- K1: NTT ----------------------------------------------------------------
+// Optional key-switch epilogue of the forward transform (ckks/evaluator.go:1515-1541): instead of
+// storing the NTT of data limb j, accumulate MRed(evk[.][tl], ntt) into acc0/acc1.  Data limbs in the
+// skip range are not transformed: their NTT-domain values are read from `cx` (evaluator.go:1579-1584).
+struct NttMac {
+    int enabled;
+    const u64* evk0;  // evk[i][0], table limb tl at evk0 + tl*N (shared by the batch)
+    const u64* evk1;
+    u64* acc0;        // limb j of batch b at acc + b*acc_bs + j*N
+    u64* acc1;
+    size_t acc_bs;
+    const u64* cx;
+    size_t cx_bs;
+    int first;        // 1: acc = MRed(..), 0: acc += MRed(..)
+    int reduce;       // 1: BRedAdd the accumulators after adding
+};
 struct NttArgs {
     RingTables T;
     LimbMap map;
@@ -17,6 +32,7 @@ struct NttArgs {
     u64* out;
     size_t in_bstride, out_bstride;  // words between consecutive batch entries
     int skip0, skip1;                // data limbs in [skip0, skip1) are left untouched
+    NttMac mac;
 };
 int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cudaStream_t st);
 
@@ -53,6 +69,7 @@ enum EwOp {
     EW_MULVEC,           // c = MRed(a, vec)   (vec = one limb of N words, shared by all limbs)
     EW_MULVEC_ADD_NOMOD, // c += MRed(a, vec)
     EW_SUB_MULMONT_SCALAR,  // c = MRed(a + (q - b), s_j)   (ModDown / rescale tail)
+    EW_SUB_MULMONT_SCALAR_ADD,  // c = CRed(c + MRed(a + (q - b), s_j))  (ModDown tail fused with the AddLvl that follows)
     EW_COPY,
     EW_NUM_OPS
 };
@@ -152,3 +169,13 @@ struct KsMacArgs {
     int reduce;         // 1: acc = BRedAdd(acc + MRed(..))
 };
 int lg_launch_ks_mac(const KsMacArgs& a, int nlimbs, int batch, cudaStream_t st);
+
+// fused tensor product of MulRelin (ckks/evaluator.go:1076-1095); limb j = table limb j
+struct TensorArgs {
+    RingTables T;
+    const u64 *a0, *a1, *b0, *b1;
+    u64 *c0, *c1, *c2;
+    size_t a_bs[2], b_bs[2], c_bs[3];
+    int square;
+};
+int lg_launch_tensor(const TensorArgs& a, int nlimbs, int batch, cudaStream_t st);

@@ -45,7 +45,54 @@ __global__ void __launch_bounds__(256) ks_mac_kernel(const KsMacArgs a) {
     }
 }
 
+// Degree-1 x degree-1 tensor product of MulRelin (ckks/evaluator.go:1076-1095) in one pass:
+//   c00 = MForm(a0), c01 = MForm(a1)
+//   c0 = MRed(c00, b0); c1 = CRed(MRed(c00, b1) + MRed(c01, b0)); c2 = MRed(c01, b1)
+// (squaring branch :1080-1085: c1 = CRed(2 * MRed(c00, b1))).  4 reads + 3 writes per coefficient
+// instead of the reference's six passes.  Outputs may alias inputs (same-index access only).
+__global__ void __launch_bounds__(256) tensor_kernel(const TensorArgs a) {
+    const int j = blockIdx.y, bt = blockIdx.z;
+    const LimbConst k = load_limb_const(a.T, j);
+    const u32 N = a.T.N;
+    const size_t off = (size_t)j * N;
+    const ulonglong2* a0 = reinterpret_cast<const ulonglong2*>(a.a0 + bt * a.a_bs[0] + off);
+    const ulonglong2* a1 = reinterpret_cast<const ulonglong2*>(a.a1 + bt * a.a_bs[1] + off);
+    const ulonglong2* b0 = reinterpret_cast<const ulonglong2*>(a.b0 + bt * a.b_bs[0] + off);
+    const ulonglong2* b1 = reinterpret_cast<const ulonglong2*>(a.b1 + bt * a.b_bs[1] + off);
+    ulonglong2* c0 = reinterpret_cast<ulonglong2*>(a.c0 + bt * a.c_bs[0] + off);
+    ulonglong2* c1 = reinterpret_cast<ulonglong2*>(a.c1 + bt * a.c_bs[1] + off);
+    ulonglong2* c2 = reinterpret_cast<ulonglong2*>(a.c2 + bt * a.c_bs[2] + off);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < (N >> 1); i += gridDim.x * blockDim.x) {
+        const ulonglong2 x0 = a0[i], x1 = a1[i], y0 = b0[i], y1 = b1[i];
+        ulonglong2 r0, r1, r2;
+#define LG_TENSOR(f)                                                                \
+    {                                                                               \
+        const u64 m0 = mform(x0.f, k.q, k.u0, k.u1), m1 = mform(x1.f, k.q, k.u0, k.u1); \
+        r0.f = mred(m0, y0.f, k.q, k.qinv);                                         \
+        const u64 t = mred(m0, y1.f, k.q, k.qinv);                                  \
+        r1.f = a.square ? cred(t + t, k.q) : cred(t + mred(m1, y0.f, k.q, k.qinv), k.q); \
+        r2.f = mred(m1, y1.f, k.q, k.qinv);                                         \
+    }
+        LG_TENSOR(x)
+        LG_TENSOR(y)
+#undef LG_TENSOR
+        c0[i] = r0;
+        c1[i] = r1;
+        c2[i] = r2;
+    }
+}
+
 }  // namespace
+
+int lg_launch_tensor(const TensorArgs& a, int nlimbs, int batch, cudaStream_t st) {
+    if (nlimbs <= 0 || batch <= 0) return 0;
+    u32 bx = ((a.T.N >> 1) + 255) / 256;
+    if (bx > 64) bx = 64;
+    if (bx == 0) bx = 1;
+    tensor_kernel<<<dim3(bx, nlimbs, batch), 256, 0, st>>>(a);
+    lg_g_launches += 1;
+    return 0;
+}
 
 int lg_launch_ks_mac(const KsMacArgs& a, int nlimbs, int batch, cudaStream_t st) {
     if (nlimbs <= 0 || batch <= 0) return 0;

@@ -142,32 +142,62 @@ __global__ void __launch_bounds__(256) ntt_fwd_strided(const NttArgs a) {
 }
 
 // ---- forward, contiguous phase: last 8 stages + BRedAdd ---------------------
+// MAC = true fuses the key-switch multiply-accumulate into the epilogue (NttMac).
+template <bool MAC>
 __global__ void __launch_bounds__(256) ntt_fwd_contig(const NttArgs a) {
     __shared__ u64 sm[4096 + 256];
     const LimbSetup s = setup_limb<true>(a);
-    if (s.skip) return;
+    if (!MAC && s.skip) return;
     const u32 N = a.T.N;
     const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
     const u32 t = threadIdx.x, seg = t >> 4, c = t & 15;
     const u32 base = blockIdx.x * 4096u;
-    const u32 j0 = base + seg * 256u + c;
-    u64 x[16];
+    if (!(MAC && s.skip)) {
+        const u32 j0 = base + seg * 256u + c;
+        u64 x[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = s.in[j0 + 16 * r];
-    fwd_stages<3, 0, false>(x, s.tw, (N + j0) >> 4, q, qinv, twoq);
+        for (int r = 0; r < 16; ++r) x[r] = s.in[j0 + 16 * r];
+        fwd_stages<3, 0, false>(x, s.tw, (N + j0) >> 4, q, qinv, twoq);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + c + 16 * r)] = x[r];
-    __syncthreads();
+        for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + c + 16 * r)] = x[r];
+        __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + 16 * c + r)];
-    const u32 j1 = base + seg * 256u + 16 * c;
-    fwd_stages<3, 0, true>(x, s.tw, N + j1, q, qinv, twoq);
-    // ring/ntt.go:83-85
+        for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + 16 * c + r)];
+        const u32 j1 = base + seg * 256u + 16 * c;
+        fwd_stages<3, 0, true>(x, s.tw, N + j1, q, qinv, twoq);
+        // ring/ntt.go:83-85
 #pragma unroll
-    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + 16 * c + r)] = bred_add(x[r], q, s.c.u0);
-    __syncthreads();
+        for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + 16 * c + r)] = bred_add(x[r], q, s.c.u0);
+        __syncthreads();
+    }
+    if (!MAC) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s.out[base + t + 256u * k] = sm[pad16(t + 256u * k)];
+        for (int k = 0; k < 16; ++k) s.out[base + t + 256u * k] = sm[pad16(t + 256u * k)];
+    } else {
+        const int j = blockIdx.y, b = blockIdx.z, tl = a.map(j);
+        const u64* e0 = a.mac.evk0 + (size_t)tl * N + base;
+        const u64* e1 = a.mac.evk1 + (size_t)tl * N + base;
+        u64* p0 = a.mac.acc0 + (size_t)b * a.mac.acc_bs + (size_t)j * N + base;
+        u64* p1 = a.mac.acc1 + (size_t)b * a.mac.acc_bs + (size_t)j * N + base;
+        const u64* cx = a.mac.cx + (size_t)b * a.mac.cx_bs + (size_t)j * N + base;
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const u32 e = t + 256u * k;
+            const u64 d = s.skip ? cx[e] : sm[pad16(e)];
+            u64 r0 = mred(__ldg(e0 + e), d, q, qinv);
+            u64 r1 = mred(__ldg(e1 + e), d, q, qinv);
+            if (!a.mac.first) {
+                r0 += p0[e];
+                r1 += p1[e];
+            }
+            if (a.mac.reduce) {
+                r0 = bred_add(r0, q, s.c.u0);
+                r1 = bred_add(r1, q, s.c.u0);
+            }
+            p0[e] = r0;
+            p1[e] = r1;
+        }
+    }
 }
 
 // ---- inverse, contiguous phase: first 8 stages -------------------------------
@@ -286,6 +316,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     if (nlimbs <= 0 || batch <= 0) return 0;
     const u32 logN = args.T.logN, N = args.T.N;
     if (logN < 1 || logN > 16) return 1;
+    if (args.mac.enabled && (logN <= 11 || inverse)) return 1;
     if (logN <= 11) {
         const u32 threads = (N >> 1) < 32 ? 32 : ((N >> 1) > 512 ? 512 : (N >> 1));
         dim3 grid(1, nlimbs, batch);
@@ -311,8 +342,19 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
         }
     };
     if (!inverse) {
-        strided(args);
-        ntt_fwd_contig<<<grid, 256, 0, st>>>(second);
+        // with the MAC epilogue the strided phase runs in place on the input (the decomposed digit)
+        NttArgs first = args;
+        if (args.mac.enabled) {
+            first.out = const_cast<u64*>(args.in);
+            first.out_bstride = args.in_bstride;
+            second.in = args.in;
+            second.in_bstride = args.in_bstride;
+        }
+        strided(first);
+        if (args.mac.enabled)
+            ntt_fwd_contig<true><<<grid, 256, 0, st>>>(second);
+        else
+            ntt_fwd_contig<false><<<grid, 256, 0, st>>>(second);
     } else {
         ntt_inv_contig<<<grid, 256, 0, st>>>(args);
         strided(second);
