@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="ops in the cpu_baseline sample (0 = one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the batch is cut into for the pipelined e2e path")
     ap.add_argument("--params", type=int, default=PARAMS_ID, help="index into ckks.DefaultParams (default PN16QP1761)")
     return ap.parse_args()
 
@@ -315,12 +316,35 @@ def run_gpu(args):
         def hp(t):
             return ctypes.cast(t.data_ptr(), u64p)
 
+        # The batch is cut into chunks that flow through `nstreams` streams: chunk c uploads both operands
+        # (pinned -> device, stream-ordered), runs MulRelin + Rescale, and downloads the result, so the
+        # copies of one chunk overlap the kernels of another.  All calls go through the C ABI.
+        nchunks = max(1, min(args.e2e_chunks, B))
+        while B % nchunks:
+            nchunks -= 1
+        cb = B // nchunks
+        nstreams = min(3, nchunks)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+        slots = []
+        for _ in range(nstreams):
+            ta = [torch.empty(cb, nQ, N, dtype=torch.int64, device=dev) for _ in range(4)]
+            to = [torch.empty(cb, nQ, N, dtype=torch.int64, device=dev) for _ in range(2)]
+            slots.append((tuple(wrap(t, nQ, cb) for t in ta[:2]), tuple(wrap(t, nQ, cb) for t in ta[2:]),
+                          tuple(wrap(t, nQ, cb) for t in to)))
+
         def e2e_step():
-            for poly, h in zip(ct_a + ct_b, h_a + h_b):
-                lattigpu._lib.check(L.lg_poly_upload(poly.h, 0, B, 0, nQ, hp(h), ctypes.c_void_p(sp)))
-            step()
-            for poly, h in zip(ct_o, h_o):
-                lattigpu._lib.check(L.lg_poly_download(poly.h, 0, B, 0, nQ - 1, hp(h), ctypes.c_void_p(sp)))
+            for c in range(nchunks):
+                s_ = streams[c % nstreams]
+                sa, sb, so = slots[c % nstreams]
+                p_ = ctypes.c_void_p(s_.cuda_stream)
+                for poly, h in zip(sa + sb, h_a + h_b):
+                    lattigpu._lib.check(L.lg_poly_upload_async(poly.h, 0, cb, 0, nQ, hp(h[c * cb:]), p_))
+                ev.MulRelin(level, sa, sb, rlk, so, stream=s_.cuda_stream)
+                ev.Rescale(nQ, so, 1, stream=s_.cuda_stream)
+                for poly, h in zip(so, h_o):
+                    lattigpu._lib.check(L.lg_poly_download_async(poly.h, 0, cb, 0, nQ - 1, hp(h[c * cb:]), p_))
+            for s_ in streams:
+                s_.synchronize()
 
         e2e_steps = max(3, min(args.steps, 5))
         for _ in range(2):
@@ -337,7 +361,8 @@ def run_gpu(args):
             dt = float(t.item())
         e2e = {"value": world * B * e2e_steps / dt, "unit": "ops/s", "h2d_bytes_per_step": 4 * B * nQ * N * 8,
                "d2h_bytes_per_step": 2 * B * (nQ - 1) * N * 8, "ms_per_step": 1e3 * dt / e2e_steps,
-               "note": "pinned host buffers; lg_poly_upload x4, MulRelin, Rescale, lg_poly_download x2 per step"}
+               "note": "pinned host buffers; per chunk of %d ciphertexts: lg_poly_upload_async x4, MulRelin, Rescale, "
+                       "lg_poly_download_async x2; %d chunks over %d streams, host sync per step" % (cb, nchunks, nstreams)}
 
     # ---- cpu baseline (rank 0, N=1 only) -----------------------------------------
     cpu = None

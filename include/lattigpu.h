@@ -98,6 +98,10 @@ size_t lg_poly_batch_stride(const lg_poly* p); /* in words */
 /* host <-> device; host layout [nbatch][nl][N]; synchronous with respect to the host buffer */
 int lg_poly_upload(lg_poly* p, int batch0, int nbatch, int limb0, int nl, const uint64_t* host, lg_stream_t stream);
 int lg_poly_download(const lg_poly* p, int batch0, int nbatch, int limb0, int nl, uint64_t* host, lg_stream_t stream);
+/* stream-ordered variants for C-allocated pinned staging buffers: the host buffer must stay valid (and
+ * for uploads unchanged) until the stream reaches the copy -- not for Go-managed memory */
+int lg_poly_upload_async(lg_poly* p, int batch0, int nbatch, int limb0, int nl, const uint64_t* host, lg_stream_t stream);
+int lg_poly_download_async(const lg_poly* p, int batch0, int nbatch, int limb0, int nl, uint64_t* host, lg_stream_t stream);
 int lg_poly_zero(lg_poly* p, lg_stream_t stream);                                /* Poly.Zero, ring_object.go:60-67 */
 int lg_poly_copy(const lg_poly* src, int nl, lg_poly* dst, lg_stream_t stream);  /* Copy/CopyLvl, ring_object.go:85-121 */
 

@@ -277,7 +277,8 @@ int lg_poly_batch(const lg_poly* p) { return p ? p->batch : 0; }
 void* lg_poly_device_ptr(const lg_poly* p) { return p ? p->d : nullptr; }
 size_t lg_poly_batch_stride(const lg_poly* p) { return p ? p->bstride : 0; }
 
-static int poly_xfer(const lg_poly* p, int batch0, int nbatch, int limb0, int nl, u64* host, bool up, cudaStream_t st) {
+static int poly_xfer(const lg_poly* p, int batch0, int nbatch, int limb0, int nl, u64* host, bool up, cudaStream_t st,
+                     bool sync = true) {
     LG_REQUIRE(p && host, "null argument");
     LG_REQUIRE(batch0 >= 0 && nbatch >= 1 && batch0 + nbatch <= p->batch, "batch range out of bounds");
     LG_REQUIRE(limb0 >= 0 && nl >= 1 && limb0 + nl <= p->nlimbs, "limb range out of bounds");
@@ -287,7 +288,7 @@ static int poly_xfer(const lg_poly* p, int batch0, int nbatch, int limb0, int nl
         LG_CUDA_CHECK(cudaMemcpy2DAsync(dev, p->bstride * sizeof(u64), host, row, row, nbatch, cudaMemcpyHostToDevice, st));
     else
         LG_CUDA_CHECK(cudaMemcpy2DAsync(host, row, dev, p->bstride * sizeof(u64), row, nbatch, cudaMemcpyDeviceToHost, st));
-    LG_CUDA_CHECK(cudaStreamSynchronize(st));  // cgo: the Go buffer may move after return
+    if (sync) LG_CUDA_CHECK(cudaStreamSynchronize(st));  // cgo: the Go buffer may move after return
     return LG_OK;
 }
 int lg_poly_upload(lg_poly* p, int batch0, int nbatch, int limb0, int nl, const uint64_t* host, lg_stream_t s) {
@@ -295,6 +296,12 @@ int lg_poly_upload(lg_poly* p, int batch0, int nbatch, int limb0, int nl, const 
 }
 int lg_poly_download(const lg_poly* p, int batch0, int nbatch, int limb0, int nl, uint64_t* host, lg_stream_t s) {
     return poly_xfer(p, batch0, nbatch, limb0, nl, host, false, cs(s));
+}
+int lg_poly_upload_async(lg_poly* p, int batch0, int nbatch, int limb0, int nl, const uint64_t* host, lg_stream_t s) {
+    return poly_xfer(p, batch0, nbatch, limb0, nl, const_cast<u64*>(host), true, cs(s), false);
+}
+int lg_poly_download_async(const lg_poly* p, int batch0, int nbatch, int limb0, int nl, uint64_t* host, lg_stream_t s) {
+    return poly_xfer(p, batch0, nbatch, limb0, nl, host, false, cs(s), false);
 }
 int lg_poly_zero(lg_poly* p, lg_stream_t s) {
     LG_REQUIRE(p, "null argument");

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "liblattigpu.so")
+LIB_PATH = os.environ.get("LATTIGPU_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "liblattigpu.so")
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "lattigpu.h")
 
 u64 = C.c_uint64
@@ -73,6 +73,8 @@ SIGNATURES = {
     "lg_poly_batch_stride": (C.c_size_t, [_P]),
     "lg_poly_upload": (ci, [_P, ci, ci, ci, ci, p64, vp]),
     "lg_poly_download": (ci, [_P, ci, ci, ci, ci, p64, vp]),
+    "lg_poly_upload_async": (ci, [_P, ci, ci, ci, ci, p64, vp]),
+    "lg_poly_download_async": (ci, [_P, ci, ci, ci, ci, p64, vp]),
     "lg_poly_zero": (ci, [_P, vp]),
     "lg_poly_copy": (ci, [_P, ci, _P, vp]),
     "lg_ring_ntt": (ci, _OP2),
