@@ -218,6 +218,26 @@ int lg_ckks_switch_keys(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
 int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_galois* g, const lg_swk* k,
                         lg_poly* out0, lg_poly* out1, lg_stream_t s);
 
+/* ---- evaluator key-switch path, bfv/evaluator.go ----------------------------- */
+/* NewEvaluator :62-104 (ring part): contexts Q, QMul, P; baseconverterQ1Q2, baseconverterQ1P, decomposer, pHalf */
+int lg_bfv_eval_create(const lg_ring* ringQ, const lg_ring* ringQMul, const lg_ring* ringP, uint64_t t, lg_bfv_eval** out);
+int lg_bfv_eval_destroy(lg_bfv_eval* e);
+/* Mul = tensorAndRescale :278-464 for two degree-1 ciphertexts (coefficient domain) -> degree 2.
+ * Passing the same handles for (a0,a1) and (b0,b1) selects the squaring branch (:334-349). */
+int lg_bfv_mul(lg_bfv_eval* e, const lg_poly* a0, const lg_poly* a1, const lg_poly* b0, const lg_poly* b1,
+               lg_poly* out0, lg_poly* out1, lg_poly* out2, lg_stream_t s);
+/* switchKeys :736-813: p0, p1 receive the #Q-limb results */
+int lg_bfv_switch_keys_core(lg_bfv_eval* e, const lg_poly* cx, const lg_swk* evk, lg_poly* p0, lg_poly* p1, lg_stream_t s);
+/* relinearize :480-500 of a degree-2 ciphertext with evakey[0] */
+int lg_bfv_relinearize(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, const lg_poly* c2, const lg_swk* rlk,
+                       lg_poly* out0, lg_poly* out1, lg_stream_t s);
+/* SwitchKeys :540-558 */
+int lg_bfv_switch_keys(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, const lg_swk* k, lg_poly* out0, lg_poly* out1,
+                       lg_stream_t s);
+/* permute :711-733 = RotateColumns with a direct key (:595, gen = galElRotColLeft[k]) / RotateRows (:669, gen = 2N-1) */
+int lg_bfv_permute(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, uint64_t gen, const lg_swk* k, lg_poly* out0,
+                   lg_poly* out1, lg_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

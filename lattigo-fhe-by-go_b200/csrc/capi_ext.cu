@@ -72,7 +72,7 @@ int ModUpDev::build(const u64* Q, int nq, const u64* P, int np) {
 }
 
 // modUpExact (:352-393) on `nsrc` source limbs into `ndst` target limbs tgt0..
-static int modup_launch(const ModUpDev& m, u64 N, int batch, const u64* in, size_t in_bs, int nsrc, u64* out,
+int lgi_modup_launch(const ModUpDev& m, u64 N, int batch, const u64* in, size_t in_bs, int nsrc, u64* out,
                         size_t out_bs, int ndst, int tgt0, cudaStream_t st) {
     LG_REQUIRE(nsrc >= 1 && nsrc <= m.nsrc && ndst >= 0 && tgt0 + ndst <= m.ndst, "modUpExact: basis out of range");
     ModUpArgs a;
@@ -131,7 +131,7 @@ int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* 
     Scratch tmp(st);
     LG_TRY(tmp.alloc((size_t)batch * nl * N));
     const size_t tbs = (size_t)nl * N;
-    LG_TRY(modup_launch(e->pq, N, batch, p1P, p1P_bs, P->nl, tmp.d, tbs, nl, 0, st));
+    LG_TRY(lgi_modup_launch(e->pq, N, batch, p1P, p1P_bs, P->nl, tmp.d, tbs, nl, 0, st));
     if (ntt) LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
     return lgi_ew(accumulate ? EW_SUB_MULMONT_SCALAR_ADD : EW_SUB_MULMONT_SCALAR, Q, limb_map_identity(), nl, batch, p1Q,
                   p1Q_bs, tmp.d, tbs, p2, p2_bs, e->moddown_pq.data(), nl, st);
@@ -161,13 +161,13 @@ int lg_extender_modup_split_qp(const lg_extender* e, int level, const lg_poly* p
     LG_REQUIRE(e, "ModUpSplitQP: null extender");
     LG_TRY(check_p(p1, e->Q->N, level + 1, -1, "ModUpSplitQP"));
     LG_TRY(check_p(p2, e->Q->N, e->P->nl, p1->batch, "ModUpSplitQP"));
-    return modup_launch(e->qp, e->Q->N, p1->batch, p1->d, p1->bstride, level + 1, p2->d, p2->bstride, e->P->nl, 0, cs(s));
+    return lgi_modup_launch(e->qp, e->Q->N, p1->batch, p1->d, p1->bstride, level + 1, p2->d, p2->bstride, e->P->nl, 0, cs(s));
 }
 int lg_extender_modup_split_pq(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s) {
     LG_REQUIRE(e, "ModUpSplitPQ: null extender");
     LG_TRY(check_p(p1, e->Q->N, level + 1, -1, "ModUpSplitPQ"));
     LG_TRY(check_p(p2, e->Q->N, e->Q->nl, p1->batch, "ModUpSplitPQ"));
-    return modup_launch(e->pq, e->Q->N, p1->batch, p1->d, p1->bstride, level + 1, p2->d, p2->bstride, e->Q->nl, 0, cs(s));
+    return lgi_modup_launch(e->pq, e->Q->N, p1->batch, p1->d, p1->bstride, level + 1, p2->d, p2->bstride, e->Q->nl, 0, cs(s));
 }
 int lg_extender_moddown_ntt_pq(const lg_extender* e, int level, lg_poly* p1, lg_poly* p2, lg_stream_t s) {
     LG_REQUIRE(e, "ModDownNTTPQ: null extender");
@@ -218,7 +218,7 @@ int lg_extender_moddown_splited_qp(const lg_extender* e, int levelQ, int levelP,
     Scratch tmp(cs(s));
     LG_TRY(tmp.alloc((size_t)batch * P->nl * N));
     const size_t tbs = (size_t)P->nl * N;
-    LG_TRY(modup_launch(e->qp, N, batch, p1Q->d, p1Q->bstride, levelQ + 1, tmp.d, tbs, P->nl, 0, cs(s)));
+    LG_TRY(lgi_modup_launch(e->qp, N, batch, p1Q->d, p1Q->bstride, levelQ + 1, tmp.d, tbs, P->nl, 0, cs(s)));
     return lgi_ew(EW_SUB_MULMONT_SCALAR, P, limb_map_identity(), levelP + 1, batch, p1P->d, p1P->bstride, tmp.d, tbs, p2->d,
                   p2->bstride, e->moddown_qp.data(), levelP + 1, cs(s));
 }
@@ -352,6 +352,63 @@ int lg_decomposer_decompose_and_split(const lg_decomposer* d, int level, int crt
 // CKKS evaluator hot ops
 // ---------------------------------------------------------------------------
 
+// Digit loop shared by the CKKS and BFV key switches (ckks/evaluator.go:1511-1552,
+// bfv/evaluator.go:760-806).  For each digit i < beta: Decompose(AndSplit) the coefficient-domain
+// input `coef` into d = [level+1 Q limbs | nP special-prime limbs]; NTT every limb outside the digit
+// (the digit's own limbs are taken from the NTT-domain copy `nttd`); acc0/acc1 += MRed(evk[i][0/1], d)
+// with BRedAdd when (i & 7) == cadence and after the last digit.
+int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, const lg_decomposer* dec, int level, int beta,
+                         int batch, const u64* coef, size_t coef_bs, const u64* nttd, size_t nttd_bs, const lg_swk* evk,
+                         u64* d, u64* acc0, u64* acc1, size_t d_bs, int cadence, cudaStream_t st) {
+    const u64 N = Q->N;
+    const int nl = level + 1, nd = nl + dec->nP, alpha = dec->alpha;
+    for (int i = 0; i < beta; ++i) {
+        // decomposeAndSplitNTT :1561-1591 / Decompose bfv:767
+        LG_TRY(lgi_decompose(dec, level, i, batch, coef, coef_bs, d, d_bs, d + (size_t)nl * N, d_bs, st));
+        const int p0idxst = i * alpha;
+        int p0idxed = p0idxst + dec->xalpha[i];
+        if (p0idxed > nl) p0idxed = nl;
+        const int first = (i == 0);
+        const int reduce = ((i & 7) == cadence) || (i == beta - 1);  // ckks :1536,:1547 / bfv :795,:803
+        if (Q->logN >= 12) {
+            // NTT of every limb outside the digit with the multiply-accumulate fused into the last
+            // NTT phase; the digit's own limbs are read straight from the NTT-domain input
+            // (ckks :1579-1584, bfv :776-780).
+            NttMac mac;
+            mac.enabled = 1;
+            mac.evk0 = evk->key(i, 0);
+            mac.evk1 = evk->key(i, 1);
+            mac.acc0 = acc0;
+            mac.acc1 = acc1;
+            mac.acc_bs = d_bs;
+            mac.cx = nttd;
+            mac.cx_bs = nttd_bs;
+            mac.first = first;
+            mac.reduce = reduce;
+            LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d, d_bs, d, d_bs, false, p0idxst, p0idxed, st, &mac));
+        } else {
+            LG_TRY(lgi_ew(EW_COPY, Q, limb_map_identity(), p0idxed - p0idxst, batch, nttd + (size_t)p0idxst * N, nttd_bs,
+                          nullptr, 0, d + (size_t)p0idxst * N, d_bs, nullptr, 0, st));
+            LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d, d_bs, d, d_bs, false, p0idxst, p0idxed, st));
+            KsMacArgs m;
+            m.T = QP->T;
+            m.map = qp_map;
+            m.d = d;
+            m.d_bs = d_bs;
+            m.evk0 = evk->key(i, 0);
+            m.evk1 = evk->key(i, 1);
+            m.acc0 = acc0;
+            m.acc1 = acc1;
+            m.acc_bs = d_bs;
+            m.first = first;
+            m.reduce = reduce;
+            lg_launch_ks_mac(m, nd, batch, st);
+            LG_LAUNCH_CHECK();
+        }
+    }
+    return LG_OK;
+}
+
 // switchKeysInPlace, ckks/evaluator.go:1475-1558, on raw device buffers.
 // cx: [batch][>=level+1][N] NTT domain.  out0/out1: level+1 limbs each; with add0/add1 the result is
 // added (CRed) into what out0/out1 already hold -- the AddLvl every caller applies next (:1103-1104,
@@ -381,50 +438,9 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
 
     // :1503  c2 = InvNTT(cx)
     LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, cx, cx_bs, c2.d, c2_bs, true, 0, 0, st));
-    for (int i = 0; i < beta; ++i) {
-        // decomposeAndSplitNTT :1561-1591
-        LG_TRY(lgi_decompose(e->dec.get(), level, i, batch, c2.d, c2_bs, d.d, d_bs, d.d + (size_t)nl * N, d_bs, st));
-        const int p0idxst = i * alpha;
-        int p0idxed = p0idxst + e->dec->xalpha[i];
-        if (p0idxed > nl) p0idxed = nl;
-        const int first = (i == 0);
-        const int reduce = ((i & 7) == 1) || (i == beta - 1);  // :1536, :1547
-        if (Q->logN >= 12) {
-            // :1586, :1590 NTT of every Q limb outside the digit and of the P limbs, with the
-            // multiply-accumulate of :1515-1534 fused into the last NTT phase; the digit's own limbs
-            // are the NTT-domain input limbs (:1579-1584), read straight from cx.
-            NttMac mac;
-            mac.enabled = 1;
-            mac.evk0 = evk->key(i, 0);
-            mac.evk1 = evk->key(i, 1);
-            mac.acc0 = acc0;
-            mac.acc1 = acc1;
-            mac.acc_bs = d_bs;
-            mac.cx = cx;
-            mac.cx_bs = cx_bs;
-            mac.first = first;
-            mac.reduce = reduce;
-            LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d.d, d_bs, d.d, d_bs, false, p0idxst, p0idxed, st, &mac));
-        } else {
-            LG_TRY(lgi_ew(EW_COPY, Q, limb_map_identity(), p0idxed - p0idxst, batch, cx + (size_t)p0idxst * N, cx_bs, nullptr,
-                          0, d.d + (size_t)p0idxst * N, d_bs, nullptr, 0, st));
-            LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d.d, d_bs, d.d, d_bs, false, p0idxst, p0idxed, st));
-            KsMacArgs m;
-            m.T = QP->T;
-            m.map = qp_map;
-            m.d = d.d;
-            m.d_bs = d_bs;
-            m.evk0 = evk->key(i, 0);
-            m.evk1 = evk->key(i, 1);
-            m.acc0 = acc0;
-            m.acc1 = acc1;
-            m.acc_bs = d_bs;
-            m.first = first;
-            m.reduce = reduce;
-            lg_launch_ks_mac(m, nd, batch, st);
-            LG_LAUNCH_CHECK();
-        }
-    }
+    // :1511-1552 digit loop (decomposeAndSplitNTT + multiply-accumulate), reduce cadence reduce&7 == 1
+    LG_TRY(lgi_keyswitch_digits(QP, Q, qp_map, e->dec.get(), level, beta, batch, c2.d, c2_bs, cx, cx_bs, evk, d.d, acc0,
+                                acc1, d_bs, 1, st));
     // :1556-1557
     LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc0, d_bs, acc0 + (size_t)nl * N, d_bs, out0, out0_bs, true, st,
                                 add0));
@@ -433,7 +449,7 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
     return LG_OK;
 }
 
-static int concat_ring(const lg_ring* Q, const lg_ring* P, std::unique_ptr<lg_ring>& out) {
+int lgi_concat_ring(const lg_ring* Q, const lg_ring* P, std::unique_ptr<lg_ring>& out) {
     std::unique_ptr<lg_ring> r(new lg_ring);
     r->N = Q->N;
     r->logN = Q->logN;
@@ -464,7 +480,7 @@ int lg_ckks_eval_create(const lg_ring* ringQ, const lg_ring* ringP, lg_ckks_eval
     e->Q = ringQ;
     e->P = ringP;
     e->alpha = ringP->nl;
-    LG_TRY(concat_ring(ringQ, ringP, e->QP));
+    LG_TRY(lgi_concat_ring(ringQ, ringP, e->QP));
     lg_extender* ext = nullptr;
     LG_TRY(lg_extender_create(ringQ, ringP, &ext));
     e->ext.reset(ext);
@@ -559,6 +575,7 @@ int lg_ckks_mul_relin(lg_ckks_eval* e, int level, const lg_poly* a0, const lg_po
     t.c_bs[1] = out1->bstride;
     t.c_bs[2] = bs;
     t.square = square ? 1 : 0;
+    t.nomod = 0;
     lg_launch_tensor(t, nl, batch, st);
     LG_LAUNCH_CHECK();
     // :1098-1104 relinearise c2 and add: out0 = CRed(c0 + pool1), out1 = CRed(c1 + pool2)

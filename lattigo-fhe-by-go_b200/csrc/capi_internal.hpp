@@ -149,5 +149,11 @@ int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* 
                          size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st, bool accumulate = false);
 int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u64* p0, size_t p0_bs, u64* outQ,
                   size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st);
+int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, const lg_decomposer* dec, int level, int beta,
+                         int batch, const u64* coef, size_t coef_bs, const u64* nttd, size_t nttd_bs, const lg_swk* evk,
+                         u64* d, u64* acc0, u64* acc1, size_t d_bs, int cadence, cudaStream_t st);
+int lgi_concat_ring(const lg_ring* Q, const lg_ring* P, std::unique_ptr<lg_ring>& out);
+int lgi_modup_launch(const ModUpDev& m, u64 N, int batch, const u64* in, size_t in_bs, int nsrc, u64* out, size_t out_bs,
+                     int ndst, int tgt0, cudaStream_t st);
 int lgi_div_by_last_modulus(const lg_ring* r, int nl, int batch, u64* p0, size_t bs, bool round, bool ntt,
                             cudaStream_t st);

@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256) tensor_kernel(const TensorArgs a) {
         const u64 m0 = mform(x0.f, k.q, k.u0, k.u1), m1 = mform(x1.f, k.q, k.u0, k.u1); \
         r0.f = mred(m0, y0.f, k.q, k.qinv);                                         \
         const u64 t = mred(m0, y1.f, k.q, k.qinv);                                  \
-        r1.f = a.square ? cred(t + t, k.q) : cred(t + mred(m1, y0.f, k.q, k.qinv), k.q); \
+        const u64 s1 = a.square ? t + t : t + mred(m1, y0.f, k.q, k.qinv);              \
+        r1.f = a.nomod ? s1 : cred(s1, k.q);                                        \
         r2.f = mred(m1, y1.f, k.q, k.qinv);                                         \
     }
         LG_TENSOR(x)

@@ -153,6 +153,13 @@ SIGNATURES = {
     "lg_ckks_rescale": (ci, [vp, ci, _P, _P, ci, vp]),
     "lg_ckks_switch_keys": (ci, [vp, ci, _P, _P, vp, _P, _P, vp]),
     "lg_ckks_permute_ntt": (ci, [vp, ci, _P, _P, vp, vp, _P, _P, vp]),
+    "lg_bfv_eval_create": (ci, [_R, _R, _R, u64, C.POINTER(vp)]),
+    "lg_bfv_eval_destroy": (ci, [vp]),
+    "lg_bfv_mul": (ci, [vp, _P, _P, _P, _P, _P, _P, _P, vp]),
+    "lg_bfv_switch_keys_core": (ci, [vp, _P, vp, _P, _P, vp]),
+    "lg_bfv_relinearize": (ci, [vp, _P, _P, _P, vp, _P, _P, vp]),
+    "lg_bfv_switch_keys": (ci, [vp, _P, _P, vp, _P, _P, vp]),
+    "lg_bfv_permute": (ci, [vp, _P, _P, u64, vp, _P, _P, vp]),
 }
 
 

@@ -1326,3 +1326,189 @@ API void orc_ckks_switch_keys(orc_ckks_eval *e, int level, const u64 *ct, const 
     orc_add(Q, nl, ct, e->poolQ[1], out);
     memcpy(out + sz, e->poolQ[2], sizeof(u64) * sz);
 }
+
+/* ---------------------------------------------------------------------- */
+/* bfv/evaluator.go hot ops                                               */
+/* ---------------------------------------------------------------------- */
+
+typedef struct {
+    const orc_ctx *Q, *QMul, *P, *QP;
+    orc_extender *q1q2; /* baseconverterQ1Q2 = NewFastBasisExtender(q, qm)  bfv/evaluator.go:95 */
+    orc_extender *q1p;  /* baseconverterQ1P  = NewFastBasisExtender(q, p)   :86 */
+    orc_decomposer *dec;
+    int alpha, beta;
+    u64 t;
+    u64 *phalf_qmul, *phalf_q; /* pHalf = QMul>>1 (:98) reduced mod each prime (host big.Int work) */
+} orc_bfv_eval;
+
+/* NewEvaluator, bfv/evaluator.go:62-104 */
+API orc_bfv_eval *orc_bfv_eval_new(const orc_ctx *Q, const orc_ctx *QMul, const orc_ctx *P, const orc_ctx *QP, u64 t,
+                                   const u64 *phalf_qmul, const u64 *phalf_q) {
+    orc_bfv_eval *e = (orc_bfv_eval *)calloc(1, sizeof(orc_bfv_eval));
+    e->Q = Q; e->QMul = QMul; e->P = P; e->QP = QP;
+    e->q1q2 = orc_extender_new(Q, QMul);
+    e->q1p = orc_extender_new(Q, P);
+    e->dec = orc_decomposer_new(Q->modulus, Q->nl, P->modulus, P->nl);
+    e->alpha = P->nl;
+    e->beta = (Q->nl + P->nl - 1) / P->nl; /* bfv/params.go: beta = ceil(len(Qi)/alpha) */
+    e->t = t;
+    e->phalf_qmul = (u64 *)malloc(sizeof(u64) * QMul->nl);
+    e->phalf_q = (u64 *)malloc(sizeof(u64) * Q->nl);
+    memcpy(e->phalf_qmul, phalf_qmul, sizeof(u64) * QMul->nl);
+    memcpy(e->phalf_q, phalf_q, sizeof(u64) * Q->nl);
+    return e;
+}
+API void orc_bfv_eval_free(orc_bfv_eval *e) {
+    if (!e) return;
+    orc_extender_free(e->q1q2); orc_extender_free(e->q1p); orc_decomposer_free(e->dec);
+    free(e->phalf_qmul); free(e->phalf_q); free(e);
+}
+
+/* tensorAndRescale, bfv/evaluator.go:278-464, degree 1 x degree 1 (:327-367; squaring when ct0 == ct1).
+ * ct0, ct1: [2][nQ][N] coefficient domain.  out: [3][nQ][N]. */
+API void orc_bfv_tensor_and_rescale(orc_bfv_eval *e, const u64 *ct0, const u64 *ct1, u64 *out) {
+    const orc_ctx *Q = e->Q, *M = e->QMul;
+    u64 N = Q->N;
+    int nQ = Q->nl, nM = M->nl;
+    int levelQ = nQ - 1, levelM = nM - 1;
+    u64 szQ = (u64)nQ * N, szM = (u64)nM * N;
+    u64 *c0Q1 = (u64 *)malloc(sizeof(u64) * szQ * 2), *c0Q2 = (u64 *)malloc(sizeof(u64) * szM * 2);
+    u64 *c1Q1 = (u64 *)malloc(sizeof(u64) * szQ * 2), *c1Q2 = (u64 *)malloc(sizeof(u64) * szM * 2);
+    u64 *c2Q1 = (u64 *)calloc(szQ * 3, sizeof(u64)), *c2Q2 = (u64 *)calloc(szM * 3, sizeof(u64));
+    u64 *c00Q = (u64 *)malloc(sizeof(u64) * szQ), *c00Q2 = (u64 *)malloc(sizeof(u64) * szM);
+    u64 *c01Q = (u64 *)malloc(sizeof(u64) * szQ), *c01P = (u64 *)malloc(sizeof(u64) * szM);
+    int square = (ct0 == ct1);
+    for (int i = 0; i < 2; i++) { /* :298-303 */
+        orc_modup_split_qp(e->q1q2, levelQ, ct0 + i * szQ, c0Q2 + i * szM);
+        orc_ntt(Q, nQ, ct0 + i * szQ, c0Q1 + i * szQ);
+        orc_ntt(M, nM, c0Q2 + i * szM, c0Q2 + i * szM);
+    }
+    if (!square) { /* :305-313 */
+        for (int i = 0; i < 2; i++) {
+            orc_modup_split_qp(e->q1q2, levelQ, ct1 + i * szQ, c1Q2 + i * szM);
+            orc_ntt(Q, nQ, ct1 + i * szQ, c1Q1 + i * szQ);
+            orc_ntt(M, nM, c1Q2 + i * szM, c1Q2 + i * szM);
+        }
+    }
+    orc_mform_poly(Q, nQ, c0Q1, c00Q);          /* :327-331 */
+    orc_mform_poly(M, nM, c0Q2, c00Q2);
+    orc_mform_poly(Q, nQ, c0Q1 + szQ, c01Q);
+    orc_mform_poly(M, nM, c0Q2 + szM, c01P);
+    if (square) { /* :334-349 */
+        orc_mulcoeffs_montgomery(Q, nQ, c00Q, c0Q1, c2Q1);
+        orc_mulcoeffs_montgomery(M, nM, c00Q2, c0Q2, c2Q2);
+        orc_mulcoeffs_montgomery(Q, nQ, c00Q, c0Q1 + szQ, c2Q1 + szQ);
+        orc_mulcoeffs_montgomery(M, nM, c00Q2, c0Q2 + szM, c2Q2 + szM);
+        orc_add_nomod(Q, nQ, c2Q1 + szQ, c2Q1 + szQ, c2Q1 + szQ);
+        orc_add_nomod(M, nM, c2Q2 + szM, c2Q2 + szM, c2Q2 + szM);
+        orc_mulcoeffs_montgomery(Q, nQ, c01Q, c0Q1 + szQ, c2Q1 + 2 * szQ);
+        orc_mulcoeffs_montgomery(M, nM, c01P, c0Q2 + szM, c2Q2 + 2 * szM);
+    } else { /* :352-367 */
+        orc_mulcoeffs_montgomery(Q, nQ, c00Q, c1Q1, c2Q1);
+        orc_mulcoeffs_montgomery(M, nM, c00Q2, c1Q2, c2Q2);
+        orc_mulcoeffs_montgomery(Q, nQ, c00Q, c1Q1 + szQ, c2Q1 + szQ);
+        orc_mulcoeffs_montgomery(M, nM, c00Q2, c1Q2 + szM, c2Q2 + szM);
+        orc_mulcoeffs_montgomery_and_add_nomod(Q, nQ, c01Q, c1Q1, c2Q1 + szQ);
+        orc_mulcoeffs_montgomery_and_add_nomod(M, nM, c01P, c1Q2, c2Q2 + szM);
+        orc_mulcoeffs_montgomery(Q, nQ, c01Q, c1Q1 + szQ, c2Q1 + 2 * szQ);
+        orc_mulcoeffs_montgomery(M, nM, c01P, c1Q2 + szM, c2Q2 + 2 * szM);
+    }
+    u64 tvec[64];
+    for (int i = 0; i < nQ; i++) tvec[i] = e->t;
+    for (int i = 0; i < 3; i++) { /* :423-463 */
+        orc_invntt(Q, nQ, c2Q1 + i * szQ, c2Q1 + i * szQ);
+        orc_invntt(M, nM, c2Q2 + i * szM, c2Q2 + i * szM);
+        orc_moddown_splited_qp(e->q1q2, levelQ, levelM, c2Q1 + i * szQ, c2Q2 + i * szM, c2Q2 + i * szM);
+        orc_add_scalar(M, nM, c2Q2 + i * szM, e->phalf_qmul);
+        orc_modup_split_pq(e->q1q2, levelM, c2Q2 + i * szM, out + i * szQ);
+        orc_sub_scalar(Q, nQ, out + i * szQ, e->phalf_q);
+        orc_mul_scalar(Q, nQ, out + i * szQ, tvec, out + i * szQ);
+    }
+    free(c0Q1); free(c0Q2); free(c1Q1); free(c1Q2); free(c2Q1); free(c2Q2);
+    free(c00Q); free(c00Q2); free(c01Q); free(c01P);
+}
+
+/* switchKeys, bfv/evaluator.go:736-813.  cx: [nQ][N] coefficient domain.  evk: [beta][2][nQ+nP][N].
+ * p0, p1: [nQ+nP][N] work polys; the results are their first nQ limbs. */
+API void orc_bfv_switch_keys_core(orc_bfv_eval *e, const u64 *cx, const u64 *evk, u64 *p0, u64 *p1) {
+    const orc_ctx *Q = e->Q, *K = e->QP;
+    u64 N = K->N;
+    int nQP = K->nl;
+    int level = Q->nl - 1;
+    u64 *c2Qi = (u64 *)calloc((u64)nQP * N, sizeof(u64));
+    u64 *c2 = (u64 *)calloc((u64)nQP * N, sizeof(u64));
+    u64 *c2QiNtt = (u64 *)malloc(sizeof(u64) * N);
+    memset(p0, 0, sizeof(u64) * nQP * N);
+    memset(p1, 0, sizeof(u64) * nQP * N);
+    orc_ntt(Q, Q->nl, cx, c2);
+    u64 reduce = 0;
+    for (int i = 0; i < e->beta; i++) {
+        int p0idxst = i * e->alpha;
+        int p0idxed = p0idxst + e->dec->xalpha[i];
+        orc_decompose(e->dec, N, level, i, cx, c2Qi);
+        const u64 *k0 = evk + ((u64)(i * 2 + 0) * nQP) * N;
+        const u64 *k1 = evk + ((u64)(i * 2 + 1) * nQP) * N;
+        for (int x = 0; x < nQP; x++) {
+            u64 qi = K->modulus[x], mp = K->mred[x];
+            if (p0idxst <= x && x < p0idxed)
+                memcpy(c2QiNtt, c2 + (u64)x * N, sizeof(u64) * N);
+            else
+                orc_ntt_limb(c2Qi + (u64)x * N, c2QiNtt, N, K->ntt_psi[x], qi, mp, K->bred[x]);
+            for (u64 y = 0; y < N; y++) {
+                p0[x * N + y] += orc_mred(k0[x * N + y], c2QiNtt[y], qi, mp);
+                p1[x * N + y] += orc_mred(k1[x * N + y], c2QiNtt[y], qi, mp);
+            }
+        }
+        if ((reduce & 7) == 7) {
+            orc_reduce(K, nQP, p0, p0);
+            orc_reduce(K, nQP, p1, p1);
+        }
+        reduce++;
+    }
+    if (((reduce - 1) & 7) != 7) {
+        orc_reduce(K, nQP, p0, p0);
+        orc_reduce(K, nQP, p1, p1);
+    }
+    orc_invntt(K, nQP, p0, p0);
+    orc_invntt(K, nQP, p1, p1);
+    orc_moddown_pq(e->q1p, level, p0, p0);
+    orc_moddown_pq(e->q1p, level, p1, p1);
+    free(c2Qi); free(c2); free(c2QiNtt);
+}
+
+/* relinearize, bfv/evaluator.go:480-500, degree 2 -> 1.  ct: [3][nQ][N], evk = evakey[0]. out: [2][nQ][N] */
+API void orc_bfv_relinearize(orc_bfv_eval *e, const u64 *ct, const u64 *evk, u64 *out) {
+    const orc_ctx *Q = e->Q;
+    u64 N = Q->N, szQ = (u64)Q->nl * N;
+    u64 *p0 = (u64 *)malloc(sizeof(u64) * e->QP->nl * N), *p1 = (u64 *)malloc(sizeof(u64) * e->QP->nl * N);
+    if (out != ct) memcpy(out, ct, sizeof(u64) * 2 * szQ);
+    orc_bfv_switch_keys_core(e, ct + 2 * szQ, evk, p0, p1);
+    orc_add(Q, Q->nl, out, p0, out);
+    orc_add(Q, Q->nl, out + szQ, p1, out + szQ);
+    free(p0); free(p1);
+}
+
+/* SwitchKeys, bfv/evaluator.go:540-558 */
+API void orc_bfv_switch_keys(orc_bfv_eval *e, const u64 *ct, const u64 *evk, u64 *out) {
+    const orc_ctx *Q = e->Q;
+    u64 N = Q->N, szQ = (u64)Q->nl * N;
+    u64 *p0 = (u64 *)malloc(sizeof(u64) * e->QP->nl * N), *p1 = (u64 *)malloc(sizeof(u64) * e->QP->nl * N);
+    orc_bfv_switch_keys_core(e, ct + szQ, evk, p0, p1);
+    orc_add(Q, Q->nl, ct, p0, out);
+    memcpy(out + szQ, p1, sizeof(u64) * szQ);
+    free(p0); free(p1);
+}
+
+/* permute, bfv/evaluator.go:711-733 (RotateColumns :578 with a direct key, RotateRows :669) */
+API void orc_bfv_permute(orc_bfv_eval *e, const u64 *ct, u64 gen, const u64 *evk, u64 *out) {
+    const orc_ctx *Q = e->Q;
+    u64 N = Q->N, szQ = (u64)Q->nl * N;
+    u64 *el = (u64 *)malloc(sizeof(u64) * 2 * szQ);
+    u64 *p0 = (u64 *)malloc(sizeof(u64) * e->QP->nl * N), *p1 = (u64 *)malloc(sizeof(u64) * e->QP->nl * N);
+    orc_permute(Q, Q->nl, ct, gen, el);
+    orc_permute(Q, Q->nl, ct + szQ, gen, el + szQ);
+    orc_bfv_switch_keys_core(e, el + szQ, evk, p0, p1);
+    orc_add(Q, Q->nl, el, p0, out);
+    memcpy(out + szQ, p1, sizeof(u64) * szQ);
+    free(el); free(p0); free(p1);
+}

@@ -394,3 +394,70 @@ class CkksEvaluator:
         out = np.zeros((2, level + 1, self.Q.N), dtype=np.uint64)
         lib().orc_ckks_switch_keys(self.h, level, ptr(ct), ptr(evk), ptr(out))
         return out
+
+
+def _declare_bfv(L):
+    def f(name, res, *args):
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+
+    f("orc_bfv_eval_new", vp, vp, vp, vp, vp, u64, p64, p64)
+    f("orc_bfv_eval_free", None, vp)
+    f("orc_bfv_tensor_and_rescale", None, vp, p64, p64, p64)
+    f("orc_bfv_switch_keys_core", None, vp, p64, p64, p64, p64)
+    f("orc_bfv_relinearize", None, vp, p64, p64, p64)
+    f("orc_bfv_switch_keys", None, vp, p64, p64, p64)
+    f("orc_bfv_permute", None, vp, p64, u64, p64, p64)
+
+
+class BfvEvaluator:
+    """Hot ops of bfv.evaluator restated (bfv/evaluator.go:278-813)."""
+
+    def __init__(self, ctxQ, ctxQMul, ctxP, t):
+        L = lib()
+        if not getattr(L, "_bfv_declared", False):
+            _declare_bfv(L)
+            L._bfv_declared = True
+        self.Q, self.QMul, self.P = ctxQ, ctxQMul, ctxP
+        self.QP = Context(ctxQ.N, ctxQ.moduli + ctxP.moduli)
+        self.t = int(t)
+        prod = 1
+        for q in ctxQMul.moduli:
+            prod *= q
+        phalf = prod >> 1  # bfv/evaluator.go:98
+        pm, pq = arr([phalf % q for q in ctxQMul.moduli]), arr([phalf % q for q in ctxQ.moduli])
+        self.h = L.orc_bfv_eval_new(ctxQ.h, ctxQMul.h, ctxP.h, self.QP.h, self.t, ptr(pm), ptr(pq))
+        self.nQ, self.nP, self.N = ctxQ.nl, ctxP.nl, ctxQ.N
+
+    def __del__(self):
+        try:
+            lib().orc_bfv_eval_free(self.h)
+        except Exception:
+            pass
+
+    def tensor_and_rescale(self, ct0, ct1):
+        out = np.zeros((3, self.nQ, self.N), dtype=np.uint64)
+        lib().orc_bfv_tensor_and_rescale(self.h, ptr(ct0), ptr(ct1), ptr(out))
+        return out
+
+    def switch_keys_core(self, cx, evk):
+        p0 = np.zeros((self.nQ + self.nP, self.N), dtype=np.uint64)
+        p1 = np.zeros((self.nQ + self.nP, self.N), dtype=np.uint64)
+        lib().orc_bfv_switch_keys_core(self.h, ptr(cx), ptr(evk), ptr(p0), ptr(p1))
+        return p0[: self.nQ].copy(), p1[: self.nQ].copy()
+
+    def relinearize(self, ct, evk):
+        out = np.zeros((2, self.nQ, self.N), dtype=np.uint64)
+        lib().orc_bfv_relinearize(self.h, ptr(ct), ptr(evk), ptr(out))
+        return out
+
+    def switch_keys(self, ct, evk):
+        out = np.zeros((2, self.nQ, self.N), dtype=np.uint64)
+        lib().orc_bfv_switch_keys(self.h, ptr(ct), ptr(evk), ptr(out))
+        return out
+
+    def permute(self, ct, gen, evk):
+        out = np.zeros((2, self.nQ, self.N), dtype=np.uint64)
+        lib().orc_bfv_permute(self.h, ptr(ct), gen, ptr(evk), ptr(out))
+        return out

@@ -288,3 +288,82 @@ def test_unreduced_inputs_are_defined():
     assert all((out[i] < QI60[i]).all() for i in range(4))
     out = ctx.invntt(a)
     assert all((out[i] < QI60[i]).all() for i in range(4))
+
+
+# ---------------------------------------------------------------------------
+# BFV drivers (bfv/evaluator.go:278-813), anchored like bfv/bfv_test.go: the ring-level
+# plaintext must come out right
+# ---------------------------------------------------------------------------
+def _bfv_small(N=32):
+    logn = N.bit_length() - 1
+    Q, P, QMul = orc.gen_moduli(logn, [39, 39, 38], [40, 40], [60, 60, 60])
+    return Q, P, QMul
+
+
+def test_bfv_tensor_and_rescale_semantics():
+    """Mul of noiseless encryptions (Delta*m, 0) x (Delta*m', 0): value[0] must be Delta*(m*m' mod t) up to
+    the rounding error of the t/Q scaling, value[1] = value[2] = 0-ish (bfv/evaluator.go:278-464)."""
+    N, t = 32, 65537
+    Q, P, QMul = _bfv_small(N)
+    rng = random.Random(31)
+    ev = orc.BfvEvaluator(orc.Context(N, Q), orc.Context(N, QMul), orc.Context(N, P), t)
+    Qp = prod(Q)
+    delta = Qp // t
+    m0 = [rng.randrange(t) for _ in range(N)]
+    m1 = [rng.randrange(t) for _ in range(N)]
+    ct0 = np.stack([crt_poly([delta * m for m in m0], Q), np.zeros((len(Q), N), np.uint64)])
+    ct1 = np.stack([crt_poly([delta * m for m in m1], Q), np.zeros((len(Q), N), np.uint64)])
+    out = ev.tensor_and_rescale(np.ascontiguousarray(ct0), np.ascontiguousarray(ct1))
+    mm = [0] * N
+    for x in range(N):
+        for y in range(N):
+            k = x + y
+            if k >= N:
+                mm[k - N] -= m0[x] * m1[y]
+            else:
+                mm[k] += m0[x] * m1[y]
+    got = crt_reconstruct(out[0], Q)
+    for k in range(N):
+        v = got[k] if got[k] < Qp // 2 else got[k] - Qp
+        # decrypt: round(t * v / Q) mod t
+        dec = ((2 * t * v + Qp) // (2 * Qp)) % t
+        assert dec == mm[k] % t, k
+    for i in (1, 2):
+        v = crt_reconstruct(out[i], Q)
+        assert all(min(x, Qp - x) < (1 << 20) for x in v)
+    sq = ev.tensor_and_rescale(np.ascontiguousarray(ct0), np.ascontiguousarray(ct0))
+    assert sq.shape == out.shape
+
+
+def test_bfv_keyswitch_semantics():
+    """bfv switchKeys (bfv/evaluator.go:736-813) with a key built as bfv/keygen.go newSwitchingKey does
+    (same structure as the ckks one): p0 + p1*s_out = cx*s_in + small, in the coefficient domain."""
+    N, t = 32, 65537
+    Q, P, QMul = _bfv_small(N)
+    rng = random.Random(32)
+    ctxQ, ctxP, ctxQP = orc.Context(N, Q), orc.Context(N, P), orc.Context(N, Q + P)
+    ev = orc.BfvEvaluator(ctxQ, orc.Context(N, QMul), ctxP, t)
+    sk_in = [rng.choice([-1, 0, 1]) for _ in range(N)]
+    sk_out = [rng.choice([-1, 0, 1]) for _ in range(N)]
+    evk = _keygen(rng, ctxQP, Q, P, N, sk_in, sk_out)
+    Qp = prod(Q)
+    cx_vals = [rng.randrange(Qp) for _ in range(N)]
+    cx = crt_poly(cx_vals, Q)
+    p0, p1 = ev.switch_keys_core(cx, evk)
+
+    def negacyclic(a, b, mod):
+        out = [0] * N
+        for x in range(N):
+            for y in range(N):
+                k = x + y
+                if k >= N:
+                    out[k - N] = (out[k - N] - a[x] * b[y]) % mod
+                else:
+                    out[k] = (out[k] + a[x] * b[y]) % mod
+        return out
+
+    p0c, p1c = crt_reconstruct(p0, Q), crt_reconstruct(p1, Q)
+    lhs = [(u + v) % Qp for u, v in zip(p0c, negacyclic(p1c, sk_out, Qp))]
+    rhs = negacyclic(cx_vals, sk_in, Qp)
+    err = max(min((l - r) % Qp, (r - l) % Qp) for l, r in zip(lhs, rhs))
+    assert err.bit_length() < 30, err.bit_length()
