@@ -1,0 +1,114 @@
+"""Parity at BASELINE.json's full sizes.  The oracle is fast enough for ONE ciphertext at the
+largest parameter sets, so each test compares one batch entry bit-for-bit against the oracle and
+pins the rest of the batch with size-independent properties: every entry of a batched call equals
+the single-entry call on the same input (batch independence), NTT -> InvNTT is the identity, and
+duplicated inputs give duplicated outputs.
+
+config 3: BFV PN15QP880  (bfv/params.go:80-87)   Mul + Relinearize + RotateColumns
+config 4: CKKS PN16QP1761 (ckks/params.go:79-86) MulRelin + Rescale + RotateColumns at level 33
+"""
+import numpy as np
+import pytest
+
+from oracle import ring_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lg():
+    import lattigpu
+    from lattigpu import ring
+
+    ring.set_device(0)
+    return lattigpu
+
+
+def uniform_ct(rng, Q, N, batch, deg=1):
+    return np.ascontiguousarray(np.stack([rng.integers(0, q, size=(batch, deg + 1, N), dtype=np.uint64) for q in Q], axis=2))
+
+
+def polys(lg, ct):
+    return tuple(lg.ring.Poly.from_numpy(np.ascontiguousarray(ct[:, i])) for i in range(ct.shape[1]))
+
+
+def host(ct, nl=None):
+    return np.stack([p.numpy(nl=nl, squeeze=False) for p in ct], axis=1)
+
+
+def test_ckks_pn16_mulrelin_rescale_rotate(lg):
+    p = lg.ckks.DefaultParams[lg.ckks.PN16QP1761]
+    N = 1 << p["LogN"]
+    Q, P = lg.ckks.GenModuli(p)
+    nQ, nP = len(Q), len(P)
+    assert (N, nQ, nP) == (65536, 34, 4)
+    beta = -(-nQ // nP)
+    rng = np.random.default_rng(0x1A771C0 + 4)
+    evk = np.ascontiguousarray(np.stack([rng.integers(0, q, size=(beta, 2, N), dtype=np.uint64) for q in Q + P], axis=2))
+    batch = 3
+    a, b = uniform_ct(rng, Q, N, batch), uniform_ct(rng, Q, N, batch)
+    a[2], b[2] = a[0], b[0]  # duplicated input -> duplicated output
+    cQ, cP = lg.ring.NewContextWithParams(N, Q), lg.ring.NewContextWithParams(N, P)
+    ev = lg.ckks.NewEvaluator(cQ, cP)
+    key = lg.ckks.SwitchingKey(evk)
+    level = nQ - 1
+    pa, pb = polys(lg, a), polys(lg, b)
+    out = (lg.ring.Poly(N, nQ, batch), lg.ring.Poly(N, nQ, batch))
+    ev.MulRelin(level, pa, pb, key, out)
+    ev.Rescale(nQ, out)
+    rot = (lg.ring.Poly(N, nQ, batch), lg.ring.Poly(N, nQ, batch))
+    idx = lg.ring.PermuteNTTIndex(5, 1, N)
+    ev.permuteNTT(level - 1, out, idx, key, rot)
+    got_mr, got_rot = host(out, nQ - 1), host(rot, nQ - 1)
+    # (1) one entry against the oracle, bit-exact
+    oev = orc.CkksEvaluator(orc.Context(N, Q), orc.Context(N, P))
+    w = oev.rescale(oev.mul_relin(level, np.ascontiguousarray(a[1]), np.ascontiguousarray(b[1]), evk))
+    assert np.array_equal(got_mr[1], w)
+    w = oev.permute_ntt(level - 1, w, orc.permute_ntt_index(5, 1, N), evk)
+    assert np.array_equal(got_rot[1], w)
+    # (2) duplicated inputs
+    assert np.array_equal(got_mr[0], got_mr[2]) and np.array_equal(got_rot[0], got_rot[2])
+    # (3) batch independence: entry 0 recomputed alone
+    pa1, pb1 = polys(lg, a[:1]), polys(lg, b[:1])
+    o1 = (lg.ring.Poly(N, nQ, 1), lg.ring.Poly(N, nQ, 1))
+    ev.MulRelin(level, pa1, pb1, key, o1)
+    ev.Rescale(nQ, o1)
+    assert np.array_equal(host(o1, nQ - 1)[0], got_mr[0])
+    # (4) NTT round trip over the whole batch at full size
+    t = lg.ring.Poly(N, nQ, batch)
+    cQ.InvNTT(pa[0], t)
+    cQ.NTT(t, t)
+    assert np.array_equal(t.numpy(squeeze=False), a[:, 0])
+
+
+def test_bfv_pn15_mul_relin_rotate(lg):
+    p = lg.bfv.DefaultParams[lg.bfv.PN15QP880]
+    N = 1 << p["LogN"]
+    Q, P, QMul = lg.bfv.GenModuli(p)
+    nQ, nP = len(Q), len(P)
+    assert (N, nQ, nP, len(QMul)) == (32768, 12, 3, 12)
+    beta = -(-nQ // nP)
+    rng = np.random.default_rng(0x1A771C0 + 3)
+    evk = np.ascontiguousarray(np.stack([rng.integers(0, q, size=(beta, 2, N), dtype=np.uint64) for q in Q + P], axis=2))
+    batch = 3
+    a, b = uniform_ct(rng, Q, N, batch), uniform_ct(rng, Q, N, batch)
+    a[2], b[2] = a[0], b[0]
+    cQ, cM, cP = (lg.ring.NewContextWithParams(N, m) for m in (Q, QMul, P))
+    ev = lg.bfv.NewEvaluator(cQ, cM, cP, p["T"])
+    key = lg.ckks.SwitchingKey(evk)
+    pa, pb = polys(lg, a), polys(lg, b)
+    d2 = tuple(lg.ring.Poly(N, nQ, batch) for _ in range(3))
+    ev.Mul(pa, pb, d2)
+    d1 = (lg.ring.Poly(N, nQ, batch), lg.ring.Poly(N, nQ, batch))
+    ev.Relinearize(d2, key, d1)
+    rot = (lg.ring.Poly(N, nQ, batch), lg.ring.Poly(N, nQ, batch))
+    gen = pow(lg.bfv.GaloisGen, 1, 2 * N)
+    ev.permute(d1, gen, key, rot)
+    got = host(rot)
+    oev = orc.BfvEvaluator(orc.Context(N, Q), orc.Context(N, QMul), orc.Context(N, P), p["T"])
+    w = oev.tensor_and_rescale(np.ascontiguousarray(a[1]), np.ascontiguousarray(b[1]))
+    assert np.array_equal(host(d2)[1], w)
+    w = oev.relinearize(w, evk)
+    w = oev.permute(w, gen, evk)
+    assert np.array_equal(got[1], w)
+    assert np.array_equal(got[0], got[2])
