@@ -48,6 +48,7 @@ typedef struct lg_galois lg_galois;         /* []uint64 index of PermuteNTTIndex
 typedef struct lg_ckks_eval lg_ckks_eval;   /* hot ops of ckks.evaluator, ckks/evaluator.go:64-76 */
 typedef struct lg_bfv_eval lg_bfv_eval;     /* hot ops of bfv.evaluator,  bfv/evaluator.go:41-60 */
 typedef struct lg_swk lg_swk;               /* ckks/bfv SwitchingKey.evakey [beta][2] QP polys, ckks/keygen.go:282-340 */
+typedef struct lg_comm lg_comm;             /* ranks of one node (NCCL over NVLink); no counterpart in the reference */
 typedef void* lg_stream_t;                  /* cudaStream_t */
 
 /* ---- library / device ---------------------------------------------------- */
@@ -237,6 +238,28 @@ int lg_bfv_switch_keys(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, con
 /* permute :711-733 = RotateColumns with a direct key (:595, gen = galElRotColLeft[k]) / RotateRows (:669, gen = 2N-1) */
 int lg_bfv_permute(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, uint64_t gen, const lg_swk* k, lg_poly* out0,
                    lg_poly* out1, lg_stream_t s);
+
+/* ---- multi-GPU (one process per GPU) ------------------------------ */
+/* The reference is single-process; these entry points add the two exchange steps the path has when it is
+ * spread over the GPUs of a node.  NCCL is resolved at run time (dlopen "libnccl.so.2"). */
+int lg_comm_get_unique_id(uint8_t* id128);            /* rank 0; ship the 128 bytes to the other ranks */
+int lg_comm_create(int world, int rank, const uint8_t* id128, lg_comm** out); /* after lg_set_device */
+int lg_comm_destroy(lg_comm* c);
+int lg_comm_world(const lg_comm* c);
+int lg_comm_rank(const lg_comm* c);
+/* ownership rule of the limb axis: rank r owns limbs [r*n/world, (r+1)*n/world)   (host only) */
+int lg_comm_limb_range(int nlimbs, int world, int rank, int* begin, int* end);
+/* party axis: AggregateShares of dckks/dbfv (e.g. dckks/publickey_gen.go:45-47) over ranks =
+ * all-reduce(sum,u64) + Reduce; p holds this rank's share on entry and the aggregate on return */
+int lg_comm_aggregate_shares(const lg_comm* c, const lg_ring* r, int nl, lg_poly* p, lg_stream_t s);
+/* limb axis: one ciphertext (or a small batch) with its RNS limbs spread over the ranks; inputs and outputs
+ * are replicated, the all-gathers sit exactly where a basis extension needs every limb */
+int lg_ckks_switch_keys_in_place_sharded(lg_ckks_eval* e, const lg_comm* c, int level, const lg_poly* cx, const lg_swk* evk,
+                                         lg_poly* p0, lg_poly* p1, lg_stream_t s);
+int lg_ckks_mul_relin_sharded(lg_ckks_eval* e, const lg_comm* c, int level, const lg_poly* a0, const lg_poly* a1,
+                              const lg_poly* b0, const lg_poly* b1, const lg_swk* rlk, lg_poly* out0, lg_poly* out1,
+                              lg_stream_t s);
+int lg_ckks_rescale_sharded(lg_ckks_eval* e, const lg_comm* c, int nl, lg_poly* c0, lg_poly* c1, lg_stream_t s);
 
 #ifdef __cplusplus
 }

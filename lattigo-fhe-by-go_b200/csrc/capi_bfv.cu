@@ -182,6 +182,7 @@ int lg_bfv_mul(lg_bfv_eval* e, const lg_poly* a0, const lg_poly* a1, const lg_po
     for (int i = 0; i < 3; ++i) ta.c_bs[i] = ws;
     ta.square = square ? 1 : 0;
     ta.nomod = 1;
+    ta.limb0 = 0;
     lg_launch_tensor(ta, nT, B, st);
     LG_LAUNCH_CHECK();
     // :424-425 InvNTT of the three outputs in both bases

@@ -576,6 +576,7 @@ int lg_ckks_mul_relin(lg_ckks_eval* e, int level, const lg_poly* a0, const lg_po
     t.c_bs[2] = bs;
     t.square = square ? 1 : 0;
     t.nomod = 0;
+    t.limb0 = 0;
     lg_launch_tensor(t, nl, batch, st);
     LG_LAUNCH_CHECK();
     // :1098-1104 relinearise c2 and add: out0 = CRed(c0 + pool1), out1 = CRed(c1 + pool2)

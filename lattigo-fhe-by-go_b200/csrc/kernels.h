@@ -178,5 +178,6 @@ struct TensorArgs {
     size_t a_bs[2], b_bs[2], c_bs[3];
     int square;
     int nomod;  // 1: BFV form, c1 is accumulated without reduction (bfv/evaluator.go:344,361)
+    int limb0;  // first limb processed (limb-sharded launches); blockIdx.y counts from it
 };
 int lg_launch_tensor(const TensorArgs& a, int nlimbs, int batch, cudaStream_t st);

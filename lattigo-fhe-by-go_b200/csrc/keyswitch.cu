@@ -52,9 +52,9 @@ __global__ void __launch_bounds__(256) ks_mac_kernel(const KsMacArgs a) {
 // instead of the reference's six passes.  Outputs may alias inputs (same-index access only).
 __global__ void __launch_bounds__(256) tensor_kernel(const TensorArgs a) {
     const int j = blockIdx.y, bt = blockIdx.z;
-    const LimbConst k = load_limb_const(a.T, j);
+    const LimbConst k = load_limb_const(a.T, a.limb0 + j);
     const u32 N = a.T.N;
-    const size_t off = (size_t)j * N;
+    const size_t off = (size_t)(a.limb0 + j) * N;
     const ulonglong2* a0 = reinterpret_cast<const ulonglong2*>(a.a0 + bt * a.a_bs[0] + off);
     const ulonglong2* a1 = reinterpret_cast<const ulonglong2*>(a.a1 + bt * a.a_bs[1] + off);
     const ulonglong2* b0 = reinterpret_cast<const ulonglong2*>(a.b0 + bt * a.b_bs[0] + off);

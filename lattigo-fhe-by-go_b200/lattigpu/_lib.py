@@ -160,6 +160,16 @@ SIGNATURES = {
     "lg_bfv_relinearize": (ci, [vp, _P, _P, _P, vp, _P, _P, vp]),
     "lg_bfv_switch_keys": (ci, [vp, _P, _P, vp, _P, _P, vp]),
     "lg_bfv_permute": (ci, [vp, _P, _P, u64, vp, _P, _P, vp]),
+    "lg_comm_get_unique_id": (ci, [C.POINTER(C.c_uint8)]),
+    "lg_comm_create": (ci, [ci, ci, C.POINTER(C.c_uint8), C.POINTER(vp)]),
+    "lg_comm_destroy": (ci, [vp]),
+    "lg_comm_world": (ci, [vp]),
+    "lg_comm_rank": (ci, [vp]),
+    "lg_comm_limb_range": (ci, [ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]),
+    "lg_comm_aggregate_shares": (ci, [vp, _R, ci, _P, vp]),
+    "lg_ckks_switch_keys_in_place_sharded": (ci, [vp, vp, ci, _P, vp, _P, _P, vp]),
+    "lg_ckks_mul_relin_sharded": (ci, [vp, vp, ci, _P, _P, _P, _P, vp, _P, _P, vp]),
+    "lg_ckks_rescale_sharded": (ci, [vp, vp, ci, _P, _P, vp]),
 }
 
 
