@@ -93,8 +93,8 @@ def _worker(rank, world, port, q):
             oQP = orc.Context(N, Q + P)
             agg = None
             for r in range(world):
-                s = np.ascontiguousarray(np.stack([np.random.default_rng(1000 + r).integers(0, m, size=(N,), dtype=np.uint64)
-                                                   for m in Q + P]))
+                g = np.random.default_rng(1000 + r)
+                s = np.ascontiguousarray(np.stack([g.integers(0, m, size=(N,), dtype=np.uint64) for m in Q + P]))
                 agg = s if agg is None else oQP.op3("add", agg, s)
             assert np.array_equal(ps.numpy(), agg)
         dist.barrier()
