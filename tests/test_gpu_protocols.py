@@ -1,0 +1,122 @@
+"""GPU parity for the dckks / dbfv protocol steps on the ring hot path (config 5): CKG and PCKS
+GenShare / AggregateShares / KeySwitch, with 3 in-process parties as dckks/dckks_test.go:63,146-168
+does.  The expected values are the same op sequences composed from the oracle's ring ops; samples
+are supplied by the test (the reference samples on the host)."""
+import numpy as np
+import pytest
+
+from oracle import ring_oracle as orc
+
+pytestmark = pytest.mark.gpu
+PARTIES = 3
+
+
+@pytest.fixture(scope="module")
+def lg():
+    import lattigpu
+    from lattigpu import ring
+
+    ring.set_device(0)
+    return lattigpu
+
+
+def uni(rng, moduli, N):
+    return np.ascontiguousarray(np.stack([rng.integers(0, q, size=(N,), dtype=np.uint64) for q in moduli]))
+
+
+def small(rng, moduli, N, bound):
+    """a small signed sample reduced mod each prime (what the host samplers produce)"""
+    v = rng.integers(-bound, bound + 1, size=(N,))
+    return np.ascontiguousarray(np.stack([np.where(v < 0, q + v, v).astype(np.uint64) for q in moduli]))
+
+
+def ternary_mont(rng, oK, moduli, N):
+    v = small(rng, moduli, N, 1)
+    return oK.op2("mform_poly", v)
+
+
+@pytest.mark.parametrize("scheme", ["dckks", "dbfv"])
+def test_ckg_pcks(lg, scheme):
+    if scheme == "dckks":
+        p = lg.ckks.DefaultParams[lg.ckks.PN13QP218]
+        Q, P = lg.ckks.GenModuli(p)
+    else:
+        p = lg.bfv.DefaultParams[lg.bfv.PN13QP218]
+        Q, P, _ = lg.bfv.GenModuli(p)
+    N = 1 << p["LogN"]
+    QP = Q + P
+    nQ = len(Q)
+    rng = np.random.default_rng(61)
+    oQ, oP, oK = orc.Context(N, Q), orc.Context(N, P), orc.Context(N, QP)
+    oext = orc.Extender(oQ, oP)
+    cQ, cP, cK = (lg.ring.NewContextWithParams(N, m) for m in (Q, P, QP))
+    mod = lg.dckks if scheme == "dckks" else lg.dbfv
+    F = lg.ring.Poly.from_numpy
+
+    # ---- CKG: share_i = NTT(e_i) - sk_i * crs ; pk0 = sum_i share_i ---------------------------
+    ckg = mod.CKGProtocol(cK)
+    crs = uni(rng, QP, N)
+    sks = [oK.op2("mform_poly", oK.ntt(small(rng, QP, N, 1))) for _ in range(PARTIES)]  # NTT + Montgomery secrets
+    es = [small(rng, QP, N, 19) for _ in range(PARTIES)]
+    want = None
+    agg = None
+    for sk, e in zip(sks, es):
+        w = oK.ntt(e)
+        oK.op3("mulcoeffs_montgomery_and_sub", sk, crs, w)
+        want = w if want is None else oK.op3("add", want, w)
+        share = ckg.AllocateShares()
+        ckg.GenShare(F(sk), F(crs), share, F(e))
+        assert np.array_equal(share.numpy(), w)
+        if agg is None:
+            agg = share
+        else:
+            ckg.AggregateShares(agg, share, agg)
+    assert np.array_equal(agg.numpy(), want)
+
+    # ---- PCKS ----------------------------------------------------------------------------------
+    pk = (want, crs)
+    level = nQ - 1 if scheme == "dbfv" else nQ - 2
+    nl = level + 1
+    ct = [uni(rng, Q, N), uni(rng, Q, N)]
+    pcks = mod.PCKSProtocol(cQ, cP, cK)
+    comb_w, comb = None, None
+    for i in range(PARTIES):
+        u = ternary_mont(rng, oK, QP, N)
+        e0, e1 = small(rng, QP, N, 40), small(rng, QP, N, 19)
+        skq = np.ascontiguousarray(sks[i][:nQ])
+        t = oK.ntt(u)
+        s0 = oK.op3("mulcoeffs_montgomery", t, pk[0])
+        s1 = oK.op3("mulcoeffs_montgomery", t, pk[1])
+        if scheme == "dckks":
+            s0 = oK.op3("add", s0, oK.ntt(e0))
+            s1 = oK.op3("add", s1, oK.ntt(e1))
+            w0 = oext.moddown_ntt_pq(level, s0)
+            w1 = oext.moddown_ntt_pq(level, s1)
+            oQ.op3("mulcoeffs_montgomery_and_add", np.ascontiguousarray(ct[1][:nl]), np.ascontiguousarray(skq[:nl]), w0, nl=nl)
+            share = pcks.AllocateShares(level)
+            pcks.GenShare(level, F(skq), (F(pk[0]), F(pk[1])), F(ct[1]), share, F(u), F(e0), F(e1))
+        else:
+            s0 = oK.op3("add", oK.invntt(s0), e0)
+            s1 = oK.op3("add", oK.invntt(s1), e1)
+            w0 = oext.moddown_pq(level, s0)
+            w1 = oext.moddown_pq(level, s1)
+            tt = oQ.invntt(oQ.op3("mulcoeffs_montgomery", oQ.ntt(ct[1]), skq))
+            w0 = oQ.op3("add", w0, tt)
+            share = pcks.AllocateShares()
+            pcks.GenShare(F(skq), (F(pk[0]), F(pk[1])), F(ct[1]), share, F(u), F(e0), F(e1))
+        assert np.array_equal(share[0].numpy(nl=nl), w0) and np.array_equal(share[1].numpy(nl=nl), w1), i
+        if comb is None:
+            comb, comb_w = share, [w0, w1]
+        else:
+            if scheme == "dckks":
+                pcks.AggregateShares(comb, share, comb, level)
+            else:
+                pcks.AggregateShares(comb, share, comb)
+            comb_w = [oQ.op3("add", comb_w[0], w0, nl=nl), oQ.op3("add", comb_w[1], w1, nl=nl)]
+    out = (cQ.NewPoly(), cQ.NewPoly())
+    if scheme == "dckks":
+        pcks.KeySwitch(comb, (F(ct[0]), F(ct[1])), out, level)
+    else:
+        pcks.KeySwitch(comb, (F(ct[0]), F(ct[1])), out)
+    assert np.array_equal(out[0].numpy(nl=nl), oQ.op3("add", np.ascontiguousarray(ct[0][:nl]), comb_w[0], nl=nl))
+    assert np.array_equal(out[1].numpy(nl=nl), comb_w[1])
