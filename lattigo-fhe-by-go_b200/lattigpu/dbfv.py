@@ -23,6 +23,7 @@ class PCKSProtocol:
     def __init__(self, contextQ, contextP, contextQP):
         self.contextQ, self.contextP, self.contextQP = contextQ, contextP, contextQP
         self.baseconverter = ring.NewFastBasisExtender(contextQ, contextP)
+        self._pool = {}  # tmp / share0tmp / share1tmp of the reference (public_keyswitching.go), per batch size
 
     def AllocateShares(self, batch=1):
         return (self.contextQ.NewPoly(batch), self.contextQ.NewPoly(batch))
@@ -32,7 +33,9 @@ class PCKSProtocol:
         Q, K = self.contextQ, self.contextQP
         batch = u.batch
         level = Q.nl - 1
-        tmp, s0, s1 = K.NewPoly(batch), K.NewPoly(batch), K.NewPoly(batch)
+        if batch not in self._pool:
+            self._pool[batch] = (K.NewPoly(batch), K.NewPoly(batch), K.NewPoly(batch), self.contextQ.NewPoly(batch))
+        tmp, s0, s1, tq = self._pool[batch]
         K.NTT(u, tmp, stream=stream)  # :118
         K.MulCoeffsMontgomery(tmp, pk[0], s0, stream=stream)  # :121-122
         K.MulCoeffsMontgomery(tmp, pk[1], s1, stream=stream)
@@ -42,7 +45,7 @@ class PCKSProtocol:
         K.Add(s1, e1, s1, stream=stream)
         self.baseconverter.ModDownPQ(level, s0, shareOut[0], stream=stream)  # :132-135
         self.baseconverter.ModDownPQ(level, s1, shareOut[1], stream=stream)
-        t = Q.NewPoly(batch)
+        t = tq
         Q.NTT(ct1, t, stream=stream)  # :138-140
         Q.MulCoeffsMontgomery(t, sk, t, stream=stream)
         Q.InvNTT(t, t, stream=stream)

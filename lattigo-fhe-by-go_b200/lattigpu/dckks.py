@@ -36,6 +36,7 @@ class PCKSProtocol:
     def __init__(self, contextQ, contextP, contextQP):
         self.contextQ, self.contextP, self.contextQP = contextQ, contextP, contextQP
         self.baseconverter = ring.NewFastBasisExtender(contextQ, contextP)
+        self._pool = {}  # tmp / share0tmp / share1tmp of the reference (public_keyswitching.go), per batch size
         self.nQP = contextQP.nl
 
     def AllocateShares(self, level, batch=1):
@@ -47,7 +48,9 @@ class PCKSProtocol:
         ct1 = ct.Value()[1]; sk over Q (NTT + Montgomery)."""
         K = self.contextQP
         batch = u.batch
-        tmp, s0, s1 = K.NewPoly(batch), K.NewPoly(batch), K.NewPoly(batch)
+        if batch not in self._pool:
+            self._pool[batch] = (K.NewPoly(batch), K.NewPoly(batch), K.NewPoly(batch), self.contextQ.NewPoly(batch))
+        tmp, s0, s1, tq = self._pool[batch]
         K.NTT(u, tmp, stream=stream)  # SampleTernaryMontgomeryNTT :68
         K.MulCoeffsMontgomery(tmp, pk[0], s0, stream=stream)  # :71-72
         K.MulCoeffsMontgomery(tmp, pk[1], s1, stream=stream)

@@ -30,6 +30,9 @@ __global__ void bench(u64* out, u32 a0, u32 b0) {
             if (KIND == 9) asm volatile("{.reg .u32 t; add.cc.u32 %0, %0, %1; addc.u32 %2, %2, %1;}" : "+r"(a[i]), "+r"(c[i]) : "r"(b[i]));
             if (KIND == 10) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b[i])); asm volatile("add.u32 %0, %0, %1;" : "+r"(c[i]) : "r"(b[i])); asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i])); }
             if (KIND == 11) { asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(c[i])); asm volatile("add.u32 %0, %0, %1;" : "+r"(c[i]) : "r"(b[i])); }
+            if (KIND == 13) { u64 t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[i]), "r"(b[i])); a[i] = (u32)t ^ (u32)(t >> 32); }
+            if (KIND == 14) { u64 t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[i]), "r"(b[i])); w[i] += t; a[i] += 1; }
+            if (KIND == 15) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b0)); }
             if (KIND == 12) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b[i])); asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d[i]) : "d"(1.0000001)); }
         }
     }
@@ -72,5 +75,8 @@ int main() {
     run<10>("IMAD.WIDE + 2 IADD (counted as 3)", 3, out);
     run<11>("IMAD + IADD (counted as 2)", 2, out);
     run<12>("IMAD.WIDE + DFMA (counted as 2)", 2, out);
+    run<13>("mul.wide (no acc) + LOP3 (2)", 2, out);
+    run<14>("mul.wide + 64-bit add + add (4)", 4, out);
+    run<15>("IMAD.WIDE uniform b operand", 1, out);
     return 0;
 }
