@@ -79,6 +79,21 @@ int lgi_ring_build_device(lg_ring* r) {
     LG_TRY(r->d_psi.upload(r->psi));
     LG_TRY(r->d_psi_inv.upload(r->psi_inv));
     LG_TRY(r->d_ninv.upload(r->ninv));
+    // twiddles of the fast forward NTT: psi out of Montgomery form and its Shoup constant (derived
+    // from the reference's nttPsi, so the root choice stays the reference's)
+    std::vector<u64> w(r->psi.size()), ws(r->psi.size());
+    for (int i = 0; i < r->nl; ++i) {
+        const u64 qi = r->q[i], qi_inv = r->mred[i];
+        for (u64 j = 0; j < r->N; ++j) {
+            const u64 plain = lgh::mred(r->psi[(size_t)i * r->N + j], 1, qi, qi_inv);  // InvMForm
+            w[(size_t)i * r->N + j] = plain;
+            ws[(size_t)i * r->N + j] = (u64)((((unsigned __int128)plain) << 64) / qi);
+        }
+    }
+    LG_TRY(r->d_psi_w.upload(w));
+    LG_TRY(r->d_psi_ws.upload(ws));
+    r->T.psi_w = r->d_psi_w.d;
+    r->T.psi_ws = r->d_psi_ws.d;
     r->T.q = r->d_q.d;
     r->T.qinv = r->d_qinv.d;
     r->T.bred = r->d_bred.d;

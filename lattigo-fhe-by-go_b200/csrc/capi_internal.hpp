@@ -79,7 +79,7 @@ struct lg_ring {
     u32 logN = 0;
     int nl = 0;
     std::vector<u64> q, bred, mred, ninv, psi, psi_inv, rescale;  // host copies
-    DevArray<u64> d_q, d_qinv, d_bred, d_psi, d_psi_inv, d_ninv;
+    DevArray<u64> d_q, d_qinv, d_bred, d_psi, d_psi_inv, d_ninv, d_psi_w, d_psi_ws;
     RingTables T;
     u64 rescale_param(int j, int i) const { return rescale[(size_t)j * (j - 1) / 2 + i]; }  // rescaleParams[j-1][i]
 };

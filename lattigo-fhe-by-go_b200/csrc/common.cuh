@@ -15,6 +15,8 @@ struct RingTables {
     const u64* psi;      // [nl][N]         nttPsi     (Montgomery, bit-reversed)
     const u64* psi_inv;  // [nl][N]         nttPsiInv
     const u64* ninv;     // [nl]            nttNInv
+    const u64* psi_w;    // [nl][N]         nttPsi out of Montgomery form (same bit-reversed order)
+    const u64* psi_ws;   // [nl][N]         floor(psi_w * 2^64 / q)  (Shoup constants of the fast forward NTT)
     u32 N;
     u32 logN;
     int nl;

@@ -105,6 +105,46 @@ LG_DEV void butterfly_fwd(u64& U, u64& V, u64 w, u64 q, u64 qinv, u64 twoq) {
     U = u + v;
     V = u + twoq - v;
 }
+// ---- fast forward butterflies ------------------------------------------------------------------
+// The forward transform of the reference never wraps 64 bits: in Butterfly (ntt.go:32-40) the Montgomery
+// product is in [1,2q-1] for ANY 64-bit V (its high word is < psi < q), so X = U'+V <= max(U,4q) and
+// Y = U'+2q-V <= max(U,4q) stay below 2^64 and every value remains congruent to the true transform; the
+// final BRedAdd is canonical for any 64-bit word.  Hence NTT(x) of the reference equals the canonical
+// negacyclic transform of (x mod q) for every input, and ANY exact lazy butterfly followed by a canonical
+// reduction is bit-identical.  The two below use Shoup/Harvey multiplication by the twiddle w in plain
+// form with ws = floor(w * 2^64 / q); they need 5-6 instead of 9 wide multiplies.
+LG_DEV u64 mul_wide(u32 a, u32 b) {
+    u64 r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+LG_DEV u64 mad_wide(u32 a, u32 b, u64 c) {
+    u64 r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+// q < 2^62, values kept in [0,4q): exact quotient floor(ws*Y/2^64) => T = w*Y - Q*q in [0,2q)
+LG_DEV void butterfly_fwd_4q(u64& X, u64& Y, u64 w, u64 ws, u64 q, u64 twoq) {
+    u64 x = X;
+    if (x >= twoq) x -= twoq;
+    const u64 qh = mul_hi(ws, Y);
+    const u64 t = mul_lo(w, Y) - mul_lo(qh, q);
+    X = x + t;
+    Y = x + twoq - t;
+}
+// q < 2^56: the quotient is taken from the three high partial products only (at most 2 too small, so
+// T = w*Y - Q*q is in [0,4q)) and no conditional subtraction is made: a value grows by at most 4q per
+// stage, 16 stages add < 64q < 2^62 to inputs that the load clamps below 2^63.  Y may be any 64-bit word.
+LG_DEV void butterfly_fwd_free(u64& X, u64& Y, u64 w, u64 ws, u64 q, u64 fourq) {
+    const u32 a0 = (u32)ws, a1 = (u32)(ws >> 32), b0 = (u32)Y, b1 = (u32)(Y >> 32);
+    const u64 m1 = mul_wide(a1, b0), m2 = mul_wide(a0, b1);
+    const u64 qh = mad_wide(a1, b1, (m1 >> 32)) + (m2 >> 32);
+    const u64 t = mul_lo(w, Y) - mul_lo(qh, q);
+    const u64 x = X;
+    X = x + t;
+    Y = x + fourq - t;
+}
+
 // InvButterfly, ring/ntt.go:43-50
 LG_DEV void butterfly_inv(u64& U, u64& V, u64 w, u64 q, u64 qinv, u64 twoq) {
     u64 x = U + V;

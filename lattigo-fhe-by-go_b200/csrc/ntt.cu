@@ -1,10 +1,15 @@
 // ntt.cu -- kernel family K1: batched per-limb negacyclic NTT / InvNTT.
 //
-// Replaces ring/ntt.go:53-139 of the reference (Cooley-Tukey forward with lazy
-// butterflies and a final BRedAdd; Gentleman-Sande inverse with a final
-// MRed by N^-1).  Every radix-2 butterfly keeps the reference's exact formula
-// (modarith.cuh) and twiddle, so outputs are bit-identical for ANY 64-bit
-// input, including the unreduced words the reference's own benchmarks feed.
+// Replaces ring/ntt.go:53-139 of the reference (Cooley-Tukey forward with lazy butterflies and a
+// final BRedAdd; Gentleman-Sande inverse with a final MRed by N^-1).
+//
+// Bit-exactness.  InvNTT keeps every radix-2 butterfly literal (InvButterfly can wrap 64 bits on
+// out-of-range input, so its result is formula-specific).  The forward transform of the reference never
+// wraps (see modarith.cuh), so its output is the canonical transform of (x mod q) for EVERY 64-bit
+// input; the forward kernels therefore use cheaper exact Shoup/Harvey butterflies (5-6 wide multiplies
+// instead of 9) and still match the reference bit for bit, including on the unreduced words its own
+// benchmarks feed (tests: "words" cases).  LATTIGPU_LITERAL_NTT=1 selects the literal forward
+// butterflies instead (A/B and cross-check).
 //
 // Schedule (N = 2^logN, one limb = N words, grid = tiles x limbs x batch):
 //   logN <= 11 : one CTA per limb, radix-2 stages in shared memory.
@@ -16,43 +21,70 @@
 //   re-distributes them through (padded, conflict-free) shared memory.
 //   Twiddle index for the butterfly on (j, j+2^s): (N >> (s+1)) + (j >> (s+1))
 //   in both directions (ring/ntt.go:74 and :120).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace {
 
+// forward butterfly flavours
+enum { BF_LITERAL = 0, BF_4Q = 1, BF_FREE = 2 };
+
 // ---- register blocks --------------------------------------------------------
 // x[r] holds the coefficient at global index j0 + r*2^s (bits [s,s+4) of j0 are
 // zero); twbase = (N + j0) >> s.  Stage u pairs r and r + 2^u (stride 2^(s+u)).
 
-template <int UHI, int ULO, bool VEC>
-LG_DEV void fwd_stages(u64 (&x)[16], const u64* __restrict__ tw, u32 twbase, u64 q, u64 qinv, u64 twoq) {
+struct FwdConst {
+    u64 q, qinv, twoq, fourq;
+    const u64* tw;   // literal: nttPsi (Montgomery).  fast: psi_w
+    const u64* tws;  // fast: psi_ws
+};
+
+template <bool VEC, int NG>
+LG_DEV void load_tw(u64 (&w)[8], const u64* __restrict__ t, u32 base) {
+    if (VEC && NG >= 2) {
 #pragma unroll
-    for (int it = 0; it <= UHI - ULO; ++it) {
-        const int u = UHI - it;
-        const u32 base = twbase >> (u + 1);
-        const int ngroups = 16 >> (u + 1);
-        u64 w[8];
-        if (VEC && ngroups >= 2) {
-#pragma unroll
-            for (int g = 0; g < ngroups; g += 2) {
-                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tw + base + g));
-                w[g] = v.x;
-                w[g + 1] = v.y;
-            }
-        } else {
-#pragma unroll
-            for (int g = 0; g < ngroups; ++g) w[g] = __ldg(tw + base + g);
+        for (int g = 0; g < NG; g += 2) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(t + base + g));
+            w[g] = v.x;
+            w[g + 1] = v.y;
         }
+    } else {
 #pragma unroll
-        for (int g = 0; g < ngroups; ++g) {
+        for (int g = 0; g < NG; ++g) w[g] = __ldg(t + base + g);
+    }
+}
+
+template <int U, bool VEC, int MODE>
+LG_DEV void fwd_stage(u64 (&x)[16], const FwdConst& c, u32 twbase) {
+    constexpr int NG = 16 >> (U + 1);
+    const u32 base = twbase >> (U + 1);
+    u64 w[8], ws[8];
+    load_tw<VEC, NG>(w, c.tw, base);
+    if (MODE != BF_LITERAL) load_tw<VEC, NG>(ws, c.tws, base);
 #pragma unroll
-            for (int k = 0; k < (1 << u); ++k) {
-                const int r = (g << (u + 1)) + k;
-                butterfly_fwd(x[r], x[r + (1 << u)], w[g], q, qinv, twoq);
-            }
+    for (int g = 0; g < NG; ++g) {
+#pragma unroll
+        for (int k = 0; k < (1 << U); ++k) {
+            const int r = (g << (U + 1)) + k;
+            if (MODE == BF_LITERAL)
+                butterfly_fwd(x[r], x[r + (1 << U)], w[g], c.q, c.qinv, c.twoq);
+            else if (MODE == BF_4Q)
+                butterfly_fwd_4q(x[r], x[r + (1 << U)], w[g], ws[g], c.q, c.twoq);
+            else
+                butterfly_fwd_free(x[r], x[r + (1 << U)], w[g], ws[g], c.q, c.fourq);
         }
     }
+}
+
+// stages UHI, UHI-1, ..., ULO
+template <int UHI, int ULO, bool VEC, int MODE>
+LG_DEV void fwd_stages(u64 (&x)[16], const FwdConst& c, u32 twbase) {
+    if (UHI >= 3 && ULO <= 3) fwd_stage<3, VEC, MODE>(x, c, twbase);
+    if (UHI >= 2 && ULO <= 2) fwd_stage<2, VEC, MODE>(x, c, twbase);
+    if (UHI >= 1 && ULO <= 1) fwd_stage<1, VEC, MODE>(x, c, twbase);
+    if (UHI >= 0 && ULO <= 0) fwd_stage<0, VEC, MODE>(x, c, twbase);
 }
 
 template <int ULO, int UHI, bool VEC>
@@ -92,6 +124,7 @@ struct LimbSetup {
     u64* out;
     const u64* tw;
     u64 ninv;
+    int tl;
     bool skip;
 };
 
@@ -100,39 +133,66 @@ LG_DEV LimbSetup setup_limb(const NttArgs& a) {
     LimbSetup s;
     const int j = blockIdx.y, b = blockIdx.z;
     s.skip = (j >= a.skip0 && j < a.skip1);
-    const int tl = a.map(j);
-    s.c = load_limb_const(a.T, tl);
-    s.tw = (FWD ? a.T.psi : a.T.psi_inv) + (size_t)tl * a.T.N;
-    s.ninv = FWD ? 0 : a.T.ninv[tl];
+    s.tl = a.map(j);
+    s.c = load_limb_const(a.T, s.tl);
+    s.tw = (FWD ? a.T.psi : a.T.psi_inv) + (size_t)s.tl * a.T.N;
+    s.ninv = FWD ? 0 : a.T.ninv[s.tl];
     s.in = a.in + (size_t)b * a.in_bstride + (size_t)j * a.T.N;
     s.out = a.out + (size_t)b * a.out_bstride + (size_t)j * a.T.N;
     return s;
 }
 
+template <int MODE>
+LG_DEV FwdConst fwd_const(const NttArgs& a, const LimbSetup& s) {
+    FwdConst c;
+    c.q = s.c.q;
+    c.qinv = s.c.qinv;
+    c.twoq = 2 * s.c.q;
+    c.fourq = 4 * s.c.q;
+    if (MODE == BF_LITERAL) {
+        c.tw = s.tw;
+        c.tws = nullptr;
+    } else {
+        c.tw = a.T.psi_w + (size_t)s.tl * a.T.N;
+        c.tws = a.T.psi_ws + (size_t)s.tl * a.T.N;
+    }
+    return c;
+}
+
+// which butterfly a limb may use: BF_FREE needs q < 2^56 (16 stages x 4q < 2^62), BF_4Q needs 4q < 2^64
+LG_DEV int fast_mode(u64 q) { return q < (1ull << 56) ? BF_FREE : BF_4Q; }
+
 // ---- forward, strided phase: stages 1..L -----------------------------------
-template <int L>
-__global__ void __launch_bounds__(256) ntt_fwd_strided(const NttArgs a) {
+template <int L, int MODE>
+LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
     constexpr int G = 1 << (L - 4);  // threads per column
     constexpr int W = 256 / G;       // columns per CTA
     constexpr int N2 = L - 4;        // stages of the second register block
-    __shared__ u64 sm[N2 > 0 ? 4096 : 1];
-    const LimbSetup s = setup_limb<true>(a);
-    if (s.skip) return;
+    const FwdConst c = fwd_const<MODE>(a, s);
     const u32 LB = a.T.logN - L;
-    const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
     const int t = threadIdx.x, col = t % W, g = t / W;
     const size_t colg = (size_t)blockIdx.x * W + col;
     u64 x[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(g + r * G) << LB) + colg];
-    fwd_stages<3, 0, false>(x, s.tw, 16u, q, qinv, twoq);
+    if (MODE == BF_FREE) {  // growth headroom: everything below 2^63 (canonical inputs never take this branch)
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (x[r] >> 63) x[r] = bred_add(x[r], c.q, s.c.u0);
+    }
+    if (MODE == BF_4Q) {  // Harvey's invariant: values in [0,4q)
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (x[r] >= c.fourq) x[r] = bred_add(x[r], c.q, s.c.u0);
+    }
+    fwd_stages<3, 0, false, MODE>(x, c, 16u);
     if (N2 > 0) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) sm[(g + r * G) * W + col] = x[r];
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = sm[(16 * g + r) * W + col];
-        fwd_stages<(N2 > 0 ? N2 - 1 : 0), 0, false>(x, s.tw, (1u << L) + 16u * g, q, qinv, twoq);
+        fwd_stages<(N2 > 0 ? N2 - 1 : 0), 0, false, MODE>(x, c, (1u << L) + 16u * g);
 #pragma unroll
         for (int r = 0; r < 16; ++r) s.out[((size_t)(16 * g + r) << LB) + colg] = x[r];
     } else {
@@ -141,42 +201,69 @@ __global__ void __launch_bounds__(256) ntt_fwd_strided(const NttArgs a) {
     }
 }
 
+template <int L, bool LITERAL>
+__global__ void __launch_bounds__(256) ntt_fwd_strided(const NttArgs a) {
+    __shared__ u64 sm[(L - 4) > 0 ? 4096 : 1];
+    const LimbSetup s = setup_limb<true>(a);
+    if (s.skip) return;
+    if (LITERAL)
+        fwd_strided_body<L, BF_LITERAL>(a, s, sm);
+    else if (fast_mode(s.c.q) == BF_FREE)
+        fwd_strided_body<L, BF_FREE>(a, s, sm);
+    else
+        fwd_strided_body<L, BF_4Q>(a, s, sm);
+}
+
 // ---- forward, contiguous phase: last 8 stages + BRedAdd ---------------------
+template <int MODE>
+LG_DEV void fwd_contig_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
+    const FwdConst c = fwd_const<MODE>(a, s);
+    const u32 N = a.T.N;
+    const u32 t = threadIdx.x, seg = t >> 4, cc = t & 15;
+    const u32 base = blockIdx.x * 4096u;
+    const u32 j0 = base + seg * 256u + cc;
+    u64 x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = s.in[j0 + 16 * r];
+    fwd_stages<3, 0, false, MODE>(x, c, (N + j0) >> 4);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + cc + 16 * r)] = x[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + 16 * cc + r)];
+    const u32 j1 = base + seg * 256u + 16 * cc;
+    fwd_stages<3, 0, true, MODE>(x, c, N + j1);
+    // ring/ntt.go:83-85
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + 16 * cc + r)] = bred_add(x[r], c.q, s.c.u0);
+    __syncthreads();
+}
+
 // MAC = true fuses the key-switch multiply-accumulate into the epilogue (NttMac).
-template <bool MAC>
+template <bool MAC, bool LITERAL>
 __global__ void __launch_bounds__(256) ntt_fwd_contig(const NttArgs a) {
     __shared__ u64 sm[4096 + 256];
     const LimbSetup s = setup_limb<true>(a);
     if (!MAC && s.skip) return;
     const u32 N = a.T.N;
-    const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
-    const u32 t = threadIdx.x, seg = t >> 4, c = t & 15;
+    const u64 q = s.c.q, qinv = s.c.qinv;
+    const u32 t = threadIdx.x;
     const u32 base = blockIdx.x * 4096u;
     if (!(MAC && s.skip)) {
-        const u32 j0 = base + seg * 256u + c;
-        u64 x[16];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) x[r] = s.in[j0 + 16 * r];
-        fwd_stages<3, 0, false>(x, s.tw, (N + j0) >> 4, q, qinv, twoq);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + c + 16 * r)] = x[r];
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + 16 * c + r)];
-        const u32 j1 = base + seg * 256u + 16 * c;
-        fwd_stages<3, 0, true>(x, s.tw, N + j1, q, qinv, twoq);
-        // ring/ntt.go:83-85
-#pragma unroll
-        for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + 16 * c + r)] = bred_add(x[r], q, s.c.u0);
-        __syncthreads();
+        if (LITERAL)
+            fwd_contig_body<BF_LITERAL>(a, s, sm);
+        else if (fast_mode(q) == BF_FREE)
+            fwd_contig_body<BF_FREE>(a, s, sm);
+        else
+            fwd_contig_body<BF_4Q>(a, s, sm);
     }
     if (!MAC) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) s.out[base + t + 256u * k] = sm[pad16(t + 256u * k)];
     } else {
-        const int j = blockIdx.y, b = blockIdx.z, tl = a.map(j);
-        const u64* e0 = a.mac.evk0 + (size_t)tl * N + base;
-        const u64* e1 = a.mac.evk1 + (size_t)tl * N + base;
+        const int j = blockIdx.y, b = blockIdx.z;
+        const u64* e0 = a.mac.evk0 + (size_t)s.tl * N + base;
+        const u64* e1 = a.mac.evk1 + (size_t)s.tl * N + base;
         u64* p0 = a.mac.acc0 + (size_t)b * a.mac.acc_bs + (size_t)j * N + base;
         u64* p1 = a.mac.acc1 + (size_t)b * a.mac.acc_bs + (size_t)j * N + base;
         const u64* cx = a.mac.cx + (size_t)b * a.mac.cx_bs + (size_t)j * N + base;
@@ -303,11 +390,21 @@ __global__ void ntt_small(const NttArgs a) {
 }
 
 template <int L>
-void launch_strided(bool fwd, const NttArgs& a, dim3 grid, cudaStream_t st) {
-    if (fwd)
-        ntt_fwd_strided<L><<<grid, 256, 0, st>>>(a);
-    else
+void launch_strided(bool fwd, bool literal, const NttArgs& a, dim3 grid, cudaStream_t st) {
+    if (!fwd)
         ntt_inv_strided<L><<<grid, 256, 0, st>>>(a);
+    else if (literal)
+        ntt_fwd_strided<L, true><<<grid, 256, 0, st>>>(a);
+    else
+        ntt_fwd_strided<L, false><<<grid, 256, 0, st>>>(a);
+}
+
+bool literal_forward() {
+    static const bool v = [] {
+        const char* e = getenv("LATTIGPU_LITERAL_NTT");
+        return e && e[0] == '1';
+    }();
+    return v;
 }
 
 }  // namespace
@@ -328,17 +425,18 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
         return 0;
     }
     const int L = (int)logN - 8;
+    const bool literal = literal_forward();
     dim3 grid(N / 4096, nlimbs, batch);
     NttArgs second = args;  // the second phase runs in place on the output
     second.in = args.out;
     second.in_bstride = args.out_bstride;
     auto strided = [&](const NttArgs& a) {
         switch (L) {
-            case 4: launch_strided<4>(!inverse, a, grid, st); break;
-            case 5: launch_strided<5>(!inverse, a, grid, st); break;
-            case 6: launch_strided<6>(!inverse, a, grid, st); break;
-            case 7: launch_strided<7>(!inverse, a, grid, st); break;
-            default: launch_strided<8>(!inverse, a, grid, st); break;
+            case 4: launch_strided<4>(!inverse, literal, a, grid, st); break;
+            case 5: launch_strided<5>(!inverse, literal, a, grid, st); break;
+            case 6: launch_strided<6>(!inverse, literal, a, grid, st); break;
+            case 7: launch_strided<7>(!inverse, literal, a, grid, st); break;
+            default: launch_strided<8>(!inverse, literal, a, grid, st); break;
         }
     };
     if (!inverse) {
@@ -351,10 +449,17 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
             second.in_bstride = args.in_bstride;
         }
         strided(first);
-        if (args.mac.enabled)
-            ntt_fwd_contig<true><<<grid, 256, 0, st>>>(second);
-        else
-            ntt_fwd_contig<false><<<grid, 256, 0, st>>>(second);
+        if (args.mac.enabled) {
+            if (literal)
+                ntt_fwd_contig<true, true><<<grid, 256, 0, st>>>(second);
+            else
+                ntt_fwd_contig<true, false><<<grid, 256, 0, st>>>(second);
+        } else {
+            if (literal)
+                ntt_fwd_contig<false, true><<<grid, 256, 0, st>>>(second);
+            else
+                ntt_fwd_contig<false, false><<<grid, 256, 0, st>>>(second);
+        }
     } else {
         ntt_inv_contig<<<grid, 256, 0, st>>>(args);
         strided(second);
