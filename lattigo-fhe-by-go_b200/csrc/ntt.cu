@@ -11,7 +11,8 @@
 // benchmarks feed (tests: "words" cases).  LATTIGPU_LITERAL_NTT=1 selects the literal forward
 // butterflies instead (A/B and cross-check).
 //
-// Schedule (N = 2^logN, one limb = N words, grid = tiles x limbs x batch):
+// Schedule (N = 2^logN, one limb = N words, grid = batch x tiles x limbs -- batch fastest, so the CTAs that
+// share a limb's twiddles and key tile run together and hit L2):
 //   logN <= 11 : one CTA per limb, radix-2 stages in shared memory.
 //   logN >= 12 : two phases of register-resident radix-16 blocks
 //     "strided" phase : the top L = logN-8 stages; a CTA owns all 2^L rows of
@@ -131,7 +132,7 @@ struct LimbSetup {
 template <bool FWD>
 LG_DEV LimbSetup setup_limb(const NttArgs& a) {
     LimbSetup s;
-    const int j = blockIdx.y, b = blockIdx.z;
+    const int j = blockIdx.z, b = blockIdx.x;
     s.skip = (j >= a.skip0 && j < a.skip1);
     s.tl = a.map(j);
     s.c = load_limb_const(a.T, s.tl);
@@ -171,7 +172,7 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
     const FwdConst c = fwd_const<MODE>(a, s);
     const u32 LB = a.T.logN - L;
     const int t = threadIdx.x, col = t % W, g = t / W;
-    const size_t colg = (size_t)blockIdx.x * W + col;
+    const size_t colg = (size_t)blockIdx.y * W + col;
     u64 x[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(g + r * G) << LB) + colg];
@@ -220,7 +221,7 @@ LG_DEV void fwd_contig_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
     const FwdConst c = fwd_const<MODE>(a, s);
     const u32 N = a.T.N;
     const u32 t = threadIdx.x, seg = t >> 4, cc = t & 15;
-    const u32 base = blockIdx.x * 4096u;
+    const u32 base = blockIdx.y * 4096u;
     const u32 j0 = base + seg * 256u + cc;
     u64 x[16];
 #pragma unroll
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_contig(const NttArgs a) {
     const u32 N = a.T.N;
     const u64 q = s.c.q, qinv = s.c.qinv;
     const u32 t = threadIdx.x;
-    const u32 base = blockIdx.x * 4096u;
+    const u32 base = blockIdx.y * 4096u;
     if (!(MAC && s.skip)) {
         if (LITERAL)
             fwd_contig_body<BF_LITERAL>(a, s, sm);
@@ -261,28 +262,44 @@ __global__ void __launch_bounds__(256) ntt_fwd_contig(const NttArgs a) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) s.out[base + t + 256u * k] = sm[pad16(t + 256u * k)];
     } else {
-        const int j = blockIdx.y, b = blockIdx.z;
-        const u64* e0 = a.mac.evk0 + (size_t)s.tl * N + base;
-        const u64* e1 = a.mac.evk1 + (size_t)s.tl * N + base;
-        u64* p0 = a.mac.acc0 + (size_t)b * a.mac.acc_bs + (size_t)j * N + base;
-        u64* p1 = a.mac.acc1 + (size_t)b * a.mac.acc_bs + (size_t)j * N + base;
-        const u64* cx = a.mac.cx + (size_t)b * a.mac.cx_bs + (size_t)j * N + base;
+        const int j = blockIdx.z, b = blockIdx.x;
+        const size_t ko = (size_t)s.tl * N + base, ao = (size_t)b * a.mac.acc_bs + (size_t)j * N + base;
+        const ulonglong2* e0 = reinterpret_cast<const ulonglong2*>(a.mac.evk0 + ko);
+        const ulonglong2* e1 = reinterpret_cast<const ulonglong2*>(a.mac.evk1 + ko);
+        ulonglong2* p0 = reinterpret_cast<ulonglong2*>(a.mac.acc0 + ao);
+        ulonglong2* p1 = reinterpret_cast<ulonglong2*>(a.mac.acc1 + ao);
+        const ulonglong2* cx = reinterpret_cast<const ulonglong2*>(a.mac.cx + (size_t)b * a.mac.cx_bs + (size_t)j * N + base);
 #pragma unroll 4
-        for (int k = 0; k < 16; ++k) {
-            const u32 e = t + 256u * k;
-            const u64 d = s.skip ? cx[e] : sm[pad16(e)];
-            u64 r0 = mred(__ldg(e0 + e), d, q, qinv);
-            u64 r1 = mred(__ldg(e1 + e), d, q, qinv);
+        for (int k = 0; k < 8; ++k) {
+            const u32 v = t + 256u * k;  // pair index: elements 2v, 2v+1
+            ulonglong2 d;
+            if (s.skip) {
+                d = cx[v];
+            } else {
+                d.x = sm[pad16(2 * v)];
+                d.y = sm[pad16(2 * v + 1)];
+            }
+            const ulonglong2 k0 = __ldg(e0 + v), k1 = __ldg(e1 + v);
+            ulonglong2 r0, r1;
+            r0.x = mred(k0.x, d.x, q, qinv);
+            r0.y = mred(k0.y, d.y, q, qinv);
+            r1.x = mred(k1.x, d.x, q, qinv);
+            r1.y = mred(k1.y, d.y, q, qinv);
             if (!a.mac.first) {
-                r0 += p0[e];
-                r1 += p1[e];
+                const ulonglong2 o0 = p0[v], o1 = p1[v];
+                r0.x += o0.x;
+                r0.y += o0.y;
+                r1.x += o1.x;
+                r1.y += o1.y;
             }
             if (a.mac.reduce) {
-                r0 = bred_add(r0, q, s.c.u0);
-                r1 = bred_add(r1, q, s.c.u0);
+                r0.x = bred_add(r0.x, q, s.c.u0);
+                r0.y = bred_add(r0.y, q, s.c.u0);
+                r1.x = bred_add(r1.x, q, s.c.u0);
+                r1.y = bred_add(r1.y, q, s.c.u0);
             }
-            p0[e] = r0;
-            p1[e] = r1;
+            p0[v] = r0;
+            p1[v] = r1;
         }
     }
 }
@@ -295,7 +312,7 @@ __global__ void __launch_bounds__(256) ntt_inv_contig(const NttArgs a) {
     const u32 N = a.T.N;
     const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
     const u32 t = threadIdx.x, seg = t >> 4, c = t & 15;
-    const u32 base = blockIdx.x * 4096u;
+    const u32 base = blockIdx.y * 4096u;
 #pragma unroll
     for (int k = 0; k < 16; ++k) sm[pad16(t + 256u * k)] = s.in[base + t + 256u * k];
     __syncthreads();
@@ -327,7 +344,7 @@ __global__ void __launch_bounds__(256) ntt_inv_strided(const NttArgs a) {
     const u32 LB = a.T.logN - L;
     const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
     const int t = threadIdx.x, col = t % W, g = t / W;
-    const size_t colg = (size_t)blockIdx.x * W + col;
+    const size_t colg = (size_t)blockIdx.y * W + col;
     u64 x[16];
     if (N2 > 0) {
 #pragma unroll
@@ -416,7 +433,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     if (args.mac.enabled && (logN <= 11 || inverse)) return 1;
     if (logN <= 11) {
         const u32 threads = (N >> 1) < 32 ? 32 : ((N >> 1) > 512 ? 512 : (N >> 1));
-        dim3 grid(1, nlimbs, batch);
+        dim3 grid(batch, 1, nlimbs);
         if (inverse)
             ntt_small<false><<<grid, threads, N * sizeof(u64), st>>>(args);
         else
@@ -426,7 +443,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     }
     const int L = (int)logN - 8;
     const bool literal = literal_forward();
-    dim3 grid(N / 4096, nlimbs, batch);
+    dim3 grid(batch, N / 4096, nlimbs);
     NttArgs second = args;  // the second phase runs in place on the output
     second.in = args.out;
     second.in_bstride = args.out_bstride;
