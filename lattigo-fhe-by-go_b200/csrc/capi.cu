@@ -3,6 +3,7 @@
 // Host-side mirror of ring/ring_context.go, ring/ring_object.go, ring/ring.go,
 // ring/ring_galois.go and ring/ring_scaling.go; all arithmetic on polynomial
 // data runs in the CUDA kernels -- there is no CPU fallback.
+#include <math.h>
 #include <string.h>
 
 #include "capi_internal.hpp"
@@ -79,21 +80,50 @@ int lgi_ring_build_device(lg_ring* r) {
     LG_TRY(r->d_psi.upload(r->psi));
     LG_TRY(r->d_psi_inv.upload(r->psi_inv));
     LG_TRY(r->d_ninv.upload(r->ninv));
-    // twiddles of the fast forward NTT: psi out of Montgomery form and its Shoup constant (derived
-    // from the reference's nttPsi, so the root choice stays the reference's)
-    std::vector<u64> w(r->psi.size()), ws(r->psi.size());
-    for (int i = 0; i < r->nl; ++i) {
-        const u64 qi = r->q[i], qi_inv = r->mred[i];
-        for (u64 j = 0; j < r->N; ++j) {
-            const u64 plain = lgh::mred(r->psi[(size_t)i * r->N + j], 1, qi, qi_inv);  // InvMForm
-            w[(size_t)i * r->N + j] = plain;
-            ws[(size_t)i * r->N + j] = (u64)((((unsigned __int128)plain) << 64) / qi);
+    // twiddles of the fast transforms: psi / psi^-1 / N^-1 out of Montgomery form and their Shoup constants
+    // (derived from the reference's tables, so the root choice stays the reference's)
+    auto shoup_tables = [&](const std::vector<u64>& mont, DevArray<u64>& dw, DevArray<u64>& dws, DevArray<u64>* dwd) -> int {
+        std::vector<u64> w(mont.size()), ws(mont.size()), wd(dwd ? mont.size() : 0);
+        const size_t per = mont.size() / (size_t)r->nl;
+        for (int i = 0; i < r->nl; ++i) {
+            const u64 qi = r->q[i], qi_inv = r->mred[i];
+            for (size_t j = 0; j < per; ++j) {
+                const u64 plain = lgh::mred(mont[(size_t)i * per + j], 1, qi, qi_inv);  // InvMForm
+                w[(size_t)i * per + j] = plain;
+                const u64 s = (u64)((((unsigned __int128)plain) << 64) / qi);
+                ws[(size_t)i * per + j] = s;
+                if (dwd) {  // RD(s) * 2^-64 as a double: never above plain/q, less than 2^-52 below it
+                    double d = (double)s;
+                    if ((unsigned __int128)d > (unsigned __int128)s) d = nextafter(d, 0.0);
+                    d = ldexp(d, -64);
+                    u64 bits;
+                    memcpy(&bits, &d, sizeof(bits));
+                    wd[(size_t)i * per + j] = bits;
+                }
+            }
         }
+        LG_TRY(dw.upload(w));
+        LG_TRY(dws.upload(ws));
+        if (dwd) LG_TRY(dwd->upload(wd));
+        return LG_OK;
+    };
+    LG_TRY(shoup_tables(r->psi, r->d_psi_w, r->d_psi_ws, &r->d_psi_wd));
+    LG_TRY(shoup_tables(r->psi_inv, r->d_psi_inv_w, r->d_psi_inv_ws, nullptr));
+    {
+        std::vector<u64> nw(2 * (size_t)r->nl);
+        for (int i = 0; i < r->nl; ++i) {
+            const u64 plain = lgh::mred(r->ninv[i], 1, r->q[i], r->mred[i]);
+            nw[2 * i] = plain;
+            nw[2 * i + 1] = (u64)((((unsigned __int128)plain) << 64) / r->q[i]);
+        }
+        LG_TRY(r->d_ninv_w.upload(nw));
     }
-    LG_TRY(r->d_psi_w.upload(w));
-    LG_TRY(r->d_psi_ws.upload(ws));
     r->T.psi_w = r->d_psi_w.d;
     r->T.psi_ws = r->d_psi_ws.d;
+    r->T.psi_wd = r->d_psi_wd.d;
+    r->T.psi_inv_w = r->d_psi_inv_w.d;
+    r->T.psi_inv_ws = r->d_psi_inv_ws.d;
+    r->T.ninv_w = r->d_ninv_w.d;
     r->T.q = r->d_q.d;
     r->T.qinv = r->d_qinv.d;
     r->T.bred = r->d_bred.d;
@@ -258,7 +288,7 @@ int lg_poly_create(uint64_t N, int nlimbs, int batch, lg_poly** out) {
 }
 int lg_poly_wrap(void* device_ptr, uint64_t N, int nlimbs, int batch, lg_poly** out) {
     LG_REQUIRE(out && device_ptr, "null argument");
-    LG_REQUIRE(((uintptr_t)device_ptr & 15) == 0, "device pointer must be 16-byte aligned");
+    LG_REQUIRE(((uintptr_t)device_ptr & 31) == 0, "device pointer must be 32-byte aligned");
     LG_REQUIRE(N >= 2 && (N & (N - 1)) == 0 && nlimbs >= 1 && batch >= 1, "invalid polynomial shape");
     lg_poly* p = new lg_poly;
     p->d = (u64*)device_ptr;
@@ -342,9 +372,9 @@ int lg_poly_copy(const lg_poly* src, int nl, lg_poly* dst, lg_stream_t s) {
 // ---------------------------------------------------------------------------
 
 int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, size_t in_bs, u64* out, size_t out_bs,
-            bool inverse, int skip0, int skip1, cudaStream_t st, const NttMac* mac) {
+            bool inverse, int skip0, int skip1, cudaStream_t st, const NttMac* mac, bool in_range) {
     NttArgs a;
-    memset(&a.mac, 0, sizeof(a.mac));
+    memset(&a, 0, sizeof(a));
     if (mac) a.mac = *mac;
     a.T = r->T;
     a.map = map;
@@ -354,6 +384,14 @@ int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, siz
     a.out_bstride = out_bs;
     a.skip0 = skip0;
     a.skip1 = skip1;
+    // The fast inverse butterflies equal the reference's only while no InvButterfly sum wraps, i.e. when
+    // every input word is <= 2q; unless the caller vouches for that, flag the limbs that break it.
+    Scratch flags(st);
+    if (inverse && !in_range && r->logN >= 12 && nl > 0 && batch > 0) {
+        LG_TRY(flags.alloc(((size_t)batch * nl + 1) / 2));
+        lg_launch_range_flags(a, nl, batch, (u32*)flags.d, st);
+        a.flags = (const u32*)flags.d;
+    }
     if (lg_launch_ntt(a, nl, batch, inverse, st) != 0) {
         lg_set_error("NTT: unsupported ring degree 2^%u", r->logN);
         return LG_ERR_ARG;

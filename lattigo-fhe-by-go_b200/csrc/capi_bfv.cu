@@ -68,7 +68,7 @@ int bfv_switch_keys(lg_bfv_eval* e, int batch, const u64* cx, size_t cx_bs, cons
     LG_REQUIRE(e->beta <= evk->beta, "switchKeys: key has %d digits, %d needed", evk->beta, e->beta);
     Scratch c2(st), d(st), acc(st);
     LG_TRY(c2.alloc((size_t)batch * nQ * N));
-    LG_TRY(d.alloc((size_t)batch * nd * N));
+    if (Q->logN < 12) LG_TRY(d.alloc((size_t)batch * nd * N));  // larger rings: the digit loop owns its scratch
     LG_TRY(acc.alloc((size_t)2 * batch * nd * N));
     const size_t c2_bs = (size_t)nQ * N, d_bs = (size_t)nd * N;
     u64* acc0 = acc.d;
@@ -79,7 +79,8 @@ int bfv_switch_keys(lg_bfv_eval* e, int batch, const u64* cx, size_t cx_bs, cons
     LG_TRY(lgi_keyswitch_digits(QP, Q, limb_map_identity(), e->dec.get(), level, e->beta, batch, cx, cx_bs, c2.d, c2_bs, evk,
                                 d.d, acc0, acc1, d_bs, 7, st));
     // :808-809 InvNTT over QP of both accumulators (contiguous: one launch over 2*batch entries)
-    LG_TRY(lgi_ntt(QP, limb_map_identity(), nd, 2 * batch, acc0, d_bs, acc0, d_bs, true, 0, 0, st));
+    // (the accumulators are canonical, so the inverse needs no range check)
+    LG_TRY(lgi_ntt(QP, limb_map_identity(), nd, 2 * batch, acc0, d_bs, acc0, d_bs, true, 0, 0, st, nullptr, true));
     // :811-812 ModDownPQ
     LG_TRY(lgi_moddown_tail_ntt(e->q1p.get(), level, batch, acc0, d_bs, acc0 + (size_t)nQ * N, d_bs, out0, out0_bs, false, st,
                                 add0));

@@ -120,14 +120,14 @@ static int check_p(const lg_poly* p, u64 N, int nl, int batch, const char* what)
 // NTT(tmp); p2 = MRed(p1Q + (q - tmp), P^-1)   (:219-240, :254-273, :287-306)
 // accumulate = true adds the result into p2 with CRed (the AddLvl the evaluators apply right after).
 int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* p1Q, size_t p1Q_bs, u64* p1P,
-                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st, bool accumulate) {
+                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st, bool accumulate, bool p_in_range) {
     const lg_ring* Q = e->Q;
     const lg_ring* P = e->P;
     const u64 N = Q->N;
     const int nl = level + 1;
     LG_REQUIRE(level >= 0 && nl <= Q->nl, "ModDown: level %d out of range", level);
     if (ntt)  // :172 / :215 -- destroys the P part of the input, like the reference
-        LG_TRY(lgi_ntt(P, limb_map_identity(), P->nl, batch, p1P, p1P_bs, p1P, p1P_bs, true, 0, 0, st));
+        LG_TRY(lgi_ntt(P, limb_map_identity(), P->nl, batch, p1P, p1P_bs, p1P, p1P_bs, true, 0, 0, st, nullptr, p_in_range));
     Scratch tmp(st);
     LG_TRY(tmp.alloc((size_t)batch * nl * N));
     const size_t tbs = (size_t)nl * N;
@@ -362,6 +362,68 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
                          u64* d, u64* acc0, u64* acc1, size_t d_bs, int cadence, cudaStream_t st) {
     const u64 N = Q->N;
     const int nl = level + 1, nd = nl + dec->nP, alpha = dec->alpha;
+    if (Q->logN >= 12) {
+        // All digits are decomposed and taken through the strided NTT phase first; one kernel then finishes
+        // the transform of every digit tile by tile, multiplies by the key and keeps both accumulators in
+        // registers over the whole digit loop.  The sums are reduced once at the end: the reference's
+        // cadence (BRedAdd when (i & 7) == cadence and after the last digit) only bounds its lazy sums and
+        // ends canonical as well, so the words are the same.
+        const size_t per_entry = (size_t)beta * nd * N;                 // scratch words per batch entry
+        const size_t budget = (size_t)6 << 27;                          // 6 GiB of u64 words
+        int chunk = (int)(budget / per_entry);
+        if (chunk < 1) chunk = 1;
+        if (chunk > batch) chunk = batch;
+        Scratch D(st);
+        LG_TRY(D.alloc((size_t)chunk * per_entry));
+        for (int b0 = 0; b0 < batch; b0 += chunk) {
+            const int cb = (batch - b0) < chunk ? (batch - b0) : chunk;
+            const size_t d_ds = (size_t)cb * d_bs;
+            for (int i = 0; i < beta; ++i) {
+                u64* Di = D.d + (size_t)i * d_ds;
+                LG_TRY(lgi_decompose(dec, level, i, cb, coef + (size_t)b0 * coef_bs, coef_bs, Di, d_bs, Di + (size_t)nl * N,
+                                     d_bs, st));
+            }
+            NttArgs a;
+            memset(&a, 0, sizeof(a));
+            a.T = QP->T;
+            a.map = qp_map;
+            a.in = D.d;
+            a.out = D.d;
+            a.in_bstride = a.out_bstride = d_bs;
+            a.skip_alpha = alpha;  // the digit's own limbs come from the NTT-domain input
+            a.skip_div = cb;
+            a.skip_nl = nl;
+            if (lg_launch_ntt_fwd_strided(a, nd, beta * cb, st) != 0) {
+                lg_set_error("switchKeys: unsupported ring degree 2^%u", Q->logN);
+                return LG_ERR_ARG;
+            }
+            LG_LAUNCH_CHECK();
+            KsFusedArgs k;
+            memset(&k, 0, sizeof(k));
+            k.T = QP->T;
+            k.map = qp_map;
+            k.D = D.d;
+            k.d_ds = d_ds;
+            k.d_bs = d_bs;
+            k.cx = nttd + (size_t)b0 * nttd_bs;
+            k.cx_bs = nttd_bs;
+            k.evk = evk->key(0, 0);
+            k.evk_ds = (size_t)(evk->key(1, 0) - evk->key(0, 0));
+            k.evk_hs = (size_t)(evk->key(0, 1) - evk->key(0, 0));
+            k.acc0 = acc0 + (size_t)b0 * d_bs;
+            k.acc1 = acc1 + (size_t)b0 * d_bs;
+            k.acc_bs = d_bs;
+            k.beta = beta;
+            k.alpha = alpha;
+            k.nl = nl;
+            if (lg_launch_ks_fused(k, nd, cb, st) != 0) {
+                lg_set_error("switchKeys: fused digit loop launch failed");
+                return LG_ERR_ARG;
+            }
+            LG_LAUNCH_CHECK();
+        }
+        return LG_OK;
+    }
     for (int i = 0; i < beta; ++i) {
         // decomposeAndSplitNTT :1561-1591 / Decompose bfv:767
         LG_TRY(lgi_decompose(dec, level, i, batch, coef, coef_bs, d, d_bs, d + (size_t)nl * N, d_bs, st));
@@ -370,41 +432,23 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
         if (p0idxed > nl) p0idxed = nl;
         const int first = (i == 0);
         const int reduce = ((i & 7) == cadence) || (i == beta - 1);  // ckks :1536,:1547 / bfv :795,:803
-        if (Q->logN >= 12) {
-            // NTT of every limb outside the digit with the multiply-accumulate fused into the last
-            // NTT phase; the digit's own limbs are read straight from the NTT-domain input
-            // (ckks :1579-1584, bfv :776-780).
-            NttMac mac;
-            mac.enabled = 1;
-            mac.evk0 = evk->key(i, 0);
-            mac.evk1 = evk->key(i, 1);
-            mac.acc0 = acc0;
-            mac.acc1 = acc1;
-            mac.acc_bs = d_bs;
-            mac.cx = nttd;
-            mac.cx_bs = nttd_bs;
-            mac.first = first;
-            mac.reduce = reduce;
-            LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d, d_bs, d, d_bs, false, p0idxst, p0idxed, st, &mac));
-        } else {
-            LG_TRY(lgi_ew(EW_COPY, Q, limb_map_identity(), p0idxed - p0idxst, batch, nttd + (size_t)p0idxst * N, nttd_bs,
-                          nullptr, 0, d + (size_t)p0idxst * N, d_bs, nullptr, 0, st));
-            LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d, d_bs, d, d_bs, false, p0idxst, p0idxed, st));
-            KsMacArgs m;
-            m.T = QP->T;
-            m.map = qp_map;
-            m.d = d;
-            m.d_bs = d_bs;
-            m.evk0 = evk->key(i, 0);
-            m.evk1 = evk->key(i, 1);
-            m.acc0 = acc0;
-            m.acc1 = acc1;
-            m.acc_bs = d_bs;
-            m.first = first;
-            m.reduce = reduce;
-            lg_launch_ks_mac(m, nd, batch, st);
-            LG_LAUNCH_CHECK();
-        }
+        LG_TRY(lgi_ew(EW_COPY, Q, limb_map_identity(), p0idxed - p0idxst, batch, nttd + (size_t)p0idxst * N, nttd_bs,
+                      nullptr, 0, d + (size_t)p0idxst * N, d_bs, nullptr, 0, st));
+        LG_TRY(lgi_ntt(QP, qp_map, nd, batch, d, d_bs, d, d_bs, false, p0idxst, p0idxed, st));
+        KsMacArgs m;
+        m.T = QP->T;
+        m.map = qp_map;
+        m.d = d;
+        m.d_bs = d_bs;
+        m.evk0 = evk->key(i, 0);
+        m.evk1 = evk->key(i, 1);
+        m.acc0 = acc0;
+        m.acc1 = acc1;
+        m.acc_bs = d_bs;
+        m.first = first;
+        m.reduce = reduce;
+        lg_launch_ks_mac(m, nd, batch, st);
+        LG_LAUNCH_CHECK();
     }
     return LG_OK;
 }
@@ -415,7 +459,7 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
 // :1158-1159, :1187, :1470).
 static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx, size_t cx_bs, const lg_swk* evk,
                             u64* out0, size_t out0_bs, u64* out1, size_t out1_bs, cudaStream_t st, bool add0 = false,
-                            bool add1 = false) {
+                            bool add1 = false, bool cx_in_range = false) {
     const lg_ring* Q = e->Q;
     const lg_ring* P = e->P;
     const lg_ring* QP = e->QP.get();
@@ -429,7 +473,7 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
 
     Scratch c2(st), d(st), acc(st);
     LG_TRY(c2.alloc((size_t)batch * nl * N));
-    LG_TRY(d.alloc((size_t)batch * nd * N));
+    if (Q->logN < 12) LG_TRY(d.alloc((size_t)batch * nd * N));  // larger rings: the digit loop owns its scratch
     LG_TRY(acc.alloc((size_t)2 * batch * nd * N));
     const size_t c2_bs = (size_t)nl * N, d_bs = (size_t)nd * N;
     u64* acc0 = acc.d;
@@ -437,15 +481,16 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
     const LimbMap qp_map{nl, 0, nQ};  // Q limbs 0..level, then the special primes at #Q.. (:1519-1525)
 
     // :1503  c2 = InvNTT(cx)
-    LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, cx, cx_bs, c2.d, c2_bs, true, 0, 0, st));
+    LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, cx, cx_bs, c2.d, c2_bs, true, 0, 0, st, nullptr, cx_in_range));
     // :1511-1552 digit loop (decomposeAndSplitNTT + multiply-accumulate), reduce cadence reduce&7 == 1
     LG_TRY(lgi_keyswitch_digits(QP, Q, qp_map, e->dec.get(), level, beta, batch, c2.d, c2_bs, cx, cx_bs, evk, d.d, acc0,
                                 acc1, d_bs, 1, st));
     // :1556-1557
+    // the accumulators are canonical, so their inverse transforms need no range check
     LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc0, d_bs, acc0 + (size_t)nl * N, d_bs, out0, out0_bs, true, st,
-                                add0));
+                                add0, true));
     LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc1, d_bs, acc1 + (size_t)nl * N, d_bs, out1, out1_bs, true, st,
-                                add1));
+                                add1, true));
     return LG_OK;
 }
 
@@ -510,7 +555,7 @@ int lg_swk_create(uint64_t N, int beta, int nQP, const uint64_t* host, lg_swk** 
 }
 int lg_swk_wrap(void* device_ptr, uint64_t N, int beta, int nQP, lg_swk** out) {
     LG_REQUIRE(device_ptr && out && beta >= 1 && nQP >= 1, "SwitchingKey: invalid argument");
-    LG_REQUIRE(((uintptr_t)device_ptr & 15) == 0, "device pointer must be 16-byte aligned");
+    LG_REQUIRE(((uintptr_t)device_ptr & 31) == 0, "device pointer must be 32-byte aligned");
     lg_swk* k = new lg_swk;
     k->d = (u64*)device_ptr;
     k->N = N;
@@ -580,7 +625,8 @@ int lg_ckks_mul_relin(lg_ckks_eval* e, int level, const lg_poly* a0, const lg_po
     lg_launch_tensor(t, nl, batch, st);
     LG_LAUNCH_CHECK();
     // :1098-1104 relinearise c2 and add: out0 = CRed(c0 + pool1), out1 = CRed(c1 + pool2)
-    return ckks_switch_keys(e, level, batch, c2, bs, rlk, out0->d, out0->bstride, out1->d, out1->bstride, st, true, true);
+    // (c2 is canonical: MRed output of the tensor kernel)
+    return ckks_switch_keys(e, level, batch, c2, bs, rlk, out0->d, out0->bstride, out1->d, out1->bstride, st, true, true, true);
 }
 
 int lg_ckks_relinearize(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_poly* c2, const lg_swk* rlk,

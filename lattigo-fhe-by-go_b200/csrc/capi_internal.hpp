@@ -79,7 +79,7 @@ struct lg_ring {
     u32 logN = 0;
     int nl = 0;
     std::vector<u64> q, bred, mred, ninv, psi, psi_inv, rescale;  // host copies
-    DevArray<u64> d_q, d_qinv, d_bred, d_psi, d_psi_inv, d_ninv, d_psi_w, d_psi_ws;
+    DevArray<u64> d_q, d_qinv, d_bred, d_psi, d_psi_inv, d_ninv, d_psi_w, d_psi_ws, d_psi_inv_w, d_psi_inv_ws, d_ninv_w, d_psi_wd;
     RingTables T;
     u64 rescale_param(int j, int i) const { return rescale[(size_t)j * (j - 1) / 2 + i]; }  // rescaleParams[j-1][i]
 };
@@ -142,11 +142,12 @@ struct lg_ckks_eval {
 // internal (non-ABI) helpers shared between translation units
 int lgi_ring_build_device(lg_ring* r);
 int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, size_t in_bs, u64* out, size_t out_bs,
-            bool inverse, int skip0, int skip1, cudaStream_t st, const NttMac* mac = nullptr);
+            bool inverse, int skip0, int skip1, cudaStream_t st, const NttMac* mac = nullptr, bool in_range = false);
 int lgi_ew(int op, const lg_ring* r, LimbMap map, int nl, int batch, const u64* a, size_t a_bs, const u64* b,
            size_t b_bs, u64* c, size_t c_bs, const u64* scalars, int nscalars, cudaStream_t st);
 int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* p1Q, size_t p1Q_bs, u64* p1P,
-                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st, bool accumulate = false);
+                         size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st, bool accumulate = false,
+                         bool p_in_range = false);
 int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u64* p0, size_t p0_bs, u64* outQ,
                   size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st);
 int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, const lg_decomposer* dec, int level, int beta,

@@ -17,6 +17,10 @@ struct RingTables {
     const u64* ninv;     // [nl]            nttNInv
     const u64* psi_w;    // [nl][N]         nttPsi out of Montgomery form (same bit-reversed order)
     const u64* psi_ws;   // [nl][N]         floor(psi_w * 2^64 / q)  (Shoup constants of the fast forward NTT)
+    const u64* psi_wd;   // [nl][N]         bits of the double RD(psi_ws) * 2^-64 <= psi_w / q (FP64-assisted forward NTT)
+    const u64* psi_inv_w;   // [nl][N]      nttPsiInv out of Montgomery form
+    const u64* psi_inv_ws;  // [nl][N]      its Shoup constants (fast inverse NTT)
+    const u64* ninv_w;   // [nl][2]         {N^-1 mod q in plain form, its Shoup constant}
     u32 N;
     u32 logN;
     int nl;

@@ -32,9 +32,40 @@ struct NttArgs {
     u64* out;
     size_t in_bstride, out_bstride;  // words between consecutive batch entries
     int skip0, skip1;                // data limbs in [skip0, skip1) are left untouched
+    // forward, digit-batched launches: when skip_alpha > 0 the batch index is digit*skip_div + b and the
+    // skipped limbs of that entry are [digit*skip_alpha, min((digit+1)*skip_alpha, skip_nl))
+    int skip_alpha, skip_div, skip_nl;
+    // inverse only: per (batch, limb) flag, non-zero = some input word is above 2q, use the literal
+    // butterflies for that limb (written by lg_launch_range_flags); nullptr = inputs known to be in range
+    const u32* flags;
     NttMac mac;
 };
 int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cudaStream_t st);
+// forward transform, strided phase only, in place or out of place (logN >= 12); the contiguous phase is
+// then run by lg_launch_ks_fused
+int lg_launch_ntt_fwd_strided(const NttArgs& args, int nlimbs, int batch, cudaStream_t st);
+// flags[b*nlimbs + j] = any word of limb j of batch entry b is > 2q
+int lg_launch_range_flags(const NttArgs& args, int nlimbs, int batch, u32* flags, cudaStream_t st);
+
+// Key-switch digit loop fused with the contiguous NTT phase (ckks/evaluator.go:1511-1552,
+// bfv/evaluator.go:760-806): for every digit i the CTA finishes the forward NTT of its tile of
+// D[i] (or takes the digit's own limbs from the NTT-domain input cx), multiplies by evk[i][0/1] and
+// accumulates in registers; one canonical store of acc0/acc1 at the end.
+struct KsFusedArgs {
+    RingTables T;       // QP tables
+    LimbMap map;        // data limb -> table limb (also the evk limb)
+    const u64* D;       // digits after the strided phase: limb j of batch b of digit i at D + i*d_ds + b*d_bs + j*N
+    size_t d_ds, d_bs;
+    const u64* cx;      // NTT-domain key-switch input: limb j of batch b at cx + b*cx_bs + j*N
+    size_t cx_bs;
+    const u64* evk;     // evk[i][h], table limb tl at evk + i*evk_ds + h*evk_hs + tl*N (shared by the batch)
+    size_t evk_ds, evk_hs;
+    u64* acc0;          // outputs, limb j of batch b at acc + b*acc_bs + j*N, canonical
+    u64* acc1;
+    size_t acc_bs;
+    int beta, alpha, nl;  // digit i owns data limbs [i*alpha, min((i+1)*alpha, nl))
+};
+int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st);
 
 // ---- K3a: coefficient-wise ops (ring/ring.go) --------------------------------
 enum EwOp {

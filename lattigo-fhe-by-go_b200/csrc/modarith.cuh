@@ -105,14 +105,19 @@ LG_DEV void butterfly_fwd(u64& U, u64& V, u64 w, u64 q, u64 qinv, u64 twoq) {
     U = u + v;
     V = u + twoq - v;
 }
-// ---- fast forward butterflies ------------------------------------------------------------------
+// ---- fast butterflies ----------------------------------------------------------------------------
 // The forward transform of the reference never wraps 64 bits: in Butterfly (ntt.go:32-40) the Montgomery
 // product is in [1,2q-1] for ANY 64-bit V (its high word is < psi < q), so X = U'+V <= max(U,4q) and
 // Y = U'+2q-V <= max(U,4q) stay below 2^64 and every value remains congruent to the true transform; the
 // final BRedAdd is canonical for any 64-bit word.  Hence NTT(x) of the reference equals the canonical
 // negacyclic transform of (x mod q) for every input, and ANY exact lazy butterfly followed by a canonical
-// reduction is bit-identical.  The two below use Shoup/Harvey multiplication by the twiddle w in plain
-// form with ws = floor(w * 2^64 / q); they need 5-6 instead of 9 wide multiplies.
+// reduction is bit-identical.  The inverse transform (InvButterfly, ntt.go:43-50) has the same property
+// only while no sum wraps, which holds when every input word is <= 2q (values then stay in [0,2q] and the
+// final MRed by N^-1 is canonical); the kernels check that per limb and fall back to the literal
+// butterflies otherwise.
+//
+// The fast butterflies multiply by the twiddle w in plain (non-Montgomery) form with the Shoup constant
+// ws = floor(w * 2^64 / q): T = w*Y - Qh*q where Qh ~ floor(ws*Y / 2^64).
 LG_DEV u64 mul_wide(u32 a, u32 b) {
     u64 r;
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
@@ -123,26 +128,110 @@ LG_DEV u64 mad_wide(u32 a, u32 b, u64 c) {
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
     return r;
 }
-// q < 2^62, values kept in [0,4q): exact quotient floor(ws*Y/2^64) => T = w*Y - Q*q in [0,2q)
-LG_DEV void butterfly_fwd_4q(u64& X, u64& Y, u64 w, u64 ws, u64 q, u64 twoq) {
-    u64 x = X;
-    if (x >= twoq) x -= twoq;
-    const u64 qh = mul_hi(ws, Y);
-    const u64 t = mul_lo(w, Y) - mul_lo(qh, q);
-    X = x + t;
-    Y = x + twoq - t;
+LG_DEV u32 mad_lo32(u32 a, u32 b, u32 c) {
+    u32 r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
 }
-// q < 2^56: the quotient is taken from the three high partial products only (at most 2 too small, so
-// T = w*Y - Q*q is in [0,4q)) and no conditional subtraction is made: a value grows by at most 4q per
-// stage, 16 stages add < 64q < 2^62 to inputs that the load clamps below 2^63.  Y may be any 64-bit word.
-LG_DEV void butterfly_fwd_free(u64& X, u64& Y, u64 w, u64 ws, u64 q, u64 fourq) {
-    const u32 a0 = (u32)ws, a1 = (u32)(ws >> 32), b0 = (u32)Y, b1 = (u32)(Y >> 32);
-    const u64 m1 = mul_wide(a1, b0), m2 = mul_wide(a0, b1);
-    const u64 qh = mad_wide(a1, b1, (m1 >> 32)) + (m2 >> 32);
-    const u64 t = mul_lo(w, Y) - mul_lo(qh, q);
+// Quotient estimate from the three high partial products of ws*y (the low x low product and the carries of
+// the low halves of the cross products are dropped): at most 2 below floor(ws*y/2^64), for any 64-bit y.
+LG_DEV u64 qhat3(u64 ws, u64 y) {
+    const u32 a0 = (u32)ws, a1 = (u32)(ws >> 32), b0 = (u32)y, b1 = (u32)(y >> 32);
+    const u64 m1 = mul_wide(a1, b0), m2 = mul_wide(a0, b1), p = mul_wide(a1, b1);
+    u32 lo, hi;
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %2, %3;\n\taddc.u32 %1, %5, 0;\n\tadd.cc.u32 %0, t, %4;\n\taddc.u32 %1, %1, 0;\n\t}"
+        : "=r"(lo), "=&r"(hi)
+        : "r"((u32)(m1 >> 32)), "r"((u32)p), "r"((u32)(m2 >> 32)), "r"((u32)(p >> 32)));
+    return ((u64)hi << 32) | lo;
+}
+// w*y + qh*nq (mod 2^64) with nq = -q: one multiply-add chain, no separate subtraction
+LG_DEV u64 shoup_tail(u64 w, u64 y, u64 qh, u64 nq) {
+    const u32 w0 = (u32)w, w1 = (u32)(w >> 32), b0 = (u32)y, b1 = (u32)(y >> 32);
+    const u32 h0 = (u32)qh, h1 = (u32)(qh >> 32), n0 = (u32)nq, n1 = (u32)(nq >> 32);
+    u64 t = mul_wide(w0, b0);
+    t = mad_wide(h0, n0, t);
+    u32 th = (u32)(t >> 32);
+    th = mad_lo32(w0, b1, th);
+    th = mad_lo32(w1, b0, th);
+    th = mad_lo32(h0, n1, th);
+    th = mad_lo32(h1, n0, th);
+    return ((u64)th << 32) | (u32)t;
+}
+// w*y mod q up to a multiple of q: in [0,4q) for any 64-bit y (q < 2^62)
+LG_DEV u64 shoup3(u64 w, u64 ws, u64 y, u64 nq) { return shoup_tail(w, y, qhat3(ws, y), nq); }
+// exact quotient: in [0,2q)
+LG_DEV u64 shoup_exact(u64 w, u64 ws, u64 y, u64 nq) { return shoup_tail(w, y, mul_hi(ws, y), nq); }
+
+// q < 2^56, no conditional subtraction at all: a value grows by at most 4q per stage, 16 stages add
+// < 64q < 2^62 to inputs that the load clamps below 2^63.  Y may be any 64-bit word.
+LG_DEV void butterfly_fwd_free(u64& X, u64& Y, u64 w, u64 ws, u64 nq, u64 fourq) {
+    const u64 t = shoup3(w, ws, Y, nq);
     const u64 x = X;
     X = x + t;
     Y = x + fourq - t;
+}
+// q < 2^61, values kept in [0,8q): X is brought below 4q, T is in [0,4q)
+LG_DEV void butterfly_fwd_8q(u64& X, u64& Y, u64 w, u64 ws, u64 nq, u64 fourq) {
+    const u64 t = shoup3(w, ws, Y, nq);
+    u64 x = X;
+    if (x >= fourq) x -= fourq;
+    X = x + t;
+    Y = x + fourq - t;
+}
+// Gentleman-Sande, q < 2^46 and inputs <= 2q: the sum path is never reduced (values double per stage,
+// <= 4q*2^s after stage s < 2^63), m = q << (s+1) bounds Y before stage s so the difference stays positive.
+LG_DEV void butterfly_inv_free(u64& X, u64& Y, u64 w, u64 ws, u64 nq, u64 m) {
+    const u64 s = X + Y;
+    const u64 d = X + m - Y;
+    X = s;
+    Y = shoup3(w, ws, d, nq);
+}
+// Gentleman-Sande, q < 2^61, values kept in [0,4q)
+LG_DEV void butterfly_inv_4q(u64& X, u64& Y, u64 w, u64 ws, u64 nq, u64 fourq) {
+    u64 s = X + Y;
+    const u64 d = X + fourq - Y;
+    if (s >= fourq) s -= fourq;
+    X = s;
+    Y = shoup3(w, ws, d, nq);
+}
+
+// ---- FP64-assisted quotient (moduli below 3*2^44, values below 2^52) ------------------------------------
+// B200 has a full-rate FP64 pipe next to the integer multiplier, so the Shoup quotient can be taken there:
+// with wd = RD(floor(w*2^64/q)) * 2^-64 <= w/q (absolute deficit < 2^-52) and cw = RD(2^52 - 2^52*wd),
+//   qd = RD((2^52 + y) * wd + cw) = 2^52 + floor(y*wd - e),  0 <= e < 1      (one DFMA, round-down)
+// holds the quotient estimate Qh = floor(y*w/q) - {0..3} in its mantissa for any y < 2^52, so
+// T = w*y - Qh*q is in [0,4q).  The exponent bits are cancelled by the constant c0 = -((0x43300000*nq0) << 32)
+// folded into the first multiply-add, which leaves 2 wide + 4 narrow integer multiplies per product.
+LG_DEV double shoup_cw(double wd) { return __fma_rd(-4503599627370496.0, wd, 4503599627370496.0); }
+LG_DEV u64 shoup_f64_c0(u64 nq) { return (u64)(0u - 0x43300000u * (u32)nq) << 32; }
+LG_DEV u64 shoup_f64(u64 w, double wd, double cw, u64 y, u64 nq, u64 c0) {
+    const u32 b0 = (u32)y, b1 = (u32)(y >> 32);
+    const double qd = __fma_rd(__hiloint2double((int)(b1 | 0x43300000u), (int)b0), wd, cw);
+    const u32 h0 = (u32)__double2loint(qd), h1 = (u32)__double2hiint(qd);
+    const u32 w0 = (u32)w, w1 = (u32)(w >> 32), n0 = (u32)nq, n1 = (u32)(nq >> 32);
+    u64 t = mad_wide(w0, b0, c0);
+    t = mad_wide(h0, n0, t);
+    u32 th = (u32)(t >> 32);
+    th = mad_lo32(w0, b1, th);
+    th = mad_lo32(w1, b0, th);
+    th = mad_lo32(h0, n1, th);
+    th = mad_lo32(h1, n0, th);
+    return ((u64)th << 32) | (u32)t;
+}
+// forward, no conditional subtraction: inputs below 2^50, 16 stages add < 64q < 2^52 - 2^50
+LG_DEV void butterfly_fwd_f64(u64& X, u64& Y, u64 w, double wd, double cw, u64 nq, u64 fourq, u64 c0) {
+    const u64 t = shoup_f64(w, wd, cw, Y, nq, c0);
+    const u64 x = X;
+    X = x + t;
+    Y = x + fourq - t;
+}
+// Gentleman-Sande, values kept in [0,4q): the difference is below 8q < 2^52
+LG_DEV void butterfly_inv_f64(u64& X, u64& Y, u64 w, double wd, double cw, u64 nq, u64 fourq, u64 c0) {
+    u64 s = X + Y;
+    const u64 d = X + fourq - Y;
+    if (s >= fourq) s -= fourq;
+    X = s;
+    Y = shoup_f64(w, wd, cw, d, nq, c0);
 }
 
 // InvButterfly, ring/ntt.go:43-50

@@ -1,25 +1,28 @@
-// ntt.cu -- kernel family K1: batched per-limb negacyclic NTT / InvNTT.
+// ntt.cu -- kernel family K1: batched per-limb negacyclic NTT / InvNTT, and the key-switch digit loop
+// fused with the last NTT phase.
 //
 // Replaces ring/ntt.go:53-139 of the reference (Cooley-Tukey forward with lazy butterflies and a
 // final BRedAdd; Gentleman-Sande inverse with a final MRed by N^-1).
 //
-// Bit-exactness.  InvNTT keeps every radix-2 butterfly literal (InvButterfly can wrap 64 bits on
-// out-of-range input, so its result is formula-specific).  The forward transform of the reference never
-// wraps (see modarith.cuh), so its output is the canonical transform of (x mod q) for EVERY 64-bit
-// input; the forward kernels therefore use cheaper exact Shoup/Harvey butterflies (5-6 wide multiplies
-// instead of 9) and still match the reference bit for bit, including on the unreduced words its own
-// benchmarks feed (tests: "words" cases).  LATTIGPU_LITERAL_NTT=1 selects the literal forward
-// butterflies instead (A/B and cross-check).
+// Bit-exactness (see modarith.cuh).  The forward transform of the reference never wraps, so its output is
+// the canonical transform of (x mod q) for EVERY 64-bit input; the forward kernels use exact lazy
+// Shoup butterflies (9 32x32 multiplies, 16 instructions) and still match the reference bit for bit,
+// including on the unreduced words its own benchmarks feed (tests: "words" cases).  The inverse transform
+// has that property only while every input word is <= 2q: callers either know that (outputs of our own
+// canonical kernels) or run lg_launch_range_flags first, and flagged limbs take the literal InvButterfly.
+// Moduli >= 2^61 and LATTIGPU_LITERAL_NTT=1 use the literal butterflies throughout (A/B and cross-check).
 //
 // Schedule (N = 2^logN, one limb = N words, grid = batch x tiles x limbs -- batch fastest, so the CTAs that
 // share a limb's twiddles and key tile run together and hit L2):
 //   logN <= 11 : one CTA per limb, radix-2 stages in shared memory.
-//   logN >= 12 : two phases of register-resident radix-16 blocks
-//     "strided" phase : the top L = logN-8 stages; a CTA owns all 2^L rows of
-//                       W = 4096/2^L adjacent columns (coalesced 8*W-byte rows),
-//     "contig"  phase : the low 8 stages on 16 contiguous 256-word segments.
-//   Each thread keeps 16 coefficients in registers for 4 stages, then the CTA
-//   re-distributes them through (padded, conflict-free) shared memory.
+//   logN >= 12 : two phases of register-resident radix-16 blocks (16 coefficients per thread, 4 stages,
+//                8 independent butterflies per stage)
+//     "strided" phase : the top L = logN-8 stages; a 256-thread CTA owns all 2^L rows of
+//                       W = 4096/2^L adjacent columns (coalesced 8*W-byte rows) and re-distributes
+//                       through shared memory once,
+//     "contig"  phase : the low 8 stages on contiguous 256-word segments; 16 threads own a segment, so
+//                       the exchange is warp-synchronous (no CTA barrier) and every thread ends with 16
+//                       consecutive words that move with 256-bit loads/stores.
 //   Twiddle index for the butterfly on (j, j+2^s): (N >> (s+1)) + (j >> (s+1))
 //   in both directions (ring/ntt.go:74 and :120).
 #include <stdlib.h>
@@ -29,139 +32,171 @@
 
 namespace {
 
-// forward butterfly flavours
-enum { BF_LITERAL = 0, BF_4Q = 1, BF_FREE = 2 };
+// butterfly flavours: forward LAZY = values in [0,8q), inverse LAZY = values in [0,4q)
+// forward M_F64 = M_FREE with the quotient taken on the FP64 pipe (moduli below 3*2^44)
+enum { M_LITERAL = 0, M_FREE = 1, M_LAZY = 2, M_F64 = 3 };
 
-// ---- register blocks --------------------------------------------------------
-// x[r] holds the coefficient at global index j0 + r*2^s (bits [s,s+4) of j0 are
-// zero); twbase = (N + j0) >> s.  Stage u pairs r and r + 2^u (stride 2^(s+u)).
+LG_DEV int fwd_mode(u64 q) {
+    return q < (3ull << 44) ? M_F64 : (q < (1ull << 56) ? M_FREE : (q < (1ull << 61) ? M_LAZY : M_LITERAL));
+}
+LG_DEV int inv_mode(u64 q) { return q < (1ull << 46) ? M_FREE : (q < (1ull << 61) ? M_LAZY : M_LITERAL); }
 
-struct FwdConst {
-    u64 q, qinv, twoq, fourq;
-    const u64* tw;   // literal: nttPsi (Montgomery).  fast: psi_w
-    const u64* tws;  // fast: psi_ws
+struct TwConst {
+    u64 q, qinv, twoq, fourq, nq;
+    const u64* tw;   // literal: nttPsi / nttPsiInv (Montgomery).  fast: the plain-domain table
+    const u64* tws;  // fast: Shoup constants (M_F64: the bits of the double table psi_wd)
+    u64 c0;          // M_F64: shoup_f64_c0(nq)
 };
 
+// 256-bit global access (sm_100: LDG.E.256 / STG.E.256); p must be 32-byte aligned
+LG_DEV void ld256(u64 (&v)[4], const u64* p) {
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+LG_DEV void ld256_nc(u64 (&v)[4], const u64* p) {
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+LG_DEV void st256(u64* p, u64 a, u64 b, u64 c, u64 d) {
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+// NG consecutive twiddles; VEC = the run is NG*8-byte aligned
 template <bool VEC, int NG>
 LG_DEV void load_tw(u64 (&w)[8], const u64* __restrict__ t, u32 base) {
-    if (VEC && NG >= 2) {
+    if (VEC && NG >= 4) {
 #pragma unroll
-        for (int g = 0; g < NG; g += 2) {
-            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(t + base + g));
-            w[g] = v.x;
-            w[g + 1] = v.y;
+        for (int g = 0; g < NG; g += 4) {
+            u64 v[4];
+            ld256_nc(v, t + base + g);
+            w[g] = v[0];
+            w[g + 1] = v[1];
+            w[g + 2] = v[2];
+            w[g + 3] = v[3];
         }
+    } else if (VEC && NG == 2) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(t + base));
+        w[0] = v.x;
+        w[1] = v.y;
     } else {
 #pragma unroll
         for (int g = 0; g < NG; ++g) w[g] = __ldg(t + base + g);
     }
 }
 
+// ---- register blocks --------------------------------------------------------
+// x[r] holds the coefficient at global index j0 + r*2^s (bits [s,s+4) of j0 are
+// zero); twbase = (N + j0) >> s.  Stage u pairs r and r + 2^u (stride 2^(s+u)).
 template <int U, bool VEC, int MODE>
-LG_DEV void fwd_stage(u64 (&x)[16], const FwdConst& c, u32 twbase) {
+LG_DEV void fwd_stage(u64 (&x)[16], const TwConst& c, u32 twbase) {
     constexpr int NG = 16 >> (U + 1);
     const u32 base = twbase >> (U + 1);
     u64 w[8], ws[8];
     load_tw<VEC, NG>(w, c.tw, base);
-    if (MODE != BF_LITERAL) load_tw<VEC, NG>(ws, c.tws, base);
+    if (MODE != M_LITERAL) load_tw<VEC, NG>(ws, c.tws, base);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const double wd = __longlong_as_double((long long)ws[g]);
+        const double cw = (MODE == M_F64) ? shoup_cw(wd) : 0.0;
+#pragma unroll
+        for (int k = 0; k < (1 << U); ++k) {
+            const int r = (g << (U + 1)) + k;
+            if (MODE == M_LITERAL)
+                butterfly_fwd(x[r], x[r + (1 << U)], w[g], c.q, c.qinv, c.twoq);
+            else if (MODE == M_FREE)
+                butterfly_fwd_free(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, c.fourq);
+            else if (MODE == M_F64)
+                butterfly_fwd_f64(x[r], x[r + (1 << U)], w[g], wd, cw, c.nq, c.fourq, c.c0);
+            else
+                butterfly_fwd_8q(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, c.fourq);
+        }
+    }
+}
+// stages UHI, UHI-1, ..., 0
+template <int UHI, bool VEC, int MODE>
+LG_DEV void fwd_stages(u64 (&x)[16], const TwConst& c, u32 twbase) {
+    if (UHI >= 3) fwd_stage<3, VEC, MODE>(x, c, twbase);
+    if (UHI >= 2) fwd_stage<2, VEC, MODE>(x, c, twbase);
+    if (UHI >= 1) fwd_stage<1, VEC, MODE>(x, c, twbase);
+    fwd_stage<0, VEC, MODE>(x, c, twbase);
+}
+
+// `stage` = index (0 = first stage of the inverse transform) of this block's u = 0 stage
+template <int U, bool VEC, int MODE>
+LG_DEV void inv_stage(u64 (&x)[16], const TwConst& c, u32 twbase, u32 stage) {
+    constexpr int NG = 16 >> (U + 1);
+    const u32 base = twbase >> (U + 1);
+    u64 w[8], ws[8];
+    load_tw<VEC, NG>(w, c.tw, base);
+    if (MODE != M_LITERAL) load_tw<VEC, NG>(ws, c.tws, base);
+    const u64 m = c.q << (stage + U + 1);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
 #pragma unroll
         for (int k = 0; k < (1 << U); ++k) {
             const int r = (g << (U + 1)) + k;
-            if (MODE == BF_LITERAL)
-                butterfly_fwd(x[r], x[r + (1 << U)], w[g], c.q, c.qinv, c.twoq);
-            else if (MODE == BF_4Q)
-                butterfly_fwd_4q(x[r], x[r + (1 << U)], w[g], ws[g], c.q, c.twoq);
+            if (MODE == M_LITERAL)
+                butterfly_inv(x[r], x[r + (1 << U)], w[g], c.q, c.qinv, c.twoq);
+            else if (MODE == M_FREE)
+                butterfly_inv_free(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, m);
             else
-                butterfly_fwd_free(x[r], x[r + (1 << U)], w[g], ws[g], c.q, c.fourq);
+                butterfly_inv_4q(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, c.fourq);
         }
     }
 }
-
-// stages UHI, UHI-1, ..., ULO
-template <int UHI, int ULO, bool VEC, int MODE>
-LG_DEV void fwd_stages(u64 (&x)[16], const FwdConst& c, u32 twbase) {
-    if (UHI >= 3 && ULO <= 3) fwd_stage<3, VEC, MODE>(x, c, twbase);
-    if (UHI >= 2 && ULO <= 2) fwd_stage<2, VEC, MODE>(x, c, twbase);
-    if (UHI >= 1 && ULO <= 1) fwd_stage<1, VEC, MODE>(x, c, twbase);
-    if (UHI >= 0 && ULO <= 0) fwd_stage<0, VEC, MODE>(x, c, twbase);
+// stages 0, 1, ..., UHI
+template <int UHI, bool VEC, int MODE>
+LG_DEV void inv_stages(u64 (&x)[16], const TwConst& c, u32 twbase, u32 stage) {
+    inv_stage<0, VEC, MODE>(x, c, twbase, stage);
+    if (UHI >= 1) inv_stage<1, VEC, MODE>(x, c, twbase, stage);
+    if (UHI >= 2) inv_stage<2, VEC, MODE>(x, c, twbase, stage);
+    if (UHI >= 3) inv_stage<3, VEC, MODE>(x, c, twbase, stage);
 }
-
-template <int ULO, int UHI, bool VEC>
-LG_DEV void inv_stages(u64 (&x)[16], const u64* __restrict__ tw, u32 twbase, u64 q, u64 qinv, u64 twoq) {
-#pragma unroll
-    for (int u = ULO; u <= UHI; ++u) {
-        const u32 base = twbase >> (u + 1);
-        const int ngroups = 16 >> (u + 1);
-        u64 w[8];
-        if (VEC && ngroups >= 2) {
-#pragma unroll
-            for (int g = 0; g < ngroups; g += 2) {
-                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tw + base + g));
-                w[g] = v.x;
-                w[g + 1] = v.y;
-            }
-        } else {
-#pragma unroll
-            for (int g = 0; g < ngroups; ++g) w[g] = __ldg(tw + base + g);
-        }
-#pragma unroll
-        for (int g = 0; g < ngroups; ++g) {
-#pragma unroll
-            for (int k = 0; k < (1 << u); ++k) {
-                const int r = (g << (u + 1)) + k;
-                butterfly_inv(x[r], x[r + (1 << u)], w[g], q, qinv, twoq);
-            }
-        }
-    }
-}
-
-LG_DEV u32 pad16(u32 e) { return e + (e >> 4); }
 
 struct LimbSetup {
     LimbConst c;
     const u64* in;
     u64* out;
-    const u64* tw;
-    u64 ninv;
     int tl;
     bool skip;
 };
 
-template <bool FWD>
 LG_DEV LimbSetup setup_limb(const NttArgs& a) {
     LimbSetup s;
     const int j = blockIdx.z, b = blockIdx.x;
-    s.skip = (j >= a.skip0 && j < a.skip1);
+    if (a.skip_alpha > 0) {
+        const int dg = b / a.skip_div;
+        s.skip = (j < a.skip_nl) && (j >= dg * a.skip_alpha) && (j < (dg + 1) * a.skip_alpha);
+    } else {
+        s.skip = (j >= a.skip0 && j < a.skip1);
+    }
     s.tl = a.map(j);
     s.c = load_limb_const(a.T, s.tl);
-    s.tw = (FWD ? a.T.psi : a.T.psi_inv) + (size_t)s.tl * a.T.N;
-    s.ninv = FWD ? 0 : a.T.ninv[s.tl];
     s.in = a.in + (size_t)b * a.in_bstride + (size_t)j * a.T.N;
     s.out = a.out + (size_t)b * a.out_bstride + (size_t)j * a.T.N;
     return s;
 }
 
-template <int MODE>
-LG_DEV FwdConst fwd_const(const NttArgs& a, const LimbSetup& s) {
-    FwdConst c;
-    c.q = s.c.q;
-    c.qinv = s.c.qinv;
-    c.twoq = 2 * s.c.q;
-    c.fourq = 4 * s.c.q;
-    if (MODE == BF_LITERAL) {
-        c.tw = s.tw;
+template <bool FWD, int MODE>
+LG_DEV TwConst tw_const(const RingTables& T, const LimbConst& lc, int tl) {
+    TwConst c;
+    c.q = lc.q;
+    c.qinv = lc.qinv;
+    c.twoq = 2 * lc.q;
+    c.fourq = 4 * lc.q;
+    c.nq = 0ull - lc.q;
+    const size_t off = (size_t)tl * T.N;
+    c.c0 = shoup_f64_c0(c.nq);
+    if (MODE == M_LITERAL) {
+        c.tw = (FWD ? T.psi : T.psi_inv) + off;
         c.tws = nullptr;
+    } else if (MODE == M_F64) {
+        c.tw = T.psi_w + off;
+        c.tws = T.psi_wd + off;
     } else {
-        c.tw = a.T.psi_w + (size_t)s.tl * a.T.N;
-        c.tws = a.T.psi_ws + (size_t)s.tl * a.T.N;
+        c.tw = (FWD ? T.psi_w : T.psi_inv_w) + off;
+        c.tws = (FWD ? T.psi_ws : T.psi_inv_ws) + off;
     }
     return c;
 }
-
-// which butterfly a limb may use: BF_FREE needs q < 2^56 (16 stages x 4q < 2^62), BF_4Q needs 4q < 2^64
-LG_DEV int fast_mode(u64 q) { return q < (1ull << 56) ? BF_FREE : BF_4Q; }
 
 // ---- forward, strided phase: stages 1..L -----------------------------------
 template <int L, int MODE>
@@ -169,31 +204,37 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
     constexpr int G = 1 << (L - 4);  // threads per column
     constexpr int W = 256 / G;       // columns per CTA
     constexpr int N2 = L - 4;        // stages of the second register block
-    const FwdConst c = fwd_const<MODE>(a, s);
+    const TwConst c = tw_const<true, MODE>(a.T, s.c, s.tl);
     const u32 LB = a.T.logN - L;
     const int t = threadIdx.x, col = t % W, g = t / W;
     const size_t colg = (size_t)blockIdx.y * W + col;
     u64 x[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(g + r * G) << LB) + colg];
-    if (MODE == BF_FREE) {  // growth headroom: everything below 2^63 (canonical inputs never take this branch)
+    if (MODE == M_FREE) {  // growth headroom: everything below 2^63 (canonical inputs never take this branch)
 #pragma unroll
         for (int r = 0; r < 16; ++r)
             if (x[r] >> 63) x[r] = bred_add(x[r], c.q, s.c.u0);
     }
-    if (MODE == BF_4Q) {  // Harvey's invariant: values in [0,4q)
+    if (MODE == M_F64) {  // values below 2^52 throughout: inputs below 2^50 (canonical inputs never take this branch)
 #pragma unroll
         for (int r = 0; r < 16; ++r)
-            if (x[r] >= c.fourq) x[r] = bred_add(x[r], c.q, s.c.u0);
+            if (x[r] >> 50) x[r] = bred_add(x[r], c.q, s.c.u0);
     }
-    fwd_stages<3, 0, false, MODE>(x, c, 16u);
+    if (MODE == M_LAZY) {  // invariant: values in [0,8q)
+        const u64 eightq = 8 * c.q;
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (x[r] >= eightq) x[r] = bred_add(x[r], c.q, s.c.u0);
+    }
+    fwd_stages<3, false, MODE>(x, c, 16u);
     if (N2 > 0) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) sm[(g + r * G) * W + col] = x[r];
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = sm[(16 * g + r) * W + col];
-        fwd_stages<(N2 > 0 ? N2 - 1 : 0), 0, false, MODE>(x, c, (1u << L) + 16u * g);
+        fwd_stages<(N2 > 0 ? N2 - 1 : 0), false, MODE>(x, c, (1u << L) + 16u * g);
 #pragma unroll
         for (int r = 0; r < 16; ++r) s.out[((size_t)(16 * g + r) << LB) + colg] = x[r];
     } else {
@@ -205,151 +246,405 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
 template <int L, bool LITERAL>
 __global__ void __launch_bounds__(256) ntt_fwd_strided(const NttArgs a) {
     __shared__ u64 sm[(L - 4) > 0 ? 4096 : 1];
-    const LimbSetup s = setup_limb<true>(a);
+    const LimbSetup s = setup_limb(a);
     if (s.skip) return;
-    if (LITERAL)
-        fwd_strided_body<L, BF_LITERAL>(a, s, sm);
-    else if (fast_mode(s.c.q) == BF_FREE)
-        fwd_strided_body<L, BF_FREE>(a, s, sm);
+    const int mode = LITERAL ? M_LITERAL : fwd_mode(s.c.q);
+    if (mode == M_F64)
+        fwd_strided_body<L, M_F64>(a, s, sm);
+    else if (mode == M_FREE)
+        fwd_strided_body<L, M_FREE>(a, s, sm);
+    else if (mode == M_LAZY)
+        fwd_strided_body<L, M_LAZY>(a, s, sm);
     else
-        fwd_strided_body<L, BF_4Q>(a, s, sm);
+        fwd_strided_body<L, M_LITERAL>(a, s, sm);
 }
 
-// ---- forward, contiguous phase: last 8 stages + BRedAdd ---------------------
+// ---- contiguous phase geometry ------------------------------------------------
+// 128-thread CTA = 4 warps = 8 segments of 256 words (tile of 2048 words); the 16 threads of a segment
+// exchange through their own 16 x 18-word shared region (row stride 18 keeps both the 64-bit column
+// accesses and the 128-bit row accesses conflict-free).
+#define CONTIG_THREADS 128
+#define CONTIG_TILE 2048u
+#define SEG_SM 288  // 16 rows x 18 words
+
+struct SegPos {
+    u32 segbase;  // first word of this thread's segment within the limb
+    u32 cc;       // position of the thread within the segment (0..15)
+    u64* sm;      // the segment's shared region
+};
+LG_DEV SegPos seg_pos(u64* smem) {
+    SegPos p;
+    const u32 t = threadIdx.x, sg = t >> 4;
+    p.cc = t & 15;
+    p.segbase = blockIdx.y * CONTIG_TILE + sg * 256u;
+    p.sm = smem + sg * SEG_SM;
+    return p;
+}
+// column layout x[r] <-> word cc + 16r ; row layout x[r] <-> word 16cc + r
+LG_DEV void seg_store_cols(const SegPos& p, const u64 (&x)[16]) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) p.sm[18 * r + p.cc] = x[r];
+}
+LG_DEV void seg_load_cols(const SegPos& p, u64 (&x)[16]) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = p.sm[18 * r + p.cc];
+}
+LG_DEV void seg_store_rows(const SegPos& p, const u64 (&x)[16]) {
+    ulonglong2* row = reinterpret_cast<ulonglong2*>(p.sm + 18 * p.cc);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) row[r] = make_ulonglong2(x[2 * r], x[2 * r + 1]);
+}
+LG_DEV void seg_load_rows(const SegPos& p, u64 (&x)[16]) {
+    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(p.sm + 18 * p.cc);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const ulonglong2 v = row[r];
+        x[2 * r] = v.x;
+        x[2 * r + 1] = v.y;
+    }
+}
+
+// forward contiguous phase of one segment: reads in[segbase + cc + 16r], leaves the (lazy, unreduced)
+// transform of words segbase + 16cc + r in x[r]
 template <int MODE>
-LG_DEV void fwd_contig_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
-    const FwdConst c = fwd_const<MODE>(a, s);
-    const u32 N = a.T.N;
-    const u32 t = threadIdx.x, seg = t >> 4, cc = t & 15;
-    const u32 base = blockIdx.y * 4096u;
-    const u32 j0 = base + seg * 256u + cc;
-    u64 x[16];
+LG_DEV void fwd_contig_seg(u64 (&x)[16], const TwConst& c, u32 N, const u64* __restrict__ in, const SegPos& p) {
+    const u32 j0 = p.segbase + p.cc;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = s.in[j0 + 16 * r];
-    fwd_stages<3, 0, false, MODE>(x, c, (N + j0) >> 4);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + cc + 16 * r)] = x[r];
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + 16 * cc + r)];
-    const u32 j1 = base + seg * 256u + 16 * cc;
-    fwd_stages<3, 0, true, MODE>(x, c, N + j1);
-    // ring/ntt.go:83-85
-#pragma unroll
-    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + 16 * cc + r)] = bred_add(x[r], c.q, s.c.u0);
-    __syncthreads();
+    for (int r = 0; r < 16; ++r) x[r] = in[j0 + 16 * r];
+    fwd_stages<3, false, MODE>(x, c, (N + j0) >> 4);
+    __syncwarp();
+    seg_store_cols(p, x);
+    __syncwarp();
+    seg_load_rows(p, x);
+    fwd_stages<3, true, MODE>(x, c, N + p.segbase + 16 * p.cc);
 }
 
-// MAC = true fuses the key-switch multiply-accumulate into the epilogue (NttMac).
-template <bool MAC, bool LITERAL>
-__global__ void __launch_bounds__(256) ntt_fwd_contig(const NttArgs a) {
-    __shared__ u64 sm[4096 + 256];
-    const LimbSetup s = setup_limb<true>(a);
-    if (!MAC && s.skip) return;
+// MAC = true: legacy per-digit key-switch epilogue (NttMac), used by the limb-sharded driver.
+template <bool MAC, int MODE>
+LG_DEV void fwd_contig_body(const NttArgs& a, const LimbSetup& s, const SegPos& p) {
     const u32 N = a.T.N;
     const u64 q = s.c.q, qinv = s.c.qinv;
-    const u32 t = threadIdx.x;
-    const u32 base = blockIdx.y * 4096u;
-    if (!(MAC && s.skip)) {
-        if (LITERAL)
-            fwd_contig_body<BF_LITERAL>(a, s, sm);
-        else if (fast_mode(q) == BF_FREE)
-            fwd_contig_body<BF_FREE>(a, s, sm);
-        else
-            fwd_contig_body<BF_4Q>(a, s, sm);
+    const u32 e0 = p.segbase + 16 * p.cc;
+    u64 x[16];
+    if (MAC && s.skip) {
+        const int j = blockIdx.z, b = blockIdx.x;
+        const u64* cx = a.mac.cx + (size_t)b * a.mac.cx_bs + (size_t)j * N + e0;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            u64 v[4];
+            ld256(v, cx + 4 * h);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[4 * h + e] = v[e];
+        }
+    } else {
+        const TwConst c = tw_const<true, MODE>(a.T, s.c, s.tl);
+        fwd_contig_seg<MODE>(x, c, N, s.in, p);
     }
     if (!MAC) {
+        // ring/ntt.go:83-85
 #pragma unroll
-        for (int k = 0; k < 16; ++k) s.out[base + t + 256u * k] = sm[pad16(t + 256u * k)];
+        for (int h = 0; h < 4; ++h)
+            st256(s.out + e0 + 4 * h, bred_add(x[4 * h], q, s.c.u0), bred_add(x[4 * h + 1], q, s.c.u0),
+                  bred_add(x[4 * h + 2], q, s.c.u0), bred_add(x[4 * h + 3], q, s.c.u0));
     } else {
         const int j = blockIdx.z, b = blockIdx.x;
-        const size_t ko = (size_t)s.tl * N + base, ao = (size_t)b * a.mac.acc_bs + (size_t)j * N + base;
-        const ulonglong2* e0 = reinterpret_cast<const ulonglong2*>(a.mac.evk0 + ko);
-        const ulonglong2* e1 = reinterpret_cast<const ulonglong2*>(a.mac.evk1 + ko);
-        ulonglong2* p0 = reinterpret_cast<ulonglong2*>(a.mac.acc0 + ao);
-        ulonglong2* p1 = reinterpret_cast<ulonglong2*>(a.mac.acc1 + ao);
-        const ulonglong2* cx = reinterpret_cast<const ulonglong2*>(a.mac.cx + (size_t)b * a.mac.cx_bs + (size_t)j * N + base);
-#pragma unroll 4
-        for (int k = 0; k < 8; ++k) {
-            const u32 v = t + 256u * k;  // pair index: elements 2v, 2v+1
-            ulonglong2 d;
-            if (s.skip) {
-                d = cx[v];
-            } else {
-                d.x = sm[pad16(2 * v)];
-                d.y = sm[pad16(2 * v + 1)];
+        const size_t ko = (size_t)s.tl * N + e0, ao = (size_t)b * a.mac.acc_bs + (size_t)j * N + e0;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            u64 k0[4], k1[4], r0[4], r1[4];
+            ld256_nc(k0, a.mac.evk0 + ko + 4 * h);
+            ld256_nc(k1, a.mac.evk1 + ko + 4 * h);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                r0[e] = mred(k0[e], x[4 * h + e], q, qinv);
+                r1[e] = mred(k1[e], x[4 * h + e], q, qinv);
             }
-            const ulonglong2 k0 = __ldg(e0 + v), k1 = __ldg(e1 + v);
-            ulonglong2 r0, r1;
-            r0.x = mred(k0.x, d.x, q, qinv);
-            r0.y = mred(k0.y, d.y, q, qinv);
-            r1.x = mred(k1.x, d.x, q, qinv);
-            r1.y = mred(k1.y, d.y, q, qinv);
             if (!a.mac.first) {
-                const ulonglong2 o0 = p0[v], o1 = p1[v];
-                r0.x += o0.x;
-                r0.y += o0.y;
-                r1.x += o1.x;
-                r1.y += o1.y;
+                u64 o0[4], o1[4];
+                ld256(o0, a.mac.acc0 + ao + 4 * h);
+                ld256(o1, a.mac.acc1 + ao + 4 * h);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    r0[e] += o0[e];
+                    r1[e] += o1[e];
+                }
             }
             if (a.mac.reduce) {
-                r0.x = bred_add(r0.x, q, s.c.u0);
-                r0.y = bred_add(r0.y, q, s.c.u0);
-                r1.x = bred_add(r1.x, q, s.c.u0);
-                r1.y = bred_add(r1.y, q, s.c.u0);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    r0[e] = bred_add(r0[e], q, s.c.u0);
+                    r1[e] = bred_add(r1[e], q, s.c.u0);
+                }
             }
-            p0[v] = r0;
-            p1[v] = r1;
+            st256(a.mac.acc0 + ao + 4 * h, r0[0], r0[1], r0[2], r0[3]);
+            st256(a.mac.acc1 + ao + 4 * h, r1[0], r1[1], r1[2], r1[3]);
         }
     }
 }
 
-// ---- inverse, contiguous phase: first 8 stages -------------------------------
-__global__ void __launch_bounds__(256) ntt_inv_contig(const NttArgs a) {
-    __shared__ u64 sm[4096 + 256];
-    const LimbSetup s = setup_limb<false>(a);
-    if (s.skip) return;
-    const u32 N = a.T.N;
-    const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
-    const u32 t = threadIdx.x, seg = t >> 4, c = t & 15;
-    const u32 base = blockIdx.y * 4096u;
+template <bool MAC, bool LITERAL>
+__global__ void __launch_bounds__(CONTIG_THREADS) ntt_fwd_contig(const NttArgs a) {
+    __shared__ __align__(16) u64 smem[8 * SEG_SM];
+    const LimbSetup s = setup_limb(a);
+    if (!MAC && s.skip) return;
+    const SegPos p = seg_pos(smem);
+    const int mode = LITERAL ? M_LITERAL : fwd_mode(s.c.q);
+    if (mode == M_F64)
+        fwd_contig_body<MAC, M_F64>(a, s, p);
+    else if (mode == M_FREE)
+        fwd_contig_body<MAC, M_FREE>(a, s, p);
+    else if (mode == M_LAZY)
+        fwd_contig_body<MAC, M_LAZY>(a, s, p);
+    else
+        fwd_contig_body<MAC, M_LITERAL>(a, s, p);
+}
+
+// ---- key-switch digit loop fused with the contiguous phase ---------------------
+// Everything the digit loop re-reads is staged once: the tile's twiddles live in shared memory for all
+// digits (thread-private slots for the second register block, one copy per segment for the first), and the
+// next digit's tile is fetched with cp.async into the other half of a double buffer while the current one
+// is transformed; the buffer a digit was read from then serves as its exchange space.
+//   shared per CTA: 2 x 16 KiB tiles + 30 KiB private twiddles + 2 KiB segment twiddles = 64 KiB (3 CTAs/SM)
+#define KS_SMEM_WORDS (2 * 2048 + 30 * CONTIG_THREADS + 8 * 32)
+
+LG_DEV void cp_async16(u64* smem_dst, const u64* gsrc) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+LG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+LG_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// a warp fetches its own two segments (512 words) of a tile
+LG_DEV void prefetch_warp_tile(u64* buf, const u64* __restrict__ src_tile) {
+    const u32 lane = threadIdx.x & 31, wbase = (threadIdx.x >> 5) * 512u;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) sm[pad16(t + 256u * k)] = s.in[base + t + 256u * k];
-    __syncthreads();
+    for (int k = 0; k < 8; ++k) {
+        const u32 o = wbase + 2u * (lane + 32u * k);
+        cp_async16(buf + o, src_tile + o);
+    }
+    cp_async_commit();
+}
+
+// stage with twiddles taken from shared memory: w[g] = wp[g*STRIDE], ws[g] = wsp[g*STRIDE]
+template <int U, int STRIDE, int MODE>
+LG_DEV void fwd_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp) {
+    constexpr int NG = 16 >> (U + 1);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const u64 w = wp[g * STRIDE];
+        const u64 ws = (MODE != M_LITERAL) ? wsp[g * STRIDE] : 0ull;
+        const double wd = __longlong_as_double((long long)ws);
+        const double cw = (MODE == M_F64) ? shoup_cw(wd) : 0.0;
+#pragma unroll
+        for (int k = 0; k < (1 << U); ++k) {
+            const int r = (g << (U + 1)) + k;
+            if (MODE == M_LITERAL)
+                butterfly_fwd(x[r], x[r + (1 << U)], w, c.q, c.qinv, c.twoq);
+            else if (MODE == M_FREE)
+                butterfly_fwd_free(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
+            else if (MODE == M_F64)
+                butterfly_fwd_f64(x[r], x[r + (1 << U)], w, wd, cw, c.nq, c.fourq, c.c0);
+            else
+                butterfly_fwd_8q(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
+        }
+    }
+}
+// heap-ordered slots: stage U uses slots [2^(3-U) - 1, 2^(4-U) - 1)
+template <int STRIDE, int MODE>
+LG_DEV void fwd_stages_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp) {
+    fwd_stage_sm<3, STRIDE, MODE>(x, c, wp, wsp);
+    fwd_stage_sm<2, STRIDE, MODE>(x, c, wp + 1 * STRIDE, wsp + 1 * STRIDE);
+    fwd_stage_sm<1, STRIDE, MODE>(x, c, wp + 3 * STRIDE, wsp + 3 * STRIDE);
+    fwd_stage_sm<0, STRIDE, MODE>(x, c, wp + 7 * STRIDE, wsp + 7 * STRIDE);
+}
+
+// LAZYACC: beta * 2q fits 64 bits, so the products are accumulated unreduced (MRedConstant, in (0,2q)).
+template <int MODE, bool LAZYACC>
+LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64* smem) {
+    const u32 N = a.T.N;
+    const int j = blockIdx.z, b = blockIdx.x;
+    const u64 q = lc.q, qinv = lc.qinv;
+    const TwConst c = tw_const<true, MODE>(a.T, lc, tl);
+    const u32 t = threadIdx.x, sg = t >> 4, cc = t & 15;
+    const u32 tile0 = blockIdx.y * CONTIG_TILE;      // first word of the CTA's tile within the limb
+    const u32 segbase = tile0 + sg * 256u;
+    const u32 e0 = segbase + 16 * cc;
+    u64* const tilebuf = smem;                        // [2][2048]
+    u64* const twp = smem + 2 * 2048 + t;             // private slots: w at slot*128, ws at (15+slot)*128
+    u64* const twseg = smem + 2 * 2048 + 30 * CONTIG_THREADS + sg * 32;  // w at [k], ws at [15+k]
+
+    const u64* din = a.D + (size_t)b * a.d_bs + (size_t)j * N + tile0;
+    const int own_i = (j < a.nl) ? j / a.alpha : -1;  // the digit whose own limb this is
+    if (own_i != 0) prefetch_warp_tile(tilebuf, din);
+
+    // twiddles of the tile, once for all digits
+    {
+        u64 w[8];
+        const u32 tb = N + e0;
+#define LG_FILL(U, SLOT)                                                    \
+    load_tw<true, (16 >> (U + 1))>(w, c.tw, tb >> (U + 1));                 \
+    _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[(SLOT + g) * CONTIG_THREADS] = w[g]; \
+    if (MODE != M_LITERAL) {                                                \
+        load_tw<true, (16 >> (U + 1))>(w, c.tws, tb >> (U + 1));            \
+        _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[(15 + SLOT + g) * CONTIG_THREADS] = w[g]; \
+    }
+        LG_FILL(3, 0)
+        LG_FILL(2, 1)
+        LG_FILL(1, 3)
+        LG_FILL(0, 7)
+#undef LG_FILL
+        if (cc < 15) {  // first block: node m = (N + segbase) >> 8 and its 15 descendants in heap order
+            const u32 lvl = 31 - __clz(cc + 1);
+            const u32 idx = (((N + segbase) >> 8) << lvl) + (cc + 1 - (1u << lvl));
+            twseg[cc] = __ldg(c.tw + idx);
+            if (MODE != M_LITERAL) twseg[15 + cc] = __ldg(c.tws + idx);
+        }
+    }
+
+    const u64* key = a.evk + (size_t)tl * N + e0;
+    u64 acc0[16], acc1[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc0[r] = acc1[r] = 0;
+#pragma unroll 1
+    for (int i = 0; i < a.beta; ++i, key += a.evk_ds) {
+        u64 x[16];
+        u64* const buf = tilebuf + (i & 1) * 2048 + sg * 256;
+        cp_async_wait_all();
+        __syncwarp();
+        // fetch the next digit's tile into the other buffer (all its readers passed the barrier above)
+        if (i + 1 < a.beta && i + 1 != own_i)
+            prefetch_warp_tile(tilebuf + ((i + 1) & 1) * 2048, din + (size_t)(i + 1) * a.d_ds);
+        if (i == own_i) {  // ckks/evaluator.go:1579-1584, bfv/evaluator.go:776-780
+            const u64* cx = a.cx + (size_t)b * a.cx_bs + (size_t)j * N + e0;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                u64 v[4];
+                ld256(v, cx + 4 * h);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[4 * h + e] = v[e];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = buf[cc + 16 * r];
+            fwd_stages_sm<1, MODE>(x, c, twseg, twseg + 15);
+            __syncwarp();
+            // exchange in place, XOR-swizzled (word 16r+cc at 16r + (cc^r)): conflict-free both ways
+#pragma unroll
+            for (int r = 0; r < 16; ++r) buf[16 * r + (cc ^ r)] = x[r];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = buf[16 * cc + (r ^ cc)];
+            fwd_stages_sm<CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS);
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            u64 k0[4], k1[4];
+            ld256_nc(k0, key + 4 * h);
+            ld256_nc(k1, key + a.evk_hs + 4 * h);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = 4 * h + e;
+                if (LAZYACC) {
+                    acc0[r] += mred_constant(k0[e], x[r], q, qinv);
+                    acc1[r] += mred_constant(k1[e], x[r], q, qinv);
+                } else {
+                    acc0[r] = cred(acc0[r] + mred(k0[e], x[r], q, qinv), q);
+                    acc1[r] = cred(acc1[r] + mred(k1[e], x[r], q, qinv), q);
+                }
+            }
+        }
+    }
+    u64* o0 = a.acc0 + (size_t)b * a.acc_bs + (size_t)j * N + e0;
+    u64* o1 = a.acc1 + (size_t)b * a.acc_bs + (size_t)j * N + e0;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        st256(o0 + 4 * h, bred_add(acc0[4 * h], q, lc.u0), bred_add(acc0[4 * h + 1], q, lc.u0),
+              bred_add(acc0[4 * h + 2], q, lc.u0), bred_add(acc0[4 * h + 3], q, lc.u0));
+        st256(o1 + 4 * h, bred_add(acc1[4 * h], q, lc.u0), bred_add(acc1[4 * h + 1], q, lc.u0),
+              bred_add(acc1[4 * h + 2], q, lc.u0), bred_add(acc1[4 * h + 3], q, lc.u0));
+    }
+}
+
+template <bool LITERAL>
+__global__ void __launch_bounds__(CONTIG_THREADS, 3) ks_fused_kernel(const KsFusedArgs a) {
+    extern __shared__ __align__(16) u64 ks_smem[];
+    const int tl = a.map(blockIdx.z);
+    const LimbConst lc = load_limb_const(a.T, tl);
+    const int mode = LITERAL ? M_LITERAL : fwd_mode(lc.q);
+    const bool lazyacc = (2 * lc.q) <= (~0ull) / (u64)a.beta;
+    if (mode == M_F64) {  // q < 2^56: beta <= 64 terms below 2q always fit
+        ks_fused_body<M_F64, true>(a, lc, tl, ks_smem);
+    } else if (mode == M_FREE) {
+        ks_fused_body<M_FREE, true>(a, lc, tl, ks_smem);
+    } else if (mode == M_LAZY) {
+        if (lazyacc)
+            ks_fused_body<M_LAZY, true>(a, lc, tl, ks_smem);
+        else
+            ks_fused_body<M_LAZY, false>(a, lc, tl, ks_smem);
+    } else {
+        ks_fused_body<M_LITERAL, false>(a, lc, tl, ks_smem);
+    }
+}
+
+// ---- inverse, contiguous phase: first 8 stages -------------------------------
+template <int MODE>
+LG_DEV void inv_contig_body(const NttArgs& a, const LimbSetup& s, const SegPos& p) {
+    const TwConst c = tw_const<false, MODE>(a.T, s.c, s.tl);
+    const u32 N = a.T.N;
+    const u32 e0 = p.segbase + 16 * p.cc;
     u64 x[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + 16 * c + r)];
-    const u32 j1 = base + seg * 256u + 16 * c;
-    inv_stages<0, 3, true>(x, s.tw, N + j1, q, qinv, twoq);
+    for (int h = 0; h < 4; ++h) {
+        u64 v[4];
+        ld256(v, s.in + e0 + 4 * h);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) sm[pad16(seg * 256u + 16 * c + r)] = x[r];
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = sm[pad16(seg * 256u + c + 16 * r)];
-    const u32 j0 = base + seg * 256u + c;
-    inv_stages<0, 3, false>(x, s.tw, (N + j0) >> 4, q, qinv, twoq);
+        for (int e = 0; e < 4; ++e) x[4 * h + e] = v[e];
+    }
+    inv_stages<3, true, MODE>(x, c, N + e0, 0u);
+    __syncwarp();
+    seg_store_rows(p, x);
+    __syncwarp();
+    seg_load_cols(p, x);
+    const u32 j0 = p.segbase + p.cc;
+    inv_stages<3, false, MODE>(x, c, (N + j0) >> 4, 4u);
 #pragma unroll
     for (int r = 0; r < 16; ++r) s.out[j0 + 16 * r] = x[r];
 }
 
+LG_DEV bool inv_flagged(const NttArgs& a) {
+    return a.flags != nullptr && a.flags[(size_t)blockIdx.x * gridDim.z + blockIdx.z] != 0;
+}
+
+template <bool LITERAL>
+__global__ void __launch_bounds__(CONTIG_THREADS) ntt_inv_contig(const NttArgs a) {
+    __shared__ __align__(16) u64 smem[8 * SEG_SM];
+    const LimbSetup s = setup_limb(a);
+    if (s.skip) return;
+    const SegPos p = seg_pos(smem);
+    const int mode = (LITERAL || inv_flagged(a)) ? M_LITERAL : inv_mode(s.c.q);
+    if (mode == M_FREE)
+        inv_contig_body<M_FREE>(a, s, p);
+    else if (mode == M_LAZY)
+        inv_contig_body<M_LAZY>(a, s, p);
+    else
+        inv_contig_body<M_LITERAL>(a, s, p);
+}
+
 // ---- inverse, strided phase: last L stages + MRed by N^-1 --------------------
-template <int L>
-__global__ void __launch_bounds__(256) ntt_inv_strided(const NttArgs a) {
+template <int L, int MODE>
+LG_DEV void inv_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
     constexpr int G = 1 << (L - 4);
     constexpr int W = 256 / G;
     constexpr int N2 = L - 4;
-    __shared__ u64 sm[N2 > 0 ? 4096 : 1];
-    const LimbSetup s = setup_limb<false>(a);
-    if (s.skip) return;
+    const TwConst c = tw_const<false, MODE>(a.T, s.c, s.tl);
     const u32 LB = a.T.logN - L;
-    const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
     const int t = threadIdx.x, col = t % W, g = t / W;
     const size_t colg = (size_t)blockIdx.y * W + col;
     u64 x[16];
     if (N2 > 0) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(16 * g + r) << LB) + colg];
-        inv_stages<0, (N2 > 0 ? N2 - 1 : 0), false>(x, s.tw, (1u << L) + 16u * g, q, qinv, twoq);
+        inv_stages<(N2 > 0 ? N2 - 1 : 0), false, MODE>(x, c, (1u << L) + 16u * g, 8u);
 #pragma unroll
         for (int r = 0; r < 16; ++r) sm[(16 * g + r) * W + col] = x[r];
         __syncthreads();
@@ -359,20 +654,59 @@ __global__ void __launch_bounds__(256) ntt_inv_strided(const NttArgs a) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(g + r * G) << LB) + colg];
     }
-    inv_stages<0, 3, false>(x, s.tw, 16u, q, qinv, twoq);
+    inv_stages<3, false, MODE>(x, c, 16u, 8u + N2);
     // ring/ntt.go:136-138
+    if (MODE == M_LITERAL) {
+        const u64 ninv = a.T.ninv[s.tl];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s.out[((size_t)(g + r * G) << LB) + colg] = mred(x[r], s.ninv, q, qinv);
+        for (int r = 0; r < 16; ++r) s.out[((size_t)(g + r * G) << LB) + colg] = mred(x[r], ninv, c.q, c.qinv);
+    } else {
+        const u64 nw = a.T.ninv_w[2 * s.tl], nws = a.T.ninv_w[2 * s.tl + 1];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            s.out[((size_t)(g + r * G) << LB) + colg] = cred(shoup_exact(nw, nws, x[r], c.nq), c.q);
+    }
+}
+
+template <int L, bool LITERAL>
+__global__ void __launch_bounds__(256) ntt_inv_strided(const NttArgs a) {
+    __shared__ u64 sm[(L - 4) > 0 ? 4096 : 1];
+    const LimbSetup s = setup_limb(a);
+    if (s.skip) return;
+    const int mode = (LITERAL || inv_flagged(a)) ? M_LITERAL : inv_mode(s.c.q);
+    if (mode == M_FREE)
+        inv_strided_body<L, M_FREE>(a, s, sm);
+    else if (mode == M_LAZY)
+        inv_strided_body<L, M_LAZY>(a, s, sm);
+    else
+        inv_strided_body<L, M_LITERAL>(a, s, sm);
+}
+
+// flags[b*nlimbs + j] != 0 when some word of the limb exceeds 2q (the inverse then has to be literal);
+// flags are zeroed by the launcher, every CTA scans up to 4096 words
+__global__ void __launch_bounds__(256) range_flags_kernel(const NttArgs a, u32* flags) {
+    const int j = blockIdx.z, b = blockIdx.x;
+    const u64 twoq = 2 * a.T.q[a.map(j)];
+    const u32 half = a.T.N >> 1, lo = blockIdx.y * 2048u, hi = (lo + 2048u < half) ? lo + 2048u : half;
+    const ulonglong2* in = reinterpret_cast<const ulonglong2*>(a.in + (size_t)b * a.in_bstride + (size_t)j * a.T.N);
+    int bad = 0;
+    for (u32 i = lo + threadIdx.x; i < hi; i += 256) {
+        const ulonglong2 v = in[i];
+        bad |= (v.x > twoq) | (v.y > twoq);
+    }
+    bad = __syncthreads_or(bad);
+    if (bad && threadIdx.x == 0) atomicOr(flags + (size_t)b * gridDim.z + j, 1u);
 }
 
 // ---- small rings (logN <= 11): one CTA per limb, radix-2 in shared memory ----
 template <bool FWD>
 __global__ void ntt_small(const NttArgs a) {
     extern __shared__ u64 dsm[];
-    const LimbSetup s = setup_limb<FWD>(a);
+    const LimbSetup s = setup_limb(a);
     if (s.skip) return;
     const u32 N = a.T.N;
     const u64 q = s.c.q, qinv = s.c.qinv, twoq = 2 * s.c.q;
+    const u64* tw = (FWD ? a.T.psi : a.T.psi_inv) + (size_t)s.tl * N;
     for (u32 i = threadIdx.x; i < N; i += blockDim.x) dsm[i] = s.in[i];
     __syncthreads();
     if (FWD) {
@@ -382,7 +716,7 @@ __global__ void ntt_small(const NttArgs a) {
                 const u32 i = k >> sh, jj = k & ((1u << sh) - 1);
                 const u32 j = (i << (sh + 1)) + jj;
                 u64 U = dsm[j], V = dsm[j + (1u << sh)];
-                butterfly_fwd(U, V, s.tw[m + i], q, qinv, twoq);
+                butterfly_fwd(U, V, tw[m + i], q, qinv, twoq);
                 dsm[j] = U;
                 dsm[j + (1u << sh)] = V;
             }
@@ -390,33 +724,49 @@ __global__ void ntt_small(const NttArgs a) {
         }
         for (u32 i = threadIdx.x; i < N; i += blockDim.x) s.out[i] = bred_add(dsm[i], q, s.c.u0);
     } else {
+        const u64 ninv = a.T.ninv[s.tl];
         u32 sh = 0;
         for (u32 h = N >> 1; h >= 1; h >>= 1, ++sh) {
             for (u32 k = threadIdx.x; k < (N >> 1); k += blockDim.x) {
                 const u32 i = k >> sh, jj = k & ((1u << sh) - 1);
                 const u32 j = (i << (sh + 1)) + jj;
                 u64 U = dsm[j], V = dsm[j + (1u << sh)];
-                butterfly_inv(U, V, s.tw[h + i], q, qinv, twoq);
+                butterfly_inv(U, V, tw[h + i], q, qinv, twoq);
                 dsm[j] = U;
                 dsm[j + (1u << sh)] = V;
             }
             __syncthreads();
         }
-        for (u32 i = threadIdx.x; i < N; i += blockDim.x) s.out[i] = mred(dsm[i], s.ninv, q, qinv);
+        for (u32 i = threadIdx.x; i < N; i += blockDim.x) s.out[i] = mred(dsm[i], ninv, q, qinv);
     }
 }
 
 template <int L>
 void launch_strided(bool fwd, bool literal, const NttArgs& a, dim3 grid, cudaStream_t st) {
-    if (!fwd)
-        ntt_inv_strided<L><<<grid, 256, 0, st>>>(a);
-    else if (literal)
-        ntt_fwd_strided<L, true><<<grid, 256, 0, st>>>(a);
-    else
-        ntt_fwd_strided<L, false><<<grid, 256, 0, st>>>(a);
+    if (fwd) {
+        if (literal)
+            ntt_fwd_strided<L, true><<<grid, 256, 0, st>>>(a);
+        else
+            ntt_fwd_strided<L, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (literal)
+            ntt_inv_strided<L, true><<<grid, 256, 0, st>>>(a);
+        else
+            ntt_inv_strided<L, false><<<grid, 256, 0, st>>>(a);
+    }
 }
 
-bool literal_forward() {
+void launch_strided_any(int L, bool fwd, bool literal, const NttArgs& a, dim3 grid, cudaStream_t st) {
+    switch (L) {
+        case 4: launch_strided<4>(fwd, literal, a, grid, st); break;
+        case 5: launch_strided<5>(fwd, literal, a, grid, st); break;
+        case 6: launch_strided<6>(fwd, literal, a, grid, st); break;
+        case 7: launch_strided<7>(fwd, literal, a, grid, st); break;
+        default: launch_strided<8>(fwd, literal, a, grid, st); break;
+    }
+}
+
+bool literal_ntt() {
     static const bool v = [] {
         const char* e = getenv("LATTIGPU_LITERAL_NTT");
         return e && e[0] == '1';
@@ -442,20 +792,11 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
         return 0;
     }
     const int L = (int)logN - 8;
-    const bool literal = literal_forward();
-    dim3 grid(batch, N / 4096, nlimbs);
+    const bool literal = literal_ntt();
+    const dim3 sgrid(batch, N / 4096, nlimbs), cgrid(batch, N / CONTIG_TILE, nlimbs);
     NttArgs second = args;  // the second phase runs in place on the output
     second.in = args.out;
     second.in_bstride = args.out_bstride;
-    auto strided = [&](const NttArgs& a) {
-        switch (L) {
-            case 4: launch_strided<4>(!inverse, literal, a, grid, st); break;
-            case 5: launch_strided<5>(!inverse, literal, a, grid, st); break;
-            case 6: launch_strided<6>(!inverse, literal, a, grid, st); break;
-            case 7: launch_strided<7>(!inverse, literal, a, grid, st); break;
-            default: launch_strided<8>(!inverse, literal, a, grid, st); break;
-        }
-    };
     if (!inverse) {
         // with the MAC epilogue the strided phase runs in place on the input (the decomposed digit)
         NttArgs first = args;
@@ -465,22 +806,59 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
             second.in = args.in;
             second.in_bstride = args.in_bstride;
         }
-        strided(first);
+        launch_strided_any(L, true, literal, first, sgrid, st);
         if (args.mac.enabled) {
             if (literal)
-                ntt_fwd_contig<true, true><<<grid, 256, 0, st>>>(second);
+                ntt_fwd_contig<true, true><<<cgrid, CONTIG_THREADS, 0, st>>>(second);
             else
-                ntt_fwd_contig<true, false><<<grid, 256, 0, st>>>(second);
+                ntt_fwd_contig<true, false><<<cgrid, CONTIG_THREADS, 0, st>>>(second);
         } else {
             if (literal)
-                ntt_fwd_contig<false, true><<<grid, 256, 0, st>>>(second);
+                ntt_fwd_contig<false, true><<<cgrid, CONTIG_THREADS, 0, st>>>(second);
             else
-                ntt_fwd_contig<false, false><<<grid, 256, 0, st>>>(second);
+                ntt_fwd_contig<false, false><<<cgrid, CONTIG_THREADS, 0, st>>>(second);
         }
     } else {
-        ntt_inv_contig<<<grid, 256, 0, st>>>(args);
-        strided(second);
+        if (literal)
+            ntt_inv_contig<true><<<cgrid, CONTIG_THREADS, 0, st>>>(args);
+        else
+            ntt_inv_contig<false><<<cgrid, CONTIG_THREADS, 0, st>>>(args);
+        launch_strided_any(L, false, literal, second, sgrid, st);
     }
     lg_g_launches += 2;
+    return 0;
+}
+
+int lg_launch_ntt_fwd_strided(const NttArgs& args, int nlimbs, int batch, cudaStream_t st) {
+    if (nlimbs <= 0 || batch <= 0) return 0;
+    const u32 logN = args.T.logN, N = args.T.N;
+    if (logN < 12 || logN > 16) return 1;
+    launch_strided_any((int)logN - 8, true, literal_ntt(), args, dim3(batch, N / 4096, nlimbs), st);
+    lg_g_launches += 1;
+    return 0;
+}
+
+int lg_launch_range_flags(const NttArgs& args, int nlimbs, int batch, u32* flags, cudaStream_t st) {
+    if (nlimbs <= 0 || batch <= 0) return 0;
+    cudaMemsetAsync(flags, 0, (size_t)batch * nlimbs * sizeof(u32), st);
+    range_flags_kernel<<<dim3(batch, (args.T.N + 4095) / 4096, nlimbs), 256, 0, st>>>(args, flags);
+    lg_g_launches += 1;
+    return 0;
+}
+
+int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st) {
+    if (nlimbs <= 0 || batch <= 0) return 0;
+    if (a.T.logN < 12 || a.T.logN > 16 || a.beta < 1) return 1;
+    const dim3 grid(batch, a.T.N / CONTIG_TILE, nlimbs);
+    const size_t smem = KS_SMEM_WORDS * sizeof(u64);
+    // (per launch: the attribute is per device and a process may drive several)
+    if (literal_ntt()) {
+        cudaFuncSetAttribute(ks_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ks_fused_kernel<true><<<grid, CONTIG_THREADS, smem, st>>>(a);
+    } else {
+        cudaFuncSetAttribute(ks_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ks_fused_kernel<false><<<grid, CONTIG_THREADS, smem, st>>>(a);
+    }
+    lg_g_launches += 1;
     return 0;
 }

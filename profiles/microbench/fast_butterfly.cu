@@ -25,7 +25,7 @@ LG_DEV void bfly(u64& X, u64& Y, u64 w, u64 ws, u64 q, u64 qinv, u64 twoq, u64 f
         const u64 t = mul_lo(w, Y) - mul_lo(qh, q);
         X = x + t;
         Y = x + twoq - t;
-    } else {
+    } else if (KIND == 2) {
         const u32 a0 = (u32)ws, a1 = (u32)(ws >> 32), b0 = (u32)Y, b1 = (u32)(Y >> 32);
         const u64 m1 = mulw(a1, b0), m2 = mulw(a0, b1);
         const u64 qh = madw(a1, b1, (m1 >> 32)) + (m2 >> 32);
@@ -33,6 +33,18 @@ LG_DEV void bfly(u64& X, u64& Y, u64 w, u64 ws, u64 q, u64 qinv, u64 twoq, u64 f
         const u64 x = X;
         X = x + t;
         Y = x + fourq - t;
+    } else if (KIND == 3) {  // library: 16-instruction chain form
+        butterfly_fwd_free(X, Y, w, ws, 0ull - q, fourq);
+    } else if (KIND == 4) {
+        butterfly_fwd_8q(X, Y, w, ws, 0ull - q, fourq);
+    } else if (KIND == 5) {
+        butterfly_inv_free(X, Y, w, ws, 0ull - q, q << 17);
+    } else if (KIND == 6) {
+        butterfly_inv_4q(X, Y, w, ws, 0ull - q, fourq);
+    } else {  // FP64-assisted quotient: ws carries the bits of wd, qinv the constant c0
+        const double wd = __longlong_as_double((long long)ws);
+        if (KIND == 7) butterfly_fwd_f64(X, Y, w, wd, shoup_cw(wd), 0ull - q, fourq, qinv);
+        else butterfly_inv_f64(X, Y, w, wd, shoup_cw(wd), 0ull - q, fourq, qinv);
     }
 }
 
@@ -45,6 +57,13 @@ __global__ void __launch_bounds__(256) loop(u64* a, const u64* __restrict__ tw, 
     u64 w[8], ws[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) { w[g] = tw[g + (threadIdx.x & 7)]; ws[g] = tw[64 + g + (threadIdx.x & 7)]; }
+    if (KIND >= 7) {
+        qinv = shoup_f64_c0(0ull - q);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) ws[g] = (u64)__double_as_longlong(__ull2double_rz(ws[g]) * 5.421010862427522e-20);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] &= 0x0003ffffffffffffull;
+    }
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -57,7 +76,7 @@ __global__ void __launch_bounds__(256) loop(u64* a, const u64* __restrict__ tw, 
                     bfly<KIND>(x[r], x[r + (1 << u)], w[g], ws[g], q, qinv, twoq, fourq);
                 }
         }
-        if (KIND == 2 && (it & 3) == 3) {  // keep the values bounded in this endless loop only
+        if ((KIND == 2 || KIND == 3 || KIND == 5) && (it & 3) == 3) {  // keep the values bounded in this endless loop only
 #pragma unroll
             for (int r = 0; r < 16; ++r) x[r] &= 0x00ffffffffffffffull;
         }
@@ -75,13 +94,29 @@ __global__ void check(const u64* xs, const u64* ys, const u64* wm, u64 q, u64 qi
     const u64 wplain = invmform(wmont, q, qinv);
     const u64 ws = (u64)((((unsigned __int128)wplain) << 64) / q);
     u64 X0 = xs[i], Y0 = ys[i];
-    if (KIND == 1) { X0 %= 4 * q; Y0 %= 4 * q; }
-    if (KIND == 2) { X0 &= (1ull << 62) - 1; }
+    if (KIND == 1 || KIND == 6) { X0 %= 4 * q; Y0 %= 4 * q; }
+    if (KIND == 4) { X0 %= 8 * q; Y0 %= 8 * q; }
+    if (KIND == 2 || KIND == 3) { X0 &= (1ull << 62) - 1; }
+    if (KIND == 5) { X0 %= 2 * q; Y0 %= 2 * q; }
+    if (KIND == 7) { X0 &= (1ull << 51) - 1; Y0 &= (1ull << 52) - 1; }
+    if (KIND == 8) { X0 %= 4 * q; Y0 %= 4 * q; }
     u64 X1 = X0, Y1 = Y0, X2 = X0, Y2 = Y0;
-    butterfly_fwd(X1, Y1, wmont, q, qinv, 2 * q);
-    bfly<KIND>(X2, Y2, wplain, ws, q, qinv, 2 * q, 4 * q);
+    if (KIND == 5 || KIND == 6 || KIND == 8) {  // Gentleman-Sande: compare with the literal InvButterfly on in-range inputs
+        X1 %= 2 * q; Y1 %= 2 * q;
+        butterfly_inv(X1, Y1, wmont, q, qinv, 2 * q);
+    } else {
+        butterfly_fwd(X1, Y1, wmont, q, qinv, 2 * q);
+    }
+    if (KIND >= 7)
+        bfly<KIND>(X2, Y2, wplain, (u64)__double_as_longlong(__ull2double_rz(ws) * 5.421010862427522e-20), q,
+                   shoup_f64_c0(0ull - q), 2 * q, 4 * q);
+    else
+        bfly<KIND>(X2, Y2, wplain, ws, q, qinv, 2 * q, 4 * q);
+    if (KIND == 7 && (X2 >= X0 + 4 * q || Y2 > X0 + 4 * q)) atomicAdd(bad, 1);
+    if (KIND == 8 && (X2 >= 4 * q || Y2 >= 4 * q)) atomicAdd(bad, 1);
     if (X1 % q != X2 % q || Y1 % q != Y2 % q) atomicAdd(bad, 1);
-    if (KIND == 1 && (X2 >= 4 * q || Y2 >= 4 * q)) atomicAdd(bad, 1);
+    if ((KIND == 1 || KIND == 6) && (X2 >= 4 * q || Y2 >= 4 * q)) atomicAdd(bad, 1);
+    if (KIND == 4 && (X2 >= 8 * q || Y2 >= 8 * q)) atomicAdd(bad, 1);
     (void)u0; (void)u1;
 }
 
@@ -111,7 +146,7 @@ void run(const char* name, u64* a, u64* tw) {
         u64* dst[3] = {xs, ys, wm};
         for (auto d : dst) { for (int i = 0; i < n; ++i) h[i] = ((u64)rand() << 43) ^ ((u64)rand() << 21) ^ rand(); cudaMemcpy(d, h, n * 8, cudaMemcpyHostToDevice); }
     }
-    for (int m = 0; m < (KIND == 2 ? 2 : 3); ++m) {
+    for (int m = 0; m < ((KIND == 2 || KIND == 3) ? 2 : ((KIND == 5 || KIND >= 7) ? 1 : 3)); ++m) {
         const u64 qq = qs[m];
         u64 qinv = qq; for (int i = 0; i < 6; ++i) qinv *= 2 - qq * qinv;
         cudaMemset(bad, 0, 4);
@@ -129,5 +164,11 @@ int main() {
     run<0>("literal Montgomery butterfly", a, tw);
     run<1>("Shoup exact quotient, lazy [0,4q)", a, tw);
     run<2>("Shoup 3-product quotient, no cond. subtraction", a, tw);
+    run<3>("butterfly_fwd_free (16-instruction chain form)", a, tw);
+    run<4>("butterfly_fwd_8q   (values in [0,8q))", a, tw);
+    run<5>("butterfly_inv_free (GS, q < 2^46)", a, tw);
+    run<6>("butterfly_inv_4q   (GS, values in [0,4q))", a, tw);
+    run<7>("butterfly_fwd_f64  (FP64 quotient, q < 3*2^44)", a, tw);
+    run<8>("butterfly_inv_f64  (GS, FP64 quotient, [0,4q))", a, tw);
     return 0;
 }
