@@ -68,6 +68,103 @@ __global__ void __launch_bounds__(256) modup_kernel(const ModUpArgs a) {
     }
 }
 
+// Fast path for 1..4 source limbs with every modulus below 2^61 (all decompositions and ModDowns of the
+// named parameter sets): two coefficients per thread (128-bit loads/stores), the per-target constants staged
+// in shared memory, and the 128-bit sum of y_i * qispjMont[i][j] kept in column form
+//   A0 = sum y0*c0 (64 bits + carry count), A1 = sum (y0*c1 + y1*c0) (2*NSRC terms below 2^61 fit 64 bits),
+//   A2 = sum y1*c1
+// i.e. four multiply-adds and one carry per term; qpjInv[j][v] joins the high word before the single
+// Montgomery reduction.  Same residue as the reference's sum of MRed terms, canonicalised the same way.
+template <int NSRC>
+__global__ void __launch_bounds__(128) modup_fast_kernel(const ModUpArgs a) {
+    constexpr int ROW = 2 * NSRC + 3;  // p, pinv, c[NSRC], qpjinv[NSRC+1]
+    __shared__ u64 tab[LG_MAX_LIMBS * ROW];
+    const ModUpTables& M = a.M;
+    int ntg = 0;
+    for (int k = 0; k < a.nruns; ++k) ntg += a.ndst[k];
+    for (int e = threadIdx.x; e < ntg * ROW; e += blockDim.x) {
+        int idx = e / ROW, f = e - idx * ROW, tg = 0;
+        for (int k = 0, o = idx; k < a.nruns; ++k) {
+            if (o < a.ndst[k]) {
+                tg = a.tgt0[k] + o;
+                break;
+            }
+            o -= a.ndst[k];
+        }
+        u64 val;
+        if (f == 0)
+            val = M.dstQ[tg];
+        else if (f == 1)
+            val = M.dstQinv[tg];
+        else if (f < 2 + NSRC)
+            val = M.qispj[(size_t)(f - 2) * M.dst_total + tg];
+        else
+            val = M.qpjinv[(size_t)tg * (M.src_total + 1) + (f - 2 - NSRC)];
+        tab[e] = val;
+    }
+    __syncthreads();
+    const u32 x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int bt = blockIdx.y;
+    if (x >= a.N) return;
+    u32 y0[NSRC][2], y1[NSRC][2];
+    u32 v[2];
+    {
+        double vi0 = 0.0, vi1 = 0.0;
+        const u64* in = a.in + bt * a.in_bs + x;
+#pragma unroll
+        for (int i = 0; i < NSRC; ++i) {
+            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(in + (size_t)i * a.N);
+            if (a.copy_out) *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x) = val;
+            const u64 qi = __ldg(M.srcQ + i), qib = __ldg(M.qib + i), qinv = __ldg(M.srcQinv + i);
+            const u64 ya = mred(val.x, qib, qi, qinv), yb = mred(val.y, qib, qi, qinv);
+            const double qd = __ull2double_rn(qi);
+            vi0 = __dadd_rn(vi0, __ddiv_rn(__ull2double_rn(ya), qd));
+            vi1 = __dadd_rn(vi1, __ddiv_rn(__ull2double_rn(yb), qd));
+            y0[i][0] = (u32)ya;
+            y1[i][0] = (u32)(ya >> 32);
+            y0[i][1] = (u32)yb;
+            y1[i][1] = (u32)(yb >> 32);
+        }
+        v[0] = (u32)__double2ull_rz(vi0);
+        v[1] = (u32)__double2ull_rz(vi1);
+    }
+    int idx = 0;
+#pragma unroll 1
+    for (int k = 0; k < a.nruns; ++k) {
+        u64* out = a.out[k] + bt * a.out_bs[k] + x;
+#pragma unroll 1
+        for (int t = 0; t < a.ndst[k]; ++t, ++idx) {
+            const u64* row = tab + idx * ROW;
+            const u64 pj = row[0], pinv = row[1];
+            u64 res[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                u64 A0 = 0, A1 = 0, A2 = 0;
+                u32 cnt = 0;
+#pragma unroll
+                for (int i = 0; i < NSRC; ++i) {
+                    const u64 c = row[2 + i];
+                    const u32 c0 = (u32)c, c1 = (u32)(c >> 32);
+                    const u64 t0 = mul_wide(y0[i][e], c0);
+                    asm("add.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+l"(A0), "+r"(cnt) : "l"(t0));
+                    A1 = mad_wide(y0[i][e], c1, A1);
+                    A1 = mad_wide(y1[i][e], c0, A1);
+                    A2 = mad_wide(y1[i][e], c1, A2);
+                }
+                // S = A0 + (A1 << 32) + ((A2 + cnt) << 64), plus qpjInv[j][v] on the high word
+                u64 slo, shi;
+                asm("add.cc.u64 %0, %2, %3;\n\taddc.u64 %1, %4, %5;"
+                    : "=l"(slo), "=l"(shi)
+                    : "l"(A0), "l"(A1 << 32), "l"(A2 + cnt), "l"(A1 >> 32));
+                shi += row[2 + NSRC + v[e]];
+                const u64 r = shi - mul_hi(mul_lo(slo, pinv), pj) + pj;  // REDC: in (0, 3p)
+                res[e] = cred(cred(r, pj), pj);
+            }
+            *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N) = make_ulonglong2(res[0], res[1]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) fanout_kernel(const FanoutArgs a) {
     const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
     const int bt = blockIdx.y;
@@ -86,6 +183,17 @@ __global__ void __launch_bounds__(256) fanout_kernel(const FanoutArgs a) {
 
 int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
     if (batch <= 0) return 0;
+    if (a.fast && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
+        dim3 fgrid((a.N / 2 + 127) / 128, batch);
+        switch (a.nsrc) {
+            case 1: modup_fast_kernel<1><<<fgrid, 128, 0, st>>>(a); break;
+            case 2: modup_fast_kernel<2><<<fgrid, 128, 0, st>>>(a); break;
+            case 3: modup_fast_kernel<3><<<fgrid, 128, 0, st>>>(a); break;
+            default: modup_fast_kernel<4><<<fgrid, 128, 0, st>>>(a); break;
+        }
+        lg_g_launches += 1;
+        return 0;
+    }
     dim3 grid((a.N + 255) / 256, batch);
     if (a.nsrc <= 2)
         modup_kernel<2><<<grid, 256, 0, st>>>(a);

@@ -102,6 +102,7 @@ struct lg_galois {
 // device modupParams (ring_basis_extension.go:20-37)
 struct ModUpDev {
     int nsrc = 0, ndst = 0;
+    bool small = false;  // all moduli below 2^61
     DevArray<u64> srcQ, srcQinv, qib, qispj, qpjinv, dstQ, dstQinv, dstU0;
     ModUpTables M;
     int build(const u64* Q, int nq, const u64* P, int np);
