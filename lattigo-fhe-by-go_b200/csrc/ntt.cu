@@ -151,6 +151,87 @@ LG_DEV void inv_stages(u64 (&x)[16], const TwConst& c, u32 twbase, u32 stage) {
     if (UHI >= 3) inv_stage<3, VEC, MODE>(x, c, twbase, stage);
 }
 
+// ---- stages with twiddles staged in shared memory ------------------------------
+// The 15 twiddles a register block needs (1 + 2 + 4 + 8 for stages u = 3..0) sit in heap order:
+// stage u uses slots [2^(3-u) - 1, 2^(4-u) - 1); w[g] = wp[(slot + g) * STRIDE], ws likewise from wsp.
+template <int U, int STRIDE, int MODE>
+LG_DEV void fwd_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp) {
+    constexpr int NG = 16 >> (U + 1);
+    constexpr int S0 = (8 >> U) - 1;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const u64 w = wp[(S0 + g) * STRIDE];
+        const u64 ws = (MODE != M_LITERAL) ? wsp[(S0 + g) * STRIDE] : 0ull;
+        const double wd = __longlong_as_double((long long)ws);
+        const double cw = (MODE == M_F64) ? shoup_cw(wd) : 0.0;
+#pragma unroll
+        for (int k = 0; k < (1 << U); ++k) {
+            const int r = (g << (U + 1)) + k;
+            if (MODE == M_LITERAL)
+                butterfly_fwd(x[r], x[r + (1 << U)], w, c.q, c.qinv, c.twoq);
+            else if (MODE == M_FREE)
+                butterfly_fwd_free(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
+            else if (MODE == M_F64)
+                butterfly_fwd_f64(x[r], x[r + (1 << U)], w, wd, cw, c.nq, c.fourq, c.c0);
+            else
+                butterfly_fwd_8q(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
+        }
+    }
+}
+// stages UHI, ..., 0
+template <int UHI, int STRIDE, int MODE>
+LG_DEV void fwd_stages_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp) {
+    if (UHI >= 3) fwd_stage_sm<3, STRIDE, MODE>(x, c, wp, wsp);
+    if (UHI >= 2) fwd_stage_sm<2, STRIDE, MODE>(x, c, wp, wsp);
+    if (UHI >= 1) fwd_stage_sm<1, STRIDE, MODE>(x, c, wp, wsp);
+    fwd_stage_sm<0, STRIDE, MODE>(x, c, wp, wsp);
+}
+template <int U, int STRIDE, int MODE>
+LG_DEV void inv_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp, u32 stage) {
+    constexpr int NG = 16 >> (U + 1);
+    constexpr int S0 = (8 >> U) - 1;
+    const u64 m = c.q << (stage + U + 1);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const u64 w = wp[(S0 + g) * STRIDE];
+        const u64 ws = (MODE != M_LITERAL) ? wsp[(S0 + g) * STRIDE] : 0ull;
+#pragma unroll
+        for (int k = 0; k < (1 << U); ++k) {
+            const int r = (g << (U + 1)) + k;
+            if (MODE == M_LITERAL)
+                butterfly_inv(x[r], x[r + (1 << U)], w, c.q, c.qinv, c.twoq);
+            else if (MODE == M_FREE)
+                butterfly_inv_free(x[r], x[r + (1 << U)], w, ws, c.nq, m);
+            else
+                butterfly_inv_4q(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
+        }
+    }
+}
+// stages 0, ..., UHI
+template <int UHI, int STRIDE, int MODE>
+LG_DEV void inv_stages_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp, u32 stage) {
+    inv_stage_sm<0, STRIDE, MODE>(x, c, wp, wsp, stage);
+    if (UHI >= 1) inv_stage_sm<1, STRIDE, MODE>(x, c, wp, wsp, stage);
+    if (UHI >= 2) inv_stage_sm<2, STRIDE, MODE>(x, c, wp, wsp, stage);
+    if (UHI >= 3) inv_stage_sm<3, STRIDE, MODE>(x, c, wp, wsp, stage);
+}
+
+// Strided phase twiddles: group 0 = the subtree under node 1 (the block on the top four stages, the same
+// for every thread), group 1+g = the subtree under node 2^(L-4) + g (the block below it).  Heap slot k of
+// the subtree under node m is table entry (m << lvl) + (k + 1 - 2^lvl), lvl = floor(log2(k + 1)).
+template <int L, bool LIT>
+LG_DEV void fill_strided_tw(u64* tws_sm, const TwConst& c) {
+    constexpr int G = 1 << (L - 4);
+    for (int e = threadIdx.x; e < 15 * (G + 1); e += 256) {
+        const int grp = e / 15, k = e - grp * 15;
+        const u32 lvl = 31 - __clz(k + 1);
+        const u32 node = grp == 0 ? 1u : (u32)(G + grp - 1);
+        const u32 idx = (node << lvl) + (k + 1 - (1u << lvl));
+        tws_sm[grp * 32 + k] = __ldg(c.tw + idx);
+        if (!LIT) tws_sm[grp * 32 + 15 + k] = __ldg(c.tws + idx);
+    }
+}
+
 struct LimbSetup {
     LimbConst c;
     const u64* in;
@@ -199,64 +280,68 @@ LG_DEV TwConst tw_const(const RingTables& T, const LimbConst& lc, int tl) {
 }
 
 // ---- forward, strided phase: stages 1..L -----------------------------------
+// (rows are 2^8 words apart: the contiguous phase always takes the low 8 stages)
 template <int L, int MODE>
-LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
+LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64* tws_sm) {
     constexpr int G = 1 << (L - 4);  // threads per column
     constexpr int W = 256 / G;       // columns per CTA
     constexpr int N2 = L - 4;        // stages of the second register block
     const TwConst c = tw_const<true, MODE>(a.T, s.c, s.tl);
-    const u32 LB = a.T.logN - L;
     const int t = threadIdx.x, col = t % W, g = t / W;
-    const size_t colg = (size_t)blockIdx.y * W + col;
+    const u32 colg = blockIdx.y * W + col;
     u64 x[16];
+    const u64* in = s.in + colg + g * 256;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(g + r * G) << LB) + colg];
-    if (MODE == M_FREE) {  // growth headroom: everything below 2^63 (canonical inputs never take this branch)
+    for (int r = 0; r < 16; ++r) x[r] = in[r * G * 256];
+    fill_strided_tw<L, MODE == M_LITERAL>(tws_sm, c);
+    if (MODE != M_LITERAL) {
+        // headroom of the lazy butterflies (canonical inputs never take the slow branch): M_FREE keeps
+        // everything below 2^63, M_F64 below 2^50, M_LAZY below 2^(bits(q)+2) <= 8q
+        const u32 sh = MODE == M_FREE ? 63u : (MODE == M_F64 ? 50u : 66u - (u32)__clzll((long long)c.q));
+        u64 o = 0;
 #pragma unroll
-        for (int r = 0; r < 16; ++r)
-            if (x[r] >> 63) x[r] = bred_add(x[r], c.q, s.c.u0);
+        for (int r = 0; r < 16; ++r) o |= x[r];
+        if (o >> sh) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (x[r] >> sh) x[r] = bred_add(x[r], c.q, s.c.u0);
+        }
     }
-    if (MODE == M_F64) {  // values below 2^52 throughout: inputs below 2^50 (canonical inputs never take this branch)
-#pragma unroll
-        for (int r = 0; r < 16; ++r)
-            if (x[r] >> 50) x[r] = bred_add(x[r], c.q, s.c.u0);
-    }
-    if (MODE == M_LAZY) {  // invariant: values in [0,8q)
-        const u64 eightq = 8 * c.q;
-#pragma unroll
-        for (int r = 0; r < 16; ++r)
-            if (x[r] >= eightq) x[r] = bred_add(x[r], c.q, s.c.u0);
-    }
-    fwd_stages<3, false, MODE>(x, c, 16u);
+    __syncthreads();
+    fwd_stages_sm<3, 1, MODE>(x, c, tws_sm, tws_sm + 15);
     if (N2 > 0) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) sm[(g + r * G) * W + col] = x[r];
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = sm[(16 * g + r) * W + col];
-        fwd_stages<(N2 > 0 ? N2 - 1 : 0), false, MODE>(x, c, (1u << L) + 16u * g);
+        const u64* twg = tws_sm + (1 + g) * 32;
+        fwd_stages_sm<(N2 > 0 ? N2 - 1 : 0), 1, MODE>(x, c, twg, twg + 15);
+        u64* out = s.out + colg + g * 16 * 256;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) s.out[((size_t)(16 * g + r) << LB) + colg] = x[r];
+        for (int r = 0; r < 16; ++r) out[r * 256] = x[r];
     } else {
+        u64* out = s.out + colg + g * 256;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) s.out[((size_t)(g + r * G) << LB) + colg] = x[r];
+        for (int r = 0; r < 16; ++r) out[r * G * 256] = x[r];
     }
 }
 
 template <int L, bool LITERAL>
 __global__ void __launch_bounds__(256) ntt_fwd_strided(const NttArgs a) {
     __shared__ u64 sm[(L - 4) > 0 ? 4096 : 1];
+    __shared__ u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
     const LimbSetup s = setup_limb(a);
     if (s.skip) return;
     const int mode = LITERAL ? M_LITERAL : fwd_mode(s.c.q);
     if (mode == M_F64)
-        fwd_strided_body<L, M_F64>(a, s, sm);
+        fwd_strided_body<L, M_F64>(a, s, sm, tws_sm);
     else if (mode == M_FREE)
-        fwd_strided_body<L, M_FREE>(a, s, sm);
+        fwd_strided_body<L, M_FREE>(a, s, sm, tws_sm);
     else if (mode == M_LAZY)
-        fwd_strided_body<L, M_LAZY>(a, s, sm);
+        fwd_strided_body<L, M_LAZY>(a, s, sm, tws_sm);
     else
-        fwd_strided_body<L, M_LITERAL>(a, s, sm);
+        fwd_strided_body<L, M_LITERAL>(a, s, sm, tws_sm);
 }
 
 // ---- contiguous phase geometry ------------------------------------------------
@@ -425,39 +510,6 @@ LG_DEV void prefetch_warp_tile(u64* buf, const u64* __restrict__ src_tile) {
     cp_async_commit();
 }
 
-// stage with twiddles taken from shared memory: w[g] = wp[g*STRIDE], ws[g] = wsp[g*STRIDE]
-template <int U, int STRIDE, int MODE>
-LG_DEV void fwd_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp) {
-    constexpr int NG = 16 >> (U + 1);
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        const u64 w = wp[g * STRIDE];
-        const u64 ws = (MODE != M_LITERAL) ? wsp[g * STRIDE] : 0ull;
-        const double wd = __longlong_as_double((long long)ws);
-        const double cw = (MODE == M_F64) ? shoup_cw(wd) : 0.0;
-#pragma unroll
-        for (int k = 0; k < (1 << U); ++k) {
-            const int r = (g << (U + 1)) + k;
-            if (MODE == M_LITERAL)
-                butterfly_fwd(x[r], x[r + (1 << U)], w, c.q, c.qinv, c.twoq);
-            else if (MODE == M_FREE)
-                butterfly_fwd_free(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
-            else if (MODE == M_F64)
-                butterfly_fwd_f64(x[r], x[r + (1 << U)], w, wd, cw, c.nq, c.fourq, c.c0);
-            else
-                butterfly_fwd_8q(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
-        }
-    }
-}
-// heap-ordered slots: stage U uses slots [2^(3-U) - 1, 2^(4-U) - 1)
-template <int STRIDE, int MODE>
-LG_DEV void fwd_stages_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp) {
-    fwd_stage_sm<3, STRIDE, MODE>(x, c, wp, wsp);
-    fwd_stage_sm<2, STRIDE, MODE>(x, c, wp + 1 * STRIDE, wsp + 1 * STRIDE);
-    fwd_stage_sm<1, STRIDE, MODE>(x, c, wp + 3 * STRIDE, wsp + 3 * STRIDE);
-    fwd_stage_sm<0, STRIDE, MODE>(x, c, wp + 7 * STRIDE, wsp + 7 * STRIDE);
-}
-
 // LAZYACC: beta * 2q fits 64 bits, so the products are accumulated unreduced (MRedConstant, in (0,2q)).
 template <int MODE, bool LAZYACC>
 LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64* smem) {
@@ -526,7 +578,7 @@ LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64
         } else {
 #pragma unroll
             for (int r = 0; r < 16; ++r) x[r] = buf[cc + 16 * r];
-            fwd_stages_sm<1, MODE>(x, c, twseg, twseg + 15);
+            fwd_stages_sm<3, 1, MODE>(x, c, twseg, twseg + 15);
             __syncwarp();
             // exchange in place, XOR-swizzled (word 16r+cc at 16r + (cc^r)): conflict-free both ways
 #pragma unroll
@@ -534,7 +586,7 @@ LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < 16; ++r) x[r] = buf[16 * cc + (r ^ cc)];
-            fwd_stages_sm<CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS);
+            fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS);
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -632,54 +684,61 @@ __global__ void __launch_bounds__(CONTIG_THREADS) ntt_inv_contig(const NttArgs a
 
 // ---- inverse, strided phase: last L stages + MRed by N^-1 --------------------
 template <int L, int MODE>
-LG_DEV void inv_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm) {
+LG_DEV void inv_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64* tws_sm) {
     constexpr int G = 1 << (L - 4);
     constexpr int W = 256 / G;
     constexpr int N2 = L - 4;
     const TwConst c = tw_const<false, MODE>(a.T, s.c, s.tl);
-    const u32 LB = a.T.logN - L;
     const int t = threadIdx.x, col = t % W, g = t / W;
-    const size_t colg = (size_t)blockIdx.y * W + col;
+    const u32 colg = blockIdx.y * W + col;
     u64 x[16];
     if (N2 > 0) {
+        const u64* in = s.in + colg + g * 16 * 256;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(16 * g + r) << LB) + colg];
-        inv_stages<(N2 > 0 ? N2 - 1 : 0), false, MODE>(x, c, (1u << L) + 16u * g, 8u);
+        for (int r = 0; r < 16; ++r) x[r] = in[r * 256];
+    } else {
+        const u64* in = s.in + colg + g * 256;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = in[r * G * 256];
+    }
+    fill_strided_tw<L, MODE == M_LITERAL>(tws_sm, c);
+    __syncthreads();
+    if (N2 > 0) {
+        const u64* twg = tws_sm + (1 + g) * 32;
+        inv_stages_sm<(N2 > 0 ? N2 - 1 : 0), 1, MODE>(x, c, twg, twg + 15, 8u);
 #pragma unroll
         for (int r = 0; r < 16; ++r) sm[(16 * g + r) * W + col] = x[r];
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = sm[(g + r * G) * W + col];
-    } else {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) x[r] = s.in[((size_t)(g + r * G) << LB) + colg];
     }
-    inv_stages<3, false, MODE>(x, c, 16u, 8u + N2);
+    inv_stages_sm<3, 1, MODE>(x, c, tws_sm, tws_sm + 15, 8u + N2);
     // ring/ntt.go:136-138
+    u64* out = s.out + colg + g * 256;
     if (MODE == M_LITERAL) {
         const u64 ninv = a.T.ninv[s.tl];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) s.out[((size_t)(g + r * G) << LB) + colg] = mred(x[r], ninv, c.q, c.qinv);
+        for (int r = 0; r < 16; ++r) out[r * G * 256] = mred(x[r], ninv, c.q, c.qinv);
     } else {
         const u64 nw = a.T.ninv_w[2 * s.tl], nws = a.T.ninv_w[2 * s.tl + 1];
 #pragma unroll
-        for (int r = 0; r < 16; ++r)
-            s.out[((size_t)(g + r * G) << LB) + colg] = cred(shoup_exact(nw, nws, x[r], c.nq), c.q);
+        for (int r = 0; r < 16; ++r) out[r * G * 256] = cred(shoup_exact(nw, nws, x[r], c.nq), c.q);
     }
 }
 
 template <int L, bool LITERAL>
 __global__ void __launch_bounds__(256) ntt_inv_strided(const NttArgs a) {
     __shared__ u64 sm[(L - 4) > 0 ? 4096 : 1];
+    __shared__ u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
     const LimbSetup s = setup_limb(a);
     if (s.skip) return;
     const int mode = (LITERAL || inv_flagged(a)) ? M_LITERAL : inv_mode(s.c.q);
     if (mode == M_FREE)
-        inv_strided_body<L, M_FREE>(a, s, sm);
+        inv_strided_body<L, M_FREE>(a, s, sm, tws_sm);
     else if (mode == M_LAZY)
-        inv_strided_body<L, M_LAZY>(a, s, sm);
+        inv_strided_body<L, M_LAZY>(a, s, sm, tws_sm);
     else
-        inv_strided_body<L, M_LITERAL>(a, s, sm);
+        inv_strided_body<L, M_LITERAL>(a, s, sm, tws_sm);
 }
 
 // flags[b*nlimbs + j] != 0 when some word of the limb exceeds 2q (the inverse then has to be literal);
