@@ -327,8 +327,11 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
     }
 }
 
+#ifndef STRIDED_MINB
+#define STRIDED_MINB 4
+#endif
 template <int L, bool LITERAL>
-__global__ void __launch_bounds__(256) ntt_fwd_strided(const NttArgs a) {
+__global__ void __launch_bounds__(256, STRIDED_MINB) ntt_fwd_strided(const NttArgs a) {
     __shared__ u64 sm[(L - 4) > 0 ? 4096 : 1];
     __shared__ u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
     const LimbSetup s = setup_limb(a);
@@ -369,15 +372,6 @@ LG_DEV SegPos seg_pos(u64* smem) {
 LG_DEV void seg_store_cols(const SegPos& p, const u64 (&x)[16]) {
 #pragma unroll
     for (int r = 0; r < 16; ++r) p.sm[18 * r + p.cc] = x[r];
-}
-LG_DEV void seg_load_cols(const SegPos& p, u64 (&x)[16]) {
-#pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = p.sm[18 * r + p.cc];
-}
-LG_DEV void seg_store_rows(const SegPos& p, const u64 (&x)[16]) {
-    ulonglong2* row = reinterpret_cast<ulonglong2*>(p.sm + 18 * p.cc);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) row[r] = make_ulonglong2(x[2 * r], x[2 * r + 1]);
 }
 LG_DEV void seg_load_rows(const SegPos& p, u64 (&x)[16]) {
     const ulonglong2* row = reinterpret_cast<const ulonglong2*>(p.sm + 18 * p.cc);
@@ -510,6 +504,144 @@ LG_DEV void prefetch_warp_tile(u64* buf, const u64* __restrict__ src_tile) {
     cp_async_commit();
 }
 
+// Twiddles of one 2048-word tile: thread-private slots for the register block on the natural layout
+// (words 16cc + r), one copy per segment for the block on the column layout (words cc + 16r).
+template <int MODE>
+LG_DEV void contig_fill_tw(const TwConst& c, u32 N, u32 segbase, u32 cc, u64* twp, u64* twseg) {
+    u64 w[8];
+    const u32 tb = N + segbase + 16 * cc;
+#define LG_FILL(U, SLOT)                                                    \
+    load_tw<true, (16 >> (U + 1))>(w, c.tw, tb >> (U + 1));                 \
+    _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[(SLOT + g) * CONTIG_THREADS] = w[g]; \
+    if (MODE != M_LITERAL) {                                                \
+        load_tw<true, (16 >> (U + 1))>(w, c.tws, tb >> (U + 1));            \
+        _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[(15 + SLOT + g) * CONTIG_THREADS] = w[g]; \
+    }
+    LG_FILL(3, 0)
+    LG_FILL(2, 1)
+    LG_FILL(1, 3)
+    LG_FILL(0, 7)
+#undef LG_FILL
+    if (cc < 15) {  // node m = (N + segbase) >> 8 and its 15 descendants in heap order
+        const u32 lvl = 31 - __clz(cc + 1);
+        const u32 idx = (((N + segbase) >> 8) << lvl) + (cc + 1 - (1u << lvl));
+        twseg[cc] = __ldg(c.tw + idx);
+        if (MODE != M_LITERAL) twseg[15 + cc] = __ldg(c.tws + idx);
+    }
+}
+
+// same fetch with the 16-byte chunks of every 16-word row rotated by the row index (chunk p of row r at
+// r*8 + (p ^ (r & 7))), so that threads reading whole rows with 128-bit loads do not collide
+LG_DEV void prefetch_warp_tile_rows(u64* buf, const u64* __restrict__ src_tile) {
+    const u32 lane = threadIdx.x & 31, wbase = (threadIdx.x >> 5) * 512u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const u32 u = lane + 32u * k, seg = u >> 7, v = u & 127u, row = v >> 3, pp = v & 7u;
+        cp_async16(buf + wbase + 2u * (seg * 128u + row * 8u + (pp ^ (row & 7u))), src_tile + wbase + 2u * u);
+    }
+    cp_async_commit();
+}
+
+// ---- contiguous phase of the plain transforms, pipelined over batch entries ------------------------
+// One CTA takes the same tile of up to `bpc` batch entries: the twiddles are staged once, entry i+1 is
+// fetched with cp.async while entry i is transformed (same structure as the key-switch digit loop).
+// Single tile buffer (48 KiB of shared memory per CTA, 4 CTAs/SM): the fetch of entry i+1 is issued as soon
+// as entry i has left the buffer for good (after the exchange), and lands during the second register block.
+#define PIPE_SMEM_WORDS (2048 + 30 * CONTIG_THREADS + 8 * 32)
+template <bool FWD, int MODE>
+LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int b0, int nb, u64* smem) {
+    const u32 N = a.T.N;
+    const int j = blockIdx.z;
+    const TwConst c = tw_const<FWD, MODE>(a.T, lc, tl);
+    const u32 t = threadIdx.x, sg = t >> 4, cc = t & 15;
+    const u32 tile0 = blockIdx.y * CONTIG_TILE;
+    const u32 segbase = tile0 + sg * 256u;
+    const u32 e0 = segbase + 16 * cc, j0 = segbase + cc;
+    u64* const tilebuf = smem;
+    u64* const buf = smem + sg * 256;
+    u64* const twp = smem + 2048 + t;
+    u64* const twseg = smem + 2048 + 30 * CONTIG_THREADS + sg * 32;
+    const u64* src = a.in + (size_t)b0 * a.in_bstride + (size_t)j * N + tile0;
+    u64* dst = a.out + (size_t)b0 * a.out_bstride + (size_t)j * N;
+    if (FWD)
+        prefetch_warp_tile(tilebuf, src);
+    else
+        prefetch_warp_tile_rows(tilebuf, src);
+    contig_fill_tw<MODE>(c, N, segbase, cc, twp, twseg);
+#pragma unroll 1
+    for (int i = 0; i < nb; ++i, dst += a.out_bstride) {
+        u64 x[16];
+        cp_async_wait_all();
+        __syncwarp();
+        if (FWD) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = buf[cc + 16 * r];
+            fwd_stages_sm<3, 1, MODE>(x, c, twseg, twseg + 15);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) buf[16 * r + (cc ^ r)] = x[r];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = buf[16 * cc + (r ^ cc)];
+            __syncwarp();
+            if (i + 1 < nb) prefetch_warp_tile(tilebuf, src + (size_t)(i + 1) * a.in_bstride);
+            fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS);
+            // ring/ntt.go:83-85
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                st256(dst + e0 + 4 * h, bred_add(x[4 * h], c.q, lc.u0), bred_add(x[4 * h + 1], c.q, lc.u0),
+                      bred_add(x[4 * h + 2], c.q, lc.u0), bred_add(x[4 * h + 3], c.q, lc.u0));
+        } else {
+            const ulonglong2* row = reinterpret_cast<const ulonglong2*>(buf + 16 * cc);
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+                const ulonglong2 v = row[pp ^ (cc & 7)];
+                x[2 * pp] = v.x;
+                x[2 * pp + 1] = v.y;
+            }
+            inv_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS, 0u);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) buf[16 * cc + (r ^ cc)] = x[r];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = buf[16 * r + (cc ^ r)];
+            __syncwarp();
+            if (i + 1 < nb) prefetch_warp_tile_rows(tilebuf, src + (size_t)(i + 1) * a.in_bstride);
+            inv_stages_sm<3, 1, MODE>(x, c, twseg, twseg + 15, 4u);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) dst[j0 + 16 * r] = x[r];
+        }
+    }
+}
+
+template <bool FWD, bool LITERAL>
+__global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttArgs a, int batch, int bpc) {
+    extern __shared__ __align__(16) u64 ks_smem[];
+    const int j = blockIdx.z;
+    if (j >= a.skip0 && j < a.skip1) return;
+    const int tl = a.map(j);
+    const LimbConst lc = load_limb_const(a.T, tl);
+    const int b0 = blockIdx.x * bpc, nb = (batch - b0) < bpc ? (batch - b0) : bpc;
+    int mode;
+    if (FWD) {
+        mode = LITERAL ? M_LITERAL : fwd_mode(lc.q);
+    } else {
+        bool flagged = LITERAL;  // one flagged entry makes the whole group literal (always exact)
+        if (a.flags != nullptr)
+            for (int i = 0; i < nb; ++i) flagged |= a.flags[(size_t)(b0 + i) * gridDim.z + j] != 0;
+        mode = flagged ? M_LITERAL : inv_mode(lc.q);
+    }
+    if (mode == M_F64)
+        contig_pipe_body<FWD, FWD ? M_F64 : M_FREE>(a, lc, tl, b0, nb, ks_smem);
+    else if (mode == M_FREE)
+        contig_pipe_body<FWD, M_FREE>(a, lc, tl, b0, nb, ks_smem);
+    else if (mode == M_LAZY)
+        contig_pipe_body<FWD, M_LAZY>(a, lc, tl, b0, nb, ks_smem);
+    else
+        contig_pipe_body<FWD, M_LITERAL>(a, lc, tl, b0, nb, ks_smem);
+}
+
 // LAZYACC: beta * 2q fits 64 bits, so the products are accumulated unreduced (MRedConstant, in (0,2q)).
 template <int MODE, bool LAZYACC>
 LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64* smem) {
@@ -529,29 +661,7 @@ LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64
     const int own_i = (j < a.nl) ? j / a.alpha : -1;  // the digit whose own limb this is
     if (own_i != 0) prefetch_warp_tile(tilebuf, din);
 
-    // twiddles of the tile, once for all digits
-    {
-        u64 w[8];
-        const u32 tb = N + e0;
-#define LG_FILL(U, SLOT)                                                    \
-    load_tw<true, (16 >> (U + 1))>(w, c.tw, tb >> (U + 1));                 \
-    _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[(SLOT + g) * CONTIG_THREADS] = w[g]; \
-    if (MODE != M_LITERAL) {                                                \
-        load_tw<true, (16 >> (U + 1))>(w, c.tws, tb >> (U + 1));            \
-        _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[(15 + SLOT + g) * CONTIG_THREADS] = w[g]; \
-    }
-        LG_FILL(3, 0)
-        LG_FILL(2, 1)
-        LG_FILL(1, 3)
-        LG_FILL(0, 7)
-#undef LG_FILL
-        if (cc < 15) {  // first block: node m = (N + segbase) >> 8 and its 15 descendants in heap order
-            const u32 lvl = 31 - __clz(cc + 1);
-            const u32 idx = (((N + segbase) >> 8) << lvl) + (cc + 1 - (1u << lvl));
-            twseg[cc] = __ldg(c.tw + idx);
-            if (MODE != M_LITERAL) twseg[15 + cc] = __ldg(c.tws + idx);
-        }
-    }
+    contig_fill_tw<MODE>(c, N, segbase, cc, twp, twseg);  // twiddles of the tile, once for all digits
 
     const u64* key = a.evk + (size_t)tl * N + e0;
     u64 acc0[16], acc1[16];
@@ -638,48 +748,8 @@ __global__ void __launch_bounds__(CONTIG_THREADS, 3) ks_fused_kernel(const KsFus
     }
 }
 
-// ---- inverse, contiguous phase: first 8 stages -------------------------------
-template <int MODE>
-LG_DEV void inv_contig_body(const NttArgs& a, const LimbSetup& s, const SegPos& p) {
-    const TwConst c = tw_const<false, MODE>(a.T, s.c, s.tl);
-    const u32 N = a.T.N;
-    const u32 e0 = p.segbase + 16 * p.cc;
-    u64 x[16];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-        u64 v[4];
-        ld256(v, s.in + e0 + 4 * h);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) x[4 * h + e] = v[e];
-    }
-    inv_stages<3, true, MODE>(x, c, N + e0, 0u);
-    __syncwarp();
-    seg_store_rows(p, x);
-    __syncwarp();
-    seg_load_cols(p, x);
-    const u32 j0 = p.segbase + p.cc;
-    inv_stages<3, false, MODE>(x, c, (N + j0) >> 4, 4u);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) s.out[j0 + 16 * r] = x[r];
-}
-
 LG_DEV bool inv_flagged(const NttArgs& a) {
     return a.flags != nullptr && a.flags[(size_t)blockIdx.x * gridDim.z + blockIdx.z] != 0;
-}
-
-template <bool LITERAL>
-__global__ void __launch_bounds__(CONTIG_THREADS) ntt_inv_contig(const NttArgs a) {
-    __shared__ __align__(16) u64 smem[8 * SEG_SM];
-    const LimbSetup s = setup_limb(a);
-    if (s.skip) return;
-    const SegPos p = seg_pos(smem);
-    const int mode = (LITERAL || inv_flagged(a)) ? M_LITERAL : inv_mode(s.c.q);
-    if (mode == M_FREE)
-        inv_contig_body<M_FREE>(a, s, p);
-    else if (mode == M_LAZY)
-        inv_contig_body<M_LAZY>(a, s, p);
-    else
-        inv_contig_body<M_LITERAL>(a, s, p);
 }
 
 // ---- inverse, strided phase: last L stages + MRed by N^-1 --------------------
@@ -727,7 +797,7 @@ LG_DEV void inv_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
 }
 
 template <int L, bool LITERAL>
-__global__ void __launch_bounds__(256) ntt_inv_strided(const NttArgs a) {
+__global__ void __launch_bounds__(256, STRIDED_MINB) ntt_inv_strided(const NttArgs a) {
     __shared__ u64 sm[(L - 4) > 0 ? 4096 : 1];
     __shared__ u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
     const LimbSetup s = setup_limb(a);
@@ -825,6 +895,30 @@ void launch_strided_any(int L, bool fwd, bool literal, const NttArgs& a, dim3 gr
     }
 }
 
+// entries per CTA of the pipelined contiguous phase: as many as keep about two waves of CTAs in flight
+template <bool FWD, bool LITERAL>
+void launch_contig_pipe_t(const NttArgs& a, int nlimbs, int batch, cudaStream_t st) {
+    const int tiles = (int)(a.T.N / CONTIG_TILE);
+    int bpc = batch < 8 ? batch : 8;
+    while (bpc > 1 && (long)tiles * nlimbs * ((batch + bpc - 1) / bpc) < 2L * 148 * 4) bpc = (bpc + 1) / 2;
+    const size_t smem = PIPE_SMEM_WORDS * sizeof(u64);
+    cudaFuncSetAttribute(ntt_contig_pipe<FWD, LITERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ntt_contig_pipe<FWD, LITERAL><<<dim3((batch + bpc - 1) / bpc, tiles, nlimbs), CONTIG_THREADS, smem, st>>>(a, batch, bpc);
+}
+void launch_contig_pipe(bool fwd, bool literal, const NttArgs& a, int nlimbs, int batch, cudaStream_t st) {
+    if (fwd) {
+        if (literal)
+            launch_contig_pipe_t<true, true>(a, nlimbs, batch, st);
+        else
+            launch_contig_pipe_t<true, false>(a, nlimbs, batch, st);
+    } else {
+        if (literal)
+            launch_contig_pipe_t<false, true>(a, nlimbs, batch, st);
+        else
+            launch_contig_pipe_t<false, false>(a, nlimbs, batch, st);
+    }
+}
+
 bool literal_ntt() {
     static const bool v = [] {
         const char* e = getenv("LATTIGPU_LITERAL_NTT");
@@ -872,16 +966,10 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
             else
                 ntt_fwd_contig<true, false><<<cgrid, CONTIG_THREADS, 0, st>>>(second);
         } else {
-            if (literal)
-                ntt_fwd_contig<false, true><<<cgrid, CONTIG_THREADS, 0, st>>>(second);
-            else
-                ntt_fwd_contig<false, false><<<cgrid, CONTIG_THREADS, 0, st>>>(second);
+            launch_contig_pipe(true, literal, second, nlimbs, batch, st);
         }
     } else {
-        if (literal)
-            ntt_inv_contig<true><<<cgrid, CONTIG_THREADS, 0, st>>>(args);
-        else
-            ntt_inv_contig<false><<<cgrid, CONTIG_THREADS, 0, st>>>(args);
+        launch_contig_pipe(false, literal, args, nlimbs, batch, st);
         launch_strided_any(L, false, literal, second, sgrid, st);
     }
     lg_g_launches += 2;
