@@ -292,14 +292,33 @@ def run_gpu(args):
     alg_bytes = 16.0 * N * nlimbs_launch  # one limb-NTT reads and writes N words once
     achieved = alg_bytes / (fwd_us * 1e-6) / 1e9
     butterflies = (N // 2) * p["LogN"] * nlimbs_launch
+    # ncu --set full DRAM bytes of the same launch pair (profiles/r01_ncu_ntt_fwd.json, captured per round)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_ntt_fwd.json")) as f:
+            prof = json.load(f)
+        if prof.get("limb_ntts_per_launch") == nlimbs_launch and prof.get("N") == N:
+            traffic = prof["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    # INT-side ceiling: register-resident butterfly rates measured on this GPU (profiles/microbench/
+    # fast_butterfly.cu, profiles/r01_butterfly_peaks.txt): FP64-quotient butterfly for moduli below 3*2^44,
+    # the 16-instruction Shoup butterfly below 2^56, the [0,8q) butterfly above
+    peak_bf = {"f64": 1.488e12, "free": 1.151e12, "lazy": 0.950e12}
+    mix = {"f64": sum(1 for q in Q if q < (3 << 44)), "free": sum(1 for q in Q if (3 << 44) <= q < (1 << 56)),
+           "lazy": sum(1 for q in Q if q >= (1 << 56))}
+    bf_per_limb = (N // 2) * p["LogN"]
+    int_floor_us = 1e6 * B * sum(mix[k] * bf_per_limb / peak_bf[k] for k in mix)
     roofline = {
-        "bound": "hbm", "kernel": "ntt_fwd (strided + contiguous phase, one batched limb-NTT launch pair)",
-        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+        "bound": "hbm", "kernel": "ntt_fwd (strided phase + pipelined contiguous phase, one batched limb-NTT launch pair)",
+        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "limb_ntts_per_launch": nlimbs_launch,
         "launch_us": fwd_us,
-        # the kernel is INT-pipe bound before it is HBM bound: 11 32x32 multiplies per butterfly
-        "int_pipe": {"butterflies_per_s": butterflies / (fwd_us * 1e-6), "imad_per_butterfly_min": 11,
-                     "gimad_per_s": 11 * butterflies / (fwd_us * 1e-6) / 1e9},
+        # the kernel is INT-pipe bound before it is HBM bound (quote the slower bound)
+        "int_pipe": {"butterflies_per_s": butterflies / (fwd_us * 1e-6),
+                     "butterfly_peak_per_s": butterflies / (int_floor_us * 1e-6),
+                     "frac": int_floor_us / fwd_us, "limb_mix": mix,
+                     "peak_source": "profiles/r01_butterfly_peaks.txt (register-resident microbenchmark, this GPU type)"},
     }
 
     # ---- e2e: host buffers through the C ABI ------------------------------------

@@ -48,6 +48,7 @@ typedef struct lg_galois lg_galois;         /* []uint64 index of PermuteNTTIndex
 typedef struct lg_ckks_eval lg_ckks_eval;   /* hot ops of ckks.evaluator, ckks/evaluator.go:64-76 */
 typedef struct lg_bfv_eval lg_bfv_eval;     /* hot ops of bfv.evaluator,  bfv/evaluator.go:41-60 */
 typedef struct lg_swk lg_swk;               /* ckks/bfv SwitchingKey.evakey [beta][2] QP polys, ckks/keygen.go:282-340 */
+typedef struct lg_hoisted lg_hoisted;       /* c2QiQDecomp/c2QiPDecomp of RotateHoisted, ckks/evaluator.go:1261-1273 */
 typedef struct lg_comm lg_comm;             /* ranks of one node (NCCL over NVLink); no counterpart in the reference */
 typedef void* lg_stream_t;                  /* cudaStream_t */
 
@@ -218,6 +219,15 @@ int lg_ckks_switch_keys(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
 /* permuteNTT :1452-1472 = RotateColumns with a direct key (:1220) / Conjugate (:1449) */
 int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_galois* g, const lg_swk* k,
                         lg_poly* out0, lg_poly* out1, lg_stream_t s);
+
+/* RotateHoisted :1252-1289.  lg_ckks_hoist is the precomputation (:1258-1273): InvNTT of value[1] and
+ * decomposeAndSplitNTT of every digit, kept on the device in the returned handle; lg_ckks_switch_key_hoisted
+ * is switchKeyHoisted (:1291-1392, ct0 != ctOut branch) for one rotation: g = permuteNTTLeftIndex[k],
+ * key = evakeyRotColLeft[k].  out0 must not alias c0 (PermuteNTTWithIndex is not in place). */
+int lg_ckks_hoist(lg_ckks_eval* e, int level, const lg_poly* c1, lg_hoisted** out, lg_stream_t s);
+int lg_ckks_switch_key_hoisted(lg_ckks_eval* e, const lg_hoisted* h, const lg_poly* c0, const lg_galois* g, const lg_swk* k,
+                               lg_poly* out0, lg_poly* out1, lg_stream_t s);
+int lg_hoisted_destroy(lg_hoisted* h);
 
 /* ---- evaluator key-switch path, bfv/evaluator.go ----------------------------- */
 /* NewEvaluator :62-104 (ring part): contexts Q, QMul, P; baseconverterQ1Q2, baseconverterQ1P, decomposer, pHalf */

@@ -699,6 +699,138 @@ int lg_ckks_switch_keys(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
                             false);
 }
 
+int lg_ckks_hoist(lg_ckks_eval* e, int level, const lg_poly* c1, lg_hoisted** out, lg_stream_t s) {
+    LG_REQUIRE(e && out, "RotateHoisted: null argument");
+    const lg_ring* Q = e->Q;
+    const lg_ring* QP = e->QP.get();
+    const u64 N = Q->N;
+    const int nQ = Q->nl, nP = e->P->nl, nl = level + 1, nd = nl + nP, alpha = e->alpha;
+    LG_REQUIRE(level >= 0 && nl <= nQ, "RotateHoisted: level %d out of range", level);
+    LG_REQUIRE(Q->logN >= 12, "RotateHoisted: ring degree below 2^12 is not supported by the hoisted path");
+    LG_TRY(check_p(c1, N, nl, -1, "RotateHoisted"));
+    const int batch = c1->batch;
+    const int beta = (nl + alpha - 1) / alpha;  // :1259
+    cudaStream_t st = cs(s);
+    std::unique_ptr<lg_hoisted> h(new lg_hoisted);
+    h->N = N;
+    h->level = level;
+    h->beta = beta;
+    h->batch = batch;
+    h->nd = nd;
+    h->d_bs = (size_t)nd * N;
+    h->d_ds = (size_t)batch * h->d_bs;
+    LG_CUDA_CHECK(cudaMalloc((void**)&h->d, (size_t)beta * h->d_ds * sizeof(u64)));
+    auto fail = [&](int rc) {
+        cudaFree(h->d);
+        h->d = nullptr;
+        return rc;
+    };
+    Scratch c2(st);
+    int rc = c2.alloc((size_t)batch * nl * N);
+    if (rc != LG_OK) return fail(rc);
+    const size_t c2_bs = (size_t)nl * N;
+    // :1256  c2InvNTT = InvNTT(value[1])
+    rc = lgi_ntt(Q, limb_map_identity(), nl, batch, c1->d, c1->bstride, c2.d, c2_bs, true, 0, 0, st);
+    if (rc != LG_OK) return fail(rc);
+    // :1267-1272 decomposeAndSplitNTT of every digit: decompose, forward NTT of the limbs outside the digit
+    // (one digit-batched launch pair), the digit's own limbs copied from the NTT-domain input (:1579-1584)
+    for (int i = 0; i < beta; ++i) {
+        u64* Di = h->d + (size_t)i * h->d_ds;
+        rc = lgi_decompose(e->dec.get(), level, i, batch, c2.d, c2_bs, Di, h->d_bs, Di + (size_t)nl * N, h->d_bs, st);
+        if (rc != LG_OK) return fail(rc);
+        const int p0 = i * alpha, p1 = (p0 + alpha < nl) ? p0 + alpha : nl;
+        rc = lgi_ew(EW_COPY, Q, limb_map_identity(), p1 - p0, batch, c1->d + (size_t)p0 * N, c1->bstride, nullptr, 0,
+                    Di + (size_t)p0 * N, h->d_bs, nullptr, 0, st);
+        if (rc != LG_OK) return fail(rc);
+    }
+    NttArgs a;
+    memset(&a, 0, sizeof(a));
+    a.T = QP->T;
+    a.map = LimbMap{nl, 0, nQ};
+    a.in = h->d;
+    a.out = h->d;
+    a.in_bstride = a.out_bstride = h->d_bs;
+    a.skip_alpha = alpha;
+    a.skip_div = batch;
+    a.skip_nl = nl;
+    if (lg_launch_ntt(a, nd, beta * batch, false, st) != 0) {
+        lg_set_error("RotateHoisted: unsupported ring degree 2^%u", Q->logN);
+        return fail(LG_ERR_ARG);
+    }
+    if (cudaPeekAtLastError() != cudaSuccess) {
+        lg_set_error("RotateHoisted: kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(LG_ERR_CUDA);
+    }
+    *out = h.release();
+    return LG_OK;
+}
+
+int lg_hoisted_destroy(lg_hoisted* h) {
+    if (h && h->d) cudaFree(h->d);
+    delete h;
+    return LG_OK;
+}
+
+int lg_ckks_switch_key_hoisted(lg_ckks_eval* e, const lg_hoisted* h, const lg_poly* c0, const lg_galois* g, const lg_swk* k,
+                               lg_poly* out0, lg_poly* out1, lg_stream_t s) {
+    LG_REQUIRE(e && h && g && k, "switchKeyHoisted: null argument");
+    const lg_ring* Q = e->Q;
+    const lg_ring* QP = e->QP.get();
+    const u64 N = Q->N;
+    const int nQ = Q->nl, nP = e->P->nl, level = h->level, nl = level + 1, nd = nl + nP;
+    LG_REQUIRE(h->N == N && h->nd == nd, "switchKeyHoisted: decomposition does not match the evaluator");
+    LG_REQUIRE(g->N == N, "switchKeyHoisted: index length mismatch");
+    LG_REQUIRE(k->N == N && k->nQP == nQ + nP, "switchKeyHoisted: switching key shape mismatch");
+    LG_REQUIRE(h->beta <= k->beta, "switchKeyHoisted: key has %d digits, %d needed", k->beta, h->beta);
+    const int batch = h->batch;
+    LG_TRY(check_p(c0, N, nl, batch, "switchKeyHoisted"));
+    LG_TRY(check_p(out0, N, nl, batch, "switchKeyHoisted"));
+    LG_TRY(check_p(out1, N, nl, batch, "switchKeyHoisted"));
+    LG_REQUIRE(c0->d != out0->d, "switchKeyHoisted: PermuteNTTWithIndex is not in place (ctOut must differ from ct0)");
+    cudaStream_t st = cs(s);
+    // :1318-1320  ctOut.value[0] = Permute(ct0.value[0])
+    PermArgs pa;
+    memset(&pa.T, 0, sizeof(pa.T));
+    pa.T.N = (u32)N;
+    pa.T.logN = Q->logN;
+    pa.map = limb_map_identity();
+    pa.index = g->d_index.d;
+    pa.gen = 0;
+    pa.in = c0->d;
+    pa.in_bs = c0->bstride;
+    pa.out = out0->d;
+    pa.out_bs = out0->bstride;
+    lg_launch_permute_ntt(pa, nl, batch, st);
+    LG_LAUNCH_CHECK();
+    // :1336-1378 the digit loop on permuted digits
+    Scratch acc(st);
+    LG_TRY(acc.alloc((size_t)2 * batch * h->d_bs));
+    u64* acc0 = acc.d;
+    u64* acc1 = acc.d + (size_t)batch * h->d_bs;
+    KsHoistArgs ka;
+    memset(&ka, 0, sizeof(ka));
+    ka.T = QP->T;
+    ka.map = LimbMap{nl, 0, nQ};
+    ka.D = h->d;
+    ka.d_ds = h->d_ds;
+    ka.d_bs = h->d_bs;
+    ka.index = g->d_index.d;
+    ka.evk = k->key(0, 0);
+    ka.evk_ds = (size_t)(k->key(1, 0) - k->key(0, 0));
+    ka.evk_hs = (size_t)(k->key(0, 1) - k->key(0, 0));
+    ka.acc0 = acc0;
+    ka.acc1 = acc1;
+    ka.acc_bs = h->d_bs;
+    ka.beta = h->beta;
+    LG_REQUIRE(lg_launch_ks_hoisted(ka, nd, batch, st) == 0, "switchKeyHoisted: launch failed");
+    LG_LAUNCH_CHECK();
+    // :1382-1386  ModDown both; value[0] += pool2Q, value[1] = pool3Q
+    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc0, h->d_bs, acc0 + (size_t)nl * N, h->d_bs, out0->d,
+                                out0->bstride, true, st, true, true));
+    return lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc1, h->d_bs, acc1 + (size_t)nl * N, h->d_bs, out1->d,
+                                out1->bstride, true, st, false, true);
+}
+
 int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_galois* g, const lg_swk* k,
                         lg_poly* out0, lg_poly* out1, lg_stream_t s) {
     LG_REQUIRE(e && g, "permuteNTT: null argument");

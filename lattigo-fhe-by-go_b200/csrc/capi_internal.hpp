@@ -131,6 +131,14 @@ struct lg_swk {
     const u64* key(int digit, int half) const { return d + ((size_t)(digit * 2 + half) * nQP) * N; }
 };
 
+// RotateHoisted precomputation: the NTT-domain digits of value[1] (ckks/evaluator.go:1258-1273)
+struct lg_hoisted {
+    u64* d = nullptr;  // [beta][batch][level+1+nP][N]
+    u64 N = 0;
+    int level = 0, beta = 0, batch = 0, nd = 0;
+    size_t d_bs = 0, d_ds = 0;
+};
+
 struct lg_ckks_eval {
     const lg_ring* Q = nullptr;
     const lg_ring* P = nullptr;

@@ -202,6 +202,24 @@ struct KsMacArgs {
 };
 int lg_launch_ks_mac(const KsMacArgs& a, int nlimbs, int batch, cudaStream_t st);
 
+// Hoisted key-switch (ckks/evaluator.go:1336-1378): acc0/acc1 = sum_i MRed(evk[i][0/1], D[i][index[.]]),
+// the NTT-domain digits D gathered through the Galois index table, accumulators in registers over the
+// digits, one canonical store.
+struct KsHoistArgs {
+    RingTables T;       // QP tables
+    LimbMap map;
+    const u64* D;       // NTT-domain digits: limb j of batch b of digit i at D + i*d_ds + b*d_bs + j*N
+    size_t d_ds, d_bs;
+    const u32* index;   // permuteNTT index table (N entries)
+    const u64* evk;
+    size_t evk_ds, evk_hs;
+    u64* acc0;
+    u64* acc1;
+    size_t acc_bs;
+    int beta;
+};
+int lg_launch_ks_hoisted(const KsHoistArgs& a, int nlimbs, int batch, cudaStream_t st);
+
 // fused tensor product of MulRelin (ckks/evaluator.go:1076-1095); limb j = table limb j
 struct TensorArgs {
     RingTables T;

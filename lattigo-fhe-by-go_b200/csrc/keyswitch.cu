@@ -83,7 +83,70 @@ __global__ void __launch_bounds__(256) tensor_kernel(const TensorArgs a) {
     }
 }
 
+// Hoisted key-switch multiply-accumulate: four consecutive outputs per thread (256-bit key loads), the
+// digit values gathered through the index table.  The NTT-domain automorphism maps aligned blocks onto
+// aligned blocks (the high bits of index[i] depend only on the high bits of i), so the gathers of a CTA
+// stay inside one 8 KiB window of the source limb.
+template <bool LAZYACC>
+__device__ __forceinline__ void ks_hoisted_body(const KsHoistArgs& a, const LimbConst& k, int tl) {
+    const int j = blockIdx.z, bt = blockIdx.x;
+    const u32 N = a.T.N;
+    const u32 e0 = 4 * (blockIdx.y * blockDim.x + threadIdx.x);
+    if (e0 >= N) return;
+    const uint4 ix = *reinterpret_cast<const uint4*>(a.index + e0);
+    const u32 idx[4] = {ix.x, ix.y, ix.z, ix.w};
+    const u64* d = a.D + (size_t)bt * a.d_bs + (size_t)j * N;
+    const u64* key = a.evk + (size_t)tl * N + e0;
+    u64 acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int i = 0; i < a.beta; ++i, d += a.d_ds, key += a.evk_ds) {
+        u64 x[4], k0[4], k1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = d[idx[e]];
+        asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(k0[0]), "=l"(k0[1]), "=l"(k0[2]), "=l"(k0[3]) : "l"(key));
+        asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(k1[0]), "=l"(k1[1]), "=l"(k1[2]), "=l"(k1[3])
+                     : "l"(key + a.evk_hs));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (LAZYACC) {
+                acc0[e] += mred_constant(k0[e], x[e], k.q, k.qinv);
+                acc1[e] += mred_constant(k1[e], x[e], k.q, k.qinv);
+            } else {
+                acc0[e] = cred(acc0[e] + mred(k0[e], x[e], k.q, k.qinv), k.q);
+                acc1[e] = cred(acc1[e] + mred(k1[e], x[e], k.q, k.qinv), k.q);
+            }
+        }
+    }
+    u64* o0 = a.acc0 + (size_t)bt * a.acc_bs + (size_t)j * N + e0;
+    u64* o1 = a.acc1 + (size_t)bt * a.acc_bs + (size_t)j * N + e0;
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(o0), "l"(bred_add(acc0[0], k.q, k.u0)),
+                 "l"(bred_add(acc0[1], k.q, k.u0)), "l"(bred_add(acc0[2], k.q, k.u0)), "l"(bred_add(acc0[3], k.q, k.u0))
+                 : "memory");
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(o1), "l"(bred_add(acc1[0], k.q, k.u0)),
+                 "l"(bred_add(acc1[1], k.q, k.u0)), "l"(bred_add(acc1[2], k.q, k.u0)), "l"(bred_add(acc1[3], k.q, k.u0))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256) ks_hoisted_kernel(const KsHoistArgs a) {
+    const int tl = a.map(blockIdx.z);
+    const LimbConst k = load_limb_const(a.T, tl);
+    if ((2 * k.q) <= (~0ull) / (u64)a.beta)
+        ks_hoisted_body<true>(a, k, tl);
+    else
+        ks_hoisted_body<false>(a, k, tl);
+}
+
 }  // namespace
+
+int lg_launch_ks_hoisted(const KsHoistArgs& a, int nlimbs, int batch, cudaStream_t st) {
+    if (nlimbs <= 0 || batch <= 0) return 0;
+    if (a.T.N < 4 || a.beta < 1) return 1;
+    const u32 threads = 256, per = 4 * threads;
+    ks_hoisted_kernel<<<dim3(batch, (a.T.N + per - 1) / per, nlimbs), threads, 0, st>>>(a);
+    lg_g_launches += 1;
+    return 0;
+}
 
 int lg_launch_tensor(const TensorArgs& a, int nlimbs, int batch, cudaStream_t st) {
     if (nlimbs <= 0 || batch <= 0) return 0;

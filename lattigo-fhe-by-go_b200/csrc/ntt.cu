@@ -619,10 +619,15 @@ template <bool FWD, bool LITERAL>
 __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttArgs a, int batch, int bpc) {
     extern __shared__ __align__(16) u64 ks_smem[];
     const int j = blockIdx.z;
-    if (j >= a.skip0 && j < a.skip1) return;
+    const int b0 = blockIdx.x * bpc, nb = (batch - b0) < bpc ? (batch - b0) : bpc;
+    if (a.skip_alpha > 0) {  // digit-batched launch: bpc divides skip_div, so a group never straddles two digits
+        const int dg = b0 / a.skip_div;
+        if (j < a.skip_nl && j >= dg * a.skip_alpha && j < (dg + 1) * a.skip_alpha) return;
+    } else if (j >= a.skip0 && j < a.skip1) {
+        return;
+    }
     const int tl = a.map(j);
     const LimbConst lc = load_limb_const(a.T, tl);
-    const int b0 = blockIdx.x * bpc, nb = (batch - b0) < bpc ? (batch - b0) : bpc;
     int mode;
     if (FWD) {
         mode = LITERAL ? M_LITERAL : fwd_mode(lc.q);
@@ -901,6 +906,8 @@ void launch_contig_pipe_t(const NttArgs& a, int nlimbs, int batch, cudaStream_t 
     const int tiles = (int)(a.T.N / CONTIG_TILE);
     int bpc = batch < 8 ? batch : 8;
     while (bpc > 1 && (long)tiles * nlimbs * ((batch + bpc - 1) / bpc) < 2L * 148 * 4) bpc = (bpc + 1) / 2;
+    if (a.skip_alpha > 0)
+        while (a.skip_div % bpc) --bpc;
     const size_t smem = PIPE_SMEM_WORDS * sizeof(u64);
     cudaFuncSetAttribute(ntt_contig_pipe<FWD, LITERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ntt_contig_pipe<FWD, LITERAL><<<dim3((batch + bpc - 1) / bpc, tiles, nlimbs), CONTIG_THREADS, smem, st>>>(a, batch, bpc);

@@ -153,6 +153,9 @@ SIGNATURES = {
     "lg_ckks_rescale": (ci, [vp, ci, _P, _P, ci, vp]),
     "lg_ckks_switch_keys": (ci, [vp, ci, _P, _P, vp, _P, _P, vp]),
     "lg_ckks_permute_ntt": (ci, [vp, ci, _P, _P, vp, vp, _P, _P, vp]),
+    "lg_ckks_hoist": (ci, [vp, ci, _P, C.POINTER(vp), vp]),
+    "lg_ckks_switch_key_hoisted": (ci, [vp, vp, _P, vp, vp, _P, _P, vp]),
+    "lg_hoisted_destroy": (ci, [vp]),
     "lg_bfv_eval_create": (ci, [_R, _R, _R, u64, C.POINTER(vp)]),
     "lg_bfv_eval_destroy": (ci, [vp]),
     "lg_bfv_mul": (ci, [vp, _P, _P, _P, _P, _P, _P, _P, vp]),

@@ -108,5 +108,19 @@ class Evaluator:
                                         _s(stream)))
 
 
+    def RotateHoisted(self, level, ct0, rotations, ctOuts, stream=None):
+        """RotateHoisted (:1252-1289): `rotations` is a list of (index, rotation key) pairs, i.e.
+        (permuteNTTLeftIndex[k], evakeyRotColLeft[k]); ctOuts[i] receives ct0 rotated by rotations[i].
+        The decomposition of ct0.value[1] is computed once and shared (switchKeyHoisted :1291-1392)."""
+        h = vp()
+        check(lib().lg_ckks_hoist(self.h, level, ct0[1].h, C.byref(h), _s(stream)))
+        try:
+            for (index, key), out in zip(rotations, ctOuts):
+                check(lib().lg_ckks_switch_key_hoisted(self.h, h, ct0[0].h, index.h, key.h, out[0].h, out[1].h, _s(stream)))
+        finally:
+            lib().lg_stream_sync(_s(stream))  # the decomposition must outlive the kernels that read it
+            lib().lg_hoisted_destroy(h)
+
+
 def NewEvaluator(contextQ, contextP):
     return Evaluator(contextQ, contextP)

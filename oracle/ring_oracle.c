@@ -1317,6 +1317,74 @@ API void orc_ckks_permute_ntt(orc_ckks_eval *e, int level, const u64 *ct, const 
     memcpy(out + sz, e->poolQ[2], sizeof(u64) * sz);
 }
 
+/* RotateHoisted precomputation, ckks/evaluator.go:1252-1275: c2InvNTT = InvNTT(ct.value[1]) and, for every
+ * digit, decomposeAndSplitNTT into full-size Q / P polys.  qdec: [beta][nQ][N] (limbs above `level` stay
+ * zero, as in a fresh contextQ.NewPoly()), pdec: [beta][nP][N]. */
+API void orc_ckks_hoist(orc_ckks_eval *e, int level, const u64 *ct, u64 *qdec, u64 *pdec) {
+    const orc_ctx *Q = e->ctxQ, *P = e->ctxP;
+    u64 N = Q->N;
+    int nl = level + 1;
+    const u64 *c2ntt = ct + (u64)nl * N;
+    u64 *c2inv = e->poolQ[3];
+    orc_invntt(Q, nl, c2ntt, c2inv);
+    int beta = (nl + e->alpha - 1) / e->alpha;
+    memset(qdec, 0, sizeof(u64) * (u64)beta * Q->nl * N);
+    memset(pdec, 0, sizeof(u64) * (u64)beta * P->nl * N);
+    for (int i = 0; i < beta; i++)
+        ckks_decompose_and_split_ntt(e, level, i, c2ntt, c2inv, qdec + (u64)i * Q->nl * N, pdec + (u64)i * P->nl * N);
+}
+
+/* switchKeyHoisted, ckks/evaluator.go:1291-1392 (ct0 != ctOut branch).  index = permuteNTTLeftIndex[k],
+ * evk = evakeyRotColLeft[k]; ct, out: [2][level+1][N]. */
+API void orc_ckks_switch_key_hoisted(orc_ckks_eval *e, int level, const u64 *ct, const u64 *qdec, const u64 *pdec,
+                                     const u64 *index, const u64 *evk, u64 *out) {
+    const orc_ctx *Q = e->ctxQ, *P = e->ctxP;
+    u64 N = Q->N;
+    int nl = level + 1, nQP = Q->nl + P->nl;
+    u64 sz = (u64)nl * N;
+    orc_permute_ntt_with_index(N, nl, ct, index, e->ringpool[0]);
+    memcpy(out, e->ringpool[0], sizeof(u64) * sz); /* CopyLvl :1320 */
+    for (int i = 0; i < 4; i++) memset(e->poolQ[i], 0, sizeof(u64) * N * Q->nl);
+    for (int i = 0; i < 3; i++) memset(e->poolP[i], 0, sizeof(u64) * N * P->nl);
+    u64 *c2QiQPermute = e->poolQ[0], *c2QiPPermute = e->poolP[0];
+    u64 *pool2Q = e->poolQ[1], *pool2P = e->poolP[1];
+    u64 *pool3Q = e->poolQ[2], *pool3P = e->poolP[2];
+    u64 reduce = 0;
+    int beta = (nl + e->alpha - 1) / e->alpha;
+    for (int i = 0; i < beta; i++) {
+        orc_permute_ntt_with_index(N, Q->nl, qdec + (u64)i * Q->nl * N, index, c2QiQPermute);
+        orc_permute_ntt_with_index(N, P->nl, pdec + (u64)i * P->nl * N, index, c2QiPPermute);
+        const u64 *k0 = evk + ((u64)(i * 2 + 0) * nQP) * N;
+        const u64 *k1 = evk + ((u64)(i * 2 + 1) * nQP) * N;
+        orc_mulcoeffs_montgomery_and_add_nomod(Q, nl, k0, c2QiQPermute, pool2Q);
+        orc_mulcoeffs_montgomery_and_add_nomod(Q, nl, k1, c2QiQPermute, pool3Q);
+        for (int j = 0, ki = e->levels; j < P->nl; j++, ki++) {
+            u64 pj = P->modulus[j], mp = P->mred[j];
+            for (u64 y = 0; y < N; y++) {
+                pool2P[j * N + y] += orc_mred(k0[ki * N + y], c2QiPPermute[j * N + y], pj, mp);
+                pool3P[j * N + y] += orc_mred(k1[ki * N + y], c2QiPPermute[j * N + y], pj, mp);
+            }
+        }
+        if ((reduce & 7) == 1) {
+            orc_reduce(Q, nl, pool2Q, pool2Q);
+            orc_reduce(Q, nl, pool3Q, pool3Q);
+            orc_reduce(P, P->nl, pool2P, pool2P);
+            orc_reduce(P, P->nl, pool3P, pool3P);
+        }
+        reduce++;
+    }
+    if (((reduce - 1) & 7) != 1) {
+        orc_reduce(Q, nl, pool2Q, pool2Q);
+        orc_reduce(Q, nl, pool3Q, pool3Q);
+        orc_reduce(P, P->nl, pool2P, pool2P);
+        orc_reduce(P, P->nl, pool3P, pool3P);
+    }
+    orc_moddown_splited_ntt_pq(e->ext, level, pool2Q, pool2P, pool2Q);
+    orc_moddown_splited_ntt_pq(e->ext, level, pool3Q, pool3P, pool3Q);
+    orc_add(Q, nl, out, pool2Q, out);
+    memcpy(out + sz, pool3Q, sizeof(u64) * sz);
+}
+
 /* SwitchKeys, ckks/evaluator.go:1176-1189 */
 API void orc_ckks_switch_keys(orc_ckks_eval *e, int level, const u64 *ct, const u64 *evk, u64 *out) {
     const orc_ctx *Q = e->ctxQ;

@@ -123,6 +123,8 @@ def _declare(L):
     f("orc_ckks_rescale", None, vp, C.c_int, p64, C.c_int)
     f("orc_ckks_permute_ntt", None, vp, C.c_int, p64, p64, p64, p64)
     f("orc_ckks_switch_keys", None, vp, C.c_int, p64, p64, p64)
+    f("orc_ckks_hoist", None, vp, C.c_int, p64, p64, p64)
+    f("orc_ckks_switch_key_hoisted", None, vp, C.c_int, p64, p64, p64, p64, p64, p64)
 
 
 def ptr(a):
@@ -394,6 +396,21 @@ class CkksEvaluator:
         out = np.zeros((2, level + 1, self.Q.N), dtype=np.uint64)
         lib().orc_ckks_switch_keys(self.h, level, ptr(ct), ptr(evk), ptr(out))
         return out
+
+    def rotate_hoisted(self, level, ct, indexes, evks):
+        """RotateHoisted (ckks/evaluator.go:1252-1289): one decomposition of ct.value[1] shared by every
+        rotation; indexes[k] = permuteNTTLeftIndex, evks[k] = evakeyRotColLeft of rotation k."""
+        nl = level + 1
+        beta = -(-nl // self.P.nl)
+        qdec = np.zeros((beta, self.Q.nl, self.Q.N), dtype=np.uint64)
+        pdec = np.zeros((beta, self.P.nl, self.Q.N), dtype=np.uint64)
+        lib().orc_ckks_hoist(self.h, level, ptr(ct), ptr(qdec), ptr(pdec))
+        outs = []
+        for index, evk in zip(indexes, evks):
+            out = np.zeros((2, nl, self.Q.N), dtype=np.uint64)
+            lib().orc_ckks_switch_key_hoisted(self.h, level, ptr(ct), ptr(qdec), ptr(pdec), ptr(index), ptr(evk), ptr(out))
+            outs.append(out)
+        return outs
 
 
 def _declare_bfv(L):

@@ -158,6 +158,33 @@ def test_rotate_conjugate_switchkeys_relinearize(lg, params):
             assert np.array_equal(out[1].numpy(nl=nl, squeeze=False)[i], s.oQ.op3("add", np.ascontiguousarray(a[i, 1, :nl]), k1))
 
 
+@pytest.mark.parametrize("params", [PN13, SMALL3, PN14], ids=["PN13", "alpha3", "PN14"])
+@pytest.mark.parametrize("kind", ["reduced", "words"])
+def test_rotate_hoisted(lg, params, kind):
+    """RotateHoisted / switchKeyHoisted (ckks/evaluator.go:1252-1392): one decomposition, several rotations,
+    each with its own rotation key; bit-exact against the oracle at the top level and at a partial level."""
+    s = Setup(lg, params)
+    rng = np.random.default_rng(29)
+    batch = 2
+    a = s.ct(rng, kind, batch)
+    pa = polys(lg, a)
+    rots = [(5, 1), (5, 3), (5, 64)]
+    evks = [s.evk(rng) for _ in rots]
+    keys = [lg.ckks.SwitchingKey(k) for k in evks]
+    for level in (s.nQ - 1, 2 if s.nQ > 3 else 0):
+        nl = level + 1
+        idxs = [lg.ring.PermuteNTTIndex(g, pw, s.N) for g, pw in rots]
+        widx = [orc.permute_ntt_index(g, pw, s.N) for g, pw in rots]
+        outs = [new_ct(lg, s, batch) for _ in rots]
+        s.ev.RotateHoisted(level, pa, list(zip(idxs, keys)), outs)
+        for i in range(batch):
+            want = s.oev.rotate_hoisted(level, np.ascontiguousarray(a[i, :, :nl]), widx, evks)
+            for r in range(len(rots)):
+                assert np.array_equal(host(outs[r], nl)[i], want[r]), (level, rots[r], i)
+    with pytest.raises(lg.LattigpuError, match="not in place"):
+        s.ev.RotateHoisted(s.nQ - 1, pa, [(idxs[0], keys[0])], [pa])
+
+
 def test_error_paths(lg):
     s = Setup(lg, PN12)
     rng = np.random.default_rng(24)

@@ -277,6 +277,60 @@ def test_ckks_keyswitch_semantics(level):
     assert err.bit_length() < 30, err.bit_length()
 
 
+@pytest.mark.parametrize("level", [4, 2])
+def test_ckks_rotate_hoisted_semantics(level):
+    """RotateHoisted / switchKeyHoisted (ckks/evaluator.go:1252-1392): for every requested rotation
+    out0 + out1*s must equal sigma_g(c0 + c1*s) up to key-switch noise, with ONE decomposition of c1
+    shared by all rotations; the rotation key switches sigma_g(s) -> s."""
+    N = 32
+    Q, P = _ckks_small(N)
+    rng = random.Random(40 + level)
+    ctxQ, ctxP, ctxQP = orc.Context(N, Q), orc.Context(N, P), orc.Context(N, Q + P)
+    ev = orc.CkksEvaluator(ctxQ, ctxP)
+    sk = [rng.choice([-1, 0, 1]) for _ in range(N)]
+    nl = level + 1
+    Ql = Q[:nl]
+    Qp = prod(Ql)
+    ctxl = orc.Context(N, Ql)
+
+    def sigma(vals, g, mod):  # X -> X^g on coefficient vectors (ring_galois.go:106-127)
+        out = [0] * N
+        for i, v in enumerate(vals):
+            k = (i * g) % (2 * N)
+            if k >= N:
+                out[k - N] = (-v) % mod
+            else:
+                out[k] = v % mod
+        return out
+
+    def negacyclic(a, b, mod):
+        out = [0] * N
+        for x in range(N):
+            for y in range(N):
+                k = x + y
+                if k >= N:
+                    out[k - N] = (out[k - N] - a[x] * b[y]) % mod
+                else:
+                    out[k] = (out[k] + a[x] * b[y]) % mod
+        return out
+
+    c0v = [rng.randrange(Qp) for _ in range(N)]
+    c1v = [rng.randrange(Qp) for _ in range(N)]
+    ct = np.ascontiguousarray(np.stack([ctxQ.ntt(crt_poly(c0v, Ql), nl=nl), ctxQ.ntt(crt_poly(c1v, Ql), nl=nl)]))
+    gens = [pow(5, k, 2 * N) for k in (1, 3)]
+    indexes = [orc.permute_ntt_index(5, k, N) for k in (1, 3)]
+    evks = [_keygen(rng, ctxQP, Q, P, N, [(x if x <= 1 else x - 3) for x in sigma(sk, g, 3)], sk) for g in gens]
+    outs = ev.rotate_hoisted(level, ct, indexes, evks)
+    msg = [(u + v) % Qp for u, v in zip(c0v, negacyclic(c1v, sk, Qp))]
+    for g, out in zip(gens, outs):
+        o0 = crt_reconstruct(ctxl.invntt(np.ascontiguousarray(out[0])), Ql)
+        o1 = crt_reconstruct(ctxl.invntt(np.ascontiguousarray(out[1])), Ql)
+        lhs = [(u + v) % Qp for u, v in zip(o0, negacyclic(o1, sk, Qp))]
+        rhs = sigma(msg, g, Qp)
+        err = max(min((l - r) % Qp, (r - l) % Qp) for l, r in zip(lhs, rhs))
+        assert err.bit_length() < 30, (g, err.bit_length())
+
+
 def test_unreduced_inputs_are_defined():
     """NewPolyUniform feeds full 64-bit words (ring_object.go:26-46); the oracle
     must be total on them (used later as a formula-exactness probe for CUDA)."""
