@@ -413,6 +413,112 @@ class CkksEvaluator:
         return outs
 
 
+# ---------------------------------------------------------------------------
+# CKKS key generator / encryptor / decryptor ring sequences (ckks/keygen.go, ckks/encryptor.go,
+# ckks/decryptor.go), restated as compositions of the oracle's ring ops.  The sampled values are inputs
+# (the reference draws them from crypto/rand): ternary / gaussian coefficients as signed ints.
+# ---------------------------------------------------------------------------
+def signed_residues(moduli, coeffs):
+    c = np.asarray(coeffs, dtype=np.int64)
+    return np.ascontiguousarray(np.stack([np.where(c < 0, np.int64(q) + c, c).astype(np.uint64) for q in moduli]))
+
+
+class CkksScheme:
+    """The non-fast encrypt paths call ModDownPQ(level, pool) with the full QP pool, literally as
+    encryptor.go:223,:348 do (below the top level its "P part" Coeffs[level+1:...] are Q limbs)."""
+
+    def __init__(self, Q, P, N):
+        self.Qm, self.Pm, self.N = list(Q), list(P), N
+        self.Q, self.P, self.QP = Context(N, self.Qm), Context(N, self.Pm), Context(N, self.Qm + self.Pm)
+        self.ext = Extender(self.Q, self.P)
+        self.levels, self.alpha = len(self.Qm), len(self.Pm)
+        self.beta = -(-self.levels // self.alpha)
+        self.Pbig = 1
+        for p in self.Pm:
+            self.Pbig *= int(p)
+
+    def gen_secret_key(self, ternary):  # keygen.go:96-112
+        return self.QP.ntt(self.QP.op2("mform_poly", signed_residues(self.Qm + self.Pm, ternary)))
+
+    def gen_public_key(self, sk, e, a):  # keygen.go:138-151
+        pk0 = self.QP.ntt(signed_residues(self.Qm + self.Pm, e))
+        self.QP.op3("mulcoeffs_montgomery_and_add", sk, np.ascontiguousarray(a), pk0)
+        return self.QP.op2("neg", pk0), np.ascontiguousarray(a).copy()
+
+    def new_switching_key(self, sk_in, sk_out, errors, uniforms):  # keygen.go:282-340
+        QP = self.Qm + self.Pm
+        sk_in = self.QP.mul_scalar(sk_in, [self.Pbig % q for q in QP])
+        evk = np.zeros((self.beta, 2, len(QP), self.N), dtype=np.uint64)
+        for i in range(self.beta):
+            k0 = self.QP.op2("mform_poly", self.QP.ntt(signed_residues(QP, errors[i])))
+            k1 = np.ascontiguousarray(uniforms[i]).copy()
+            for j in range(self.alpha):
+                index = i * self.alpha + j
+                qi = np.uint64(QP[index])
+                t = k0[index] + sk_in[index]
+                k0[index] = np.where(t >= qi, t - qi, t)  # CRed :325
+                if index >= self.levels - 1:
+                    break
+            self.QP.op3("mulcoeffs_montgomery_and_sub", k1, sk_out, k0)
+            evk[i, 0], evk[i, 1] = k0, k1
+        return evk
+
+    def gen_relin_key(self, sk, errors, uniforms):  # keygen.go:190-203
+        return self.new_switching_key(self.QP.op3("mulcoeffs_montgomery", sk, sk), sk, errors, uniforms)
+
+    def gen_rot_key(self, sk, gen, errors, uniforms):  # keygen.go:487-494
+        idx = permute_ntt_index(gen, 1, self.N)
+        return self.new_switching_key(permute_ntt_with_index(sk, idx), sk, errors, uniforms)
+
+    def encrypt_pk(self, level, pt, pk, u, e0, e1, fast=False):  # encryptor.go:179-237
+        nl = level + 1
+        if fast:
+            up = self.Q.ntt(self.Q.op2("mform_poly", signed_residues(self.Qm, u)))
+            c0 = self.Q.op3("mulcoeffs_montgomery", up, np.ascontiguousarray(pk[0][: self.levels]))
+            c1 = self.Q.op3("mulcoeffs_montgomery", up, np.ascontiguousarray(pk[1][: self.levels]))
+            c0 = self.Q.op3("add", c0, self.Q.ntt(signed_residues(self.Qm, e0)))
+            c1 = self.Q.op3("add", c1, self.Q.ntt(signed_residues(self.Qm, e1)))
+            c0, c1 = c0[:nl].copy(), c1[:nl].copy()
+        else:
+            QP = self.Qm + self.Pm
+            up = self.QP.ntt(self.QP.op2("mform_poly", signed_residues(QP, u)))
+            p0 = self.QP.invntt(self.QP.op3("mulcoeffs_montgomery", up, pk[0]))
+            p1 = self.QP.invntt(self.QP.op3("mulcoeffs_montgomery", up, pk[1]))
+            p0 = self.QP.op3("add", p0, signed_residues(QP, e0))
+            p1 = self.QP.op3("add", p1, signed_residues(QP, e1))
+            c0 = self.Q.ntt(self.ext.moddown_pq(level, p0)[:nl].copy(), nl=nl)
+            c1 = self.Q.ntt(self.ext.moddown_pq(level, p1)[:nl].copy(), nl=nl)
+        return np.stack([self.Q.op3("add", c0, np.ascontiguousarray(pt[:nl]), nl=nl), c1])
+
+    def encrypt_sk(self, level, pt, sk, crp, e, fast=False):  # encryptor.go:318-362
+        nl = level + 1
+        if fast:
+            c0 = self.Q.op2("neg", self.Q.op3("mulcoeffs_montgomery", np.ascontiguousarray(crp), np.ascontiguousarray(sk[: self.levels])))
+            c0 = self.Q.op3("add", c0, self.Q.ntt(signed_residues(self.Qm, e)))[:nl].copy()
+            c1 = np.ascontiguousarray(crp[:nl]).copy()
+        else:
+            QP = self.Qm + self.Pm
+            p0 = self.QP.invntt(self.QP.op2("neg", self.QP.op3("mulcoeffs_montgomery", np.ascontiguousarray(crp), sk)))
+            p0 = self.QP.op3("add", p0, signed_residues(QP, e))
+            c0 = self.Q.ntt(self.ext.moddown_pq(level, p0)[:nl].copy(), nl=nl)
+            c1 = self.ext.moddown_ntt_pq(level, np.ascontiguousarray(crp).copy())[:nl].copy()
+        return np.stack([self.Q.op3("add", c0, np.ascontiguousarray(pt[:nl]), nl=nl), c1])
+
+    def decrypt(self, level, ct, sk):  # decryptor.go:53-78
+        nl = level + 1
+        skq = np.ascontiguousarray(sk[:nl])
+        degree = len(ct) - 1
+        pt = np.ascontiguousarray(ct[degree][:nl]).copy()
+        for i in range(degree, 0, -1):
+            pt = self.Q.op3("mulcoeffs_montgomery", pt, skq, nl=nl)
+            pt = self.Q.op3("add", pt, np.ascontiguousarray(ct[i - 1][:nl]), nl=nl)
+            if i & 7 == 7:
+                pt = self.Q.op2("reduce", pt, nl=nl)
+        if degree & 7 != 7:
+            pt = self.Q.op2("reduce", pt, nl=nl)
+        return pt
+
+
 def _declare_bfv(L):
     def f(name, res, *args):
         fn = getattr(L, name)

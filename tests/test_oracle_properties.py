@@ -331,6 +331,81 @@ def test_ckks_rotate_hoisted_semantics(level):
         assert err.bit_length() < 30, (g, err.bit_length())
 
 
+def test_ckks_keygen_encrypt_decrypt_semantics():
+    """Key generator / encryptor / decryptor ring sequences (ckks/keygen.go, encryptor.go, decryptor.go):
+    pk and sk encryption (fast and ModDown paths) decrypt to the message, and a relinearisation key built
+    by newSwitchingKey makes MulRelin + Rescale decrypt to the product (what ckks_test.go checks through
+    the encoder, here at ring level with integer messages)."""
+    N = 32
+    Q, P = _ckks_small(N)
+    rng = random.Random(77)
+    S = orc.CkksScheme(Q, P, N)
+    nQP = len(Q) + len(P)
+    tern = lambda: [rng.choice([-1, 0, 1]) for _ in range(N)]
+    gauss = lambda: [rng.choice([-2, -1, 0, 0, 1, 2]) for _ in range(N)]
+    unif = lambda mods: np.array([[rng.randrange(q) for _ in range(N)] for q in mods], dtype=np.uint64)
+    sk_c = tern()
+    sk = S.gen_secret_key(sk_c)
+    pk = S.gen_public_key(sk, gauss(), unif(Q + P))
+    rlk = S.gen_relin_key(sk, [gauss() for _ in range(S.beta)], [unif(Q + P) for _ in range(S.beta)])
+    level = len(Q) - 1
+    Qp = prod(Q)
+    scale = 1 << 20
+
+    def negacyclic(a, b):
+        out = [0] * N
+        for x in range(N):
+            for y in range(N):
+                k = x + y
+                if k >= N:
+                    out[k - N] -= a[x] * b[y]
+                else:
+                    out[k] += a[x] * b[y]
+        return out
+
+    def centered(vals, mod):
+        return [v if v < mod // 2 else v - mod for v in vals]
+
+    def plaintext(m):
+        return S.Q.ntt(crt_poly([x * scale for x in m], Q))
+
+    m0 = [rng.randrange(-500, 500) for _ in range(N)]
+    m1 = [rng.randrange(-500, 500) for _ in range(N)]
+    cts = {
+        "pk": S.encrypt_pk(level, plaintext(m0), pk, tern(), gauss(), gauss()),
+        "pk_fast": S.encrypt_pk(level, plaintext(m0), pk, tern(), gauss(), gauss(), fast=True),
+        "sk": S.encrypt_sk(level, plaintext(m0), sk, unif(Q + P), gauss()),
+        "sk_fast": S.encrypt_sk(level, plaintext(m0), sk, unif(Q), gauss(), fast=True),
+    }
+    for name, ct in cts.items():
+        dec = centered(crt_reconstruct(S.Q.invntt(S.decrypt(level, ct, sk)), Q), Qp)
+        err = max(abs(d - x * scale) for d, x in zip(dec, m0))
+        assert err < (1 << 12), (name, err)
+    ct1 = S.encrypt_pk(level, plaintext(m1), pk, tern(), gauss(), gauss())
+    ev = orc.CkksEvaluator(S.Q, S.P)
+    prod_ct = ev.rescale(ev.mul_relin(level, np.ascontiguousarray(cts["pk"]), np.ascontiguousarray(ct1), rlk))
+    Ql = Q[:-1]
+    ctxl = orc.Context(N, Ql)
+    dec = centered(crt_reconstruct(ctxl.invntt(S.decrypt(level - 1, prod_ct, sk)), Ql), prod(Ql))
+    want = negacyclic(m0, m1)
+    err = max(abs(d - div_round(w * scale * scale, Q[-1])) for d, w in zip(dec, want))
+    assert err < (1 << 12), err
+    # a rotation key switches sigma_5(sk) back to sk: permuteNTT then decrypts to the rotated message
+    rot = S.gen_rot_key(sk, 5, [gauss() for _ in range(S.beta)], [unif(Q + P) for _ in range(S.beta)])
+    idx = orc.permute_ntt_index(5, 1, N)
+    r = ev.permute_ntt(level, np.ascontiguousarray(cts["pk"]), idx, rot)
+    dec = centered(crt_reconstruct(S.Q.invntt(S.decrypt(level, r, sk)), Q), Qp)
+    want = [0] * N
+    for i, v in enumerate(m0):
+        k = (i * 5) % (2 * N)
+        if k >= N:
+            want[k - N] = -v
+        else:
+            want[k] = v
+    err = max(abs(d - w * scale) for d, w in zip(dec, want))
+    assert err < (1 << 12), err
+
+
 def test_unreduced_inputs_are_defined():
     """NewPolyUniform feeds full 64-bit words (ring_object.go:26-46); the oracle
     must be total on them (used later as a formula-exactness probe for CUDA)."""
