@@ -147,6 +147,13 @@ int lg_ring_invmform(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, l
 int lg_ring_add_scalar(const lg_ring* r, int nl, lg_poly* p1, const uint64_t* scalar, lg_stream_t s);
 int lg_ring_sub_scalar(const lg_ring* r, int nl, lg_poly* p1, const uint64_t* scalar, lg_stream_t s);
 int lg_ring_mul_scalar(const lg_ring* r, int nl, const lg_poly* p1, const uint64_t* scalar, lg_poly* p2, lg_stream_t s);
+/* Inner loops of the CKKS constant ops, ckks/evaluator.go:373-833 (AddConst :433-444, MultByConstAndAdd :590-609,
+ * MultByConst :700-727, MultByi :762-783, DivByi :811-832): per limb one scalar for coefficients [0, N/2) (lo[i]) and one
+ * for [N/2, N) (hi[i]); the scalars (scaleUpExact, MRed by psi^2, MForm) are computed by the host as in the reference.
+ *   add:      p2 = CRed(p1 + s)          mul: p2 = MRed(p1, s)          mul_and_add: p2 = CRed(p2 + MRed(p1, s)) */
+int lg_ring_add_scalar_halves(const lg_ring* r, int nl, const lg_poly* p1, const uint64_t* lo, const uint64_t* hi, lg_poly* p2, lg_stream_t s);
+int lg_ring_mul_scalar_montgomery_halves(const lg_ring* r, int nl, const lg_poly* p1, const uint64_t* lo, const uint64_t* hi, lg_poly* p2, lg_stream_t s);
+int lg_ring_mul_scalar_montgomery_halves_and_add(const lg_ring* r, int nl, const lg_poly* p1, const uint64_t* lo, const uint64_t* hi, lg_poly* p2, lg_stream_t s);
 int lg_ring_mul_by_pow2(const lg_ring* r, int nl, const lg_poly* p1, uint64_t pow2, lg_poly* p2, lg_stream_t s);          /* :629-653 */
 int lg_ring_mult_by_monomial(const lg_ring* r, int nl, const lg_poly* p1, uint64_t deg, lg_poly* p2, lg_stream_t s);      /* :663-723 */
 /* vector = device poly with one limb of N words */

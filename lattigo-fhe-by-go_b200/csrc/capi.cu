@@ -551,6 +551,46 @@ int lg_ring_mul_scalar(const lg_ring* r, int nl, const lg_poly* p1, const uint64
     LG_REQUIRE(scalar, "MulScalar: null scalar");
     return ring_op_scalar(EW_MUL_SCALAR, r, nl, p1, scalar, nl, p2, s, "MulScalar");
 }
+static int ring_op_halves(int op, const lg_ring* r, int nl, const lg_poly* p1, const uint64_t* lo, const uint64_t* hi,
+                          lg_poly* p2, lg_stream_t s, const char* what) {
+    LG_REQUIRE(r && lo && hi, "%s: null argument", what);
+    LG_REQUIRE(nl >= 1 && nl <= r->nl, "%s: %d limbs requested, ring has %d", what, nl, r->nl);
+    LG_TRY(check_poly(r, nl, p1, what));
+    LG_TRY(check_poly(r, nl, p2, what));
+    LG_REQUIRE(p1->batch == p2->batch, "%s: batch mismatch", what);
+    EwArgs g;
+    g.T = r->T;
+    g.map = limb_map_identity();
+    g.a = p1->d;
+    g.b = nullptr;
+    g.c = p2->d;
+    g.a_bs = p1->bstride;
+    g.b_bs = 0;
+    g.c_bs = p2->bstride;
+    g.a_ls = g.b_ls = g.c_ls = r->N;
+    for (int i = 0; i < nl; ++i) {
+        g.s[i] = lo[i];
+        g.shi[i] = hi[i];
+    }
+    if (lg_launch_ew(op, g, nl, p2->batch, cs(s)) != 0) {
+        lg_set_error("%s: bad op", what);
+        return LG_ERR_ARG;
+    }
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+int lg_ring_add_scalar_halves(const lg_ring* r, int nl, const lg_poly* p1, const uint64_t* lo, const uint64_t* hi, lg_poly* p2,
+                              lg_stream_t s) {
+    return ring_op_halves(EW_ADD_SCALAR2, r, nl, p1, lo, hi, p2, s, "AddConst");
+}
+int lg_ring_mul_scalar_montgomery_halves(const lg_ring* r, int nl, const lg_poly* p1, const uint64_t* lo, const uint64_t* hi,
+                                         lg_poly* p2, lg_stream_t s) {
+    return ring_op_halves(EW_MUL_SCALAR_MONT2, r, nl, p1, lo, hi, p2, s, "MultByConst");
+}
+int lg_ring_mul_scalar_montgomery_halves_and_add(const lg_ring* r, int nl, const lg_poly* p1, const uint64_t* lo,
+                                                 const uint64_t* hi, lg_poly* p2, lg_stream_t s) {
+    return ring_op_halves(EW_MUL_SCALAR_MONT2_ADD, r, nl, p1, lo, hi, p2, s, "MultByConstAndAdd");
+}
 int lg_ring_mul_by_pow2(const lg_ring* r, int nl, const lg_poly* p1, uint64_t pow2, lg_poly* p2, lg_stream_t s) {
     // ring.go:629-653: MForm(p1, p2) followed by PowerOf2 of p1's words.  When
     // p1 != p2 the MForm result is overwritten, so only the aliased call sees it.

@@ -46,6 +46,9 @@ LG_DEV u64 ew_apply(u64 a, u64 b, u64 c, const LimbConst& k, u64 s, u64 s2) {
         case EW_SUB_MULMONT_SCALAR: return mred(a + (q - b), s, q, k.qinv);   // ring_basis_extension.go:236-238
         case EW_SUB_MULMONT_SCALAR_ADD: return cred(c + mred(a + (q - b), s, q, k.qinv), q);  // + ckks/evaluator.go:1103
         case EW_COPY: return a;
+        case EW_ADD_SCALAR2: return cred(a + s, q);                           // ckks/evaluator.go:433-444
+        case EW_MUL_SCALAR_MONT2: return mred(a, s, q, k.qinv);               // :700-727, :762-783, :811-832
+        case EW_MUL_SCALAR_MONT2_ADD: return cred(c + mred(a, s, q, k.qinv), q);  // :590-609
     }
     return 0;
 }
@@ -58,7 +61,12 @@ __host__ __device__ constexpr bool ew_reads_b(int op) {
 __host__ __device__ constexpr bool ew_reads_c(int op) {
     return op == EW_MUL_BARRETT_ADD || op == EW_MUL_BARRETT_ADD_NOMOD || op == EW_MULMONT_ADD ||
            op == EW_MULMONT_ADD_NOMOD || op == EW_MULMONT_CONSTANT_ADD_NOMOD || op == EW_MULMONT_SUB ||
-           op == EW_MULMONT_SUB_NOMOD || op == EW_MULVEC_ADD_NOMOD || op == EW_SUB_MULMONT_SCALAR_ADD;
+           op == EW_MULMONT_SUB_NOMOD || op == EW_MULVEC_ADD_NOMOD || op == EW_SUB_MULMONT_SCALAR_ADD ||
+           op == EW_MUL_SCALAR_MONT2_ADD;
+}
+
+__host__ __device__ constexpr bool ew_two_scalars(int op) {
+    return op == EW_ADD_SCALAR2 || op == EW_MUL_SCALAR_MONT2 || op == EW_MUL_SCALAR_MONT2_ADD;
 }
 
 template <int OP>
@@ -79,14 +87,15 @@ __global__ void __launch_bounds__(256) ew_kernel(const EwArgs g) {
         ew_reads_b(OP) ? reinterpret_cast<const ulonglong2*>(g.b + bt * g.b_bs + j * g.b_ls) : nullptr;
     ulonglong2* pc = reinterpret_cast<ulonglong2*>(g.c + bt * g.c_bs + j * g.c_ls);
     const u32 n2 = g.T.N >> 1;
+    const u64 sh = ew_two_scalars(OP) ? g.shi[j < LG_MAX_LIMBS ? j : 0] : 0;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
         const ulonglong2 a = pa[i];
         ulonglong2 b = make_ulonglong2(0, 0), c = make_ulonglong2(0, 0);
         if (ew_reads_b(OP)) b = pb[i];
         if (ew_reads_c(OP)) c = pc[i];
         ulonglong2 r;
-        r.x = ew_apply<OP>(a.x, b.x, c.x, k, s, s2);
-        r.y = ew_apply<OP>(a.y, b.y, c.y, k, s, s2);
+        r.x = ew_apply<OP>(a.x, b.x, c.x, k, (ew_two_scalars(OP) && 2 * i >= n2) ? sh : s, s2);
+        r.y = ew_apply<OP>(a.y, b.y, c.y, k, (ew_two_scalars(OP) && 2 * i + 1 >= n2) ? sh : s, s2);
         pc[i] = r;
     }
 }

@@ -102,6 +102,11 @@ enum EwOp {
     EW_SUB_MULMONT_SCALAR,  // c = MRed(a + (q - b), s_j)   (ModDown / rescale tail)
     EW_SUB_MULMONT_SCALAR_ADD,  // c = CRed(c + MRed(a + (q - b), s_j))  (ModDown tail fused with the AddLvl that follows)
     EW_COPY,
+    // CKKS constant ops (ckks/evaluator.go:373-833): one scalar for the first N/2 coefficients (s_j) and one
+    // for the last N/2 (shi_j) -- a + b*psi^2 and a - b*psi^2 in the NTT domain
+    EW_ADD_SCALAR2,           // c = CRed(a + s)
+    EW_MUL_SCALAR_MONT2,      // c = MRed(a, s)
+    EW_MUL_SCALAR_MONT2_ADD,  // c = CRed(c + MRed(a, s))
     EW_NUM_OPS
 };
 
@@ -114,6 +119,7 @@ struct EwArgs {
     size_t a_bs, b_bs, c_bs;  // batch strides (words); 0 broadcasts one entry over the batch
     size_t a_ls, b_ls, c_ls;  // limb strides (words); normally N, 0 broadcasts one limb
     u64 s[LG_MAX_LIMBS];      // per-data-limb scalars
+    u64 shi[LG_MAX_LIMBS];    // *_SCALAR2 ops: the scalars of the upper half of the coefficients
 };
 int lg_launch_ew(int op, const EwArgs& args, int nlimbs, int batch, cudaStream_t st);
 

@@ -107,6 +107,9 @@ SIGNATURES = {
     "lg_ring_add_scalar": (ci, [_R, ci, _P, p64, vp]),
     "lg_ring_sub_scalar": (ci, [_R, ci, _P, p64, vp]),
     "lg_ring_mul_scalar": (ci, [_R, ci, _P, p64, _P, vp]),
+    "lg_ring_add_scalar_halves": (ci, [_R, ci, _P, p64, p64, _P, vp]),
+    "lg_ring_mul_scalar_montgomery_halves": (ci, [_R, ci, _P, p64, p64, _P, vp]),
+    "lg_ring_mul_scalar_montgomery_halves_and_add": (ci, [_R, ci, _P, p64, p64, _P, vp]),
     "lg_ring_mul_by_pow2": (ci, [_R, ci, _P, u64, _P, vp]),
     "lg_ring_mult_by_monomial": (ci, [_R, ci, _P, u64, _P, vp]),
     "lg_ring_mul_by_vector_montgomery": (ci, [_R, ci, _P, _P, _P, vp]),

@@ -43,6 +43,28 @@ def GenModuli(params):
     return Q, P
 
 
+def scaleUpExact(value, n, q):
+    """ckks/utils.go:22-49.  big.NewFloat(n*value) carries 53 bits, so adding 0.5 rounds like float64
+    addition; Int() truncates.  A negative value whose magnitude is 0 mod q yields q (kept literal)."""
+    x = -n * value if value < 0 else n * value
+    res = int(x + 0.5) % q
+    return q - res if value < 0 else res
+
+
+def _mred(x, y, q, qinv):  # ring/modular_reduction.go:70-79
+    M = (1 << 64) - 1
+    t = x * y
+    h = (((t & M) * qinv) & M) * q >> 64
+    r = ((t >> 64) - h + q) & M
+    return r - q if r >= q else r
+
+
+def _mform(a, q, u0, u1):  # ring/modular_reduction.go:15-22
+    M = (1 << 64) - 1
+    r = (-((a * u0 + ((a * u1) >> 64)) & M) * q) & M
+    return r - q if r >= q else r
+
+
 class SwitchingKey:
     """ckks.SwitchingKey.evakey: [beta][2] polys over QP, NTT + Montgomery form
     (ckks/keygen.go:282-340), uploaded once and shared by every ciphertext of a batch."""
@@ -107,6 +129,91 @@ class Evaluator:
         check(lib().lg_ckks_permute_ntt(self.h, level, ct0[0].h, ct0[1].h, index.h, evakey.h, ctOut[0].h, ctOut[1].h,
                                         _s(stream)))
 
+
+    # ---- constant ops (ckks/evaluator.go:373-833): the per-limb scalars are host arithmetic as in the
+    # reference, the coefficient loops run on the device; scale / level bookkeeping stays with the caller
+    def _tables(self):
+        if not hasattr(self, "_tb"):
+            t = self.contextQ.tables()
+            self._tb = dict(q=[int(x) for x in self.contextQ.Modulus], qinv=[int(x) for x in t["mred"]],
+                            bred=[(int(a), int(b)) for a, b in t["bred"]], psi2=[int(p[1]) for p in t["psi"]])
+        return self._tb
+
+    @staticmethod
+    def _parts(constant):
+        c = complex(constant)
+        return float(c.real), float(c.imag)
+
+    def _const_halves(self, level, cReal, cImag, scale, mont):
+        """[a + b*psi^2] for the first N/2 NTT coefficients, [a - b*psi^2] for the rest (:413-444, :560-609, :684-727)"""
+        tb = self._tables()
+        lo, hi = [], []
+        for i in range(level + 1):
+            q, qinv, (u0, u1) = tb["q"][i], tb["qinv"][i], tb["bred"][i]
+            re = im = sc = 0
+            if cReal != 0:
+                re = scaleUpExact(cReal, scale, q)
+                sc = re
+            if cImag != 0:
+                im = _mred(scaleUpExact(cImag, scale, q), tb["psi2"][i], q, qinv)
+                t = sc + im
+                sc = t - q if t >= q else t
+            first = _mform(sc, q, u0, u1) if mont else sc
+            second = first
+            if cImag != 0:
+                t = re + (q - im)
+                t = t - q if t >= q else t
+                second = _mform(t, q, u0, u1) if mont else t
+            lo.append(first)
+            hi.append(second)
+        return _arr(lo), _arr(hi)
+
+    def AddConst(self, level, ct0, constant, scale, ctOut, stream=None):
+        """:373-448 -- `scale` = ct0.Scale(); only value[0] is touched"""
+        cReal, cImag = self._parts(constant)
+        lo, hi = self._const_halves(level, cReal, cImag, scale, False)
+        check(lib().lg_ring_add_scalar_halves(self.contextQ.h, level + 1, ct0[0].h, _ptr(lo), _ptr(hi), ctOut[0].h, _s(stream)))
+
+    def const_scale(self, constant, default_scale):
+        """the scaling MultByConst / MultByConstAndAdd apply to a constant with a fractional part (:631-668)"""
+        cReal, cImag = self._parts(constant)
+        scale = 1.0
+        if isinstance(constant, (complex, float)):
+            for v in (cReal, cImag):
+                if v != 0 and v - float(int(v)) != 0:
+                    scale = default_scale
+        return scale
+
+    def MultByConst(self, level, ct0, constant, scale, ctOut, stream=None):
+        """:622-730 -- `scale` as returned by const_scale(); every value[u] is multiplied"""
+        cReal, cImag = self._parts(constant)
+        lo, hi = self._const_halves(level, cReal, cImag, scale, True)
+        for a, c in zip(ct0, ctOut):
+            check(lib().lg_ring_mul_scalar_montgomery_halves(self.contextQ.h, level + 1, a.h, _ptr(lo), _ptr(hi), c.h, _s(stream)))
+
+    def MultByConstAndAdd(self, level, ct0, constant, scale, ctOut, stream=None):
+        """:451-610 inner loops (:560-609) -- `scale` is the factor the reference derives from the two scales"""
+        cReal, cImag = self._parts(constant)
+        lo, hi = self._const_halves(level, cReal, cImag, scale, True)
+        for a, c in zip(ct0, ctOut):
+            check(lib().lg_ring_mul_scalar_montgomery_halves_and_add(self.contextQ.h, level + 1, a.h, _ptr(lo), _ptr(hi), c.h,
+                                                                     _s(stream)))
+
+    def _by_i(self, level, ct0, ctOut, div, stream):
+        tb = self._tables()
+        psi2 = [tb["psi2"][i] for i in range(level + 1)]
+        neg = [tb["q"][i] - psi2[i] for i in range(level + 1)]
+        lo, hi = (_arr(neg), _arr(psi2)) if div else (_arr(psi2), _arr(neg))
+        for a, c in zip(ct0, ctOut):
+            check(lib().lg_ring_mul_scalar_montgomery_halves(self.contextQ.h, level + 1, a.h, _ptr(lo), _ptr(hi), c.h, _s(stream)))
+
+    def MultByi(self, level, ct0, ctOut, stream=None):
+        """:746-784: multiplication by X^(N/2)"""
+        self._by_i(level, ct0, ctOut, False, stream)
+
+    def DivByi(self, level, ct0, ctOut, stream=None):
+        """:795-833: multiplication by X^(3N/2)"""
+        self._by_i(level, ct0, ctOut, True, stream)
 
     def RotateHoisted(self, level, ct0, rotations, ctOuts, stream=None):
         """RotateHoisted (:1252-1289): `rotations` is a list of (index, rotation key) pairs, i.e.

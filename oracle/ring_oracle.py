@@ -519,6 +519,69 @@ class CkksScheme:
         return pt
 
 
+# ---------------------------------------------------------------------------
+# CKKS constant ops, ckks/evaluator.go:373-833, restated whole (host scalars + coefficient loops)
+# ---------------------------------------------------------------------------
+def scale_up_exact(value, n, q):  # ckks/utils.go:22-49 (big.Float at 53 bits: x + 0.5 rounds like float64)
+    x = -n * value if value < 0 else n * value
+    res = int(x + 0.5) % q
+    return q - res if value < 0 else res
+
+
+def _mred_vec(a, s, q, qinv):
+    """MRed(a[j], s) for a uint64 vector a (modular_reduction.go:70-79), exact via Python integers"""
+    M = (1 << 64) - 1
+    out = np.empty(a.shape, dtype=np.uint64)
+    for j, x in enumerate(a.tolist()):
+        t = x * s
+        h = (((t & M) * qinv) & M) * q >> 64
+        r = ((t >> 64) - h + q) & M
+        out[j] = r - q if r >= q else r
+    return out
+
+
+def _cred_vec(v, q):
+    return np.where(v >= np.uint64(q), v - np.uint64(q), v)
+
+
+def ckks_const_op(ctx, op, level, polys_in, polys_out, c_real=0.0, c_imag=0.0, scale=1.0):
+    """op in {"add", "mul", "mul_add", "mul_i", "div_i"}: AddConst :373-448 (value[0] only: pass one poly),
+    MultByConst :622-730, MultByConstAndAdd inner loops :560-609, MultByi :746-784, DivByi :795-833.
+    polys_*: lists of [nl][N] arrays (NTT domain); returns the new polys_out."""
+    N = ctx.N
+    h = N >> 1
+    outs = [p.copy() for p in polys_out]
+    for i in range(level + 1):
+        q, qinv = int(ctx.moduli[i]), int(ctx.mred[i])
+        bred = np.ascontiguousarray(ctx.bred[i])
+        psi2 = int(ctx.tables(i)[0][1])
+        if op in ("mul_i", "div_i"):
+            first, second = (psi2, q - psi2) if op == "mul_i" else (q - psi2, psi2)
+        else:
+            re = im = sc = 0
+            if c_real != 0:
+                re = scale_up_exact(c_real, scale, q)
+                sc = re
+            if c_imag != 0:
+                im = int(lib().orc_mred(scale_up_exact(c_imag, scale, q), psi2, q, qinv))
+                sc = int(lib().orc_cred(sc + im, q))
+            first = sc if op == "add" else int(lib().orc_mform(sc, q, ptr(bred)))
+            second = first
+            if c_imag != 0:
+                t = int(lib().orc_cred(re + (q - im), q))
+                second = t if op == "add" else int(lib().orc_mform(t, q, ptr(bred)))
+        for u, pin in enumerate(polys_in):
+            for sl, c in ((slice(0, h), first), (slice(h, N), second)):
+                a = pin[i, sl]
+                if op == "add":
+                    outs[u][i, sl] = _cred_vec(a + np.uint64(c), q)
+                elif op == "mul_add":
+                    outs[u][i, sl] = _cred_vec(outs[u][i, sl] + _mred_vec(a, c, q, qinv), q)
+                else:
+                    outs[u][i, sl] = _mred_vec(a, c, q, qinv)
+    return outs
+
+
 def _declare_bfv(L):
     def f(name, res, *args):
         fn = getattr(L, name)

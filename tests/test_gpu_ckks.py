@@ -185,6 +185,46 @@ def test_rotate_hoisted(lg, params, kind):
         s.ev.RotateHoisted(s.nQ - 1, pa, [(idxs[0], keys[0])], [pa])
 
 
+@pytest.mark.parametrize("params", [PN13, SMALL3], ids=["PN13", "alpha3"])
+def test_const_ops(lg, params):
+    """AddConst, MultByConst, MultByConstAndAdd, MultByi, DivByi (ckks/evaluator.go:373-833) bit-exact against
+    the oracle, complex / fractional / negative / integer constants, full and partial level."""
+    s = Setup(lg, params)
+    rng = np.random.default_rng(31)
+    batch = 2
+    a = s.ct(rng, "reduced", batch)
+    acc = s.ct(rng, "reduced", batch)
+    pa = polys(lg, a)
+    scale = float(1 << 30)
+    for level in (s.nQ - 1, 1):
+        nl = level + 1
+        for const in (3.25 - 1.5j, -2.0, 7, 0.0 + 2.5j, -0.75 + 0.0j):
+            c = complex(const)
+            out = new_ct(lg, s, batch)
+            s.ev.AddConst(level, pa, const, scale, out)
+            sc = s.ev.const_scale(const, scale)
+            out2 = new_ct(lg, s, batch)
+            s.ev.MultByConst(level, pa, const, sc, out2)
+            out3 = polys(lg, acc)
+            s.ev.MultByConstAndAdd(level, pa, const, sc, out3)
+            for i in range(batch):
+                ins = [np.ascontiguousarray(a[i, u, :nl]) for u in range(2)]
+                w = orc.ckks_const_op(s.oQ, "add", level, ins[:1], ins[:1], c.real, c.imag, scale)
+                assert np.array_equal(out[0].numpy(nl=nl, squeeze=False)[i], w[0]), (level, const, "add")
+                w = orc.ckks_const_op(s.oQ, "mul", level, ins, ins, c.real, c.imag, sc)
+                assert np.array_equal(host(out2, nl)[i], np.stack(w)), (level, const, "mul")
+                accs = [np.ascontiguousarray(acc[i, u, :nl]) for u in range(2)]
+                w = orc.ckks_const_op(s.oQ, "mul_add", level, ins, accs, c.real, c.imag, sc)
+                assert np.array_equal(host(out3, nl)[i], np.stack(w)), (level, const, "mul_add")
+        oi, od = new_ct(lg, s, batch), new_ct(lg, s, batch)
+        s.ev.MultByi(level, pa, oi)
+        s.ev.DivByi(level, pa, od)
+        for i in range(batch):
+            ins = [np.ascontiguousarray(a[i, u, :nl]) for u in range(2)]
+            assert np.array_equal(host(oi, nl)[i], np.stack(orc.ckks_const_op(s.oQ, "mul_i", level, ins, ins)))
+            assert np.array_equal(host(od, nl)[i], np.stack(orc.ckks_const_op(s.oQ, "div_i", level, ins, ins)))
+
+
 def test_error_paths(lg):
     s = Setup(lg, PN12)
     rng = np.random.default_rng(24)

@@ -406,6 +406,50 @@ def test_ckks_keygen_encrypt_decrypt_semantics():
     assert err < (1 << 12), err
 
 
+def test_ckks_const_ops_semantics():
+    """Constant ops (ckks/evaluator.go:373-833) in the coefficient domain: AddConst(a+bi) adds round(a*scale)
+    to coefficient 0 and round(b*scale) to coefficient N/2; MultByConst multiplies the polynomial by
+    round(a*scale) + round(b*scale)*X^(N/2); MultByi / DivByi multiply by X^(N/2) / X^(3N/2)."""
+    N = 32
+    Q, _ = _ckks_small(N)
+    rng = random.Random(91)
+    ctx = orc.Context(N, Q)
+    Qp = prod(Q)
+    vals = [rng.randrange(Qp) for _ in range(N)]
+    p = ctx.ntt(crt_poly(vals, Q))
+    level = len(Q) - 1
+    scale = float(1 << 30)
+
+    def coeffs(poly):
+        return crt_reconstruct(ctx.invntt(np.ascontiguousarray(poly)), Q)
+
+    def mul_monomial(v, k, c=1):  # c * X^k * v in Z_Q[X]/(X^N+1)
+        out = [0] * N
+        for i, x in enumerate(v):
+            d = (i + k) % (2 * N)
+            if d >= N:
+                out[d - N] = (out[d - N] - c * x) % Qp
+            else:
+                out[d] = (out[d] + c * x) % Qp
+        return out
+
+    a, b = 3.25, -1.5
+    A, B = int(a * scale + 0.5), -int(-b * scale + 0.5)
+    got = coeffs(orc.ckks_const_op(ctx, "add", level, [p], [p], a, b, scale)[0])
+    want = list(vals)
+    want[0] = (want[0] + A) % Qp
+    want[N // 2] = (want[N // 2] + B) % Qp
+    assert got == want
+    got = coeffs(orc.ckks_const_op(ctx, "mul", level, [p], [p], a, b, scale)[0])
+    want = [(x + y) % Qp for x, y in zip(mul_monomial(vals, 0, A), mul_monomial(vals, N // 2, B))]
+    assert got == want
+    acc = ctx.ntt(crt_poly([7] * N, Q))
+    got = coeffs(orc.ckks_const_op(ctx, "mul_add", level, [p], [acc], 5.0, 0.0, 1.0)[0])
+    assert got == [(7 + 5 * x) % Qp for x in vals]
+    assert coeffs(orc.ckks_const_op(ctx, "mul_i", level, [p], [p])[0]) == mul_monomial(vals, N // 2)
+    assert coeffs(orc.ckks_const_op(ctx, "div_i", level, [p], [p])[0]) == mul_monomial(vals, 3 * N // 2)
+
+
 def test_unreduced_inputs_are_defined():
     """NewPolyUniform feeds full 64-bit words (ring_object.go:26-46); the oracle
     must be total on them (used later as a formula-exactness probe for CUDA)."""
