@@ -101,7 +101,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nops = args.cpu_sample or cores
+    nops = args.cpu_sample or 4 * cores
     vals = []
     for _ in range(max(args.warmup, 0) and 1):
         cpu_mulrelin_rescale(args.params, min(nops, cores), cores)
@@ -378,7 +378,28 @@ def run_gpu(args):
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # the same bytes with no compute in between: what PCIe alone allows (both directions overlapped)
+        def copy_only():
+            for c in range(nchunks):
+                s_ = streams[c % nstreams]
+                sa, sb, so = slots[c % nstreams]
+                p_ = ctypes.c_void_p(s_.cuda_stream)
+                for poly, h in zip(sa + sb, h_a + h_b):
+                    lattigpu._lib.check(L.lg_poly_upload_async(poly.h, 0, cb, 0, nQ, hp(h[c * cb:]), p_))
+                for poly, h in zip(so, h_o):
+                    lattigpu._lib.check(L.lg_poly_download_async(poly.h, 0, cb, 0, nQ - 1, hp(h[c * cb:]), p_))
+            for s_ in streams:
+                s_.synchronize()
+
+        copy_only()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copy_only()
+        barrier()
+        copy_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
         e2e = {"value": world * B * e2e_steps / dt, "unit": "ops/s", "h2d_bytes_per_step": 4 * B * nQ * N * 8,
+               "copy_only_ms_per_step": copy_ms,
                "d2h_bytes_per_step": 2 * B * (nQ - 1) * N * 8, "ms_per_step": 1e3 * dt / e2e_steps,
                "note": "pinned host buffers; per chunk of %d ciphertexts: lg_poly_upload_async x4, MulRelin, Rescale, "
                        "lg_poly_download_async x2; %d chunks over %d streams, host sync per step" % (cb, nchunks, nstreams)}
@@ -387,7 +408,7 @@ def run_gpu(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        nops = args.cpu_sample or cores
+        nops = args.cpu_sample or 8 * cores  # about 15 s of CPU work on the box
         v, dt = cpu_mulrelin_rescale(args.params, nops, cores)
         cpu = {"value": v, "unit": "ops/s", "cores": cores, "kind": "port",
                "sample": "%d MulRelin+Rescale ops, one oracle evaluator per host thread, %.1f s wall" % (nops, dt)}
