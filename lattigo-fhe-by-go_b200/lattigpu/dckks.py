@@ -1,6 +1,8 @@
 """Host-side mirror of the dckks protocols that sit on the ring hot path: collective public-key
-generation (CKG, dckks/publickey_gen.go:18-52) and public collective key switching (PCKS,
-dckks/public_keyswitching.go:9-113).  As in the reference the protocol logic is host code that
+generation (CKG, dckks/publickey_gen.go:18-52), public collective key switching (PCKS,
+dckks/public_keyswitching.go:9-113), collective key switching (CKS, dckks/keyswitching.go:55-108),
+rotation-key generation (RTG, dckks/rotkey_gen.go:75-174) and the three-round relinearisation-key
+generation (RKG, dckks/relinkey_gen.go:60-223).  As in the reference the protocol logic is host code that
 calls ring ops; here every ring op runs on the GPU through the C ABI.
 
 Sampling stays with the caller (the reference draws from crypto/rand on the host): GenShare takes
@@ -69,3 +71,180 @@ class PCKSProtocol:
     def KeySwitch(self, combined, ct, ctOut, level, stream=None):
         self.contextQ.AddLvl(level, ct[0], combined[0], ctOut[0], stream=stream)  # :107-111
         self.contextQ.CopyLvl(level, combined[1], ctOut[1], stream=stream)
+
+
+def _add_digit_limbs(K, src, dst, i, alpha, levels, tmp, stream):
+    """dst[index] = CRed(dst[index] + src[index]) for the limbs index = i*alpha + j of digit i that lie
+    below `levels` (the j-loops of relinkey_gen.go:88-105 / rotkey_gen.go:116-132); dst is canonical, so adding a
+    poly that is zero elsewhere leaves the other limbs unchanged."""
+    lo = i * alpha
+    hi = min(lo + alpha, levels)
+    tmp.Zero(stream=stream)
+    K.CopyLvl(hi - lo - 1, src.view(lo, hi - lo), tmp.view(lo, hi - lo), stream=stream)
+    K.Add(dst, tmp, dst, stream=stream)
+
+
+class CKSProtocol:
+    """dckks/keyswitching.go:9-108"""
+
+    def __init__(self, contextQ, contextP, contextQP):
+        self.contextQ, self.contextP, self.contextQP = contextQ, contextP, contextQP
+        self.baseconverter = ring.NewFastBasisExtender(contextQ, contextP)
+        self.Pbig = 1
+        for p in contextP.Modulus:
+            self.Pbig *= int(p)
+
+    def AllocateShare(self, level, batch=1):
+        return self.contextQ.NewPolyLvl(level, batch)
+
+    def GenShare(self, level, skInput, skOutput, ct1, shareOut, e, stream=None):
+        """:62-96.  skInput / skOutput over Q (NTT + Montgomery), ct1 = ct.Value()[1], e = smudging sample over
+        QP in the coefficient domain.  shareOut = ((skIn - skOut) * ct1 * P + NTT(e)) / P"""
+        Q, K = self.contextQ, self.contextQP
+        nQ = Q.nl
+        delta = Q.NewPoly(skInput.batch)
+        Q.Sub(skInput, skOutput, delta, stream=stream)  # :64
+        Q.MulCoeffsMontgomeryLvl(level, ct1, delta, shareOut, stream=stream)  # :74
+        Q.MulScalarBigintLvl(level, shareOut, self.Pbig, shareOut, stream=stream)  # :76
+        tmp = K.NewPoly(e.batch)
+        K.NTT(e, tmp, stream=stream)  # SampleNTT :79
+        Q.AddLvl(level, shareOut, tmp.view(0, nQ), shareOut, stream=stream)  # :80
+        hP = tmp.view(nQ, self.contextP.nl)  # :82-88 (hP starts at zero)
+        self.baseconverter.ModDownSplitedNTTPQ(level, shareOut, hP, shareOut, stream=stream)  # :90
+
+    def AggregateShares(self, level, share1, share2, shareOut, stream=None):
+        self.contextQ.AddLvl(level, share1, share2, shareOut, stream=stream)  # :100-102
+
+    def KeySwitch(self, level, combined, ct, ctOut, stream=None):
+        self.contextQ.AddLvl(level, ct[0], combined, ctOut[0], stream=stream)  # :105-108
+        self.contextQ.CopyLvl(level, ct[1], ctOut[1], stream=stream)
+
+
+class RTGProtocol:
+    """dckks/rotkey_gen.go:9-174 over contextQP"""
+
+    def __init__(self, contextQ, contextP, contextQP):
+        self.contextQP = contextQP
+        self.levels, self.alpha = contextQ.nl, contextP.nl
+        self.beta = -(-self.levels // self.alpha)
+        self.Pbig = 1
+        for p in contextP.Modulus:
+            self.Pbig *= int(p)
+
+    def genShare(self, sk, galEl, crp, errors, stream=None):
+        """:95-141.  sk over QP (NTT + Montgomery); crp[i] uniform over QP; errors[i] gaussian coefficients
+        (device polys, coefficient domain).  Returns the beta share polys."""
+        K = self.contextQP
+        tmpPoly, tmp = K.NewPoly(), K.NewPoly()
+        ring.PermuteNTT(sk, galEl, tmpPoly, stream=stream)  # :99
+        K.MulScalarBigint(tmpPoly, self.Pbig, tmpPoly, stream=stream)  # :101
+        K.InvMForm(tmpPoly, tmpPoly, stream=stream)  # :103
+        out = []
+        for i in range(self.beta):
+            ek = K.NewPoly()
+            K.NTT(errors[i], ek, stream=stream)  # SampleNTTNew :110
+            _add_digit_limbs(K, tmpPoly, ek, i, self.alpha, self.levels, tmp, stream)  # :116-132
+            K.MulCoeffsMontgomeryAndSub(crp[i], sk, ek, stream=stream)  # :135
+            K.MForm(ek, ek, stream=stream)  # :136
+            out.append(ek)
+        return out
+
+    def Aggregate(self, share1, share2, shareOut, stream=None):
+        for a, b, c in zip(share1, share2, shareOut):
+            self.contextQP.Add(a, b, c, stream=stream)  # :158-160
+
+    def Finalize(self, share, crp, stream=None):
+        """:164-174: evakey[i] = (share[i], MForm(crp[i])) -> [beta][2] polys over QP"""
+        K = self.contextQP
+        key = []
+        for i in range(self.beta):
+            k1 = K.NewPoly()
+            K.MForm(crp[i], k1, stream=stream)
+            key.append((share[i].CopyNew(stream=stream), k1))
+        return key
+
+
+class RKGProtocol:
+    """dckks/relinkey_gen.go:9-223 over contextQP; u = ephemeral key, sk = secret share (NTT + Montgomery)"""
+
+    def __init__(self, contextQ, contextP, contextQP):
+        self.contextQP = contextQP
+        self.levels, self.alpha = contextQ.nl, contextP.nl
+        self.beta = -(-self.levels // self.alpha)
+        self.Pbig = 1
+        for p in contextP.Modulus:
+            self.Pbig *= int(p)
+
+    def GenShareRoundOne(self, u, sk, crp, errors, stream=None):
+        """:65-112: share[i] = -u*crp[i] + P*s*w_i + NTT(e_i)"""
+        K = self.contextQP
+        pool, tmp = sk.CopyNew(stream=stream), K.NewPoly()
+        K.MulScalarBigint(pool, self.Pbig, pool, stream=stream)  # :77
+        K.InvMForm(pool, pool, stream=stream)  # :79
+        out = []
+        for i in range(self.beta):
+            h = K.NewPoly()
+            K.NTT(errors[i], h, stream=stream)  # :84
+            _add_digit_limbs(K, pool, h, i, self.alpha, self.levels, tmp, stream)  # :87-105
+            K.MulCoeffsMontgomeryAndSub(u, crp[i], h, stream=stream)  # :108
+            out.append(h)
+        return out
+
+    def AggregateShareRoundOne(self, share1, share2, shareOut, stream=None):
+        for a, b, c in zip(share1, share2, shareOut):
+            self.contextQP.Add(a, b, c, stream=stream)
+
+    def GenShareRoundTwo(self, round1, sk, crp, errors1, errors2, stream=None):
+        """:135-163: (round1[i]*sk + NTT(e1_i), sk*crp[i] + NTT(e2_i))"""
+        K = self.contextQP
+        out = []
+        for i in range(self.beta):
+            s0, s1, pool = K.NewPoly(), K.NewPoly(), K.NewPoly()
+            K.MulCoeffsMontgomery(round1[i], sk, s0, stream=stream)  # :146
+            K.NTT(errors1[i], pool, stream=stream)  # :149
+            K.Add(s0, pool, s0, stream=stream)
+            K.NTT(errors2[i], s1, stream=stream)  # :154
+            K.MulCoeffsMontgomeryAndAdd(sk, crp[i], s1, stream=stream)  # :156
+            out.append((s0, s1))
+        return out
+
+    def AggregateShareRoundTwo(self, share1, share2, shareOut, stream=None):
+        for a, b, c in zip(share1, share2, shareOut):
+            self.contextQP.Add(a[0], b[0], c[0], stream=stream)
+            self.contextQP.Add(a[1], b[1], c[1], stream=stream)
+
+    def GenShareRoundThree(self, round2, u, sk, errors, stream=None):
+        """:186-199: (u - sk) * round2[i][1] + NTT(e3_i)"""
+        K = self.contextQP
+        pool = K.NewPoly()
+        K.Sub(u, sk, pool, stream=stream)  # :191
+        out = []
+        for i in range(self.beta):
+            h = K.NewPoly()
+            K.NTT(errors[i], h, stream=stream)  # :196
+            K.MulCoeffsMontgomeryAndAdd(pool, round2[i][1], h, stream=stream)  # :197
+            out.append(h)
+        return out
+
+    def AggregateShareRoundThree(self, share1, share2, shareOut, stream=None):
+        for a, b, c in zip(share1, share2, shareOut):
+            self.contextQP.Add(a, b, c, stream=stream)
+
+    def GenRelinearizationKey(self, round2, round3, stream=None):
+        """:210-223: key[i] = (MForm(round2[i][0] + round3[i]), MForm(round2[i][1]))"""
+        K = self.contextQP
+        key = []
+        for i in range(self.beta):
+            k0, k1 = K.NewPoly(), K.NewPoly()
+            K.Add(round2[i][0], round3[i], k0, stream=stream)
+            K.MForm(k0, k0, stream=stream)
+            K.MForm(round2[i][1], k1, stream=stream)
+            key.append((k0, k1))
+        return key
+
+
+def evakey_to_numpy(key):
+    """[beta] x (poly, poly) -> [beta][2][nQP][N] uint64, the layout of ckks.SwitchingKey"""
+    import numpy as np
+
+    return np.ascontiguousarray(np.stack([np.stack([k0.numpy(), k1.numpy()]) for k0, k1 in key]))

@@ -520,6 +520,95 @@ class CkksScheme:
 
 
 # ---------------------------------------------------------------------------
+# dckks protocols CKS / RTG / RKG (dckks/keyswitching.go, rotkey_gen.go, relinkey_gen.go) restated as
+# compositions of the oracle's ring ops; sampled values are inputs (signed coefficient vectors)
+# ---------------------------------------------------------------------------
+class DckksProtocols:
+    def __init__(self, scheme):
+        self.S = scheme
+        self.K = scheme.QP
+        self.mods = scheme.Qm + scheme.Pm
+
+    def _add_digit(self, dst, src, i):
+        S = self.S
+        for j in range(S.alpha):
+            index = i * S.alpha + j
+            qi = np.uint64(self.mods[index])
+            t = dst[index] + src[index]
+            dst[index] = np.where(t >= qi, t - qi, t)
+            if index >= S.levels - 1:
+                break
+
+    def cks_gen_share(self, level, sk_in, sk_out, ct1, e):  # keyswitching.go:62-96
+        S = self.S
+        nl, nQ = level + 1, S.levels
+        delta = S.Q.op3("sub", np.ascontiguousarray(sk_in[:nQ]), np.ascontiguousarray(sk_out[:nQ]))
+        share = S.Q.op3("mulcoeffs_montgomery", np.ascontiguousarray(ct1[:nl]), np.ascontiguousarray(delta[:nl]), nl=nl)
+        share = S.Q.mul_scalar(share, [S.Pbig % q for q in S.Qm[:nl]], nl=nl)
+        tmp = self.K.ntt(signed_residues(self.mods, e))
+        share = S.Q.op3("add", share, np.ascontiguousarray(tmp[:nl]), nl=nl)
+        return S.ext.moddown_splited_ntt_pq(level, share, np.ascontiguousarray(tmp[nQ:]))
+
+    def rtg_gen_share(self, sk, gal_el, crp, errors):  # rotkey_gen.go:95-141
+        S = self.S
+        idx = permute_ntt_index(gal_el, 1, S.N)
+        tmp = permute_ntt_with_index(sk, idx)
+        tmp = self.K.op2("invmform_poly", self.K.mul_scalar(tmp, [S.Pbig % q for q in self.mods]))
+        out = []
+        for i in range(S.beta):
+            ek = self.K.ntt(signed_residues(self.mods, errors[i]))
+            self._add_digit(ek, tmp, i)
+            self.K.op3("mulcoeffs_montgomery_and_sub", np.ascontiguousarray(crp[i]), sk, ek)
+            out.append(self.K.op2("mform_poly", ek))
+        return out
+
+    def rtg_finalize(self, share, crp):  # rotkey_gen.go:164-174
+        return np.ascontiguousarray(np.stack([np.stack([share[i], self.K.op2("mform_poly", np.ascontiguousarray(crp[i]))])
+                                              for i in range(self.S.beta)]))
+
+    def rkg_round1(self, u, sk, crp, errors):  # relinkey_gen.go:65-112
+        S = self.S
+        pool = self.K.op2("invmform_poly", self.K.mul_scalar(sk, [S.Pbig % q for q in self.mods]))
+        out = []
+        for i in range(S.beta):
+            h = self.K.ntt(signed_residues(self.mods, errors[i]))
+            self._add_digit(h, pool, i)
+            self.K.op3("mulcoeffs_montgomery_and_sub", u, np.ascontiguousarray(crp[i]), h)
+            out.append(h)
+        return out
+
+    def rkg_round2(self, round1, sk, crp, errors1, errors2):  # :135-163
+        out = []
+        for i in range(self.S.beta):
+            s0 = self.K.op3("mulcoeffs_montgomery", round1[i], sk)
+            s0 = self.K.op3("add", s0, self.K.ntt(signed_residues(self.mods, errors1[i])))
+            s1 = self.K.ntt(signed_residues(self.mods, errors2[i]))
+            self.K.op3("mulcoeffs_montgomery_and_add", sk, np.ascontiguousarray(crp[i]), s1)
+            out.append((s0, s1))
+        return out
+
+    def rkg_round3(self, round2, u, sk, errors):  # :186-199
+        pool = self.K.op3("sub", u, sk)
+        out = []
+        for i in range(self.S.beta):
+            h = self.K.ntt(signed_residues(self.mods, errors[i]))
+            self.K.op3("mulcoeffs_montgomery_and_add", pool, round2[i][1], h)
+            out.append(h)
+        return out
+
+    def rkg_key(self, round2, round3):  # :210-223
+        return np.ascontiguousarray(np.stack([np.stack([
+            self.K.op2("mform_poly", self.K.op3("add", round2[i][0], round3[i])),
+            self.K.op2("mform_poly", round2[i][1])]) for i in range(self.S.beta)]))
+
+    def add_lists(self, a, b):
+        return [self.K.op3("add", x, y) for x, y in zip(a, b)]
+
+    def add_pairs(self, a, b):
+        return [(self.K.op3("add", x[0], y[0]), self.K.op3("add", x[1], y[1])) for x, y in zip(a, b)]
+
+
+# ---------------------------------------------------------------------------
 # CKKS constant ops, ckks/evaluator.go:373-833, restated whole (host scalars + coefficient loops)
 # ---------------------------------------------------------------------------
 def scale_up_exact(value, n, q):  # ckks/utils.go:22-49 (big.Float at 53 bits: x + 0.5 rounds like float64)

@@ -120,3 +120,105 @@ def test_ckg_pcks(lg, scheme):
         pcks.KeySwitch(comb, (F(ct[0]), F(ct[1])), out)
     assert np.array_equal(out[0].numpy(nl=nl), oQ.op3("add", np.ascontiguousarray(ct[0][:nl]), comb_w[0], nl=nl))
     assert np.array_equal(out[1].numpy(nl=nl), comb_w[1])
+
+
+def test_dckks_cks_rtg_rkg(lg):
+    """CKS (dckks/keyswitching.go:55-108), RTG (rotkey_gen.go:75-174) and the three rounds of RKG
+    (relinkey_gen.go:60-223) with 3 parties, every share and the final keys bit-exact against the oracle."""
+    p = lg.ckks.DefaultParams[lg.ckks.PN13QP218]
+    Q, P = lg.ckks.GenModuli(p)
+    N = 1 << p["LogN"]
+    QP = Q + P
+    nQ = len(Q)
+    rng = np.random.default_rng(67)
+    S = orc.CkksScheme(Q, P, N)
+    D = orc.DckksProtocols(S)
+    cQ, cP, cK = (lg.ring.NewContextWithParams(N, m) for m in (Q, P, QP))
+    F = lg.ring.Poly.from_numpy
+    from lattigpu.ckks_scheme import signed_to_poly
+
+    tern = lambda: rng.integers(-1, 2, size=N)
+    gauss = lambda: np.rint(rng.normal(0, 3.2, size=N)).astype(np.int64)
+    gl = lambda: [gauss() for _ in range(S.beta)]
+    dev = lambda es: [signed_to_poly(cK, e) for e in es]
+    sks = [S.gen_secret_key(tern()) for _ in range(PARTIES)]
+    us = [S.gen_secret_key(tern()) for _ in range(PARTIES)]
+    crp = [uni(rng, QP, N) for _ in range(S.beta)]
+    dcrp = [F(c) for c in crp]
+
+    def same_list(got, want):
+        return all(np.array_equal(g.numpy(), w) for g, w in zip(got, want))
+
+    # ---- RKG ----
+    rkg = lg.dckks.RKGProtocol(cQ, cP, cK)
+    r1 = r1w = None
+    for u, s_i in zip(us, sks):
+        e = gl()
+        sh, w = rkg.GenShareRoundOne(F(u), F(s_i), dcrp, dev(e)), D.rkg_round1(u, s_i, crp, e)
+        assert same_list(sh, w)
+        if r1 is None:
+            r1, r1w = sh, w
+        else:
+            rkg.AggregateShareRoundOne(r1, sh, r1)
+            r1w = D.add_lists(r1w, w)
+    r2 = r2w = None
+    for s_i in sks:
+        e1, e2 = gl(), gl()
+        sh, w = rkg.GenShareRoundTwo(r1, F(s_i), dcrp, dev(e1), dev(e2)), D.rkg_round2(r1w, s_i, crp, e1, e2)
+        assert all(np.array_equal(a[0].numpy(), b[0]) and np.array_equal(a[1].numpy(), b[1]) for a, b in zip(sh, w))
+        if r2 is None:
+            r2, r2w = sh, w
+        else:
+            rkg.AggregateShareRoundTwo(r2, sh, r2)
+            r2w = D.add_pairs(r2w, w)
+    r3 = r3w = None
+    for u, s_i in zip(us, sks):
+        e = gl()
+        sh, w = rkg.GenShareRoundThree(r2, F(u), F(s_i), dev(e)), D.rkg_round3(r2w, u, s_i, e)
+        assert same_list(sh, w)
+        if r3 is None:
+            r3, r3w = sh, w
+        else:
+            rkg.AggregateShareRoundThree(r3, sh, r3)
+            r3w = D.add_lists(r3w, w)
+    key = lg.dckks.evakey_to_numpy(rkg.GenRelinearizationKey(r2, r3))
+    assert np.array_equal(key, D.rkg_key(r2w, r3w))
+
+    # ---- RTG, rotation by 3 (Galois element 5^3) ----
+    rtg = lg.dckks.RTGProtocol(cQ, cP, cK)
+    gal = pow(5, 3, 2 * N)
+    agg = aggw = None
+    for s_i in sks:
+        e = gl()
+        sh, w = rtg.genShare(F(s_i), gal, dcrp, dev(e)), D.rtg_gen_share(s_i, gal, crp, e)
+        assert same_list(sh, w)
+        if agg is None:
+            agg, aggw = sh, w
+        else:
+            rtg.Aggregate(agg, sh, agg)
+            aggw = D.add_lists(aggw, w)
+    assert np.array_equal(lg.dckks.evakey_to_numpy(rtg.Finalize(agg, dcrp)), D.rtg_finalize(aggw, crp))
+
+    # ---- CKS at the top level and one below ----
+    cks = lg.dckks.CKSProtocol(cQ, cP, cK)
+    sks_out = [S.gen_secret_key(tern()) for _ in range(PARTIES)]
+    ct = [uni(rng, Q, N), uni(rng, Q, N)]
+    for level in (nQ - 1, nQ - 2):
+        nl = level + 1
+        comb = combw = None
+        for a, b in zip(sks, sks_out):
+            e = np.rint(rng.normal(0, 40.0, size=N)).astype(np.int64)
+            share = cks.AllocateShare(level)
+            cks.GenShare(level, F(np.ascontiguousarray(a[:nQ])), F(np.ascontiguousarray(b[:nQ])), F(ct[1]), share,
+                         signed_to_poly(cK, e))
+            w = D.cks_gen_share(level, a, b, ct[1], e)
+            assert np.array_equal(share.numpy(nl=nl), w), level
+            if comb is None:
+                comb, combw = share, w
+            else:
+                cks.AggregateShares(level, comb, share, comb)
+                combw = S.Q.op3("add", combw, w, nl=nl)
+        out = (cQ.NewPoly(), cQ.NewPoly())
+        cks.KeySwitch(level, comb, (F(ct[0]), F(ct[1])), out)
+        assert np.array_equal(out[0].numpy(nl=nl), S.Q.op3("add", np.ascontiguousarray(ct[0][:nl]), combw, nl=nl))
+        assert np.array_equal(out[1].numpy(nl=nl), ct[1][:nl])

@@ -406,6 +406,106 @@ def test_ckks_keygen_encrypt_decrypt_semantics():
     assert err < (1 << 12), err
 
 
+def test_dckks_cks_rtg_rkg_semantics():
+    """dckks CKS / RTG / RKG (keyswitching.go, rotkey_gen.go, relinkey_gen.go) with 3 parties, as
+    dckks_test.go does: the collective relinearisation key relinearises, the collective rotation key rotates,
+    and CKS re-encrypts from the sum of the input shares to the sum of the output shares."""
+    N, parties = 32, 3
+    Q, P = _ckks_small(N)
+    rng = random.Random(123)
+    S = orc.CkksScheme(Q, P, N)
+    D = orc.DckksProtocols(S)
+    K = S.QP
+    tern = lambda: [rng.choice([-1, 0, 1]) for _ in range(N)]
+    gauss = lambda: [rng.choice([-2, -1, 0, 0, 1, 2]) for _ in range(N)]
+    gl = lambda: [gauss() for _ in range(S.beta)]
+    unif = lambda mods: np.array([[rng.randrange(q) for _ in range(N)] for q in mods], dtype=np.uint64)
+    level = len(Q) - 1
+    Qp = prod(Q)
+    scale = 1 << 20
+
+    def centered(vals, mod):
+        return [v if v < mod // 2 else v - mod for v in vals]
+
+    def negacyclic(a, b):
+        out = [0] * N
+        for x in range(N):
+            for y in range(N):
+                k = x + y
+                if k >= N:
+                    out[k - N] -= a[x] * b[y]
+                else:
+                    out[k] += a[x] * b[y]
+        return out
+
+    sks = [S.gen_secret_key(tern()) for _ in range(parties)]
+    sk = sks[0]
+    for x in sks[1:]:
+        sk = K.op3("add", sk, x)
+    plaintext = lambda m: S.Q.ntt(crt_poly([x * scale for x in m], Q))
+    m0 = [rng.randrange(-500, 500) for _ in range(N)]
+    m1 = [rng.randrange(-500, 500) for _ in range(N)]
+    ct0 = S.encrypt_sk(level, plaintext(m0), sk, unif(Q + P), gauss())
+    ct1 = S.encrypt_sk(level, plaintext(m1), sk, unif(Q + P), gauss())
+    ev = orc.CkksEvaluator(S.Q, S.P)
+
+    # RKG, three rounds
+    crp = [unif(Q + P) for _ in range(S.beta)]
+    us = [S.gen_secret_key(tern()) for _ in range(parties)]
+    r1 = None
+    for u, s_i in zip(us, sks):
+        sh = D.rkg_round1(u, s_i, crp, gl())
+        r1 = sh if r1 is None else D.add_lists(r1, sh)
+    r2 = None
+    for s_i in sks:
+        sh = D.rkg_round2(r1, s_i, crp, gl(), gl())
+        r2 = sh if r2 is None else D.add_pairs(r2, sh)
+    r3 = None
+    for u, s_i in zip(us, sks):
+        sh = D.rkg_round3(r2, u, s_i, gl())
+        r3 = sh if r3 is None else D.add_lists(r3, sh)
+    rlk = D.rkg_key(r2, r3)
+    prod_ct = ev.rescale(ev.mul_relin(level, np.ascontiguousarray(ct0), np.ascontiguousarray(ct1), rlk))
+    Ql = Q[:-1]
+    dec = centered(crt_reconstruct(orc.Context(N, Ql).invntt(S.decrypt(level - 1, prod_ct, sk)), Ql), prod(Ql))
+    want = negacyclic(m0, m1)
+    err = max(abs(d - div_round(w * scale * scale, Q[-1])) for d, w in zip(dec, want))
+    assert err < (1 << 14), err
+
+    # RTG for the Galois element 5
+    crp = [unif(Q + P) for _ in range(S.beta)]
+    agg = None
+    for s_i in sks:
+        sh = D.rtg_gen_share(s_i, 5, crp, gl())
+        agg = sh if agg is None else D.add_lists(agg, sh)
+    rot = D.rtg_finalize(agg, crp)
+    r = ev.permute_ntt(level, np.ascontiguousarray(ct0), orc.permute_ntt_index(5, 1, N), rot)
+    dec = centered(crt_reconstruct(S.Q.invntt(S.decrypt(level, r, sk)), Q), Qp)
+    wantr = [0] * N
+    for i, v in enumerate(m0):
+        k = (i * 5) % (2 * N)
+        if k >= N:
+            wantr[k - N] = -v
+        else:
+            wantr[k] = v
+    err = max(abs(d - w * scale) for d, w in zip(dec, wantr))
+    assert err < (1 << 14), err
+
+    # CKS from sum(sks) to sum(sks_out)
+    sks_out = [S.gen_secret_key(tern()) for _ in range(parties)]
+    sk_out = sks_out[0]
+    for x in sks_out[1:]:
+        sk_out = K.op3("add", sk_out, x)
+    comb = None
+    for a, b in zip(sks, sks_out):
+        sh = D.cks_gen_share(level, a, b, ct0[1], gauss())
+        comb = sh if comb is None else S.Q.op3("add", comb, sh)
+    switched = np.stack([S.Q.op3("add", np.ascontiguousarray(ct0[0]), comb), ct0[1]])
+    dec = centered(crt_reconstruct(S.Q.invntt(S.decrypt(level, switched, sk_out)), Q), Qp)
+    err = max(abs(d - x * scale) for d, x in zip(dec, m0))
+    assert err < (1 << 14), err
+
+
 def test_ckks_const_ops_semantics():
     """Constant ops (ckks/evaluator.go:373-833) in the coefficient domain: AddConst(a+bi) adds round(a*scale)
     to coefficient 0 and round(b*scale) to coefficient N/2; MultByConst multiplies the polynomial by
