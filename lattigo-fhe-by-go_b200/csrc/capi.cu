@@ -372,10 +372,9 @@ int lg_poly_copy(const lg_poly* src, int nl, lg_poly* dst, lg_stream_t s) {
 // ---------------------------------------------------------------------------
 
 int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, size_t in_bs, u64* out, size_t out_bs,
-            bool inverse, int skip0, int skip1, cudaStream_t st, const NttMac* mac, bool in_range) {
+            bool inverse, int skip0, int skip1, cudaStream_t st, bool in_range) {
     NttArgs a;
     memset(&a, 0, sizeof(a));
-    if (mac) a.mac = *mac;
     a.T = r->T;
     a.map = map;
     a.in = in;

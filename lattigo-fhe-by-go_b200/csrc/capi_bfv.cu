@@ -80,7 +80,7 @@ int bfv_switch_keys(lg_bfv_eval* e, int batch, const u64* cx, size_t cx_bs, cons
                                 d.d, acc0, acc1, d_bs, 7, st));
     // :808-809 InvNTT over QP of both accumulators (contiguous: one launch over 2*batch entries)
     // (the accumulators are canonical, so the inverse needs no range check)
-    LG_TRY(lgi_ntt(QP, limb_map_identity(), nd, 2 * batch, acc0, d_bs, acc0, d_bs, true, 0, 0, st, nullptr, true));
+    LG_TRY(lgi_ntt(QP, limb_map_identity(), nd, 2 * batch, acc0, d_bs, acc0, d_bs, true, 0, 0, st, true));
     // :811-812 ModDownPQ
     LG_TRY(lgi_moddown_tail_ntt(e->q1p.get(), level, batch, acc0, d_bs, acc0 + (size_t)nQ * N, d_bs, out0, out0_bs, false, st,
                                 add0));

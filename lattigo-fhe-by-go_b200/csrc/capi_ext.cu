@@ -131,7 +131,7 @@ int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* 
     const int nl = level + 1;
     LG_REQUIRE(level >= 0 && nl <= Q->nl, "ModDown: level %d out of range", level);
     if (ntt)  // :172 / :215 -- destroys the P part of the input, like the reference
-        LG_TRY(lgi_ntt(P, limb_map_identity(), P->nl, batch, p1P, p1P_bs, p1P, p1P_bs, true, 0, 0, st, nullptr, p_in_range));
+        LG_TRY(lgi_ntt(P, limb_map_identity(), P->nl, batch, p1P, p1P_bs, p1P, p1P_bs, true, 0, 0, st, p_in_range));
     Scratch tmp(st);
     LG_TRY(tmp.alloc((size_t)batch * nl * N));
     const size_t tbs = (size_t)nl * N;
@@ -486,7 +486,7 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
     const LimbMap qp_map{nl, 0, nQ};  // Q limbs 0..level, then the special primes at #Q.. (:1519-1525)
 
     // :1503  c2 = InvNTT(cx)
-    LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, cx, cx_bs, c2.d, c2_bs, true, 0, 0, st, nullptr, cx_in_range));
+    LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, cx, cx_bs, c2.d, c2_bs, true, 0, 0, st, cx_in_range));
     // :1511-1552 digit loop (decomposeAndSplitNTT + multiply-accumulate), reduce cadence reduce&7 == 1
     LG_TRY(lgi_keyswitch_digits(QP, Q, qp_map, e->dec.get(), level, beta, batch, c2.d, c2_bs, cx, cx_bs, evk, d.d, acc0,
                                 acc1, d_bs, 1, st));

@@ -200,9 +200,8 @@ int switch_keys_sharded(lg_ckks_eval* e, const lg_comm* c, int level, int batch,
     const LimbMap qp_map{nl, 0, nQ};
     const LimbMap idm = limb_map_identity();
 
-    Scratch c2(st), d(st), acc(st), tmp(st);
+    Scratch c2(st), acc(st), tmp(st);
     LG_TRY(c2.alloc((size_t)batch * nl * N));
-    LG_TRY(d.alloc((size_t)batch * nd * N));
     LG_TRY(acc.alloc((size_t)2 * batch * nd * N));
     LG_TRY(tmp.alloc((size_t)2 * batch * nl * N));
     const size_t c2_bs = (size_t)nl * N, d_bs = (size_t)nd * N;
@@ -215,27 +214,49 @@ int switch_keys_sharded(lg_ckks_eval* e, const lg_comm* c, int level, int batch,
                        true, 0, 0, st));
     LG_TRY(allgather_limbs(c, c2.d, c2_bs, batch, N, all_ranges(c, nd, 0, nl), st));
 
-    // :1511-1552 digit loop on the own target limbs
-    for (int i = 0; i < beta; ++i) {
-        LG_TRY(decompose_range(e->dec.get(), level, i, batch, c2.d, c2_bs, d.d, d_bs, myq, myp, st));
-        const int p0idxst = i * alpha;
-        int p0idxed = p0idxst + e->dec->xalpha[i];
-        if (p0idxed > nl) p0idxed = nl;
-        const Range skip = clip(Range{p0idxst, p0idxed}, mine.b, mine.e);  // digit limbs inside the own block
-        NttMac mac;
-        mac.enabled = 1;
-        mac.evk0 = evk->key(i, 0);
-        mac.evk1 = evk->key(i, 1);
-        mac.acc0 = acc0 + (size_t)mine.b * N;
-        mac.acc1 = acc1 + (size_t)mine.b * N;
-        mac.acc_bs = d_bs;
-        mac.cx = cx + (size_t)mine.b * N;
-        mac.cx_bs = cx_bs;
-        mac.first = (i == 0);
-        mac.reduce = ((i & 7) == 1) || (i == beta - 1);
-        if (mine.n() > 0)
-            LG_TRY(lgi_ntt(QP, sub_map(qp_map, mine.b), mine.n(), batch, d.d + (size_t)mine.b * N, d_bs, d.d + (size_t)mine.b * N,
-                           d_bs, false, skip.b, skip.e, st, &mac));
+    // :1511-1552 digit loop on the own target limbs: every digit decomposed and taken through the strided NTT
+    // phase, then the fused contiguous-phase + multiply-accumulate kernel over the own limbs (register
+    // accumulators across the digits, as on one GPU)
+    if (mine.n() > 0) {
+        Scratch D(st);
+        LG_TRY(D.alloc((size_t)beta * batch * d_bs));
+        const size_t d_ds = (size_t)batch * d_bs;
+        for (int i = 0; i < beta; ++i)
+            LG_TRY(decompose_range(e->dec.get(), level, i, batch, c2.d, c2_bs, D.d + (size_t)i * d_ds, d_bs, myq, myp, st));
+        NttArgs a;
+        memset(&a, 0, sizeof(a));
+        a.T = QP->T;
+        a.map = sub_map(qp_map, mine.b);
+        a.in = D.d + (size_t)mine.b * N;
+        a.out = D.d + (size_t)mine.b * N;
+        a.in_bstride = a.out_bstride = d_bs;
+        a.skip_alpha = alpha;
+        a.skip_div = batch;
+        a.skip_nl = nl;
+        a.skip_limb0 = mine.b;
+        LG_REQUIRE(lg_launch_ntt_fwd_strided(a, mine.n(), beta * batch, st) == 0, "switchKeys: strided NTT launch failed");
+        LG_LAUNCH_CHECK();
+        KsFusedArgs k;
+        memset(&k, 0, sizeof(k));
+        k.T = QP->T;
+        k.map = sub_map(qp_map, mine.b);
+        k.D = D.d + (size_t)mine.b * N;
+        k.d_ds = d_ds;
+        k.d_bs = d_bs;
+        k.cx = cx + (size_t)mine.b * N;
+        k.cx_bs = cx_bs;
+        k.evk = evk->key(0, 0);
+        k.evk_ds = (size_t)(evk->key(1, 0) - evk->key(0, 0));
+        k.evk_hs = (size_t)(evk->key(0, 1) - evk->key(0, 0));
+        k.acc0 = acc0 + (size_t)mine.b * N;
+        k.acc1 = acc1 + (size_t)mine.b * N;
+        k.acc_bs = d_bs;
+        k.beta = beta;
+        k.alpha = alpha;
+        k.nl = nl;
+        k.limb0 = mine.b;
+        LG_REQUIRE(lg_launch_ks_fused(k, mine.n(), batch, st) == 0, "switchKeys: fused digit loop launch failed");
+        LG_LAUNCH_CHECK();
     }
 
     // :1556-1557 ModDownSplitedNTTPQ: InvNTT of the own special-prime limbs, all-gather them (modUpExact

@@ -10,21 +10,6 @@ extern std::atomic<uint64_t> lg_g_launches;  // kernels launched by this library
 #define LG_MAX_LIMBS 64
 
 // ---- K1: NTT ----------------------------------------------------------------
-// Optional key-switch epilogue of the forward transform (ckks/evaluator.go:1515-1541): instead of
-// storing the NTT of data limb j, accumulate MRed(evk[.][tl], ntt) into acc0/acc1.  Data limbs in the
-// skip range are not transformed: their NTT-domain values are read from `cx` (evaluator.go:1579-1584).
-struct NttMac {
-    int enabled;
-    const u64* evk0;  // evk[i][0], table limb tl at evk0 + tl*N (shared by the batch)
-    const u64* evk1;
-    u64* acc0;        // limb j of batch b at acc + b*acc_bs + j*N
-    u64* acc1;
-    size_t acc_bs;
-    const u64* cx;
-    size_t cx_bs;
-    int first;        // 1: acc = MRed(..), 0: acc += MRed(..)
-    int reduce;       // 1: BRedAdd the accumulators after adding
-};
 struct NttArgs {
     RingTables T;
     LimbMap map;
@@ -35,10 +20,10 @@ struct NttArgs {
     // forward, digit-batched launches: when skip_alpha > 0 the batch index is digit*skip_div + b and the
     // skipped limbs of that entry are [digit*skip_alpha, min((digit+1)*skip_alpha, skip_nl))
     int skip_alpha, skip_div, skip_nl;
+    int skip_limb0;                  // ... of the launch's first data limb (limb-sharded launches), default 0
     // inverse only: per (batch, limb) flag, non-zero = some input word is above 2q, use the literal
     // butterflies for that limb (written by lg_launch_range_flags); nullptr = inputs known to be in range
     const u32* flags;
-    NttMac mac;
 };
 int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cudaStream_t st);
 // forward transform, strided phase only, in place or out of place (logN >= 12); the contiguous phase is
@@ -64,6 +49,7 @@ struct KsFusedArgs {
     u64* acc1;
     size_t acc_bs;
     int beta, alpha, nl;  // digit i owns data limbs [i*alpha, min((i+1)*alpha, nl))
+    int limb0;            // index of the launch's first data limb (limb-sharded launches; pointers are pre-offset)
 };
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st);
 

@@ -244,8 +244,8 @@ LG_DEV LimbSetup setup_limb(const NttArgs& a) {
     LimbSetup s;
     const int j = blockIdx.z, b = blockIdx.x;
     if (a.skip_alpha > 0) {
-        const int dg = b / a.skip_div;
-        s.skip = (j < a.skip_nl) && (j >= dg * a.skip_alpha) && (j < (dg + 1) * a.skip_alpha);
+        const int dg = b / a.skip_div, gj = a.skip_limb0 + j;
+        s.skip = (gj < a.skip_nl) && (gj >= dg * a.skip_alpha) && (gj < (dg + 1) * a.skip_alpha);
     } else {
         s.skip = (j >= a.skip0 && j < a.skip1);
     }
@@ -349,134 +349,9 @@ __global__ void __launch_bounds__(256, STRIDED_MINB) ntt_fwd_strided(const NttAr
 
 // ---- contiguous phase geometry ------------------------------------------------
 // 128-thread CTA = 4 warps = 8 segments of 256 words (tile of 2048 words); the 16 threads of a segment
-// exchange through their own 16 x 18-word shared region (row stride 18 keeps both the 64-bit column
-// accesses and the 128-bit row accesses conflict-free).
+// exchange through shared memory warp-synchronously.
 #define CONTIG_THREADS 128
 #define CONTIG_TILE 2048u
-#define SEG_SM 288  // 16 rows x 18 words
-
-struct SegPos {
-    u32 segbase;  // first word of this thread's segment within the limb
-    u32 cc;       // position of the thread within the segment (0..15)
-    u64* sm;      // the segment's shared region
-};
-LG_DEV SegPos seg_pos(u64* smem) {
-    SegPos p;
-    const u32 t = threadIdx.x, sg = t >> 4;
-    p.cc = t & 15;
-    p.segbase = blockIdx.y * CONTIG_TILE + sg * 256u;
-    p.sm = smem + sg * SEG_SM;
-    return p;
-}
-// column layout x[r] <-> word cc + 16r ; row layout x[r] <-> word 16cc + r
-LG_DEV void seg_store_cols(const SegPos& p, const u64 (&x)[16]) {
-#pragma unroll
-    for (int r = 0; r < 16; ++r) p.sm[18 * r + p.cc] = x[r];
-}
-LG_DEV void seg_load_rows(const SegPos& p, u64 (&x)[16]) {
-    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(p.sm + 18 * p.cc);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const ulonglong2 v = row[r];
-        x[2 * r] = v.x;
-        x[2 * r + 1] = v.y;
-    }
-}
-
-// forward contiguous phase of one segment: reads in[segbase + cc + 16r], leaves the (lazy, unreduced)
-// transform of words segbase + 16cc + r in x[r]
-template <int MODE>
-LG_DEV void fwd_contig_seg(u64 (&x)[16], const TwConst& c, u32 N, const u64* __restrict__ in, const SegPos& p) {
-    const u32 j0 = p.segbase + p.cc;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = in[j0 + 16 * r];
-    fwd_stages<3, false, MODE>(x, c, (N + j0) >> 4);
-    __syncwarp();
-    seg_store_cols(p, x);
-    __syncwarp();
-    seg_load_rows(p, x);
-    fwd_stages<3, true, MODE>(x, c, N + p.segbase + 16 * p.cc);
-}
-
-// MAC = true: legacy per-digit key-switch epilogue (NttMac), used by the limb-sharded driver.
-template <bool MAC, int MODE>
-LG_DEV void fwd_contig_body(const NttArgs& a, const LimbSetup& s, const SegPos& p) {
-    const u32 N = a.T.N;
-    const u64 q = s.c.q, qinv = s.c.qinv;
-    const u32 e0 = p.segbase + 16 * p.cc;
-    u64 x[16];
-    if (MAC && s.skip) {
-        const int j = blockIdx.z, b = blockIdx.x;
-        const u64* cx = a.mac.cx + (size_t)b * a.mac.cx_bs + (size_t)j * N + e0;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            u64 v[4];
-            ld256(v, cx + 4 * h);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[4 * h + e] = v[e];
-        }
-    } else {
-        const TwConst c = tw_const<true, MODE>(a.T, s.c, s.tl);
-        fwd_contig_seg<MODE>(x, c, N, s.in, p);
-    }
-    if (!MAC) {
-        // ring/ntt.go:83-85
-#pragma unroll
-        for (int h = 0; h < 4; ++h)
-            st256(s.out + e0 + 4 * h, bred_add(x[4 * h], q, s.c.u0), bred_add(x[4 * h + 1], q, s.c.u0),
-                  bred_add(x[4 * h + 2], q, s.c.u0), bred_add(x[4 * h + 3], q, s.c.u0));
-    } else {
-        const int j = blockIdx.z, b = blockIdx.x;
-        const size_t ko = (size_t)s.tl * N + e0, ao = (size_t)b * a.mac.acc_bs + (size_t)j * N + e0;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            u64 k0[4], k1[4], r0[4], r1[4];
-            ld256_nc(k0, a.mac.evk0 + ko + 4 * h);
-            ld256_nc(k1, a.mac.evk1 + ko + 4 * h);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                r0[e] = mred(k0[e], x[4 * h + e], q, qinv);
-                r1[e] = mred(k1[e], x[4 * h + e], q, qinv);
-            }
-            if (!a.mac.first) {
-                u64 o0[4], o1[4];
-                ld256(o0, a.mac.acc0 + ao + 4 * h);
-                ld256(o1, a.mac.acc1 + ao + 4 * h);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    r0[e] += o0[e];
-                    r1[e] += o1[e];
-                }
-            }
-            if (a.mac.reduce) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    r0[e] = bred_add(r0[e], q, s.c.u0);
-                    r1[e] = bred_add(r1[e], q, s.c.u0);
-                }
-            }
-            st256(a.mac.acc0 + ao + 4 * h, r0[0], r0[1], r0[2], r0[3]);
-            st256(a.mac.acc1 + ao + 4 * h, r1[0], r1[1], r1[2], r1[3]);
-        }
-    }
-}
-
-template <bool MAC, bool LITERAL>
-__global__ void __launch_bounds__(CONTIG_THREADS) ntt_fwd_contig(const NttArgs a) {
-    __shared__ __align__(16) u64 smem[8 * SEG_SM];
-    const LimbSetup s = setup_limb(a);
-    if (!MAC && s.skip) return;
-    const SegPos p = seg_pos(smem);
-    const int mode = LITERAL ? M_LITERAL : fwd_mode(s.c.q);
-    if (mode == M_F64)
-        fwd_contig_body<MAC, M_F64>(a, s, p);
-    else if (mode == M_FREE)
-        fwd_contig_body<MAC, M_FREE>(a, s, p);
-    else if (mode == M_LAZY)
-        fwd_contig_body<MAC, M_LAZY>(a, s, p);
-    else
-        fwd_contig_body<MAC, M_LITERAL>(a, s, p);
-}
 
 // ---- key-switch digit loop fused with the contiguous phase ---------------------
 // Everything the digit loop re-reads is staged once: the tile's twiddles live in shared memory for all
@@ -621,8 +496,8 @@ __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttAr
     const int j = blockIdx.z;
     const int b0 = blockIdx.x * bpc, nb = (batch - b0) < bpc ? (batch - b0) : bpc;
     if (a.skip_alpha > 0) {  // digit-batched launch: bpc divides skip_div, so a group never straddles two digits
-        const int dg = b0 / a.skip_div;
-        if (j < a.skip_nl && j >= dg * a.skip_alpha && j < (dg + 1) * a.skip_alpha) return;
+        const int dg = b0 / a.skip_div, gj = a.skip_limb0 + j;
+        if (gj < a.skip_nl && gj >= dg * a.skip_alpha && gj < (dg + 1) * a.skip_alpha) return;
     } else if (j >= a.skip0 && j < a.skip1) {
         return;
     }
@@ -663,7 +538,7 @@ LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64
     u64* const twseg = smem + 2 * 2048 + 30 * CONTIG_THREADS + sg * 32;  // w at [k], ws at [15+k]
 
     const u64* din = a.D + (size_t)b * a.d_bs + (size_t)j * N + tile0;
-    const int own_i = (j < a.nl) ? j / a.alpha : -1;  // the digit whose own limb this is
+    const int own_i = (a.limb0 + j < a.nl) ? (a.limb0 + j) / a.alpha : -1;  // the digit whose own limb this is
     if (own_i != 0) prefetch_warp_tile(tilebuf, din);
 
     contig_fill_tw<MODE>(c, N, segbase, cc, twp, twseg);  // twiddles of the tile, once for all digits
@@ -940,7 +815,6 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     if (nlimbs <= 0 || batch <= 0) return 0;
     const u32 logN = args.T.logN, N = args.T.N;
     if (logN < 1 || logN > 16) return 1;
-    if (args.mac.enabled && (logN <= 11 || inverse)) return 1;
     if (logN <= 11) {
         const u32 threads = (N >> 1) < 32 ? 32 : ((N >> 1) > 512 ? 512 : (N >> 1));
         dim3 grid(batch, 1, nlimbs);
@@ -953,28 +827,13 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     }
     const int L = (int)logN - 8;
     const bool literal = literal_ntt();
-    const dim3 sgrid(batch, N / 4096, nlimbs), cgrid(batch, N / CONTIG_TILE, nlimbs);
+    const dim3 sgrid(batch, N / 4096, nlimbs);
     NttArgs second = args;  // the second phase runs in place on the output
     second.in = args.out;
     second.in_bstride = args.out_bstride;
     if (!inverse) {
-        // with the MAC epilogue the strided phase runs in place on the input (the decomposed digit)
-        NttArgs first = args;
-        if (args.mac.enabled) {
-            first.out = const_cast<u64*>(args.in);
-            first.out_bstride = args.in_bstride;
-            second.in = args.in;
-            second.in_bstride = args.in_bstride;
-        }
-        launch_strided_any(L, true, literal, first, sgrid, st);
-        if (args.mac.enabled) {
-            if (literal)
-                ntt_fwd_contig<true, true><<<cgrid, CONTIG_THREADS, 0, st>>>(second);
-            else
-                ntt_fwd_contig<true, false><<<cgrid, CONTIG_THREADS, 0, st>>>(second);
-        } else {
-            launch_contig_pipe(true, literal, second, nlimbs, batch, st);
-        }
+        launch_strided_any(L, true, literal, args, sgrid, st);
+        launch_contig_pipe(true, literal, second, nlimbs, batch, st);
     } else {
         launch_contig_pipe(false, literal, args, nlimbs, batch, st);
         launch_strided_any(L, false, literal, second, sgrid, st);

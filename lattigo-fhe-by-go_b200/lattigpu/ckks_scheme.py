@@ -17,7 +17,10 @@ from .ckks import SwitchingKey
 
 def signed_to_poly(context, coeffs, batch=1):
     """Residues of small signed coefficients over every modulus of `context`: x >= 0 -> x, x < 0 -> q + x
-    (what the samplers write, e.g. ring/gaussianSampler.go:271).  coeffs: int array [N] or [batch][N]."""
+    (what the samplers write, e.g. ring/gaussianSampler.go:271).  coeffs: int array [N] or [batch][N], or a
+    device Poly that already holds the residues (returned as is)."""
+    if isinstance(coeffs, ring.Poly):
+        return coeffs
     c = np.asarray(coeffs, dtype=np.int64)
     if c.ndim == 1:
         c = c[None, :]
