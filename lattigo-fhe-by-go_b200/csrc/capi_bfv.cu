@@ -82,10 +82,8 @@ int bfv_switch_keys(lg_bfv_eval* e, int batch, const u64* cx, size_t cx_bs, cons
     // (the accumulators are canonical, so the inverse needs no range check)
     LG_TRY(lgi_ntt(QP, limb_map_identity(), nd, 2 * batch, acc0, d_bs, acc0, d_bs, true, 0, 0, st, true));
     // :811-812 ModDownPQ
-    LG_TRY(lgi_moddown_tail_ntt(e->q1p.get(), level, batch, acc0, d_bs, acc0 + (size_t)nQ * N, d_bs, out0, out0_bs, false, st,
-                                add0));
-    LG_TRY(lgi_moddown_tail_ntt(e->q1p.get(), level, batch, acc1, d_bs, acc1 + (size_t)nQ * N, d_bs, out1, out1_bs, false, st,
-                                add1));
+    LG_TRY(lgi_moddown_pair_ntt(e->q1p.get(), level, batch, acc0, acc1, d_bs, nQ, out0, out0_bs, add0, out1, out1_bs, add1, false,
+                                st, true));
     return LG_OK;
 }
 

@@ -141,6 +141,35 @@ int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* 
                   p1Q_bs, tmp.d, tbs, p2, p2_bs, e->moddown_pq.data(), nl, st);
 }
 
+// Two ModDowns whose inputs sit back to back ([2][batch][...] accumulators of a key switch): InvNTT, modUpExact and
+// NTT run once over 2*batch entries, only the final (x - y) * P^-1 (+ add) differs per output.
+int lgi_moddown_pair_ntt(const lg_extender* e, int level, int batch, u64* acc0, u64* acc1, size_t acc_bs, int p_off, u64* out0,
+                         size_t out0_bs, bool add0, u64* out1, size_t out1_bs, bool add1, bool ntt, cudaStream_t st,
+                         bool p_in_range) {
+    const lg_ring* Q = e->Q;
+    const lg_ring* P = e->P;
+    const u64 N = Q->N;
+    const int nl = level + 1;
+    LG_REQUIRE(level >= 0 && nl <= Q->nl, "ModDown: level %d out of range", level);
+    if (acc1 != acc0 + (size_t)batch * acc_bs) {  // not contiguous: two independent passes
+        LG_TRY(lgi_moddown_tail_ntt(e, level, batch, acc0, acc_bs, acc0 + (size_t)p_off * N, acc_bs, out0, out0_bs, ntt, st, add0,
+                                    p_in_range));
+        return lgi_moddown_tail_ntt(e, level, batch, acc1, acc_bs, acc1 + (size_t)p_off * N, acc_bs, out1, out1_bs, ntt, st, add1,
+                                    p_in_range);
+    }
+    u64* pP = acc0 + (size_t)p_off * N;
+    if (ntt) LG_TRY(lgi_ntt(P, limb_map_identity(), P->nl, 2 * batch, pP, acc_bs, pP, acc_bs, true, 0, 0, st, p_in_range));
+    Scratch tmp(st);
+    LG_TRY(tmp.alloc((size_t)2 * batch * nl * N));
+    const size_t tbs = (size_t)nl * N;
+    LG_TRY(lgi_modup_launch(e->pq, N, 2 * batch, pP, acc_bs, P->nl, tmp.d, tbs, nl, 0, st));
+    if (ntt) LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, 2 * batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
+    LG_TRY(lgi_ew(add0 ? EW_SUB_MULMONT_SCALAR_ADD : EW_SUB_MULMONT_SCALAR, Q, limb_map_identity(), nl, batch, acc0, acc_bs,
+                  tmp.d, tbs, out0, out0_bs, e->moddown_pq.data(), nl, st));
+    return lgi_ew(add1 ? EW_SUB_MULMONT_SCALAR_ADD : EW_SUB_MULMONT_SCALAR, Q, limb_map_identity(), nl, batch, acc1, acc_bs,
+                  tmp.d + (size_t)batch * tbs, tbs, out1, out1_bs, e->moddown_pq.data(), nl, st);
+}
+
 extern "C" {
 
 int lg_extender_create(const lg_ring* ringQ, const lg_ring* ringP, lg_extender** out) {
@@ -492,11 +521,8 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
                                 acc1, d_bs, 1, st));
     // :1556-1557
     // the accumulators are canonical, so their inverse transforms need no range check
-    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc0, d_bs, acc0 + (size_t)nl * N, d_bs, out0, out0_bs, true, st,
-                                add0, true));
-    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc1, d_bs, acc1 + (size_t)nl * N, d_bs, out1, out1_bs, true, st,
-                                add1, true));
-    return LG_OK;
+    return lgi_moddown_pair_ntt(e->ext.get(), level, batch, acc0, acc1, d_bs, nl, out0, out0_bs, add0, out1, out1_bs, add1, true,
+                                st, true);
 }
 
 int lgi_concat_ring(const lg_ring* Q, const lg_ring* P, std::unique_ptr<lg_ring>& out) {
@@ -825,10 +851,8 @@ int lg_ckks_switch_key_hoisted(lg_ckks_eval* e, const lg_hoisted* h, const lg_po
     LG_REQUIRE(lg_launch_ks_hoisted(ka, nd, batch, st) == 0, "switchKeyHoisted: launch failed");
     LG_LAUNCH_CHECK();
     // :1382-1386  ModDown both; value[0] += pool2Q, value[1] = pool3Q
-    LG_TRY(lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc0, h->d_bs, acc0 + (size_t)nl * N, h->d_bs, out0->d,
-                                out0->bstride, true, st, true, true));
-    return lgi_moddown_tail_ntt(e->ext.get(), level, batch, acc1, h->d_bs, acc1 + (size_t)nl * N, h->d_bs, out1->d,
-                                out1->bstride, true, st, false, true);
+    return lgi_moddown_pair_ntt(e->ext.get(), level, batch, acc0, acc1, h->d_bs, nl, out0->d, out0->bstride, true, out1->d,
+                                out1->bstride, false, true, st, true);
 }
 
 int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_galois* g, const lg_swk* k,

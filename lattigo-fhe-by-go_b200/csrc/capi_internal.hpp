@@ -157,6 +157,9 @@ int lgi_ew(int op, const lg_ring* r, LimbMap map, int nl, int batch, const u64* 
 int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* p1Q, size_t p1Q_bs, u64* p1P,
                          size_t p1P_bs, u64* p2, size_t p2_bs, bool ntt, cudaStream_t st, bool accumulate = false,
                          bool p_in_range = false);
+int lgi_moddown_pair_ntt(const lg_extender* e, int level, int batch, u64* acc0, u64* acc1, size_t acc_bs, int p_off, u64* out0,
+                         size_t out0_bs, bool add0, u64* out1, size_t out1_bs, bool add1, bool ntt, cudaStream_t st,
+                         bool p_in_range);
 int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u64* p0, size_t p0_bs, u64* outQ,
                   size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st);
 int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, const lg_decomposer* dec, int level, int beta,
