@@ -103,6 +103,13 @@ int lg_poly_download(const lg_poly* p, int batch0, int nbatch, int limb0, int nl
 /* stream-ordered variants for C-allocated pinned staging buffers: the host buffer must stay valid (and
  * for uploads unchanged) until the stream reaches the copy -- not for Go-managed memory */
 int lg_poly_upload_async(lg_poly* p, int batch0, int nbatch, int limb0, int nl, const uint64_t* host, lg_stream_t stream);
+/* Wire format, ring/ring_object.go:146-289: WriteTo / WriteCoeffs (:161-184), GetDataLen (:186-192), DecodePolyNew /
+ * UnmarshalBinary / DecodeCoeffs (:194-289).  data[0] = log2(N), data[1] = #moduli, then big-endian uint64 limb-major;
+ * with_metadata = 0 is the header-less WriteCoeffs / DecodeCoeffs form.  Entry `batch_index` of the handle is written /
+ * filled; the byte swap runs on the device, the call returns when `data` is complete. */
+uint64_t lg_poly_get_data_len(const lg_poly* p, int nl, int with_metadata);
+int lg_poly_write_to(const lg_poly* p, int batch_index, int nl, uint8_t* data, uint64_t len, int with_metadata, lg_stream_t stream);
+int lg_poly_decode(lg_poly* p, int batch_index, const uint8_t* data, uint64_t len, int with_metadata, int nl, lg_stream_t stream);
 int lg_poly_download_async(const lg_poly* p, int batch0, int nbatch, int limb0, int nl, uint64_t* host, lg_stream_t stream);
 int lg_poly_zero(lg_poly* p, lg_stream_t stream);                                /* Poly.Zero, ring_object.go:60-67 */
 int lg_poly_copy(const lg_poly* src, int nl, lg_poly* dst, lg_stream_t stream);  /* Copy/CopyLvl, ring_object.go:85-121 */

@@ -348,6 +348,58 @@ int lg_poly_upload_async(lg_poly* p, int batch0, int nbatch, int limb0, int nl, 
 int lg_poly_download_async(const lg_poly* p, int batch0, int nbatch, int limb0, int nl, uint64_t* host, lg_stream_t s) {
     return poly_xfer(p, batch0, nbatch, limb0, nl, host, false, cs(s), false);
 }
+// Wire format of ring.Poly (ring/ring_object.go:146-289): data[0] = log2(N), data[1] = number of moduli, then the
+// coefficients limb-major as big-endian 64-bit words.  The byte swap runs on the device.
+uint64_t lg_poly_get_data_len(const lg_poly* p, int nl, int with_metadata) {  // GetDataLen :186-192
+    if (!p) return 0;
+    return (uint64_t)(with_metadata ? 2 : 0) + (((uint64_t)nl * p->N) << 3);
+}
+int lg_poly_write_to(const lg_poly* p, int batch_index, int nl, uint8_t* data, uint64_t len, int with_metadata, lg_stream_t s) {
+    LG_REQUIRE(p && data, "WriteTo: null argument");
+    LG_REQUIRE(batch_index >= 0 && batch_index < p->batch, "WriteTo: batch index out of range");
+    LG_REQUIRE(nl >= 0 && nl <= p->nlimbs && nl <= 255, "WriteTo: limb count out of range");
+    LG_REQUIRE(len >= lg_poly_get_data_len(p, nl, with_metadata), "Data array is too small to write ring.Poly");  // :165-168
+    size_t off = 0;
+    if (with_metadata) {
+        data[0] = (uint8_t)lgh::log2u(p->N);  // :169-170
+        data[1] = (uint8_t)nl;
+        off = 2;
+    }
+    const size_t words = (size_t)nl * p->N;
+    if (words == 0) return LG_OK;
+    Scratch tmp(cs(s));
+    LG_TRY(tmp.alloc(words));
+    lg_launch_bswap64(p->d + (size_t)batch_index * p->bstride, tmp.d, words, cs(s));
+    LG_LAUNCH_CHECK();
+    LG_CUDA_CHECK(cudaMemcpyAsync(data + off, tmp.d, words * sizeof(u64), cudaMemcpyDeviceToHost, cs(s)));
+    LG_CUDA_CHECK(cudaStreamSynchronize(cs(s)));
+    return LG_OK;
+}
+int lg_poly_decode(lg_poly* p, int batch_index, const uint8_t* data, uint64_t len, int with_metadata, int nl, lg_stream_t s) {
+    LG_REQUIRE(p && data, "DecodePoly: null argument");
+    LG_REQUIRE(batch_index >= 0 && batch_index < p->batch, "DecodePoly: batch index out of range");
+    size_t off = 0;
+    if (with_metadata) {  // UnmarshalBinary :257-274
+        LG_REQUIRE(len >= 2, "error : invalid polynomial encoding");
+        const uint64_t N = 1ull << (data[0] & 63);
+        nl = data[1];
+        LG_REQUIRE(((len - 2) >> 3) == N * (uint64_t)nl, "error : invalid polynomial encoding");
+        LG_REQUIRE(N == p->N, "DecodePoly: encoded degree 2^%u differs from the polynomial's", (unsigned)data[0]);
+        off = 2;
+    } else {
+        LG_REQUIRE(len >= (((uint64_t)nl * p->N) << 3), "DecodeCoeffs: data array too small");
+    }
+    LG_REQUIRE(nl >= 0 && nl <= p->nlimbs, "DecodePoly: %d moduli encoded, polynomial has %d", nl, p->nlimbs);
+    const size_t words = (size_t)nl * p->N;
+    if (words == 0) return LG_OK;
+    Scratch tmp(cs(s));
+    LG_TRY(tmp.alloc(words));
+    LG_CUDA_CHECK(cudaMemcpyAsync(tmp.d, data + off, words * sizeof(u64), cudaMemcpyHostToDevice, cs(s)));
+    lg_launch_bswap64(tmp.d, p->d + (size_t)batch_index * p->bstride, words, cs(s));
+    LG_LAUNCH_CHECK();
+    LG_CUDA_CHECK(cudaStreamSynchronize(cs(s)));
+    return LG_OK;
+}
 int lg_poly_zero(lg_poly* p, lg_stream_t s) {
     LG_REQUIRE(p, "null argument");
     LG_CUDA_CHECK(cudaMemset2DAsync(p->d, p->bstride * sizeof(u64), 0, (size_t)p->nlimbs * p->N * sizeof(u64), p->batch,

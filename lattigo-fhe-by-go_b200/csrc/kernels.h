@@ -123,6 +123,7 @@ int lg_launch_permute_ntt(const PermArgs& a, int nlimbs, int batch, cudaStream_t
 int lg_launch_permute_coeff(const PermArgs& a, int nlimbs, int batch, cudaStream_t st);
 int lg_launch_mult_by_monomial(const PermArgs& a, int nlimbs, int batch, cudaStream_t st);
 int lg_launch_bitreverse(const PermArgs& a, int nlimbs, int batch, cudaStream_t st);
+int lg_launch_bswap64(const u64* in, u64* out, size_t words, cudaStream_t st);  // byte-reversed words (wire format)
 
 // ---- K3b: exact basis extension (ring/ring_basis_extension.go:352-393) ------
 // Device-resident modupParams.  Source basis = nsrc primes, target basis = ndst

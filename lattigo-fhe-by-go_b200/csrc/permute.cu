@@ -74,6 +74,15 @@ dim3 perm_grid(u32 N, int nlimbs, int batch) {
     return dim3(bx, nlimbs, batch);
 }
 
+// big-endian <-> host-endian words (ring/ring_object.go:146-156, :196-206: binary.BigEndian.PutUint64 / Uint64)
+__global__ void __launch_bounds__(256) bswap64_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const u64 x = in[i];
+        const u32 lo = (u32)x, hi = (u32)(x >> 32);
+        out[i] = ((u64)__byte_perm(lo, 0, 0x0123) << 32) | (u64)__byte_perm(hi, 0, 0x0123);
+    }
+}
+
 }  // namespace
 
 int lg_launch_permute_ntt(const PermArgs& a, int nlimbs, int batch, cudaStream_t st) {
@@ -97,6 +106,15 @@ int lg_launch_mult_by_monomial(const PermArgs& a, int nlimbs, int batch, cudaStr
 int lg_launch_bitreverse(const PermArgs& a, int nlimbs, int batch, cudaStream_t st) {
     if (nlimbs <= 0 || batch <= 0) return 0;
     bitrev_kernel<<<perm_grid(a.T.N, nlimbs, batch), 256, 0, st>>>(a);
+    lg_g_launches += 1;
+    return 0;
+}
+
+int lg_launch_bswap64(const u64* in, u64* out, size_t words, cudaStream_t st) {
+    if (words == 0) return 0;
+    size_t bx = (words + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    bswap64_kernel<<<(unsigned)bx, 256, 0, st>>>(in, out, words);
     lg_g_launches += 1;
     return 0;
 }

@@ -66,6 +66,9 @@ SIGNATURES = {
     "lg_poly_wrap": (ci, [vp, u64, ci, ci, C.POINTER(vp)]),
     "lg_poly_view": (ci, [_P, ci, ci, C.POINTER(vp)]),
     "lg_poly_destroy": (ci, [_P]),
+    "lg_poly_get_data_len": (u64, [_P, ci, ci]),
+    "lg_poly_write_to": (ci, [_P, ci, ci, C.c_char_p, u64, ci, vp]),
+    "lg_poly_decode": (ci, [_P, ci, C.c_char_p, u64, ci, ci, vp]),
     "lg_poly_n": (u64, [_P]),
     "lg_poly_nlimbs": (ci, [_P]),
     "lg_poly_batch": (ci, [_P]),

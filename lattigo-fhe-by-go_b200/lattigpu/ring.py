@@ -134,6 +134,23 @@ class Poly:
         check(lib().lg_poly_download(self.h, 0, self.batch, limb0, nl, _ptr(out), _s(stream)))
         return out[0] if (squeeze and self.batch == 1) else out
 
+    # ring/ring_object.go:146-289 -- wire format (2-byte header, big-endian words, limb-major)
+    def GetDataLen(self, WithMetadata=True, nl=None):
+        return int(lib().lg_poly_get_data_len(self.h, self.nlimbs if nl is None else nl, 1 if WithMetadata else 0))
+
+    def MarshalBinary(self, batch_index=0, nl=None, WithMetadata=True, stream=None):
+        """WriteTo / MarshalBinary (:161-175, :224-231); WithMetadata=False is WriteCoeffs (:177-184)"""
+        nl = self.nlimbs if nl is None else nl
+        buf = C.create_string_buffer(self.GetDataLen(WithMetadata, nl))
+        check(lib().lg_poly_write_to(self.h, batch_index, nl, buf, len(buf), 1 if WithMetadata else 0, _s(stream)))
+        return buf.raw
+
+    def UnmarshalBinary(self, data, batch_index=0, WithMetadata=True, nl=None, stream=None):
+        """UnmarshalBinary / DecodePolyNew (:257-289); WithMetadata=False is DecodeCoeffs over `nl` moduli"""
+        data = bytes(data)
+        check(lib().lg_poly_decode(self.h, batch_index, data, len(data), 1 if WithMetadata else 0,
+                                   self.nlimbs if nl is None else nl, _s(stream)))
+
     def device_ptr(self):
         return lib().lg_poly_device_ptr(self.h)
 

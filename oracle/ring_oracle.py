@@ -671,6 +671,24 @@ def ckks_const_op(ctx, op, level, polys_in, polys_out, c_real=0.0, c_imag=0.0, s
     return outs
 
 
+# ---------------------------------------------------------------------------
+# ring.Poly wire format (ring/ring_object.go:146-289)
+# ---------------------------------------------------------------------------
+def poly_marshal(p, with_metadata=True):
+    """WriteTo :161-175: data[0] = log2(N), data[1] = #moduli, then binary.BigEndian.PutUint64 limb-major"""
+    nl, N = p.shape
+    head = bytes([N.bit_length() - 1, nl]) if with_metadata else b""
+    return head + np.ascontiguousarray(p).astype(">u8").tobytes()
+
+
+def poly_unmarshal(data):
+    """UnmarshalBinary :257-274"""
+    N, nl = 1 << data[0], data[1]
+    if ((len(data) - 2) >> 3) != N * nl:
+        raise ValueError("error : invalid polynomial encoding")
+    return np.frombuffer(data, dtype=">u8", offset=2).astype(np.uint64).reshape(nl, N)
+
+
 def _declare_bfv(L):
     def f(name, res, *args):
         fn = getattr(L, name)

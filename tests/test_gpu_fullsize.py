@@ -79,6 +79,16 @@ def test_ckks_pn16_mulrelin_rescale_rotate(lg):
     cQ.InvNTT(pa[0], t)
     cQ.NTT(t, t)
     assert np.array_equal(t.numpy(squeeze=False), a[:, 0])
+    # (5) RotateHoisted at full size: two rotations off one decomposition, one entry against the oracle,
+    # duplicated inputs elsewhere (the same key stands in for both rotation keys)
+    idxs = [lg.ring.PermuteNTTIndex(5, k, N) for k in (1, 7)]
+    outs = [(lg.ring.Poly(N, nQ, batch), lg.ring.Poly(N, nQ, batch)) for _ in idxs]
+    ev.RotateHoisted(level, pa, [(i, key) for i in idxs], outs)
+    want = oev.rotate_hoisted(level, np.ascontiguousarray(a[1]), [orc.permute_ntt_index(5, k, N) for k in (1, 7)], [evk, evk])
+    for o, w in zip(outs, want):
+        g = host(o, nQ)
+        assert np.array_equal(g[1], w)
+        assert np.array_equal(g[0], g[2])
 
 
 def test_bfv_pn15_mul_relin_rotate(lg):

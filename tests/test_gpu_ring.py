@@ -403,3 +403,28 @@ def test_decomposer(lg, N, nQ, nP, kind):
                 wq, wp = od.decompose_and_split(level, crt, a[b])
                 assert np.array_equal(gq[b], wq) and np.array_equal(gp[b], wp), (level, crt)
                 assert np.array_equal(g1[b], od.decompose(level, crt, a[b])), (level, crt)
+
+
+def test_poly_wire_format(lg):
+    """MarshalBinary / WriteCoeffs / UnmarshalBinary (ring/ring_object.go:146-289) against the oracle's bytes:
+    device-side byte swap, any batch entry, partial limb count, error on a truncated encoding."""
+    N, nl, batch = 4096, 3, 2
+    rng = np.random.default_rng(71)
+    a = rng.integers(0, 1 << 64, size=(batch, nl, N), dtype=np.uint64)
+    p = lg.ring.Poly.from_numpy(a)
+    for b in range(batch):
+        assert p.MarshalBinary(batch_index=b) == orc.poly_marshal(a[b])
+        assert p.MarshalBinary(batch_index=b, nl=2) == orc.poly_marshal(a[b, :2])
+        assert p.MarshalBinary(batch_index=b, WithMetadata=False) == orc.poly_marshal(a[b], with_metadata=False)
+    assert p.GetDataLen() == 2 + nl * N * 8 and p.GetDataLen(False) == nl * N * 8
+    q = lg.ring.Poly(N, nl, batch)
+    q.Zero()
+    q.UnmarshalBinary(orc.poly_marshal(a[1]), batch_index=0)
+    q.UnmarshalBinary(orc.poly_marshal(a[0]), batch_index=1)
+    got = q.numpy(squeeze=False)
+    assert np.array_equal(got[0], a[1]) and np.array_equal(got[1], a[0])
+    assert np.array_equal(orc.poly_unmarshal(p.MarshalBinary(1)), a[1])
+    with pytest.raises(lg.LattigpuError, match="invalid polynomial encoding"):
+        q.UnmarshalBinary(orc.poly_marshal(a[0])[:-8])
+    with pytest.raises(lg.LattigpuError, match="moduli encoded"):
+        lg.ring.Poly(N, 2, 1).UnmarshalBinary(orc.poly_marshal(a[0]))

@@ -640,3 +640,17 @@ def test_bfv_keyswitch_semantics():
     rhs = negacyclic(cx_vals, sk_in, Qp)
     err = max(min((l - r) % Qp, (r - l) % Qp) for l, r in zip(lhs, rhs))
     assert err.bit_length() < 30, err.bit_length()
+
+
+def test_poly_wire_format():
+    """ring.Poly.MarshalBinary / UnmarshalBinary (ring_object.go:146-289): header bytes, big-endian words,
+    limb-major order, round trip, and the length check of UnmarshalBinary."""
+    N = 16
+    p = np.arange(3 * N, dtype=np.uint64).reshape(3, N) * np.uint64(0x0102030405060708)
+    data = orc.poly_marshal(p)
+    assert len(data) == 2 + 3 * N * 8 and data[0] == 4 and data[1] == 3
+    assert data[2 + 8:2 + 16] == int(p[0, 1]).to_bytes(8, "big")
+    assert data[2 + N * 8:2 + N * 8 + 8] == int(p[1, 0]).to_bytes(8, "big")
+    assert np.array_equal(orc.poly_unmarshal(data), p)
+    with pytest.raises(ValueError, match="invalid polynomial encoding"):
+        orc.poly_unmarshal(data[:-8])
