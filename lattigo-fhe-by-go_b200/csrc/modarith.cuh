@@ -200,16 +200,17 @@ LG_DEV void butterfly_inv_4q(u64& X, u64& Y, u64 w, u64 ws, u64 nq, u64 fourq) {
 // with wd = RD(floor(w*2^64/q)) * 2^-64 <= w/q (absolute deficit < 2^-52) and cw = RD(2^52 - 2^52*wd),
 //   qd = RD((2^52 + y) * wd + cw) = 2^52 + floor(y*wd - e),  0 <= e < 1      (one DFMA, round-down)
 // holds the quotient estimate Qh = floor(y*w/q) - {0..3} in its mantissa for any y < 2^52, so
-// T = w*y - Qh*q is in [0,4q).  The exponent bits are cancelled by the constant c0 = -((0x43300000*nq0) << 32)
-// folded into the first multiply-add, which leaves 2 wide + 4 narrow integer multiplies per product.
+// T = w*y - Qh*q is in [0,4q).  Qh = -1 (y*wd < e, e.g. y = 0) shows as the double just below 2^52, i.e.
+// mantissa all ones under exponent 0x432: subtracting 0x43300000 from the high word gives the two's complement
+// high word of Qh in both cases.  That leaves 2 wide + 4 narrow integer multiplies, one LOP3, one IADD and the
+// DFMA per product (13 instructions per butterfly with the two 64-bit adds).
 LG_DEV double shoup_cw(double wd) { return __fma_rd(-4503599627370496.0, wd, 4503599627370496.0); }
-LG_DEV u64 shoup_f64_c0(u64 nq) { return (u64)(0u - 0x43300000u * (u32)nq) << 32; }
-LG_DEV u64 shoup_f64(u64 w, double wd, double cw, u64 y, u64 nq, u64 c0) {
+LG_DEV u64 shoup_f64(u64 w, double wd, double cw, u64 y, u64 nq) {
     const u32 b0 = (u32)y, b1 = (u32)(y >> 32);
     const double qd = __fma_rd(__hiloint2double((int)(b1 | 0x43300000u), (int)b0), wd, cw);
-    const u32 h0 = (u32)__double2loint(qd), h1 = (u32)__double2hiint(qd);
+    const u32 h0 = (u32)__double2loint(qd), h1 = (u32)__double2hiint(qd) - 0x43300000u;
     const u32 w0 = (u32)w, w1 = (u32)(w >> 32), n0 = (u32)nq, n1 = (u32)(nq >> 32);
-    u64 t = mad_wide(w0, b0, c0);
+    u64 t = mul_wide(w0, b0);
     t = mad_wide(h0, n0, t);
     u32 th = (u32)(t >> 32);
     th = mad_lo32(w0, b1, th);
@@ -219,19 +220,20 @@ LG_DEV u64 shoup_f64(u64 w, double wd, double cw, u64 y, u64 nq, u64 c0) {
     return ((u64)th << 32) | (u32)t;
 }
 // forward, no conditional subtraction: inputs below 2^50, 16 stages add < 64q < 2^52 - 2^50
-LG_DEV void butterfly_fwd_f64(u64& X, u64& Y, u64 w, double wd, double cw, u64 nq, u64 fourq, u64 c0) {
-    const u64 t = shoup_f64(w, wd, cw, Y, nq, c0);
+LG_DEV void butterfly_fwd_f64(u64& X, u64& Y, u64 w, double wd, double cw, u64 nq, u64 fourq) {
+    const u64 t = shoup_f64(w, wd, cw, Y, nq);
     const u64 x = X;
     X = x + t;
     Y = x + fourq - t;
 }
-// Gentleman-Sande, values kept in [0,4q): the difference is below 8q < 2^52
-LG_DEV void butterfly_inv_f64(u64& X, u64& Y, u64 w, double wd, double cw, u64 nq, u64 fourq, u64 c0) {
+// Gentleman-Sande, values kept in [0,4q): the difference is below 8q < 2^52 (microbenchmark only: the
+// reduction-free integer butterfly is faster)
+LG_DEV void butterfly_inv_f64(u64& X, u64& Y, u64 w, double wd, double cw, u64 nq, u64 fourq) {
     u64 s = X + Y;
     const u64 d = X + fourq - Y;
     if (s >= fourq) s -= fourq;
     X = s;
-    Y = shoup_f64(w, wd, cw, d, nq, c0);
+    Y = shoup_f64(w, wd, cw, d, nq);
 }
 
 // InvButterfly, ring/ntt.go:43-50

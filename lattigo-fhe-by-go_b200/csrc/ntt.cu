@@ -45,7 +45,6 @@ struct TwConst {
     u64 q, qinv, twoq, fourq, nq;
     const u64* tw;   // literal: nttPsi / nttPsiInv (Montgomery).  fast: the plain-domain table
     const u64* tws;  // fast: Shoup constants (M_F64: the bits of the double table psi_wd)
-    u64 c0;          // M_F64: shoup_f64_c0(nq)
 };
 
 // 256-bit global access (sm_100: LDG.E.256 / STG.E.256); p must be 32-byte aligned
@@ -104,7 +103,7 @@ LG_DEV void fwd_stage(u64 (&x)[16], const TwConst& c, u32 twbase) {
             else if (MODE == M_FREE)
                 butterfly_fwd_free(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, c.fourq);
             else if (MODE == M_F64)
-                butterfly_fwd_f64(x[r], x[r + (1 << U)], w[g], wd, cw, c.nq, c.fourq, c.c0);
+                butterfly_fwd_f64(x[r], x[r + (1 << U)], w[g], wd, cw, c.nq, c.fourq);
             else
                 butterfly_fwd_8q(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, c.fourq);
         }
@@ -172,7 +171,7 @@ LG_DEV void fwd_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u6
             else if (MODE == M_FREE)
                 butterfly_fwd_free(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
             else if (MODE == M_F64)
-                butterfly_fwd_f64(x[r], x[r + (1 << U)], w, wd, cw, c.nq, c.fourq, c.c0);
+                butterfly_fwd_f64(x[r], x[r + (1 << U)], w, wd, cw, c.nq, c.fourq);
             else
                 butterfly_fwd_8q(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
         }
@@ -265,7 +264,6 @@ LG_DEV TwConst tw_const(const RingTables& T, const LimbConst& lc, int tl) {
     c.fourq = 4 * lc.q;
     c.nq = 0ull - lc.q;
     const size_t off = (size_t)tl * T.N;
-    c.c0 = shoup_f64_c0(c.nq);
     if (MODE == M_LITERAL) {
         c.tw = (FWD ? T.psi : T.psi_inv) + off;
         c.tws = nullptr;

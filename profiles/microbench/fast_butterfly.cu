@@ -43,8 +43,8 @@ LG_DEV void bfly(u64& X, u64& Y, u64 w, u64 ws, u64 q, u64 qinv, u64 twoq, u64 f
         butterfly_inv_4q(X, Y, w, ws, 0ull - q, fourq);
     } else {  // FP64-assisted quotient: ws carries the bits of wd, qinv the constant c0
         const double wd = __longlong_as_double((long long)ws);
-        if (KIND == 7) butterfly_fwd_f64(X, Y, w, wd, shoup_cw(wd), 0ull - q, fourq, qinv);
-        else butterfly_inv_f64(X, Y, w, wd, shoup_cw(wd), 0ull - q, fourq, qinv);
+        if (KIND == 7) butterfly_fwd_f64(X, Y, w, wd, shoup_cw(wd), 0ull - q, fourq);
+        else butterfly_inv_f64(X, Y, w, wd, shoup_cw(wd), 0ull - q, fourq);
     }
 }
 
@@ -58,7 +58,6 @@ __global__ void __launch_bounds__(256) loop(u64* a, const u64* __restrict__ tw, 
 #pragma unroll
     for (int g = 0; g < 8; ++g) { w[g] = tw[g + (threadIdx.x & 7)]; ws[g] = tw[64 + g + (threadIdx.x & 7)]; }
     if (KIND >= 7) {
-        qinv = shoup_f64_c0(0ull - q);
 #pragma unroll
         for (int g = 0; g < 8; ++g) ws[g] = (u64)__double_as_longlong(__ull2double_rz(ws[g]) * 5.421010862427522e-20);
 #pragma unroll
@@ -108,8 +107,8 @@ __global__ void check(const u64* xs, const u64* ys, const u64* wm, u64 q, u64 qi
         butterfly_fwd(X1, Y1, wmont, q, qinv, 2 * q);
     }
     if (KIND >= 7)
-        bfly<KIND>(X2, Y2, wplain, (u64)__double_as_longlong(__ull2double_rz(ws) * 5.421010862427522e-20), q,
-                   shoup_f64_c0(0ull - q), 2 * q, 4 * q);
+        bfly<KIND>(X2, Y2, wplain, (u64)__double_as_longlong(__ull2double_rz(ws) * 5.421010862427522e-20), q, qinv, 2 * q,
+                   4 * q);
     else
         bfly<KIND>(X2, Y2, wplain, ws, q, qinv, 2 * q, 4 * q);
     if (KIND == 7 && (X2 >= X0 + 4 * q || Y2 > X0 + 4 * q)) atomicAdd(bad, 1);

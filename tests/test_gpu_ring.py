@@ -428,3 +428,31 @@ def test_poly_wire_format(lg):
         q.UnmarshalBinary(orc.poly_marshal(a[0])[:-8])
     with pytest.raises(lg.LattigpuError, match="moduli encoded"):
         lg.ring.Poly(N, 2, 1).UnmarshalBinary(orc.poly_marshal(a[0]))
+
+
+@pytest.mark.parametrize("logN", [12, 14, 16])
+def test_ntt_zero_and_sparse_inputs(lg, logN):
+    """Zero and sparse polynomials through every butterfly flavour (45-bit: FP64 quotient, where y = 0 makes the
+    quotient estimate -1; 55-bit: Shoup; 60-bit: [0,8q) / [0,4q)), forward and inverse, against the oracle."""
+    N = 1 << logN
+    moduli = orc.generate_ntt_primes(45, logN, 2) + orc.generate_ntt_primes(55, logN, 1) + orc.generate_ntt_primes(60, logN, 1)
+    octx = orc.Context(N, moduli)
+    ctx = lg.ring.NewContextWithParams(N, moduli)
+    rng = np.random.default_rng(83 + logN)
+    a = np.zeros((3, len(moduli), N), dtype=np.uint64)
+    pos = rng.integers(0, N, size=37)
+    for i, q in enumerate(moduli):
+        a[1, i, pos] = rng.integers(0, q, size=37, dtype=np.uint64)  # sparse
+        a[2, i] = rng.integers(0, q, size=N, dtype=np.uint64)
+        a[2, i, ::2] = 0  # every other coefficient zero
+        a[2, i, 1] = q - 1
+    p = lg.ring.Poly.from_numpy(a)
+    out = lg.ring.Poly(N, len(moduli), 3)
+    ctx.NTT(p, out)
+    got = out.numpy(squeeze=False)
+    for b in range(3):
+        assert np.array_equal(got[b], octx.ntt(np.ascontiguousarray(a[b]))), ("fwd", b)
+    ctx.InvNTT(p, out)
+    got = out.numpy(squeeze=False)
+    for b in range(3):
+        assert np.array_equal(got[b], octx.invntt(np.ascontiguousarray(a[b]))), ("inv", b)
