@@ -304,7 +304,7 @@ def run_gpu(args):
     # INT-side ceiling: register-resident butterfly rates measured on this GPU (profiles/microbench/
     # fast_butterfly.cu, profiles/r01_butterfly_peaks.txt): FP64-quotient butterfly for moduli below 3*2^44,
     # the 16-instruction Shoup butterfly below 2^56, the [0,8q) butterfly above
-    peak_bf = {"f64": 1.488e12, "free": 1.151e12, "lazy": 0.950e12}
+    peak_bf = {"f64": 1.584e12, "free": 1.151e12, "lazy": 0.950e12}
     mix = {"f64": sum(1 for q in Q if q < (3 << 44)), "free": sum(1 for q in Q if (3 << 44) <= q < (1 << 56)),
            "lazy": sum(1 for q in Q if q >= (1 << 56))}
     bf_per_limb = (N // 2) * p["LogN"]
