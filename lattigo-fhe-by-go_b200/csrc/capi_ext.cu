@@ -1,6 +1,7 @@
 // capi_ext.cu -- C-ABI host layer, part 2: FastBasisExtender, Decomposer and the
 // CKKS evaluator key-switch path.  Host-side mirror of
 // ring/ring_basis_extension.go and ckks/evaluator.go:933-1591 (hot ops only).
+#include <stdlib.h>
 #include <string.h>
 
 #include "capi_internal.hpp"
@@ -403,7 +404,10 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
         // cadence (BRedAdd when (i & 7) == cadence and after the last digit) only bounds its lazy sums and
         // ends canonical as well, so the words are the same.
         const size_t per_entry = (size_t)beta * nd * N;                 // scratch words per batch entry
-        const size_t budget = (size_t)6 << 27;                          // 6 GiB of u64 words
+        static const size_t budget = [] {                               // 6 GiB of u64 words unless overridden (tests)
+            const char* e = getenv("LATTIGPU_KS_SCRATCH_WORDS");
+            return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)6 << 27);
+        }();
         int chunk = (int)(budget / per_entry);
         if (chunk < 1) chunk = 1;
         if (chunk > batch) chunk = batch;

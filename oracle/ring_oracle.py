@@ -549,6 +549,16 @@ class DckksProtocols:
         share = S.Q.op3("add", share, np.ascontiguousarray(tmp[:nl]), nl=nl)
         return S.ext.moddown_splited_ntt_pq(level, share, np.ascontiguousarray(tmp[nQ:]))
 
+    def bfv_cks_gen_share(self, sk_in, sk_out, ct1, e):  # dbfv/keyswitching.go:73-106 (coefficient-domain ciphertext)
+        S = self.S
+        nQ = S.levels
+        delta = S.Q.op3("sub", np.ascontiguousarray(sk_in[:nQ]), np.ascontiguousarray(sk_out[:nQ]))
+        share = S.Q.op3("mulcoeffs_montgomery", S.Q.ntt(np.ascontiguousarray(ct1)), delta)
+        share = S.Q.invntt(S.Q.mul_scalar(share, [S.Pbig % q for q in S.Qm]))
+        tmp = signed_residues(self.mods, e)
+        share = S.Q.op3("add", share, np.ascontiguousarray(tmp[:nQ]))
+        return S.ext.moddown_splited_pq(nQ - 1, share, np.ascontiguousarray(tmp[nQ:]))
+
     def rtg_gen_share(self, sk, gal_el, crp, errors):  # rotkey_gen.go:95-141
         S = self.S
         idx = permute_ntt_index(gal_el, 1, S.N)

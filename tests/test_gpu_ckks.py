@@ -237,3 +237,46 @@ def test_error_paths(lg):
     short = lg.ckks.SwitchingKey(s.evk(rng)[:1])
     with pytest.raises(lg.LattigpuError, match="digits"):
         s.ev.MulRelin(1, a, a, short, a)
+
+
+def test_keyswitch_batch_chunking():
+    """The digit scratch of a key switch is bounded: large batches are processed in chunks.  Forced here with a
+    tiny budget (LATTIGPU_KS_SCRATCH_WORDS, read once per process -> subprocess) so that a batch of 5 takes three
+    chunks; results must equal the unchunked ones bit for bit."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, os
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "lattigo-fhe-by-go_b200"))
+import numpy as np
+import lattigpu
+from lattigpu import ckks, ring
+ring.set_device(0)
+p = dict(LogN=12, LogQi=[50, 40, 40, 40, 40, 40, 40], LogPi=[50, 50, 50])
+N = 1 << p["LogN"]; Q, P = ckks.GenModuli(p); nQ, nP = len(Q), len(P); beta = -(-nQ // nP)
+rng = np.random.default_rng(3)
+evk = np.ascontiguousarray(np.stack([rng.integers(0, q, size=(beta, 2, N), dtype=np.uint64) for q in Q + P], axis=2))
+B = 5
+a = np.ascontiguousarray(np.stack([rng.integers(0, q, size=(B, 2, N), dtype=np.uint64) for q in Q], axis=2))
+b = np.ascontiguousarray(np.stack([rng.integers(0, q, size=(B, 2, N), dtype=np.uint64) for q in Q], axis=2))
+ev = ckks.NewEvaluator(ring.NewContextWithParams(N, Q), ring.NewContextWithParams(N, P))
+key = ckks.SwitchingKey(evk)
+F = lambda x: (ring.Poly.from_numpy(np.ascontiguousarray(x[:, 0])), ring.Poly.from_numpy(np.ascontiguousarray(x[:, 1])))
+out = (ring.Poly(N, nQ, B), ring.Poly(N, nQ, B))
+ev.MulRelin(nQ - 1, F(a), F(b), key, out)
+np.save(sys.argv[1], np.stack([out[0].numpy(squeeze=False), out[1].numpy(squeeze=False)]))
+""" % (root, root)
+    import tempfile
+
+    outs = []
+    for budget in (None, str(2 * 3 * 10 * 4096)):  # second run: room for two batch entries per chunk
+        env = dict(os.environ)
+        if budget:
+            env["LATTIGPU_KS_SCRATCH_WORDS"] = budget
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
+            outs.append(np.load(f.name))
+    assert np.array_equal(outs[0], outs[1])

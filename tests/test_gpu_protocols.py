@@ -222,3 +222,52 @@ def test_dckks_cks_rtg_rkg(lg):
         cks.KeySwitch(level, comb, (F(ct[0]), F(ct[1])), out)
         assert np.array_equal(out[0].numpy(nl=nl), S.Q.op3("add", np.ascontiguousarray(ct[0][:nl]), combw, nl=nl))
         assert np.array_equal(out[1].numpy(nl=nl), ct[1][:nl])
+
+
+def test_dbfv_cks_rtg_rkg(lg):
+    """dbfv CKS (dbfv/keyswitching.go:66-122) with 3 parties against the oracle; the BFV RTG / RKG mirrors are the
+    dckks ring sequences (checked here on the BFV moduli for one share each)."""
+    p = lg.bfv.DefaultParams[lg.bfv.PN13QP218]
+    Q, P, _ = lg.bfv.GenModuli(p)
+    N = 1 << p["LogN"]
+    QP = Q + P
+    nQ = len(Q)
+    rng = np.random.default_rng(69)
+    S = orc.CkksScheme(Q, P, N)
+    D = orc.DckksProtocols(S)
+    cQ, cP, cK = (lg.ring.NewContextWithParams(N, m) for m in (Q, P, QP))
+    F = lg.ring.Poly.from_numpy
+    from lattigpu.ckks_scheme import signed_to_poly
+
+    tern = lambda: rng.integers(-1, 2, size=N)
+    gauss = lambda: np.rint(rng.normal(0, 3.2, size=N)).astype(np.int64)
+    sks = [S.gen_secret_key(tern()) for _ in range(PARTIES)]
+    sks_out = [S.gen_secret_key(tern()) for _ in range(PARTIES)]
+    ct = [uni(rng, Q, N), uni(rng, Q, N)]
+    cks = lg.dbfv.CKSProtocol(cQ, cP, cK)
+    comb = combw = None
+    for a, b in zip(sks, sks_out):
+        e = np.rint(rng.normal(0, 40.0, size=N)).astype(np.int64)
+        share = cks.AllocateShare()
+        cks.GenShare(F(np.ascontiguousarray(a[:nQ])), F(np.ascontiguousarray(b[:nQ])), F(ct[1]), share, signed_to_poly(cK, e))
+        w = D.bfv_cks_gen_share(a, b, ct[1], e)
+        assert np.array_equal(share.numpy(), w)
+        if comb is None:
+            comb, combw = share, w
+        else:
+            cks.AggregateShares(comb, share, comb)
+            combw = S.Q.op3("add", combw, w)
+    out = (cQ.NewPoly(), cQ.NewPoly())
+    cks.KeySwitch(comb, (F(ct[0]), F(ct[1])), out)
+    assert np.array_equal(out[0].numpy(), S.Q.op3("add", ct[0], combw)) and np.array_equal(out[1].numpy(), ct[1])
+
+    crp = [uni(rng, QP, N) for _ in range(S.beta)]
+    dcrp = [F(c) for c in crp]
+    e = [gauss() for _ in range(S.beta)]
+    rtg = lg.dbfv.RTGProtocol(cQ, cP, cK)
+    got = rtg.genShare(F(sks[0]), pow(5, 2, 2 * N), dcrp, [signed_to_poly(cK, x) for x in e])
+    assert all(np.array_equal(g.numpy(), w) for g, w in zip(got, D.rtg_gen_share(sks[0], pow(5, 2, 2 * N), crp, e)))
+    rkg = lg.dbfv.RKGProtocol(cQ, cP, cK)
+    u = S.gen_secret_key(tern())
+    got = rkg.GenShareRoundOne(F(u), F(sks[0]), dcrp, [signed_to_poly(cK, x) for x in e])
+    assert all(np.array_equal(g.numpy(), w) for g, w in zip(got, D.rkg_round1(u, sks[0], crp, e)))

@@ -506,6 +506,47 @@ def test_dckks_cks_rtg_rkg_semantics():
     assert err < (1 << 14), err
 
 
+def test_dbfv_cks_semantics():
+    """dbfv CKS (dbfv/keyswitching.go:66-122) on a coefficient-domain ciphertext: c0 + sum(shares) + c1*s_out
+    equals c0 + c1*s_in up to the smudging noise."""
+    N, parties = 32, 3
+    Q, P, _ = _bfv_small(N)
+    rng = random.Random(321)
+    S = orc.CkksScheme(Q, P, N)  # contexts Q, P, QP + extender; nothing CKKS-specific is used
+    D = orc.DckksProtocols(S)
+    Qp = prod(Q)
+    tern = lambda: [rng.choice([-1, 0, 1]) for _ in range(N)]
+    sin_c, sout_c = [tern() for _ in range(parties)], [tern() for _ in range(parties)]
+    sks_in = [S.gen_secret_key(c) for c in sin_c]
+    sks_out = [S.gen_secret_key(c) for c in sout_c]
+    c0v = [rng.randrange(Qp) for _ in range(N)]
+    c1v = [rng.randrange(Qp) for _ in range(N)]
+    c1 = crt_poly(c1v, Q)
+    comb = None
+    for a, b in zip(sks_in, sks_out):
+        sh = D.bfv_cks_gen_share(a, b, c1, [rng.randrange(-40, 41) for _ in range(N)])
+        comb = sh if comb is None else S.Q.op3("add", comb, sh)
+    combv = crt_reconstruct(comb, Q)
+
+    def negacyclic(a, b):
+        out = [0] * N
+        for x in range(N):
+            for y in range(N):
+                k = x + y
+                if k >= N:
+                    out[k - N] = (out[k - N] - a[x] * b[y]) % Qp
+                else:
+                    out[k] = (out[k] + a[x] * b[y]) % Qp
+        return out
+
+    s_in = [sum(c[i] for c in sin_c) for i in range(N)]
+    s_out = [sum(c[i] for c in sout_c) for i in range(N)]
+    lhs = [(u + v + w) % Qp for u, v, w in zip(c0v, combv, negacyclic(c1v, s_out))]
+    rhs = [(u + w) % Qp for u, w in zip(c0v, negacyclic(c1v, s_in))]
+    err = max(min((l - r) % Qp, (r - l) % Qp) for l, r in zip(lhs, rhs))
+    assert err < (1 << 12), err
+
+
 def test_ckks_const_ops_semantics():
     """Constant ops (ckks/evaluator.go:373-833) in the coefficient domain: AddConst(a+bi) adds round(a*scale)
     to coefficient 0 and round(b*scale) to coefficient N/2; MultByConst multiplies the polynomial by
