@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="ops in the cpu_baseline sample (0 = one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rotate", action="store_true")
+    ap.add_argument("--hoisted-rotations", type=int, default=8, help="rotations per RotateHoisted call")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the batch is cut into for the pipelined e2e path")
     ap.add_argument("--params", type=int, default=PARAMS_ID, help="index into ckks.DefaultParams (default PN16QP1761)")
     return ap.parse_args()
@@ -281,6 +283,28 @@ def run_gpu(args):
     ntt_fwd_rate = world * nlimbs_launch / (fwd_us * 1e-6)
     ntt_inv_rate = world * nlimbs_launch / (inv_us * 1e-6)
 
+    # ---- Rotate (BASELINE config 4 names MulRelin + Rescale + Rotate): RotateColumns with a direct key
+    # (ckks/evaluator.go:1201-1248) and RotateHoisted over `nrot` rotations (:1252-1392), same batch, resident
+    rotate = None
+    if not args.no_rotate:
+        GaloisGen = 5
+        nrot = args.hoisted_rotations
+        idxs = [gring.PermuteNTTIndex(GaloisGen, k + 1, N) for k in range(nrot)]
+        rk = gckks.SwitchingKey(N=N, device_ptr=evk_t.data_ptr(), beta=beta, nQP=nQ + nP, keep=evk_t)  # any uniform key
+
+        def rot():
+            ev.permuteNTT(level, ct_a, idxs[0], rk, ct_o, stream=sp)
+
+        def hoisted():
+            ev.RotateHoisted(level, ct_a, [(ix, rk) for ix in idxs], [ct_o] * nrot, stream=sp)  # stream-ordered: one output buffer
+
+        rsteps = max(3, min(args.steps, 10))
+        rot_ms, _ = timed(rot, rsteps, 3)
+        hst_ms, _ = timed(hoisted, rsteps, 3)
+        rotate = {"rotate_columns_ops_per_s": world * B * rsteps * 1e3 / rot_ms,
+                  "rotate_hoisted_rotations_per_s": world * B * nrot * rsteps * 1e3 / hst_ms,
+                  "hoisted_rotations_per_call": nrot, "batch_per_gpu": B, "level": level}
+
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -424,7 +448,7 @@ def run_gpu(args):
                        "parallelism": "batch-sharded x%d, no collective" % world, "seed": SEED},
             "ntt": {"fwd_limb_ntt_per_s": ntt_fwd_rate, "inv_limb_ntt_per_s": ntt_inv_rate, "N": N,
                     "limbs_per_launch": nlimbs_launch, "fwd_us_per_launch": fwd_us, "inv_us_per_launch": inv_us},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "rotate": rotate, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

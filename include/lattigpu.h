@@ -263,6 +263,31 @@ int lg_bfv_switch_keys(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, con
 int lg_bfv_permute(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, uint64_t gen, const lg_swk* k, lg_poly* out0,
                    lg_poly* out1, lg_stream_t s);
 
+/* ---- common reference polynomials: utils/prng.go, ring/prng.go ------------------------------------- */
+/* utils.PRNG (utils/prng.go:11-72): BLAKE2b-512 hash chain, optional key of at most 64 bytes (NewPRNG :22-28).
+ * Seed :38-43 resets the state (keeping the key) and the clock; Clock :51-56 returns the 64-byte digest of the
+ * current state and absorbs it; SetClock :61-72 clocks forward, LG_ERR_ARG when n is behind the clock.
+ * Host code: the chain is sequential by construction (see csrc/crp.cu). */
+typedef struct lg_prng lg_prng;
+typedef struct lg_crp lg_crp;
+int lg_prng_create(const uint8_t* key, size_t keylen, lg_prng** out);
+int lg_prng_destroy(lg_prng* p);
+int lg_prng_seed(lg_prng* p, const uint8_t* seed, size_t len);
+uint64_t lg_prng_get_clock(const lg_prng* p);
+int lg_prng_clock(lg_prng* p, uint8_t out[64]);
+int lg_prng_set_clock(lg_prng* p, uint64_t n);
+/* ring.CRPGenerator (ring/prng.go:11-69): NewCRPGenerator :21-37, Seed :45-47, GetClock :40-42, SetClock :57-61.
+ * The ring handle must outlive the generator. */
+int lg_crp_create(const uint8_t* key, size_t keylen, const lg_ring* ring, lg_crp** out);
+int lg_crp_destroy(lg_crp* g);
+int lg_crp_seed(lg_crp* g, const uint8_t* seed, size_t len);
+uint64_t lg_crp_get_clock(const lg_crp* g);
+int lg_crp_set_clock(lg_crp* g, uint64_t n);
+/* Clock :71-103: the next uniform polynomial of the ring (masked big-endian words, rejection sampling, coefficient-major
+ * consumption of the stream) into entry `batch_index` of a device handle / into host memory [nlimbs][N] */
+int lg_crp_clock(lg_crp* g, lg_poly* out, int batch_index, lg_stream_t stream);
+int lg_crp_clock_host(lg_crp* g, uint64_t* host);
+
 /* ---- multi-GPU (one process per GPU) ------------------------------ */
 /* The reference is single-process; these entry points add the two exchange steps the path has when it is
  * spread over the GPUs of a node.  NCCL is resolved at run time (dlopen "libnccl.so.2"). */

@@ -179,6 +179,19 @@ SIGNATURES = {
     "lg_ckks_switch_keys_in_place_sharded": (ci, [vp, vp, ci, _P, vp, _P, _P, vp]),
     "lg_ckks_mul_relin_sharded": (ci, [vp, vp, ci, _P, _P, _P, _P, vp, _P, _P, vp]),
     "lg_ckks_rescale_sharded": (ci, [vp, vp, ci, _P, _P, vp]),
+    "lg_prng_create": (ci, [C.c_char_p, C.c_size_t, C.POINTER(vp)]),
+    "lg_prng_destroy": (ci, [vp]),
+    "lg_prng_seed": (ci, [vp, C.c_char_p, C.c_size_t]),
+    "lg_prng_get_clock": (u64, [vp]),
+    "lg_prng_clock": (ci, [vp, C.c_char_p]),
+    "lg_prng_set_clock": (ci, [vp, u64]),
+    "lg_crp_create": (ci, [C.c_char_p, C.c_size_t, _R, C.POINTER(vp)]),
+    "lg_crp_destroy": (ci, [vp]),
+    "lg_crp_seed": (ci, [vp, C.c_char_p, C.c_size_t]),
+    "lg_crp_get_clock": (u64, [vp]),
+    "lg_crp_set_clock": (ci, [vp, u64]),
+    "lg_crp_clock": (ci, [vp, _P, ci, vp]),
+    "lg_crp_clock_host": (ci, [vp, p64]),
 }
 
 

@@ -487,3 +487,84 @@ class Decomposer:
 
 def NewDecomposer(N, Q, P):
     return Decomposer(N, Q, P)
+
+
+class PRNG:
+    """utils.PRNG (utils/prng.go:11-72): keyed BLAKE2b-512 hash chain; host code in the library"""
+
+    def __init__(self, key=None):
+        key = bytes(key or b"")
+        h = vp()
+        check(lib().lg_prng_create(key, len(key), C.byref(h)))
+        self.h = h
+        self._seed = b""
+
+    def __del__(self):
+        try:
+            lib().lg_prng_destroy(self.h)
+        except Exception:
+            pass
+
+    def GetClock(self):
+        return int(lib().lg_prng_get_clock(self.h))
+
+    def Seed(self, seed):
+        self._seed = bytes(seed)
+        check(lib().lg_prng_seed(self.h, self._seed, len(self._seed)))
+
+    def GetSeed(self):
+        return self._seed
+
+    def Clock(self):
+        out = C.create_string_buffer(64)
+        check(lib().lg_prng_clock(self.h, out))
+        return out.raw
+
+    def SetClock(self, n):
+        check(lib().lg_prng_set_clock(self.h, n))
+
+
+def NewPRNG(key=None):
+    return PRNG(key)
+
+
+class CRPGenerator:
+    """ring.CRPGenerator (ring/prng.go:11-103): deterministic uniform polynomials of `context` from the PRNG"""
+
+    def __init__(self, key, context):
+        key = bytes(key or b"")
+        h = vp()
+        check(lib().lg_crp_create(key, len(key), context.h, C.byref(h)))
+        self.h, self.context = h, context
+        self._seed = b""
+
+    def __del__(self):
+        try:
+            lib().lg_crp_destroy(self.h)
+        except Exception:
+            pass
+
+    def GetClock(self):
+        return int(lib().lg_crp_get_clock(self.h))
+
+    def Seed(self, seed):
+        self._seed = bytes(seed)
+        check(lib().lg_crp_seed(self.h, self._seed, len(self._seed)))
+
+    def GetSeed(self):
+        return self._seed
+
+    def SetClock(self, n):
+        check(lib().lg_crp_set_clock(self.h, n))
+
+    def Clock(self, crp, batch_index=0, stream=None):
+        check(lib().lg_crp_clock(self.h, crp.h, batch_index, _s(stream)))
+
+    def ClockNew(self):
+        crp = self.context.NewPoly()
+        self.Clock(crp)
+        return crp
+
+
+def NewCRPGenerator(key, context):
+    return CRPGenerator(key, context)
