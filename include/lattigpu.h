@@ -263,6 +263,27 @@ int lg_bfv_switch_keys(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, con
 int lg_bfv_permute(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, uint64_t gen, const lg_swk* k, lg_poly* out0,
                    lg_poly* out1, lg_stream_t s);
 
+/* ---- t/Q scaling and the BFV plaintext lift: ring/ring_scaling.go:166-300, ring/float128.go, bfv/encoder.go ---- */
+/* ring.SimpleScaler: NewSimpleScaler :188-262 (w_i, t_i from "Float128" double-double divisions, generated by the
+ * same sequence of IEEE binary64 operations as float128.go), Scale :271-300: p2[j][x] = round(t/Q * p1[.][x]) mod t
+ * for every limb j of p2; p2 may be p1.  The ring handle must outlive the scaler. */
+typedef struct lg_scaler lg_scaler;
+int lg_scaler_create(uint64_t t, const lg_ring* ring, lg_scaler** out);
+/* the same parameters for a bare modulus list (host only, no device needed): wi[nl], ti[nl][2], BRed / MRed constants of t */
+int lg_scaler_params_host(uint64_t t, const uint64_t* moduli, int nl, uint64_t* wi, double* ti, uint64_t* add_param,
+                          uint64_t* mul_param);
+int lg_scaler_destroy(lg_scaler* s);
+int lg_scaler_get_params(const lg_scaler* s, uint64_t* wi, double* ti /* [nlimbs][2] */);
+int lg_scaler_scale(const lg_scaler* s, const lg_poly* p1, lg_poly* p2, lg_stream_t stream);
+/* GenLiftParams bfv/utils.go:9-23 + encodePlaintext bfv/encoder.go:121-136 (after the InvNTT over contextT):
+ * pt[i][x] = MRed(m[0][x], deltaMont[i]); m may be a view of limb 0 of pt, as in the reference's plaintext. */
+typedef struct lg_bfv_lift lg_bfv_lift;
+int lg_bfv_lift_create(const lg_ring* ringQ, uint64_t t, lg_bfv_lift** out);
+int lg_bfv_lift_params_host(const uint64_t* moduli, int nl, uint64_t t, uint64_t* delta_mont); /* host only */
+int lg_bfv_lift_destroy(lg_bfv_lift* l);
+int lg_bfv_lift_get_params(const lg_bfv_lift* l, uint64_t* delta_mont);
+int lg_bfv_lift_apply(const lg_bfv_lift* l, const lg_poly* m, lg_poly* pt, lg_stream_t stream);
+
 /* ---- common reference polynomials: utils/prng.go, ring/prng.go ------------------------------------- */
 /* utils.PRNG (utils/prng.go:11-72): BLAKE2b-512 hash chain, optional key of at most 64 bytes (NewPRNG :22-28).
  * Seed :38-43 resets the state (keeping the key) and the clock; Clock :51-56 returns the 64-byte digest of the

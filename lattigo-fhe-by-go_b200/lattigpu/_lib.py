@@ -179,6 +179,16 @@ SIGNATURES = {
     "lg_ckks_switch_keys_in_place_sharded": (ci, [vp, vp, ci, _P, vp, _P, _P, vp]),
     "lg_ckks_mul_relin_sharded": (ci, [vp, vp, ci, _P, _P, _P, _P, vp, _P, _P, vp]),
     "lg_ckks_rescale_sharded": (ci, [vp, vp, ci, _P, _P, vp]),
+    "lg_scaler_create": (ci, [u64, _R, C.POINTER(vp)]),
+    "lg_scaler_params_host": (ci, [u64, p64, ci, p64, C.POINTER(C.c_double), p64, p64]),
+    "lg_scaler_destroy": (ci, [vp]),
+    "lg_scaler_get_params": (ci, [vp, p64, C.POINTER(C.c_double)]),
+    "lg_scaler_scale": (ci, [vp, _P, _P, vp]),
+    "lg_bfv_lift_create": (ci, [_R, u64, C.POINTER(vp)]),
+    "lg_bfv_lift_params_host": (ci, [p64, ci, u64, p64]),
+    "lg_bfv_lift_destroy": (ci, [vp]),
+    "lg_bfv_lift_get_params": (ci, [vp, p64]),
+    "lg_bfv_lift_apply": (ci, [vp, _P, _P, vp]),
     "lg_prng_create": (ci, [C.c_char_p, C.c_size_t, C.POINTER(vp)]),
     "lg_prng_destroy": (ci, [vp]),
     "lg_prng_seed": (ci, [vp, C.c_char_p, C.c_size_t]),

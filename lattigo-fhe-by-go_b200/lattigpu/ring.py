@@ -568,3 +568,42 @@ class CRPGenerator:
 
 def NewCRPGenerator(key, context):
     return CRPGenerator(key, context)
+
+
+class SimpleScaler:
+    """ring.SimpleScaler (ring/ring_scaling.go:166-300): Scale(p1, p2) writes round(t/Q * p1) mod t to every limb of
+    p2; the Float128 accumulation of ring/float128.go runs on the device, one coefficient per thread."""
+
+    def __init__(self, t, context):
+        h = vp()
+        check(lib().lg_scaler_create(t, context.h, C.byref(h)))
+        self.h, self.context, self.t = h, context, int(t)
+
+    def __del__(self):
+        try:
+            lib().lg_scaler_destroy(self.h)
+        except Exception:
+            pass
+
+    def params(self):
+        wi = np.zeros(self.context.nl, np.uint64)
+        ti = np.zeros((self.context.nl, 2), np.float64)
+        check(lib().lg_scaler_get_params(self.h, _ptr(wi), ti.ctypes.data_as(C.POINTER(C.c_double))))
+        return wi, ti
+
+    def Scale(self, p1, p2, stream=None):
+        check(lib().lg_scaler_scale(self.h, p1.h, p2.h, _s(stream)))
+
+
+def NewSimpleScaler(t, context):
+    return SimpleScaler(t, context)
+
+
+def SimpleScalerParams(t, moduli):
+    """NewSimpleScaler's tables for a bare modulus list, computed on the host (no device needed)"""
+    q = _arr(list(moduli))
+    wi = np.zeros(len(q), np.uint64)
+    ti = np.zeros((len(q), 2), np.float64)
+    a, m = C.c_uint64(), C.c_uint64()
+    check(lib().lg_scaler_params_host(t, _ptr(q), len(q), _ptr(wi), ti.ctypes.data_as(C.POINTER(C.c_double)), C.byref(a), C.byref(m)))
+    return wi, ti, int(a.value), int(m.value)

@@ -1580,3 +1580,190 @@ API void orc_bfv_permute(orc_bfv_eval *e, const u64 *ct, u64 gen, const u64 *evk
     memcpy(out + szQ, p1, sizeof(u64) * szQ);
     free(el); free(p0); free(p1);
 }
+
+/* ---------------------------------------------------------------------- */
+/* ring/float128.go + SimpleScaler, ring/ring_scaling.go:166-300           */
+/* ---------------------------------------------------------------------- */
+/* Double-double arithmetic exactly as ring/float128.go writes it: every   */
+/* operation is one IEEE binary64 RN operation (the file is built with     */
+/* -ffp-contract=off; Go's amd64 back end at its default GOAMD64=v1 level  */
+/* does not fuse multiply-adds either).                                    */
+
+typedef struct { double v[2]; } f128;
+
+/* Go's uint64(float64) on amd64: CVTTSD2SQ below 2^63 (negative inputs wrap as two's complement), the upper half
+ * handled by converting f - 2^63 and flipping the top bit.  CVTTSD2SQ returns 0x8000000000000000 out of range; that
+ * is spelled out so that out-of-contract inputs do not depend on C's undefined conversion. */
+static inline int64_t x86_cvttsd2sq(double f) {
+    return (f >= -9223372036854775808.0 && f < 9223372036854775808.0) ? (int64_t)f : (int64_t)0x8000000000000000ull;
+}
+static inline u64 go_f64_to_u64(double f) {
+    if (f < 9223372036854775808.0) return (u64)x86_cvttsd2sq(f);
+    return (u64)x86_cvttsd2sq(f - 9223372036854775808.0) ^ 0x8000000000000000ull;
+}
+/* math.Round: half away from zero */
+static inline double go_round(double x) {
+    if (!(x > -4503599627370496.0 && x < 4503599627370496.0)) return x; /* already integral (or NaN) */
+    double t = (double)(int64_t)x;
+    double d = x - t;
+    if (d >= 0.5) t += 1.0;
+    else if (d <= -0.5) t -= 1.0;
+    return t;
+}
+static inline f128 f128_set_u53(u64 i) { f128 r = {{(double)i, 0.0}}; return r; }                     /* float128.go:33-37 */
+static inline f128 f128_set_u64(u64 i) { f128 r = {{(double)(i >> 12), (double)(i & 0xfff) / 4096.0}}; return r; } /* :44-48 */
+static inline u64 f128_to_u53(f128 f) { return go_f64_to_u64(f.v[0]); }                                /* :72-74 */
+static inline u64 f128_to_u64(f128 f) {                                                                /* :80-82 */
+    double a = f.v[0] * 4096.0;
+    u64 ai = go_f64_to_u64(a);
+    return ai + go_f64_to_u64(go_round((a - (double)ai) + f.v[1] * 4096.0));
+}
+static inline void two_sum(double a, double b, double *s, double *e) {   /* :85-90 */
+    *s = a + b;
+    double bb = *s - a;
+    *e = (a - (*s - bb)) + (b - bb);
+}
+static inline void quick_two_sum(double a, double b, double *s, double *e) { /* :93-97 */
+    *s = a + b;
+    *e = b - (*s - a);
+}
+static inline void two_diff(double a, double b, double *s, double *e) {  /* :111-116 */
+    *s = a - b;
+    double bb = *s - a;
+    *e = (a - (*s - bb)) - (b + bb);
+}
+static inline f128 f128_add(f128 a, f128 b) {                            /* :100-108 */
+    double s1, s2, t1, t2;
+    two_sum(a.v[0], b.v[0], &s1, &s2);
+    two_sum(a.v[1], b.v[1], &t1, &t2);
+    s2 += t1;
+    quick_two_sum(s1, s2, &s1, &s2);
+    s2 += t2;
+    f128 f;
+    quick_two_sum(s1, s2, &f.v[0], &f.v[1]);
+    return f;
+}
+static inline void f_split(double a, double *hi, double *lo) {           /* :132-137 */
+    double temp = 134217729.0 * a;
+    *hi = temp - (temp - a);
+    *lo = a - *hi;
+}
+static inline void two_prod(double a, double b, double *p, double *e) {  /* :140-146 */
+    *p = a * b;
+    double ahi, alo, bhi, blo;
+    f_split(a, &ahi, &alo);
+    f_split(b, &bhi, &blo);
+    *e = ((ahi * bhi - *p) + ahi * blo + alo * bhi) + alo * blo;
+}
+static inline f128 f128_mul(f128 a, f128 b) {                            /* :149-154 */
+    double p1, p2;
+    two_prod(a.v[0], b.v[0], &p1, &p2);
+    p2 += a.v[0] * b.v[1] + a.v[1] * b.v[0];
+    f128 f;
+    quick_two_sum(p1, p2, &f.v[0], &f.v[1]);
+    return f;
+}
+static inline f128 f128_div(f128 a, f128 b) {                            /* :157-217 (the live statements) */
+    double q1, p1, p2, p3, p4, v1, v2, r, t0, t1;
+    q1 = a.v[0] / b.v[0];
+    two_prod(q1, b.v[0], &p1, &p2);
+    p2 += q1 * b.v[1];
+    t0 = p1 + p2;
+    t1 = p2 - (t0 - p1);
+    two_diff(a.v[0], t0, &p3, &p4);
+    two_diff(a.v[1], t1, &v1, &v2);
+    p4 += v1;
+    quick_two_sum(p3, p4, &p3, &p4);
+    p4 += v2;
+    r = (p3 + p4) / b.v[0];
+    f128 f;
+    f.v[0] = q1 + r;
+    f.v[1] = r - (f.v[0] - q1);
+    return f;
+}
+
+/* exported one-op probes so the tests can compare the double-double ops against an independent restatement */
+API void orc_f128_op(int op, const double a[2], const double b[2], double out[2]) {
+    f128 x = {{a[0], a[1]}}, y = {{b[0], b[1]}}, r;
+    r = op == 0 ? f128_add(x, y) : op == 1 ? f128_mul(x, y) : f128_div(x, y);
+    out[0] = r.v[0];
+    out[1] = r.v[1];
+}
+API u64 orc_f128_to_u64(const double a[2]) { f128 x = {{a[0], a[1]}}; return f128_to_u64(x); }
+
+typedef struct {
+    int nl;
+    u64 N, t;
+    int pow2;
+    u64 add_param, mul_param; /* reducealgoAddParam / reducealgoMulParam (:183-184) */
+    u64 *q, *wi;
+    double *ti; /* [nl][2] */
+} orc_scaler;
+
+/* NewSimpleScaler, ring_scaling.go:188-262 */
+API orc_scaler *orc_scaler_new(u64 t, const orc_ctx *c) {
+    orc_scaler *s = (orc_scaler *)calloc(1, sizeof(orc_scaler));
+    s->nl = c->nl; s->N = c->N; s->t = t;
+    s->q = (u64 *)malloc(sizeof(u64) * c->nl);
+    s->wi = (u64 *)malloc(sizeof(u64) * c->nl);
+    s->ti = (double *)malloc(sizeof(double) * 2 * c->nl);
+    s->pow2 = (t & (t - 1)) == 0 && t != 0;
+    u64 bred_t[2] = {0, 0};
+    if (s->pow2) {
+        s->add_param = t - 1; s->mul_param = t - 1;            /* :203-204 */
+    } else {
+        orc_bred_params(t, bred_t);
+        s->add_param = bred_t[0];                               /* :216 */
+        s->mul_param = orc_mred_params(t);                      /* :217 */
+    }
+    for (int i = 0; i < c->nl; i++) {
+        u64 qi = c->modulus[i];
+        s->q[i] = qi;
+        /* QiBarre = (Q/qi)^-1 mod qi (:241-247); qi prime */
+        u64 star = 1;
+        for (int k = 0; k < c->nl; k++) if (k != i) star = mulmod(star, c->modulus[k] % qi, qi);
+        u64 barre = powmod(star, qi - 2, qi);
+        f128 tmp = f128_div(f128_set_u53(t), f128_set_u64(qi)); /* :249 */
+        tmp = f128_mul(tmp, f128_set_u64(barre));               /* :251 */
+        s->wi[i] = f128_to_u53(tmp);                            /* :254 */
+        if (!s->pow2) s->wi[i] = orc_mform(s->wi[i], t, bred_t);/* :257-259 */
+        u64 barre_t = mulmod(barre, t % qi, qi);                /* :261-262 */
+        f128 ti = f128_div(f128_set_u64(barre_t), f128_set_u64(qi)); /* :264 */
+        s->ti[2 * i] = ti.v[0];
+        s->ti[2 * i + 1] = ti.v[1];
+    }
+    return s;
+}
+API void orc_scaler_free(orc_scaler *s) {
+    if (!s) return;
+    free(s->q); free(s->wi); free(s->ti); free(s);
+}
+API void orc_scaler_params(const orc_scaler *s, u64 *wi, double *ti) {
+    memcpy(wi, s->wi, sizeof(u64) * s->nl);
+    memcpy(ti, s->ti, sizeof(double) * 2 * s->nl);
+}
+
+/* SimpleScaler.Scale, ring_scaling.go:271-300: p1 has the context's nl limbs; every one of p2's nl2 limbs gets the result */
+API void orc_scaler_scale(const orc_scaler *s, const u64 *p1, u64 *p2, int nl2) {
+    const u64 N = s->N, t = s->t;
+    for (u64 i = 0; i < N; i++) {
+        u64 a = 0;
+        f128 b = {{0.0, 0.0}};
+        for (int j = 0; j < s->nl; j++) {
+            u64 x = p1[(u64)j * N + i];
+            if (s->pow2) a += (s->wi[j] * x) & s->add_param;                 /* :206-208 */
+            else a += orc_mred(s->wi[j], x, t, s->mul_param);                /* :219-230 */
+            f128 tj = {{s->ti[2 * j], s->ti[2 * j + 1]}};
+            b = f128_add(b, f128_mul(tj, f128_set_u64(x)));                  /* :288 */
+        }
+        a += f128_to_u64(b);                                                 /* :291 */
+        if (s->pow2) a &= s->mul_param;                                      /* :210-212 */
+        else {                                                               /* :232-243 */
+            u64 s0 = hi64(a, s->add_param);
+            u64 r = a - s0 * t;
+            if (r >= t) r -= t;
+            a = r;
+        }
+        for (int j = 0; j < nl2; j++) p2[(u64)j * N + i] = a;               /* :295-297 */
+    }
+}

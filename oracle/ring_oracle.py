@@ -764,3 +764,221 @@ class BfvEvaluator:
         out = np.zeros((2, self.nQ, self.N), dtype=np.uint64)
         lib().orc_bfv_permute(self.h, ptr(ct), gen, ptr(evk), ptr(out))
         return out
+
+
+# ---------------------------------------------------------------------------
+# SimpleScaler (ring/ring_scaling.go:166-300, ring/float128.go) and the BFV key generator /
+# encryptor / decryptor / encoder ring sequences (bfv/keygen.go, encryptor.go, decryptor.go,
+# encoder.go) restated as compositions of the oracle's ring ops; sampled values are inputs
+# ---------------------------------------------------------------------------
+def _declare_scaler(L):
+    def f(name, res, *args):
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+
+    pd = C.POINTER(C.c_double)
+    f("orc_scaler_new", vp, u64, vp)
+    f("orc_scaler_free", None, vp)
+    f("orc_scaler_params", None, vp, p64, pd)
+    f("orc_scaler_scale", None, vp, p64, p64, C.c_int)
+    f("orc_f128_op", None, C.c_int, pd, pd, pd)
+    f("orc_f128_to_u64", u64, pd)
+
+
+def _scaler_lib():
+    L = lib()
+    if not getattr(L, "_scaler_declared", False):
+        _declare_scaler(L)
+        L._scaler_declared = True
+    return L
+
+
+def f128_op(op, a, b):
+    """op 0/1/2 = Float128Add / Mul / Div on (hi, lo) pairs"""
+    D = C.c_double * 2
+    out = D()
+    _scaler_lib().orc_f128_op(op, D(*a), D(*b), out)
+    return (out[0], out[1])
+
+
+def f128_to_u64(a):
+    return int(_scaler_lib().orc_f128_to_u64((C.c_double * 2)(*a)))
+
+
+class Scaler:
+    """ring.SimpleScaler: t/Q scaling of an RNS polynomial, result mod t on every limb of the output"""
+
+    def __init__(self, t, ctx):
+        self.ctx, self.t = ctx, int(t)
+        self.h = _scaler_lib().orc_scaler_new(self.t, ctx.h)
+
+    def __del__(self):
+        try:
+            lib().orc_scaler_free(self.h)
+        except Exception:
+            pass
+
+    def params(self):
+        wi = np.zeros(self.ctx.nl, dtype=np.uint64)
+        ti = np.zeros((self.ctx.nl, 2), dtype=np.float64)
+        lib().orc_scaler_params(self.h, ptr(wi), ti.ctypes.data_as(C.POINTER(C.c_double)))
+        return wi, ti
+
+    def scale(self, p1, nl_out=1):
+        p1 = np.ascontiguousarray(p1)
+        out = np.zeros((nl_out, self.ctx.N), dtype=np.uint64)
+        lib().orc_scaler_scale(self.h, ptr(p1), ptr(out), nl_out)
+        return out
+
+
+def bit_reverse(x, bits):
+    return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
+
+
+def bfv_index_matrix(N, galois_gen=5):  # bfv/encoder.go:36-58
+    logN = N.bit_length() - 1
+    row, m, pos = N >> 1, N << 1, 1
+    idx = np.zeros(N, dtype=np.uint64)
+    for i in range(row):
+        idx[i] = bit_reverse((pos - 1) >> 1, logN)
+        idx[i | row] = bit_reverse((m - pos - 1) >> 1, logN)
+        pos = (pos * galois_gen) & (m - 1)
+    return idx
+
+
+class BfvScheme:
+    def __init__(self, Q, P, N, t):
+        self.Qm, self.Pm, self.N, self.t = list(Q), list(P), N, int(t)
+        self.Q, self.P, self.QP = Context(N, self.Qm), Context(N, self.Pm), Context(N, self.Qm + self.Pm)
+        self.T = Context(N, [self.t])  # contextT, bfv/bfv.go:47
+        self.ext = Extender(self.Q, self.P)
+        self.nQ, self.alpha = len(self.Qm), len(self.Pm)
+        self.beta = -(-self.nQ // self.alpha)
+        self.Pbig = 1
+        for p in self.Pm:
+            self.Pbig *= int(p)
+        Qbig = 1
+        for q in self.Qm:
+            Qbig *= int(q)
+        delta = Qbig // self.t  # GenLiftParams, bfv/utils.go:9-23
+        self.delta_mont = [int(lib().orc_mform(delta % q, q, ptr(arr(bred_params(q))))) for q in self.Qm]
+        self.index_matrix = bfv_index_matrix(N)
+        self.scaler = Scaler(self.t, self.Q)
+
+    # --- keygen.go
+    def gen_secret_key(self, ternary):  # :82-96
+        return self.QP.ntt(self.QP.op2("mform_poly", signed_residues(self.Qm + self.Pm, ternary)))
+
+    def gen_public_key(self, sk, e, a):  # :120-135
+        pk0 = self.QP.ntt(signed_residues(self.Qm + self.Pm, e))
+        self.QP.op3("mulcoeffs_montgomery_and_add", sk, np.ascontiguousarray(a), pk0)
+        return self.QP.op2("neg", pk0), np.ascontiguousarray(a).copy()
+
+    def _times_p(self, p):
+        return self.QP.mul_scalar(p, [self.Pbig % q for q in self.Qm + self.Pm])
+
+    def new_switching_key(self, sk_in, sk_out, errors, uniforms):  # newswitchingkey :285-334 (sk_in already times P)
+        QP = self.Qm + self.Pm
+        evk = np.zeros((self.beta, 2, len(QP), self.N), dtype=np.uint64)
+        for i in range(self.beta):
+            k0 = self.QP.op2("mform_poly", self.QP.ntt(signed_residues(QP, errors[i])))
+            k1 = np.ascontiguousarray(uniforms[i]).copy()
+            for j in range(self.alpha):
+                index = i * self.alpha + j
+                qi = np.uint64(QP[index])
+                t = k0[index] + sk_in[index]
+                k0[index] = np.where(t >= qi, t - qi, t)  # CRed :319
+                if index >= len(QP) - 1:  # :323 (the bound is the QP context's, not Q's)
+                    break
+            self.QP.op3("mulcoeffs_montgomery_and_sub", k1, sk_out, k0)
+            evk[i, 0], evk[i, 1] = k0, k1
+        return evk
+
+    def gen_relin_key(self, sk, errors, uniforms):  # GenRelinKey :171-195, maxDegree 1
+        pool = self._times_p(sk)
+        pool = self.QP.op3("mulcoeffs_montgomery", pool, sk)
+        return self.new_switching_key(pool, sk, errors, uniforms)
+
+    def gen_switching_key(self, sk_in, sk_out, errors, uniforms):  # :248-262
+        return self.new_switching_key(self._times_p(sk_in), sk_out, errors, uniforms)
+
+    def gen_rot_key(self, sk, gen, errors, uniforms):  # genrotkey :429-441
+        idx = permute_ntt_index(gen, 1, self.N)
+        return self.new_switching_key(self._times_p(permute_ntt_with_index(sk, idx)), sk, errors, uniforms)
+
+    # --- encryptor.go
+    def encrypt_pk(self, pt, pk, u, e0, e1, fast=False, ct=None):  # pkEncryptor.encrypt :168-222
+        nQ = self.nQ
+        ct = np.zeros((2, nQ, self.N), dtype=np.uint64) if ct is None else ct.copy()
+        if fast:
+            # :174-192 computes pk*u + e into the pools and never copies them to the ciphertext: the
+            # receiver only gets the plaintext added (:221).  Kept literal.
+            pass
+        else:
+            QP = self.Qm + self.Pm
+            up = self.QP.ntt(self.QP.op2("mform_poly", signed_residues(QP, u)))
+            p0 = self.QP.invntt(self.QP.op3("mulcoeffs_montgomery", up, pk[0]))
+            p1 = self.QP.invntt(self.QP.op3("mulcoeffs_montgomery", up, pk[1]))
+            p0 = self.QP.op3("add", p0, signed_residues(QP, e0))
+            p1 = self.QP.op3("add", p1, signed_residues(QP, e1))
+            ct[0] = self.ext.moddown_pq(nQ - 1, p0)[:nQ]
+            ct[1] = self.ext.moddown_pq(nQ - 1, p1)[:nQ]
+        ct[0] = self.Q.op3("add", np.ascontiguousarray(ct[0]), np.ascontiguousarray(pt))
+        return ct
+
+    def encrypt_sk(self, pt, sk, crp, e, fast=False):  # skEncryptor.encrypt :296-345
+        nQ = self.nQ
+        ct = np.zeros((2, nQ, self.N), dtype=np.uint64)
+        if fast:
+            c0 = self.Q.op2("neg", self.Q.op3("mulcoeffs_montgomery", np.ascontiguousarray(crp), np.ascontiguousarray(sk[:nQ])))
+            ct[0] = self.Q.op3("add", self.Q.invntt(c0), signed_residues(self.Qm, e))
+            ct[1] = self.Q.invntt(np.ascontiguousarray(crp))
+        else:
+            QP = self.Qm + self.Pm
+            p0 = self.QP.invntt(self.QP.op2("neg", self.QP.op3("mulcoeffs_montgomery", np.ascontiguousarray(crp), sk)))
+            a = self.QP.invntt(np.ascontiguousarray(crp))
+            p0 = self.QP.op3("add", p0, signed_residues(QP, e))
+            ct[0] = self.ext.moddown_pq(nQ - 1, p0)[:nQ]
+            ct[1] = self.ext.moddown_pq(nQ - 1, a)[:nQ]
+        ct[0] = self.Q.op3("add", np.ascontiguousarray(ct[0]), np.ascontiguousarray(pt))
+        return ct
+
+    # --- decryptor.go:55-75
+    def decrypt(self, ct, sk):
+        nQ = self.nQ
+        skq = np.ascontiguousarray(sk[:nQ])
+        degree = len(ct) - 1
+        pt = self.Q.ntt(np.ascontiguousarray(ct[degree]))
+        for i in range(degree, 0, -1):
+            pt = self.Q.op3("mulcoeffs_montgomery", pt, skq)
+            pt = self.Q.op3("add", pt, self.Q.ntt(np.ascontiguousarray(ct[i - 1])))
+            if i & 7 == 7:
+                pt = self.Q.op2("reduce", pt)
+        if degree & 7 != 7:
+            pt = self.Q.op2("reduce", pt)
+        return self.Q.invntt(pt)
+
+    # --- encoder.go
+    def encode_uint(self, coeffs):  # EncodeUint :69-90 + encodePlaintext :121-136
+        c = np.asarray(coeffs, dtype=np.uint64)
+        slots = np.zeros((1, self.N), dtype=np.uint64)
+        slots[0, self.index_matrix[: len(c)].astype(np.int64)] = c
+        m = self.T.invntt(slots)[0]
+        pt = np.zeros((self.nQ, self.N), dtype=np.uint64)
+        for i in range(self.nQ - 1, -1, -1):
+            q = self.Qm[i]
+            pt[i] = _mred_vec(m, self.delta_mont[i], q, int(lib().orc_mred_params(q)))
+        return pt
+
+    def encode_int(self, coeffs):  # EncodeInt :94-119
+        c = np.asarray(coeffs, dtype=np.int64)
+        return self.encode_uint(np.where(c < 0, np.int64(self.t) + c, c).astype(np.uint64))
+
+    def decode_uint(self, pt):  # DecodeUint :139-153
+        pool = self.T.ntt(self.scaler.scale(pt, 1))
+        return pool[0, self.index_matrix.astype(np.int64)].copy()
+
+    def decode_int(self, pt):  # DecodeInt :157-182
+        v = self.decode_uint(pt).astype(np.int64)
+        return np.where(v > (self.t >> 1), v - self.t, v)

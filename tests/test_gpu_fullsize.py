@@ -122,3 +122,66 @@ def test_bfv_pn15_mul_relin_rotate(lg):
     w = oev.permute(w, gen, evk)
     assert np.array_equal(got[1], w)
     assert np.array_equal(got[0], got[2])
+
+
+def test_bfv_pn15_scheme_pipeline(lg):
+    """BASELINE config 3 at full size (BFV PN15QP880), whole scheme pipeline on the device: keygen -> encode ->
+    encrypt -> Mul -> Relinearize -> RotateColumns -> decrypt -> decode.  Size-independent property: the decoded
+    slots are the rotated slot-wise product mod t; one batch entry is also compared with the oracle bit for bit."""
+    p = lg.bfv.DefaultParams[lg.bfv.PN15QP880]
+    N, t = 1 << p["LogN"], p["T"]
+    Q, P, QMul = lg.bfv.GenModuli(p)
+    nQ = len(Q)
+    R = lg.ring
+    rng = np.random.default_rng(0x1A771C0 + 33)
+    cQ, cM, cP = (R.NewContextWithParams(N, m) for m in (Q, QMul, P))
+    kg = lg.bfv_scheme.KeyGenerator(cQ, cP)
+    enc = lg.bfv_scheme.Encoder(cQ, t)
+    ev = lg.bfv.NewEvaluator(cQ, cM, cP, t)
+    tern = lambda *s: rng.integers(-1, 2, size=s + (N,))
+    gauss = lambda *s: np.rint(rng.normal(0, 3.2, size=s + (N,))).astype(np.int64)
+    unif = lambda: np.ascontiguousarray(np.stack([rng.integers(0, q, size=N, dtype=np.uint64) for q in Q + P]))
+    sk_c = tern()
+    sk = kg.GenSecretKey(sk_c)
+    e_pk, a_pk = gauss(), unif()
+    pk = kg.GenPublicKey(sk, e_pk, a_pk)
+    rl_e, rl_u = [gauss() for _ in range(kg.beta)], [unif() for _ in range(kg.beta)]
+    rlk, rlk_host = kg.GenRelinKey(sk, rl_e, rl_u)
+    k = 5
+    gen = pow(lg.bfv.GaloisGen, k, 2 * N)
+    ro_e, ro_u = [gauss() for _ in range(kg.beta)], [unif() for _ in range(kg.beta)]
+    rot, rot_host = kg.genrotkey(sk, gen, ro_e, ro_u)
+    E = lg.bfv_scheme.Encryptor(cQ, cP, kg.contextQP, pk=pk, sk=sk)
+    D = lg.bfv_scheme.Decryptor(cQ, sk)
+    batch = 4
+    m0 = rng.integers(0, t, size=(batch, N), dtype=np.uint64)
+    m1 = rng.integers(0, t, size=(batch, N), dtype=np.uint64)
+    new = lambda n: tuple(R.Poly(N, nQ, batch) for _ in range(n))
+    (pt0, pt1), ct0, ct1 = new(2), new(2), new(2)
+    enc.EncodeUint(m0, pt0)
+    enc.EncodeUint(m1, pt1)
+    u, e0, e1 = tern(batch), gauss(batch), gauss(batch)
+    E.EncryptPk(pt0, ct0, u, e0, e1)
+    E.EncryptPk(pt1, ct1, tern(batch), gauss(batch), gauss(batch))
+    ct2, ctr, cto = new(3), new(2), new(2)
+    ev.Mul(ct0, ct1, ct2)
+    ev.Relinearize(ct2, rlk, ctr)
+    ev.permute(ctr, gen, rot, cto)
+    (dec,) = new(1)
+    D.Decrypt(cto, dec)
+    slots = enc.DecodeUint(dec)
+    row = N // 2
+    prod = (m0.astype(np.uint64) * m1.astype(np.uint64)) % np.uint64(t)  # t^2 < 2^64
+    want = np.concatenate([np.roll(prod[:, :row], -k, axis=1), np.roll(prod[:, row:], -k, axis=1)], axis=1)
+    assert np.array_equal(slots, want)
+    # oracle, entry 0: keys, first ciphertext and the decode of the final plaintext
+    S = orc.BfvScheme(Q, P, N, t)
+    osk = S.gen_secret_key(sk_c)
+    opk = S.gen_public_key(osk, e_pk, a_pk)
+    assert np.array_equal(rlk_host, S.gen_relin_key(osk, rl_e, rl_u))
+    o0 = S.encrypt_pk(S.encode_uint(m0[0]), opk, u[0], e0[0], e1[0])
+    assert np.array_equal(host(ct0)[0], o0)
+    final = host(cto)[0]
+    odec = S.decrypt(final, osk)
+    assert np.array_equal(dec.numpy(squeeze=False)[0], odec)
+    assert np.array_equal(S.decode_uint(odec), slots[0])
