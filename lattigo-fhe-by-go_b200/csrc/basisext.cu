@@ -9,6 +9,8 @@
 // __ull2double_rn / __ddiv_rn / __dadd_rn in the reference's order (no FMA
 // contraction, no reciprocal), and truncation toward zero for uint64(vi).
 // One thread per coefficient; every load/store is coalesced across the warp.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -165,6 +167,124 @@ __global__ void __launch_bounds__(128) modup_fast_kernel(const ModUpArgs a) {
     }
 }
 
+// FP64-quotient path for 1..4 source limbs whose moduli sum to less than 2^48 (every digit of the CKKS scale primes),
+// targets below 2^61.  The value to produce is R = (sum_i y_i*C_ij + qpjInv[j][v]) mod p_j with C_ij = Q/q_i mod p_j in
+// plain form (the canonical residue the reference's chain of MRed terms and its final BRedAdd return, :379-389).
+//   * low words:  S' = sum_i y_i*C_ij + K_v taken mod 2^64 -- one IMAD.WIDE and two IMADs per term;
+//   * quotient:   every y_i < 2^48 is exact in binary64; with C_ij, K_v, 1/p_j rounded DOWN and every operation
+//                 rounded down, t = RD(s * (1/p_j) + 2^52) holds an integer qh in its mantissa with
+//                 S'/p_j - 1 - (sum_i q_i + 1) * 2^-49 < qh <= S'/p_j, so S' - qh*p_j lies in [0, 2*p_j)
+//                 (nine downward roundings of relative size 2^-52 at most: 2^-49 on a value below sum_i q_i + 1);
+//   * the product qh*p_j is taken mod 2^64 as bits(t) * (2^64 - p_j), the exponent bits of t being folded
+//     into the K_v table entry, and one conditional subtraction canonicalises.
+// 16 integer multiply-adds, 6 FP64 operations and one CRed per target coefficient instead of the 128-bit
+// column sums and the Montgomery reduction of modup_fast_kernel.
+template <int NSRC>
+__global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
+    constexpr int ROW = 4 * NSRC + 5;  // np, p, 1/p, C[NSRC], Cd[NSRC], K'[NSRC+1], Kd[NSRC+1]
+    constexpr int O_C = 3, O_CD = 3 + NSRC, O_K = 3 + 2 * NSRC, O_KD = 4 + 3 * NSRC;
+    __shared__ u64 tab[LG_MAX_LIMBS * ROW];
+    const ModUpTables& M = a.M;
+    int ntg = 0;
+    for (int k = 0; k < a.nruns; ++k) ntg += a.ndst[k];
+    for (int idx = threadIdx.x; idx < ntg; idx += blockDim.x) {
+        int tg = 0;
+        for (int k = 0, o = idx; k < a.nruns; ++k) {
+            if (o < a.ndst[k]) {
+                tg = a.tgt0[k] + o;
+                break;
+            }
+            o -= a.ndst[k];
+        }
+        u64* row = tab + idx * ROW;
+        const u64 p = M.dstQ[tg], pinv = M.dstQinv[tg];
+        row[0] = 0 - p;
+        row[1] = p;
+        row[2] = (u64)__double_as_longlong(__ddiv_rd(1.0, __ull2double_ru(p)));
+#pragma unroll
+        for (int i = 0; i < NSRC; ++i) {
+            const u64 c = mred(M.qispj[(size_t)i * M.dst_total + tg], 1, p, pinv);  // out of Montgomery form
+            row[O_C + i] = c;
+            row[O_CD + i] = (u64)__double_as_longlong(__ull2double_rd(c));
+        }
+#pragma unroll
+        for (int v = 0; v <= NSRC; ++v) {
+            const u64 kv = M.qpjinv[(size_t)tg * (M.src_total + 1) + v];
+            row[O_K + v] = kv + 0x4330000000000000ull * p;  // + bits(2^52) * p: cancels the exponent field of t
+            row[O_KD + v] = (u64)__double_as_longlong(__ull2double_rd(kv));
+        }
+    }
+    __syncthreads();
+    const u32 x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int bt = blockIdx.y;
+    if (x >= a.N) return;
+    u32 y0[NSRC][2], y1[NSRC][2];
+    double yd[NSRC][2];
+    u32 v[2];
+    {
+        double vi0 = 0.0, vi1 = 0.0;
+        const u64* in = a.in + bt * a.in_bs + x;
+#pragma unroll
+        for (int i = 0; i < NSRC; ++i) {
+            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(in + (size_t)i * a.N);
+            if (a.copy_out) *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x) = val;
+            const u64 qi = __ldg(M.srcQ + i), qib = __ldg(M.qib + i), qinv = __ldg(M.srcQinv + i);
+            const u64 ya = mred(val.x, qib, qi, qinv), yb = mred(val.y, qib, qi, qinv);
+            const double qd = __ull2double_rn(qi);
+            yd[i][0] = __ull2double_rn(ya);  // exact: below 2^48
+            yd[i][1] = __ull2double_rn(yb);
+            vi0 = __dadd_rn(vi0, __ddiv_rn(yd[i][0], qd));
+            vi1 = __dadd_rn(vi1, __ddiv_rn(yd[i][1], qd));
+            y0[i][0] = (u32)ya;
+            y1[i][0] = (u32)(ya >> 32);
+            y0[i][1] = (u32)yb;
+            y1[i][1] = (u32)(yb >> 32);
+        }
+        v[0] = (u32)__double2ull_rz(vi0);
+        v[1] = (u32)__double2ull_rz(vi1);
+    }
+    int idx = 0;
+#pragma unroll 1
+    for (int k = 0; k < a.nruns; ++k) {
+        u64* out = a.out[k] + bt * a.out_bs[k] + x;
+#pragma unroll 1
+        for (int t = 0; t < a.ndst[k]; ++t, ++idx) {
+            const u64* row = tab + idx * ROW;
+            const u64 np = row[0], pj = row[1];
+            const double pinvd = __longlong_as_double((long long)row[2]);
+            u64 c[NSRC];
+            double cd[NSRC];
+#pragma unroll
+            for (int i = 0; i < NSRC; ++i) {
+                c[i] = row[O_C + i];
+                cd[i] = __longlong_as_double((long long)row[O_CD + i]);
+            }
+            u64 res[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double s = __dmul_rd(yd[0][e], cd[0]);
+#pragma unroll
+                for (int i = 1; i < NSRC; ++i) s = __fma_rd(yd[i][e], cd[i], s);
+                s = __dadd_rd(s, __longlong_as_double((long long)row[O_KD + v[e]]));
+                const u64 tb = (u64)__double_as_longlong(__fma_rd(s, pinvd, 4503599627370496.0));
+                u64 acc = row[O_K + v[e]];
+                u32 h = 0;
+#pragma unroll
+                for (int i = 0; i < NSRC; ++i) {
+                    acc = mad_wide(y0[i][e], (u32)c[i], acc);
+                    h = mad_lo32(y0[i][e], (u32)(c[i] >> 32), h);
+                    h = mad_lo32(y1[i][e], (u32)c[i], h);
+                }
+                acc = mad_wide((u32)tb, (u32)np, acc);
+                h = mad_lo32((u32)tb, (u32)(np >> 32), h);
+                h = mad_lo32((u32)(tb >> 32), (u32)np, h);
+                res[e] = cred(acc + ((u64)h << 32), pj);
+            }
+            *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N) = make_ulonglong2(res[0], res[1]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) fanout_kernel(const FanoutArgs a) {
     const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
     const int bt = blockIdx.y;
@@ -183,6 +303,18 @@ __global__ void __launch_bounds__(256) fanout_kernel(const FanoutArgs a) {
 
 int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
     if (batch <= 0) return 0;
+    static const bool no_fp = getenv("LATTIGPU_NO_FP_MODUP") != nullptr;  // A/B switch
+    if (a.fast == 2 && !no_fp && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
+        dim3 fgrid((a.N / 2 + 127) / 128, batch);
+        switch (a.nsrc) {
+            case 1: modup_fp_kernel<1><<<fgrid, 128, 0, st>>>(a); break;
+            case 2: modup_fp_kernel<2><<<fgrid, 128, 0, st>>>(a); break;
+            case 3: modup_fp_kernel<3><<<fgrid, 128, 0, st>>>(a); break;
+            default: modup_fp_kernel<4><<<fgrid, 128, 0, st>>>(a); break;
+        }
+        lg_g_launches += 1;
+        return 0;
+    }
     if (a.fast && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
         dim3 fgrid((a.N / 2 + 127) / 128, batch);
         switch (a.nsrc) {

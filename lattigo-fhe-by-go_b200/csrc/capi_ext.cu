@@ -18,6 +18,7 @@ int ModUpDev::build(const u64* Q, int nq, const u64* P, int np) {
     nsrc = nq;
     ndst = np;
     small = true;
+    hsrc.assign(Q, Q + nq);
     for (int i = 0; i < nq; ++i) small = small && (Q[i] >> 61) == 0;
     for (int j = 0; j < np; ++j) small = small && (P[j] >> 61) == 0;
     std::vector<u64> sQ(Q, Q + nq), sQinv(nq), vqib(nq), vqispj((size_t)nq * np), vqpj((size_t)np * (nq + 1));
@@ -92,7 +93,7 @@ int lgi_modup_launch(const ModUpDev& m, u64 N, int batch, const u64* in, size_t 
     a.ndst[0] = ndst;
     a.tgt0[0] = tgt0;
     a.copy_out = nullptr;
-    a.fast = m.small ? 1 : 0;
+    a.fast = m.fast_level(a.nsrc);
     if (lg_launch_modup(a, batch, st) != 0) {
         lg_set_error("modUpExact: too many source limbs (%d)", nsrc);
         return LG_ERR_ARG;
@@ -319,7 +320,7 @@ int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u
     a.ndst[1] = d->nP;
     a.tgt0[1] = d->nQ;
     a.copy_out = nullptr;
-    a.fast = m.small ? 1 : 0;
+    a.fast = m.fast_level(a.nsrc);
     if (lg_launch_modup(a, batch, st) != 0) {
         lg_set_error("Decompose: too many source limbs");
         return LG_ERR_ARG;
@@ -392,6 +393,7 @@ int lg_decomposer_decompose_and_split(const lg_decomposer* d, int level, int crt
 // input `coef` into d = [level+1 Q limbs | nP special-prime limbs]; NTT every limb outside the digit
 // (the digit's own limbs are taken from the NTT-domain copy `nttd`); acc0/acc1 += MRed(evk[i][0/1], d)
 // with BRedAdd when (i & 7) == cadence and after the last digit.
+
 int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, const lg_decomposer* dec, int level, int beta,
                          int batch, const u64* coef, size_t coef_bs, const u64* nttd, size_t nttd_bs, const lg_swk* evk,
                          u64* d, u64* acc0, u64* acc1, size_t d_bs, int cadence, cudaStream_t st) {

@@ -103,6 +103,16 @@ struct lg_galois {
 struct ModUpDev {
     int nsrc = 0, ndst = 0;
     bool small = false;  // all moduli below 2^61
+    std::vector<u64> hsrc;  // host copy of the source moduli
+    // kernel choice for the first `n` sources: 0 generic, 1 modup_fast_kernel (all moduli below 2^61), 2 modup_fp_kernel
+    // (additionally the source moduli sum to less than 2^48, see basisext.cu)
+    int fast_level(int n) const {
+        if (!small) return 0;
+        if (n > 4) return 1;
+        unsigned __int128 sum = 0;
+        for (int i = 0; i < n && i < (int)hsrc.size(); ++i) sum += hsrc[i];
+        return sum < ((unsigned __int128)1 << 48) ? 2 : 1;
+    }
     DevArray<u64> srcQ, srcQinv, qib, qispj, qpjinv, dstQ, dstQinv, dstU0;
     ModUpTables M;
     int build(const u64* Q, int nq, const u64* P, int np);

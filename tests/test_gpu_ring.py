@@ -456,3 +456,41 @@ def test_ntt_zero_and_sparse_inputs(lg, logN):
     got = out.numpy(squeeze=False)
     for b in range(3):
         assert np.array_equal(got[b], octx.invntt(np.ascontiguousarray(a[b]))), ("inv", b)
+
+
+@pytest.mark.parametrize("src_bits,nsrc", [(45, 4), (45, 3), (34, 2), (45, 1), (46, 3)], ids=["4x45", "3x45", "2x34", "1x45", "3x46"])
+@pytest.mark.parametrize("dst_bits", [[60, 60, 55, 45, 34], [36, 59]], ids=["wide", "narrow"])
+def test_modup_fp64_quotient_path(lg, src_bits, nsrc, dst_bits):
+    """modup_fp_kernel (csrc/basisext.cu): sources summing below 2^48 take the FP64-quotient basis extension.
+    Besides random residues, the inputs are built so that every y_i = MRed(a_i, qibMont_i) sits at the ends of its
+    range (0, 1, q_i - 1, q_i - 2, and mixed), where the quotient estimate and the correction index v are extreme;
+    bit-exact against the oracle's modUpExact (ring_basis_extension.go:352-393)."""
+    logN = 10
+    N = 1 << logN
+    Qm = orc.generate_ntt_primes(src_bits, logN, nsrc)
+    Pm = []
+    for b in dst_bits:
+        Pm.append([p for p in orc.generate_ntt_primes(b, logN, len(dst_bits) + nsrc) if p not in Qm and p not in Pm][0])
+    oe = orc.Extender(orc.Context(N, Qm), orc.Context(N, Pm))
+    cQ, cP = lg.ring.NewContextWithParams(N, Qm), lg.ring.NewContextWithParams(N, Pm)
+    be = lg.ring.NewFastBasisExtender(cQ, cP)
+    rng = np.random.default_rng(src_bits * 10 + nsrc)
+    a = np.stack([rng.integers(0, q, size=N, dtype=np.uint64) for q in Qm])
+    Qbig = 1
+    for q in Qm:
+        Qbig *= q
+    ends = lambda q: [0, 1, q - 1, q - 2, q // 2]
+    for col in range(min(N, 400)):
+        for i, q in enumerate(Qm):
+            star = (Qbig // q) % q  # y = a * (Q/q)^-1 mod q  =>  a = y * (Q/q) mod q
+            y = ends(q)[(col // (5 ** i)) % 5] if col < 5 ** min(nsrc, 3) else ends(q)[rng.integers(0, 5)]
+            a[i, col] = (y * star) % q
+    pQ = lg.ring.Poly.from_numpy(a)
+    for level in range(nsrc):
+        out = cP.NewPoly()
+        be.ModUpSplitQP(level, pQ, out)
+        assert np.array_equal(out.numpy(), oe.modup_split_qp(level, a)), level
+    w = rng.integers(0, 1 << 64, size=(nsrc, N), dtype=np.uint64)  # unreduced words
+    out = cP.NewPoly()
+    be.ModUpSplitQP(nsrc - 1, lg.ring.Poly.from_numpy(w), out)
+    assert np.array_equal(out.numpy(), oe.modup_split_qp(nsrc - 1, w))
