@@ -216,6 +216,13 @@ int lg_ckks_eval_destroy(lg_ckks_eval* e);
 /* host layout [beta][2][nQ+nP][N], NTT + Montgomery form (ckks/keygen.go:282-340) */
 int lg_swk_create(uint64_t N, int beta, int nQP, const uint64_t* host, lg_swk** out);
 int lg_swk_wrap(void* device_ptr, uint64_t N, int beta, int nQP, lg_swk** out);
+/* marshaling support (ckks/marshaler.go:193-283, bfv/marshaler.go:202-287): an empty key of a given shape, and
+ * evakey[digit][half] as a non-owning ring.Poly handle over QP for lg_poly_write_to / lg_poly_decode */
+int lg_swk_alloc(uint64_t N, int beta, int nQP, lg_swk** out);
+int lg_swk_poly(const lg_swk* k, int digit, int half, lg_poly** out);
+int lg_swk_beta(const lg_swk* k);
+int lg_swk_nlimbs(const lg_swk* k);
+uint64_t lg_swk_n(const lg_swk* k);
 int lg_swk_destroy(lg_swk* k);
 /* switchKeysInPlace :1475-1558: p0,p1 receive the level+1 limb results */
 int lg_ckks_switch_keys_in_place(lg_ckks_eval* e, int level, const lg_poly* cx, const lg_swk* evk, lg_poly* p0, lg_poly* p1, lg_stream_t s);

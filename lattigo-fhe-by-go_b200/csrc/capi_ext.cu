@@ -602,6 +602,29 @@ int lg_swk_wrap(void* device_ptr, uint64_t N, int beta, int nQP, lg_swk** out) {
     *out = k;
     return LG_OK;
 }
+// an uninitialised key of the given shape (filled through lg_swk_poly views, e.g. by lg_poly_decode)
+int lg_swk_alloc(uint64_t N, int beta, int nQP, lg_swk** out) {
+    LG_REQUIRE(out && beta >= 1 && nQP >= 1 && N >= 1, "SwitchingKey: invalid argument");
+    std::unique_ptr<lg_swk> k(new lg_swk);
+    k->N = N;
+    k->beta = beta;
+    k->nQP = nQP;
+    k->owns = true;
+    const size_t bytes = (size_t)beta * 2 * nQP * N * sizeof(u64);
+    LG_CUDA_CHECK(cudaMalloc((void**)&k->d, bytes));
+    LG_CUDA_CHECK(cudaMemset(k->d, 0, bytes));
+    *out = k.release();
+    return LG_OK;
+}
+// evakey[digit][half] as a non-owning polynomial handle over QP (the key must outlive it)
+int lg_swk_poly(const lg_swk* k, int digit, int half, lg_poly** out) {
+    LG_REQUIRE(k && out, "SwitchingKey: null argument");
+    LG_REQUIRE(digit >= 0 && digit < k->beta && (half == 0 || half == 1), "SwitchingKey: evakey[%d][%d] out of range", digit, half);
+    return lg_poly_wrap((void*)k->key(digit, half), k->N, k->nQP, 1, out);
+}
+int lg_swk_beta(const lg_swk* k) { return k ? k->beta : 0; }
+int lg_swk_nlimbs(const lg_swk* k) { return k ? k->nQP : 0; }
+uint64_t lg_swk_n(const lg_swk* k) { return k ? k->N : 0; }
 int lg_swk_destroy(lg_swk* k) {
     if (k && k->owns && k->d) cudaFree(k->d);
     delete k;

@@ -151,6 +151,11 @@ SIGNATURES = {
     "lg_ckks_eval_create": (ci, [_R, _R, C.POINTER(vp)]),
     "lg_ckks_eval_destroy": (ci, [vp]),
     "lg_swk_create": (ci, [u64, ci, ci, p64, C.POINTER(vp)]),
+    "lg_swk_alloc": (ci, [u64, ci, ci, C.POINTER(vp)]),
+    "lg_swk_poly": (ci, [vp, ci, ci, C.POINTER(vp)]),
+    "lg_swk_beta": (ci, [vp]),
+    "lg_swk_nlimbs": (ci, [vp]),
+    "lg_swk_n": (u64, [vp]),
     "lg_swk_wrap": (ci, [vp, u64, ci, ci, C.POINTER(vp)]),
     "lg_swk_destroy": (ci, [vp]),
     "lg_ckks_switch_keys_in_place": (ci, [vp, ci, _P, vp, _P, _P, vp]),

@@ -982,3 +982,77 @@ class BfvScheme:
     def decode_int(self, pt):  # DecodeInt :157-182
         v = self.decode_uint(pt).astype(np.int64)
         return np.where(v > (self.t >> 1), v - self.t, v)
+
+
+# ---------------------------------------------------------------------------
+# wire formats of the scheme objects (ckks/marshaler.go, bfv/marshaler.go): byte strings built from numpy
+# polynomials [nlimbs][N]; switching keys are [beta][2][nQP][N]
+# ---------------------------------------------------------------------------
+import struct as _struct
+
+
+def ckks_ciphertext_marshal(value, scale, is_ntt=True):  # ckks/marshaler.go:24-52
+    head = bytes([len(value)]) + _struct.pack("<d", scale) + bytes([0, 1 if is_ntt else 0])
+    return head + b"".join(poly_marshal(p) for p in value)
+
+
+def bfv_ciphertext_marshal(value, is_ntt=False):  # bfv/marshaler.go:9-33
+    return bytes([len(value), 1 if is_ntt else 0]) + b"".join(poly_marshal(p) for p in value)
+
+
+def _poly_at(data, pointer):  # DecodePolyNew ring_object.go:277-289
+    N, nl = 1 << data[pointer], data[pointer + 1]
+    inc = 2 + ((N * nl) << 3)
+    return poly_unmarshal(data[pointer:pointer + inc]), inc
+
+
+def ckks_ciphertext_unmarshal(data):  # ckks/marshaler.go:57-91
+    scale = _struct.unpack("<d", data[1:9])[0]
+    value, pointer = [], 11
+    for _ in range(data[0]):
+        p, inc = _poly_at(data, pointer)
+        value.append(p)
+        pointer += inc
+    return value, scale, data[10] == 1
+
+
+def bfv_ciphertext_unmarshal(data):  # bfv/marshaler.go:36-60
+    value, pointer = [], 2
+    for _ in range(data[0]):
+        p, inc = _poly_at(data, pointer)
+        value.append(p)
+        pointer += inc
+    return value, data[1] == 1
+
+
+def public_key_marshal(pk):  # ckks/marshaler.go:133-143
+    return poly_marshal(pk[0]) + poly_marshal(pk[1])
+
+
+def swk_marshal(evk):  # SwitchingKey.encode ckks/marshaler.go:230-257
+    return bytes([evk.shape[0]]) + b"".join(poly_marshal(evk[j, h]) for j in range(evk.shape[0]) for h in (0, 1))
+
+
+def swk_unmarshal(data, pointer=0):  # decode :259-283
+    beta, start = data[pointer], pointer
+    pointer += 1
+    polys = []
+    for _ in range(2 * beta):
+        p, inc = _poly_at(data, pointer)
+        polys.append(p)
+        pointer += inc
+    return np.stack(polys).reshape(beta, 2, *polys[0].shape), pointer - start
+
+
+def bfv_evaluation_key_marshal(keys):  # bfv/marshaler.go:166-183
+    return bytes([len(keys)]) + b"".join(swk_marshal(k) for k in keys)
+
+
+def rotation_keys_marshal(left, right, third=None):  # ckks/marshaler.go:312-355: type byte over the big-endian amount
+    out = []
+    for typ, keys in ((2, left), (1, right)):
+        for i, k in keys.items():
+            out.append(bytes([typ]) + _struct.pack(">I", i)[1:] + swk_marshal(k))
+    if third is not None:
+        out.append(bytes([3, 0, 0, 0]) + swk_marshal(third))
+    return b"".join(out)
