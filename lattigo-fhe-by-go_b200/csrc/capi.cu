@@ -6,6 +6,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "capi_internal.hpp"
 
 std::atomic<uint64_t> lg_g_launches{0};
@@ -424,9 +426,10 @@ int lg_poly_copy(const lg_poly* src, int nl, lg_poly* dst, lg_stream_t s) {
 // ---------------------------------------------------------------------------
 
 int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, size_t in_bs, u64* out, size_t out_bs,
-            bool inverse, int skip0, int skip1, cudaStream_t st, bool in_range) {
+            bool inverse, int skip0, int skip1, cudaStream_t st, bool in_range, const NttTail* tail) {
     NttArgs a;
     memset(&a, 0, sizeof(a));
+    if (tail) a.tail = *tail;
     a.T = r->T;
     a.map = map;
     a.in = in;
@@ -449,6 +452,11 @@ int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, siz
     }
     LG_LAUNCH_CHECK();
     return LG_OK;
+}
+
+bool lgi_ntt_tail_ok(const lg_ring* r) {
+    static const bool off = getenv("LATTIGPU_NO_FUSED_TAIL") != nullptr;  // A/B switch
+    return !off && r->logN >= 12;
 }
 
 int lgi_ew(int op, const lg_ring* r, LimbMap map, int nl, int batch, const u64* a, size_t a_bs, const u64* b,
@@ -846,6 +854,17 @@ int lgi_div_by_last_modulus(const lg_ring* r, int nl, int batch, u64* p0, size_t
     }
     lg_launch_fanout(f, batch, st);
     LG_LAUNCH_CHECK();
+    if (ntt && lgi_ntt_tail_ok(r)) {  // :21-30 / :105-109 in one pass: the tail rides on the transform's last phase
+        NttTail t;
+        memset(&t, 0, sizeof(t));
+        t.enabled = 1;
+        t.split = batch;
+        t.a[0] = p0;
+        t.out[0] = p0;
+        t.a_bs[0] = t.out_bs[0] = bs;
+        for (int i = 0; i < level; ++i) t.s[i] = r->rescale_param(level, i);
+        return lgi_ntt(r, limb_map_identity(), level, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st, false, &t);
+    }
     if (ntt)  // :21 / :105
         LG_TRY(lgi_ntt(r, limb_map_identity(), level, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
     else  // :48 / :143  BRedAdd of the broadcast limb

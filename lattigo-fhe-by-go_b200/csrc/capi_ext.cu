@@ -138,6 +138,19 @@ int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* 
     LG_TRY(tmp.alloc((size_t)batch * nl * N));
     const size_t tbs = (size_t)nl * N;
     LG_TRY(lgi_modup_launch(e->pq, N, batch, p1P, p1P_bs, P->nl, tmp.d, tbs, nl, 0, st));
+    if (ntt && lgi_ntt_tail_ok(Q)) {  // :228-238 in one pass
+        NttTail t;
+        memset(&t, 0, sizeof(t));
+        t.enabled = 1;
+        t.split = batch;
+        t.add[0] = accumulate ? 1 : 0;
+        t.a[0] = p1Q;
+        t.a_bs[0] = p1Q_bs;
+        t.out[0] = p2;
+        t.out_bs[0] = p2_bs;
+        for (int i = 0; i < nl; ++i) t.s[i] = e->moddown_pq[i];
+        return lgi_ntt(Q, limb_map_identity(), nl, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st, false, &t);
+    }
     if (ntt) LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
     return lgi_ew(accumulate ? EW_SUB_MULMONT_SCALAR_ADD : EW_SUB_MULMONT_SCALAR, Q, limb_map_identity(), nl, batch, p1Q,
                   p1Q_bs, tmp.d, tbs, p2, p2_bs, e->moddown_pq.data(), nl, st);
@@ -165,6 +178,23 @@ int lgi_moddown_pair_ntt(const lg_extender* e, int level, int batch, u64* acc0, 
     LG_TRY(tmp.alloc((size_t)2 * batch * nl * N));
     const size_t tbs = (size_t)nl * N;
     LG_TRY(lgi_modup_launch(e->pq, N, 2 * batch, pP, acc_bs, P->nl, tmp.d, tbs, nl, 0, st));
+    if (ntt && lgi_ntt_tail_ok(Q)) {  // both tails ride on the last phase of the one transform over 2*batch entries
+        NttTail t;
+        memset(&t, 0, sizeof(t));
+        t.enabled = 1;
+        t.split = batch;
+        t.add[0] = add0 ? 1 : 0;
+        t.add[1] = add1 ? 1 : 0;
+        t.a[0] = acc0;
+        t.a[1] = acc1;
+        t.a_bs[0] = t.a_bs[1] = acc_bs;
+        t.out[0] = out0;
+        t.out[1] = out1;
+        t.out_bs[0] = out0_bs;
+        t.out_bs[1] = out1_bs;
+        for (int i = 0; i < nl; ++i) t.s[i] = e->moddown_pq[i];
+        return lgi_ntt(Q, limb_map_identity(), nl, 2 * batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st, false, &t);
+    }
     if (ntt) LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, 2 * batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
     LG_TRY(lgi_ew(add0 ? EW_SUB_MULMONT_SCALAR_ADD : EW_SUB_MULMONT_SCALAR, Q, limb_map_identity(), nl, batch, acc0, acc_bs,
                   tmp.d, tbs, out0, out0_bs, e->moddown_pq.data(), nl, st));

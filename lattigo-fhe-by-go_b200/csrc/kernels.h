@@ -10,6 +10,19 @@ extern std::atomic<uint64_t> lg_g_launches;  // kernels launched by this library
 #define LG_MAX_LIMBS 64
 
 // ---- K1: NTT ----------------------------------------------------------------
+// Epilogue of the forward transform's last phase (logN >= 12): instead of storing NTT(x) the kernel stores
+//   out = MRed(a + (q - NTT(x)), s_j)            (the (x - y) * P^-1 / q_last^-1 tail of ModDown and of the rescaling,
+//   out = CRed(out + MRed(a + (q - NTT(x)), s_j)) ring_basis_extension.go:236-238, ring_scaling.go:30,:109; + the Add that follows)
+// for data limb j of batch entry b.  Entries b >= split use the second (a, out, add) set with index b - split.
+struct NttTail {
+    int enabled;
+    int split;
+    int add[2];
+    const u64* a[2];
+    u64* out[2];
+    size_t a_bs[2], out_bs[2];
+    u64 s[LG_MAX_LIMBS];
+};
 struct NttArgs {
     RingTables T;
     LimbMap map;
@@ -24,6 +37,7 @@ struct NttArgs {
     // inverse only: per (batch, limb) flag, non-zero = some input word is above 2q, use the literal
     // butterflies for that limb (written by lg_launch_range_flags); nullptr = inputs known to be in range
     const u32* flags;
+    NttTail tail;                    // forward only
 };
 int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cudaStream_t st);
 // forward transform, strided phase only, in place or out of place (logN >= 12); the contiguous phase is

@@ -459,6 +459,31 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
             __syncwarp();
             if (i + 1 < nb) prefetch_warp_tile(tilebuf, src + (size_t)(i + 1) * a.in_bstride);
             fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS);
+            if (a.tail.enabled) {
+                // the caller's (x - NTT(y)) * s_j tail (+ add) on the canonical transform, straight from the registers
+                const int bi = b0 + i, set = bi >= a.tail.split ? 1 : 0;
+                const size_t bb = (size_t)(bi - (set ? a.tail.split : 0));
+                const u64* ta = a.tail.a[set] + bb * a.tail.a_bs[set] + (size_t)j * N + e0;
+                u64* to = a.tail.out[set] + bb * a.tail.out_bs[set] + (size_t)j * N + e0;
+                const u64 sj = a.tail.s[j];
+                const bool add = a.tail.add[set] != 0;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    u64 va[4], r[4];
+                    ld256(va, ta + 4 * h);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        r[e] = mred(va[e] + (c.q - bred_add(x[4 * h + e], c.q, lc.u0)), sj, c.q, c.qinv);
+                    if (add) {
+                        u64 vo[4];
+                        ld256(vo, to + 4 * h);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) r[e] = cred(vo[e] + r[e], c.q);
+                    }
+                    st256(to + 4 * h, r[0], r[1], r[2], r[3]);
+                }
+                continue;
+            }
             // ring/ntt.go:83-85
 #pragma unroll
             for (int h = 0; h < 4; ++h)
@@ -813,6 +838,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     if (nlimbs <= 0 || batch <= 0) return 0;
     const u32 logN = args.T.logN, N = args.T.N;
     if (logN < 1 || logN > 16) return 1;
+    if (args.tail.enabled && (inverse || logN <= 11)) return 1;
     if (logN <= 11) {
         const u32 threads = (N >> 1) < 32 ? 32 : ((N >> 1) > 512 ? 512 : (N >> 1));
         dim3 grid(batch, 1, nlimbs);
