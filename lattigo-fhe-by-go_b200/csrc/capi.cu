@@ -426,10 +426,12 @@ int lg_poly_copy(const lg_poly* src, int nl, lg_poly* dst, lg_stream_t s) {
 // ---------------------------------------------------------------------------
 
 int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, size_t in_bs, u64* out, size_t out_bs,
-            bool inverse, int skip0, int skip1, cudaStream_t st, bool in_range, const NttTail* tail) {
+            bool inverse, int skip0, int skip1, cudaStream_t st, bool in_range, const NttTail* tail,
+            const NttBcast* bcast) {
     NttArgs a;
     memset(&a, 0, sizeof(a));
     if (tail) a.tail = *tail;
+    if (bcast) a.bcast = *bcast;
     a.T = r->T;
     a.map = map;
     a.in = in;
@@ -836,6 +838,28 @@ int lgi_div_by_last_modulus(const lg_ring* r, int nl, int batch, u64* p0, size_t
     Scratch tmp(st);
     LG_TRY(tmp.alloc((size_t)batch * level * N));
     const size_t tbs = (size_t)level * N;
+    if (ntt && lgi_ntt_tail_ok(r)) {
+        // :17-30 / :80-109 in one transform: the first phase reads the last limb for every target limb (+ pHalf terms),
+        // the last phase applies (x - y) * q_last^-1 straight from its registers
+        NttBcast bc;
+        memset(&bc, 0, sizeof(bc));
+        bc.enabled = 1;
+        bc.round = round ? 1 : 0;
+        bc.plast = r->q[level];
+        if (round) {
+            bc.phalf = (r->q[level] - 1) >> 1;  // :82
+            for (int i = 0; i < level; ++i) bc.add[i] = r->q[i] - (bc.phalf % r->q[i]);  // :97 pHalfNegQi
+        }
+        NttTail t;
+        memset(&t, 0, sizeof(t));
+        t.enabled = 1;
+        t.split = batch;
+        t.a[0] = p0;
+        t.out[0] = p0;
+        t.a_bs[0] = t.out_bs[0] = bs;
+        for (int i = 0; i < level; ++i) t.s[i] = r->rescale_param(level, i);
+        return lgi_ntt(r, limb_map_identity(), level, batch, last, bs, tmp.d, tbs, false, 0, 0, st, false, &t, &bc);
+    }
     FanoutArgs f;
     f.N = (u32)N;
     f.in = last;
@@ -854,17 +878,6 @@ int lgi_div_by_last_modulus(const lg_ring* r, int nl, int batch, u64* p0, size_t
     }
     lg_launch_fanout(f, batch, st);
     LG_LAUNCH_CHECK();
-    if (ntt && lgi_ntt_tail_ok(r)) {  // :21-30 / :105-109 in one pass: the tail rides on the transform's last phase
-        NttTail t;
-        memset(&t, 0, sizeof(t));
-        t.enabled = 1;
-        t.split = batch;
-        t.a[0] = p0;
-        t.out[0] = p0;
-        t.a_bs[0] = t.out_bs[0] = bs;
-        for (int i = 0; i < level; ++i) t.s[i] = r->rescale_param(level, i);
-        return lgi_ntt(r, limb_map_identity(), level, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st, false, &t);
-    }
     if (ntt)  // :21 / :105
         LG_TRY(lgi_ntt(r, limb_map_identity(), level, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
     else  // :48 / :143  BRedAdd of the broadcast limb

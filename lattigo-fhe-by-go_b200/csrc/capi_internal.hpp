@@ -161,7 +161,8 @@ struct lg_ckks_eval {
 // internal (non-ABI) helpers shared between translation units
 int lgi_ring_build_device(lg_ring* r);
 int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, size_t in_bs, u64* out, size_t out_bs,
-            bool inverse, int skip0, int skip1, cudaStream_t st, bool in_range = false, const NttTail* tail = nullptr);
+            bool inverse, int skip0, int skip1, cudaStream_t st, bool in_range = false, const NttTail* tail = nullptr,
+            const NttBcast* bcast = nullptr);
 // the forward transform can carry the (x - y) * s tail of ModDown / rescaling in its last phase (logN >= 12)
 bool lgi_ntt_tail_ok(const lg_ring* r);
 int lgi_ew(int op, const lg_ring* r, LimbMap map, int nl, int batch, const u64* a, size_t a_bs, const u64* b,

@@ -23,6 +23,14 @@ struct NttTail {
     size_t a_bs[2], out_bs[2];
     u64 s[LG_MAX_LIMBS];
 };
+// Broadcast input of the forward transform's first phase (logN >= 12): every data limb j transforms the same source
+// limb, x_j = f(v) + add[j] with f(v) = CRed(v + phalf, plast) when round, else v -- the rescaling's "last limb
+// (+ pHalf) to every other limb" (ring_scaling.go:17-28, :80-103) without materialising the copies.
+struct NttBcast {
+    int enabled, round;
+    u64 phalf, plast;
+    u64 add[LG_MAX_LIMBS];
+};
 struct NttArgs {
     RingTables T;
     LimbMap map;
@@ -38,6 +46,7 @@ struct NttArgs {
     // butterflies for that limb (written by lg_launch_range_flags); nullptr = inputs known to be in range
     const u32* flags;
     NttTail tail;                    // forward only
+    NttBcast bcast;                  // forward only
 };
 int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cudaStream_t st);
 // forward transform, strided phase only, in place or out of place (logN >= 12); the contiguous phase is

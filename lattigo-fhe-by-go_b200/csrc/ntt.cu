@@ -250,7 +250,7 @@ LG_DEV LimbSetup setup_limb(const NttArgs& a) {
     }
     s.tl = a.map(j);
     s.c = load_limb_const(a.T, s.tl);
-    s.in = a.in + (size_t)b * a.in_bstride + (size_t)j * a.T.N;
+    s.in = a.in + (size_t)b * a.in_bstride + (a.bcast.enabled ? 0 : (size_t)j * a.T.N);
     s.out = a.out + (size_t)b * a.out_bstride + (size_t)j * a.T.N;
     return s;
 }
@@ -291,6 +291,11 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
     const u64* in = s.in + colg + g * 256;
 #pragma unroll
     for (int r = 0; r < 16; ++r) x[r] = in[r * G * 256];
+    if (a.bcast.enabled) {  // ring_scaling.go:83-88 / :99-103: (last limb + pHalf mod q_last) + (q_j - pHalf mod q_j), unreduced
+        const u64 add = a.bcast.add[blockIdx.z];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = (a.bcast.round ? cred(x[r] + a.bcast.phalf, a.bcast.plast) : x[r]) + add;
+    }
     fill_strided_tw<L, MODE == M_LITERAL>(tws_sm, c);
     if (MODE != M_LITERAL) {
         // headroom of the lazy butterflies (canonical inputs never take the slow branch): M_FREE keeps
@@ -838,7 +843,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     if (nlimbs <= 0 || batch <= 0) return 0;
     const u32 logN = args.T.logN, N = args.T.N;
     if (logN < 1 || logN > 16) return 1;
-    if (args.tail.enabled && (inverse || logN <= 11)) return 1;
+    if ((args.tail.enabled || args.bcast.enabled) && (inverse || logN <= 11)) return 1;
     if (logN <= 11) {
         const u32 threads = (N >> 1) < 32 ? 32 : ((N >> 1) > 512 ? 512 : (N >> 1));
         dim3 grid(batch, 1, nlimbs);
@@ -855,6 +860,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     NttArgs second = args;  // the second phase runs in place on the output
     second.in = args.out;
     second.in_bstride = args.out_bstride;
+    second.bcast.enabled = 0;
     if (!inverse) {
         launch_strided_any(L, true, literal, args, sgrid, st);
         launch_contig_pipe(true, literal, second, nlimbs, batch, st);
