@@ -285,6 +285,124 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
     }
 }
 
+// Two-step variant for wider sources (e.g. the 55-bit special primes of a ModDown, or a digit holding the first
+// prime): sum_i q_i < 2^(50+SH).  The first quotient is taken at a granularity of 2^SH -- t = RD(s * (1/p) + 2^(52+SH))
+// holds qh1 / 2^SH in its mantissa, s <= S being the all-rounded-down binary64 image of S = sum_i y_i*C_ij (the y_i
+// themselves rounded down) -- so that r1 = S + K_v - qh1*p lies in [0, (2^SH + 8 * 2^-52 * sum_i q_i + 2) * p) (eight downward roundings), which
+// the host checks to be below 2^64 for every target before choosing this kernel.  A second quotient on r1 (converted
+// rounding down) leaves [0, 2p) and one conditional subtraction.  Everything integer is mod 2^64 as in modup_fp_kernel.
+template <int NSRC>
+__global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
+    constexpr int ROW = 3 * NSRC + 6;  // np << SH, p, 1/p, bits(2^52) * p, np, C[NSRC], Cd[NSRC], K'[NSRC+1]
+    constexpr int O_C = 5, O_CD = 5 + NSRC, O_K = 5 + 2 * NSRC;
+    __shared__ u64 tab[LG_MAX_LIMBS * ROW];
+    const ModUpTables& M = a.M;
+    const int sh = a.fp_shift;
+    const u64 magic_bits = (u64)(0x433 + sh) << 52;  // 2^(52+sh)
+    int ntg = 0;
+    for (int k = 0; k < a.nruns; ++k) ntg += a.ndst[k];
+    for (int idx = threadIdx.x; idx < ntg; idx += blockDim.x) {
+        int tg = 0;
+        for (int k = 0, o = idx; k < a.nruns; ++k) {
+            if (o < a.ndst[k]) {
+                tg = a.tgt0[k] + o;
+                break;
+            }
+            o -= a.ndst[k];
+        }
+        u64* row = tab + idx * ROW;
+        const u64 p = M.dstQ[tg], pinv = M.dstQinv[tg];
+        row[0] = (0 - p) << sh;
+        row[1] = p;
+        row[2] = (u64)__double_as_longlong(__ddiv_rd(1.0, __ull2double_ru(p)));
+        row[3] = 0x4330000000000000ull * p;
+        row[4] = 0 - p;
+#pragma unroll
+        for (int i = 0; i < NSRC; ++i) {
+            const u64 c = mred(M.qispj[(size_t)i * M.dst_total + tg], 1, p, pinv);  // out of Montgomery form
+            row[O_C + i] = c;
+            row[O_CD + i] = (u64)__double_as_longlong(__ull2double_rd(c));
+        }
+#pragma unroll
+        for (int v = 0; v <= NSRC; ++v)
+            row[O_K + v] = M.qpjinv[(size_t)tg * (M.src_total + 1) + v] + magic_bits * (p << sh);
+    }
+    __syncthreads();
+    const double magic = __longlong_as_double((long long)magic_bits);
+    const u32 x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int bt = blockIdx.y;
+    if (x >= a.N) return;
+    u32 y0[NSRC][2], y1[NSRC][2];
+    double yd[NSRC][2];
+    u32 v[2];
+    {
+        double vi0 = 0.0, vi1 = 0.0;
+        const u64* in = a.in + bt * a.in_bs + x;
+#pragma unroll
+        for (int i = 0; i < NSRC; ++i) {
+            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(in + (size_t)i * a.N);
+            if (a.copy_out) *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x) = val;
+            const u64 qi = __ldg(M.srcQ + i), qib = __ldg(M.qib + i), qinv = __ldg(M.srcQinv + i);
+            const u64 ya = mred(val.x, qib, qi, qinv), yb = mred(val.y, qib, qi, qinv);
+            const double qd = __ull2double_rn(qi);
+            vi0 = __dadd_rn(vi0, __ddiv_rn(__ull2double_rn(ya), qd));
+            vi1 = __dadd_rn(vi1, __ddiv_rn(__ull2double_rn(yb), qd));
+            yd[i][0] = __ull2double_rd(ya);
+            yd[i][1] = __ull2double_rd(yb);
+            y0[i][0] = (u32)ya;
+            y1[i][0] = (u32)(ya >> 32);
+            y0[i][1] = (u32)yb;
+            y1[i][1] = (u32)(yb >> 32);
+        }
+        v[0] = (u32)__double2ull_rz(vi0);
+        v[1] = (u32)__double2ull_rz(vi1);
+    }
+    int idx = 0;
+#pragma unroll 1
+    for (int k = 0; k < a.nruns; ++k) {
+        u64* out = a.out[k] + bt * a.out_bs[k] + x;
+#pragma unroll 1
+        for (int t = 0; t < a.ndst[k]; ++t, ++idx) {
+            const u64* row = tab + idx * ROW;
+            const u64 npsh = row[0], pj = row[1], c52 = row[3], np = row[4];
+            const double pinvd = __longlong_as_double((long long)row[2]);
+            u64 c[NSRC];
+            double cd[NSRC];
+#pragma unroll
+            for (int i = 0; i < NSRC; ++i) {
+                c[i] = row[O_C + i];
+                cd[i] = __longlong_as_double((long long)row[O_CD + i]);
+            }
+            u64 res[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double s = __dmul_rd(yd[0][e], cd[0]);
+#pragma unroll
+                for (int i = 1; i < NSRC; ++i) s = __fma_rd(yd[i][e], cd[i], s);
+                const u64 tb = (u64)__double_as_longlong(__fma_rd(s, pinvd, magic));
+                u64 acc = row[O_K + v[e]];
+                u32 h = 0;
+#pragma unroll
+                for (int i = 0; i < NSRC; ++i) {
+                    acc = mad_wide(y0[i][e], (u32)c[i], acc);
+                    h = mad_lo32(y0[i][e], (u32)(c[i] >> 32), h);
+                    h = mad_lo32(y1[i][e], (u32)c[i], h);
+                }
+                acc = mad_wide((u32)tb, (u32)npsh, acc);
+                h = mad_lo32((u32)tb, (u32)(npsh >> 32), h);
+                h = mad_lo32((u32)(tb >> 32), (u32)npsh, h);
+                const u64 r1 = acc + ((u64)h << 32);
+                const u64 t2 = (u64)__double_as_longlong(__fma_rd(__ull2double_rd(r1), pinvd, 4503599627370496.0));
+                u64 r2 = mad_wide((u32)t2, (u32)np, r1 + c52);
+                u32 h2 = mad_lo32((u32)t2, (u32)(np >> 32), (u32)(t2 >> 32) * (u32)np);
+                r2 += (u64)h2 << 32;
+                res[e] = cred(r2, pj);
+            }
+            *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N) = make_ulonglong2(res[0], res[1]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) fanout_kernel(const FanoutArgs a) {
     const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
     const int bt = blockIdx.y;
@@ -311,6 +429,17 @@ int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
             case 2: modup_fp_kernel<2><<<fgrid, 128, 0, st>>>(a); break;
             case 3: modup_fp_kernel<3><<<fgrid, 128, 0, st>>>(a); break;
             default: modup_fp_kernel<4><<<fgrid, 128, 0, st>>>(a); break;
+        }
+        lg_g_launches += 1;
+        return 0;
+    }
+    if (a.fast == 3 && !no_fp && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
+        dim3 fgrid((a.N / 2 + 127) / 128, batch);
+        switch (a.nsrc) {
+            case 1: modup_fp2_kernel<1><<<fgrid, 128, 0, st>>>(a); break;
+            case 2: modup_fp2_kernel<2><<<fgrid, 128, 0, st>>>(a); break;
+            case 3: modup_fp2_kernel<3><<<fgrid, 128, 0, st>>>(a); break;
+            default: modup_fp2_kernel<4><<<fgrid, 128, 0, st>>>(a); break;
         }
         lg_g_launches += 1;
         return 0;

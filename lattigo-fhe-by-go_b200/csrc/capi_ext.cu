@@ -19,6 +19,7 @@ int ModUpDev::build(const u64* Q, int nq, const u64* P, int np) {
     ndst = np;
     small = true;
     hsrc.assign(Q, Q + nq);
+    hdst.assign(P, P + np);
     for (int i = 0; i < nq; ++i) small = small && (Q[i] >> 61) == 0;
     for (int j = 0; j < np; ++j) small = small && (P[j] >> 61) == 0;
     std::vector<u64> sQ(Q, Q + nq), sQinv(nq), vqib(nq), vqispj((size_t)nq * np), vqpj((size_t)np * (nq + 1));
@@ -93,7 +94,7 @@ int lgi_modup_launch(const ModUpDev& m, u64 N, int batch, const u64* in, size_t 
     a.ndst[0] = ndst;
     a.tgt0[0] = tgt0;
     a.copy_out = nullptr;
-    a.fast = m.fast_level(a.nsrc);
+    a.fast = m.fast_level(a.nsrc, &a.fp_shift);
     if (lg_launch_modup(a, batch, st) != 0) {
         lg_set_error("modUpExact: too many source limbs (%d)", nsrc);
         return LG_ERR_ARG;
@@ -350,7 +351,7 @@ int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u
     a.ndst[1] = d->nP;
     a.tgt0[1] = d->nQ;
     a.copy_out = nullptr;
-    a.fast = m.fast_level(a.nsrc);
+    a.fast = m.fast_level(a.nsrc, &a.fp_shift);
     if (lg_launch_modup(a, batch, st) != 0) {
         lg_set_error("Decompose: too many source limbs");
         return LG_ERR_ARG;

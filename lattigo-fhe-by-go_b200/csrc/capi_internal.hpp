@@ -104,14 +104,26 @@ struct ModUpDev {
     int nsrc = 0, ndst = 0;
     bool small = false;  // all moduli below 2^61
     std::vector<u64> hsrc;  // host copy of the source moduli
+    std::vector<u64> hdst;  // ... and of the target moduli
     // kernel choice for the first `n` sources: 0 generic, 1 modup_fast_kernel (all moduli below 2^61), 2 modup_fp_kernel
-    // (additionally the source moduli sum to less than 2^48, see basisext.cu)
-    int fast_level(int n) const {
+    // (additionally the source moduli sum to less than 2^48), 3 modup_fp2_kernel with *shift = SH (sum below 2^(50+SH)
+    // and the first remainder, below (2^SH + 8 * 2^-52 * sum + 2) * p, fits 64 bits for every target p); see basisext.cu
+    int fast_level(int n, int* shift = nullptr) const {
+        if (shift) *shift = 0;
         if (!small) return 0;
         if (n > 4) return 1;
         unsigned __int128 sum = 0;
         for (int i = 0; i < n && i < (int)hsrc.size(); ++i) sum += hsrc[i];
-        return sum < ((unsigned __int128)1 << 48) ? 2 : 1;
+        if (sum < ((unsigned __int128)1 << 48)) return 2;
+        int sh = 0;
+        while ((sum >> (50 + sh)) != 0) ++sh;
+        if (sh > 11) return 1;
+        const unsigned __int128 bound = ((unsigned __int128)1 << sh) + (sum >> 49) + 3;
+        u64 pmax = 0;
+        for (u64 p : hdst) pmax = p > pmax ? p : pmax;
+        if (bound * pmax >= ((unsigned __int128)1 << 64)) return 1;
+        if (shift) *shift = sh;
+        return 3;
     }
     DevArray<u64> srcQ, srcQinv, qib, qispj, qpjinv, dstQ, dstQinv, dstU0;
     ModUpTables M;

@@ -173,7 +173,7 @@ int decompose_range(const lg_decomposer* d, int level, int crt, int batch, const
     a.out_bs[1] = d_bs;
     a.ndst[1] = p.n();
     a.tgt0[1] = d->nQ + p.b;
-    a.fast = m.fast_level(a.nsrc);
+    a.fast = m.fast_level(a.nsrc, &a.fp_shift);
     LG_REQUIRE(lg_launch_modup(a, batch, st) == 0, "Decompose: too many source limbs");
     LG_LAUNCH_CHECK();
     return LG_OK;
@@ -279,7 +279,7 @@ int switch_keys_sharded(lg_ckks_eval* e, const lg_comm* c, int level, int batch,
         a.out_bs[0] = t_bs;
         a.ndst[0] = myq.n();
         a.tgt0[0] = myq.b;
-        a.fast = e->ext->pq.fast_level(a.nsrc);
+        a.fast = e->ext->pq.fast_level(a.nsrc, &a.fp_shift);
         LG_REQUIRE(lg_launch_modup(a, 2 * batch, st) == 0, "modUpExact: too many source limbs");
         LG_LAUNCH_CHECK();
         u64* t0 = tmp.d + (size_t)myq.b * N;

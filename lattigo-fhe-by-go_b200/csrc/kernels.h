@@ -181,7 +181,9 @@ struct ModUpArgs {
     // "p1.Coeffs[i+p0idxst][x] = p0.Coeffs[i+p0idxst][x]")
     u64* copy_out;
     size_t copy_bs;
-    int fast;            // 1: every modulus is below 2^61 (modup_fast_kernel); 2: and the sources sum below 2^48 (modup_fp_kernel)
+    int fast;            // 1: every modulus is below 2^61 (modup_fast_kernel); 2: and the sources sum below 2^48 (modup_fp_kernel);
+                         // 3: two-step FP64 quotient at granularity 2^fp_shift (modup_fp2_kernel)
+    int fp_shift;
 };
 int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st);
 

@@ -458,23 +458,29 @@ def test_ntt_zero_and_sparse_inputs(lg, logN):
         assert np.array_equal(got[b], octx.invntt(np.ascontiguousarray(a[b]))), ("inv", b)
 
 
-@pytest.mark.parametrize("src_bits,nsrc", [(45, 4), (45, 3), (34, 2), (45, 1), (46, 3)], ids=["4x45", "3x45", "2x34", "1x45", "3x46"])
-@pytest.mark.parametrize("dst_bits", [[60, 60, 55, 45, 34], [36, 59]], ids=["wide", "narrow"])
-def test_modup_fp64_quotient_path(lg, src_bits, nsrc, dst_bits):
-    """modup_fp_kernel (csrc/basisext.cu): sources summing below 2^48 take the FP64-quotient basis extension.
-    Besides random residues, the inputs are built so that every y_i = MRed(a_i, qibMont_i) sits at the ends of its
-    range (0, 1, q_i - 1, q_i - 2, and mixed), where the quotient estimate and the correction index v are extreme;
-    bit-exact against the oracle's modUpExact (ring_basis_extension.go:352-393)."""
+@pytest.mark.parametrize("src", [[45] * 4, [45] * 3, [34, 34], [45], [46] * 3, [55] * 4, [55, 45, 45, 45], [55, 55], [49] * 3, [56]],
+                         ids=["4x45", "3x45", "2x34", "1x45", "3x46", "4x55", "55+3x45", "2x55", "3x49", "1x56"])
+@pytest.mark.parametrize("dst_bits", [[60, 60, 55, 45, 34], [36, 59], [55, 45, 45, 34]], ids=["wide", "narrow", "ckks"])
+def test_modup_fp64_quotient_path(lg, src, dst_bits):
+    """modup_fp_kernel / modup_fp2_kernel (csrc/basisext.cu): sources summing below 2^48 take the FP64-quotient basis
+    extension, wider ones its two-step variant when the first remainder fits 64 bits for every target (e.g. the 55-bit
+    special primes of a ModDown onto 45/55-bit targets; the 60-bit targets of the "wide" set send them back to the integer
+    kernel).  Besides random residues, the inputs are built so that every y_i = MRed(a_i, qibMont_i) sits at the ends of
+    its range (0, 1, q_i - 1, q_i - 2, q_i / 2 and mixtures), where the quotient estimates and the correction index v are
+    extreme; bit-exact against the oracle's modUpExact (ring_basis_extension.go:352-393)."""
     logN = 10
     N = 1 << logN
-    Qm = orc.generate_ntt_primes(src_bits, logN, nsrc)
+    nsrc = len(src)
+    Qm = []
+    for b in src:
+        Qm.append([p for p in orc.generate_ntt_primes(b, logN, nsrc + 1) if p not in Qm][0])
     Pm = []
     for b in dst_bits:
-        Pm.append([p for p in orc.generate_ntt_primes(b, logN, len(dst_bits) + nsrc) if p not in Qm and p not in Pm][0])
+        Pm.append([p for p in orc.generate_ntt_primes(b, logN, len(dst_bits) + nsrc + 1) if p not in Qm and p not in Pm][0])
     oe = orc.Extender(orc.Context(N, Qm), orc.Context(N, Pm))
     cQ, cP = lg.ring.NewContextWithParams(N, Qm), lg.ring.NewContextWithParams(N, Pm)
     be = lg.ring.NewFastBasisExtender(cQ, cP)
-    rng = np.random.default_rng(src_bits * 10 + nsrc)
+    rng = np.random.default_rng(sum(src) * 10 + nsrc)
     a = np.stack([rng.integers(0, q, size=N, dtype=np.uint64) for q in Qm])
     Qbig = 1
     for q in Qm:
