@@ -82,6 +82,13 @@ int lgi_ring_build_device(lg_ring* r) {
     LG_TRY(r->d_psi.upload(r->psi));
     LG_TRY(r->d_psi_inv.upload(r->psi_inv));
     LG_TRY(r->d_ninv.upload(r->ninv));
+    if (!r->rescale.empty()) {
+        std::vector<u64> neg(r->rescale.size());
+        for (int j = 1; j < r->nl; ++j)
+            for (int i = 0; i < j; ++i) neg[(size_t)j * (j - 1) / 2 + i] = r->q[i] - (((r->q[j] - 1) >> 1) % r->q[i]);
+        LG_TRY(r->d_rescale.upload(r->rescale));
+        LG_TRY(r->d_phalfneg.upload(neg));
+    }
     // twiddles of the fast transforms: psi / psi^-1 / N^-1 out of Montgomery form and their Shoup constants
     // (derived from the reference's tables, so the root choice stays the reference's)
     auto shoup_tables = [&](const std::vector<u64>& mont, DevArray<u64>& dw, DevArray<u64>& dws, DevArray<u64>* dwd) -> int {
@@ -844,11 +851,13 @@ int lgi_div_by_last_modulus(const lg_ring* r, int nl, int batch, u64* p0, size_t
         NttBcast bc;
         memset(&bc, 0, sizeof(bc));
         bc.enabled = 1;
-        bc.round = round ? 1 : 0;
-        bc.plast = r->q[level];
+        const size_t row = (size_t)level * (level - 1) / 2;
         if (round) {
-            bc.phalf = (r->q[level] - 1) >> 1;  // :82
-            for (int i = 0; i < level; ++i) bc.add[i] = r->q[i] - (bc.phalf % r->q[i]);  // :97 pHalfNegQi
+            // :82-88 once, in place on the last limb as the reference does: last = CRed(last + pHalf, q_last)
+            const u64 phalf = (r->q[level] - 1) >> 1;
+            LimbMap m{1 << 30, level, 0};
+            LG_TRY(lgi_ew(EW_ADD_SCALAR, r, m, 1, batch, last, bs, nullptr, 0, last, bs, &phalf, 1, st));
+            bc.add = r->d_phalfneg.d + row;  // :97 pHalfNegQi
         }
         NttTail t;
         memset(&t, 0, sizeof(t));
@@ -857,7 +866,7 @@ int lgi_div_by_last_modulus(const lg_ring* r, int nl, int batch, u64* p0, size_t
         t.a[0] = p0;
         t.out[0] = p0;
         t.a_bs[0] = t.out_bs[0] = bs;
-        for (int i = 0; i < level; ++i) t.s[i] = r->rescale_param(level, i);
+        t.s = r->d_rescale.d + row;  // rescaleParams[level-1][.]
         return lgi_ntt(r, limb_map_identity(), level, batch, last, bs, tmp.d, tbs, false, 0, 0, st, false, &t, &bc);
     }
     FanoutArgs f;

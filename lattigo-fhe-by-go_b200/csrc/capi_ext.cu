@@ -149,7 +149,7 @@ int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* 
         t.a_bs[0] = p1Q_bs;
         t.out[0] = p2;
         t.out_bs[0] = p2_bs;
-        for (int i = 0; i < nl; ++i) t.s[i] = e->moddown_pq[i];
+        t.s = e->d_moddown_pq.d;
         return lgi_ntt(Q, limb_map_identity(), nl, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st, false, &t);
     }
     if (ntt) LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
@@ -193,7 +193,7 @@ int lgi_moddown_pair_ntt(const lg_extender* e, int level, int batch, u64* acc0, 
         t.out[1] = out1;
         t.out_bs[0] = out0_bs;
         t.out_bs[1] = out1_bs;
-        for (int i = 0; i < nl; ++i) t.s[i] = e->moddown_pq[i];
+        t.s = e->d_moddown_pq.d;
         return lgi_ntt(Q, limb_map_identity(), nl, 2 * batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st, false, &t);
     }
     if (ntt) LG_TRY(lgi_ntt(Q, limb_map_identity(), nl, 2 * batch, tmp.d, tbs, tmp.d, tbs, false, 0, 0, st));
@@ -214,6 +214,7 @@ int lg_extender_create(const lg_ring* ringQ, const lg_ring* ringP, lg_extender**
     LG_TRY(e->qp.build(ringQ->q.data(), ringQ->nl, ringP->q.data(), ringP->nl));
     LG_TRY(e->pq.build(ringP->q.data(), ringP->nl, ringQ->q.data(), ringQ->nl));
     e->moddown_pq = gen_moddown(ringQ, ringP);
+    LG_TRY(e->d_moddown_pq.upload(e->moddown_pq));
     e->moddown_qp = gen_moddown(ringP, ringQ);
     *out = e.release();
     return LG_OK;

@@ -80,6 +80,8 @@ struct lg_ring {
     int nl = 0;
     std::vector<u64> q, bred, mred, ninv, psi, psi_inv, rescale;  // host copies
     DevArray<u64> d_q, d_qinv, d_bred, d_psi, d_psi_inv, d_ninv, d_psi_w, d_psi_ws, d_psi_inv_w, d_psi_inv_ws, d_ninv_w, d_psi_wd;
+    // rescaleParams[j-1][i] and pHalfNegQi = q_i - ((q_j - 1)/2 mod q_i) (ring_scaling.go:82,:97), both triangular [j(j-1)/2 + i]
+    DevArray<u64> d_rescale, d_phalfneg;
     RingTables T;
     u64 rescale_param(int j, int i) const { return rescale[(size_t)j * (j - 1) / 2 + i]; }  // rescaleParams[j-1][i]
 };
@@ -135,6 +137,7 @@ struct lg_extender {
     const lg_ring* P = nullptr;
     ModUpDev qp, pq;
     std::vector<u64> moddown_pq;  // per Q limb: MForm(P^-1 mod q_i)
+    DevArray<u64> d_moddown_pq;
     std::vector<u64> moddown_qp;  // per P limb: MForm(Q^-1 mod p_j)
 };
 

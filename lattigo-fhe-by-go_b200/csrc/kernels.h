@@ -21,15 +21,14 @@ struct NttTail {
     const u64* a[2];
     u64* out[2];
     size_t a_bs[2], out_bs[2];
-    u64 s[LG_MAX_LIMBS];
+    const u64* s;  // device array, one scalar per data limb (kept out of the kernel parameters: every NTT CTA loads those)
 };
 // Broadcast input of the forward transform's first phase (logN >= 12): every data limb j transforms the same source
-// limb, x_j = f(v) + add[j] with f(v) = CRed(v + phalf, plast) when round, else v -- the rescaling's "last limb
-// (+ pHalf) to every other limb" (ring_scaling.go:17-28, :80-103) without materialising the copies.
+// limb plus a per-limb constant, x_j = v + add[j] (unreduced) -- the rescaling's "last limb to every other limb"
+// (ring_scaling.go:17-28, :80-103, add = pHalfNegQi or nothing) without materialising the copies.
 struct NttBcast {
-    int enabled, round;
-    u64 phalf, plast;
-    u64 add[LG_MAX_LIMBS];
+    int enabled;
+    const u64* add;  // device array per data limb, or nullptr
 };
 struct NttArgs {
     RingTables T;

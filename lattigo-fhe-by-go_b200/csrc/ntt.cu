@@ -291,10 +291,10 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
     const u64* in = s.in + colg + g * 256;
 #pragma unroll
     for (int r = 0; r < 16; ++r) x[r] = in[r * G * 256];
-    if (a.bcast.enabled) {  // ring_scaling.go:83-88 / :99-103: (last limb + pHalf mod q_last) + (q_j - pHalf mod q_j), unreduced
-        const u64 add = a.bcast.add[blockIdx.z];
+    if (a.bcast.enabled && a.bcast.add != nullptr) {  // ring_scaling.go:99-103: + (q_j - pHalf mod q_j), unreduced
+        const u64 add = __ldg(a.bcast.add + blockIdx.z);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) x[r] = (a.bcast.round ? cred(x[r] + a.bcast.phalf, a.bcast.plast) : x[r]) + add;
+        for (int r = 0; r < 16; ++r) x[r] += add;
     }
     fill_strided_tw<L, MODE == M_LITERAL>(tws_sm, c);
     if (MODE != M_LITERAL) {
@@ -426,7 +426,7 @@ LG_DEV void prefetch_warp_tile_rows(u64* buf, const u64* __restrict__ src_tile) 
 // Single tile buffer (48 KiB of shared memory per CTA, 4 CTAs/SM): the fetch of entry i+1 is issued as soon
 // as entry i has left the buffer for good (after the exchange), and lands during the second register block.
 #define PIPE_SMEM_WORDS (2048 + 30 * CONTIG_THREADS + 8 * 32)
-template <bool FWD, int MODE>
+template <bool FWD, int MODE, bool TAIL>
 LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int b0, int nb, u64* smem) {
     const u32 N = a.T.N;
     const int j = blockIdx.z;
@@ -464,13 +464,13 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
             __syncwarp();
             if (i + 1 < nb) prefetch_warp_tile(tilebuf, src + (size_t)(i + 1) * a.in_bstride);
             fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS);
-            if (a.tail.enabled) {
+            if (TAIL) {
                 // the caller's (x - NTT(y)) * s_j tail (+ add) on the canonical transform, straight from the registers
                 const int bi = b0 + i, set = bi >= a.tail.split ? 1 : 0;
                 const size_t bb = (size_t)(bi - (set ? a.tail.split : 0));
                 const u64* ta = a.tail.a[set] + bb * a.tail.a_bs[set] + (size_t)j * N + e0;
                 u64* to = a.tail.out[set] + bb * a.tail.out_bs[set] + (size_t)j * N + e0;
-                const u64 sj = a.tail.s[j];
+                const u64 sj = __ldg(a.tail.s + j);
                 const bool add = a.tail.add[set] != 0;
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
@@ -518,7 +518,9 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
     }
 }
 
-template <bool FWD, bool LITERAL>
+// TAIL: the store is the caller's (x - NTT(y)) * s_j epilogue (NttTail); a separate instantiation, so the plain
+// transform keeps its register budget
+template <bool FWD, bool LITERAL, bool TAIL = false>
 __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttArgs a, int batch, int bpc) {
     extern __shared__ __align__(16) u64 ks_smem[];
     const int j = blockIdx.z;
@@ -541,13 +543,13 @@ __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttAr
         mode = flagged ? M_LITERAL : inv_mode(lc.q);
     }
     if (mode == M_F64)
-        contig_pipe_body<FWD, FWD ? M_F64 : M_FREE>(a, lc, tl, b0, nb, ks_smem);
+        contig_pipe_body<FWD, FWD ? M_F64 : M_FREE, TAIL>(a, lc, tl, b0, nb, ks_smem);
     else if (mode == M_FREE)
-        contig_pipe_body<FWD, M_FREE>(a, lc, tl, b0, nb, ks_smem);
+        contig_pipe_body<FWD, M_FREE, TAIL>(a, lc, tl, b0, nb, ks_smem);
     else if (mode == M_LAZY)
-        contig_pipe_body<FWD, M_LAZY>(a, lc, tl, b0, nb, ks_smem);
+        contig_pipe_body<FWD, M_LAZY, TAIL>(a, lc, tl, b0, nb, ks_smem);
     else
-        contig_pipe_body<FWD, M_LITERAL>(a, lc, tl, b0, nb, ks_smem);
+        contig_pipe_body<FWD, M_LITERAL, TAIL>(a, lc, tl, b0, nb, ks_smem);
 }
 
 // LAZYACC: beta * 2q fits 64 bits, so the products are accumulated unreduced (MRedConstant, in (0,2q)).
@@ -804,7 +806,7 @@ void launch_strided_any(int L, bool fwd, bool literal, const NttArgs& a, dim3 gr
 }
 
 // entries per CTA of the pipelined contiguous phase: as many as keep about two waves of CTAs in flight
-template <bool FWD, bool LITERAL>
+template <bool FWD, bool LITERAL, bool TAIL>
 void launch_contig_pipe_t(const NttArgs& a, int nlimbs, int batch, cudaStream_t st) {
     const int tiles = (int)(a.T.N / CONTIG_TILE);
     int bpc = batch < 8 ? batch : 8;
@@ -812,20 +814,25 @@ void launch_contig_pipe_t(const NttArgs& a, int nlimbs, int batch, cudaStream_t 
     if (a.skip_alpha > 0)
         while (a.skip_div % bpc) --bpc;
     const size_t smem = PIPE_SMEM_WORDS * sizeof(u64);
-    cudaFuncSetAttribute(ntt_contig_pipe<FWD, LITERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ntt_contig_pipe<FWD, LITERAL><<<dim3((batch + bpc - 1) / bpc, tiles, nlimbs), CONTIG_THREADS, smem, st>>>(a, batch, bpc);
+    cudaFuncSetAttribute(ntt_contig_pipe<FWD, LITERAL, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ntt_contig_pipe<FWD, LITERAL, TAIL><<<dim3((batch + bpc - 1) / bpc, tiles, nlimbs), CONTIG_THREADS, smem, st>>>(a, batch, bpc);
 }
 void launch_contig_pipe(bool fwd, bool literal, const NttArgs& a, int nlimbs, int batch, cudaStream_t st) {
-    if (fwd) {
+    if (fwd && a.tail.enabled) {
         if (literal)
-            launch_contig_pipe_t<true, true>(a, nlimbs, batch, st);
+            launch_contig_pipe_t<true, true, true>(a, nlimbs, batch, st);
         else
-            launch_contig_pipe_t<true, false>(a, nlimbs, batch, st);
+            launch_contig_pipe_t<true, false, true>(a, nlimbs, batch, st);
+    } else if (fwd) {
+        if (literal)
+            launch_contig_pipe_t<true, true, false>(a, nlimbs, batch, st);
+        else
+            launch_contig_pipe_t<true, false, false>(a, nlimbs, batch, st);
     } else {
         if (literal)
-            launch_contig_pipe_t<false, true>(a, nlimbs, batch, st);
+            launch_contig_pipe_t<false, true, false>(a, nlimbs, batch, st);
         else
-            launch_contig_pipe_t<false, false>(a, nlimbs, batch, st);
+            launch_contig_pipe_t<false, false, false>(a, nlimbs, batch, st);
     }
 }
 
