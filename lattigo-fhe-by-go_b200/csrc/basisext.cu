@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
 }
 
 // Two-step variant for wider sources (e.g. the 55-bit special primes of a ModDown, or a digit holding the first
-// prime): sum_i q_i < 2^(50+SH).  The first quotient is taken at a granularity of 2^SH -- t = RD(s * (1/p) + 2^(52+SH))
+// prime): sum_i q_i < 2^(52+SH).  The first quotient is taken at a granularity of 2^SH -- t = RD(s * (1/p) + 2^(52+SH))
 // holds qh1 / 2^SH in its mantissa, s <= S being the all-rounded-down binary64 image of S = sum_i y_i*C_ij (the y_i
 // themselves rounded down) -- so that r1 = S + K_v - qh1*p lies in [0, (2^SH + 8 * 2^-52 * sum_i q_i + 2) * p) (eight downward roundings), which
 // the host checks to be below 2^64 for every target before choosing this kernel.  A second quotient on r1 (converted

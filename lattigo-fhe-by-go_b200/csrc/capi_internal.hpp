@@ -108,7 +108,7 @@ struct ModUpDev {
     std::vector<u64> hsrc;  // host copy of the source moduli
     std::vector<u64> hdst;  // ... and of the target moduli
     // kernel choice for the first `n` sources: 0 generic, 1 modup_fast_kernel (all moduli below 2^61), 2 modup_fp_kernel
-    // (additionally the source moduli sum to less than 2^48), 3 modup_fp2_kernel with *shift = SH (sum below 2^(50+SH)
+    // (additionally the source moduli sum to less than 2^48), 3 modup_fp2_kernel with *shift = SH (sum below 2^(52+SH)
     // and the first remainder, below (2^SH + 8 * 2^-52 * sum + 2) * p, fits 64 bits for every target p); see basisext.cu
     int fast_level(int n, int* shift = nullptr) const {
         if (shift) *shift = 0;
@@ -118,7 +118,7 @@ struct ModUpDev {
         for (int i = 0; i < n && i < (int)hsrc.size(); ++i) sum += hsrc[i];
         if (sum < ((unsigned __int128)1 << 48)) return 2;
         int sh = 0;
-        while ((sum >> (50 + sh)) != 0) ++sh;
+        while (((sum + 1) >> (52 + sh)) != 0) ++sh;  // the first quotient, below sum + 1, must fit the mantissa at 2^sh
         if (sh > 11) return 1;
         const unsigned __int128 bound = ((unsigned __int128)1 << sh) + (sum >> 49) + 3;
         u64 pmax = 0;

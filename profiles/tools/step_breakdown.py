@@ -11,8 +11,15 @@ def main(path, first="tensor_kernel"):
     idx = [i for i, n in enumerate(names) if n[0].startswith(first)]
     s = idx[-1]
     e = len(names)
-    # the step ends where the NTT-rate loop begins: stop at the last ew_kernel after s
-    last = max(i for i, n in enumerate(names) if i >= s and n[0].startswith("ew_kernel"))
+    # One MulRelin+Rescale = tensor ... key switch ... ModDown ... two rescalings.  Since the tails ride on the forward
+    # transform, the step ends with the third forward contiguous-phase launch after the tensor product (ModDown pair,
+    # rescale c0, rescale c1); older lists end with the last ew_kernel before the NTT-rate loop.
+    fwd = [i for i, n in enumerate(names) if i > s and n[0].startswith("ntt_contig_pipe<1")]
+    tails = [i for i, n in enumerate(names) if i > s and n[0].startswith("ew_kernel<3")]
+    if len(fwd) >= 3 and (not tails or tails[0] > fwd[2]):
+        last = fwd[2]
+    else:
+        last = max(i for i, n in enumerate(names) if i >= s and n[0].startswith("ew_kernel"))
     step = names[s:last + 1]
     tot = sum(n[2] for n in step)
     print("step: %d launches, %.1f us (serialised, cold cache)" % (len(step), tot / 1e3))
