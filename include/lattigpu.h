@@ -244,7 +244,10 @@ int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
 /* RotateHoisted :1252-1289.  lg_ckks_hoist is the precomputation (:1258-1273): InvNTT of value[1] and
  * decomposeAndSplitNTT of every digit, kept on the device in the returned handle; lg_ckks_switch_key_hoisted
  * is switchKeyHoisted (:1291-1392, ct0 != ctOut branch) for one rotation: g = permuteNTTLeftIndex[k],
- * key = evakeyRotColLeft[k].  out0 must not alias c0 (PermuteNTTWithIndex is not in place). */
+ * key = evakeyRotColLeft[k].  out0 must not alias c0 (PermuteNTTWithIndex is not in place).
+ * The handle's device memory is allocated and released in stream order on the stream given to lg_ckks_hoist:
+ * lg_hoisted_destroy may be called right after the last rotation was issued on that stream; rotations issued on
+ * another stream must have completed (lg_stream_sync) before it. */
 int lg_ckks_hoist(lg_ckks_eval* e, int level, const lg_poly* c1, lg_hoisted** out, lg_stream_t s);
 int lg_ckks_switch_key_hoisted(lg_ckks_eval* e, const lg_hoisted* h, const lg_poly* c0, const lg_galois* g, const lg_swk* k,
                                lg_poly* out0, lg_poly* out1, lg_stream_t s);

@@ -158,7 +158,8 @@ struct lg_swk {
 
 // RotateHoisted precomputation: the NTT-domain digits of value[1] (ckks/evaluator.go:1258-1273)
 struct lg_hoisted {
-    u64* d = nullptr;  // [beta][batch][level+1+nP][N]
+    u64* d = nullptr;  // [beta][batch][level+1+nP][N], allocated and freed in stream order on st
+    cudaStream_t st = nullptr;
     u64 N = 0;
     int level = 0, beta = 0, batch = 0, nd = 0;
     size_t d_bs = 0, d_ds = 0;

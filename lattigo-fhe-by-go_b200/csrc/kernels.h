@@ -72,6 +72,7 @@ struct KsFusedArgs {
     size_t acc_bs;
     int beta, alpha, nl;  // digit i owns data limbs [i*alpha, min((i+1)*alpha, nl))
     int limb0;            // index of the launch's first data limb (limb-sharded launches; pointers are pre-offset)
+    int acc64;            // 1 = never take the 96-bit accumulators (LATTIGPU_KS_ACC64=1: A/B and cross-check)
 };
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st);
 

@@ -425,6 +425,12 @@ LG_DEV void prefetch_warp_tile_rows(u64* buf, const u64* __restrict__ src_tile) 
 // fetched with cp.async while entry i is transformed (same structure as the key-switch digit loop).
 // Single tile buffer (48 KiB of shared memory per CTA, 4 CTAs/SM): the fetch of entry i+1 is issued as soon
 // as entry i has left the buffer for good (after the exchange), and lands during the second register block.
+#ifndef KS_MINB
+#define KS_MINB 3
+#endif
+#ifndef KS_KEYPREFETCH
+#define KS_KEYPREFETCH 0
+#endif
 #define PIPE_SMEM_WORDS (2048 + 30 * CONTIG_THREADS + 8 * 32)
 template <bool FWD, int MODE, bool TAIL>
 LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int b0, int nb, u64* smem) {
@@ -552,9 +558,66 @@ __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttAr
         contig_pipe_body<FWD, M_LITERAL, TAIL>(a, lc, tl, b0, nb, ks_smem);
 }
 
-// LAZYACC: beta * 2q fits 64 bits, so the products are accumulated unreduced (MRedConstant, in (0,2q)).
-template <int MODE, bool LAZYACC>
-LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64* smem) {
+// ---- key-switch accumulators ------------------------------------------------------------------------------
+// The reference adds MRed(evk, d) terms lazily and ends canonical (ckks/evaluator.go:1515-1552), i.e. it returns
+// (sum_i evk_i * d_i) * 2^-64 mod q.  Montgomery reduction is linear, so the same word comes out of ONE reduction
+// of the exact integer sum of the products.  For the FP64-butterfly limbs (q < 3*2^44, transform values below 2^52)
+// the digit value is first brought below 3q with one round-down DFMA (quotient by q as in shoup_f64, w = 1), the
+// product then stays below 3q^2 and beta of them fit a 96-bit accumulator: 3 wide + 1 narrow multiply and two adds
+// per term instead of the 11 multiplies of a Montgomery reduction per term.  Key words may be any 64-bit value (the
+// reference's MRed is total): the kernel ORs their high halves on the way and a CTA that saw a word of more bits
+// than q repeats its tile on the 64-bit path, which is exact for every word.
+enum { ACC_CRED = 0, ACC_LAZY64 = 1, ACC_WIDE96 = 2 };
+
+// (a2 : A) += k * x, caller guarantees the running sum stays below 2^96
+LG_DEV void mac96(u64& A, u32& a2, u64 k, u64 x) {
+    const u32 k0 = (u32)k, k1 = (u32)(k >> 32), x0 = (u32)x, x1 = (u32)(x >> 32);
+    u64 h = mul_wide(k1, x0);
+    h = mad_wide(k0, x1, h);
+    const u32 hl = (u32)h, hh = mad_lo32(k1, x1, (u32)(h >> 32));
+    asm("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\t"
+        "mad.lo.cc.u32 l, %2, %3, l;\n\tmadc.hi.cc.u32 h, %2, %3, h;\n\taddc.u32 %1, %1, 0;\n\t"
+        "add.cc.u32 h, h, %4;\n\taddc.u32 %1, %1, %5;\n\tmov.b64 %0, {l, h};\n\t}"
+        : "+l"(A), "+r"(a2)
+        : "r"(k0), "r"(x0), "r"(hl), "r"(hh));
+}
+// x < 2^52 -> x - Qh*q in [0,3q), Qh = floor(x/q) - {0,1,2} from one round-down DFMA (see shoup_f64; Qh = -1 for
+// tiny x arrives in two's complement and adds q)
+LG_DEV u64 reduce_f64(u64 x, double qd1, double cq1, u64 nq) {
+    const u32 b0 = (u32)x, b1 = (u32)(x >> 32);
+    const double qd = __fma_rd(__hiloint2double((int)(b1 | 0x43300000u), (int)b0), qd1, cq1);
+    const u32 h0 = (u32)__double2loint(qd), h1 = (u32)__double2hiint(qd) - 0x43300000u;
+    const u32 n0 = (u32)nq, n1 = (u32)(nq >> 32);
+    const u64 t = mad_wide(h0, n0, x);
+    u32 th = (u32)(t >> 32);
+    th = mad_lo32(h0, n1, th);
+    th = mad_lo32(h1, n0, th);
+    return ((u64)th << 32) | (u32)t;
+}
+// Montgomery reduction of the 96-bit sum (a2 < 2^32 < q): canonical
+LG_DEV u64 mred96(u64 A, u32 a2, u64 q, u64 qinv) {
+    const u64 H = mul_hi(mul_lo(A, qinv), q);
+    return cred((u64)a2 - H + q, q);
+}
+
+// the thread's 16 words of evk[i][0] and evk[i][1]
+LG_DEV void ks_load_keys(u64 (&k0)[16], u64 (&k1)[16], const u64* key, size_t hs) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        u64 v[4], w[4];
+        ld256_nc(v, key + 4 * h);
+        ld256_nc(w, key + hs + 4 * h);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            k0[4 * h + e] = v[e];
+            k1[4 * h + e] = w[e];
+        }
+    }
+}
+
+// ACC_LAZY64: beta * 2q fits 64 bits, so the products are accumulated unreduced (MRedConstant, in (0,2q)).
+template <int MODE, int ACC>
+LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64* smem) {
     const u32 N = a.T.N;
     const int j = blockIdx.z, b = blockIdx.x;
     const u64 q = lc.q, qinv = lc.qinv;
@@ -573,20 +636,38 @@ LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64
 
     contig_fill_tw<MODE>(c, N, segbase, cc, twp, twseg);  // twiddles of the tile, once for all digits
 
+    // floor(2^64/q) is the high Barrett word (modular_reduction.go:97-106); rounded down it is the Shoup double of w = 1
+    const double qd1 = (ACC == ACC_WIDE96) ? __ull2double_rd(lc.u0) * 5.421010862427522170037e-20 : 0.0;
+    const double cq1 = (ACC == ACC_WIDE96) ? shoup_cw(qd1) : 0.0;
+
     const u64* key = a.evk + (size_t)tl * N + e0;
     u64 acc0[16], acc1[16];
+    u32 top0[16], top1[16], keyhi = 0;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) acc0[r] = acc1[r] = 0;
+    for (int r = 0; r < 16; ++r) {
+        acc0[r] = acc1[r] = 0;
+        top0[r] = top1[r] = 0;
+    }
 #pragma unroll 1
     for (int i = 0; i < a.beta; ++i, key += a.evk_ds) {
         u64 x[16];
+#if KS_KEYPREFETCH == 1
+        u64 kk0[16], kk1[16];
+#endif
         u64* const buf = tilebuf + (i & 1) * 2048 + sg * 256;
         cp_async_wait_all();
         __syncwarp();
         // fetch the next digit's tile into the other buffer (all its readers passed the barrier above)
         if (i + 1 < a.beta && i + 1 != own_i)
             prefetch_warp_tile(tilebuf + ((i + 1) & 1) * 2048, din + (size_t)(i + 1) * a.d_ds);
+#if KS_KEYPREFETCH == 2
+        u64 kk0[16], kk1[16];
+        ks_load_keys(kk0, kk1, key, a.evk_hs);
+#endif
         if (i == own_i) {  // ckks/evaluator.go:1579-1584, bfv/evaluator.go:776-780
+#if KS_KEYPREFETCH == 1
+            ks_load_keys(kk0, kk1, key, a.evk_hs);
+#endif
             const u64* cx = a.cx + (size_t)b * a.cx_bs + (size_t)j * N + e0;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -594,6 +675,10 @@ LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64
                 ld256(v, cx + 4 * h);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) x[4 * h + e] = v[e];
+            }
+            if (ACC == ACC_WIDE96) {  // caller data, any 64-bit word: canonical
+#pragma unroll
+                for (int r = 0; r < 16; ++r) x[r] = bred_add(x[r], q, lc.u0);
             }
         } else {
 #pragma unroll
@@ -606,55 +691,83 @@ LG_DEV void ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < 16; ++r) x[r] = buf[16 * cc + (r ^ cc)];
+#if KS_KEYPREFETCH == 1
+            ks_load_keys(kk0, kk1, key, a.evk_hs);  // in flight during the second register block
+#endif
             fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS);
+            if (ACC == ACC_WIDE96) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) x[r] = reduce_f64(x[r], qd1, cq1, c.nq);
+            }
         }
+#if KS_KEYPREFETCH == 0
+        u64 kk0[16], kk1[16];
+        ks_load_keys(kk0, kk1, key, a.evk_hs);
+#endif
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            u64 k0[4], k1[4];
-            ld256_nc(k0, key + 4 * h);
-            ld256_nc(k1, key + a.evk_hs + 4 * h);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = 4 * h + e;
-                if (LAZYACC) {
-                    acc0[r] += mred_constant(k0[e], x[r], q, qinv);
-                    acc1[r] += mred_constant(k1[e], x[r], q, qinv);
-                } else {
-                    acc0[r] = cred(acc0[r] + mred(k0[e], x[r], q, qinv), q);
-                    acc1[r] = cred(acc1[r] + mred(k1[e], x[r], q, qinv), q);
-                }
+        for (int r = 0; r < 16; ++r) {
+            if (ACC == ACC_WIDE96) {
+                keyhi |= (u32)(kk0[r] >> 32) | (u32)(kk1[r] >> 32);
+                mac96(acc0[r], top0[r], kk0[r], x[r]);
+                mac96(acc1[r], top1[r], kk1[r], x[r]);
+            } else if (ACC == ACC_LAZY64) {
+                acc0[r] += mred_constant(kk0[r], x[r], q, qinv);
+                acc1[r] += mred_constant(kk1[r], x[r], q, qinv);
+            } else {
+                acc0[r] = cred(acc0[r] + mred(kk0[r], x[r], q, qinv), q);
+                acc1[r] = cred(acc1[r] + mred(kk1[r], x[r], q, qinv), q);
             }
         }
     }
     u64* o0 = a.acc0 + (size_t)b * a.acc_bs + (size_t)j * N + e0;
     u64* o1 = a.acc1 + (size_t)b * a.acc_bs + (size_t)j * N + e0;
+    if (ACC == ACC_WIDE96) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            acc0[r] = mred96(acc0[r], top0[r], q, qinv);
+            acc1[r] = mred96(acc1[r], top1[r], q, qinv);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            acc0[r] = bred_add(acc0[r], q, lc.u0);
+            acc1[r] = bred_add(acc1[r], q, lc.u0);
+        }
+    }
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
-        st256(o0 + 4 * h, bred_add(acc0[4 * h], q, lc.u0), bred_add(acc0[4 * h + 1], q, lc.u0),
-              bred_add(acc0[4 * h + 2], q, lc.u0), bred_add(acc0[4 * h + 3], q, lc.u0));
-        st256(o1 + 4 * h, bred_add(acc1[4 * h], q, lc.u0), bred_add(acc1[4 * h + 1], q, lc.u0),
-              bred_add(acc1[4 * h + 2], q, lc.u0), bred_add(acc1[4 * h + 3], q, lc.u0));
+        st256(o0 + 4 * h, acc0[4 * h], acc0[4 * h + 1], acc0[4 * h + 2], acc0[4 * h + 3]);
+        st256(o1 + 4 * h, acc1[4 * h], acc1[4 * h + 1], acc1[4 * h + 2], acc1[4 * h + 3]);
     }
+    return keyhi;
 }
 
 template <bool LITERAL>
-__global__ void __launch_bounds__(CONTIG_THREADS, 3) ks_fused_kernel(const KsFusedArgs a) {
+__global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const KsFusedArgs a) {
     extern __shared__ __align__(16) u64 ks_smem[];
     const int tl = a.map(blockIdx.z);
     const LimbConst lc = load_limb_const(a.T, tl);
     const int mode = LITERAL ? M_LITERAL : fwd_mode(lc.q);
     const bool lazyacc = (2 * lc.q) <= (~0ull) / (u64)a.beta;
     if (mode == M_F64) {  // q < 2^56: beta <= 64 terms below 2q always fit
-        ks_fused_body<M_F64, true>(a, lc, tl, ks_smem);
+        // beta products of a key word below 2^kb (kb = bits of q, at least 32: only the high halves are watched) and a
+        // digit value below 3q fit 96 bits
+        const int qbits = 64 - __clzll((long long)lc.q), kb = qbits < 32 ? 32 : qbits;
+        if (!a.acc64 && ((3ull * (u64)a.beta * lc.q) >> (96 - kb)) == 0) {
+            const u32 keyhi = ks_fused_body<M_F64, ACC_WIDE96>(a, lc, tl, ks_smem);
+            if (__syncthreads_or((keyhi >> (kb - 32)) != 0)) ks_fused_body<M_F64, ACC_LAZY64>(a, lc, tl, ks_smem);
+        } else {
+            ks_fused_body<M_F64, ACC_LAZY64>(a, lc, tl, ks_smem);
+        }
     } else if (mode == M_FREE) {
-        ks_fused_body<M_FREE, true>(a, lc, tl, ks_smem);
+        ks_fused_body<M_FREE, ACC_LAZY64>(a, lc, tl, ks_smem);
     } else if (mode == M_LAZY) {
         if (lazyacc)
-            ks_fused_body<M_LAZY, true>(a, lc, tl, ks_smem);
+            ks_fused_body<M_LAZY, ACC_LAZY64>(a, lc, tl, ks_smem);
         else
-            ks_fused_body<M_LAZY, false>(a, lc, tl, ks_smem);
+            ks_fused_body<M_LAZY, ACC_CRED>(a, lc, tl, ks_smem);
     } else {
-        ks_fused_body<M_LITERAL, false>(a, lc, tl, ks_smem);
+        ks_fused_body<M_LITERAL, ACC_CRED>(a, lc, tl, ks_smem);
     }
 }
 
@@ -901,13 +1014,16 @@ int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t
     if (a.T.logN < 12 || a.T.logN > 16 || a.beta < 1) return 1;
     const dim3 grid(batch, a.T.N / CONTIG_TILE, nlimbs);
     const size_t smem = KS_SMEM_WORDS * sizeof(u64);
+    KsFusedArgs k = a;
+    const char* e = getenv("LATTIGPU_KS_ACC64");  // read per call: the tests switch it inside one process
+    k.acc64 = (e && e[0] == '1') ? 1 : 0;
     // (per launch: the attribute is per device and a process may drive several)
     if (literal_ntt()) {
         cudaFuncSetAttribute(ks_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ks_fused_kernel<true><<<grid, CONTIG_THREADS, smem, st>>>(a);
+        ks_fused_kernel<true><<<grid, CONTIG_THREADS, smem, st>>>(k);
     } else {
         cudaFuncSetAttribute(ks_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ks_fused_kernel<false><<<grid, CONTIG_THREADS, smem, st>>>(a);
+        ks_fused_kernel<false><<<grid, CONTIG_THREADS, smem, st>>>(k);
     }
     lg_g_launches += 1;
     return 0;

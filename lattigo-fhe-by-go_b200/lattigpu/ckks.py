@@ -225,8 +225,7 @@ class Evaluator:
             for (index, key), out in zip(rotations, ctOuts):
                 check(lib().lg_ckks_switch_key_hoisted(self.h, h, ct0[0].h, index.h, key.h, out[0].h, out[1].h, _s(stream)))
         finally:
-            lib().lg_stream_sync(_s(stream))  # the decomposition must outlive the kernels that read it
-            lib().lg_hoisted_destroy(h)
+            lib().lg_hoisted_destroy(h)  # stream-ordered release: after the rotations issued on this stream
 
 
 def NewEvaluator(contextQ, contextP):

@@ -86,6 +86,34 @@ def test_switch_keys_in_place_all_levels(lg, params, kind):
             assert np.array_equal(g0[b], w0) and np.array_equal(g1[b], w1), level
 
 
+@pytest.mark.parametrize("params", [PN13, PN14], ids=["PN13", "PN14"])
+@pytest.mark.parametrize("keykind", ["words", "one-word"])
+def test_switch_keys_unreduced_key_words(lg, params, keykind, monkeypatch):
+    """MRed is total (modular_reduction.go:70-79): a switching key holding arbitrary 64-bit words still has a defined
+    result in the reference.  The 96-bit key-switch accumulators assume key words of at most bits(q) bits; a CTA that
+    meets a wider word must fall back to the 64-bit path and still match, as must LATTIGPU_KS_ACC64=1 on in-range keys."""
+    s = Setup(lg, params)
+    rng = np.random.default_rng(27)
+    evk = s.evk(rng)
+    if keykind == "words":
+        evk = rng.integers(0, 1 << 64, size=evk.shape, dtype=np.uint64)
+    else:  # a single out-of-range word in one tile of one limb of one digit
+        evk[s.beta - 1, 1, 1, 2049] = np.uint64((1 << 64) - 3)
+        evk[0, 0, s.nQ, 5] = np.uint64(1 << 47)
+    cx = s.ct(rng, "reduced", 2)[:, 0]
+    pcx = lg.ring.Poly.from_numpy(np.ascontiguousarray(cx))
+    for acc64 in ("0", "1"):
+        monkeypatch.setenv("LATTIGPU_KS_ACC64", acc64)
+        dk = lg.ckks.SwitchingKey(evk)
+        for level in (s.nQ - 1, s.nQ - 2):
+            p0, p1 = lg.ring.Poly(s.N, s.nQ, 2), lg.ring.Poly(s.N, s.nQ, 2)
+            s.ev.switchKeysInPlace(level, pcx, dk, p0, p1)
+            g0, g1 = p0.numpy(nl=level + 1), p1.numpy(nl=level + 1)
+            for b in range(2):
+                w0, w1 = s.oev.switch_keys_in_place(level, np.ascontiguousarray(cx[b]), evk)
+                assert np.array_equal(g0[b], w0) and np.array_equal(g1[b], w1), (level, acc64)
+
+
 @pytest.mark.parametrize("params", [PN12, PN13, SMALL3, PN14], ids=["PN12", "PN13", "alpha3", "PN14"])
 @pytest.mark.parametrize("kind", ["reduced", "words"])
 def test_mul_relin_rescale(lg, params, kind):
