@@ -2,7 +2,7 @@
 generation (CKG, dckks/publickey_gen.go:18-52), public collective key switching (PCKS,
 dckks/public_keyswitching.go:9-113), collective key switching (CKS, dckks/keyswitching.go:55-108),
 rotation-key generation (RTG, dckks/rotkey_gen.go:75-174) and the three-round relinearisation-key
-generation (RKG, dckks/relinkey_gen.go:60-223).  As in the reference the protocol logic is host code that
+generation (RKG, dckks/relinkey_gen.go:60-223) and the collective refresh (dckks/public_refresh.go:9-147).  As in the reference the protocol logic is host code that
 calls ring ops; here every ring op runs on the GPU through the C ABI.
 
 Sampling stays with the caller (the reference draws from crypto/rand on the host): GenShare takes
@@ -241,6 +241,84 @@ class RKGProtocol:
             K.MForm(round2[i][1], k1, stream=stream)
             key.append((k0, k1))
         return key
+
+
+class RefreshProtocol:
+    """dckks/public_refresh.go:9-147 over contextQ.  The ring ops run on the device; the big-integer steps of the
+    reference (ring.RandInt mask, SetCoefficientsBigint, PolyToBigint: math/big host code, ring_context.go:343-421)
+    stay host code here as well (Python integers).  One ciphertext per call (batch 1), like the reference."""
+
+    def __init__(self, contextQ):
+        self.contextQ = contextQ
+        self.tmp = contextQ.NewPoly()
+
+    def AllocateShares(self, levelStart):
+        return self.contextQ.NewPolyLvl(levelStart), self.contextQ.NewPoly()  # :38-40
+
+    def _modulus(self, nl):
+        q = 1
+        for m in self.contextQ.Modulus[:nl]:
+            q *= int(m)
+        return q
+
+    def _set_bigint(self, nl, coeffs, p):
+        """SetCoefficientsBigintLvl (ring_context.go:356-367): Euclidean residues, like big.Int.Mod"""
+        import numpy as np
+        a = np.array([[int(c) % int(q) for c in coeffs] for q in self.contextQ.Modulus[:nl]], dtype=np.uint64)
+        p.set(a)
+
+    def GenShares(self, sk, levelStart, nParties, ct1, crs, shareDecrypt, shareRecrypt, mask, e0, e1, stream=None):
+        """:43-98.  mask = the N values ring.RandInt(bound) returned (bound = Q_levelStart / (2 nParties), :48-54),
+        centred here as :57-63 do; e0 / e1 = the two gaussian samples (coefficient domain, over contextQ);
+        sk over Q (NTT + Montgomery), ct1 = ciphertext.Value()[1], crs in the NTT domain."""
+        K = self.contextQ
+        bound = self._modulus(levelStart + 1) // (2 * nParties)
+        half = bound >> 1
+        mask = [int(m) - bound if int(m) >= half else int(m) for m in mask]
+        self._set_bigint(levelStart + 1, mask, shareDecrypt)  # :66
+        self._set_bigint(K.nl, mask, shareRecrypt)  # :68
+        K.NTTLvl(levelStart, shareDecrypt, shareDecrypt, stream=stream)  # :75
+        K.NTT(shareRecrypt, shareRecrypt, stream=stream)  # :76
+        K.MulCoeffsMontgomeryAndAddLvl(levelStart, sk, ct1, shareDecrypt, stream=stream)  # :79
+        K.MulCoeffsMontgomeryAndAdd(sk, crs, shareRecrypt, stream=stream)  # :82
+        K.NTT(e0, self.tmp, stream=stream)  # SampleNTT :85
+        K.AddLvl(levelStart, shareDecrypt, self.tmp, shareDecrypt, stream=stream)
+        K.NTT(e1, self.tmp, stream=stream)  # :89
+        K.Add(shareRecrypt, self.tmp, shareRecrypt, stream=stream)
+        K.Neg(shareRecrypt, shareRecrypt, stream=stream)  # :93
+        self.tmp.Zero(stream=stream)  # :95
+
+    def Aggregate(self, share1, share2, shareOut, stream=None):
+        self.contextQ.AddLvl(share1.nlimbs - 1, share1, share2, shareOut, stream=stream)  # :101-103
+
+    def Decrypt(self, level, ct0, shareDecrypt, stream=None):
+        """:106-108 on ciphertext.Value()[0] at `level`"""
+        self.contextQ.AddLvl(level, ct0, shareDecrypt, ct0, stream=stream)
+
+    def Recode(self, level, ct0, stream=None):
+        """:111-139.  Returns value[0] grown to every limb of Q (the reference appends the missing limbs to Coeffs)."""
+        K = self.contextQ
+        nl = level + 1
+        K.InvNTTLvl(level, ct0, ct0, stream=stream)
+        a = ct0.numpy(nl=nl, stream=stream, squeeze=False)[0]
+        mods = [int(q) for q in K.Modulus[:nl]]
+        big = self._modulus(nl)
+        rec = [(big // q) * pow(big // q, -1, q) for q in mods]  # PolyToBigint, ring_context.go:384-421
+        cols = [a[i].tolist() for i in range(nl)]
+        half = big >> 1
+        vals = []
+        for x in range(K.N):
+            v = sum(cols[i][x] * rec[i] for i in range(nl)) % big
+            vals.append(v - big if v >= half else v)  # :131-136
+        out = K.NewPoly()
+        self._set_bigint(K.nl, vals, out)  # :138
+        K.NTT(out, out, stream=stream)  # :140
+        return out
+
+    def Recrypt(self, ct0, crs, shareRecrypt, stream=None):
+        """:142-147: returns (value[0] + shareRecrypt, copy of crs)"""
+        self.contextQ.Add(ct0, shareRecrypt, ct0, stream=stream)
+        return ct0, crs.CopyNew(stream=stream)
 
 
 def evakey_to_numpy(key):

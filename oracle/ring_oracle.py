@@ -985,6 +985,124 @@ class BfvScheme:
 
 
 # ---------------------------------------------------------------------------
+# Refresh protocols (dckks/public_refresh.go:43-147, dbfv/public_refresh.go:105-205) restated over the oracle's ring
+# ops.  Sampled values (masks, errors) are inputs; the big-integer steps (SetCoefficientsBigint, PolyToBigint,
+# ring/ring_context.go:343-421) are exact Python integers.
+# ---------------------------------------------------------------------------
+def set_coefficients_bigint(moduli, coeffs):  # ring_context.go:343-367 (big.Int.Mod is Euclidean, like Python's %)
+    return np.array([[int(c) % int(q) for c in coeffs] for q in moduli], dtype=np.uint64)
+
+
+def poly_to_bigint(poly, moduli):  # ring_context.go:384-421: the CRT value in [0, prod(moduli of the poly's limbs))
+    nl = poly.shape[0]
+    mods = [int(q) for q in moduli[:nl]]
+    big = 1
+    for q in mods:
+        big *= q
+    rec = [(big // q) * pow(big // q, -1, q) for q in mods]
+    cols = [poly[i].tolist() for i in range(nl)]
+    return [sum(cols[i][x] * rec[i] for i in range(nl)) % big for x in range(poly.shape[1])]
+
+
+class DckksRefresh:
+    """dckks/public_refresh.go over contextQ of a CkksScheme"""
+
+    def __init__(self, scheme):
+        self.S = scheme
+
+    def center_mask(self, level_start, n_parties, raw):  # :48-63, raw[i] = ring.RandInt(bound)
+        bound = 1
+        for q in self.S.Qm[: level_start + 1]:
+            bound *= int(q)
+        bound //= 2 * n_parties
+        half = bound >> 1
+        assert all(0 <= m < bound for m in raw)
+        return [m - bound if m >= half else m for m in raw]
+
+    def gen_shares(self, sk, level_start, n_parties, ct1, crs, raw_mask, e0, e1):  # :43-98
+        S = self.S
+        nl, nQ = level_start + 1, S.levels
+        skq = np.ascontiguousarray(sk[:nQ])
+        mask = self.center_mask(level_start, n_parties, raw_mask)
+        h0 = S.Q.ntt(set_coefficients_bigint(S.Qm[:nl], mask), nl=nl)  # :66,:75
+        h1 = S.Q.ntt(set_coefficients_bigint(S.Qm, mask))  # :68,:76
+        S.Q.op3("mulcoeffs_montgomery_and_add", np.ascontiguousarray(skq[:nl]), np.ascontiguousarray(ct1[:nl]), h0, nl=nl)  # :79
+        S.Q.op3("mulcoeffs_montgomery_and_add", skq, np.ascontiguousarray(crs), h1)  # :82
+        tmp = S.Q.ntt(signed_residues(S.Qm, e0))  # SampleNTT :85
+        h0 = S.Q.op3("add", h0, np.ascontiguousarray(tmp[:nl]), nl=nl)
+        tmp = S.Q.ntt(signed_residues(S.Qm, e1))  # :89
+        h1 = S.Q.op3("add", h1, tmp)
+        return h0, S.Q.op2("neg", h1)  # :93
+
+    def aggregate(self, a, b):  # :101-103
+        return self.S.Q.op3("add", a, b, nl=a.shape[0])
+
+    def decrypt(self, ct0, share_decrypt):  # :106-108
+        return self.S.Q.op3("add", np.ascontiguousarray(ct0), share_decrypt, nl=ct0.shape[0])
+
+    def recode(self, ct0):  # :111-139: value[0] at level len(ct0)-1 -> the same centred values over every limb of Q
+        S = self.S
+        nl = ct0.shape[0]
+        vals = poly_to_bigint(S.Q.invntt(np.ascontiguousarray(ct0), nl=nl), S.Qm)
+        qstart = 1
+        for q in S.Qm[:nl]:
+            qstart *= int(q)
+        half = qstart >> 1
+        vals = [v - qstart if v >= half else v for v in vals]
+        return S.Q.ntt(set_coefficients_bigint(S.Qm, vals))
+
+    def recrypt(self, ct0, crs, share_recrypt):  # :142-147
+        return np.stack([self.S.Q.op3("add", ct0, share_recrypt), np.ascontiguousarray(crs)])
+
+
+class DbfvRefresh:
+    """dbfv/public_refresh.go over a BfvScheme.  hP is protocol state: GenShares adds the P limbs of the error sample
+    into it without ever clearing it (:137-143), so a second call on the same object sees the first call's words."""
+
+    def __init__(self, scheme):
+        self.S = scheme
+        self.hP = np.zeros((scheme.alpha, scheme.N), dtype=np.uint64)
+
+    def lift(self, p0):  # :207-214: MRed(p0.Coeffs[0], deltaMont[i]) into every limb
+        S = self.S
+        out = np.zeros((S.nQ, S.N), dtype=np.uint64)
+        for i in range(S.nQ - 1, -1, -1):
+            q = S.Qm[i]
+            out[i] = _mred_vec(np.ascontiguousarray(p0[0]), S.delta_mont[i], q, int(lib().orc_mred_params(q)))
+        return out
+
+    def gen_shares(self, sk, ct1, crs, e, e_prime, mask):  # :105-169
+        S = self.S
+        nQ = S.nQ
+        QP = S.Qm + S.Pm
+        skq = np.ascontiguousarray(sk[:nQ])
+        h0 = S.Q.invntt(S.Q.op3("mulcoeffs_montgomery", skq, S.Q.ntt(np.ascontiguousarray(ct1))))  # :116-119
+        h0 = S.Q.mul_scalar(h0, [S.Pbig % q for q in S.Qm])  # :122
+        tmp1 = signed_residues(QP, e)  # sampler.Sample over QP :125
+        h0 = S.Q.op3("add", h0, np.ascontiguousarray(tmp1[:nQ]))  # :126
+        self.hP = self.hP + tmp1[nQ:]  # :128-134 (plain uint64 +=)
+        h0 = S.ext.moddown_splited_pq(nQ - 1, h0, np.ascontiguousarray(self.hP))  # :137
+        t2 = S.QP.op3("mulcoeffs_montgomery", np.ascontiguousarray(sk), S.QP.ntt(np.ascontiguousarray(crs)))  # :140-141
+        t2 = S.QP.invntt(S.QP.op2("neg", t2))  # :142-143
+        t2 = S.QP.op3("add", t2, signed_residues(QP, e_prime))  # SampleAndAdd :146
+        h1 = S.ext.moddown_pq(nQ - 1, t2)[:nQ].copy()  # :149
+        m = self.lift(np.asarray(mask, dtype=np.uint64)[None, :])  # :152-153
+        return S.Q.op3("add", h0, m), S.Q.op3("sub", h1, m)  # :156,:159
+
+    def aggregate(self, a, b):  # :172-175
+        return self.S.Q.op3("add", a[0], b[0]), self.S.Q.op3("add", a[1], b[1])
+
+    def finalize(self, ct, crs, share):  # Decrypt :178-180, Recode :183-188, Recrypt :191-199
+        S = self.S
+        nQ = S.nQ
+        pt = S.Q.op3("add", np.ascontiguousarray(ct[0]), share[0])
+        pt = self.lift(S.scaler.scale(pt, nQ))
+        c0 = S.Q.op3("add", pt, share[1])
+        c1 = S.ext.moddown_pq(nQ - 1, np.ascontiguousarray(crs))[:nQ].copy()
+        return np.stack([c0, c1])
+
+
+# ---------------------------------------------------------------------------
 # wire formats of the scheme objects (ckks/marshaler.go, bfv/marshaler.go): byte strings built from numpy
 # polynomials [nlimbs][N]; switching keys are [beta][2][nQP][N]
 # ---------------------------------------------------------------------------

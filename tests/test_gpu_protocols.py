@@ -271,3 +271,109 @@ def test_dbfv_cks_rtg_rkg(lg):
     u = S.gen_secret_key(tern())
     got = rkg.GenShareRoundOne(F(u), F(sks[0]), dcrp, [signed_to_poly(cK, x) for x in e])
     assert all(np.array_equal(g.numpy(), w) for g, w in zip(got, D.rkg_round1(u, sks[0], crp, e)))
+
+
+def test_dckks_refresh(lg):
+    """dckks Refresh (public_refresh.go:43-147) with 3 parties from two start levels: every share, the masked
+    decryption, the recoded polynomial and the refreshed ciphertext bit-exact against the oracle."""
+    p = lg.ckks.DefaultParams[lg.ckks.PN13QP218]
+    Q, P = lg.ckks.GenModuli(p)
+    N = 1 << p["LogN"]
+    nQ = len(Q)
+    rng = np.random.default_rng(71)
+    S = orc.CkksScheme(Q, P, N)
+    R = orc.DckksRefresh(S)
+    cQ = lg.ring.NewContextWithParams(N, Q)
+    F = lg.ring.Poly.from_numpy
+    from lattigpu.ckks_scheme import signed_to_poly
+
+    tern = lambda: rng.integers(-1, 2, size=N)
+    gauss = lambda: np.rint(rng.normal(0, 3.2, size=N)).astype(np.int64)
+    sks = [np.ascontiguousarray(S.gen_secret_key(tern())[:nQ]) for _ in range(PARTIES)]
+    proto = lg.dckks.RefreshProtocol(cQ)
+    for level in (0, 2):
+        nl = level + 1
+        ct = [uni(rng, Q[:nl], N), uni(rng, Q[:nl], N)]
+        crs = uni(rng, Q, N)
+        bound = 1
+        for q in Q[:nl]:
+            bound *= int(q)
+        bound //= 2 * PARTIES
+        nbytes = (bound.bit_length() + 7) // 8 + 8
+        h0 = h1 = h0w = h1w = None
+        for s_i in sks:
+            raw = [int.from_bytes(rng.bytes(nbytes), "big") % bound for _ in range(N)]
+            e0, e1 = gauss(), gauss()
+            d, r = proto.AllocateShares(level)
+            proto.GenShares(F(s_i), level, PARTIES, F(ct[1]), F(crs), d, r, raw, signed_to_poly(cQ, e0), signed_to_poly(cQ, e1))
+            dw, rw = R.gen_shares(s_i, level, PARTIES, ct[1], crs, raw, e0, e1)
+            assert np.array_equal(d.numpy(squeeze=False)[0], dw) and np.array_equal(r.numpy(squeeze=False)[0], rw), level
+            if h0 is None:
+                h0, h1, h0w, h1w = d, r, dw, rw
+            else:
+                proto.Aggregate(h0, d, h0)
+                proto.Aggregate(h1, r, h1)
+                h0w, h1w = R.aggregate(h0w, dw), R.aggregate(h1w, rw)
+        c0 = F(ct[0])
+        proto.Decrypt(level, c0, h0)
+        md = R.decrypt(ct[0], h0w)
+        assert np.array_equal(c0.numpy(squeeze=False)[0], md)
+        rec = proto.Recode(level, c0)
+        recw = R.recode(md)
+        assert rec.nlimbs == nQ and np.array_equal(rec.numpy(), recw)
+        o0, o1 = proto.Recrypt(rec, F(crs), h1)
+        want = R.recrypt(recw, crs, h1w)
+        assert np.array_equal(o0.numpy(), want[0]) and np.array_equal(o1.numpy(), want[1])
+
+
+def test_dbfv_refresh(lg):
+    """dbfv Refresh (public_refresh.go:105-205) with 3 parties: shares (including the second call on the same protocol
+    object, which sees the hP words the first call left), aggregation and Finalize bit-exact against the oracle;
+    the refreshed ciphertext decrypts to the encoded slots."""
+    p = lg.bfv.DefaultParams[lg.bfv.PN13QP218]
+    Q, P, _ = lg.bfv.GenModuli(p)
+    N, t = 1 << p["LogN"], p["T"]
+    QP = Q + P
+    nQ = len(Q)
+    rng = np.random.default_rng(73)
+    S = orc.BfvScheme(Q, P, N, t)
+    cQ, cP, cK = (lg.ring.NewContextWithParams(N, m) for m in (Q, P, QP))
+    F = lg.ring.Poly.from_numpy
+    from lattigpu.ckks_scheme import signed_to_poly
+
+    tern = lambda: rng.integers(-1, 2, size=N)
+    gauss = lambda: np.rint(rng.normal(0, 3.2, size=N)).astype(np.int64)
+    sks = [S.gen_secret_key(tern()) for _ in range(PARTIES)]
+    sk = sks[0]
+    for x in sks[1:]:
+        sk = S.QP.op3("add", sk, x)
+    slots = rng.integers(0, t, size=N, dtype=np.uint64)
+    ct = S.encrypt_sk(S.encode_uint(slots), sk, uni(rng, QP, N), gauss())
+    crs = uni(rng, QP, N)
+    share = sharew = None
+    protos, oracles = [], []
+    for s_i in sks:
+        pr, ow = lg.dbfv.RefreshProtocol(cQ, cP, cK, t), orc.DbfvRefresh(S)
+        protos.append(pr)
+        oracles.append(ow)
+        e, e2, mask = gauss(), gauss(), rng.integers(0, t, size=N, dtype=np.uint64)
+        sh = pr.AllocateShares()
+        pr.GenShares(F(s_i), F(ct[1]), F(crs), sh, signed_to_poly(cK, e), signed_to_poly(cK, e2), mask)
+        w = ow.gen_shares(s_i, ct[1], crs, e, e2, mask)
+        assert np.array_equal(sh[0].numpy(), w[0]) and np.array_equal(sh[1].numpy(), w[1])
+        if share is None:
+            share, sharew = sh, w
+        else:
+            pr.Aggregate(share, sh, share)
+            sharew = ow.aggregate(sharew, w)
+    out = (cQ.NewPoly(), cQ.NewPoly())
+    protos[0].Finalize((F(ct[0]), F(ct[1])), F(crs), share, out)
+    want = oracles[0].finalize(ct, crs, sharew)
+    assert np.array_equal(out[0].numpy(), want[0]) and np.array_equal(out[1].numpy(), want[1])
+    assert np.array_equal(S.decode_uint(S.decrypt(want, sk)), slots)
+    # second GenShares on the same object: hP still holds the first sample's P limbs
+    e, e2, mask = gauss(), gauss(), rng.integers(0, t, size=N, dtype=np.uint64)
+    sh = protos[0].AllocateShares()
+    protos[0].GenShares(F(sks[0]), F(ct[1]), F(crs), sh, signed_to_poly(cK, e), signed_to_poly(cK, e2), mask)
+    w = oracles[0].gen_shares(sks[0], ct[1], crs, e, e2, mask)
+    assert np.array_equal(sh[0].numpy(), w[0]) and np.array_equal(sh[1].numpy(), w[1])

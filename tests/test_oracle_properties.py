@@ -547,6 +547,83 @@ def test_dbfv_cks_semantics():
     assert err < (1 << 12), err
 
 
+def test_dckks_refresh_semantics():
+    """dckks Refresh (public_refresh.go:43-147) with 3 parties, as dckks_test.go's testRefresh: a ciphertext at a low
+    level is masked-decrypted, recoded at the top level and re-encrypted under the common reference polynomial; it
+    must decrypt (collective key) to the same message at the top level."""
+    N, parties = 32, 3
+    Q, P = _ckks_small(N)
+    rng = random.Random(77)
+    S = orc.CkksScheme(Q, P, N)
+    R = orc.DckksRefresh(S)
+    K = S.QP
+    nQ = len(Q)
+    tern = lambda: [rng.choice([-1, 0, 1]) for _ in range(N)]
+    gauss = lambda: [rng.choice([-2, -1, 0, 0, 1, 2]) for _ in range(N)]
+    unif = lambda mods: np.array([[rng.randrange(q) for _ in range(N)] for q in mods], dtype=np.uint64)
+    sks = [S.gen_secret_key(tern()) for _ in range(parties)]
+    sk = sks[0]
+    for x in sks[1:]:
+        sk = K.op3("add", sk, x)
+    scale = 1 << 20
+    m = [rng.randrange(-500, 500) for _ in range(N)]
+    for level_start in (0, 1):
+        nl = level_start + 1
+        # encrypted at the top level, then the upper limbs dropped (what a ciphertext that went down the levels is)
+        pt = S.Q.ntt(crt_poly([x * scale for x in m], Q))
+        ct = np.ascontiguousarray(S.encrypt_sk(nQ - 1, pt, sk, unif(Q + P), gauss())[:, :nl])
+        crs = unif(Q)
+        bound = prod(Q[:nl]) // (2 * parties)
+        h0 = h1 = None
+        for s_i in sks:
+            a, b = R.gen_shares(s_i, level_start, parties, ct[1], crs, [rng.randrange(bound) for _ in range(N)], gauss(), gauss())
+            assert a.shape[0] == nl and b.shape[0] == nQ
+            h0, h1 = (a, b) if h0 is None else (R.aggregate(h0, a), R.aggregate(h1, b))
+        fresh = R.recrypt(R.recode(R.decrypt(np.ascontiguousarray(ct[0]), h0)), crs, h1)
+        assert fresh.shape == (2, nQ, N)
+        dec = crt_reconstruct(S.Q.invntt(S.decrypt(nQ - 1, fresh, sk)), Q)
+        Qp = prod(Q)
+        dec = [v if v < Qp // 2 else v - Qp for v in dec]
+        err = max(abs(d - x * scale) for d, x in zip(dec, m))
+        assert err < (1 << 12), (level_start, err)
+    # the CRT helpers are the big-integer maps of ring_context.go:343-421
+    vals = [rng.randrange(-prod(Q) // 2, prod(Q) // 2) for _ in range(N)]
+    assert orc.poly_to_bigint(orc.set_coefficients_bigint(Q, vals), Q) == [v % prod(Q) for v in vals]
+
+
+def test_dbfv_refresh_semantics():
+    """dbfv Refresh (public_refresh.go:105-205) with 3 parties, as dbfv_test.go's testRefresh: after Finalize the
+    ciphertext decrypts (collective key) to the same plaintext slots, with fresh noise."""
+    N, parties, t = 32, 3, 65537
+    Q, P, _ = _bfv_small(N)
+    rng = random.Random(78)
+    S = orc.BfvScheme(Q, P, N, t)
+    K = S.QP
+    tern = lambda: [rng.choice([-1, 0, 1]) for _ in range(N)]
+    gauss = lambda: [rng.choice([-2, -1, 0, 0, 1, 2]) for _ in range(N)]
+    unif = lambda mods: np.array([[rng.randrange(q) for _ in range(N)] for q in mods], dtype=np.uint64)
+    sks = [S.gen_secret_key(tern()) for _ in range(parties)]
+    sk = sks[0]
+    for x in sks[1:]:
+        sk = K.op3("add", sk, x)
+    slots = [rng.randrange(t) for _ in range(N)]
+    ct = S.encrypt_sk(S.encode_uint(slots), sk, unif(Q + P), gauss())
+    # some noise growth a refresh is meant to remove: add an encryption of zero scaled up
+    crs = unif(Q + P)
+    protos = [orc.DbfvRefresh(S) for _ in range(parties)]
+    share = None
+    for pr, s_i in zip(protos, sks):
+        sh = pr.gen_shares(s_i, ct[1], crs, gauss(), gauss(), [rng.randrange(t) for _ in range(N)])
+        share = sh if share is None else pr.aggregate(share, sh)
+    fresh = protos[0].finalize(ct, crs, share)
+    assert np.array_equal(S.decode_uint(S.decrypt(fresh, sk)), np.array(slots, dtype=np.uint64))
+    # hP is state: a second GenShares on the same object differs from a fresh object's by the first error's P limbs
+    e1, e2, e3, mask = gauss(), gauss(), gauss(), [rng.randrange(t) for _ in range(N)]
+    again = protos[0].gen_shares(sks[0], ct[1], crs, e2, e3, mask)
+    clean = orc.DbfvRefresh(S).gen_shares(sks[0], ct[1], crs, e2, e3, mask)
+    assert np.array_equal(again[1], clean[1]) and not np.array_equal(again[0], clean[0])
+
+
 def test_ckks_const_ops_semantics():
     """Constant ops (ckks/evaluator.go:373-833) in the coefficient domain: AddConst(a+bi) adds round(a*scale)
     to coefficient 0 and round(b*scale) to coefficient N/2; MultByConst multiplies the polynomial by
