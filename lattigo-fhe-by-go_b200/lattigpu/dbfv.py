@@ -17,6 +17,11 @@ RTGProtocol = dckks.RTGProtocol
 RKGProtocol = dckks.RKGProtocol
 
 
+def RKGProtocolNaive(contextQ, contextP, contextQP):
+    """dbfv/relinkey_gen_naive.go: the dckks sequence, with the second round-one sample going to shareOut[i][1] (:76)"""
+    return dckks.RKGProtocolNaive(contextQ, contextP, contextQP, second_error_into=1)
+
+
 class CKGProtocol:
     def __init__(self, contextQP):
         self.context = contextQP

@@ -2,7 +2,7 @@
 generation (CKG, dckks/publickey_gen.go:18-52), public collective key switching (PCKS,
 dckks/public_keyswitching.go:9-113), collective key switching (CKS, dckks/keyswitching.go:55-108),
 rotation-key generation (RTG, dckks/rotkey_gen.go:75-174) and the three-round relinearisation-key
-generation (RKG, dckks/relinkey_gen.go:60-223) and the collective refresh (dckks/public_refresh.go:9-147).  As in the reference the protocol logic is host code that
+generation (RKG, dckks/relinkey_gen.go:60-223), its two-round "naive" variant (relinkey_gen_naive.go) and the collective refresh (dckks/public_refresh.go:9-147).  As in the reference the protocol logic is host code that
 calls ring ops; here every ring op runs on the GPU through the C ABI.
 
 Sampling stays with the caller (the reference draws from crypto/rand on the host): GenShare takes
@@ -238,6 +238,83 @@ class RKGProtocol:
             k0, k1 = K.NewPoly(), K.NewPoly()
             K.Add(round2[i][0], round3[i], k0, stream=stream)
             K.MForm(k0, k0, stream=stream)
+            K.MForm(round2[i][1], k1, stream=stream)
+            key.append((k0, k1))
+        return key
+
+
+class RKGProtocolNaive:
+    """dckks/relinkey_gen_naive.go:11-200 (and dbfv/relinkey_gen_naive.go with `second_error_into=1`) over contextQP.
+    pk = (pk0, pk1) collective public key; sk = secret share (NTT + Montgomery).  Round one draws two gaussian samples
+    per digit: the dbfv file transforms them into shareOut[i][0] and shareOut[i][1] (:74-76); the dckks file writes
+    BOTH into shareOut[i][0] (:73,:75), so the first is overwritten and shareOut[i][1] keeps its content (zero for
+    freshly allocated shares).  `second_error_into` selects which (0 = dckks, 1 = dbfv)."""
+
+    def __init__(self, contextQ, contextP, contextQP, second_error_into=0):
+        self.contextQP = contextQP
+        self.levels, self.alpha = contextQ.nl, contextP.nl
+        self.beta = -(-self.levels // self.alpha)
+        self.second = int(second_error_into)
+        self.Pbig = 1
+        for p in contextP.Modulus:
+            self.Pbig *= int(p)
+
+    def AllocateShares(self):
+        K = self.contextQP
+        mk = lambda: [(self._zero(K), self._zero(K)) for _ in range(self.beta)]
+        return mk(), mk()
+
+    @staticmethod
+    def _zero(K):
+        p = K.NewPoly()
+        p.Zero()
+        return p
+
+    def GenShareRoundOne(self, sk, pk, shareOut, errors, us, stream=None):
+        """:53-108.  errors[i] = (first, second) gaussian samples of digit i (coefficient domain, over QP);
+        us[i] = ternary sample of digit i (Montgomery form, coefficient domain)."""
+        K = self.contextQP
+        pool, tmp = sk.CopyNew(stream=stream), K.NewPoly()
+        K.MulScalarBigint(pool, self.Pbig, pool, stream=stream)  # :59
+        K.InvMForm(pool, pool, stream=stream)  # :61
+        for i in range(self.beta):
+            K.NTT(errors[i][0], shareOut[i][0], stream=stream)  # :73
+            K.NTT(errors[i][1], shareOut[i][self.second], stream=stream)  # :75 (dbfv :76)
+            _add_digit_limbs(K, pool, shareOut[i][0], i, self.alpha, self.levels, tmp, stream)  # :78-95
+        for i in range(self.beta):
+            K.NTT(us[i], pool, stream=stream)  # SampleTernaryMontgomeryNTT :100
+            K.MulCoeffsMontgomeryAndAdd(pk[0], pool, shareOut[i][0], stream=stream)  # :101
+            K.MulCoeffsMontgomeryAndAdd(pk[1], pool, shareOut[i][1], stream=stream)  # :102
+
+    def AggregateShareRoundOne(self, share1, share2, shareOut, stream=None):
+        for a, b, c in zip(share1, share2, shareOut):  # :111-120
+            self.contextQP.Add(a[0], b[0], c[0], stream=stream)
+            self.contextQP.Add(a[1], b[1], c[1], stream=stream)
+
+    def GenShareRoundTwo(self, round1, sk, pk, shareOut, us, errors, stream=None):
+        """:129-166.  us[i] = ternary sample; errors[i] = (e0, e1) gaussian samples of digit i"""
+        K = self.contextQP
+        pool = K.NewPoly()
+        for i in range(self.beta):
+            K.MulCoeffsMontgomery(round1[i][0], sk, shareOut[i][0], stream=stream)  # :141
+            K.MulCoeffsMontgomery(round1[i][1], sk, shareOut[i][1], stream=stream)  # :142
+            K.NTT(us[i], pool, stream=stream)  # :145
+            K.MulCoeffsMontgomeryAndAdd(pk[0], pool, shareOut[i][0], stream=stream)  # :148
+            K.MulCoeffsMontgomeryAndAdd(pk[1], pool, shareOut[i][1], stream=stream)  # :151
+            K.NTT(errors[i][0], pool, stream=stream)  # :154
+            K.Add(shareOut[i][0], pool, shareOut[i][0], stream=stream)
+            K.NTT(errors[i][1], pool, stream=stream)  # :158
+            K.Add(shareOut[i][1], pool, shareOut[i][1], stream=stream)
+
+    AggregateShareRoundTwo = AggregateShareRoundOne  # :169-177
+
+    def GenRelinearizationKey(self, round2, stream=None):
+        """:180-200: key[i] = (MForm(round2[i][0]), MForm(round2[i][1]))"""
+        K = self.contextQP
+        key = []
+        for i in range(self.beta):
+            k0, k1 = K.NewPoly(), K.NewPoly()
+            K.MForm(round2[i][0], k0, stream=stream)
             K.MForm(round2[i][1], k1, stream=stream)
             key.append((k0, k1))
         return key

@@ -611,6 +611,39 @@ class DckksProtocols:
             self.K.op2("mform_poly", self.K.op3("add", round2[i][0], round3[i])),
             self.K.op2("mform_poly", round2[i][1])]) for i in range(self.S.beta)]))
 
+    # relinkey_gen_naive.go (dckks :53-200; dbfv identical except where round one's second sample lands, :76)
+    def rkg_naive_round1(self, sk, pk, errors, us, second_error_into=0, share=None):
+        S = self.S
+        pool = self.K.op2("invmform_poly", self.K.mul_scalar(sk, [S.Pbig % q for q in self.mods]))
+        zero = lambda: np.zeros((len(self.mods), S.N), dtype=np.uint64)
+        out = [[zero(), zero()] for _ in range(S.beta)] if share is None else [[a.copy(), b.copy()] for a, b in share]
+        for i in range(S.beta):
+            out[i][0] = self.K.ntt(signed_residues(self.mods, errors[i][0]))
+            out[i][second_error_into] = self.K.ntt(signed_residues(self.mods, errors[i][1]))
+            self._add_digit(out[i][0], pool, i)
+        for i in range(S.beta):
+            u = self.K.ntt(np.ascontiguousarray(us[i]))
+            self.K.op3("mulcoeffs_montgomery_and_add", pk[0], u, out[i][0])
+            self.K.op3("mulcoeffs_montgomery_and_add", pk[1], u, out[i][1])
+        return [(a, b) for a, b in out]
+
+    def rkg_naive_round2(self, round1, sk, pk, us, errors):
+        out = []
+        for i in range(self.S.beta):
+            s0 = self.K.op3("mulcoeffs_montgomery", round1[i][0], sk)
+            s1 = self.K.op3("mulcoeffs_montgomery", round1[i][1], sk)
+            u = self.K.ntt(np.ascontiguousarray(us[i]))
+            self.K.op3("mulcoeffs_montgomery_and_add", pk[0], u, s0)
+            self.K.op3("mulcoeffs_montgomery_and_add", pk[1], u, s1)
+            s0 = self.K.op3("add", s0, self.K.ntt(signed_residues(self.mods, errors[i][0])))
+            s1 = self.K.op3("add", s1, self.K.ntt(signed_residues(self.mods, errors[i][1])))
+            out.append((s0, s1))
+        return out
+
+    def rkg_naive_key(self, round2):
+        return np.ascontiguousarray(np.stack([np.stack([self.K.op2("mform_poly", a), self.K.op2("mform_poly", b)])
+                                              for a, b in round2]))
+
     def add_lists(self, a, b):
         return [self.K.op3("add", x, y) for x, y in zip(a, b)]
 

@@ -377,3 +377,64 @@ def test_dbfv_refresh(lg):
     protos[0].GenShares(F(sks[0]), F(ct[1]), F(crs), sh, signed_to_poly(cK, e), signed_to_poly(cK, e2), mask)
     w = oracles[0].gen_shares(sks[0], ct[1], crs, e, e2, mask)
     assert np.array_equal(sh[0].numpy(), w[0]) and np.array_equal(sh[1].numpy(), w[1])
+
+
+@pytest.mark.parametrize("scheme", ["dckks", "dbfv"])
+def test_rkg_naive(lg, scheme):
+    """relinkey_gen_naive.go, two rounds with 3 parties, shares and key bit-exact against the oracle; the dckks file
+    writes both round-one samples into shareOut[i][0] (:73,:75), the dbfv file into [0] and [1] (:74,:76)."""
+    if scheme == "dckks":
+        Q, P = lg.ckks.GenModuli(lg.ckks.DefaultParams[lg.ckks.PN13QP218])
+        N, second, mod = 1 << 13, 0, lg.dckks
+    else:
+        Q, P, _ = lg.bfv.GenModuli(lg.bfv.DefaultParams[lg.bfv.PN13QP218])
+        N, second, mod = 1 << 13, 1, lg.dbfv
+    QP = Q + P
+    rng = np.random.default_rng(75)
+    S = orc.CkksScheme(Q, P, N)
+    D = orc.DckksProtocols(S)
+    cQ, cP, cK = (lg.ring.NewContextWithParams(N, m) for m in (Q, P, QP))
+    F = lg.ring.Poly.from_numpy
+    from lattigpu.ckks_scheme import signed_to_poly
+
+    tern = lambda: rng.integers(-1, 2, size=N)
+    gauss = lambda: np.rint(rng.normal(0, 3.2, size=N)).astype(np.int64)
+    pairs = lambda: [(gauss(), gauss()) for _ in range(S.beta)]
+    dev_pairs = lambda es: [(signed_to_poly(cK, a), signed_to_poly(cK, b)) for a, b in es]
+    terns = lambda: [ternary_mont(rng, S.QP, QP, N) for _ in range(S.beta)]
+    sks = [S.gen_secret_key(tern()) for _ in range(PARTIES)]
+    sk = sks[0]
+    for x in sks[1:]:
+        sk = S.QP.op3("add", sk, x)
+    pk = S.gen_public_key(sk, gauss(), uni(rng, QP, N))
+    dpk = (F(pk[0]), F(pk[1]))
+    rkg = mod.RKGProtocolNaive(cQ, cP, cK)
+
+    def same(got, want):
+        return all(np.array_equal(g[0].numpy(), w[0]) and np.array_equal(g[1].numpy(), w[1]) for g, w in zip(got, want))
+
+    r1 = r1w = None
+    for s_i in sks:
+        e, u = pairs(), terns()
+        sh, _ = rkg.AllocateShares()
+        rkg.GenShareRoundOne(F(s_i), dpk, sh, dev_pairs(e), [F(x) for x in u])
+        w = D.rkg_naive_round1(s_i, pk, e, u, second)
+        assert same(sh, w)
+        if r1 is None:
+            r1, r1w = sh, w
+        else:
+            rkg.AggregateShareRoundOne(r1, sh, r1)
+            r1w = D.add_pairs(r1w, w)
+    r2 = r2w = None
+    for s_i in sks:
+        e, u = pairs(), terns()
+        _, sh = rkg.AllocateShares()
+        rkg.GenShareRoundTwo(r1, F(s_i), dpk, sh, [F(x) for x in u], dev_pairs(e))
+        w = D.rkg_naive_round2(r1w, s_i, pk, u, e)
+        assert same(sh, w)
+        if r2 is None:
+            r2, r2w = sh, w
+        else:
+            rkg.AggregateShareRoundTwo(r2, sh, r2)
+            r2w = D.add_pairs(r2w, w)
+    assert np.array_equal(lg.dckks.evakey_to_numpy(rkg.GenRelinearizationKey(r2)), D.rkg_naive_key(r2w))

@@ -547,6 +547,59 @@ def test_dbfv_cks_semantics():
     assert err < (1 << 12), err
 
 
+@pytest.mark.parametrize("second", [0, 1], ids=["dckks", "dbfv"])
+def test_rkg_naive_semantics(second):
+    """relinkey_gen_naive.go with 3 parties: the two-round key relinearises a product (the dckks file loses round
+    one's second error sample, the dbfv file keeps it; both are valid keys)."""
+    N, parties = 32, 3
+    Q, P = _ckks_small(N)
+    rng = random.Random(91 + second)
+    S = orc.CkksScheme(Q, P, N)
+    D = orc.DckksProtocols(S)
+    K = S.QP
+    tern = lambda: [rng.choice([-1, 0, 1]) for _ in range(N)]
+    gauss = lambda: [rng.choice([-2, -1, 0, 0, 1, 2]) for _ in range(N)]
+    unif = lambda mods: np.array([[rng.randrange(q) for _ in range(N)] for q in mods], dtype=np.uint64)
+    tern_mont = lambda: K.op2("mform_poly", orc.signed_residues(Q + P, tern()))
+    level = len(Q) - 1
+    scale = 1 << 20
+    sks = [S.gen_secret_key(tern()) for _ in range(parties)]
+    sk = sks[0]
+    for x in sks[1:]:
+        sk = K.op3("add", sk, x)
+    pk = S.gen_public_key(sk, gauss(), unif(Q + P))
+    r1 = None
+    for s_i in sks:
+        sh = D.rkg_naive_round1(s_i, pk, [(gauss(), gauss()) for _ in range(S.beta)], [tern_mont() for _ in range(S.beta)], second)
+        r1 = sh if r1 is None else D.add_pairs(r1, sh)
+    r2 = None
+    for s_i in sks:
+        sh = D.rkg_naive_round2(r1, s_i, pk, [tern_mont() for _ in range(S.beta)], [(gauss(), gauss()) for _ in range(S.beta)])
+        r2 = sh if r2 is None else D.add_pairs(r2, sh)
+    rlk = D.rkg_naive_key(r2)
+    plaintext = lambda m: S.Q.ntt(crt_poly([x * scale for x in m], Q))
+    m0 = [rng.randrange(-500, 500) for _ in range(N)]
+    m1 = [rng.randrange(-500, 500) for _ in range(N)]
+    ct0 = S.encrypt_sk(level, plaintext(m0), sk, unif(Q + P), gauss())
+    ct1 = S.encrypt_sk(level, plaintext(m1), sk, unif(Q + P), gauss())
+    ev = orc.CkksEvaluator(S.Q, S.P)
+    prod_ct = ev.rescale(ev.mul_relin(level, np.ascontiguousarray(ct0), np.ascontiguousarray(ct1), rlk))
+    Ql = Q[:-1]
+    dec = crt_reconstruct(orc.Context(N, Ql).invntt(S.decrypt(level - 1, prod_ct, sk)), Ql)
+    dec = [v if v < prod(Ql) // 2 else v - prod(Ql) for v in dec]
+    want = [0] * N
+    for x in range(N):
+        for y in range(N):
+            k = x + y
+            if k >= N:
+                want[k - N] -= m0[x] * m1[y]
+            else:
+                want[k] += m0[x] * m1[y]
+    err = max(abs(d - div_round(w * scale * scale, Q[-1])) if w >= 0 else abs(d + div_round(-w * scale * scale, Q[-1]))
+              for d, w in zip(dec, want))
+    assert err < (1 << 16), err
+
+
 def test_dckks_refresh_semantics():
     """dckks Refresh (public_refresh.go:43-147) with 3 parties, as dckks_test.go's testRefresh: a ciphertext at a low
     level is masked-decrypted, recoded at the top level and re-encrypted under the common reference polynomial; it
