@@ -109,9 +109,42 @@ class Evaluator:
         check(lib().lg_ckks_switch_keys_in_place(self.h, level, cx.h, evakey.h, p0.h, p1.h, _s(stream)))
 
     def MulRelin(self, level, ct0, ct1, evakey, ctOut, stream=None):
-        """ct = (value0, value1).  ct0 is ct1 selects the squaring branch."""
-        check(lib().lg_ckks_mul_relin(self.h, level, ct0[0].h, ct0[1].h, ct1[0].h, ct1[1].h, evakey.h, ctOut[0].h, ctOut[1].h,
-                                      _s(stream)))
+        """MulRelin (:1016-1133).  An operand is its tuple of value polys: (v0, v1) a ciphertext, (v0,) a plaintext.
+        ct0 is ct1 selects the squaring branch.  Ciphertext x ciphertext with a key is the fused device path; with
+        evakey None the degree-2 result goes to the three polys of ctOut (:1059-1063, :1111-1117); plaintext x
+        ciphertext (either order) is the :1121-1137 branch.  The last two are the reference's ring-op sequences."""
+        K = self.contextQ
+        if len(ct0) == 2 and len(ct1) == 2 and evakey is not None:
+            check(lib().lg_ckks_mul_relin(self.h, level, ct0[0].h, ct0[1].h, ct1[0].h, ct1[1].h, evakey.h, ctOut[0].h,
+                                          ctOut[1].h, _s(stream)))
+            return
+        batch = ct0[0].batch
+        if len(ct0) == 2 and len(ct1) == 2:
+            if len(ctOut) != 3:
+                raise ValueError("cannot MulRelin: a degree 2 receiver is needed when no evaluation key is given")
+            c00, c01 = K.NewPolyLvl(level, batch), K.NewPolyLvl(level, batch)  # ringpool[0], ringpool[1]
+            alias = any(o is x for o in ctOut for x in tuple(ct0) + tuple(ct1))
+            c0, c1, c2 = [K.NewPolyLvl(level, batch) for _ in range(3)] if alias else ctOut
+            K.MFormLvl(level, ct0[0], c00, stream=stream)  # :1080-1081
+            K.MFormLvl(level, ct0[1], c01, stream=stream)
+            K.MulCoeffsMontgomeryLvl(level, c00, ct1[0], c0, stream=stream)
+            K.MulCoeffsMontgomeryLvl(level, c00, ct1[1], c1, stream=stream)
+            if ct0 is ct1:  # :1083-1088
+                K.AddLvl(level, c1, c1, c1, stream=stream)
+            else:  # :1092-1095
+                K.MulCoeffsMontgomeryAndAddLvl(level, c01, ct1[0], c1, stream=stream)
+            K.MulCoeffsMontgomeryLvl(level, c01, ct1[1], c2, stream=stream)
+            if alias:  # :1111-1116
+                for src, dst in zip((c0, c1, c2), ctOut):
+                    K.CopyLvl(level, src, dst, stream=stream)
+            return
+        if len(ct0) + len(ct1) != 3:
+            raise ValueError("cannot MulRelin: input elements must be of degree 0 or 1")
+        tmp0, tmp1 = (ct1, ct0) if len(ct0) == 2 else (ct0, ct1)  # :1125-1129
+        c00 = K.NewPolyLvl(level, batch)
+        K.MFormLvl(level, tmp0[0], c00, stream=stream)  # :1134
+        K.MulCoeffsMontgomeryLvl(level, c00, tmp1[0], ctOut[0], stream=stream)
+        K.MulCoeffsMontgomeryLvl(level, c00, tmp1[1], ctOut[1], stream=stream)
 
     def Relinearize(self, level, ct0, evakey, ctOut, stream=None):
         check(lib().lg_ckks_relinearize(self.h, level, ct0[0].h, ct0[1].h, ct0[2].h, evakey.h, ctOut[0].h, ctOut[1].h,

@@ -151,6 +151,64 @@ def test_mul_relin_rescale(lg, params, kind):
             assert np.array_equal(host(out, s.nQ - 2)[i], s.oev.rescale(np.ascontiguousarray(a[i]), nb=2))
 
 
+def test_mul_relin_without_key_and_with_plaintext(lg):
+    """The other branches of MulRelin: evakey == nil leaves a degree-2 ciphertext (:1059-1063, :1111-1117) that
+    Relinearize (:1144-1162) brings to the keyed result; plaintext x ciphertext in either order (:1121-1137)."""
+    s = Setup(lg, PN13)
+    rng = np.random.default_rng(29)
+    evk = s.evk(rng)
+    rlk = lg.ckks.SwitchingKey(evk)
+    batch, level = 2, s.nQ - 2
+    nl = level + 1
+    for kind in ("reduced", "words"):
+        a, b = s.ct(rng, kind, batch), s.ct(rng, kind, batch)
+        oq = s.oQ
+        mf = lambda x: oq.op2("mform_poly", np.ascontiguousarray(x[:nl]), nl=nl)
+        mul = lambda x, y: oq.op3("mulcoeffs_montgomery", x, np.ascontiguousarray(y[:nl]), nl=nl)
+        for sq in (False, True):
+            pa = polys(lg, a)
+            pb = pa if sq else polys(lg, b)
+            out = tuple(lg.ring.Poly(s.N, s.nQ, batch) for _ in range(3))
+            s.ev.MulRelin(level, pa, pb, None, out)
+            bb = a if sq else b
+            for i in range(batch):
+                c00, c01 = mf(a[i, 0]), mf(a[i, 1])
+                w0 = mul(c00, bb[i, 0])
+                if sq:
+                    w1 = mul(c00, bb[i, 1])
+                    w1 = oq.op3("add", w1, w1.copy(), nl=nl)
+                else:
+                    w1 = oq.op3("mulcoeffs_montgomery_and_add", c01, np.ascontiguousarray(bb[i, 0, :nl]), mul(c00, bb[i, 1]), nl=nl)
+                w2 = mul(c01, bb[i, 1])
+                for got, want in zip(out, (w0, w1, w2)):
+                    assert np.array_equal(got.numpy(nl=nl, squeeze=False)[i], want), (kind, sq)
+            rel = new_ct(lg, s, batch)
+            s.ev.Relinearize(level, out, rlk, rel)
+            for i in range(batch):
+                x, y = np.ascontiguousarray(a[i, :, :nl]), np.ascontiguousarray(bb[i, :, :nl])
+                assert np.array_equal(host(rel, nl)[i], s.oev.mul_relin(level, x, y, evk)), (kind, sq)
+        # receiver aliasing an input: the three products go through the pool and are copied (:1111-1116)
+        pa, pb = polys(lg, a), polys(lg, b)
+        out = (pa[0], pa[1], lg.ring.Poly(s.N, s.nQ, batch))
+        s.ev.MulRelin(level, pa, pb, None, out)
+        i = 1
+        assert np.array_equal(out[0].numpy(nl=nl, squeeze=False)[i], mul(mf(a[i, 0]), b[i, 0]))
+        assert np.array_equal(out[2].numpy(nl=nl, squeeze=False)[i], mul(mf(a[i, 1]), b[i, 1]))
+        # plaintext (degree 0) x ciphertext, both orders
+        pt = a[:, 0]
+        ppt = (lg.ring.Poly.from_numpy(np.ascontiguousarray(pt)),)
+        for order in (0, 1):
+            pb, out = polys(lg, b), new_ct(lg, s, batch)
+            if order == 0:
+                s.ev.MulRelin(level, ppt, pb, None, out)
+            else:
+                s.ev.MulRelin(level, pb, ppt, rlk, out)
+            for i in range(batch):
+                c = mf(pt[i])
+                assert np.array_equal(out[0].numpy(nl=nl, squeeze=False)[i], mul(c, b[i, 0])), kind
+                assert np.array_equal(out[1].numpy(nl=nl, squeeze=False)[i], mul(c, b[i, 1])), kind
+
+
 @pytest.mark.parametrize("params", [PN13, SMALL3], ids=["PN13", "alpha3"])
 def test_rotate_conjugate_switchkeys_relinearize(lg, params):
     s = Setup(lg, params)
