@@ -318,13 +318,15 @@ def run_gpu(args):
     butterflies = (N // 2) * p["LogN"] * nlimbs_launch
     # ncu --set full DRAM bytes of the same launch pair (profiles/r01_ncu_ntt_fwd.json, captured per round)
     traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_ntt_fwd.json")) as f:
-            prof = json.load(f)
-        if prof.get("limb_ntts_per_launch") == nlimbs_launch and prof.get("N") == N:
-            traffic = prof["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    for name in ("r01_ncu_ntt_fwd.json", "r01_ncu_ntt_fwd_b16.json"):  # one capture per batch size
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                prof = json.load(f)
+            if prof.get("limb_ntts_per_launch") == nlimbs_launch and prof.get("N") == N:
+                traffic = prof["dram_bytes_per_launch"]
+                break
+        except Exception:
+            pass
     # INT-side ceiling: register-resident butterfly rates measured on this GPU (profiles/microbench/
     # fast_butterfly.cu, profiles/r01_butterfly_peaks.txt): FP64-quotient butterfly for moduli below 3*2^44,
     # the 16-instruction Shoup butterfly below 2^56, the [0,8q) butterfly above
@@ -343,6 +345,33 @@ def run_gpu(args):
                      "butterfly_peak_per_s": butterflies / (int_floor_us * 1e-6),
                      "frac": int_floor_us / fwd_us, "limb_mix": mix,
                      "peak_source": "profiles/r01_butterfly_peaks.txt (register-resident microbenchmark, this GPU type)"},
+    }
+
+    # ---- op-level roofline, SURVEY.md 8(d): max(INT work / INT peak, compulsory bytes / HBM peak) over the measured
+    # time of one MulRelin+Rescale.  Work counts are the reference algorithm's (every butterfly and every
+    # coefficient product = one 64-bit modular multiplication = 11 32x32 multiplies, modular_reduction.go:70-79);
+    # INT peak = the measured IMAD issue rate (profiles/r01_int_pipe.txt: 61 thread-instructions/clk/SM) at the
+    # clock of this run.  The kernels need fewer multiplies than that per product (6 with the FP64 quotient), so this
+    # fraction is an efficiency against the reference's arithmetic, not a hard ceiling; roofline.int_pipe above is
+    # the ceiling of the instruction sequences actually issued.
+    nl_top = level + 1
+    xal = [min(alpha, nl_top - i * alpha) for i in range(beta)]
+    ntts_per_op = (beta + 2) * (nl_top + alpha) + 2 * nl_top
+    mm_coeff = (sum(x * (1 + nl_top - x + alpha) for x in xal) + 2 * beta * (nl_top + alpha)
+                + 2 * alpha * (1 + nl_top) + 2 * nl_top + 6 * nl_top + 2 * (nl_top - 1))
+    modmuls_per_op = ntts_per_op * (N // 2) * p["LogN"] + mm_coeff * N
+    sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    imad_per_s = 61.0 * 148 * sm_mhz * 1e6
+    int_us = 1e6 * modmuls_per_op * 11 / imad_per_s
+    bytes_op = 8.0 * N * (4 * nl_top + 2 * (nl_top - 1)) + 8.0 * N * 2 * beta * (nl_top + alpha) / B
+    hbm_us = 1e6 * bytes_op / (hbm_peak * 1e9)
+    us_per_op = 1e3 * ms_per_step / B
+    roofline_op = {
+        "what": "one MulRelin+Rescale (SURVEY.md 8(d) counts), key bytes amortised over the batch",
+        "limb_ntts_per_op": ntts_per_op, "modmuls_per_op": modmuls_per_op, "compulsory_bytes_per_op": bytes_op,
+        "int_bound_us": int_us, "hbm_bound_us": hbm_us, "measured_us": us_per_op,
+        "bound": "int" if int_us >= hbm_us else "hbm", "frac": max(int_us, hbm_us) / us_per_op,
+        "int_peak": "61 IMAD/clk/SM x 148 SMs x %.0f MHz (profiles/r01_int_pipe.txt), 11 multiplies per modular product" % sm_mhz,
     }
 
     # ---- e2e: host buffers through the C ABI ------------------------------------
@@ -448,7 +477,7 @@ def run_gpu(args):
                        "parallelism": "batch-sharded x%d, no collective" % world, "seed": SEED},
             "ntt": {"fwd_limb_ntt_per_s": ntt_fwd_rate, "inv_limb_ntt_per_s": ntt_inv_rate, "N": N,
                     "limbs_per_launch": nlimbs_launch, "fwd_us_per_launch": fwd_us, "inv_us_per_launch": inv_us},
-            "rotate": rotate, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "rotate": rotate, "roofline": roofline, "roofline_op": roofline_op, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -167,6 +167,112 @@ __global__ void __launch_bounds__(128) modup_fast_kernel(const ModUpArgs a) {
     }
 }
 
+// The same column form for 5..MAXSRC source limbs (every modulus below 2^61): BFV's tensor product extends 12 limbs
+// of Q to QMul and back (bfv/evaluator.go:300-372).  Sources are taken four at a time -- 8 cross terms below 2^61
+// fit the middle column -- and every group of four is folded into a 128-bit running sum (nsrc * 2^122 < 2^128);
+// one Montgomery reduction and a BRedAdd (the high word can exceed 2p) per target.  Constants sit in shared memory
+// (row = p, pinv, bredParams[0], c[nsrc], qpjinv[nsrc+1]); two coefficients per thread, 128-bit access.
+template <int MAXSRC>
+__global__ void __launch_bounds__(128) modup_wide_kernel(const ModUpArgs a) {
+    extern __shared__ u64 wtab[];
+    const ModUpTables& M = a.M;
+    const int nsrc = a.nsrc, ROW = 2 * nsrc + 4;
+    int ntg = 0;
+    for (int k = 0; k < a.nruns; ++k) ntg += a.ndst[k];
+    for (int e = threadIdx.x; e < ntg * ROW; e += blockDim.x) {
+        int idx = e / ROW, f = e - idx * ROW, tg = 0;
+        for (int k = 0, o = idx; k < a.nruns; ++k) {
+            if (o < a.ndst[k]) {
+                tg = a.tgt0[k] + o;
+                break;
+            }
+            o -= a.ndst[k];
+        }
+        u64 val;
+        if (f == 0)
+            val = M.dstQ[tg];
+        else if (f == 1)
+            val = M.dstQinv[tg];
+        else if (f == 2)
+            val = M.dstU0[tg];
+        else if (f < 3 + nsrc)
+            val = M.qispj[(size_t)(f - 3) * M.dst_total + tg];
+        else
+            val = M.qpjinv[(size_t)tg * (M.src_total + 1) + (f - 3 - nsrc)];
+        wtab[e] = val;
+    }
+    __syncthreads();
+    const u32 x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int bt = blockIdx.y;
+    if (x >= a.N) return;
+    u32 y0[MAXSRC][2], y1[MAXSRC][2];
+    u32 v[2];
+    {
+        double vi0 = 0.0, vi1 = 0.0;
+        const u64* in = a.in + bt * a.in_bs + x;
+#pragma unroll
+        for (int i = 0; i < MAXSRC; ++i) {
+            y0[i][0] = y0[i][1] = y1[i][0] = y1[i][1] = 0;
+            if (i < nsrc) {
+                const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(in + (size_t)i * a.N);
+                if (a.copy_out) *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x) = val;
+                const u64 qi = __ldg(M.srcQ + i), qib = __ldg(M.qib + i), qinv = __ldg(M.srcQinv + i);
+                const u64 ya = mred(val.x, qib, qi, qinv), yb = mred(val.y, qib, qi, qinv);
+                const double qd = __ull2double_rn(qi);
+                vi0 = __dadd_rn(vi0, __ddiv_rn(__ull2double_rn(ya), qd));  // :363-375, sequential as in the reference
+                vi1 = __dadd_rn(vi1, __ddiv_rn(__ull2double_rn(yb), qd));
+                y0[i][0] = (u32)ya;
+                y1[i][0] = (u32)(ya >> 32);
+                y0[i][1] = (u32)yb;
+                y1[i][1] = (u32)(yb >> 32);
+            }
+        }
+        v[0] = (u32)__double2ull_rz(vi0);
+        v[1] = (u32)__double2ull_rz(vi1);
+    }
+    int idx = 0;
+#pragma unroll 1
+    for (int k = 0; k < a.nruns; ++k) {
+        u64* out = a.out[k] + bt * a.out_bs[k] + x;
+#pragma unroll 1
+        for (int t = 0; t < a.ndst[k]; ++t, ++idx) {
+            const u64* row = wtab + idx * ROW;
+            const u64 pj = row[0], pinv = row[1], u0 = row[2];
+            u64 res[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                u64 slo = 0, shi = 0;
+#pragma unroll
+                for (int g = 0; g < MAXSRC; g += 4) {
+                    if (g < nsrc) {  // sources beyond nsrc hold zeros; their constants are read as zero below
+                        u64 A0 = 0, A1 = 0, A2 = 0;
+                        u32 cnt = 0;
+#pragma unroll
+                        for (int i = g; i < g + 4 && i < MAXSRC; ++i) {
+                            const u64 c = i < nsrc ? row[3 + i] : 0ull;
+                            const u32 c0 = (u32)c, c1 = (u32)(c >> 32);
+                            const u64 t0 = mul_wide(y0[i][e], c0);
+                            asm("add.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+l"(A0), "+r"(cnt) : "l"(t0));
+                            A1 = mad_wide(y0[i][e], c1, A1);
+                            A1 = mad_wide(y1[i][e], c0, A1);
+                            A2 = mad_wide(y1[i][e], c1, A2);
+                        }
+                        // (shi:slo) += A0 + (A1 << 32) + ((A2 + cnt) << 64)
+                        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;\n\t"
+                            "add.cc.u64 %0, %0, %4;\n\taddc.u64 %1, %1, %5;"
+                            : "+l"(slo), "+l"(shi)
+                            : "l"(A0), "l"(A2 + cnt), "l"(A1 << 32), "l"(A1 >> 32));
+                    }
+                }
+                shi += row[3 + nsrc + v[e]];
+                const u64 r = shi - mul_hi(mul_lo(slo, pinv), pj) + pj;  // REDC: congruent, below 2^64
+                res[e] = bred_add(r, pj, u0);
+            }
+            *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N) = make_ulonglong2(res[0], res[1]);
+        }
+    }
+}
+
 // FP64-quotient path for 1..4 source limbs whose moduli sum to less than 2^48 (every digit of the CKKS scale primes),
 // targets below 2^61.  The value to produce is R = (sum_i y_i*C_ij + qpjInv[j][v]) mod p_j with C_ij = Q/q_i mod p_j in
 // plain form (the canonical residue the reference's chain of MRed terms and its final BRedAdd return, :379-389).
@@ -452,6 +558,21 @@ int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
             case 3: modup_fast_kernel<3><<<fgrid, 128, 0, st>>>(a); break;
             default: modup_fast_kernel<4><<<fgrid, 128, 0, st>>>(a); break;
         }
+        lg_g_launches += 1;
+        return 0;
+    }
+    static const bool no_wide = getenv("LATTIGPU_NO_WIDE_MODUP") != nullptr;  // A/B switch
+    if (a.fast && !no_wide && a.nsrc > 4 && a.nsrc <= 16 && a.N >= 2) {
+        dim3 fgrid((a.N / 2 + 127) / 128, batch);
+        int ntg = 0;
+        for (int k = 0; k < a.nruns; ++k) ntg += a.ndst[k];
+        const size_t smem = (size_t)ntg * (2 * a.nsrc + 4) * sizeof(u64);  // at most 64 * 36 words = 18 KiB
+        if (a.nsrc <= 8)
+            modup_wide_kernel<8><<<fgrid, 128, smem, st>>>(a);
+        else if (a.nsrc <= 12)
+            modup_wide_kernel<12><<<fgrid, 128, smem, st>>>(a);
+        else
+            modup_wide_kernel<16><<<fgrid, 128, smem, st>>>(a);
         lg_g_launches += 1;
         return 0;
     }

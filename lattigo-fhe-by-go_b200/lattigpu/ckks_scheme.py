@@ -105,7 +105,8 @@ class KeyGenerator:
 
 class Encryptor:
     """pkEncryptor / skEncryptor (ckks/encryptor.go:13-362).  Plaintexts and ciphertexts are device polys over
-    Q in the NTT domain (batch of independent messages); pools are allocated per call.
+    Q in the NTT domain (batch of independent messages); the QP pools are kept per batch size like the reference's
+    encryptor.polypool (:16, :117-119) -- a synchronous cudaMalloc / cudaFree pair per call costs more than the ring ops.
 
     Like the reference, the non-fast paths hand the full QP pool to ModDownPQ(level, ...), which reads its
     "P part" at Coeffs[level+1 : level+1+#P] (ring_basis_extension.go:254): at the top level those are the
@@ -116,6 +117,12 @@ class Encryptor:
         self.pk, self.sk = pk, sk
         self.baseconverter = ring.NewFastBasisExtender(contextQ, contextP)
         self.nQ = contextQ.nl
+        self._pools = {}
+
+    def _pool(self, batch):
+        if batch not in self._pools:
+            self._pools[batch] = (self.contextQP.NewPoly(batch), self.contextQP.NewPoly(batch))
+        return self._pools[batch]
 
     def EncryptPk(self, level, plaintext, ctOut, u, e0, e1, fast=False, stream=None):
         """pkEncryptor.encrypt :179-237.  u: ternary coefficients [batch][N]; e0, e1: gaussian coefficients.
@@ -136,7 +143,7 @@ class Encryptor:
             up = signed_to_poly(K, u, batch)
             K.MForm(up, up, stream=stream)
             K.NTT(up, up, stream=stream)  # :206
-            p0, p1 = K.NewPoly(batch), K.NewPoly(batch)
+            p0, p1 = self._pool(batch)
             K.MulCoeffsMontgomery(up, self.pk[0], p0, stream=stream)  # :209
             K.MulCoeffsMontgomery(up, self.pk[1], p1, stream=stream)  # :211
             K.InvNTT(p0, p0, stream=stream)  # :214-215
@@ -163,7 +170,7 @@ class Encryptor:
             Q.Add(ctOut[0], ep, ctOut[0], stream=stream)
             Q.Copy(a, ctOut[1], stream=stream)  # :330
         else:
-            p0 = K.NewPoly(batch)
+            p0, _ = self._pool(batch)
             K.MulCoeffsMontgomery(a, self.sk, p0, stream=stream)  # :337
             K.Neg(p0, p0, stream=stream)
             K.InvNTT(p0, p0, stream=stream)  # :341

@@ -332,10 +332,11 @@ def test_div_by_last_modulus(lg, N, kind):
 # ---------------------------------------------------------------------------
 # FastBasisExtender (ring/ring_basis_extension.go:9-393), cf. ring_test.go:550
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("N,nQ,nP", [(32, 4, 4), (1 << 12, 2, 2), (1 << 13, 8, 3), (1 << 12, 12, 12)])
+@pytest.mark.parametrize("N,nQ,nP", [(32, 4, 4), (1 << 12, 2, 2), (1 << 13, 8, 3), (1 << 12, 12, 12), (1 << 12, 16, 4)])
 @pytest.mark.parametrize("kind", ["reduced", "words"])
 def test_basis_extender(lg, N, nQ, nP, kind):
-    Qm, Pm = QI60[-nQ:], PI60[-nP:]
+    # 5..16 source limbs take the wide column-form kernel (8 / 12 / 16 instantiations), 1..4 the fast ones
+    Qm, Pm = (QI60 + PI60[: nQ - 12] if nQ > 12 else QI60[-nQ:]), PI60[-nP:]
     rng = np.random.default_rng(N + nQ)
     oQ, oP = orc.Context(N, Qm), orc.Context(N, Pm)
     oe = orc.Extender(oQ, oP)
