@@ -192,6 +192,8 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     gring.set_device(local_rank)
     if world > 1:
+        # stdout carries the one JSON line: NCCL's own messages (the version banner under NCCL_DEBUG=VERSION/INFO) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
