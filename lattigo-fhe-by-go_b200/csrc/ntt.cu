@@ -753,7 +753,8 @@ __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const
         // beta products of a key word below 2^kb (kb = bits of q, at least 32: only the high halves are watched) and a
         // digit value below 3q fit 96 bits
         const int qbits = 64 - __clzll((long long)lc.q), kb = qbits < 32 ? 32 : qbits;
-        if (!a.acc64 && ((3ull * (u64)a.beta * lc.q) >> (96 - kb)) == 0) {
+        const int sh = 96 - kb;  // 50..64; a shift by 64 is not defined in C++: every product fits then
+        if (!a.acc64 && (sh >= 64 || ((3ull * (u64)a.beta * lc.q) >> sh) == 0)) {
             const u32 keyhi = ks_fused_body<M_F64, ACC_WIDE96>(a, lc, tl, ks_smem);
             if (__syncthreads_or((keyhi >> (kb - 32)) != 0)) ks_fused_body<M_F64, ACC_LAZY64>(a, lc, tl, ks_smem);
         } else {
