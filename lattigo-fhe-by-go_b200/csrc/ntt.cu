@@ -425,6 +425,9 @@ LG_DEV void prefetch_warp_tile_rows(u64* buf, const u64* __restrict__ src_tile) 
 // fetched with cp.async while entry i is transformed (same structure as the key-switch digit loop).
 // Single tile buffer (48 KiB of shared memory per CTA, 4 CTAs/SM): the fetch of entry i+1 is issued as soon
 // as entry i has left the buffer for good (after the exchange), and lands during the second register block.
+// Build-time variants of the fused digit loop (A/B numbers in profiles/README.md): resident CTAs per SM, and where the
+// 32 key words of a digit are loaded -- 0: in the multiply-accumulate, 1: before the last register block (needs
+// KS_MINB 2: 254 registers), 2: at the top of the iteration (spills).  The shipped build is 3 / 0.
 #ifndef KS_MINB
 #define KS_MINB 3
 #endif
