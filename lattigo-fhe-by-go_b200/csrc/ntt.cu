@@ -153,14 +153,17 @@ LG_DEV void inv_stages(u64 (&x)[16], const TwConst& c, u32 twbase, u32 stage) {
 // ---- stages with twiddles staged in shared memory ------------------------------
 // The 15 twiddles a register block needs (1 + 2 + 4 + 8 for stages u = 3..0) sit in heap order:
 // stage u uses slots [2^(3-u) - 1, 2^(4-u) - 1); w[g] = wp[(slot + g) * STRIDE], ws likewise from wsp.
+// Twiddles staged in shared memory sit as (w, ws) pairs -- pair of heap slot k at wp[2*k*STRIDE], 16-byte aligned --
+// so one 128-bit load brings both words of a butterfly group.
 template <int U, int STRIDE, int MODE>
-LG_DEV void fwd_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp) {
+LG_DEV void fwd_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp) {
     constexpr int NG = 16 >> (U + 1);
     constexpr int S0 = (8 >> U) - 1;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-        const u64 w = wp[(S0 + g) * STRIDE];
-        const u64 ws = (MODE != M_LITERAL) ? wsp[(S0 + g) * STRIDE] : 0ull;
+        const ulonglong2 pr = *reinterpret_cast<const ulonglong2*>(wp + 2 * (S0 + g) * STRIDE);
+        const u64 w = pr.x;
+        const u64 ws = (MODE != M_LITERAL) ? pr.y : 0ull;
         const double wd = __longlong_as_double((long long)ws);
         const double cw = (MODE == M_F64) ? shoup_cw(wd) : 0.0;
 #pragma unroll
@@ -179,21 +182,22 @@ LG_DEV void fwd_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u6
 }
 // stages UHI, ..., 0
 template <int UHI, int STRIDE, int MODE>
-LG_DEV void fwd_stages_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp) {
-    if (UHI >= 3) fwd_stage_sm<3, STRIDE, MODE>(x, c, wp, wsp);
-    if (UHI >= 2) fwd_stage_sm<2, STRIDE, MODE>(x, c, wp, wsp);
-    if (UHI >= 1) fwd_stage_sm<1, STRIDE, MODE>(x, c, wp, wsp);
-    fwd_stage_sm<0, STRIDE, MODE>(x, c, wp, wsp);
+LG_DEV void fwd_stages_sm(u64 (&x)[16], const TwConst& c, const u64* wp) {
+    if (UHI >= 3) fwd_stage_sm<3, STRIDE, MODE>(x, c, wp);
+    if (UHI >= 2) fwd_stage_sm<2, STRIDE, MODE>(x, c, wp);
+    if (UHI >= 1) fwd_stage_sm<1, STRIDE, MODE>(x, c, wp);
+    fwd_stage_sm<0, STRIDE, MODE>(x, c, wp);
 }
 template <int U, int STRIDE, int MODE>
-LG_DEV void inv_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp, u32 stage) {
+LG_DEV void inv_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, u32 stage) {
     constexpr int NG = 16 >> (U + 1);
     constexpr int S0 = (8 >> U) - 1;
     const u64 m = c.q << (stage + U + 1);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-        const u64 w = wp[(S0 + g) * STRIDE];
-        const u64 ws = (MODE != M_LITERAL) ? wsp[(S0 + g) * STRIDE] : 0ull;
+        const ulonglong2 pr = *reinterpret_cast<const ulonglong2*>(wp + 2 * (S0 + g) * STRIDE);
+        const u64 w = pr.x;
+        const u64 ws = (MODE != M_LITERAL) ? pr.y : 0ull;
 #pragma unroll
         for (int k = 0; k < (1 << U); ++k) {
             const int r = (g << (U + 1)) + k;
@@ -208,11 +212,11 @@ LG_DEV void inv_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u6
 }
 // stages 0, ..., UHI
 template <int UHI, int STRIDE, int MODE>
-LG_DEV void inv_stages_sm(u64 (&x)[16], const TwConst& c, const u64* wp, const u64* wsp, u32 stage) {
-    inv_stage_sm<0, STRIDE, MODE>(x, c, wp, wsp, stage);
-    if (UHI >= 1) inv_stage_sm<1, STRIDE, MODE>(x, c, wp, wsp, stage);
-    if (UHI >= 2) inv_stage_sm<2, STRIDE, MODE>(x, c, wp, wsp, stage);
-    if (UHI >= 3) inv_stage_sm<3, STRIDE, MODE>(x, c, wp, wsp, stage);
+LG_DEV void inv_stages_sm(u64 (&x)[16], const TwConst& c, const u64* wp, u32 stage) {
+    inv_stage_sm<0, STRIDE, MODE>(x, c, wp, stage);
+    if (UHI >= 1) inv_stage_sm<1, STRIDE, MODE>(x, c, wp, stage);
+    if (UHI >= 2) inv_stage_sm<2, STRIDE, MODE>(x, c, wp, stage);
+    if (UHI >= 3) inv_stage_sm<3, STRIDE, MODE>(x, c, wp, stage);
 }
 
 // Strided phase twiddles: group 0 = the subtree under node 1 (the block on the top four stages, the same
@@ -226,8 +230,8 @@ LG_DEV void fill_strided_tw(u64* tws_sm, const TwConst& c) {
         const u32 lvl = 31 - __clz(k + 1);
         const u32 node = grp == 0 ? 1u : (u32)(G + grp - 1);
         const u32 idx = (node << lvl) + (k + 1 - (1u << lvl));
-        tws_sm[grp * 32 + k] = __ldg(c.tw + idx);
-        if (!LIT) tws_sm[grp * 32 + 15 + k] = __ldg(c.tws + idx);
+        tws_sm[grp * 32 + 2 * k] = __ldg(c.tw + idx);
+        if (!LIT) tws_sm[grp * 32 + 2 * k + 1] = __ldg(c.tws + idx);
     }
 }
 
@@ -311,7 +315,7 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
         }
     }
     __syncthreads();
-    fwd_stages_sm<3, 1, MODE>(x, c, tws_sm, tws_sm + 15);
+    fwd_stages_sm<3, 1, MODE>(x, c, tws_sm);
     if (N2 > 0) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) sm[(g + r * G) * W + col] = x[r];
@@ -319,7 +323,7 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = sm[(16 * g + r) * W + col];
         const u64* twg = tws_sm + (1 + g) * 32;
-        fwd_stages_sm<(N2 > 0 ? N2 - 1 : 0), 1, MODE>(x, c, twg, twg + 15);
+        fwd_stages_sm<(N2 > 0 ? N2 - 1 : 0), 1, MODE>(x, c, twg);
         u64* out = s.out + colg + g * 16 * 256;
 #pragma unroll
         for (int r = 0; r < 16; ++r) out[r * 256] = x[r];
@@ -336,7 +340,7 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
 template <int L, bool LITERAL>
 __global__ void __launch_bounds__(256, STRIDED_MINB) ntt_fwd_strided(const NttArgs a) {
     __shared__ u64 sm[(L - 4) > 0 ? 4096 : 1];
-    __shared__ u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
+    __shared__ __align__(16) u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
     const LimbSetup s = setup_limb(a);
     if (s.skip) return;
     const int mode = LITERAL ? M_LITERAL : fwd_mode(s.c.q);
@@ -390,10 +394,10 @@ LG_DEV void contig_fill_tw(const TwConst& c, u32 N, u32 segbase, u32 cc, u64* tw
     const u32 tb = N + segbase + 16 * cc;
 #define LG_FILL(U, SLOT)                                                    \
     load_tw<true, (16 >> (U + 1))>(w, c.tw, tb >> (U + 1));                 \
-    _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[(SLOT + g) * CONTIG_THREADS] = w[g]; \
+    _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[2 * (SLOT + g) * CONTIG_THREADS] = w[g]; \
     if (MODE != M_LITERAL) {                                                \
         load_tw<true, (16 >> (U + 1))>(w, c.tws, tb >> (U + 1));            \
-        _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[(15 + SLOT + g) * CONTIG_THREADS] = w[g]; \
+        _Pragma("unroll") for (int g = 0; g < (16 >> (U + 1)); ++g) twp[2 * (SLOT + g) * CONTIG_THREADS + 1] = w[g]; \
     }
     LG_FILL(3, 0)
     LG_FILL(2, 1)
@@ -403,8 +407,8 @@ LG_DEV void contig_fill_tw(const TwConst& c, u32 N, u32 segbase, u32 cc, u64* tw
     if (cc < 15) {  // node m = (N + segbase) >> 8 and its 15 descendants in heap order
         const u32 lvl = 31 - __clz(cc + 1);
         const u32 idx = (((N + segbase) >> 8) << lvl) + (cc + 1 - (1u << lvl));
-        twseg[cc] = __ldg(c.tw + idx);
-        if (MODE != M_LITERAL) twseg[15 + cc] = __ldg(c.tws + idx);
+        twseg[2 * cc] = __ldg(c.tw + idx);
+        if (MODE != M_LITERAL) twseg[2 * cc + 1] = __ldg(c.tws + idx);
     }
 }
 
@@ -446,7 +450,7 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
     const u32 e0 = segbase + 16 * cc, j0 = segbase + cc;
     u64* const tilebuf = smem;
     u64* const buf = smem + sg * 256;
-    u64* const twp = smem + 2048 + t;
+    u64* const twp = smem + 2048 + 2 * t;  // private (w, ws) pairs: slot k at twp[2*k*CONTIG_THREADS]
     u64* const twseg = smem + 2048 + 30 * CONTIG_THREADS + sg * 32;
     const u64* src = a.in + (size_t)b0 * a.in_bstride + (size_t)j * N + tile0;
     u64* dst = a.out + (size_t)b0 * a.out_bstride + (size_t)j * N;
@@ -463,7 +467,7 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
         if (FWD) {
 #pragma unroll
             for (int r = 0; r < 16; ++r) x[r] = buf[cc + 16 * r];
-            fwd_stages_sm<3, 1, MODE>(x, c, twseg, twseg + 15);
+            fwd_stages_sm<3, 1, MODE>(x, c, twseg);
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < 16; ++r) buf[16 * r + (cc ^ r)] = x[r];
@@ -472,7 +476,7 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
             for (int r = 0; r < 16; ++r) x[r] = buf[16 * cc + (r ^ cc)];
             __syncwarp();
             if (i + 1 < nb) prefetch_warp_tile(tilebuf, src + (size_t)(i + 1) * a.in_bstride);
-            fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS);
+            fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp);
             if (TAIL) {
                 // the caller's (x - NTT(y)) * s_j tail (+ add) on the canonical transform, straight from the registers
                 const int bi = b0 + i, set = bi >= a.tail.split ? 1 : 0;
@@ -511,7 +515,7 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
                 x[2 * pp] = v.x;
                 x[2 * pp + 1] = v.y;
             }
-            inv_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS, 0u);
+            inv_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, 0u);
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < 16; ++r) buf[16 * cc + (r ^ cc)] = x[r];
@@ -520,7 +524,7 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
             for (int r = 0; r < 16; ++r) x[r] = buf[16 * r + (cc ^ r)];
             __syncwarp();
             if (i + 1 < nb) prefetch_warp_tile_rows(tilebuf, src + (size_t)(i + 1) * a.in_bstride);
-            inv_stages_sm<3, 1, MODE>(x, c, twseg, twseg + 15, 4u);
+            inv_stages_sm<3, 1, MODE>(x, c, twseg, 4u);
 #pragma unroll
             for (int r = 0; r < 16; ++r) dst[j0 + 16 * r] = x[r];
         }
@@ -630,8 +634,8 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
     const u32 segbase = tile0 + sg * 256u;
     const u32 e0 = segbase + 16 * cc;
     u64* const tilebuf = smem;                        // [2][2048]
-    u64* const twp = smem + 2 * 2048 + t;             // private slots: w at slot*128, ws at (15+slot)*128
-    u64* const twseg = smem + 2 * 2048 + 30 * CONTIG_THREADS + sg * 32;  // w at [k], ws at [15+k]
+    u64* const twp = smem + 2 * 2048 + 2 * t;         // private (w, ws) pairs: slot k at twp[2*k*CONTIG_THREADS]
+    u64* const twseg = smem + 2 * 2048 + 30 * CONTIG_THREADS + sg * 32;  // segment pairs: slot k at twseg[2*k]
 
     const u64* din = a.D + (size_t)b * a.d_bs + (size_t)j * N + tile0;
     const int own_i = (a.limb0 + j < a.nl) ? (a.limb0 + j) / a.alpha : -1;  // the digit whose own limb this is
@@ -686,7 +690,7 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
         } else {
 #pragma unroll
             for (int r = 0; r < 16; ++r) x[r] = buf[cc + 16 * r];
-            fwd_stages_sm<3, 1, MODE>(x, c, twseg, twseg + 15);
+            fwd_stages_sm<3, 1, MODE>(x, c, twseg);
             __syncwarp();
             // exchange in place, XOR-swizzled (word 16r+cc at 16r + (cc^r)): conflict-free both ways
 #pragma unroll
@@ -697,7 +701,7 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
 #if KS_KEYPREFETCH == 1
             ks_load_keys(kk0, kk1, key, a.evk_hs);  // in flight during the second register block
 #endif
-            fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, twp + 15 * CONTIG_THREADS);
+            fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp);
             if (ACC == ACC_WIDE96) {
 #pragma unroll
                 for (int r = 0; r < 16; ++r) x[r] = reduce_f64(x[r], qd1, cq1, c.nq);
@@ -802,14 +806,14 @@ LG_DEV void inv_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
     __syncthreads();
     if (N2 > 0) {
         const u64* twg = tws_sm + (1 + g) * 32;
-        inv_stages_sm<(N2 > 0 ? N2 - 1 : 0), 1, MODE>(x, c, twg, twg + 15, 8u);
+        inv_stages_sm<(N2 > 0 ? N2 - 1 : 0), 1, MODE>(x, c, twg, 8u);
 #pragma unroll
         for (int r = 0; r < 16; ++r) sm[(16 * g + r) * W + col] = x[r];
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = sm[(g + r * G) * W + col];
     }
-    inv_stages_sm<3, 1, MODE>(x, c, tws_sm, tws_sm + 15, 8u + N2);
+    inv_stages_sm<3, 1, MODE>(x, c, tws_sm, 8u + N2);
     // ring/ntt.go:136-138
     u64* out = s.out + colg + g * 256;
     if (MODE == M_LITERAL) {
@@ -826,7 +830,7 @@ LG_DEV void inv_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
 template <int L, bool LITERAL>
 __global__ void __launch_bounds__(256, STRIDED_MINB) ntt_inv_strided(const NttArgs a) {
     __shared__ u64 sm[(L - 4) > 0 ? 4096 : 1];
-    __shared__ u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
+    __shared__ __align__(16) u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
     const LimbSetup s = setup_limb(a);
     if (s.skip) return;
     const int mode = (LITERAL || inv_flagged(a)) ? M_LITERAL : inv_mode(s.c.q);
