@@ -35,6 +35,13 @@ PARAMS_ID = 4  # ckks.PN16QP1761
 WORKLOAD = "CKKS PN16QP1761 (N=2^16, 34+4 limbs, level 33): MulRelin+Rescale, batch of independent ciphertexts"
 
 
+def workload(params_id):
+    """config.workload: the headline set by default; --params runs another ckks.DefaultParams entry and says so"""
+    if params_id == PARAMS_ID:
+        return WORKLOAD
+    return "CKKS DefaultParams[%d] at the top level: MulRelin+Rescale, batch of independent ciphertexts (not the headline set)" % params_id
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -118,9 +125,10 @@ def run_reference(args):
     sample = "%d MulRelin+Rescale ops per step (one oracle evaluator per host thread), median of %d steps" % (nops, len(vals))
     line = {
         "impl": "reference", "metric": "CKKS MulRelin+Rescale ops/s at logN=16 (batched)", "value": value,
-        "unit": "ops/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 1, "ms_per_step": 1e3 * nops / value,
+        "unit": "ops/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 1 if args.warmup > 0 else 0,
+        "ms_per_step": 1e3 * nops / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": nops},
+        "config": {"workload": workload(args.params), "batch_per_step": nops},
         "cpu_baseline": {"value": value, "unit": "ops/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -473,7 +481,7 @@ def run_gpu(args):
             "metric": "CKKS MulRelin+Rescale ops/s at logN=16 (batched)", "value": value, "unit": "ops/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "level": level,
+            "config": {"workload": workload(args.params), "batch_per_gpu": B, "global_batch": B * world, "level": level,
                        "l2_policy": "inputs+key larger than L2 (%.0f MiB per step per GPU), no flush" %
                                     ((4 * B * nQ + 2 * beta * (nQ + nP)) * N * 8 / 2**20),
                        "parallelism": "batch-sharded x%d, no collective" % world, "seed": SEED},

@@ -6,6 +6,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -68,3 +69,27 @@ def test_sass_is_sm100a(built):
     out = subprocess.check_output(["cuobjdump", "-lelf", built], text=True)
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): one JSON line with the contract's
+    keys, no GPU work.  Run on the smallest parameter set so the check takes a second."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--params", "0",
+                          "--cpu-sample", "2", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "ops/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "not the headline set" in d["config"]["workload"]
+    # under torchrun only rank 0 works: the other ranks exit 0 without output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
