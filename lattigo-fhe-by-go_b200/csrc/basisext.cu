@@ -285,7 +285,9 @@ __global__ void __launch_bounds__(128) modup_wide_kernel(const ModUpArgs a) {
 //     into the K_v table entry, and one conditional subtraction canonicalises.
 // 16 integer multiply-adds, 6 FP64 operations and one CRed per target coefficient instead of the 128-bit
 // column sums and the Montgomery reduction of modup_fast_kernel.
-template <int NSRC>
+// LAZY: the result is left in [0, 2p) (no conditional subtraction) -- for the key-switch digits, whose only reader
+// is the forward NTT (exact for any input below its headroom).
+template <int NSRC, bool LAZY>
 __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
     constexpr int ROW = 4 * NSRC + 5;  // np, p, 1/p, C[NSRC], Cd[NSRC], K'[NSRC+1], Kd[NSRC+1]
     constexpr int O_C = 3, O_CD = 3 + NSRC, O_K = 3 + 2 * NSRC, O_KD = 4 + 3 * NSRC;
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
                 acc = mad_wide((u32)tb, (u32)np, acc);
                 h = mad_lo32((u32)tb, (u32)(np >> 32), h);
                 h = mad_lo32((u32)(tb >> 32), (u32)np, h);
-                res[e] = cred(acc + ((u64)h << 32), pj);
+                res[e] = LAZY ? acc + ((u64)h << 32) : cred(acc + ((u64)h << 32), pj);
             }
             *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N) = make_ulonglong2(res[0], res[1]);
         }
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
 // themselves rounded down) -- so that r1 = S + K_v - qh1*p lies in [0, (2^SH + 8 * 2^-52 * sum_i q_i + 2) * p) (eight downward roundings), which
 // the host checks to be below 2^64 for every target before choosing this kernel.  A second quotient on r1 (converted
 // rounding down) leaves [0, 2p) and one conditional subtraction.  Everything integer is mod 2^64 as in modup_fp_kernel.
-template <int NSRC>
+template <int NSRC, bool LAZY>
 __global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
     constexpr int ROW = 3 * NSRC + 6;  // np << SH, p, 1/p, bits(2^52) * p, np, C[NSRC], Cd[NSRC], K'[NSRC+1]
     constexpr int O_C = 5, O_CD = 5 + NSRC, O_K = 5 + 2 * NSRC;
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
                 u64 r2 = mad_wide((u32)t2, (u32)np, r1 + c52);
                 u32 h2 = mad_lo32((u32)t2, (u32)(np >> 32), (u32)(t2 >> 32) * (u32)np);
                 r2 += (u64)h2 << 32;
-                res[e] = cred(r2, pj);
+                res[e] = LAZY ? r2 : cred(r2, pj);
             }
             *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N) = make_ulonglong2(res[0], res[1]);
         }
@@ -528,24 +530,44 @@ __global__ void __launch_bounds__(256) fanout_kernel(const FanoutArgs a) {
 int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
     if (batch <= 0) return 0;
     static const bool no_fp = getenv("LATTIGPU_NO_FP_MODUP") != nullptr;  // A/B switch
+    static const bool no_lazy = getenv("LATTIGPU_NO_LAZY_MODUP") != nullptr;  // A/B switch
+    const bool lazy = a.lazy_out && !no_lazy;
     if (a.fast == 2 && !no_fp && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
         dim3 fgrid((a.N / 2 + 127) / 128, batch);
-        switch (a.nsrc) {
-            case 1: modup_fp_kernel<1><<<fgrid, 128, 0, st>>>(a); break;
-            case 2: modup_fp_kernel<2><<<fgrid, 128, 0, st>>>(a); break;
-            case 3: modup_fp_kernel<3><<<fgrid, 128, 0, st>>>(a); break;
-            default: modup_fp_kernel<4><<<fgrid, 128, 0, st>>>(a); break;
+        if (lazy) {
+            switch (a.nsrc) {
+                case 1: modup_fp_kernel<1, true><<<fgrid, 128, 0, st>>>(a); break;
+                case 2: modup_fp_kernel<2, true><<<fgrid, 128, 0, st>>>(a); break;
+                case 3: modup_fp_kernel<3, true><<<fgrid, 128, 0, st>>>(a); break;
+                default: modup_fp_kernel<4, true><<<fgrid, 128, 0, st>>>(a); break;
+            }
+        } else {
+            switch (a.nsrc) {
+                case 1: modup_fp_kernel<1, false><<<fgrid, 128, 0, st>>>(a); break;
+                case 2: modup_fp_kernel<2, false><<<fgrid, 128, 0, st>>>(a); break;
+                case 3: modup_fp_kernel<3, false><<<fgrid, 128, 0, st>>>(a); break;
+                default: modup_fp_kernel<4, false><<<fgrid, 128, 0, st>>>(a); break;
+            }
         }
         lg_g_launches += 1;
         return 0;
     }
     if (a.fast == 3 && !no_fp && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
         dim3 fgrid((a.N / 2 + 127) / 128, batch);
-        switch (a.nsrc) {
-            case 1: modup_fp2_kernel<1><<<fgrid, 128, 0, st>>>(a); break;
-            case 2: modup_fp2_kernel<2><<<fgrid, 128, 0, st>>>(a); break;
-            case 3: modup_fp2_kernel<3><<<fgrid, 128, 0, st>>>(a); break;
-            default: modup_fp2_kernel<4><<<fgrid, 128, 0, st>>>(a); break;
+        if (lazy) {
+            switch (a.nsrc) {
+                case 1: modup_fp2_kernel<1, true><<<fgrid, 128, 0, st>>>(a); break;
+                case 2: modup_fp2_kernel<2, true><<<fgrid, 128, 0, st>>>(a); break;
+                case 3: modup_fp2_kernel<3, true><<<fgrid, 128, 0, st>>>(a); break;
+                default: modup_fp2_kernel<4, true><<<fgrid, 128, 0, st>>>(a); break;
+            }
+        } else {
+            switch (a.nsrc) {
+                case 1: modup_fp2_kernel<1, false><<<fgrid, 128, 0, st>>>(a); break;
+                case 2: modup_fp2_kernel<2, false><<<fgrid, 128, 0, st>>>(a); break;
+                case 3: modup_fp2_kernel<3, false><<<fgrid, 128, 0, st>>>(a); break;
+                default: modup_fp2_kernel<4, false><<<fgrid, 128, 0, st>>>(a); break;
+            }
         }
         lg_g_launches += 1;
         return 0;

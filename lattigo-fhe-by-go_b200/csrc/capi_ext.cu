@@ -302,7 +302,7 @@ int lg_extender_moddown_splited_qp(const lg_extender* e, int levelQ, int levelP,
 // second target loop starts at alpha*crt, :548 / :664), so only the conversion
 // is materialised.
 int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u64* p0, size_t p0_bs, u64* outQ,
-                  size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st) {
+                  size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st, bool lazy_out) {
     LG_REQUIRE(level >= 0 && level < d->nQ, "Decompose: level %d out of range", level);
     LG_REQUIRE(crt >= 0 && crt < d->beta, "Decompose: digit %d out of range", crt);
     const int alphai = d->xalpha[crt];
@@ -353,6 +353,7 @@ int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u
     a.tgt0[1] = d->nQ;
     a.copy_out = nullptr;
     a.fast = m.fast_level(a.nsrc, &a.fp_shift);
+    a.lazy_out = lazy_out ? 1 : 0;
     if (lg_launch_modup(a, batch, st) != 0) {
         lg_set_error("Decompose: too many source limbs");
         return LG_ERR_ARG;
@@ -452,8 +453,9 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
             const size_t d_ds = (size_t)cb * d_bs;
             for (int i = 0; i < beta; ++i) {
                 u64* Di = D.d + (size_t)i * d_ds;
+                // the digits are read by the forward NTT alone: no conditional subtraction needed
                 LG_TRY(lgi_decompose(dec, level, i, cb, coef + (size_t)b0 * coef_bs, coef_bs, Di, d_bs, Di + (size_t)nl * N,
-                                     d_bs, st));
+                                     d_bs, st, true));
             }
             NttArgs a;
             memset(&a, 0, sizeof(a));
@@ -826,7 +828,7 @@ int lg_ckks_hoist(lg_ckks_eval* e, int level, const lg_poly* c1, lg_hoisted** ou
     // (one digit-batched launch pair), the digit's own limbs copied from the NTT-domain input (:1579-1584)
     for (int i = 0; i < beta; ++i) {
         u64* Di = h->d + (size_t)i * h->d_ds;
-        rc = lgi_decompose(e->dec.get(), level, i, batch, c2.d, c2_bs, Di, h->d_bs, Di + (size_t)nl * N, h->d_bs, st);
+        rc = lgi_decompose(e->dec.get(), level, i, batch, c2.d, c2_bs, Di, h->d_bs, Di + (size_t)nl * N, h->d_bs, st, true);
         if (rc != LG_OK) return fail(rc);
         const int p0 = i * alpha, p1 = (p0 + alpha < nl) ? p0 + alpha : nl;
         rc = lgi_ew(EW_COPY, Q, limb_map_identity(), p1 - p0, batch, c1->d + (size_t)p0 * N, c1->bstride, nullptr, 0,

@@ -189,8 +189,9 @@ int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* 
 int lgi_moddown_pair_ntt(const lg_extender* e, int level, int batch, u64* acc0, u64* acc1, size_t acc_bs, int p_off, u64* out0,
                          size_t out0_bs, bool add0, u64* out1, size_t out1_bs, bool add1, bool ntt, cudaStream_t st,
                          bool p_in_range);
+// lazy_out: the converted limbs may be left in [0, 2p) (callers whose only reader is the forward NTT)
 int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u64* p0, size_t p0_bs, u64* outQ,
-                  size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st);
+                  size_t outQ_bs, u64* outP, size_t outP_bs, cudaStream_t st, bool lazy_out = false);
 int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, const lg_decomposer* dec, int level, int beta,
                          int batch, const u64* coef, size_t coef_bs, const u64* nttd, size_t nttd_bs, const lg_swk* evk,
                          u64* d, u64* acc0, u64* acc1, size_t d_bs, int cadence, cudaStream_t st);

@@ -184,6 +184,7 @@ struct ModUpArgs {
     int fast;            // 1: every modulus is below 2^61 (modup_fast_kernel); 2: and the sources sum below 2^48 (modup_fp_kernel);
                          // 3: two-step FP64 quotient at granularity 2^fp_shift (modup_fp2_kernel)
     int fp_shift;
+    int lazy_out;        // FP64 kernels only: leave the results in [0, 2p) (key-switch digits, read by the forward NTT alone)
 };
 int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st);
 
