@@ -79,7 +79,7 @@ int ModUpDev::build(const u64* Q, int nq, const u64* P, int np) {
 
 // modUpExact (:352-393) on `nsrc` source limbs into `ndst` target limbs tgt0..
 int lgi_modup_launch(const ModUpDev& m, u64 N, int batch, const u64* in, size_t in_bs, int nsrc, u64* out,
-                        size_t out_bs, int ndst, int tgt0, cudaStream_t st) {
+                        size_t out_bs, int ndst, int tgt0, cudaStream_t st, bool lazy_out) {
     LG_REQUIRE(nsrc >= 1 && nsrc <= m.nsrc && ndst >= 0 && tgt0 + ndst <= m.ndst, "modUpExact: basis out of range");
     ModUpArgs a;
     memset(&a, 0, sizeof(a));
@@ -95,6 +95,7 @@ int lgi_modup_launch(const ModUpDev& m, u64 N, int batch, const u64* in, size_t 
     a.tgt0[0] = tgt0;
     a.copy_out = nullptr;
     a.fast = m.fast_level(a.nsrc, &a.fp_shift);
+    a.lazy_out = lazy_out ? 1 : 0;
     if (lg_launch_modup(a, batch, st) != 0) {
         lg_set_error("modUpExact: too many source limbs (%d)", nsrc);
         return LG_ERR_ARG;
@@ -123,6 +124,11 @@ static int check_p(const lg_poly* p, u64 N, int nl, int batch, const char* what)
     return LG_OK;
 }
 
+static bool no_tail_canon() {  // A/B switch
+    static const bool v = getenv("LATTIGPU_NO_TAIL_CANON") != nullptr;
+    return v;
+}
+
 // Shared tail of every ModDown*: tmp = modUp(P part -> Q[:level+1]); optionally
 // NTT(tmp); p2 = MRed(p1Q + (q - tmp), P^-1)   (:219-240, :254-273, :287-306)
 // accumulate = true adds the result into p2 with CRed (the AddLvl the evaluators apply right after).
@@ -138,13 +144,15 @@ int lgi_moddown_tail_ntt(const lg_extender* e, int level, int batch, const u64* 
     Scratch tmp(st);
     LG_TRY(tmp.alloc((size_t)batch * nl * N));
     const size_t tbs = (size_t)nl * N;
-    LG_TRY(lgi_modup_launch(e->pq, N, batch, p1P, p1P_bs, P->nl, tmp.d, tbs, nl, 0, st));
+    // (with `ntt` the forward transform is the only reader of tmp: the conversion may stay in [0, 2q))
+    LG_TRY(lgi_modup_launch(e->pq, N, batch, p1P, p1P_bs, P->nl, tmp.d, tbs, nl, 0, st, ntt));
     if (ntt && lgi_ntt_tail_ok(Q)) {  // :228-238 in one pass
         NttTail t;
         memset(&t, 0, sizeof(t));
         t.enabled = 1;
         t.split = batch;
         t.add[0] = accumulate ? 1 : 0;
+        t.a_canon = (p_in_range && !no_tail_canon()) ? 1 : 0;  // internal callers only: canonical key-switch accumulators
         t.a[0] = p1Q;
         t.a_bs[0] = p1Q_bs;
         t.out[0] = p2;
@@ -178,7 +186,7 @@ int lgi_moddown_pair_ntt(const lg_extender* e, int level, int batch, u64* acc0, 
     Scratch tmp(st);
     LG_TRY(tmp.alloc((size_t)2 * batch * nl * N));
     const size_t tbs = (size_t)nl * N;
-    LG_TRY(lgi_modup_launch(e->pq, N, 2 * batch, pP, acc_bs, P->nl, tmp.d, tbs, nl, 0, st));
+    LG_TRY(lgi_modup_launch(e->pq, N, 2 * batch, pP, acc_bs, P->nl, tmp.d, tbs, nl, 0, st, ntt));
     if (ntt && lgi_ntt_tail_ok(Q)) {  // both tails ride on the last phase of the one transform over 2*batch entries
         NttTail t;
         memset(&t, 0, sizeof(t));
@@ -186,6 +194,7 @@ int lgi_moddown_pair_ntt(const lg_extender* e, int level, int batch, u64* acc0, 
         t.split = batch;
         t.add[0] = add0 ? 1 : 0;
         t.add[1] = add1 ? 1 : 0;
+        t.a_canon = (p_in_range && !no_tail_canon()) ? 1 : 0;
         t.a[0] = acc0;
         t.a[1] = acc1;
         t.a_bs[0] = t.a_bs[1] = acc_bs;

@@ -197,6 +197,6 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
                          u64* d, u64* acc0, u64* acc1, size_t d_bs, int cadence, cudaStream_t st);
 int lgi_concat_ring(const lg_ring* Q, const lg_ring* P, std::unique_ptr<lg_ring>& out);
 int lgi_modup_launch(const ModUpDev& m, u64 N, int batch, const u64* in, size_t in_bs, int nsrc, u64* out, size_t out_bs,
-                     int ndst, int tgt0, cudaStream_t st);
+                     int ndst, int tgt0, cudaStream_t st, bool lazy_out = false);
 int lgi_div_by_last_modulus(const lg_ring* r, int nl, int batch, u64* p0, size_t bs, bool round, bool ntt,
                             cudaStream_t st);

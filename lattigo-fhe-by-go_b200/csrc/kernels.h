@@ -22,6 +22,7 @@ struct NttTail {
     u64* out[2];
     size_t a_bs[2], out_bs[2];
     const u64* s;  // device array, one scalar per data limb (kept out of the kernel parameters: every NTT CTA loads those)
+    int a_canon;   // the words of a[] are known to be below q (key-switch accumulators): the transform is subtracted unreduced
 };
 // Broadcast input of the forward transform's first phase (logN >= 12): every data limb j transforms the same source
 // limb plus a per-limb constant, x_j = v + add[j] (unreduced) -- the rescaling's "last limb to every other limb"

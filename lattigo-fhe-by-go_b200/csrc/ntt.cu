@@ -485,13 +485,22 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
                 u64* to = a.tail.out[set] + bb * a.tail.out_bs[set] + (size_t)j * N + e0;
                 const u64 sj = __ldg(a.tail.s + j);
                 const bool add = a.tail.add[set] != 0;
+                const bool canon = a.tail.a_canon != 0;
+                const u64 kq = ((lc.u0 >> 12) + 1) * c.q;  // the first multiple of q above 2^52 (u0 = floor(2^64/q))
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     u64 va[4], r[4];
                     ld256(va, ta + 4 * h);
+                    if (MODE == M_F64 && canon) {
+                        // va < q and x < 2^52 (FP64 transform): va + (kq - x) is positive, below 2^53 and congruent, so the
+                        // one canonical word MRed + CRed returns is the reference's
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        r[e] = mred(va[e] + (c.q - bred_add(x[4 * h + e], c.q, lc.u0)), sj, c.q, c.qinv);
+                        for (int e = 0; e < 4; ++e) r[e] = mred(va[e] + (kq - x[4 * h + e]), sj, c.q, c.qinv);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            r[e] = mred(va[e] + (c.q - bred_add(x[4 * h + e], c.q, lc.u0)), sj, c.q, c.qinv);
+                    }
                     if (add) {
                         u64 vo[4];
                         ld256(vo, to + 4 * h);
