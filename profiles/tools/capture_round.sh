@@ -1,7 +1,7 @@
 # End-of-round evidence: GPU tests, bench line, launch list, ncu --set full of one step and of the NTT launch pair,
 # the other BASELINE configurations.  Run on the GPU box from the repo root; outputs land in gpurun_out/.
 set -x
-V=${1:-v7}
+V=${1:-v9}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r01_gpu_tests_$V.log 2>&1; echo "tests rc=$?"
 python bench.py > gpurun_out/r01_bench_$V.json 2> gpurun_out/r01_bench_$V.err; echo "bench rc=$?"
