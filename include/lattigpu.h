@@ -56,12 +56,26 @@ typedef void* lg_stream_t;                  /* cudaStream_t */
 const char* lg_last_error(void);
 const char* lg_version(void);
 int lg_device_count(int* count);
+/* Sets the calling thread's current device (objects are created on it).  Every handle remembers the device it was
+ * created on (wrapped pointers: the device that owns the pointer), and every entry point that touches the GPU switches
+ * to its handles' device for the duration of the call and restores the caller's -- a Go host whose goroutines migrate
+ * between OS threads, or one process driving several GPUs, needs no further care (SURVEY.md 8(b) Threading).
+ * Operands that live on different devices return LG_ERR_ARG. */
 int lg_set_device(int device);
 int lg_stream_create(lg_stream_t* stream);
 int lg_stream_destroy(lg_stream_t stream);
 int lg_stream_sync(lg_stream_t stream);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t lg_launch_count(void);
+/* Diagnostic A/B switches.  They select between kernel variants that return IDENTICAL words (every variant is
+ * parity-tested); they exist for cross-checks and profiling, not for tuning by users.  Each is initialised ONCE per
+ * process from the environment variable LATTIGPU_<NAME IN UPPER CASE> (no getenv on any launch path) and can then only
+ * be changed through this call.  Names (value 0/1 unless noted): "literal_ntt" (literal Butterfly/InvButterfly of
+ * ring/ntt.go:32-50 in every transform), "ks_acc64" (64-bit instead of 96-bit key-switch accumulators),
+ * "no_fp_modup" / "no_lazy_modup" / "no_wide_modup" (basis-extension kernel choice), "no_tail_canon" /
+ * "no_fused_tail" (ModDown / rescale tail placement), "ks_scratch_words" (value = digit scratch budget of the key
+ * switch in 64-bit words, 0 restores the 6 GiB default).  Unknown names return LG_ERR_ARG. */
+int lg_debug_set_switch(const char* name, uint64_t value);
 
 /* ---- ring.Context -------------------------------------------------------- */
 /* NewContextWithParams = SetParameters + GenNTTParams, ring_context.go:60-209:

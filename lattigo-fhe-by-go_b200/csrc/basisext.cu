@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(256) fanout_kernel(const FanoutArgs a) {
 
 int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
     if (batch <= 0) return 0;
-    static const bool no_fp = getenv("LATTIGPU_NO_FP_MODUP") != nullptr;  // A/B switch
-    static const bool no_lazy = getenv("LATTIGPU_NO_LAZY_MODUP") != nullptr;  // A/B switch
+    const bool no_fp = lg_switches().no_fp_modup.load(std::memory_order_relaxed) != 0;
+    const bool no_lazy = lg_switches().no_lazy_modup.load(std::memory_order_relaxed) != 0;
     const bool lazy = a.lazy_out && !no_lazy;
     if (a.fast == 2 && !no_fp && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
         dim3 fgrid((a.N / 2 + 127) / 128, batch);
@@ -583,7 +583,7 @@ int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
         lg_g_launches += 1;
         return 0;
     }
-    static const bool no_wide = getenv("LATTIGPU_NO_WIDE_MODUP") != nullptr;  // A/B switch
+    const bool no_wide = lg_switches().no_wide_modup.load(std::memory_order_relaxed) != 0;
     if (a.fast && !no_wide && a.nsrc > 4 && a.nsrc <= 16 && a.N >= 2) {
         dim3 fgrid((a.N / 2 + 127) / 128, batch);
         int ntg = 0;

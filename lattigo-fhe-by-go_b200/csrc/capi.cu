@@ -8,6 +8,8 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "capi_internal.hpp"
 
 std::atomic<uint64_t> lg_g_launches{0};
@@ -23,9 +25,100 @@ void lg_set_error(const char* fmt, ...) {
 
 static inline cudaStream_t cs(lg_stream_t s) { return (cudaStream_t)s; }
 
+LgSwitches& lg_switches() {
+    static LgSwitches sw;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto flag = [](const char* name, bool any_value) {
+            const char* e = getenv(name);
+            return (e && (any_value || e[0] == '1')) ? 1 : 0;
+        };
+        sw.literal_ntt = flag("LATTIGPU_LITERAL_NTT", false);
+        sw.ks_acc64 = flag("LATTIGPU_KS_ACC64", false);
+        sw.no_fp_modup = flag("LATTIGPU_NO_FP_MODUP", true);
+        sw.no_lazy_modup = flag("LATTIGPU_NO_LAZY_MODUP", true);
+        sw.no_wide_modup = flag("LATTIGPU_NO_WIDE_MODUP", true);
+        sw.no_tail_canon = flag("LATTIGPU_NO_TAIL_CANON", true);
+        sw.no_fused_tail = flag("LATTIGPU_NO_FUSED_TAIL", true);
+        if (const char* e = getenv("LATTIGPU_KS_SCRATCH_WORDS")) sw.ks_scratch_words = strtoull(e, nullptr, 10);
+    });
+    return sw;
+}
+
+int lgi_current_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return dev;
+}
+int lgi_pointer_device(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return lgi_current_device();
+    }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return at.device;
+    return lgi_current_device();
+}
+static thread_local int g_expected_dev = -1;
+int lgi_expected_device() { return g_expected_dev; }
+// first use of a device: keep stream-ordered scratch cached in the pool instead of returning it to the driver
+static void device_init_once(int dev) {
+    static std::atomic<uint64_t> done{0};
+    if (dev < 0 || dev >= 64 || (done.load(std::memory_order_acquire) >> dev & 1)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done.fetch_or(1ull << dev, std::memory_order_release);
+}
+DeviceGuard::DeviceGuard(int dev) {
+    outer = g_expected_dev;
+    if (dev < 0) return;
+    g_expected_dev = dev;
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+        lg_set_error("cudaGetDevice: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = LG_ERR_CUDA;
+        return;
+    }
+    if (prev != dev) {
+        if (cudaSetDevice(dev) != cudaSuccess) {
+            lg_set_error("cudaSetDevice(%d): %s", dev, cudaGetErrorString(cudaGetLastError()));
+            rc = LG_ERR_CUDA;
+            return;
+        }
+        switched = true;
+    }
+}
+DeviceGuard::~DeviceGuard() {
+    g_expected_dev = outer;
+    if (switched) cudaSetDevice(prev);
+}
+
 extern "C" {
 
 const char* lg_last_error(void) { return g_err; }
+int lg_debug_set_switch(const char* name, uint64_t value) {
+    LG_REQUIRE(name, "lg_debug_set_switch: null name");
+    LgSwitches& sw = lg_switches();
+    const int v = value ? 1 : 0;
+    if (!strcmp(name, "literal_ntt")) sw.literal_ntt = v;
+    else if (!strcmp(name, "ks_acc64")) sw.ks_acc64 = v;
+    else if (!strcmp(name, "no_fp_modup")) sw.no_fp_modup = v;
+    else if (!strcmp(name, "no_lazy_modup")) sw.no_lazy_modup = v;
+    else if (!strcmp(name, "no_wide_modup")) sw.no_wide_modup = v;
+    else if (!strcmp(name, "no_tail_canon")) sw.no_tail_canon = v;
+    else if (!strcmp(name, "no_fused_tail")) sw.no_fused_tail = v;
+    else if (!strcmp(name, "ks_scratch_words")) sw.ks_scratch_words = value ? value : ((uint64_t)6 << 27);
+    else {
+        lg_set_error("lg_debug_set_switch: unknown switch '%s'", name);
+        return LG_ERR_ARG;
+    }
+    return LG_OK;
+}
 const char* lg_version(void) { return "lattigpu 0.1 (sm_100a)"; }
 uint64_t lg_launch_count(void) { return lg_g_launches.load(); }
 
@@ -45,12 +138,7 @@ int lg_device_count(int* count) {
 }
 int lg_set_device(int device) {
     LG_CUDA_CHECK(cudaSetDevice(device));
-    // keep stream-ordered scratch cached in the pool instead of returning it to the driver
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
+    device_init_once(device);
     return LG_OK;
 }
 int lg_stream_create(lg_stream_t* stream) {
@@ -162,6 +250,8 @@ int lg_ring_create(uint64_t N, int nlimbs, const uint64_t* moduli, lg_ring** out
     int ndev;
     LG_TRY(lg_device_count(&ndev));
     std::unique_ptr<lg_ring> r(new lg_ring);
+    r->device = lgi_current_device();
+    device_init_once(r->device);
     r->N = N;
     r->logN = lgh::log2u(N);
     r->nl = nlimbs;
@@ -220,6 +310,8 @@ int lg_ring_create_from_tables(uint64_t N, int nlimbs, const uint64_t* moduli, c
     int ndev;
     LG_TRY(lg_device_count(&ndev));
     std::unique_ptr<lg_ring> r(new lg_ring);
+    r->device = lgi_current_device();
+    device_init_once(r->device);
     r->N = N;
     r->logN = lgh::log2u(N);
     r->nl = nlimbs;
@@ -237,6 +329,8 @@ int lg_ring_create_from_tables(uint64_t N, int nlimbs, const uint64_t* moduli, c
 }
 
 int lg_ring_destroy(lg_ring* ring) {
+    if (!ring) return LG_OK;
+    LG_ON_DEVICE(ring->device);
     delete ring;
     return LG_OK;
 }
@@ -284,6 +378,7 @@ int lg_poly_create(uint64_t N, int nlimbs, int batch, lg_poly** out) {
     LG_REQUIRE(out, "null argument");
     LG_REQUIRE(N >= 2 && (N & (N - 1)) == 0 && nlimbs >= 1 && batch >= 1, "invalid polynomial shape");
     std::unique_ptr<lg_poly> p(new lg_poly);
+    p->device = lgi_current_device();
     p->N = N;
     p->nlimbs = nlimbs;
     p->batch = batch;
@@ -300,6 +395,7 @@ int lg_poly_wrap(void* device_ptr, uint64_t N, int nlimbs, int batch, lg_poly** 
     LG_REQUIRE(((uintptr_t)device_ptr & 31) == 0, "device pointer must be 32-byte aligned");
     LG_REQUIRE(N >= 2 && (N & (N - 1)) == 0 && nlimbs >= 1 && batch >= 1, "invalid polynomial shape");
     lg_poly* p = new lg_poly;
+    p->device = lgi_pointer_device(device_ptr);
     p->d = (u64*)device_ptr;
     p->N = N;
     p->nlimbs = nlimbs;
@@ -321,7 +417,9 @@ int lg_poly_view(const lg_poly* parent, int limb0, int nlimbs, lg_poly** out) {
     return LG_OK;
 }
 int lg_poly_destroy(lg_poly* p) {
-    if (p && p->owns && p->d) cudaFree(p->d);
+    if (!p) return LG_OK;
+    LG_ON_DEVICE(p->device);
+    if (p->owns && p->d) cudaFree(p->d);
     delete p;
     return LG_OK;
 }
@@ -336,6 +434,7 @@ static int poly_xfer(const lg_poly* p, int batch0, int nbatch, int limb0, int nl
     LG_REQUIRE(p && host, "null argument");
     LG_REQUIRE(batch0 >= 0 && nbatch >= 1 && batch0 + nbatch <= p->batch, "batch range out of bounds");
     LG_REQUIRE(limb0 >= 0 && nl >= 1 && limb0 + nl <= p->nlimbs, "limb range out of bounds");
+    LG_ON_DEVICE(p->device);
     const size_t row = (size_t)nl * p->N * sizeof(u64);
     u64* dev = p->d + (size_t)batch0 * p->bstride + (size_t)limb0 * p->N;
     if (up)
@@ -368,6 +467,7 @@ int lg_poly_write_to(const lg_poly* p, int batch_index, int nl, uint8_t* data, u
     LG_REQUIRE(batch_index >= 0 && batch_index < p->batch, "WriteTo: batch index out of range");
     LG_REQUIRE(nl >= 0 && nl <= p->nlimbs && nl <= 255, "WriteTo: limb count out of range");
     LG_REQUIRE(len >= lg_poly_get_data_len(p, nl, with_metadata), "Data array is too small to write ring.Poly");  // :165-168
+    LG_ON_DEVICE(p->device);
     size_t off = 0;
     if (with_metadata) {
         data[0] = (uint8_t)lgh::log2u(p->N);  // :169-170
@@ -387,6 +487,7 @@ int lg_poly_write_to(const lg_poly* p, int batch_index, int nl, uint8_t* data, u
 int lg_poly_decode(lg_poly* p, int batch_index, const uint8_t* data, uint64_t len, int with_metadata, int nl, lg_stream_t s) {
     LG_REQUIRE(p && data, "DecodePoly: null argument");
     LG_REQUIRE(batch_index >= 0 && batch_index < p->batch, "DecodePoly: batch index out of range");
+    LG_ON_DEVICE(p->device);
     size_t off = 0;
     if (with_metadata) {  // UnmarshalBinary :257-274
         LG_REQUIRE(len >= 2, "error : invalid polynomial encoding");
@@ -411,6 +512,7 @@ int lg_poly_decode(lg_poly* p, int batch_index, const uint8_t* data, uint64_t le
 }
 int lg_poly_zero(lg_poly* p, lg_stream_t s) {
     LG_REQUIRE(p, "null argument");
+    LG_ON_DEVICE(p->device);
     LG_CUDA_CHECK(cudaMemset2DAsync(p->d, p->bstride * sizeof(u64), 0, (size_t)p->nlimbs * p->N * sizeof(u64), p->batch,
                                     cs(s)));
     return LG_OK;
@@ -420,6 +522,8 @@ int lg_poly_copy(const lg_poly* src, int nl, lg_poly* dst, lg_stream_t s) {
     LG_REQUIRE(src->N == dst->N && src->batch == dst->batch, "shape mismatch");
     LG_REQUIRE(nl >= 1 && nl <= src->nlimbs && nl <= dst->nlimbs, "limb count out of range");
     if (src->d == dst->d) return LG_OK;  // ring_object.go:87 (p0 != p1)
+    LG_SAME_DEVICE("Copy", src->device, dst->device);
+    LG_ON_DEVICE(dst->device);
     const size_t row = (size_t)nl * src->N * sizeof(u64);
     LG_CUDA_CHECK(cudaMemcpy2DAsync(dst->d, dst->bstride * sizeof(u64), src->d, src->bstride * sizeof(u64), row, src->batch,
                                     cudaMemcpyDeviceToDevice, cs(s)));
@@ -464,8 +568,7 @@ int lgi_ntt(const lg_ring* r, LimbMap map, int nl, int batch, const u64* in, siz
 }
 
 bool lgi_ntt_tail_ok(const lg_ring* r) {
-    static const bool off = getenv("LATTIGPU_NO_FUSED_TAIL") != nullptr;  // A/B switch
-    return !off && r->logN >= 12;
+    return !lg_switches().no_fused_tail.load(std::memory_order_relaxed) && r->logN >= 12;
 }
 
 int lgi_ew(int op, const lg_ring* r, LimbMap map, int nl, int batch, const u64* a, size_t a_bs, const u64* b,
@@ -494,6 +597,7 @@ static int check_poly(const lg_ring* r, int nl, const lg_poly* p, const char* wh
     LG_REQUIRE(p->N == r->N, "%s: polynomial degree %llu != ring degree %llu", what, (unsigned long long)p->N,
                (unsigned long long)r->N);
     LG_REQUIRE(nl <= p->nlimbs, "%s: %d limbs requested, polynomial has %d", what, nl, p->nlimbs);
+    LG_SAME_DEVICE(what, r->device, p->device);
     return LG_OK;
 }
 
@@ -507,6 +611,7 @@ static int ring_op3(int op, const lg_ring* r, int nl, const lg_poly* p1, const l
     const int batch = p3->batch;
     LG_REQUIRE(p1->batch == batch || p1->batch == 1, "%s: batch mismatch", what);
     LG_REQUIRE(!p2 || p2->batch == batch || p2->batch == 1, "%s: batch mismatch", what);
+    LG_ON_DEVICE(r->device);
     return lgi_ew(op, r, limb_map_identity(), nl, batch, p1->d, p1->batch == 1 && batch > 1 ? 0 : p1->bstride,
                   p2 ? p2->d : nullptr, p2 ? (p2->batch == 1 && batch > 1 ? 0 : p2->bstride) : 0, p3->d, p3->bstride,
                   nullptr, 0, cs(s));
@@ -519,6 +624,7 @@ static int ring_op_scalar(int op, const lg_ring* r, int nl, const lg_poly* p1, c
     LG_TRY(check_poly(r, nl, p1, what));
     LG_TRY(check_poly(r, nl, p2, what));
     LG_REQUIRE(p1->batch == p2->batch, "%s: batch mismatch", what);
+    LG_ON_DEVICE(r->device);
     return lgi_ew(op, r, limb_map_identity(), nl, p2->batch, p1->d, p1->bstride, nullptr, 0, p2->d, p2->bstride, scalars,
                   nscalars, cs(s));
 }
@@ -534,6 +640,7 @@ static int ring_ntt(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, bo
     LG_TRY(check_poly(r, nl, p1, "NTT"));
     LG_TRY(check_poly(r, nl, p2, "NTT"));
     LG_REQUIRE(p1->batch == p2->batch, "NTT: batch mismatch");
+    LG_ON_DEVICE(r->device);
     return lgi_ntt(r, limb_map_identity(), nl, p2->batch, p1->d, p1->bstride, p2->d, p2->bstride, inv, 0, 0, cs(s));
 }
 int lg_ring_ntt(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, lg_stream_t s) {
@@ -548,6 +655,9 @@ static int ring_ntt_limb(const lg_ring* r, int tl, const lg_poly* p1, int l1, lg
     LG_REQUIRE(tl >= 0 && tl < r->nl, "NTT: table limb %d out of range", tl);
     LG_REQUIRE(l1 >= 0 && l1 < p1->nlimbs && l2 >= 0 && l2 < p2->nlimbs, "NTT: limb out of range");
     LG_REQUIRE(p1->N == r->N && p2->N == r->N && p1->batch == p2->batch, "NTT: shape mismatch");
+    LG_SAME_DEVICE("NTT", r->device, p1->device);
+    LG_SAME_DEVICE("NTT", r->device, p2->device);
+    LG_ON_DEVICE(r->device);
     LimbMap m{1 << 30, tl, 0};
     return lgi_ntt(r, m, 1, p2->batch, p1->d + (size_t)l1 * r->N, p1->bstride, p2->d + (size_t)l2 * r->N, p2->bstride, inv,
                    0, 0, cs(s));
@@ -626,6 +736,7 @@ static int ring_op_halves(int op, const lg_ring* r, int nl, const lg_poly* p1, c
     LG_TRY(check_poly(r, nl, p1, what));
     LG_TRY(check_poly(r, nl, p2, what));
     LG_REQUIRE(p1->batch == p2->batch, "%s: batch mismatch", what);
+    LG_ON_DEVICE(r->device);
     EwArgs g;
     g.T = r->T;
     g.map = limb_map_identity();
@@ -672,6 +783,8 @@ int lg_ring_mul_by_vector_montgomery(const lg_ring* r, int nl, const lg_poly* p1
     LG_TRY(check_poly(r, nl, p1, "MulByVectorMontgomery"));
     LG_TRY(check_poly(r, nl, p2, "MulByVectorMontgomery"));
     LG_REQUIRE(vec->N == r->N && nl <= r->nl && p1->batch == p2->batch, "MulByVectorMontgomery: shape mismatch");
+    LG_SAME_DEVICE("MulByVectorMontgomery", r->device, vec->device);
+    LG_ON_DEVICE(r->device);
     EwArgs g;
     g.T = r->T;
     g.map = limb_map_identity();
@@ -693,6 +806,8 @@ int lg_ring_mul_by_vector_montgomery_and_add_nomod(const lg_ring* r, int nl, con
     LG_TRY(check_poly(r, nl, p1, "MulByVectorMontgomeryAndAddNoMod"));
     LG_TRY(check_poly(r, nl, p2, "MulByVectorMontgomeryAndAddNoMod"));
     LG_REQUIRE(vec->N == r->N && nl <= r->nl && p1->batch == p2->batch, "shape mismatch");
+    LG_SAME_DEVICE("MulByVectorMontgomeryAndAddNoMod", r->device, vec->device);
+    LG_ON_DEVICE(r->device);
     EwArgs g;
     g.T = r->T;
     g.map = limb_map_identity();
@@ -714,6 +829,7 @@ int lg_ring_mul_by_vector_montgomery_and_add_nomod(const lg_ring* r, int nl, con
 // ---------------------------------------------------------------------------
 static int make_galois(std::vector<u64>&& idx, u64 N, lg_galois** out) {
     std::unique_ptr<lg_galois> g(new lg_galois);
+    g->device = lgi_current_device();
     g->N = N;
     g->index = std::move(idx);
     std::vector<u32> i32(N);
@@ -751,6 +867,8 @@ int lg_galois_get_index(const lg_galois* g, uint64_t* index) {
     return LG_OK;
 }
 int lg_galois_destroy(lg_galois* g) {
+    if (!g) return LG_OK;
+    LG_ON_DEVICE(g->device);
     delete g;
     return LG_OK;
 }
@@ -760,8 +878,10 @@ static int perm_args(PermArgs& a, const lg_ring* r, int nl, const lg_poly* in, l
     LG_REQUIRE(in->N == out->N && in->batch == out->batch, "%s: shape mismatch", what);
     LG_REQUIRE(nl >= 1 && nl <= in->nlimbs && nl <= out->nlimbs, "%s: limb count out of range", what);
     LG_REQUIRE(in->d != out->d, "%s: not in place (ring_galois.go:54,88,105)", what);
+    LG_SAME_DEVICE(what, in->device, out->device);
     if (r) {
         LG_REQUIRE(r->N == in->N && nl <= r->nl, "%s: ring mismatch", what);
+        LG_SAME_DEVICE(what, r->device, in->device);
         a.T = r->T;
     } else {
         memset(&a.T, 0, sizeof(a.T));
@@ -782,6 +902,8 @@ int lg_ring_permute_ntt_with_index(int nl, const lg_poly* in, const lg_galois* g
     LG_REQUIRE(g, "PermuteNTTWithIndex: null index");
     LG_TRY(perm_args(a, nullptr, nl, in, out, "PermuteNTTWithIndex"));
     LG_REQUIRE(g->N == in->N, "PermuteNTTWithIndex: index length mismatch");
+    LG_SAME_DEVICE("PermuteNTTWithIndex", g->device, in->device);
+    LG_ON_DEVICE(in->device);
     a.index = g->d_index.d;
     lg_launch_permute_ntt(a, nl, out->batch, cs(s));
     LG_LAUNCH_CHECK();
@@ -790,6 +912,7 @@ int lg_ring_permute_ntt_with_index(int nl, const lg_poly* in, const lg_galois* g
 int lg_ring_permute_ntt(int nl, const lg_poly* in, uint64_t gen, lg_poly* out, lg_stream_t s) {
     // ring_galois.go:55-84: the index is rebuilt per call from gen (not exponentiated)
     LG_REQUIRE(in, "PermuteNTT: null polynomial");
+    LG_ON_DEVICE(in->device);
     lg_galois* g = nullptr;
     LG_TRY(make_galois(permute_ntt_index(gen, in->N), in->N, &g));
     int rc = lg_ring_permute_ntt_with_index(nl, in, g, out, s);
@@ -801,6 +924,7 @@ int lg_ring_permute(const lg_ring* r, int nl, const lg_poly* in, uint64_t gen, l
     PermArgs a;
     LG_REQUIRE(r, "Permute: null ring");
     LG_TRY(perm_args(a, r, nl, in, out, "Permute"));
+    LG_ON_DEVICE(r->device);
     a.gen = gen;
     lg_launch_permute_coeff(a, nl, out->batch, cs(s));
     LG_LAUNCH_CHECK();
@@ -810,6 +934,7 @@ int lg_ring_mult_by_monomial(const lg_ring* r, int nl, const lg_poly* p1, uint64
     PermArgs a;
     LG_REQUIRE(r, "MultByMonomial: null ring");
     LG_TRY(perm_args(a, r, nl, p1, p2, "MultByMonomial"));
+    LG_ON_DEVICE(r->device);
     a.gen = deg;
     lg_launch_mult_by_monomial(a, nl, p2->batch, cs(s));
     LG_LAUNCH_CHECK();
@@ -819,6 +944,7 @@ int lg_ring_bitreverse(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2,
     PermArgs a;
     LG_REQUIRE(r, "BitReverse: null ring");
     LG_TRY(perm_args(a, r, nl, p1, p2, "BitReverse"));
+    LG_ON_DEVICE(r->device);
     lg_launch_bitreverse(a, nl, p2->batch, cs(s));
     LG_LAUNCH_CHECK();
     return LG_OK;
@@ -903,6 +1029,7 @@ static int ring_div(const lg_ring* r, int nl, lg_poly* p0, int nb, bool round, b
     LG_REQUIRE(r, "%s: null ring", what);
     LG_TRY(check_poly(r, nl, p0, what));
     LG_REQUIRE(nb >= 1 && nb < nl, "%s: cannot drop %d of %d limbs", what, nb, nl);
+    LG_ON_DEVICE(r->device);
     if (many_ntt)  // :58 / :153
         LG_TRY(lgi_ntt(r, limb_map_identity(), nl, p0->batch, p0->d, p0->bstride, p0->d, p0->bstride, true, 0, 0, cs(s)));
     for (int k = 0; k < nb; ++k) LG_TRY(lgi_div_by_last_modulus(r, nl - k, p0->batch, p0->d, p0->bstride, round, ntt, cs(s)));

@@ -52,6 +52,7 @@ int check_p(const lg_poly* p, u64 N, int nl, int batch, const char* what) {
     LG_REQUIRE(p->N == N, "%s: degree mismatch", what);
     LG_REQUIRE(p->nlimbs >= nl, "%s: polynomial has %d limbs, %d needed", what, p->nlimbs, nl);
     LG_REQUIRE(batch < 0 || p->batch == batch, "%s: batch mismatch", what);
+    LG_SAME_DEVICE(what, lgi_expected_device(), p->device);
     return LG_OK;
 }
 
@@ -65,6 +66,7 @@ int bfv_switch_keys(lg_bfv_eval* e, int batch, const u64* cx, size_t cx_bs, cons
     const u64 N = Q->N;
     const int nQ = Q->nl, nP = e->P->nl, nd = nQ + nP, level = nQ - 1;
     LG_REQUIRE(evk && evk->N == N && evk->nQP == nd, "switchKeys: switching key shape mismatch");
+    LG_SAME_DEVICE("switchKeys", Q->device, evk->device);
     LG_REQUIRE(e->beta <= evk->beta, "switchKeys: key has %d digits, %d needed", evk->beta, e->beta);
     Scratch c2(st), d(st), acc(st);
     LG_TRY(c2.alloc((size_t)batch * nQ * N));
@@ -101,6 +103,9 @@ int lg_bfv_eval_create(const lg_ring* ringQ, const lg_ring* ringQMul, const lg_r
     LG_REQUIRE(ringQ && ringQMul && ringP && out, "NewEvaluator: null argument");
     LG_REQUIRE(ringQ->N == ringQMul->N && ringQ->N == ringP->N, "NewEvaluator: ring degrees differ");
     LG_REQUIRE(ringQ->nl + ringQMul->nl <= LG_MAX_LIMBS && ringQ->nl + ringP->nl <= LG_MAX_LIMBS, "NewEvaluator: too many moduli");
+    LG_SAME_DEVICE("NewEvaluator", ringQ->device, ringQMul->device);
+    LG_SAME_DEVICE("NewEvaluator", ringQ->device, ringP->device);
+    LG_ON_DEVICE(ringQ->device);
     std::unique_ptr<lg_bfv_eval> e(new lg_bfv_eval);
     e->Q = ringQ;
     e->M = ringQMul;
@@ -127,6 +132,8 @@ int lg_bfv_eval_create(const lg_ring* ringQ, const lg_ring* ringQMul, const lg_r
     return LG_OK;
 }
 int lg_bfv_eval_destroy(lg_bfv_eval* e) {
+    if (!e) return LG_OK;
+    LG_ON_DEVICE(e->Q->device);
     delete e;
     return LG_OK;
 }
@@ -136,6 +143,7 @@ int lg_bfv_eval_destroy(lg_bfv_eval* e) {
 int lg_bfv_mul(lg_bfv_eval* e, const lg_poly* a0, const lg_poly* a1, const lg_poly* b0, const lg_poly* b1, lg_poly* out0,
                lg_poly* out1, lg_poly* out2, lg_stream_t s) {
     LG_REQUIRE(e, "Mul: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     const lg_ring* Q = e->Q;
     const lg_ring* M = e->M;
     const lg_ring* QM = e->QM.get();
@@ -209,6 +217,7 @@ int lg_bfv_mul(lg_bfv_eval* e, const lg_poly* a0, const lg_poly* a1, const lg_po
 
 int lg_bfv_switch_keys_core(lg_bfv_eval* e, const lg_poly* cx, const lg_swk* evk, lg_poly* p0, lg_poly* p1, lg_stream_t s) {
     LG_REQUIRE(e, "switchKeys: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     const u64 N = e->Q->N;
     const int nQ = e->Q->nl;
     LG_TRY(check_p(cx, N, nQ, -1, "switchKeys"));
@@ -221,6 +230,7 @@ int lg_bfv_switch_keys_core(lg_bfv_eval* e, const lg_poly* cx, const lg_swk* evk
 int lg_bfv_relinearize(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, const lg_poly* c2, const lg_swk* rlk, lg_poly* out0,
                        lg_poly* out1, lg_stream_t s) {
     LG_REQUIRE(e, "Relinearize: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     const lg_ring* Q = e->Q;
     const u64 N = Q->N;
     const int nQ = Q->nl;
@@ -241,6 +251,7 @@ int lg_bfv_relinearize(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, con
 int lg_bfv_switch_keys(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, const lg_swk* k, lg_poly* out0, lg_poly* out1,
                        lg_stream_t s) {
     LG_REQUIRE(e, "SwitchKeys: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     const lg_ring* Q = e->Q;
     const u64 N = Q->N;
     const int nQ = Q->nl;
@@ -259,6 +270,7 @@ int lg_bfv_switch_keys(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, con
 int lg_bfv_permute(lg_bfv_eval* e, const lg_poly* c0, const lg_poly* c1, uint64_t gen, const lg_swk* k, lg_poly* out0,
                    lg_poly* out1, lg_stream_t s) {
     LG_REQUIRE(e, "permute: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     const lg_ring* Q = e->Q;
     const u64 N = Q->N;
     const int nQ = Q->nl;

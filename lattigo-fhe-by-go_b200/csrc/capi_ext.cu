@@ -121,13 +121,11 @@ static int check_p(const lg_poly* p, u64 N, int nl, int batch, const char* what)
     LG_REQUIRE(p->N == N, "%s: degree mismatch", what);
     LG_REQUIRE(p->nlimbs >= nl, "%s: polynomial has %d limbs, %d needed", what, p->nlimbs, nl);
     LG_REQUIRE(batch < 0 || p->batch == batch, "%s: batch mismatch", what);
+    LG_SAME_DEVICE(what, lgi_expected_device(), p->device);
     return LG_OK;
 }
 
-static bool no_tail_canon() {  // A/B switch
-    static const bool v = getenv("LATTIGPU_NO_TAIL_CANON") != nullptr;
-    return v;
-}
+static bool no_tail_canon() { return lg_switches().no_tail_canon.load(std::memory_order_relaxed) != 0; }
 
 // Shared tail of every ModDown*: tmp = modUp(P part -> Q[:level+1]); optionally
 // NTT(tmp); p2 = MRed(p1Q + (q - tmp), P^-1)   (:219-240, :254-273, :287-306)
@@ -217,6 +215,8 @@ extern "C" {
 int lg_extender_create(const lg_ring* ringQ, const lg_ring* ringP, lg_extender** out) {
     LG_REQUIRE(ringQ && ringP && out, "NewFastBasisExtender: null argument");
     LG_REQUIRE(ringQ->N == ringP->N, "NewFastBasisExtender: ring degrees differ");
+    LG_SAME_DEVICE("NewFastBasisExtender", ringQ->device, ringP->device);
+    LG_ON_DEVICE(ringQ->device);
     std::unique_ptr<lg_extender> e(new lg_extender);
     e->Q = ringQ;
     e->P = ringP;
@@ -229,24 +229,29 @@ int lg_extender_create(const lg_ring* ringQ, const lg_ring* ringP, lg_extender**
     return LG_OK;
 }
 int lg_extender_destroy(lg_extender* e) {
+    if (!e) return LG_OK;
+    LG_ON_DEVICE(e->Q->device);
     delete e;
     return LG_OK;
 }
 
 int lg_extender_modup_split_qp(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s) {
     LG_REQUIRE(e, "ModUpSplitQP: null extender");
+    LG_ON_DEVICE(e->Q->device);
     LG_TRY(check_p(p1, e->Q->N, level + 1, -1, "ModUpSplitQP"));
     LG_TRY(check_p(p2, e->Q->N, e->P->nl, p1->batch, "ModUpSplitQP"));
     return lgi_modup_launch(e->qp, e->Q->N, p1->batch, p1->d, p1->bstride, level + 1, p2->d, p2->bstride, e->P->nl, 0, cs(s));
 }
 int lg_extender_modup_split_pq(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s) {
     LG_REQUIRE(e, "ModUpSplitPQ: null extender");
+    LG_ON_DEVICE(e->Q->device);
     LG_TRY(check_p(p1, e->Q->N, level + 1, -1, "ModUpSplitPQ"));
     LG_TRY(check_p(p2, e->Q->N, e->Q->nl, p1->batch, "ModUpSplitPQ"));
     return lgi_modup_launch(e->pq, e->Q->N, p1->batch, p1->d, p1->bstride, level + 1, p2->d, p2->bstride, e->Q->nl, 0, cs(s));
 }
 int lg_extender_moddown_ntt_pq(const lg_extender* e, int level, lg_poly* p1, lg_poly* p2, lg_stream_t s) {
     LG_REQUIRE(e, "ModDownNTTPQ: null extender");
+    LG_ON_DEVICE(e->Q->device);
     const int nQ = e->Q->nl, nP = e->P->nl;
     LG_TRY(check_p(p1, e->Q->N, nQ + nP, -1, "ModDownNTTPQ"));
     LG_TRY(check_p(p2, e->Q->N, level + 1, p1->batch, "ModDownNTTPQ"));
@@ -256,6 +261,7 @@ int lg_extender_moddown_ntt_pq(const lg_extender* e, int level, lg_poly* p1, lg_
 int lg_extender_moddown_splited_ntt_pq(const lg_extender* e, int level, const lg_poly* p1Q, lg_poly* p1P, lg_poly* p2,
                                        lg_stream_t s) {
     LG_REQUIRE(e, "ModDownSplitedNTTPQ: null extender");
+    LG_ON_DEVICE(e->Q->device);
     LG_TRY(check_p(p1Q, e->Q->N, level + 1, -1, "ModDownSplitedNTTPQ"));
     LG_TRY(check_p(p1P, e->Q->N, e->P->nl, p1Q->batch, "ModDownSplitedNTTPQ"));
     LG_TRY(check_p(p2, e->Q->N, level + 1, p1Q->batch, "ModDownSplitedNTTPQ"));
@@ -264,6 +270,7 @@ int lg_extender_moddown_splited_ntt_pq(const lg_extender* e, int level, const lg
 }
 int lg_extender_moddown_pq(const lg_extender* e, int level, const lg_poly* p1, lg_poly* p2, lg_stream_t s) {
     LG_REQUIRE(e, "ModDownPQ: null extender");
+    LG_ON_DEVICE(e->Q->device);
     const int nP = e->P->nl;
     LG_TRY(check_p(p1, e->Q->N, level + 1 + nP, -1, "ModDownPQ"));
     LG_TRY(check_p(p2, e->Q->N, level + 1, p1->batch, "ModDownPQ"));
@@ -274,6 +281,7 @@ int lg_extender_moddown_pq(const lg_extender* e, int level, const lg_poly* p1, l
 int lg_extender_moddown_splited_pq(const lg_extender* e, int level, const lg_poly* p1Q, const lg_poly* p1P, lg_poly* p2,
                                    lg_stream_t s) {
     LG_REQUIRE(e, "ModDownSplitedPQ: null extender");
+    LG_ON_DEVICE(e->Q->device);
     LG_TRY(check_p(p1Q, e->Q->N, level + 1, -1, "ModDownSplitedPQ"));
     LG_TRY(check_p(p1P, e->Q->N, e->P->nl, p1Q->batch, "ModDownSplitedPQ"));
     LG_TRY(check_p(p2, e->Q->N, level + 1, p1Q->batch, "ModDownSplitedPQ"));
@@ -284,6 +292,7 @@ int lg_extender_moddown_splited_qp(const lg_extender* e, int levelQ, int levelP,
                                    lg_poly* p2, lg_stream_t s) {
     // :314-350: polypoolP = ModUpSplitQP(levelQ, p1Q); p2 = MRed(p1P + (p - pool), Q^-1)
     LG_REQUIRE(e, "ModDownSplitedQP: null extender");
+    LG_ON_DEVICE(e->Q->device);
     const lg_ring* P = e->P;
     const u64 N = P->N;
     LG_REQUIRE(levelP >= 0 && levelP < P->nl && levelQ >= 0 && levelQ < e->Q->nl, "ModDownSplitedQP: level out of range");
@@ -397,11 +406,14 @@ int lg_decomposer_create(uint64_t N, const uint64_t* Q, int nQ, const uint64_t* 
     LG_REQUIRE(Q && P && out && nQ >= 1 && nP >= 1, "NewDecomposer: invalid argument");
     LG_REQUIRE(nQ + nP <= LG_MAX_LIMBS, "NewDecomposer: too many moduli");
     std::unique_ptr<lg_decomposer> d(new lg_decomposer);
+    d->device = lgi_current_device();
     LG_TRY(decomposer_build(d.get(), N, Q, nQ, P, nP));
     *out = d.release();
     return LG_OK;
 }
 int lg_decomposer_destroy(lg_decomposer* d) {
+    if (!d) return LG_OK;
+    LG_ON_DEVICE(d->device);
     delete d;
     return LG_OK;
 }
@@ -410,6 +422,7 @@ int lg_decomposer_xalpha(const lg_decomposer* d, int i) { return (d && i >= 0 &&
 
 int lg_decomposer_decompose(const lg_decomposer* d, int level, int crt, const lg_poly* p0, lg_poly* p1, lg_stream_t s) {
     LG_REQUIRE(d, "Decompose: null decomposer");
+    LG_ON_DEVICE(d->device);
     LG_TRY(check_p(p0, d->N, level + 1, -1, "Decompose"));
     LG_TRY(check_p(p1, d->N, level + 1 + d->nP, p0->batch, "Decompose"));
     return lgi_decompose(d, level, crt, p0->batch, p0->d, p0->bstride, p1->d, p1->bstride,
@@ -418,6 +431,7 @@ int lg_decomposer_decompose(const lg_decomposer* d, int level, int crt, const lg
 int lg_decomposer_decompose_and_split(const lg_decomposer* d, int level, int crt, const lg_poly* p0, lg_poly* p1Q,
                                       lg_poly* p1P, lg_stream_t s) {
     LG_REQUIRE(d, "DecomposeAndSplit: null decomposer");
+    LG_ON_DEVICE(d->device);
     LG_TRY(check_p(p0, d->N, level + 1, -1, "DecomposeAndSplit"));
     LG_TRY(check_p(p1Q, d->N, level + 1, p0->batch, "DecomposeAndSplit"));
     LG_TRY(check_p(p1P, d->N, d->nP, p0->batch, "DecomposeAndSplit"));
@@ -448,10 +462,7 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
         // cadence (BRedAdd when (i & 7) == cadence and after the last digit) only bounds its lazy sums and
         // ends canonical as well, so the words are the same.
         const size_t per_entry = (size_t)beta * nd * N;                 // scratch words per batch entry
-        static const size_t budget = [] {                               // 6 GiB of u64 words unless overridden (tests)
-            const char* e = getenv("LATTIGPU_KS_SCRATCH_WORDS");
-            return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)6 << 27);
-        }();
+        const size_t budget = (size_t)lg_switches().ks_scratch_words.load(std::memory_order_relaxed);  // 6 GiB of words by default
         int chunk = (int)(budget / per_entry);
         if (chunk < 1) chunk = 1;
         if (chunk > batch) chunk = batch;
@@ -550,6 +561,7 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
     const int nQ = Q->nl, nP = P->nl, nl = level + 1, nd = nl + nP;
     LG_REQUIRE(level >= 0 && level < nQ, "switchKeys: level %d out of range", level);
     LG_REQUIRE(evk && evk->N == N && evk->nQP == nQ + nP, "switchKeys: switching key shape mismatch");
+    LG_SAME_DEVICE("switchKeys", Q->device, evk->device);
     const int alpha = e->alpha;
     const int beta = (nl + alpha - 1) / alpha;  // :1508
     LG_REQUIRE(beta <= evk->beta, "switchKeys: key has %d digits, %d needed", evk->beta, beta);
@@ -576,6 +588,7 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
 
 int lgi_concat_ring(const lg_ring* Q, const lg_ring* P, std::unique_ptr<lg_ring>& out) {
     std::unique_ptr<lg_ring> r(new lg_ring);
+    r->device = Q->device;
     r->N = Q->N;
     r->logN = Q->logN;
     r->nl = Q->nl + P->nl;
@@ -601,6 +614,8 @@ int lg_ckks_eval_create(const lg_ring* ringQ, const lg_ring* ringP, lg_ckks_eval
     LG_REQUIRE(ringQ && ringP && out, "NewEvaluator: null argument");
     LG_REQUIRE(ringQ->N == ringP->N, "NewEvaluator: ring degrees differ");
     LG_REQUIRE(ringQ->nl + ringP->nl <= LG_MAX_LIMBS, "NewEvaluator: too many moduli");
+    LG_SAME_DEVICE("NewEvaluator", ringQ->device, ringP->device);
+    LG_ON_DEVICE(ringQ->device);
     std::unique_ptr<lg_ckks_eval> e(new lg_ckks_eval);
     e->Q = ringQ;
     e->P = ringP;
@@ -616,6 +631,8 @@ int lg_ckks_eval_create(const lg_ring* ringQ, const lg_ring* ringP, lg_ckks_eval
     return LG_OK;
 }
 int lg_ckks_eval_destroy(lg_ckks_eval* e) {
+    if (!e) return LG_OK;
+    LG_ON_DEVICE(e->Q->device);
     delete e;
     return LG_OK;
 }
@@ -623,6 +640,7 @@ int lg_ckks_eval_destroy(lg_ckks_eval* e) {
 int lg_swk_create(uint64_t N, int beta, int nQP, const uint64_t* host, lg_swk** out) {
     LG_REQUIRE(host && out && beta >= 1 && nQP >= 1, "SwitchingKey: invalid argument");
     std::unique_ptr<lg_swk> k(new lg_swk);
+    k->device = lgi_current_device();
     k->N = N;
     k->beta = beta;
     k->nQP = nQP;
@@ -637,6 +655,7 @@ int lg_swk_wrap(void* device_ptr, uint64_t N, int beta, int nQP, lg_swk** out) {
     LG_REQUIRE(device_ptr && out && beta >= 1 && nQP >= 1, "SwitchingKey: invalid argument");
     LG_REQUIRE(((uintptr_t)device_ptr & 31) == 0, "device pointer must be 32-byte aligned");
     lg_swk* k = new lg_swk;
+    k->device = lgi_pointer_device(device_ptr);
     k->d = (u64*)device_ptr;
     k->N = N;
     k->beta = beta;
@@ -649,6 +668,7 @@ int lg_swk_wrap(void* device_ptr, uint64_t N, int beta, int nQP, lg_swk** out) {
 int lg_swk_alloc(uint64_t N, int beta, int nQP, lg_swk** out) {
     LG_REQUIRE(out && beta >= 1 && nQP >= 1 && N >= 1, "SwitchingKey: invalid argument");
     std::unique_ptr<lg_swk> k(new lg_swk);
+    k->device = lgi_current_device();
     k->N = N;
     k->beta = beta;
     k->nQP = nQP;
@@ -663,13 +683,16 @@ int lg_swk_alloc(uint64_t N, int beta, int nQP, lg_swk** out) {
 int lg_swk_poly(const lg_swk* k, int digit, int half, lg_poly** out) {
     LG_REQUIRE(k && out, "SwitchingKey: null argument");
     LG_REQUIRE(digit >= 0 && digit < k->beta && (half == 0 || half == 1), "SwitchingKey: evakey[%d][%d] out of range", digit, half);
+    LG_ON_DEVICE(k->device);
     return lg_poly_wrap((void*)k->key(digit, half), k->N, k->nQP, 1, out);
 }
 int lg_swk_beta(const lg_swk* k) { return k ? k->beta : 0; }
 int lg_swk_nlimbs(const lg_swk* k) { return k ? k->nQP : 0; }
 uint64_t lg_swk_n(const lg_swk* k) { return k ? k->N : 0; }
 int lg_swk_destroy(lg_swk* k) {
-    if (k && k->owns && k->d) cudaFree(k->d);
+    if (!k) return LG_OK;
+    LG_ON_DEVICE(k->device);
+    if (k->owns && k->d) cudaFree(k->d);
     delete k;
     return LG_OK;
 }
@@ -677,6 +700,7 @@ int lg_swk_destroy(lg_swk* k) {
 int lg_ckks_switch_keys_in_place(lg_ckks_eval* e, int level, const lg_poly* cx, const lg_swk* evk, lg_poly* p0, lg_poly* p1,
                                  lg_stream_t s) {
     LG_REQUIRE(e, "switchKeysInPlace: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     const u64 N = e->Q->N;
     LG_TRY(check_p(cx, N, level + 1, -1, "switchKeysInPlace"));
     LG_TRY(check_p(p0, N, level + 1, cx->batch, "switchKeysInPlace"));
@@ -687,6 +711,7 @@ int lg_ckks_switch_keys_in_place(lg_ckks_eval* e, int level, const lg_poly* cx, 
 int lg_ckks_mul_relin(lg_ckks_eval* e, int level, const lg_poly* a0, const lg_poly* a1, const lg_poly* b0, const lg_poly* b1,
                       const lg_swk* rlk, lg_poly* out0, lg_poly* out1, lg_stream_t s) {
     LG_REQUIRE(e, "MulRelin: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     const lg_ring* Q = e->Q;
     const u64 N = Q->N;
     const int nl = level + 1;
@@ -735,6 +760,7 @@ int lg_ckks_mul_relin(lg_ckks_eval* e, int level, const lg_poly* a0, const lg_po
 int lg_ckks_relinearize(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_poly* c2, const lg_swk* rlk,
                         lg_poly* out0, lg_poly* out1, lg_stream_t s) {
     LG_REQUIRE(e, "Relinearize: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     const lg_ring* Q = e->Q;
     const u64 N = Q->N;
     const int nl = level + 1;
@@ -746,8 +772,6 @@ int lg_ckks_relinearize(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
     LG_TRY(check_p(out0, N, nl, batch, "Relinearize"));
     LG_TRY(check_p(out1, N, nl, batch, "Relinearize"));
     cudaStream_t st = cs(s);
-    const size_t bs = (size_t)nl * N;
-    (void)bs;
     const LimbMap id = limb_map_identity();
     LG_REQUIRE(c2->d != out0->d && c2->d != out1->d, "Relinearize: value[2] must not alias the receiver");
     if (c0->d != out0->d) LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, c0->d, c0->bstride, nullptr, 0, out0->d, out0->bstride, nullptr, 0, st));
@@ -759,6 +783,7 @@ int lg_ckks_relinearize(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
 
 int lg_ckks_rescale(lg_ckks_eval* e, int nl, lg_poly* c0, lg_poly* c1, int nb, lg_stream_t s) {
     LG_REQUIRE(e, "Rescale: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     LG_TRY(check_p(c0, e->Q->N, nl, -1, "Rescale"));
     LG_TRY(check_p(c1, e->Q->N, nl, c0->batch, "Rescale"));
     LG_REQUIRE(nb >= 1 && nb < nl, "cannot Rescale: input Ciphertext already at level 0");  // ckks/evaluator.go:938
@@ -772,6 +797,7 @@ int lg_ckks_rescale(lg_ckks_eval* e, int nl, lg_poly* c0, lg_poly* c1, int nb, l
 int lg_ckks_switch_keys(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_swk* k, lg_poly* out0,
                         lg_poly* out1, lg_stream_t s) {
     LG_REQUIRE(e, "SwitchKeys: null evaluator");
+    LG_ON_DEVICE(e->Q->device);
     const lg_ring* Q = e->Q;
     const u64 N = Q->N;
     const int nl = level + 1;
@@ -782,13 +808,6 @@ int lg_ckks_switch_keys(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
     LG_TRY(check_p(out0, N, nl, batch, "SwitchKeys"));
     LG_TRY(check_p(out1, N, nl, batch, "SwitchKeys"));
     cudaStream_t st = cs(s);
-    const size_t bs = (size_t)nl * N;
-    Scratch w(st);
-    LG_TRY(w.alloc((size_t)2 * batch * bs));
-    u64* k0 = w.d;
-    u64* k1 = k0 + batch * bs;
-    (void)k0;
-    (void)k1;
     const LimbMap id = limb_map_identity();
     LG_REQUIRE(out0->d != c1->d, "SwitchKeys: receiver value[0] must not alias input value[1]");
     if (c0->d != out0->d) LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, c0->d, c0->bstride, nullptr, 0, out0->d, out0->bstride, nullptr, 0, st));
@@ -799,6 +818,7 @@ int lg_ckks_switch_keys(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
 
 int lg_ckks_hoist(lg_ckks_eval* e, int level, const lg_poly* c1, lg_hoisted** out, lg_stream_t s) {
     LG_REQUIRE(e && out, "RotateHoisted: null argument");
+    LG_ON_DEVICE(e->Q->device);
     const lg_ring* Q = e->Q;
     const lg_ring* QP = e->QP.get();
     const u64 N = Q->N;
@@ -810,6 +830,7 @@ int lg_ckks_hoist(lg_ckks_eval* e, int level, const lg_poly* c1, lg_hoisted** ou
     const int beta = (nl + alpha - 1) / alpha;  // :1259
     cudaStream_t st = cs(s);
     std::unique_ptr<lg_hoisted> h(new lg_hoisted);
+    h->device = Q->device;
     h->N = N;
     h->level = level;
     h->beta = beta;
@@ -867,7 +888,9 @@ int lg_ckks_hoist(lg_ckks_eval* e, int level, const lg_poly* c1, lg_hoisted** ou
 }
 
 int lg_hoisted_destroy(lg_hoisted* h) {
-    if (h && h->d) cudaFreeAsync(h->d, h->st);  // after the rotations issued on the hoist's stream
+    if (!h) return LG_OK;
+    LG_ON_DEVICE(h->device);
+    if (h->d) cudaFreeAsync(h->d, h->st);  // after the rotations issued on the hoist's stream
     delete h;
     return LG_OK;
 }
@@ -875,6 +898,10 @@ int lg_hoisted_destroy(lg_hoisted* h) {
 int lg_ckks_switch_key_hoisted(lg_ckks_eval* e, const lg_hoisted* h, const lg_poly* c0, const lg_galois* g, const lg_swk* k,
                                lg_poly* out0, lg_poly* out1, lg_stream_t s) {
     LG_REQUIRE(e && h && g && k, "switchKeyHoisted: null argument");
+    LG_ON_DEVICE(e->Q->device);
+    LG_SAME_DEVICE("switchKeyHoisted", e->Q->device, h->device);
+    LG_SAME_DEVICE("switchKeyHoisted", e->Q->device, g->device);
+    LG_SAME_DEVICE("switchKeyHoisted", e->Q->device, k->device);
     const lg_ring* Q = e->Q;
     const lg_ring* QP = e->QP.get();
     const u64 N = Q->N;
@@ -933,6 +960,8 @@ int lg_ckks_switch_key_hoisted(lg_ckks_eval* e, const lg_hoisted* h, const lg_po
 int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_poly* c1, const lg_galois* g, const lg_swk* k,
                         lg_poly* out0, lg_poly* out1, lg_stream_t s) {
     LG_REQUIRE(e && g, "permuteNTT: null argument");
+    LG_ON_DEVICE(e->Q->device);
+    LG_SAME_DEVICE("permuteNTT", e->Q->device, g->device);
     const lg_ring* Q = e->Q;
     const u64 N = Q->N;
     const int nl = level + 1;
@@ -946,11 +975,9 @@ int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
     cudaStream_t st = cs(s);
     const size_t bs = (size_t)nl * N;
     Scratch w(st);
-    LG_TRY(w.alloc((size_t)4 * batch * bs));
+    LG_TRY(w.alloc((size_t)2 * batch * bs));
     u64* el0 = w.d;
     u64* el1 = el0 + batch * bs;
-    u64* k0 = el1 + batch * bs;
-    u64* k1 = k0 + batch * bs;
     PermArgs a;
     memset(&a.T, 0, sizeof(a.T));
     a.T.N = (u32)N;
@@ -968,8 +995,6 @@ int lg_ckks_permute_ntt(lg_ckks_eval* e, int level, const lg_poly* c0, const lg_
     a.out = el1;
     lg_launch_permute_ntt(a, nl, batch, st);
     LG_LAUNCH_CHECK();
-    (void)k0;
-    (void)k1;
     const LimbMap id = limb_map_identity();
     // :1468-1471: value[0] = el0 + pool1, value[1] = pool2
     LG_TRY(lgi_ew(EW_COPY, Q, id, nl, batch, el0, bs, nullptr, 0, out0->d, out0->bstride, nullptr, 0, st));

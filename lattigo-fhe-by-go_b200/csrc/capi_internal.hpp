@@ -29,6 +29,29 @@ extern std::atomic<uint64_t> lg_g_launches;
         if (_rc != LG_OK) return _rc; \
     } while (0)
 
+// Every handle that owns or wraps device memory remembers its CUDA device; every entry point that touches the device
+// runs under a DeviceGuard for it, so a host whose threads migrate (goroutines over OS threads, SURVEY.md 8(b)
+// Threading) or that drives several GPUs from one process never launches on the wrong current device.  The previous
+// device of the calling thread is restored on return.  device < 0 (host-only handle) is a no-op.
+int lgi_current_device();
+int lgi_pointer_device(const void* p);  // device of a cudaMalloc'ed pointer (cudaPointerGetAttributes), else the current one
+int lgi_expected_device();  // device of the innermost DeviceGuard of this thread (-1: none): operand checks compare with it
+struct DeviceGuard {
+    int prev = -1;
+    int outer = -1;
+    bool switched = false;
+    int rc = LG_OK;
+    explicit DeviceGuard(int dev);
+    ~DeviceGuard();
+    DeviceGuard(const DeviceGuard&) = delete;
+};
+#define LG_ON_DEVICE(dev)           \
+    DeviceGuard _lg_guard(dev);     \
+    if (_lg_guard.rc != LG_OK) return _lg_guard.rc
+// operands of one call must live on one device
+#define LG_SAME_DEVICE(what, d0, d1) \
+    LG_REQUIRE((d0) < 0 || (d1) < 0 || (d0) == (d1), "%s: operands live on different devices (%d and %d)", what, (int)(d0), (int)(d1))
+
 #define LG_LAUNCH_CHECK()                                                               \
     do {                                                                                \
         cudaError_t _e = cudaPeekAtLastError();                                         \
@@ -75,6 +98,7 @@ struct Scratch {
 };
 
 struct lg_ring {
+    int device = -1;  // CUDA device of the tables
     u64 N = 0;
     u32 logN = 0;
     int nl = 0;
@@ -87,6 +111,7 @@ struct lg_ring {
 };
 
 struct lg_poly {
+    int device = -1;
     u64* d = nullptr;
     u64 N = 0;
     int nlimbs = 0;
@@ -96,6 +121,7 @@ struct lg_poly {
 };
 
 struct lg_galois {
+    int device = -1;
     u64 N = 0;
     std::vector<u64> index;
     DevArray<u32> d_index;
@@ -142,6 +168,7 @@ struct lg_extender {
 };
 
 struct lg_decomposer {
+    int device = -1;
     u64 N = 0;
     int nQ = 0, nP = 0, alpha = 0, beta = 0;
     std::vector<int> xalpha;
@@ -149,6 +176,7 @@ struct lg_decomposer {
 };
 
 struct lg_swk {
+    int device = -1;
     u64* d = nullptr;
     u64 N = 0;
     int beta = 0, nQP = 0;
@@ -158,6 +186,7 @@ struct lg_swk {
 
 // RotateHoisted precomputation: the NTT-domain digits of value[1] (ckks/evaluator.go:1258-1273)
 struct lg_hoisted {
+    int device = -1;
     u64* d = nullptr;  // [beta][batch][level+1+nP][N], allocated and freed in stream order on st
     cudaStream_t st = nullptr;
     u64 N = 0;

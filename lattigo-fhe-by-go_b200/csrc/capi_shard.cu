@@ -15,6 +15,8 @@
 #include <dlfcn.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "capi_internal.hpp"
 
 static inline cudaStream_t cs(lg_stream_t s) { return (cudaStream_t)s; }
@@ -41,9 +43,8 @@ struct NcclApi {
 
 NcclApi* nccl() {
     static NcclApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char* n : names) {
             api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -61,7 +62,7 @@ NcclApi* nccl() {
             LG_SYM(GetErrorString, "ncclGetErrorString");
 #undef LG_SYM
         }
-    }
+    });
     return &api;
 }
 
@@ -94,6 +95,7 @@ LimbMap sub_map(LimbMap m, int b) {
 }  // namespace
 
 struct lg_comm {
+    int device = -1;  // the rank's GPU
     int world = 1, rank = 0;
     NcclComm comm = nullptr;
 };
@@ -107,14 +109,17 @@ int allgather_limbs(const lg_comm* c, u64* base, size_t bstride, int batch, u64 
     if (c->world == 1) return LG_OK;
     NcclApi* n = nccl();
     LG_NCCL_CHECK(n->GroupStart());
-    for (int r = 0; r < c->world; ++r) {
+    int first = 0;  // an error inside the group must not leave it open
+    for (int r = 0; r < c->world && !first; ++r) {
         if (ranges[r].n() <= 0) continue;
-        for (int bt = 0; bt < batch; ++bt) {
+        for (int bt = 0; bt < batch && !first; ++bt) {
             u64* p = base + (size_t)bt * bstride + (size_t)ranges[r].b * N;
-            LG_NCCL_CHECK(n->Broadcast(p, p, (size_t)ranges[r].n() * N, kNcclUint64, r, c->comm, st));
+            first = n->Broadcast(p, p, (size_t)ranges[r].n() * N, kNcclUint64, r, c->comm, st);
         }
     }
-    LG_NCCL_CHECK(n->GroupEnd());
+    const int end = n->GroupEnd();
+    LG_NCCL_CHECK(first);
+    LG_NCCL_CHECK(end);
     return LG_OK;
 }
 
@@ -304,6 +309,7 @@ int check_p(const lg_poly* p, u64 N, int nl, int batch, const char* what) {
     LG_REQUIRE(p->N == N, "%s: degree mismatch", what);
     LG_REQUIRE(p->nlimbs >= nl, "%s: polynomial has %d limbs, %d needed", what, p->nlimbs, nl);
     LG_REQUIRE(batch < 0 || p->batch == batch, "%s: batch mismatch", what);
+    LG_SAME_DEVICE(what, lgi_expected_device(), p->device);
     return LG_OK;
 }
 
@@ -323,6 +329,7 @@ int lg_comm_get_unique_id(uint8_t* id128) {
 int lg_comm_create(int world, int rank, const uint8_t* id128, lg_comm** out) {
     LG_REQUIRE(out && world >= 1 && rank >= 0 && rank < world, "lg_comm_create: invalid argument");
     std::unique_ptr<lg_comm> c(new lg_comm);
+    c->device = lgi_current_device();
     c->world = world;
     c->rank = rank;
     if (world > 1) {
@@ -337,7 +344,9 @@ int lg_comm_create(int world, int rank, const uint8_t* id128, lg_comm** out) {
     return LG_OK;
 }
 int lg_comm_destroy(lg_comm* c) {
-    if (c && c->comm && nccl()->CommDestroy) nccl()->CommDestroy(c->comm);
+    if (!c) return LG_OK;
+    LG_ON_DEVICE(c->device);
+    if (c->comm && nccl()->CommDestroy) nccl()->CommDestroy(c->comm);
     delete c;
     return LG_OK;
 }
@@ -360,14 +369,20 @@ int lg_comm_aggregate_shares(const lg_comm* c, const lg_ring* r, int nl, lg_poly
     LG_REQUIRE(c && r && p, "AggregateShares: null argument");
     LG_REQUIRE(c->world <= 8, "AggregateShares: at most 8 ranks (64-bit lazy sum)");
     LG_REQUIRE(nl >= 1 && nl <= r->nl && nl <= p->nlimbs && p->N == r->N, "AggregateShares: shape mismatch");
+    LG_SAME_DEVICE("AggregateShares", c->device, r->device);
+    LG_SAME_DEVICE("AggregateShares", c->device, p->device);
+    LG_ON_DEVICE(c->device);
     if (c->world > 1) {
         NcclApi* n = nccl();
         LG_NCCL_CHECK(n->GroupStart());
-        for (int bt = 0; bt < p->batch; ++bt) {
+        int first = 0;
+        for (int bt = 0; bt < p->batch && !first; ++bt) {
             u64* ptr = p->d + (size_t)bt * p->bstride;
-            LG_NCCL_CHECK(n->AllReduce(ptr, ptr, (size_t)nl * r->N, kNcclUint64, kNcclSum, c->comm, cs(s)));
+            first = n->AllReduce(ptr, ptr, (size_t)nl * r->N, kNcclUint64, kNcclSum, c->comm, cs(s));
         }
-        LG_NCCL_CHECK(n->GroupEnd());
+        const int end = n->GroupEnd();
+        LG_NCCL_CHECK(first);
+        LG_NCCL_CHECK(end);
     }
     return lgi_ew(EW_REDUCE, r, limb_map_identity(), nl, p->batch, p->d, p->bstride, nullptr, 0, p->d, p->bstride, nullptr, 0,
                   cs(s));
@@ -376,6 +391,8 @@ int lg_comm_aggregate_shares(const lg_comm* c, const lg_ring* r, int nl, lg_poly
 int lg_ckks_switch_keys_in_place_sharded(lg_ckks_eval* e, const lg_comm* c, int level, const lg_poly* cx, const lg_swk* evk,
                                          lg_poly* p0, lg_poly* p1, lg_stream_t s) {
     LG_REQUIRE(e && c, "switchKeysInPlace: null argument");
+    LG_SAME_DEVICE("switchKeysInPlace", c->device, e->Q->device);
+    LG_ON_DEVICE(c->device);
     const u64 N = e->Q->N;
     LG_TRY(check_p(cx, N, level + 1, -1, "switchKeysInPlace"));
     LG_TRY(check_p(p0, N, level + 1, cx->batch, "switchKeysInPlace"));
@@ -390,6 +407,8 @@ int lg_ckks_mul_relin_sharded(lg_ckks_eval* e, const lg_comm* c, int level, cons
                               const lg_poly* b0, const lg_poly* b1, const lg_swk* rlk, lg_poly* out0, lg_poly* out1,
                               lg_stream_t s) {
     LG_REQUIRE(e && c, "MulRelin: null argument");
+    LG_SAME_DEVICE("MulRelin", c->device, e->Q->device);
+    LG_ON_DEVICE(c->device);
     const lg_ring* Q = e->Q;
     const u64 N = Q->N;
     const int nl = level + 1, nd = nl + e->P->nl;
@@ -437,6 +456,8 @@ int lg_ckks_mul_relin_sharded(lg_ckks_eval* e, const lg_comm* c, int level, cons
 // is inverse-transformed redundantly on every rank (one limb), so no exchange precedes the fan-out.
 int lg_ckks_rescale_sharded(lg_ckks_eval* e, const lg_comm* c, int nl, lg_poly* c0, lg_poly* c1, lg_stream_t s) {
     LG_REQUIRE(e && c, "Rescale: null argument");
+    LG_SAME_DEVICE("Rescale", c->device, e->Q->device);
+    LG_ON_DEVICE(c->device);
     const lg_ring* Q = e->Q;
     const u64 N = Q->N;
     LG_TRY(check_p(c0, N, nl, -1, "Rescale"));

@@ -243,6 +243,7 @@ int lg_crp_clock(lg_crp* g, lg_poly* out, int batch_index, lg_stream_t stream) {
     LG_REQUIRE(g && out, "CRPGenerator.Clock: null argument");
     LG_REQUIRE(out->N == g->ring->N && out->nlimbs >= g->ring->nl, "CRPGenerator.Clock: polynomial does not fit the context");
     LG_REQUIRE(batch_index >= 0 && batch_index < out->batch, "CRPGenerator.Clock: batch index out of range");
+    LG_ON_DEVICE(out->device);
     const size_t words = (size_t)g->ring->nl * g->ring->N;
     if (!g->stage) LG_CUDA_CHECK(cudaMallocHost((void**)&g->stage, words * sizeof(u64)));
     LG_TRY(lg_crp_clock_host(g, g->stage));

@@ -7,6 +7,32 @@
 
 extern std::atomic<uint64_t> lg_g_launches;  // kernels launched by this library
 
+// Diagnostic A/B switches (lattigpu.h: lg_debug_set_switch).  Read from the LATTIGPU_* environment ONCE, at first use
+// (std::call_once), then only changed through lg_debug_set_switch -- no getenv on any launch path.  All default to 0.
+struct LgSwitches {
+    std::atomic<int> literal_ntt{0};     // LATTIGPU_LITERAL_NTT: literal Butterfly/InvButterfly in every transform
+    std::atomic<int> ks_acc64{0};        // LATTIGPU_KS_ACC64: never take the 96-bit key-switch accumulators
+    std::atomic<int> no_fp_modup{0};     // LATTIGPU_NO_FP_MODUP: integer-only basis extension
+    std::atomic<int> no_lazy_modup{0};   // LATTIGPU_NO_LAZY_MODUP: canonical key-switch digits
+    std::atomic<int> no_wide_modup{0};   // LATTIGPU_NO_WIDE_MODUP: generic kernel for 5..16 sources
+    std::atomic<int> no_tail_canon{0};   // LATTIGPU_NO_TAIL_CANON: reduce the transform before the ModDown tail
+    std::atomic<int> no_fused_tail{0};   // LATTIGPU_NO_FUSED_TAIL: separate ModDown / rescale tail kernels
+    std::atomic<uint64_t> ks_scratch_words{(uint64_t)6 << 27};  // LATTIGPU_KS_SCRATCH_WORDS: digit scratch budget (words)
+};
+LgSwitches& lg_switches();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device)
+template <auto Kernel>
+inline void lg_ensure_dyn_smem(size_t bytes) {
+    static std::atomic<uint64_t> done{0};  // bit d = set on device d (devices >= 64: set every time)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = dev < 64 ? (1ull << dev) : 0ull;
+    if (bit && (done.load(std::memory_order_acquire) & bit)) return;
+    cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (bit) done.fetch_or(bit, std::memory_order_release);
+}
+
 #define LG_MAX_LIMBS 64
 
 // ---- K1: NTT ----------------------------------------------------------------

@@ -583,7 +583,10 @@ __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttAr
 // per term instead of the 11 multiplies of a Montgomery reduction per term.  Key words may be any 64-bit value (the
 // reference's MRed is total): the kernel ORs their high halves on the way and a CTA that saw a word of more bits
 // than q repeats its tile on the 64-bit path, which is exact for every word.
-enum { ACC_CRED = 0, ACC_LAZY64 = 1, ACC_WIDE96 = 2 };
+// ACC_EXACT is the always-valid form: the digit value is made canonical first (as the reference's c2QiQ / c2QiP are) and
+// every term is a full MRed + CRed, exact for ANY 64-bit key word.  The two lazy forms assume key words of at most
+// bits(q) bits; they watch the high halves of the key words and the CTA repeats its tile with ACC_EXACT otherwise.
+enum { ACC_EXACT = 0, ACC_LAZY64 = 1, ACC_WIDE96 = 2 };
 
 // (a2 : A) += k * x, caller guarantees the running sum stays below 2^96
 LG_DEV void mac96(u64& A, u32& a2, u64 k, u64 x) {
@@ -692,7 +695,7 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
 #pragma unroll
                 for (int e = 0; e < 4; ++e) x[4 * h + e] = v[e];
             }
-            if (ACC == ACC_WIDE96) {  // caller data, any 64-bit word: canonical
+            if (ACC == ACC_WIDE96 || ACC == ACC_EXACT) {  // caller data, any 64-bit word: canonical
 #pragma unroll
                 for (int r = 0; r < 16; ++r) x[r] = bred_add(x[r], q, lc.u0);
             }
@@ -714,6 +717,9 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
             if (ACC == ACC_WIDE96) {
 #pragma unroll
                 for (int r = 0; r < 16; ++r) x[r] = reduce_f64(x[r], qd1, cq1, c.nq);
+            } else if (ACC == ACC_EXACT) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) x[r] = bred_add(x[r], q, lc.u0);
             }
         }
 #if KS_KEYPREFETCH == 0
@@ -727,6 +733,7 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
                 mac96(acc0[r], top0[r], kk0[r], x[r]);
                 mac96(acc1[r], top1[r], kk1[r], x[r]);
             } else if (ACC == ACC_LAZY64) {
+                keyhi |= (u32)(kk0[r] >> 32) | (u32)(kk1[r] >> 32);
                 acc0[r] += mred_constant(kk0[r], x[r], q, qinv);
                 acc1[r] += mred_constant(kk1[r], x[r], q, qinv);
             } else {
@@ -764,27 +771,33 @@ __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const
     const int tl = a.map(blockIdx.z);
     const LimbConst lc = load_limb_const(a.T, tl);
     const int mode = LITERAL ? M_LITERAL : fwd_mode(lc.q);
+    // beta lazy terms below 2q fit 64 bits (a term is below 2q when the key word has at most bits(q) bits: its product
+    // with a transform value below 2^63 (M_FREE), 8q (M_LAZY) or 2^52 (M_F64) then has a high word below q)
     const bool lazyacc = (2 * lc.q) <= (~0ull) / (u64)a.beta;
-    if (mode == M_F64) {  // q < 2^56: beta <= 64 terms below 2q always fit
-        // beta products of a key word below 2^kb (kb = bits of q, at least 32: only the high halves are watched) and a
-        // digit value below 3q fit 96 bits
-        const int qbits = 64 - __clzll((long long)lc.q), kb = qbits < 32 ? 32 : qbits;
+    // key words of at most kb bits are what the lazy forms assume (kb = bits of q, at least 32: only the high halves
+    // are watched -- below 2^32 a key word is harmless for any q)
+    const int qbits = 64 - __clzll((long long)lc.q), kb = qbits < 32 ? 32 : qbits;
+    u32 keyhi = 0;
+    if (mode == M_F64) {
+        // beta products of a key word below 2^kb and a digit value below 3q fit 96 bits
         const int sh = 96 - kb;  // 50..64; a shift by 64 is not defined in C++: every product fits then
-        if (!a.acc64 && (sh >= 64 || ((3ull * (u64)a.beta * lc.q) >> sh) == 0)) {
-            const u32 keyhi = ks_fused_body<M_F64, ACC_WIDE96>(a, lc, tl, ks_smem);
-            if (__syncthreads_or((keyhi >> (kb - 32)) != 0)) ks_fused_body<M_F64, ACC_LAZY64>(a, lc, tl, ks_smem);
-        } else {
-            ks_fused_body<M_F64, ACC_LAZY64>(a, lc, tl, ks_smem);
-        }
+        if (!a.acc64 && (sh >= 64 || ((3ull * (u64)a.beta * lc.q) >> sh) == 0))
+            keyhi = ks_fused_body<M_F64, ACC_WIDE96>(a, lc, tl, ks_smem);
+        else  // q < 2^56: beta <= 64 terms below 2q always fit
+            keyhi = ks_fused_body<M_F64, ACC_LAZY64>(a, lc, tl, ks_smem);
+        if (__syncthreads_or((keyhi >> (kb - 32)) != 0)) ks_fused_body<M_F64, ACC_EXACT>(a, lc, tl, ks_smem);
     } else if (mode == M_FREE) {
-        ks_fused_body<M_FREE, ACC_LAZY64>(a, lc, tl, ks_smem);
+        keyhi = ks_fused_body<M_FREE, ACC_LAZY64>(a, lc, tl, ks_smem);
+        if (__syncthreads_or((keyhi >> (kb - 32)) != 0)) ks_fused_body<M_FREE, ACC_EXACT>(a, lc, tl, ks_smem);
     } else if (mode == M_LAZY) {
-        if (lazyacc)
-            ks_fused_body<M_LAZY, ACC_LAZY64>(a, lc, tl, ks_smem);
-        else
-            ks_fused_body<M_LAZY, ACC_CRED>(a, lc, tl, ks_smem);
+        if (lazyacc) {
+            keyhi = ks_fused_body<M_LAZY, ACC_LAZY64>(a, lc, tl, ks_smem);
+            if (__syncthreads_or((keyhi >> (kb - 32)) != 0)) ks_fused_body<M_LAZY, ACC_EXACT>(a, lc, tl, ks_smem);
+        } else {
+            ks_fused_body<M_LAZY, ACC_EXACT>(a, lc, tl, ks_smem);
+        }
     } else {
-        ks_fused_body<M_LITERAL, ACC_CRED>(a, lc, tl, ks_smem);
+        ks_fused_body<M_LITERAL, ACC_EXACT>(a, lc, tl, ks_smem);
     }
 }
 
@@ -944,7 +957,7 @@ void launch_contig_pipe_t(const NttArgs& a, int nlimbs, int batch, cudaStream_t 
     if (a.skip_alpha > 0)
         while (a.skip_div % bpc) --bpc;
     const size_t smem = PIPE_SMEM_WORDS * sizeof(u64);
-    cudaFuncSetAttribute(ntt_contig_pipe<FWD, LITERAL, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lg_ensure_dyn_smem<ntt_contig_pipe<FWD, LITERAL, TAIL>>(smem);
     ntt_contig_pipe<FWD, LITERAL, TAIL><<<dim3((batch + bpc - 1) / bpc, tiles, nlimbs), CONTIG_THREADS, smem, st>>>(a, batch, bpc);
 }
 void launch_contig_pipe(bool fwd, bool literal, const NttArgs& a, int nlimbs, int batch, cudaStream_t st) {
@@ -966,13 +979,7 @@ void launch_contig_pipe(bool fwd, bool literal, const NttArgs& a, int nlimbs, in
     }
 }
 
-bool literal_ntt() {
-    static const bool v = [] {
-        const char* e = getenv("LATTIGPU_LITERAL_NTT");
-        return e && e[0] == '1';
-    }();
-    return v;
-}
+bool literal_ntt() { return lg_switches().literal_ntt.load(std::memory_order_relaxed) != 0; }
 
 }  // namespace
 
@@ -1032,14 +1039,12 @@ int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t
     const dim3 grid(batch, a.T.N / CONTIG_TILE, nlimbs);
     const size_t smem = KS_SMEM_WORDS * sizeof(u64);
     KsFusedArgs k = a;
-    const char* e = getenv("LATTIGPU_KS_ACC64");  // read per call: the tests switch it inside one process
-    k.acc64 = (e && e[0] == '1') ? 1 : 0;
-    // (per launch: the attribute is per device and a process may drive several)
+    k.acc64 = lg_switches().ks_acc64.load(std::memory_order_relaxed) ? 1 : 0;
     if (literal_ntt()) {
-        cudaFuncSetAttribute(ks_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lg_ensure_dyn_smem<ks_fused_kernel<true>>(smem);
         ks_fused_kernel<true><<<grid, CONTIG_THREADS, smem, st>>>(k);
     } else {
-        cudaFuncSetAttribute(ks_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lg_ensure_dyn_smem<ks_fused_kernel<false>>(smem);
         ks_fused_kernel<false><<<grid, CONTIG_THREADS, smem, st>>>(k);
     }
     lg_g_launches += 1;

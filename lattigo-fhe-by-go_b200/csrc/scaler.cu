@@ -261,6 +261,7 @@ int lg_scaler_params_host(uint64_t t, const uint64_t* moduli, int nl, uint64_t* 
 int lg_scaler_create(uint64_t t, const lg_ring* ring, lg_scaler** out) {
     LG_REQUIRE(ring && out, "NewSimpleScaler: null argument");
     LG_REQUIRE(ring->nl <= kScaleMaxLimbs, "NewSimpleScaler: at most %d moduli", kScaleMaxLimbs);
+    LG_ON_DEVICE(ring->device);
     std::unique_ptr<lg_scaler> s(new lg_scaler);
     s->ring = ring;
     s->t = t;
@@ -275,6 +276,8 @@ int lg_scaler_create(uint64_t t, const lg_ring* ring, lg_scaler** out) {
 }
 
 int lg_scaler_destroy(lg_scaler* s) {
+    if (!s) return LG_OK;
+    LG_ON_DEVICE(s->ring->device);
     delete s;
     return LG_OK;
 }
@@ -293,6 +296,9 @@ int lg_scaler_scale(const lg_scaler* s, const lg_poly* p1, lg_poly* p2, lg_strea
     LG_REQUIRE(p1->N == r->N && p2->N == r->N, "Scale: degree mismatch");
     LG_REQUIRE(p1->nlimbs >= r->nl, "Scale: input has %d limbs, the context has %d", p1->nlimbs, r->nl);
     LG_REQUIRE(p1->batch == p2->batch, "Scale: batch mismatch");
+    LG_SAME_DEVICE("Scale", r->device, p1->device);
+    LG_SAME_DEVICE("Scale", r->device, p2->device);
+    LG_ON_DEVICE(r->device);
     ScaleArgs a;
     a.in = p1->d;
     a.out = p2->d;
@@ -344,6 +350,7 @@ int lg_bfv_lift_params_host(const uint64_t* moduli, int nl, uint64_t t, uint64_t
 
 int lg_bfv_lift_create(const lg_ring* ringQ, uint64_t t, lg_bfv_lift** out) {
     LG_REQUIRE(ringQ && out, "GenLiftParams: null argument");
+    LG_ON_DEVICE(ringQ->device);
     std::unique_ptr<lg_bfv_lift> l(new lg_bfv_lift);
     l->ring = ringQ;
     l->delta.resize(ringQ->nl);
@@ -354,6 +361,8 @@ int lg_bfv_lift_create(const lg_ring* ringQ, uint64_t t, lg_bfv_lift** out) {
 }
 
 int lg_bfv_lift_destroy(lg_bfv_lift* l) {
+    if (!l) return LG_OK;
+    LG_ON_DEVICE(l->ring->device);
     delete l;
     return LG_OK;
 }
@@ -371,6 +380,9 @@ int lg_bfv_lift_apply(const lg_bfv_lift* l, const lg_poly* m, lg_poly* pt, lg_st
     LG_REQUIRE(m->N == r->N && pt->N == r->N, "encodePlaintext: degree mismatch");
     LG_REQUIRE(pt->nlimbs >= r->nl, "encodePlaintext: plaintext has %d limbs, %d needed", pt->nlimbs, r->nl);
     LG_REQUIRE(m->batch == pt->batch, "encodePlaintext: batch mismatch");
+    LG_SAME_DEVICE("encodePlaintext", r->device, m->device);
+    LG_SAME_DEVICE("encodePlaintext", r->device, pt->device);
+    LG_ON_DEVICE(r->device);
     LiftArgs a;
     a.m = m->d;
     a.out = pt->d;

@@ -53,6 +53,7 @@ SIGNATURES = {
     "lg_stream_destroy": (ci, [vp]),
     "lg_stream_sync": (ci, [vp]),
     "lg_launch_count": (u64, []),
+    "lg_debug_set_switch": (ci, [C.c_char_p, u64]),
     "lg_ring_create": (ci, [u64, ci, p64, C.POINTER(vp)]),
     "lg_ring_create_from_tables": (ci, [u64, ci, p64, p64, p64, p64, p64, p64, p64, C.POINTER(vp)]),
     "lg_ring_destroy": (ci, [_R]),

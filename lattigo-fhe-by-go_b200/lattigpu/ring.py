@@ -37,6 +37,11 @@ def launch_count():
     return int(lib().lg_launch_count())
 
 
+def debug_set_switch(name, value):
+    """lg_debug_set_switch: diagnostic A/B switches between kernel variants that return identical words"""
+    check(lib().lg_debug_set_switch(name.encode(), int(value)))
+
+
 def GenerateNTTPrimes(logQ, logN, levels):
     """ring/utils.go:133-175 (host only)"""
     out = np.zeros(levels, dtype=np.uint64)

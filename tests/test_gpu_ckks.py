@@ -18,6 +18,12 @@ PN12 = (12, [37, 32], [38])
 PN13 = (13, [33, 30, 30, 30, 30, 30], [35])
 PN14 = (14, [45] + [34] * 9, [43, 43])
 SMALL3 = (12, [50, 40, 40, 40, 40, 40, 40], [50, 50, 50])  # alpha=3, beta=3 with a partial last digit
+# the headline set's digit shape (ckks/params.go:79-86: 34 + 4 limbs, alpha = 4, beta = 9) on a ring the oracle walks in
+# seconds: every level exercises one of SURVEY.md Appendix A's digit cases (level 33: digit 8 has two limbs, index 0;
+# level 32: digit 8 is a broadcast copy; level 30: digit 7 has three limbs, index 1; ...) through the fused digit loop,
+# its own-limb selection and the 96-bit accumulators (beta = 9 terms of 45-bit primes)
+ALPHA4 = (12, [55] + [45] * 33, [55] * 4)
+WIDE = (12, [60, 59, 59, 59], [60, 60])  # q >= 2^56: the [0,8q) butterflies and their accumulator forms
 
 
 @pytest.fixture(scope="module")
@@ -67,7 +73,7 @@ def host(ct, nl):
     return np.stack([ct[0].numpy(nl=nl, squeeze=False), ct[1].numpy(nl=nl, squeeze=False)], axis=1)
 
 
-@pytest.mark.parametrize("params", [PN12, PN13, SMALL3, PN14], ids=["PN12", "PN13", "alpha3", "PN14"])
+@pytest.mark.parametrize("params", [PN12, PN13, SMALL3, PN14, ALPHA4, WIDE], ids=["PN12", "PN13", "alpha3", "PN14", "alpha4", "wide"])
 @pytest.mark.parametrize("kind", ["reduced", "words"])
 def test_switch_keys_in_place_all_levels(lg, params, kind):
     s = Setup(lg, params)
@@ -86,12 +92,13 @@ def test_switch_keys_in_place_all_levels(lg, params, kind):
             assert np.array_equal(g0[b], w0) and np.array_equal(g1[b], w1), level
 
 
-@pytest.mark.parametrize("params", [PN13, PN14], ids=["PN13", "PN14"])
+@pytest.mark.parametrize("params", [PN13, PN14, SMALL3, WIDE], ids=["PN13", "PN14", "alpha3", "wide"])
 @pytest.mark.parametrize("keykind", ["words", "one-word"])
-def test_switch_keys_unreduced_key_words(lg, params, keykind, monkeypatch):
+def test_switch_keys_unreduced_key_words(lg, params, keykind):
     """MRed is total (modular_reduction.go:70-79): a switching key holding arbitrary 64-bit words still has a defined
-    result in the reference.  The 96-bit key-switch accumulators assume key words of at most bits(q) bits; a CTA that
-    meets a wider word must fall back to the 64-bit path and still match, as must LATTIGPU_KS_ACC64=1 on in-range keys."""
+    result in the reference.  The lazy key-switch accumulators (96-bit and 64-bit) assume key words of at most bits(q)
+    bits; a CTA that meets a wider word must repeat its tile on the exact path (canonical digit, MRed + CRed per term) and
+    still match -- on every butterfly class (45-bit, 50-bit and 60-bit limbs) -- as must the "ks_acc64" switch."""
     s = Setup(lg, params)
     rng = np.random.default_rng(27)
     evk = s.evk(rng)
@@ -99,19 +106,22 @@ def test_switch_keys_unreduced_key_words(lg, params, keykind, monkeypatch):
         evk = rng.integers(0, 1 << 64, size=evk.shape, dtype=np.uint64)
     else:  # a single out-of-range word in one tile of one limb of one digit
         evk[s.beta - 1, 1, 1, 2049] = np.uint64((1 << 64) - 3)
-        evk[0, 0, s.nQ, 5] = np.uint64(1 << 47)
+        evk[0, 0, s.nQ, 5] = np.uint64(1 << 62)
     cx = s.ct(rng, "reduced", 2)[:, 0]
     pcx = lg.ring.Poly.from_numpy(np.ascontiguousarray(cx))
-    for acc64 in ("0", "1"):
-        monkeypatch.setenv("LATTIGPU_KS_ACC64", acc64)
-        dk = lg.ckks.SwitchingKey(evk)
-        for level in (s.nQ - 1, s.nQ - 2):
-            p0, p1 = lg.ring.Poly(s.N, s.nQ, 2), lg.ring.Poly(s.N, s.nQ, 2)
-            s.ev.switchKeysInPlace(level, pcx, dk, p0, p1)
-            g0, g1 = p0.numpy(nl=level + 1), p1.numpy(nl=level + 1)
-            for b in range(2):
-                w0, w1 = s.oev.switch_keys_in_place(level, np.ascontiguousarray(cx[b]), evk)
-                assert np.array_equal(g0[b], w0) and np.array_equal(g1[b], w1), (level, acc64)
+    try:
+        for acc64 in (0, 1):
+            lg.ring.debug_set_switch("ks_acc64", acc64)
+            dk = lg.ckks.SwitchingKey(evk)
+            for level in (s.nQ - 1, s.nQ - 2):
+                p0, p1 = lg.ring.Poly(s.N, s.nQ, 2), lg.ring.Poly(s.N, s.nQ, 2)
+                s.ev.switchKeysInPlace(level, pcx, dk, p0, p1)
+                g0, g1 = p0.numpy(nl=level + 1), p1.numpy(nl=level + 1)
+                for b in range(2):
+                    w0, w1 = s.oev.switch_keys_in_place(level, np.ascontiguousarray(cx[b]), evk)
+                    assert np.array_equal(g0[b], w0) and np.array_equal(g1[b], w1), (level, acc64)
+    finally:
+        lg.ring.debug_set_switch("ks_acc64", 0)
 
 
 @pytest.mark.parametrize("params", [PN12, PN13, SMALL3, PN14], ids=["PN12", "PN13", "alpha3", "PN14"])
@@ -149,6 +159,29 @@ def test_mul_relin_rescale(lg, params, kind):
         s.ev.Rescale(s.nQ, out, nb=2)
         for i in range(batch):
             assert np.array_equal(host(out, s.nQ - 2)[i], s.oev.rescale(np.ascontiguousarray(a[i]), nb=2))
+
+
+@pytest.mark.parametrize("kind", ["reduced", "words"])
+def test_mul_relin_rescale_alpha4_all_levels(lg, kind):
+    """MulRelin -> Rescale at EVERY level 33..1 of the headline digit shape (34 + 4 limbs, alpha 4, beta 9; N = 2^12)."""
+    s = Setup(lg, ALPHA4)
+    rng = np.random.default_rng(31)
+    evk = s.evk(rng)
+    rlk = lg.ckks.SwitchingKey(evk)
+    batch = 2
+    a, b = s.ct(rng, kind, batch), s.ct(rng, kind, batch)
+    for level in range(s.nQ - 1, 0, -1):
+        nl = level + 1
+        pa, pb, out = polys(lg, a), polys(lg, b), new_ct(lg, s, batch)
+        s.ev.MulRelin(level, pa, pb, rlk, out)
+        got = host(out, nl)
+        want = np.stack([s.oev.mul_relin(level, np.ascontiguousarray(a[i, :, :nl]), np.ascontiguousarray(b[i, :, :nl]), evk)
+                         for i in range(batch)])
+        assert np.array_equal(got, want), level
+        s.ev.Rescale(nl, out)
+        got = host(out, nl - 1)
+        wr = np.stack([s.oev.rescale(want[i]) for i in range(batch)])
+        assert np.array_equal(got, wr), level
 
 
 def test_mul_relin_without_key_and_with_plaintext(lg):

@@ -91,6 +91,36 @@ def test_ckks_pn16_mulrelin_rescale_rotate(lg):
         assert np.array_equal(g[0], g[2])
 
 
+@pytest.mark.parametrize("level", [32, 30])
+def test_ckks_pn16_partial_digit_levels(lg, level):
+    """PN16QP1761 at full size below the top level: level 32 (digit 8 is a broadcast copy of limb 32) and level 30
+    (beta = 8, digit 7 has three active limbs and takes modUpParams[7][1]) -- SURVEY.md Appendix A's worked cases.
+    One entry against the oracle, duplicated inputs elsewhere."""
+    p = lg.ckks.DefaultParams[lg.ckks.PN16QP1761]
+    N = 1 << p["LogN"]
+    Q, P = lg.ckks.GenModuli(p)
+    nQ, nP = len(Q), len(P)
+    beta = -(-nQ // nP)
+    nl = level + 1
+    rng = np.random.default_rng(0x1A771C0 + 40 + level)
+    evk = np.ascontiguousarray(np.stack([rng.integers(0, q, size=(beta, 2, N), dtype=np.uint64) for q in Q + P], axis=2))
+    batch = 2
+    a, b = uniform_ct(rng, Q[:nl], N, batch), uniform_ct(rng, Q[:nl], N, batch)
+    a[1], b[1] = a[0], b[0]
+    cQ, cP = lg.ring.NewContextWithParams(N, Q), lg.ring.NewContextWithParams(N, P)
+    ev = lg.ckks.NewEvaluator(cQ, cP)
+    key = lg.ckks.SwitchingKey(evk)
+    pa, pb = polys(lg, a), polys(lg, b)
+    out = (lg.ring.Poly(N, nl, batch), lg.ring.Poly(N, nl, batch))
+    ev.MulRelin(level, pa, pb, key, out)
+    ev.Rescale(nl, out)
+    got = host(out, nl - 1)
+    oev = orc.CkksEvaluator(orc.Context(N, Q), orc.Context(N, P))
+    w = oev.rescale(oev.mul_relin(level, np.ascontiguousarray(a[0]), np.ascontiguousarray(b[0]), evk))
+    assert np.array_equal(got[0], w)
+    assert np.array_equal(got[0], got[1])
+
+
 def test_bfv_pn15_mul_relin_rotate(lg):
     p = lg.bfv.DefaultParams[lg.bfv.PN15QP880]
     N = 1 << p["LogN"]
