@@ -56,6 +56,10 @@ def parse():
     ap.add_argument("--hoisted-rotations", type=int, default=8, help="rotations per RotateHoisted call")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the batch is cut into for the pipelined e2e path")
     ap.add_argument("--params", type=int, default=PARAMS_ID, help="index into ckks.DefaultParams (default PN16QP1761)")
+    ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="BASELINE.json configuration (default C4 = the headline; the others print the same JSON contract)")
+    ap.add_argument("--no-legs", action="store_true", help="skip the limb-axis / party-axis legs of a multi-GPU run")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle compare of one timed batch entry")
     return ap.parse_args()
 
 
@@ -135,6 +139,183 @@ def run_reference(args):
     }
     print(json.dumps(line), flush=True)
 
+
+
+# ----------------------------------------------------------------------------
+# Multi-GPU legs (world > 1): the two shard axes that have a real exchange step.
+# Both check their result bit for bit inside the leg and abort the run on a mismatch.
+# ----------------------------------------------------------------------------
+def leg_limb_sharded(args, dev, world, rank, timed_ms):
+    """BASELINE config 4, limb axis: ONE CKKS PN16QP1761 ciphertext pair (and a batch of 8), MulRelin + Rescale with
+    the RNS limbs spread over the ranks, against the same call on this rank's GPU alone.  The sharded result is
+    compared with the single-GPU result on every rank (ckks/evaluator.go:1016-1133, :933-968, :1475-1558)."""
+    import torch
+    import torch.distributed as dist
+
+    import lattigpu
+    from lattigpu import ckks as gckks
+    from lattigpu import ring as gring
+
+    p = gckks.DefaultParams[PARAMS_ID]
+    N = 1 << p["LogN"]
+    Q, P = gckks.GenModuli(p)
+    nQ, nP = len(Q), len(P)
+    beta = -(-nQ // nP)
+    level = nQ - 1
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + 1000)  # the SAME ciphertext on every rank
+    sp = torch.cuda.current_stream().cuda_stream
+
+    def uniform(prefix, moduli):
+        t = torch.empty(*prefix, len(moduli), N, dtype=torch.int64, device=dev)
+        for i, q in enumerate(moduli):
+            t[..., i, :] = torch.randint(0, q, (*prefix, N), dtype=torch.int64, device=dev, generator=g)
+        return t
+
+    cQ, cP = gring.NewContextWithParams(N, Q), gring.NewContextWithParams(N, P)
+    ev = gckks.NewEvaluator(cQ, cP)
+    comm = lattigpu.dist.Comm()
+    evk_t = uniform((beta, 2), Q + P)
+    rlk = gckks.SwitchingKey(N=N, device_ptr=evk_t.data_ptr(), beta=beta, nQP=nQ + nP, keep=evk_t)
+    out = {"what": "CKKS PN16QP1761 MulRelin+Rescale at level 33, limbs of each ciphertext spread over %d GPUs" % world,
+           "exchange": comm.exchange_description(), "cases": []}
+    ok_all = True
+    for batch in (1, 8):
+        wrap = lambda t: gring.Poly.wrap(t.data_ptr(), N, nQ, batch, keep=t)
+        a_t = [uniform((batch,), Q) for _ in range(2)]
+        b_t = [uniform((batch,), Q) for _ in range(2)]
+        o_t = [torch.zeros(batch, nQ, N, dtype=torch.int64, device=dev) for _ in range(2)]
+        s_t = [torch.zeros(batch, nQ, N, dtype=torch.int64, device=dev) for _ in range(2)]
+        a, b = tuple(wrap(t) for t in a_t), tuple(wrap(t) for t in b_t)
+        o, so = tuple(wrap(t) for t in o_t), tuple(wrap(t) for t in s_t)
+
+        def local():
+            ev.MulRelin(level, a, b, rlk, o, stream=sp)
+            ev.Rescale(nQ, o, 1, stream=sp)
+
+        def sharded():
+            comm.MulRelinRescale(ev, level, a, b, rlk, so, stream=sp)
+
+        t_local = timed_ms(local, 20, 5)
+        t_shard = timed_ms(sharded, 20, 5)
+        # parity: gather the limb-resident result (outside the timed region) and compare with the single-GPU words
+        comm.GatherLimbs(ev, nQ - 1, so, stream=sp)
+        torch.cuda.synchronize()
+        same = all(bool(torch.equal(x[:, :nQ - 1], y[:, :nQ - 1])) for x, y in zip(o_t, s_t))
+        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item())
+        ok_all &= same
+        out["cases"].append({"batch": batch, "ms_per_op_one_gpu": t_local / batch, "ms_per_op_sharded": t_shard / batch,
+                             "speedup": t_local / t_shard, "parity": same,
+                             "nvlink_bytes_per_op_per_gpu": comm.exchange_bytes(ev, level, 1)})
+    out["parity"] = ok_all
+    if not ok_all:
+        raise SystemExit("bench.py: limb-sharded MulRelin+Rescale differs from the single-GPU result: %r" % (out,))
+    return out
+
+
+def leg_party(args, dev, world, rank, timed_ms):
+    """BASELINE config 5, party axis: dckks over CKKS PN15QP880 (N=2^15, 18+3 limbs), 8 parties spread over the ranks.
+    Every rank runs CKG.GenShare (dckks/publickey_gen.go:39-42) and PCKS.GenShare (dckks/public_keyswitching.go:63-96)
+    for its parties, adds its own shares, and the ranks aggregate with one all-reduce + Reduce
+    (lg_comm_aggregate_shares).  Checked against the reference's sequential chain of AggregateShares
+    (publickey_gen.go:45-47, public_keyswitching.go:99-103) over all 8 shares, recomputed on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    import lattigpu
+    from lattigpu import ckks as gckks
+    from lattigpu import dckks as gdckks
+    from lattigpu import ring as gring
+
+    parties = 8
+    if parties % world:
+        return {"skipped": "8 parties do not divide over %d ranks" % world}
+    mine = parties // world
+    p = gckks.DefaultParams[gckks.PN15QP880]
+    N = 1 << p["LogN"]
+    Q, P = gckks.GenModuli(p)
+    QP = Q + P
+    nQ, nK = len(Q), len(QP)
+    level = nQ - 1
+    sp = torch.cuda.current_stream().cuda_stream
+    cQ, cP, cK = (gring.NewContextWithParams(N, m) for m in (Q, P, QP))
+    ckg, pcks = gdckks.CKGProtocol(cK), gdckks.PCKSProtocol(cQ, cP, cK)
+    comm = lattigpu.dist.Comm()
+
+    def party_inputs(idx, mods, salt):
+        """[len(idx)][len(mods)][N] uniform words, party i seeded by its index (so every rank can rebuild any party)"""
+        t = torch.empty(len(idx), len(mods), N, dtype=torch.int64, device=dev)
+        for k, i in enumerate(idx):
+            g = torch.Generator(device=dev)
+            g.manual_seed(SEED + 5000 + 64 * i + salt)
+            for j, q in enumerate(mods):
+                t[k, j] = torch.randint(0, q, (N,), dtype=torch.int64, device=dev, generator=g)
+        return t
+
+    def shared_inputs(mods, salt):
+        g = torch.Generator(device=dev)
+        g.manual_seed(SEED + 7000 + salt)
+        t = torch.empty(1, len(mods), N, dtype=torch.int64, device=dev)
+        for j, q in enumerate(mods):
+            t[0, j] = torch.randint(0, q, (N,), dtype=torch.int64, device=dev, generator=g)
+        return t
+
+    W = lambda t, nl: gring.Poly.wrap(t.data_ptr(), N, nl, t.shape[0], keep=t)
+    crs_1, pk0_1, pk1_1, ct1_1 = shared_inputs(QP, 1), shared_inputs(QP, 2), shared_inputs(QP, 3), shared_inputs(Q, 4)
+
+    def build(idx):
+        n = len(idx)
+        t = {"sk": party_inputs(idx, QP, 0), "e": party_inputs(idx, QP, 1), "u": party_inputs(idx, QP, 2),
+             "e0": party_inputs(idx, QP, 3), "e1": party_inputs(idx, QP, 4), "skq": party_inputs(idx, Q, 5),
+             "crs": crs_1.expand(n, -1, -1).contiguous(), "pk0": pk0_1.expand(n, -1, -1).contiguous(),
+             "pk1": pk1_1.expand(n, -1, -1).contiguous(), "ct1": ct1_1.expand(n, -1, -1).contiguous(),
+             "ckg": torch.zeros(n, nK, N, dtype=torch.int64, device=dev),
+             "s0": torch.zeros(n, nQ, N, dtype=torch.int64, device=dev), "s1": torch.zeros(n, nQ, N, dtype=torch.int64, device=dev)}
+        return t
+
+    def gen_shares(t):
+        ckg.GenShare(W(t["sk"], nK), W(t["crs"], nK), W(t["ckg"], nK), W(t["e"], nK), stream=sp)
+        pcks.GenShare(level, W(t["skq"], nQ), (W(t["pk0"], nK), W(t["pk1"], nK)), W(t["ct1"], nQ), (W(t["s0"], nQ), W(t["s1"], nQ)),
+                      W(t["u"], nK), W(t["e0"], nK), W(t["e1"], nK), stream=sp)
+
+    def chain(ctx, t, nl):
+        """the reference's AggregateShares chain over the batch entries of t, into entry 0"""
+        acc = W(t[0:1], nl)
+        for k in range(1, t.shape[0]):
+            ctx.Add(acc, W(t[k:k + 1], nl), acc, stream=sp)
+        return t[0:1]
+
+    my_idx = list(range(rank * mine, (rank + 1) * mine))
+    tm = build(my_idx)
+
+    def round_():
+        gen_shares(tm)
+        for key, ctx, nl in (("ckg", cK, nK), ("s0", cQ, nQ), ("s1", cQ, nQ)):
+            chain(ctx, tm[key], nl)
+            comm.AggregateShares(ctx, W(tm[key][0:1], nl), stream=sp)
+
+    t_round = timed_ms(round_, 10, 3)
+    # parity: all 8 parties on this rank, sequential chain in party order
+    ta = build(list(range(parties)))
+    gen_shares(ta)
+    round_()  # leaves the aggregates in entry 0 of tm[*]
+    ok = True
+    for key, ctx, nl in (("ckg", cK, nK), ("s0", cQ, nQ), ("s1", cQ, nQ)):
+        want = chain(ctx, ta[key], nl)
+        torch.cuda.synchronize()
+        ok &= bool(torch.equal(want, tm[key][0:1]))
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok = bool(flag.item())
+    res = {"what": "dckks PN15QP880: CKG.GenShare + PCKS.GenShare for 8 parties (%d per GPU), AggregateShares over %d GPUs" % (mine, world),
+           "collective": "ncclAllReduce(sum, uint64) + Reduce kernel, 3 polys per round", "parties": parties,
+           "allreduce_bytes_per_round": (nK + 2 * nQ) * N * 8, "ms_per_round": t_round,
+           "party_shares_per_s": parties * 1e3 / t_round, "parity": ok}
+    if not ok:
+        raise SystemExit("bench.py: aggregated shares differ from the sequential AggregateShares chain: %r" % (res,))
+    return res
 
 # ----------------------------------------------------------------------------
 # GPU arm
@@ -268,6 +449,10 @@ def run_gpu(args):
             ms = float(t.item())
         return ms, launches
 
+    def timed_ms(fn, reps, warm):
+        ms_, _ = timed(fn, reps, warm)
+        return ms_ / reps
+
     # ---- headline: MulRelin + Rescale, inputs resident in HBM -------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, launches = timed(step, args.steps, args.warmup)
@@ -328,7 +513,7 @@ def run_gpu(args):
     butterflies = (N // 2) * p["LogN"] * nlimbs_launch
     # ncu --set full DRAM bytes of the same launch pair (profiles/r01_ncu_ntt_fwd.json, captured per round)
     traffic = None
-    for name in ("r01_ncu_ntt_fwd.json", "r01_ncu_ntt_fwd_b16.json"):  # one capture per batch size
+    for name in ("r02_ncu_ntt_fwd.json", "r01_ncu_ntt_fwd.json", "r01_ncu_ntt_fwd_b16.json"):  # one capture per round / batch size
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 prof = json.load(f)
@@ -345,16 +530,20 @@ def run_gpu(args):
            "lazy": sum(1 for q in Q if q >= (1 << 56))}
     bf_per_limb = (N // 2) * p["LogN"]
     int_floor_us = 1e6 * B * sum(mix[k] * bf_per_limb / peak_bf[k] for k in mix)
+    # quote the SLOWER bound.  The transform is INT-pipe bound long before it is HBM bound, so the
+    # binding roof (bound/achieved/peak/frac) is the register-resident butterfly rate; the HBM side (algorithmic bytes
+    # against the measured copy bandwidth, and the DRAM traffic ncu saw) stands beside it.
+    bf_rate = butterflies / (fwd_us * 1e-6)
+    bf_peak = butterflies / (int_floor_us * 1e-6)
     roofline = {
-        "bound": "hbm", "kernel": "ntt_fwd (strided phase + pipelined contiguous phase, one batched limb-NTT launch pair)",
-        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "limb_ntts_per_launch": nlimbs_launch,
-        "launch_us": fwd_us,
-        # the kernel is INT-pipe bound before it is HBM bound (quote the slower bound)
-        "int_pipe": {"butterflies_per_s": butterflies / (fwd_us * 1e-6),
-                     "butterfly_peak_per_s": butterflies / (int_floor_us * 1e-6),
-                     "frac": int_floor_us / fwd_us, "limb_mix": mix,
-                     "peak_source": "profiles/r01_butterfly_peaks.txt (register-resident microbenchmark, this GPU type)"},
+        "bound": "int", "kernel": "ntt_fwd (strided phase + pipelined contiguous phase, one batched limb-NTT launch pair)",
+        "achieved": bf_rate / 1e9, "peak": bf_peak / 1e9, "unit": "Gbutterfly/s", "frac": bf_rate / bf_peak,
+        "traffic": traffic, "limb_mix": mix,
+        "peak_source": "profiles/r01_butterfly_peaks.txt (register-resident butterfly microbenchmark on B200, weighted by "
+                       "the limb mix); tensor cores unused: exact 64-bit modular integer arithmetic",
+        "algorithmic_bytes_per_launch": alg_bytes, "limb_ntts_per_launch": nlimbs_launch, "launch_us": fwd_us,
+        "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
+                "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None},
     }
 
     # ---- op-level roofline, SURVEY.md 8(d): max(INT work / INT peak, compulsory bytes / HBM peak) over the measured
@@ -376,13 +565,53 @@ def run_gpu(args):
     bytes_op = 8.0 * N * (4 * nl_top + 2 * (nl_top - 1)) + 8.0 * N * 2 * beta * (nl_top + alpha) / B
     hbm_us = 1e6 * bytes_op / (hbm_peak * 1e9)
     us_per_op = 1e3 * ms_per_step / B
+    traffic_step = None  # total DRAM bytes of one step, summed over its launches in the ncu --set full capture
+    for name in ("r02_step_traffic.json", "r01_step_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                prof = json.load(f)
+            if prof.get("batch") == B and prof.get("N") == N:
+                traffic_step = prof["dram_bytes_per_step"]
+                break
+        except Exception:
+            pass
     roofline_op = {
         "what": "one MulRelin+Rescale (SURVEY.md 8(d) counts), key bytes amortised over the batch",
+        "traffic_step": traffic_step, "compulsory_bytes_per_step": bytes_op * B,
         "limb_ntts_per_op": ntts_per_op, "modmuls_per_op": modmuls_per_op, "compulsory_bytes_per_op": bytes_op,
         "int_bound_us": int_us, "hbm_bound_us": hbm_us, "measured_us": us_per_op,
         "bound": "int" if int_us >= hbm_us else "hbm", "frac": max(int_us, hbm_us) / us_per_op,
         "int_peak": "61 IMAD/clk/SM x 148 SMs x %.0f MHz (profiles/r01_int_pipe.txt), 11 multiplies per modular product" % sm_mhz,
     }
+
+    # ---- one entry of the timed batch against the oracle (outside the timed region) ------------------
+    parity_check = None
+    if rank == 0 and not args.no_parity_check:
+        from oracle import ring_oracle as orc
+
+        step()
+        torch.cuda.synchronize()
+        i = B - 1
+        ha = np.ascontiguousarray(np.stack([a_t[0][i].cpu().numpy(), a_t[1][i].cpu().numpy()]).astype(np.uint64))
+        hb = np.ascontiguousarray(np.stack([b_t[0][i].cpu().numpy(), b_t[1][i].cpu().numpy()]).astype(np.uint64))
+        hk = np.ascontiguousarray(evk_t.cpu().numpy().astype(np.uint64))
+        oev = orc.CkksEvaluator(orc.Context(N, Q), orc.Context(N, P))
+        t0 = time.perf_counter()
+        want = oev.rescale(oev.mul_relin(level, ha, hb, hk))
+        got = np.stack([o_t[0][i, :nQ - 1].cpu().numpy(), o_t[1][i, :nQ - 1].cpu().numpy()]).astype(np.uint64)
+        equal = bool(np.array_equal(got, want))
+        parity_check = {"entry": i, "of_batch": B, "against": "oracle/ring_oracle.c (CPU restatement)", "equal": equal,
+                        "oracle_s": time.perf_counter() - t0}
+        if not equal:
+            raise SystemExit("bench.py: entry %d of the timed batch differs from the oracle" % i)
+
+    # ---- multi-GPU legs: limb axis (config 4) and party axis (config 5) -----------------------------
+    legs = {"limb_sharded": None, "party": None}
+    if world > 1 and not args.no_legs:
+        legs["limb_sharded"] = leg_limb_sharded(args, dev, world, rank, timed_ms)
+        torch.cuda.empty_cache()
+        legs["party"] = leg_party(args, dev, world, rank, timed_ms)
+        torch.cuda.empty_cache()
 
     # ---- e2e: host buffers through the C ABI ------------------------------------
     e2e = None
@@ -461,8 +690,15 @@ def run_gpu(args):
             copy_only()
         barrier()
         copy_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
-        e2e = {"value": world * B * e2e_steps / dt, "unit": "ops/s", "h2d_bytes_per_step": 4 * B * nQ * N * 8,
+        h2d_b, d2h_b = 4 * B * nQ * N * 8, 2 * B * (nQ - 1) * N * 8
+        e2e = {"value": world * B * e2e_steps / dt, "unit": "ops/s", "h2d_bytes_per_step": h2d_b,
                "copy_only_ms_per_step": copy_ms,
+               # what this rank's host link delivered with all ranks copying at once (both directions overlapped)
+               "per_rank_copy_GBps": {"h2d": h2d_b / copy_ms / 1e6, "d2h": d2h_b / copy_ms / 1e6,
+                                      "aggregate_all_ranks": world * (h2d_b + d2h_b) / copy_ms / 1e6},
+               "limiter": "host link: the step moves %.2f GB per GPU over PCIe; with N ranks copying concurrently the "
+                          "aggregate host-memory / root-complex bandwidth of the box (all GPUs report one NUMA node) caps "
+                          "the rate, not a kernel or a collective" % ((h2d_b + d2h_b) / 1e9),
                "d2h_bytes_per_step": 2 * B * (nQ - 1) * N * 8, "ms_per_step": 1e3 * dt / e2e_steps,
                "note": "pinned host buffers; per chunk of %d ciphertexts: lg_poly_upload_async x4, MulRelin, Rescale, "
                        "lg_poly_download_async x2; %d chunks over %d streams, host sync per step" % (cb, nchunks, nstreams)}
@@ -488,6 +724,7 @@ def run_gpu(args):
             "ntt": {"fwd_limb_ntt_per_s": ntt_fwd_rate, "inv_limb_ntt_per_s": ntt_inv_rate, "N": N,
                     "limbs_per_launch": nlimbs_launch, "fwd_us_per_launch": fwd_us, "inv_us_per_launch": inv_us},
             "rotate": rotate, "roofline": roofline, "roofline_op": roofline_op, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "parity_check": parity_check, "limb_sharded": legs["limb_sharded"], "party": legs["party"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:

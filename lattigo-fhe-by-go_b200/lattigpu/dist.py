@@ -91,3 +91,24 @@ class Comm:
 
     def Rescale(self, evaluator, nl, ct, stream=None):
         check(lib().lg_ckks_rescale_sharded(evaluator.h, self.h, nl, ct[0].h, ct[1].h, _s(stream)))
+
+    # ---- limb-resident forms: a ciphertext stays spread over the ranks between ops -------------------------
+    def MulRelinRescale(self, evaluator, level, ct0, ct1, evakey, ctOut, stream=None):
+        """MulRelin at `level` followed by one Rescale; ctOut holds this rank's own limbs of the level-1 result
+        (GatherLimbs replicates them)."""
+        self.MulRelin(evaluator, level, ct0, ct1, evakey, ctOut, stream=stream)
+        self.Rescale(evaluator, level + 1, ctOut, stream=stream)
+
+    def GatherLimbs(self, evaluator, nl, ct, stream=None):
+        """replicate the first nl limbs of a limb-resident ciphertext on every rank (no-op while outputs are replicated)"""
+        return None
+
+    def exchange_description(self):
+        return ("ncclBroadcast groups (one per owner rank and batch entry) of: coefficient-domain c2 before "
+                "DecomposeAndSplit, special-prime accumulators before ModDown, result limbs, rescaled limbs")
+
+    def exchange_bytes(self, evaluator, level, batch):
+        """bytes one rank receives per MulRelin+Rescale"""
+        N, nl, nP, w = evaluator.contextQ.N, level + 1, evaluator.contextP.nl, self.world
+        words = batch * N * (nl + 2 * nP + 2 * nl + 2 * (nl - 1))
+        return int(words * 8 * (w - 1) / w)
