@@ -174,7 +174,8 @@ def leg_limb_sharded(args, dev, world, rank, timed_ms):
 
     cQ, cP = gring.NewContextWithParams(N, Q), gring.NewContextWithParams(N, P)
     ev = gckks.NewEvaluator(cQ, cP)
-    comm = lattigpu.dist.Comm()
+    comm = lattigpu.dist.Comm(nccl=False)  # the limb axis exchanges through peer memory: no NCCL communicator
+    comm.reserve(ev, 8)                    # exchange buffers for the largest batch of the leg, IPC-mapped by every peer
     evk_t = uniform((beta, 2), Q + P)
     rlk = gckks.SwitchingKey(N=N, device_ptr=evk_t.data_ptr(), beta=beta, nQP=nQ + nP, keep=evk_t)
     out = {"what": "CKKS PN16QP1761 MulRelin+Rescale at level 33, limbs of each ciphertext spread over %d GPUs" % world,
@@ -198,6 +199,7 @@ def leg_limb_sharded(args, dev, world, rank, timed_ms):
 
         t_local = timed_ms(local, 20, 5)
         t_shard = timed_ms(sharded, 20, 5)
+        comm.check(stream=sp)  # raises if a cross-rank barrier timed out
         # parity: gather the limb-resident result (outside the timed region) and compare with the single-GPU words
         comm.GatherLimbs(ev, nQ - 1, so, stream=sp)
         torch.cuda.synchronize()

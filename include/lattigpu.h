@@ -334,26 +334,54 @@ int lg_crp_clock(lg_crp* g, lg_poly* out, int batch_index, lg_stream_t stream);
 int lg_crp_clock_host(lg_crp* g, uint64_t* host);
 
 /* ---- multi-GPU (one process per GPU) ------------------------------ */
-/* The reference is single-process; these entry points add the two exchange steps the path has when it is
- * spread over the GPUs of a node.  NCCL is resolved at run time (dlopen "libnccl.so.2"). */
+/* The reference is single-process; these entry points add the exchange steps the path has when it is spread over the
+ * GPUs of a node.  NCCL (resolved at run time, dlopen "libnccl.so.2") serves the one reduction, AggregateShares; the
+ * limb axis moves its limbs through peer memory over NVLink with no library collective on the data path. */
 int lg_comm_get_unique_id(uint8_t* id128);            /* rank 0; ship the 128 bytes to the other ranks */
-int lg_comm_create(int world, int rank, const uint8_t* id128, lg_comm** out); /* after lg_set_device */
+/* after lg_set_device; id128 = NULL creates a handle for the peer-memory (limb-axis) paths only */
+int lg_comm_create(int world, int rank, const uint8_t* id128, lg_comm** out);
 int lg_comm_destroy(lg_comm* c);
 int lg_comm_world(const lg_comm* c);
 int lg_comm_rank(const lg_comm* c);
-/* ownership rule of the limb axis: rank r owns limbs [r*n/world, (r+1)*n/world)   (host only) */
-int lg_comm_limb_range(int nlimbs, int world, int rank, int* begin, int* end);
 /* party axis: AggregateShares of dckks/dbfv (e.g. dckks/publickey_gen.go:45-47) over ranks =
  * all-reduce(sum,u64) + Reduce; p holds this rank's share on entry and the aggregate on return */
 int lg_comm_aggregate_shares(const lg_comm* c, const lg_ring* r, int nl, lg_poly* p, lg_stream_t s);
-/* limb axis: one ciphertext (or a small batch) with its RNS limbs spread over the ranks; inputs and outputs
- * are replicated, the all-gathers sit exactly where a basis extension needs every limb */
-int lg_ckks_switch_keys_in_place_sharded(lg_ckks_eval* e, const lg_comm* c, int level, const lg_poly* cx, const lg_swk* evk,
+
+/* Limb axis (BASELINE config 4): the RNS limbs of a ciphertext are spread cyclically over the ranks -- limb t of
+ * Q || P belongs to rank t mod world (lg_comm_limb_owner), balanced at every level and stable when a limb is dropped.
+ * A limb-resident polynomial is a full-size handle of which only the rank's own limbs are meaningful.
+ * Exchange: every rank owns one exchange buffer that its peers map; limbs cross NVLink exactly where a basis
+ * extension needs every source limb (c2 before DecomposeAndSplit ckks/evaluator.go:1503-1513, the special-prime
+ * accumulators before ModDown ring_basis_extension.go:219-226, the last limb of a rescale ring_scaling.go:80-103):
+ * the consuming kernels load them from the owner's buffer, ordered by a one-CTA barrier kernel in stream order.
+ *   setup (once):  lg_comm_xbuf_alloc on every rank, ship handle128 to the peers, lg_comm_xbuf_open for each of them
+ *                  (ranks living in ONE process attach directly: lg_comm_xbuf_attach).
+ * Every rank must issue the same sequence of limb-axis calls.  A barrier that waits more than 5 s for a peer sets an
+ * error that lg_comm_check reports (after synchronising the stream). */
+int lg_comm_limb_owner(int limb, int world);                                    /* host only */
+size_t lg_comm_xbuf_words_needed(uint64_t N, int nQ, int nP, int batch);        /* host only: MulRelin+Rescale+gather */
+int lg_comm_xbuf_alloc(lg_comm* c, size_t words, uint8_t* handle128);           /* handle128 may be NULL (one process) */
+int lg_comm_xbuf_open(lg_comm* c, int peer, const uint8_t* handle128);          /* CUDA IPC mapping of a peer's buffer */
+int lg_comm_xbuf_attach(lg_comm* c, int peer, const lg_comm* peer_comm);        /* same process: direct pointers */
+size_t lg_comm_xbuf_words(const lg_comm* c);
+int lg_comm_check(lg_comm* c, lg_stream_t s);
+/* replicate the first nl limbs of a limb-resident polynomial on every rank */
+int lg_comm_gather_limbs(lg_comm* c, const lg_ring* r, int nl, lg_poly* p, lg_stream_t s);
+/* limb-resident forms of switchKeysInPlace (ckks/evaluator.go:1475-1558), MulRelin (:1016-1133) followed by
+ * nrescale Rescale steps (:933-968), and Rescale: inputs and outputs hold the rank's own limbs */
+int lg_ckks_switch_keys_in_place_resident(lg_ckks_eval* e, lg_comm* c, int level, const lg_poly* cx, const lg_swk* evk,
+                                          lg_poly* p0, lg_poly* p1, lg_stream_t s);
+int lg_ckks_mul_relin_rescale_resident(lg_ckks_eval* e, lg_comm* c, int level, const lg_poly* a0, const lg_poly* a1,
+                                       const lg_poly* b0, const lg_poly* b1, const lg_swk* rlk, lg_poly* out0, lg_poly* out1,
+                                       int nrescale, lg_stream_t s);
+int lg_ckks_rescale_resident(lg_ckks_eval* e, lg_comm* c, int nl, lg_poly* c0, lg_poly* c1, lg_stream_t s);
+/* replicated forms: inputs are read on the rank's own limbs only, outputs are gathered onto every rank */
+int lg_ckks_switch_keys_in_place_sharded(lg_ckks_eval* e, lg_comm* c, int level, const lg_poly* cx, const lg_swk* evk,
                                          lg_poly* p0, lg_poly* p1, lg_stream_t s);
-int lg_ckks_mul_relin_sharded(lg_ckks_eval* e, const lg_comm* c, int level, const lg_poly* a0, const lg_poly* a1,
+int lg_ckks_mul_relin_sharded(lg_ckks_eval* e, lg_comm* c, int level, const lg_poly* a0, const lg_poly* a1,
                               const lg_poly* b0, const lg_poly* b1, const lg_swk* rlk, lg_poly* out0, lg_poly* out1,
                               lg_stream_t s);
-int lg_ckks_rescale_sharded(lg_ckks_eval* e, const lg_comm* c, int nl, lg_poly* c0, lg_poly* c1, lg_stream_t s);
+int lg_ckks_rescale_sharded(lg_ckks_eval* e, lg_comm* c, int nl, lg_poly* c0, lg_poly* c1, lg_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) modup_kernel(const ModUpArgs a) {
         u64* out = a.out[k] + bt * a.out_bs[k] + x;
 #pragma unroll 1
         for (int t = 0; t < a.ndst[k]; ++t) {
-            const int tg = a.tgt0[k] + t;
+            const int tg = a.tgt0[k] + t * (a.tstep ? a.tstep : 1);
             const u64 pj = __ldg(M.dstQ + tg), pinv = __ldg(M.dstQinv + tg);
             // The reference sums canonical MRed(y_i, qispjMont[i][j]) terms (BRedAdd when i&7==6) and
             // canonicalises with a final BRedAdd (:379-389), i.e. it returns
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128) modup_fast_kernel(const ModUpArgs a) {
         int idx = e / ROW, f = e - idx * ROW, tg = 0;
         for (int k = 0, o = idx; k < a.nruns; ++k) {
             if (o < a.ndst[k]) {
-                tg = a.tgt0[k] + o;
+                tg = a.tgt0[k] + o * (a.tstep ? a.tstep : 1);
                 break;
             }
             o -= a.ndst[k];
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(128) modup_fast_kernel(const ModUpArgs a) {
         const u64* in = a.in + bt * a.in_bs + x;
 #pragma unroll
         for (int i = 0; i < NSRC; ++i) {
-            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(in + (size_t)i * a.N);
+            const u64* srcp = a.src[0] ? a.src[i] + bt * a.in_bs + x : in + (size_t)i * a.N;
+            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(srcp);
             if (a.copy_out) *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x) = val;
             const u64 qi = __ldg(M.srcQ + i), qib = __ldg(M.qib + i), qinv = __ldg(M.srcQinv + i);
             const u64 ya = mred(val.x, qib, qi, qinv), yb = mred(val.y, qib, qi, qinv);
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(128) modup_wide_kernel(const ModUpArgs a) {
         int idx = e / ROW, f = e - idx * ROW, tg = 0;
         for (int k = 0, o = idx; k < a.nruns; ++k) {
             if (o < a.ndst[k]) {
-                tg = a.tgt0[k] + o;
+                tg = a.tgt0[k] + o * (a.tstep ? a.tstep : 1);
                 break;
             }
             o -= a.ndst[k];
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
         int tg = 0;
         for (int k = 0, o = idx; k < a.nruns; ++k) {
             if (o < a.ndst[k]) {
-                tg = a.tgt0[k] + o;
+                tg = a.tgt0[k] + o * (a.tstep ? a.tstep : 1);
                 break;
             }
             o -= a.ndst[k];
@@ -334,7 +335,8 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
         const u64* in = a.in + bt * a.in_bs + x;
 #pragma unroll
         for (int i = 0; i < NSRC; ++i) {
-            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(in + (size_t)i * a.N);
+            const u64* srcp = a.src[0] ? a.src[i] + bt * a.in_bs + x : in + (size_t)i * a.N;
+            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(srcp);
             if (a.copy_out) *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x) = val;
             const u64 qi = __ldg(M.srcQ + i), qib = __ldg(M.qib + i), qinv = __ldg(M.srcQinv + i);
             const u64 ya = mred(val.x, qib, qi, qinv), yb = mred(val.y, qib, qi, qinv);
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
         int tg = 0;
         for (int k = 0, o = idx; k < a.nruns; ++k) {
             if (o < a.ndst[k]) {
-                tg = a.tgt0[k] + o;
+                tg = a.tgt0[k] + o * (a.tstep ? a.tstep : 1);
                 break;
             }
             o -= a.ndst[k];
@@ -448,7 +450,8 @@ __global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
         const u64* in = a.in + bt * a.in_bs + x;
 #pragma unroll
         for (int i = 0; i < NSRC; ++i) {
-            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(in + (size_t)i * a.N);
+            const u64* srcp = a.src[0] ? a.src[i] + bt * a.in_bs + x : in + (size_t)i * a.N;
+            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(srcp);
             if (a.copy_out) *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x) = val;
             const u64 qi = __ldg(M.srcQ + i), qib = __ldg(M.qib + i), qinv = __ldg(M.srcQinv + i);
             const u64 ya = mred(val.x, qib, qi, qinv), yb = mred(val.y, qib, qi, qinv);

@@ -29,11 +29,14 @@ struct RingTables {
 // Maps the j-th data limb of a launch to a table limb: the first n0 data limbs
 // use table limbs l0.., the rest use l1...  (Q limbs 0..level followed by the
 // special primes at #Q.., as in ckks/evaluator.go:1519-1525.)
+// With st > 1 consecutive data limbs are st table limbs apart: the cyclic limb ownership of the multi-GPU limb axis
+// (rank r of w owns table limbs r, r+w, r+2w, ...: l0 = first own Q limb, l1 = first own special prime, st = w).
 struct LimbMap {
     int n0, l0, l1;
-    __host__ __device__ int operator()(int j) const { return j < n0 ? l0 + j : l1 + (j - n0); }
+    int st = 1;
+    __host__ __device__ int operator()(int j) const { return j < n0 ? l0 + j * st : l1 + (j - n0) * st; }
 };
-static inline LimbMap limb_map_identity() { return LimbMap{1 << 30, 0, 0}; }
+static inline LimbMap limb_map_identity() { return LimbMap{1 << 30, 0, 0, 1}; }
 
 __device__ __forceinline__ LimbConst load_limb_const(const RingTables& T, int tl) {
     LimbConst c;

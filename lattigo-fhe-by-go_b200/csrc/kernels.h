@@ -47,7 +47,8 @@ struct NttTail {
     const u64* a[2];
     u64* out[2];
     size_t a_bs[2], out_bs[2];
-    const u64* s;  // device array, one scalar per data limb (kept out of the kernel parameters: every NTT CTA loads those)
+    size_t a_ls, out_ls;  // words between consecutive data limbs of a[] / out[] (0 = N)
+    const u64* s;  // device array, one scalar per TABLE limb (kept out of the kernel parameters: every NTT CTA loads those)
     int a_canon;   // the words of a[] are known to be below q (key-switch accumulators): the transform is subtracted unreduced
 };
 // Broadcast input of the forward transform's first phase (logN >= 12): every data limb j transforms the same source
@@ -55,7 +56,7 @@ struct NttTail {
 // (ring_scaling.go:17-28, :80-103, add = pHalfNegQi or nothing) without materialising the copies.
 struct NttBcast {
     int enabled;
-    const u64* add;  // device array per data limb, or nullptr
+    const u64* add;  // device array per TABLE limb, or nullptr
 };
 struct NttArgs {
     RingTables T;
@@ -63,11 +64,12 @@ struct NttArgs {
     const u64* in;
     u64* out;
     size_t in_bstride, out_bstride;  // words between consecutive batch entries
+    size_t in_ls, out_ls;            // words between consecutive data limbs (0 = N); the second phase runs in place on out
     int skip0, skip1;                // data limbs in [skip0, skip1) are left untouched
-    // forward, digit-batched launches: when skip_alpha > 0 the batch index is digit*skip_div + b and the
-    // skipped limbs of that entry are [digit*skip_alpha, min((digit+1)*skip_alpha, skip_nl))
+    // forward, digit-batched launches: when skip_alpha > 0 the batch index is digit*skip_div + b and the skipped limbs
+    // of that entry are the digit's own ones: data limbs whose TABLE limb tl lies in
+    // [digit*skip_alpha, min((digit+1)*skip_alpha, skip_nl))
     int skip_alpha, skip_div, skip_nl;
-    int skip_limb0;                  // ... of the launch's first data limb (limb-sharded launches), default 0
     // inverse only: per (batch, limb) flag, non-zero = some input word is above 2q, use the literal
     // butterflies for that limb (written by lg_launch_range_flags); nullptr = inputs known to be in range
     const u32* flags;
@@ -90,15 +92,14 @@ struct KsFusedArgs {
     LimbMap map;        // data limb -> table limb (also the evk limb)
     const u64* D;       // digits after the strided phase: limb j of batch b of digit i at D + i*d_ds + b*d_bs + j*N
     size_t d_ds, d_bs;
-    const u64* cx;      // NTT-domain key-switch input: limb j of batch b at cx + b*cx_bs + j*N
-    size_t cx_bs;
+    const u64* cx;      // NTT-domain key-switch input: limb j of batch b at cx + b*cx_bs + j*cx_ls
+    size_t cx_bs, cx_ls;  // cx_ls = 0: N
     const u64* evk;     // evk[i][h], table limb tl at evk + i*evk_ds + h*evk_hs + tl*N (shared by the batch)
     size_t evk_ds, evk_hs;
     u64* acc0;          // outputs, limb j of batch b at acc + b*acc_bs + j*N, canonical
     u64* acc1;
     size_t acc_bs;
-    int beta, alpha, nl;  // digit i owns data limbs [i*alpha, min((i+1)*alpha, nl))
-    int limb0;            // index of the launch's first data limb (limb-sharded launches; pointers are pre-offset)
+    int beta, alpha, nl;  // digit i owns the data limbs whose TABLE limb lies in [i*alpha, min((i+1)*alpha, nl))
     int acc64;            // 1 = never take the 96-bit accumulators (LATTIGPU_KS_ACC64=1: A/B and cross-check)
 };
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st);
@@ -195,7 +196,9 @@ struct ModUpArgs {
     ModUpTables M;
     u32 N;
     int nsrc;            // active sources: tables rows 0..nsrc-1
-    const u64* in;       // source limb i at in + b*in_bs + i*N
+    const u64* in;       // source limb i at in + b*in_bs + i*N ...
+    const u64* src[4];   // ... unless src[0] != nullptr (nsrc <= 4): source limb i at src[i] + b*in_bs -- limbs that live in
+                         // different buffers, e.g. on peer GPUs (multi-GPU limb axis)
     size_t in_bs;
     // targets are described by up to 3 runs: run k writes ndst_k limbs starting at
     // out_k (limb stride N) using table targets tgt0_k, tgt0_k+1, ...
@@ -204,6 +207,7 @@ struct ModUpArgs {
     size_t out_bs[3];
     int ndst[3];
     int tgt0[3];
+    int tstep;           // table targets of a run are tgt0, tgt0 + tstep, ... (0 = 1); the output limbs stay N words apart
     // optional pass-through: copy the nsrc source limbs to copy_out (Decompose*'s
     // "p1.Coeffs[i+p0idxst][x] = p0.Coeffs[i+p0idxst][x]")
     u64* copy_out;
@@ -274,6 +278,8 @@ struct TensorArgs {
     size_t a_bs[2], b_bs[2], c_bs[3];
     int square;
     int nomod;  // 1: BFV form, c1 is accumulated without reduction (bfv/evaluator.go:344,361)
-    int limb0;  // first limb processed (limb-sharded launches); blockIdx.y counts from it
+    int limb0;  // first limb processed (limb-sharded launches); blockIdx.y counts from it ...
+    int lstep = 0;  // ... in steps of lstep limbs (0 = 1)
+    int c2_compact = 0;  // 1: c2 limb y of the launch goes to slot y of c2 (rank-private scratch) instead of its own limb index
 };
 int lg_launch_tensor(const TensorArgs& a, int nlimbs, int batch, cudaStream_t st);

@@ -52,16 +52,17 @@ __global__ void __launch_bounds__(256) ks_mac_kernel(const KsMacArgs a) {
 // instead of the reference's six passes.  Outputs may alias inputs (same-index access only).
 __global__ void __launch_bounds__(256) tensor_kernel(const TensorArgs a) {
     const int j = blockIdx.y, bt = blockIdx.z;
-    const LimbConst k = load_limb_const(a.T, a.limb0 + j);
+    const int limb = a.limb0 + j * (a.lstep ? a.lstep : 1);
+    const LimbConst k = load_limb_const(a.T, limb);
     const u32 N = a.T.N;
-    const size_t off = (size_t)(a.limb0 + j) * N;
+    const size_t off = (size_t)limb * N;
     const ulonglong2* a0 = reinterpret_cast<const ulonglong2*>(a.a0 + bt * a.a_bs[0] + off);
     const ulonglong2* a1 = reinterpret_cast<const ulonglong2*>(a.a1 + bt * a.a_bs[1] + off);
     const ulonglong2* b0 = reinterpret_cast<const ulonglong2*>(a.b0 + bt * a.b_bs[0] + off);
     const ulonglong2* b1 = reinterpret_cast<const ulonglong2*>(a.b1 + bt * a.b_bs[1] + off);
     ulonglong2* c0 = reinterpret_cast<ulonglong2*>(a.c0 + bt * a.c_bs[0] + off);
     ulonglong2* c1 = reinterpret_cast<ulonglong2*>(a.c1 + bt * a.c_bs[1] + off);
-    ulonglong2* c2 = reinterpret_cast<ulonglong2*>(a.c2 + bt * a.c_bs[2] + off);
+    ulonglong2* c2 = reinterpret_cast<ulonglong2*>(a.c2 + bt * a.c_bs[2] + (a.c2_compact ? (size_t)j * N : off));
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < (N >> 1); i += gridDim.x * blockDim.x) {
         const ulonglong2 x0 = a0[i], x1 = a1[i], y0 = b0[i], y1 = b1[i];
         ulonglong2 r0, r1, r2;

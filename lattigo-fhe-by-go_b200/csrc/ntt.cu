@@ -246,16 +246,16 @@ struct LimbSetup {
 LG_DEV LimbSetup setup_limb(const NttArgs& a) {
     LimbSetup s;
     const int j = blockIdx.z, b = blockIdx.x;
+    s.tl = a.map(j);
     if (a.skip_alpha > 0) {
-        const int dg = b / a.skip_div, gj = a.skip_limb0 + j;
-        s.skip = (gj < a.skip_nl) && (gj >= dg * a.skip_alpha) && (gj < (dg + 1) * a.skip_alpha);
+        const int dg = b / a.skip_div;
+        s.skip = (s.tl < a.skip_nl) && (s.tl >= dg * a.skip_alpha) && (s.tl < (dg + 1) * a.skip_alpha);
     } else {
         s.skip = (j >= a.skip0 && j < a.skip1);
     }
-    s.tl = a.map(j);
     s.c = load_limb_const(a.T, s.tl);
-    s.in = a.in + (size_t)b * a.in_bstride + (a.bcast.enabled ? 0 : (size_t)j * a.T.N);
-    s.out = a.out + (size_t)b * a.out_bstride + (size_t)j * a.T.N;
+    s.in = a.in + (size_t)b * a.in_bstride + (a.bcast.enabled ? 0 : (size_t)j * (a.in_ls ? a.in_ls : a.T.N));
+    s.out = a.out + (size_t)b * a.out_bstride + (size_t)j * (a.out_ls ? a.out_ls : a.T.N);
     return s;
 }
 
@@ -296,7 +296,7 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
 #pragma unroll
     for (int r = 0; r < 16; ++r) x[r] = in[r * G * 256];
     if (a.bcast.enabled && a.bcast.add != nullptr) {  // ring_scaling.go:99-103: + (q_j - pHalf mod q_j), unreduced
-        const u64 add = __ldg(a.bcast.add + blockIdx.z);
+        const u64 add = __ldg(a.bcast.add + s.tl);
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] += add;
     }
@@ -452,8 +452,8 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
     u64* const buf = smem + sg * 256;
     u64* const twp = smem + 2048 + 2 * t;  // private (w, ws) pairs: slot k at twp[2*k*CONTIG_THREADS]
     u64* const twseg = smem + 2048 + 30 * CONTIG_THREADS + sg * 32;
-    const u64* src = a.in + (size_t)b0 * a.in_bstride + (size_t)j * N + tile0;
-    u64* dst = a.out + (size_t)b0 * a.out_bstride + (size_t)j * N;
+    const u64* src = a.in + (size_t)b0 * a.in_bstride + (size_t)j * (a.in_ls ? a.in_ls : N) + tile0;
+    u64* dst = a.out + (size_t)b0 * a.out_bstride + (size_t)j * (a.out_ls ? a.out_ls : N);
     if (FWD)
         prefetch_warp_tile(tilebuf, src);
     else
@@ -481,9 +481,9 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
                 // the caller's (x - NTT(y)) * s_j tail (+ add) on the canonical transform, straight from the registers
                 const int bi = b0 + i, set = bi >= a.tail.split ? 1 : 0;
                 const size_t bb = (size_t)(bi - (set ? a.tail.split : 0));
-                const u64* ta = a.tail.a[set] + bb * a.tail.a_bs[set] + (size_t)j * N + e0;
-                u64* to = a.tail.out[set] + bb * a.tail.out_bs[set] + (size_t)j * N + e0;
-                const u64 sj = __ldg(a.tail.s + j);
+                const u64* ta = a.tail.a[set] + bb * a.tail.a_bs[set] + (size_t)j * (a.tail.a_ls ? a.tail.a_ls : N) + e0;
+                u64* to = a.tail.out[set] + bb * a.tail.out_bs[set] + (size_t)j * (a.tail.out_ls ? a.tail.out_ls : N) + e0;
+                const u64 sj = __ldg(a.tail.s + tl);
                 const bool add = a.tail.add[set] != 0;
                 const bool canon = a.tail.a_canon != 0;
                 const u64 kq = ((lc.u0 >> 12) + 1) * c.q;  // the first multiple of q above 2^52 (u0 = floor(2^64/q))
@@ -547,13 +547,13 @@ __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttAr
     extern __shared__ __align__(16) u64 ks_smem[];
     const int j = blockIdx.z;
     const int b0 = blockIdx.x * bpc, nb = (batch - b0) < bpc ? (batch - b0) : bpc;
+    const int tl = a.map(j);
     if (a.skip_alpha > 0) {  // digit-batched launch: bpc divides skip_div, so a group never straddles two digits
-        const int dg = b0 / a.skip_div, gj = a.skip_limb0 + j;
-        if (gj < a.skip_nl && gj >= dg * a.skip_alpha && gj < (dg + 1) * a.skip_alpha) return;
+        const int dg = b0 / a.skip_div;
+        if (tl < a.skip_nl && tl >= dg * a.skip_alpha && tl < (dg + 1) * a.skip_alpha) return;
     } else if (j >= a.skip0 && j < a.skip1) {
         return;
     }
-    const int tl = a.map(j);
     const LimbConst lc = load_limb_const(a.T, tl);
     int mode;
     if (FWD) {
@@ -650,7 +650,7 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
     u64* const twseg = smem + 2 * 2048 + 30 * CONTIG_THREADS + sg * 32;  // segment pairs: slot k at twseg[2*k]
 
     const u64* din = a.D + (size_t)b * a.d_bs + (size_t)j * N + tile0;
-    const int own_i = (a.limb0 + j < a.nl) ? (a.limb0 + j) / a.alpha : -1;  // the digit whose own limb this is
+    const int own_i = (tl < a.nl) ? tl / a.alpha : -1;  // the digit whose own limb this is
     if (own_i != 0) prefetch_warp_tile(tilebuf, din);
 
     contig_fill_tw<MODE>(c, N, segbase, cc, twp, twseg);  // twiddles of the tile, once for all digits
@@ -687,7 +687,7 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
 #if KS_KEYPREFETCH == 1
             ks_load_keys(kk0, kk1, key, a.evk_hs);
 #endif
-            const u64* cx = a.cx + (size_t)b * a.cx_bs + (size_t)j * N + e0;
+            const u64* cx = a.cx + (size_t)b * a.cx_bs + (size_t)j * (a.cx_ls ? a.cx_ls : N) + e0;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
                 u64 v[4];
@@ -870,7 +870,7 @@ __global__ void __launch_bounds__(256) range_flags_kernel(const NttArgs a, u32* 
     const int j = blockIdx.z, b = blockIdx.x;
     const u64 twoq = 2 * a.T.q[a.map(j)];
     const u32 half = a.T.N >> 1, lo = blockIdx.y * 2048u, hi = (lo + 2048u < half) ? lo + 2048u : half;
-    const ulonglong2* in = reinterpret_cast<const ulonglong2*>(a.in + (size_t)b * a.in_bstride + (size_t)j * a.T.N);
+    const ulonglong2* in = reinterpret_cast<const ulonglong2*>(a.in + (size_t)b * a.in_bstride + (size_t)j * (a.in_ls ? a.in_ls : a.T.N));
     int bad = 0;
     for (u32 i = lo + threadIdx.x; i < hi; i += 256) {
         const ulonglong2 v = in[i];
@@ -1004,6 +1004,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     NttArgs second = args;  // the second phase runs in place on the output
     second.in = args.out;
     second.in_bstride = args.out_bstride;
+    second.in_ls = args.out_ls;
     second.bcast.enabled = 0;
     if (!inverse) {
         launch_strided_any(L, true, literal, args, sgrid, st);

@@ -180,8 +180,18 @@ SIGNATURES = {
     "lg_comm_destroy": (ci, [vp]),
     "lg_comm_world": (ci, [vp]),
     "lg_comm_rank": (ci, [vp]),
-    "lg_comm_limb_range": (ci, [ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]),
     "lg_comm_aggregate_shares": (ci, [vp, _R, ci, _P, vp]),
+    "lg_comm_limb_owner": (ci, [ci, ci]),
+    "lg_comm_xbuf_words_needed": (C.c_size_t, [u64, ci, ci, ci]),
+    "lg_comm_xbuf_alloc": (ci, [vp, C.c_size_t, C.POINTER(C.c_uint8)]),
+    "lg_comm_xbuf_open": (ci, [vp, ci, C.POINTER(C.c_uint8)]),
+    "lg_comm_xbuf_attach": (ci, [vp, ci, vp]),
+    "lg_comm_xbuf_words": (C.c_size_t, [vp]),
+    "lg_comm_check": (ci, [vp, vp]),
+    "lg_comm_gather_limbs": (ci, [vp, _R, ci, _P, vp]),
+    "lg_ckks_switch_keys_in_place_resident": (ci, [vp, vp, ci, _P, vp, _P, _P, vp]),
+    "lg_ckks_mul_relin_rescale_resident": (ci, [vp, vp, ci, _P, _P, _P, _P, vp, _P, _P, ci, vp]),
+    "lg_ckks_rescale_resident": (ci, [vp, vp, ci, _P, _P, vp]),
     "lg_ckks_switch_keys_in_place_sharded": (ci, [vp, vp, ci, _P, vp, _P, _P, vp]),
     "lg_ckks_mul_relin_sharded": (ci, [vp, vp, ci, _P, _P, _P, _P, vp, _P, _P, vp]),
     "lg_ckks_rescale_sharded": (ci, [vp, vp, ci, _P, _P, vp]),

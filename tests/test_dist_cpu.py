@@ -20,13 +20,12 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # every rank derives the same partition of the 38 data limbs of CKKS PN16 (34 Q + 4 P)
-        mine = ld.limb_range(38, world, rank)
-        all_ranges = [None] * world
-        dist.all_gather_object(all_ranges, mine)
-        assert all_ranges == [ld.limb_range(38, world, r) for r in range(world)]
-        covered = [j for b, e in all_ranges for j in range(b, e)]
-        assert covered == list(range(38))
+        # every rank derives the same (cyclic) partition of the 38 table limbs of CKKS PN16 (34 Q + 4 P)
+        mine = ld.own_limbs(38, world, rank)
+        all_sets = [None] * world
+        dist.all_gather_object(all_sets, mine)
+        assert all_sets == [ld.own_limbs(38, world, r) for r in range(world)]
+        assert sorted(j for s in all_sets for j in s) == list(range(38))
         # batch axis
         blocks = [ld.shard_batch(1024, world, r) for r in range(world)]
         assert blocks[0][0] == 0 and blocks[-1][1] == 1024 and all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
@@ -57,12 +56,17 @@ def test_gloo_world2_host_logic():
 
 
 @pytest.mark.parametrize("n,world", [(38, 8), (38, 3), (5, 8), (34, 1), (12, 4)])
-def test_limb_ranges_partition(n, world):
+def test_limb_ownership_partition(n, world):
+    """cyclic ownership: a partition, balanced within one limb at EVERY level (prefix of the limb list), and stable when
+    the last limb is dropped (a rescale never moves a limb between ranks)"""
     sys.path.insert(0, os.path.join(ROOT, "lattigo-fhe-by-go_b200"))
     from lattigpu import dist as ld
 
-    rs = [ld.limb_range(n, world, r) for r in range(world)]
-    assert rs[0][0] == 0 and rs[-1][1] == n
-    assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
-    sizes = [e - b for b, e in rs]
-    assert max(sizes) - min(sizes) <= 1
+    for nl in range(1, n + 1):
+        sets = [ld.own_limbs(nl, world, r) for r in range(world)]
+        assert sorted(j for s in sets for j in s) == list(range(nl))
+        sizes = [len(s) for s in sets]
+        assert max(sizes) - min(sizes) <= 1
+        if nl > 1:
+            prev = [ld.own_limbs(nl - 1, world, r) for r in range(world)]
+            assert all(set(p) <= set(s) for p, s in zip(prev, sets))

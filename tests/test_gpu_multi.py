@@ -32,9 +32,13 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         comm = lattigpu.dist.Comm()
-        for params in (dict(LogN=13, LogQi=[33, 30, 30, 30, 30, 30], LogPi=[35]),  # PN13QP218
-                       dict(LogN=12, LogQi=[50, 40, 40, 40, 40, 40, 40], LogPi=[50, 50, 50]),
-                       dict(LogN=14, LogQi=[45] + [34] * 9, LogPi=[43, 43])):  # PN14QP438
+        cases = (dict(LogN=13, LogQi=[33, 30, 30, 30, 30, 30], LogPi=[35]),  # PN13QP218
+                 dict(LogN=12, LogQi=[50, 40, 40, 40, 40, 40, 40], LogPi=[50, 50, 50]),
+                 dict(LogN=12, LogQi=[55] + [45] * 33, LogPi=[55] * 4),  # the headline digit shape (alpha 4, beta 9)
+                 dict(LogN=14, LogQi=[45] + [34] * 9, LogPi=[43, 43]))  # PN14QP438
+        # exchange buffers of the limb axis: mapped between the processes with CUDA IPC, sized for the largest case
+        comm.reserve_words(max(comm.words_needed(1 << c["LogN"], len(c["LogQi"]), len(c["LogPi"]), 2) for c in cases))
+        for params in cases:
             N = 1 << params["LogN"]
             Q, P = ckks.GenModuli(params)
             nQ, nP = len(Q), len(P)
@@ -83,6 +87,19 @@ def _worker(rank, world, port, q):
             comm.Rescale(ev, nQ, out)
             if rank == 0 and params["LogN"] == 13:
                 assert np.array_equal(host(out, nQ - 1)[0], w)
+            # limb-resident forms: own limbs after MulRelin + Rescale, then the gathered result
+            ref = (ring.Poly(N, nQ, batch), ring.Poly(N, nQ, batch))
+            ev.MulRelin(nQ - 1, polys(a), polys(b), key, ref)
+            ev.Rescale(nQ, ref)
+            want = host(ref, nQ - 1)
+            out = (ring.Poly(N, nQ, batch), ring.Poly(N, nQ, batch))
+            comm.MulRelinRescale(ev, nQ - 1, polys(a), polys(b), key, out)
+            comm.check()
+            own = lattigpu.dist.own_limbs(nQ - 1, world, rank)
+            assert np.array_equal(host(out, nQ - 1)[:, :, own], want[:, :, own]), ("resident", params["LogN"])
+            comm.GatherLimbs(ev, nQ - 1, out)
+            comm.check()
+            assert np.array_equal(host(out, nQ - 1), want), ("gathered", params["LogN"])
 
             # party axis: every rank holds one party's share over QP
             cQP = ring.NewContextWithParams(N, Q + P)
