@@ -260,6 +260,115 @@ class Evaluator:
         finally:
             lib().lg_hoisted_destroy(h)  # stream-ordered release: after the rotations issued on this stream
 
+    # ---- drivers around permuteNTT / DivRoundByLastModulus*: host logic of the reference, device ops through the ABI
+    def RotateColumns(self, level, ct0, k, evakey, ctOut, stream=None):
+        """RotateColumns (:1201-1248): the key of rotation k when it exists, otherwise the power-of-two decomposition over
+        the left or the right keys, whichever needs fewer rotations; `evakey` is a RotationKeys."""
+        N = self.contextQ.N
+        k &= (N >> 1) - 1  # :1207
+        if k == 0:  # :1209-1211
+            for a, c in zip(ct0, ctOut):
+                self.contextQ.CopyLvl(level, a, c, stream=stream)
+            return
+        if evakey.evakeyRotColLeft.get(k) is not None:  # :1218-1220
+            self.permuteNTT(level, ct0, evakey.permuteNTTLeftIndex[k], evakey.evakeyRotColLeft[k], ctOut, stream=stream)
+            return
+        i, has = 1, True  # :1225-1231
+        while i < (N >> 1):
+            if evakey.evakeyRotColLeft.get(i) is None or evakey.evakeyRotColRight.get(i) is None:
+                has = False
+                break
+            i <<= 1
+        if not has:
+            raise ValueError("cannot RotateColumns: specific rotation and pow2 rotations have not been generated")  # :1245
+        if bin(k).count("1") <= bin((N >> 1) - k).count("1"):  # :1236-1240
+            self.rotateColumnsPow2(level, ct0, k, evakey.permuteNTTLeftIndex, evakey.evakeyRotColLeft, ctOut, stream=stream)
+        else:
+            self.rotateColumnsPow2(level, ct0, (N >> 1) - k, evakey.permuteNTTRightIndex, evakey.evakeyRotColRight, ctOut,
+                                   stream=stream)
+
+    def rotateColumnsPow2(self, level, ct0, k, permuteNTTIndex, evakeyRotCol, ctOut, stream=None):
+        """:1402-1424: copy, then one in-place permuteNTT per set bit of k"""
+        for a, c in zip(ct0, ctOut):
+            self.contextQ.CopyLvl(level, a, c, stream=stream)
+        evakeyIndex = 1
+        while k > 0:
+            if k & 1:
+                self.permuteNTT(level, ctOut, permuteNTTIndex[evakeyIndex], evakeyRotCol[evakeyIndex], ctOut, stream=stream)
+            evakeyIndex <<= 1
+            k >>= 1
+
+    def Conjugate(self, level, ct0, evakey, ctOut, stream=None):
+        """:1437-1450"""
+        if evakey.evakeyConjugate is None:
+            raise ValueError("cannot Conjugate: rows rotation key not generated")
+        self.permuteNTT(level, ct0, evakey.permuteNTTConjugateIndex, evakey.evakeyConjugate, ctOut, stream=stream)
+
+    def RescaleMany(self, nl, ct, nbRescales, stream=None):
+        """RescaleMany (:971-1000): DivRoundByLastModulusManyNTT on every value; the result lives in the first
+        nl - nbRescales limbs.  Returns the factor the scale is divided by."""
+        if nl - 1 < nbRescales:
+            raise ValueError("cannot RescaleMany: input Ciphertext level too low")  # :974
+        div = 1.0
+        for i in range(nbRescales):  # :987-989
+            div *= float(self.contextQ.Modulus[nl - 1 - i])
+        for v in ct:  # :991-993
+            self.contextQ.DivRoundByLastModulusManyNTT(v, nbRescales, nl=nl, stream=stream)
+        return div
+
+    def RescaleThreshold(self, nl, ct, scale, threshold, stream=None):
+        """Rescale (:933-968): divide by the last modulus while scale >= threshold * q_level / 2; returns (scale, nl)"""
+        if nl - 1 == 0:
+            raise ValueError("cannot Rescale: input Ciphertext already at level 0")  # :938
+        q = self.contextQ.Modulus
+        while scale >= (threshold * float(q[nl - 1])) / 2 and nl - 1 != 0:  # :955
+            scale /= float(q[nl - 1])
+            for v in ct:
+                self.contextQ.DivRoundByLastModulusNTT(v, nl=nl, stream=stream)
+            nl -= 1
+        return scale, nl
+
+
+GaloisGen = 5  # ckks/ckks.go:13
+
+
+class RotationKeys:
+    """ckks.RotationKeys (ckks/keygen.go:24-33): switching keys of the column rotations and of the conjugation with the
+    index tables permuteNTT gathers through.  SetRotKey mirrors keygen.go:418-478 (including its right-rotation index
+    exponent 2N-1-k, where GenRot's power-of-two set uses 2N-n, :410)."""
+    RotationLeft, RotationRight, Conjugate = 0, 1, 2
+
+    def __init__(self, N):
+        self.N = N
+        self.evakeyRotColLeft, self.evakeyRotColRight = {}, {}
+        self.permuteNTTLeftIndex, self.permuteNTTRightIndex = {}, {}
+        self.evakeyConjugate, self.permuteNTTConjugateIndex = None, None
+
+    def SetRotKey(self, key, rotType, k=0):
+        from . import ring
+
+        N = self.N
+        if rotType == self.RotationLeft:
+            if self.evakeyRotColLeft.get(k) is None and k != 0:
+                self.permuteNTTLeftIndex[k] = ring.PermuteNTTIndex(GaloisGen, k, N)
+                self.evakeyRotColLeft[k] = key
+        elif rotType == self.RotationRight:
+            if self.evakeyRotColRight.get(k) is None and k != 0:
+                self.permuteNTTRightIndex[k] = ring.PermuteNTTIndex(GaloisGen, 2 * N - 1 - k, N)
+                self.evakeyRotColRight[k] = key
+        else:
+            if self.evakeyConjugate is None:
+                self.permuteNTTConjugateIndex = ring.PermuteNTTIndex(2 * N - 1, 1, N)
+                self.evakeyConjugate = key
+
+    def SetPow2(self, n, left_key, right_key):
+        """one entry of GenRot's power-of-two set (keygen.go:405-413)"""
+        from . import ring
+
+        self.permuteNTTLeftIndex[n] = ring.PermuteNTTIndex(GaloisGen, n, self.N)
+        self.permuteNTTRightIndex[n] = ring.PermuteNTTIndex(GaloisGen, 2 * self.N - n, self.N)
+        self.evakeyRotColLeft[n], self.evakeyRotColRight[n] = left_key, right_key
+
 
 def NewEvaluator(contextQ, contextP):
     return Evaluator(contextQ, contextP)

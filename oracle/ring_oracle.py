@@ -397,6 +397,45 @@ class CkksEvaluator:
         lib().orc_ckks_switch_keys(self.h, level, ptr(ct), ptr(evk), ptr(out))
         return out
 
+    def rotate_columns_pow2(self, level, ct, k, indexes, evks):
+        """rotateColumnsPow2 (ckks/evaluator.go:1402-1424): indexes / evks = maps of the power-of-two rotations"""
+        out = np.ascontiguousarray(ct[:, : level + 1]).copy()
+        i = 1
+        while k > 0:
+            if k & 1:
+                out = self.permute_ntt(level, out, indexes[i], evks[i])
+            i <<= 1
+            k >>= 1
+        return out
+
+    def rotate_columns(self, level, ct, k, left, right):
+        """RotateColumns (ckks/evaluator.go:1201-1248); left / right = {k: (index, evk)} as RotationKeys holds them"""
+        N = self.Q.N
+        k &= (N >> 1) - 1
+        if k == 0:
+            return np.ascontiguousarray(ct[:, : level + 1]).copy()
+        if k in left:
+            return self.permute_ntt(level, ct, left[k][0], left[k][1])
+        i = 1
+        while i < (N >> 1):
+            if i not in left or i not in right:
+                raise ValueError("cannot RotateColumns: specific rotation and pow2 rotations have not been generated")
+            i <<= 1
+        if bin(k).count("1") <= bin((N >> 1) - k).count("1"):
+            return self.rotate_columns_pow2(level, ct, k, {j: v[0] for j, v in left.items()}, {j: v[1] for j, v in left.items()})
+        return self.rotate_columns_pow2(level, ct, (N >> 1) - k, {j: v[0] for j, v in right.items()},
+                                        {j: v[1] for j, v in right.items()})
+
+    def rescale_many(self, ct, nb):
+        """RescaleMany (ckks/evaluator.go:971-1000): DivRoundByLastModulusManyNTT (ring_scaling.go:152-156) per value"""
+        nl = ct.shape[1]
+        outs = []
+        for v in ct:
+            buf = np.ascontiguousarray(v).copy()
+            lib().orc_div_round_by_last_modulus_many_ntt(self.Q.h, nl, ptr(buf), nb)
+            outs.append(buf[: nl - nb].copy())
+        return np.stack(outs)
+
     def rotate_hoisted(self, level, ct, indexes, evks):
         """RotateHoisted (ckks/evaluator.go:1252-1289): one decomposition of ct.value[1] shared by every
         rotation; indexes[k] = permuteNTTLeftIndex, evks[k] = evakeyRotColLeft of rotation k."""

@@ -277,6 +277,65 @@ def test_rotate_conjugate_switchkeys_relinearize(lg, params):
             assert np.array_equal(out[1].numpy(nl=nl, squeeze=False)[i], s.oQ.op3("add", np.ascontiguousarray(a[i, 1, :nl]), k1))
 
 
+@pytest.mark.parametrize("params", [PN12, SMALL3], ids=["PN12", "alpha3"])
+def test_rotate_columns_pow2_conjugate_rescale_many(lg, params):
+    """The drivers around permuteNTT: RotateColumns with a direct key, its power-of-two fallback over the left or the
+    right keys (ckks/evaluator.go:1201-1248, :1402-1424), Conjugate (:1437-1450), RescaleMany (:971-1000) and the
+    threshold loop of Rescale (:933-968).  One (uniform) switching key per rotation, as RotationKeys holds them."""
+    s = Setup(lg, params)
+    rng = np.random.default_rng(41)
+    N, half = s.N, s.N >> 1
+    rk = lg.ckks.RotationKeys(N)
+    left, right = {}, {}
+    n = 1
+    while n < half:  # GenRot's power-of-two set (keygen.go:405-413)
+        kl, kr = s.evk(rng), s.evk(rng)
+        rk.SetPow2(n, lg.ckks.SwitchingKey(kl), lg.ckks.SwitchingKey(kr))
+        left[n] = (orc.permute_ntt_index(5, n, N), kl)
+        right[n] = (orc.permute_ntt_index(5, 2 * N - n, N), kr)
+        n <<= 1
+    kd = s.evk(rng)  # a specific rotation: direct key
+    rk.SetRotKey(lg.ckks.SwitchingKey(kd), rk.RotationLeft, 3)
+    left[3] = (orc.permute_ntt_index(5, 3, N), kd)
+    kc = s.evk(rng)
+    rk.SetRotKey(lg.ckks.SwitchingKey(kc), rk.Conjugate)
+    batch = 2
+    a = s.ct(rng, "reduced", batch)
+    pa = polys(lg, a)
+    level = s.nQ - 1
+    nl = level + 1
+    # k = 3: direct key; 5: two left rotations; half - 1: one right rotation; 0 and half: copy
+    for k in (3, 5, half - 1, half - 3, 0, half, N + 6):
+        out = new_ct(lg, s, batch)
+        s.ev.RotateColumns(level, pa, k, rk, out)
+        for i in range(batch):
+            want = s.oev.rotate_columns(level, np.ascontiguousarray(a[i, :, :nl]), k, left, right)
+            assert np.array_equal(host(out, nl)[i], want), k
+    out = new_ct(lg, s, batch)
+    s.ev.Conjugate(level, pa, rk, out)
+    cidx = orc.permute_ntt_index(2 * N - 1, 1, N)
+    for i in range(batch):
+        assert np.array_equal(host(out, nl)[i], s.oev.permute_ntt(level, np.ascontiguousarray(a[i, :, :nl]), cidx, kc))
+    with pytest.raises(ValueError):  # neither the rotation nor the power-of-two set
+        s.ev.RotateColumns(level, pa, 5, lg.ckks.RotationKeys(N), new_ct(lg, s, batch))
+    if s.nQ >= 3:
+        out = polys(lg, a)
+        div = s.ev.RescaleMany(s.nQ, out, 2)
+        assert div == float(s.Q[-1]) * float(s.Q[-2])
+        for i in range(batch):
+            assert np.array_equal(host(out, s.nQ - 2)[i], s.oev.rescale_many(np.ascontiguousarray(a[i]), 2))
+        with pytest.raises(ValueError):
+            s.ev.RescaleMany(2, out, 2)
+    # Rescale's threshold loop: a scale of about q_top * q_top-1 * 2^10 drops two levels against threshold 2^10
+    out = polys(lg, a)
+    scale0 = float(s.Q[-1]) * float(s.Q[-2]) * 1024.0 if s.nQ >= 3 else float(s.Q[-1]) * 1024.0
+    scale, nl2 = s.ev.RescaleThreshold(s.nQ, out, scale0, 1024.0)
+    drops = s.nQ - nl2
+    assert drops == (2 if s.nQ >= 3 else 1)
+    for i in range(batch):
+        assert np.array_equal(host(out, nl2)[i], s.oev.rescale(np.ascontiguousarray(a[i]), nb=drops))
+
+
 @pytest.mark.parametrize("params", [PN13, SMALL3, PN14], ids=["PN13", "alpha3", "PN14"])
 @pytest.mark.parametrize("kind", ["reduced", "words"])
 def test_rotate_hoisted(lg, params, kind):

@@ -8,7 +8,8 @@ can see it; tests/test_gpu_multi.py runs the same entry points over real peers (
 Checked bit for bit: every rank's own limbs of MulRelin + Rescale (ckks/evaluator.go:1016-1133, :933-968) and of
 switchKeysInPlace (:1475-1558) against the single-GPU evaluator (itself pinned to the oracle), the gathered result,
 and one case directly against the oracle.  Runs in a subprocess with CUDA_DEVICE_MAX_CONNECTIONS=32 so that the ranks'
-streams never share a hardware queue (a rank waiting in a barrier must not hold back another rank's kernels)."""
+streams never share a hardware queue (a rank waiting in a barrier must not hold back another rank's kernels) and with
+eager module loading (a lazy first launch waits for running kernels, i.e. for a barrier whose peer is not issued yet)."""
 import os
 import subprocess
 import sys
@@ -140,5 +141,8 @@ print("ok")
 def test_limb_axis_ranks_in_one_process(world):
     env = dict(os.environ)
     env["CUDA_DEVICE_MAX_CONNECTIONS"] = "32"
+    # a kernel's first launch loads its module, which waits for running kernels: with the ranks in ONE process the host
+    # thread would block behind a rank's barrier kernel before the peer's work is issued (separate processes only stall)
+    env["CUDA_MODULE_LOADING"] = "EAGER"
     res = subprocess.run([sys.executable, "-c", SCRIPT % ROOT, str(world)], env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and res.stdout.strip().endswith("ok"), (res.stdout[-2000:], res.stderr[-4000:])
