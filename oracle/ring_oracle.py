@@ -837,6 +837,96 @@ class BfvEvaluator:
         lib().orc_bfv_permute(self.h, ptr(ct), gen, ptr(evk), ptr(out))
         return out
 
+    # ---- general-degree forms, restated over the oracle's ring ops (bfv/evaluator.go:278-464, :480-507, :578-690) ----
+    def tensor_and_rescale_general(self, ct0, ct1, square=False):
+        """tensorAndRescale for operands of any degree: ct = [deg+1][nQ][N] (a plaintext has one poly); the branch the
+        reference takes when NOT both operands have degree 1 (:374-417), squaring when the operands are the same object"""
+        Q, M = self.Q, self.QMul
+        if not hasattr(self, "_q1q2"):
+            self._q1q2 = Extender(Q, M)
+        bc = self._q1q2
+        levelQ, levelM = Q.nl - 1, M.nl - 1
+        n0, n1 = ct0.shape[0], ct1.shape[0]
+        nout = n0 + n1 - 1
+
+        def extend(ct):  # :299-312
+            q1 = [Q.ntt(np.ascontiguousarray(v)) for v in ct]
+            q2 = [M.ntt(bc.modup_split_qp(levelQ, np.ascontiguousarray(v))) for v in ct]
+            return q1, q2
+
+        c0Q1, c0Q2 = extend(ct0)
+        c1Q1, c1Q2 = (c0Q1, c0Q2) if square else extend(ct1)
+        c2Q1 = [Q.new_poly() for _ in range(nout)]
+        c2Q2 = [M.new_poly() for _ in range(nout)]
+        if square:  # :382-404
+            m1 = [Q.op2("mform_poly", x) for x in c0Q1]
+            m2 = [M.op2("mform_poly", x) for x in c0Q2]
+            for i in range(n0):
+                for j in range(i + 1, n0):
+                    c2Q1[i + j] = Q.op3("mulcoeffs_montgomery", m1[i], c0Q1[j])
+                    c2Q2[i + j] = M.op3("mulcoeffs_montgomery", m2[i], c0Q2[j])
+                    c2Q1[i + j] = Q.op3("add", c2Q1[i + j], c2Q1[i + j])
+                    c2Q2[i + j] = M.op3("add", c2Q2[i + j], c2Q2[i + j])
+            for i in range(n0):
+                Q.op3("mulcoeffs_montgomery_and_add", m1[i], c0Q1[i], c2Q1[i << 1])
+                M.op3("mulcoeffs_montgomery_and_add", m2[i], c0Q2[i], c2Q2[i << 1])
+        else:  # :407-416
+            for i in range(n0):
+                a1, a2 = Q.op2("mform_poly", c0Q1[i]), M.op2("mform_poly", c0Q2[i])
+                for j in range(n1):
+                    Q.op3("mulcoeffs_montgomery_and_add", a1, c1Q1[j], c2Q1[i + j])
+                    M.op3("mulcoeffs_montgomery_and_add", a2, c1Q2[j], c2Q2[i + j])
+        prod = 1
+        for q in M.moduli:
+            prod *= q
+        phalf = prod >> 1
+        pm, pq = arr([phalf % q for q in M.moduli]), arr([phalf % q for q in Q.moduli])
+        out = np.zeros((nout, Q.nl, self.N), dtype=np.uint64)
+        for i in range(nout):  # :424-463
+            x1, x2 = Q.invntt(c2Q1[i]), M.invntt(c2Q2[i])
+            x2 = bc.moddown_splited_qp(levelQ, levelM, x1, x2)
+            lib().orc_add_scalar(M.h, M.nl, ptr(x2), ptr(pm))
+            y = bc.modup_split_pq(levelM, x2)
+            lib().orc_sub_scalar(Q.h, Q.nl, ptr(y), ptr(pq))
+            out[i] = Q.mul_scalar(y, [self.t] * Q.nl)
+        return out
+
+    def relinearize_general(self, ct, evks):
+        """relinearize (:480-500) of a ciphertext of any degree >= 2; evks[deg-2] as EvaluationKey.evakey"""
+        out = np.ascontiguousarray(ct[:2]).copy()
+        for d in range(ct.shape[0] - 1, 1, -1):
+            p0, p1 = self.switch_keys_core(np.ascontiguousarray(ct[d]), evks[d - 2])
+            out[0] = self.Q.op3("add", np.ascontiguousarray(out[0]), p0)
+            out[1] = self.Q.op3("add", np.ascontiguousarray(out[1]), p1)
+        return out
+
+    def rotate_columns(self, ct, k, left, right, galois_gen=5):
+        """RotateColumns (:578-625) with rotateColumnsPow2 (:637-666); left / right = {k: evk}"""
+        N = self.N
+        k &= (N >> 1) - 1
+        if k == 0:
+            return np.ascontiguousarray(ct).copy()
+        if k in left:
+            return self.permute(np.ascontiguousarray(ct), pow(galois_gen, k, 2 * N), left[k])
+        i = 1
+        while i < (N >> 1):
+            if i not in left or i not in right:
+                raise ValueError("cannot RotateColumns: specific rotation and pow2 rotations have not been generated")
+            i <<= 1
+        if bin(k).count("1") <= bin((N >> 1) - k).count("1"):
+            gen, keys = galois_gen, left
+        else:
+            gen, keys, k = pow(galois_gen, 2 * N - 1, 2 * N), right, (N >> 1) - k
+        out = np.ascontiguousarray(ct).copy()
+        mask, idx = (N << 1) - 1, 1
+        while k > 0:
+            if k & 1:
+                out = self.permute(out, gen, keys[idx])
+            gen = (gen * gen) & mask
+            idx <<= 1
+            k >>= 1
+        return out
+
 
 # ---------------------------------------------------------------------------
 # SimpleScaler (ring/ring_scaling.go:166-300, ring/float128.go) and the BFV key generator /

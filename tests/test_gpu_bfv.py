@@ -105,3 +105,80 @@ def test_bfv_keyswitch_relin_rotate(lg, pid, kind):
     s.ev.Relinearize(pc, key, pc[:2])
     for i in range(batch):
         assert np.array_equal(host(pc[:2])[i], s.oev.relinearize(np.ascontiguousarray(c[i]), evk))
+
+
+@pytest.mark.parametrize("pid", [0, 1], ids=["PN12", "PN13"])
+def test_bfv_general_degree_mul_relinearize(lg, pid):
+    """tensorAndRescale for operands that are not both of degree 1 (bfv/evaluator.go:374-417): ciphertext x plaintext,
+    degree 2 x degree 1, squaring of a degree-2 ciphertext; Relinearize of a degree-3 ciphertext with two keys
+    (:480-507, evakey[deg-2])."""
+    s = Setup(lg, pid)
+    rng = np.random.default_rng(61 + pid)
+    batch = 2
+    c1 = s.ct(rng, "reduced", batch, deg=1)
+    c2 = s.ct(rng, "reduced", batch, deg=2)
+    pt = s.ct(rng, "reduced", batch, deg=0)
+    new = lambda n: tuple(lg.ring.Poly(s.N, s.nQ, batch) for _ in range(n))
+    for x, y, square in ((c1, pt, False), (c2, c1, False), (c2, c2, True), (c1, c2, False)):
+        px = polys(lg, x)
+        py = px if square else polys(lg, y)
+        out = new(x.shape[1] + y.shape[1] - 1)
+        s.ev.Mul(px, py, out)
+        got = host(out)
+        for i in range(batch):
+            want = s.oev.tensor_and_rescale_general(np.ascontiguousarray(x[i]), np.ascontiguousarray(y[i]), square)
+            assert np.array_equal(got[i], want), (x.shape, y.shape, square)
+    with pytest.raises(ValueError):
+        s.ev.Mul(polys(lg, c2), polys(lg, c1), new(3))
+    # the general path on two degree-1 operands equals the fused one's oracle (same values, different schedule)
+    g = s.oev.tensor_and_rescale_general(np.ascontiguousarray(c1[0]), np.ascontiguousarray(c1[1]))
+    assert np.array_equal(g, s.oev.tensor_and_rescale(np.ascontiguousarray(c1[0]), np.ascontiguousarray(c1[1])))
+    # Relinearize, degree 3 -> 1 with evakey[1] (degree 3) and evakey[0] (degree 2)
+    c3 = s.ct(rng, "reduced", batch, deg=3)
+    evks = [s.evk(rng), s.evk(rng)]
+    keys = [lg.ckks.SwitchingKey(k) for k in evks]
+    out = new(2)
+    s.ev.Relinearize(polys(lg, c3), keys, out)
+    for i in range(batch):
+        assert np.array_equal(host(out)[i], s.oev.relinearize_general(np.ascontiguousarray(c3[i]), evks))
+    with pytest.raises(ValueError):
+        s.ev.Relinearize(polys(lg, c3), keys[:1], out)
+    # degree 1 in: copy (:521-524)
+    s.ev.Relinearize(polys(lg, c1), keys, out)
+    assert np.array_equal(host(out), c1)
+
+
+def test_bfv_rotate_columns_pow2_rotate_rows(lg):
+    """RotateColumns with a direct key and its power-of-two fallback over the left / right keys (bfv/evaluator.go:578-666),
+    RotateRows (:669-680)."""
+    s = Setup(lg, 0)
+    rng = np.random.default_rng(71)
+    N, half = s.N, s.N >> 1
+    rk = lg.bfv.RotationKeys()
+    left, right = {}, {}
+    n = 1
+    while n < half:
+        kl, kr = s.evk(rng), s.evk(rng)
+        rk.evakeyRotColLeft[n], rk.evakeyRotColRight[n] = lg.ckks.SwitchingKey(kl), lg.ckks.SwitchingKey(kr)
+        left[n], right[n] = kl, kr
+        n <<= 1
+    kd, krow = s.evk(rng), s.evk(rng)
+    rk.evakeyRotColLeft[3] = lg.ckks.SwitchingKey(kd)
+    left[3] = kd
+    rk.evakeyRotRow = lg.ckks.SwitchingKey(krow)
+    batch = 2
+    c = s.ct(rng, "reduced", batch)
+    pc = polys(lg, c)
+    for k in (3, 5, half - 1, half - 3, 0, half + 2):
+        out = (lg.ring.Poly(N, s.nQ, batch), lg.ring.Poly(N, s.nQ, batch))
+        s.ev.RotateColumns(pc, k, rk, out)
+        for i in range(batch):
+            assert np.array_equal(host(out)[i], s.oev.rotate_columns(np.ascontiguousarray(c[i]), k, left, right)), k
+    out = (lg.ring.Poly(N, s.nQ, batch), lg.ring.Poly(N, s.nQ, batch))
+    s.ev.RotateRows(pc, rk, out)
+    for i in range(batch):
+        assert np.array_equal(host(out)[i], s.oev.permute(np.ascontiguousarray(c[i]), 2 * N - 1, krow))
+    with pytest.raises(ValueError):
+        s.ev.RotateColumns(pc, 5, lg.bfv.RotationKeys(), out)
+    with pytest.raises(ValueError):
+        s.ev.RotateRows(pc, lg.bfv.RotationKeys(), out)

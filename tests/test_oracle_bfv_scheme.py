@@ -280,3 +280,22 @@ def test_host_parameter_generators_match_oracle():
             assert lattigpu.lib().lg_bfv_lift_params_host(q.ctypes.data_as(p64), len(Q), t, d.ctypes.data_as(p64)) == 0
             assert [int(x) for x in d] == [((prod(Q) // t) % x << 64) % x for x in Q]
     assert np.array_equal(lattigpu.bfv_scheme.index_matrix(256), orc.bfv_index_matrix(256))
+
+
+def test_general_degree_tensor_matches_degree1_restatement():
+    """The general-degree restatement of tensorAndRescale (bfv/evaluator.go:374-417, composed from the oracle's ring ops)
+    must return the degree-1 x degree-1 restatement's words on degree-1 operands: both branches compute the same
+    canonical products, only the schedule of reductions differs."""
+    logN = 12
+    Q, P, M = orc.gen_moduli(logN, [39, 39], [30], [60, 60])
+    N = 1 << logN
+    ev = orc.BfvEvaluator(orc.Context(N, Q), orc.Context(N, M), orc.Context(N, P), 65537)
+    rng = np.random.default_rng(5)
+    a = np.ascontiguousarray(np.stack([rng.integers(0, q, size=(2, N), dtype=np.uint64) for q in Q], axis=1))
+    b = np.ascontiguousarray(np.stack([rng.integers(0, q, size=(2, N), dtype=np.uint64) for q in Q], axis=1))
+    assert np.array_equal(ev.tensor_and_rescale_general(a, b), ev.tensor_and_rescale(a, b))
+    assert np.array_equal(ev.tensor_and_rescale_general(a, a, True), ev.tensor_and_rescale(a, a))
+    # plaintext x ciphertext: linear in the ciphertext components
+    pt = np.ascontiguousarray(a[:1])
+    out = ev.tensor_and_rescale_general(b, pt)
+    assert out.shape == (2, len(Q), N)
