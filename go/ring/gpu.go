@@ -375,7 +375,7 @@ func (g *GPUContext) MultByMonomial(p1 *GPUPoly, monomialDeg uint64, p2 *GPUPoly
 	must(C.lg_ring_mult_by_monomial(g.h, g.all(), p1.h, C.uint64_t(monomialDeg), p2.h, g.st()))
 }
 
-// MulByVectorMontgomery / ...AndAddNoMod: ring.go:726-745; vector is a one-limb device polynomial
+// MulByVectorMontgomery and MulByVectorMontgomeryAndAddNoMod: ring.go:726-745; vector is a one-limb device polynomial
 func (g *GPUContext) MulByVectorMontgomery(p1 *GPUPoly, vector *GPUPoly, p2 *GPUPoly) {
 	must(C.lg_ring_mul_by_vector_montgomery(g.h, g.all(), p1.h, vector.h, p2.h, g.st()))
 }

@@ -93,3 +93,46 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+C_EXAMPLE = os.path.join(ROOT, "examples", "c", "ring_smoke.c")
+
+
+def _build_c_example(built, out):
+    libdir = os.path.dirname(built)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           C_EXAMPLE, "-L" + libdir, "-llattigpu", "-Wl,-rpath," + libdir, "-o", out])
+
+
+def test_plain_c_program_builds_against_the_header(built, tmp_path):
+    """the boundary is usable from plain C (what cgo sees): the header is C99 -pedantic clean and the example links"""
+    out = str(tmp_path / "ring_smoke")
+    _build_c_example(built, out)
+    import torch
+
+    if not torch.cuda.is_available():  # without a GPU it must fail loudly, not compute on the CPU
+        res = subprocess.run([out], capture_output=True, text=True)
+        assert res.returncode != 0 and "no CUDA device" in res.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_program_runs(built, tmp_path):
+    """NTT round trip, a key switch and an argument check driven from C, no Python in the process"""
+    out = str(tmp_path / "ring_smoke")
+    _build_c_example(built, out)
+    res = subprocess.run([out, "0"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ring_smoke: ok"), (res.stdout, res.stderr)
+
+
+def test_go_shim_calls_only_declared_entry_points():
+    """go/ring/gpu.go and go/ckks/evaluator_gpu.go (complete cgo bindings; no Go toolchain in the image) may only call
+    functions that include/lattigpu.h declares"""
+    from lattigpu import _lib
+
+    declared = set(_lib.header_symbols())
+    for rel in ("go/ring/gpu.go", "go/ckks/evaluator_gpu.go"):
+        src = open(os.path.join(ROOT, rel)).read()
+        # no elisions: "..." may only appear as Go's variadic spread inside append(...)
+        assert not [ln for ln in src.splitlines() if "..." in ln and not re.search(r"append\(.*\.\.\.\)", ln)], rel
+        used = set(re.findall(r"C\.(lg_[a-z0-9_]+)\(", src))
+        assert used and not (used - declared), (rel, sorted(used - declared))
