@@ -71,7 +71,8 @@ uint64_t lg_launch_count(void);
  * parity-tested); they exist for cross-checks and profiling, not for tuning by users.  Each is initialised ONCE per
  * process from the environment variable LATTIGPU_<NAME IN UPPER CASE> (no getenv on any launch path) and can then only
  * be changed through this call.  Names (value 0/1 unless noted): "literal_ntt" (literal Butterfly/InvButterfly of
- * ring/ntt.go:32-50 in every transform), "ks_acc64" (64-bit instead of 96-bit key-switch accumulators),
+ * ring/ntt.go:32-50 in every transform), "no_d64_ntt" (integer instead of FP64-only butterflies for moduli below
+ * 3*2^44), "ks_acc64" (64-bit instead of 96-bit key-switch accumulators),
  * "no_fp_modup" / "no_lazy_modup" / "no_wide_modup" (basis-extension kernel choice), "no_tail_canon" /
  * "no_fused_tail" (ModDown / rescale tail placement), "ks_scratch_words" (value = digit scratch budget of the key
  * switch in 64-bit words, 0 restores the 6 GiB default).  Unknown names return LG_ERR_ARG. */

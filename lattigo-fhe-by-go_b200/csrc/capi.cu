@@ -35,6 +35,7 @@ LgSwitches& lg_switches() {
         };
         sw.literal_ntt = flag("LATTIGPU_LITERAL_NTT", false);
         sw.ks_acc64 = flag("LATTIGPU_KS_ACC64", false);
+        sw.no_d64_ntt = flag("LATTIGPU_NO_D64_NTT", true);
         sw.no_fp_modup = flag("LATTIGPU_NO_FP_MODUP", true);
         sw.no_lazy_modup = flag("LATTIGPU_NO_LAZY_MODUP", true);
         sw.no_wide_modup = flag("LATTIGPU_NO_WIDE_MODUP", true);
@@ -107,6 +108,7 @@ int lg_debug_set_switch(const char* name, uint64_t value) {
     const int v = value ? 1 : 0;
     if (!strcmp(name, "literal_ntt")) sw.literal_ntt = v;
     else if (!strcmp(name, "ks_acc64")) sw.ks_acc64 = v;
+    else if (!strcmp(name, "no_d64_ntt")) sw.no_d64_ntt = v;
     else if (!strcmp(name, "no_fp_modup")) sw.no_fp_modup = v;
     else if (!strcmp(name, "no_lazy_modup")) sw.no_lazy_modup = v;
     else if (!strcmp(name, "no_wide_modup")) sw.no_wide_modup = v;
@@ -179,8 +181,24 @@ int lgi_ring_build_device(lg_ring* r) {
     }
     // twiddles of the fast transforms: psi / psi^-1 / N^-1 out of Montgomery form and their Shoup constants
     // (derived from the reference's tables, so the root choice stays the reference's)
-    auto shoup_tables = [&](const std::vector<u64>& mont, DevArray<u64>& dw, DevArray<u64>& dws, DevArray<u64>* dwd) -> int {
-        std::vector<u64> w(mont.size()), ws(mont.size()), wd(dwd ? mont.size() : 0);
+    // RD(s) * 2^-64 as a double for s = floor(plain * 2^64 / q): never above plain/q, less than 2^-52 below it
+    auto ratio_bits = [](u64 s) {
+        double d = (double)s;
+        if ((unsigned __int128)d > (unsigned __int128)s) d = nextafter(d, 0.0);
+        d = ldexp(d, -64);
+        u64 bits;
+        memcpy(&bits, &d, sizeof(bits));
+        return bits;
+    };
+    auto double_bits = [](u64 v) {  // exact: every table word is below 2^53 where this form is used
+        const double d = (double)v;
+        u64 bits;
+        memcpy(&bits, &d, sizeof(bits));
+        return bits;
+    };
+    auto shoup_tables = [&](const std::vector<u64>& mont, DevArray<u64>& dw, DevArray<u64>& dws, DevArray<u64>& dwd,
+                            DevArray<u64>& dwf) -> int {
+        std::vector<u64> w(mont.size()), ws(mont.size()), wd(mont.size()), wf(mont.size());
         const size_t per = mont.size() / (size_t)r->nl;
         for (int i = 0; i < r->nl; ++i) {
             const u64 qi = r->q[i], qi_inv = r->mred[i];
@@ -189,32 +207,34 @@ int lgi_ring_build_device(lg_ring* r) {
                 w[(size_t)i * per + j] = plain;
                 const u64 s = (u64)((((unsigned __int128)plain) << 64) / qi);
                 ws[(size_t)i * per + j] = s;
-                if (dwd) {  // RD(s) * 2^-64 as a double: never above plain/q, less than 2^-52 below it
-                    double d = (double)s;
-                    if ((unsigned __int128)d > (unsigned __int128)s) d = nextafter(d, 0.0);
-                    d = ldexp(d, -64);
-                    u64 bits;
-                    memcpy(&bits, &d, sizeof(bits));
-                    wd[(size_t)i * per + j] = bits;
-                }
+                wd[(size_t)i * per + j] = ratio_bits(s);
+                wf[(size_t)i * per + j] = double_bits(plain);
             }
         }
         LG_TRY(dw.upload(w));
         LG_TRY(dws.upload(ws));
-        if (dwd) LG_TRY(dwd->upload(wd));
+        LG_TRY(dwd.upload(wd));
+        LG_TRY(dwf.upload(wf));
         return LG_OK;
     };
-    LG_TRY(shoup_tables(r->psi, r->d_psi_w, r->d_psi_ws, &r->d_psi_wd));
-    LG_TRY(shoup_tables(r->psi_inv, r->d_psi_inv_w, r->d_psi_inv_ws, nullptr));
+    LG_TRY(shoup_tables(r->psi, r->d_psi_w, r->d_psi_ws, r->d_psi_wd, r->d_psi_wf));
+    LG_TRY(shoup_tables(r->psi_inv, r->d_psi_inv_w, r->d_psi_inv_ws, r->d_psi_inv_wd, r->d_psi_inv_wf));
     {
-        std::vector<u64> nw(2 * (size_t)r->nl);
+        std::vector<u64> nw(2 * (size_t)r->nl), nf(2 * (size_t)r->nl);
         for (int i = 0; i < r->nl; ++i) {
             const u64 plain = lgh::mred(r->ninv[i], 1, r->q[i], r->mred[i]);
             nw[2 * i] = plain;
             nw[2 * i + 1] = (u64)((((unsigned __int128)plain) << 64) / r->q[i]);
+            nf[2 * i] = double_bits(plain);
+            nf[2 * i + 1] = ratio_bits(nw[2 * i + 1]);
         }
         LG_TRY(r->d_ninv_w.upload(nw));
+        LG_TRY(r->d_ninv_f.upload(nf));
     }
+    r->T.psi_wf = r->d_psi_wf.d;
+    r->T.psi_inv_wf = r->d_psi_inv_wf.d;
+    r->T.psi_inv_wd = r->d_psi_inv_wd.d;
+    r->T.ninv_f = r->d_ninv_f.d;
     r->T.psi_w = r->d_psi_w.d;
     r->T.psi_ws = r->d_psi_ws.d;
     r->T.psi_wd = r->d_psi_wd.d;

@@ -104,6 +104,7 @@ struct lg_ring {
     int nl = 0;
     std::vector<u64> q, bred, mred, ninv, psi, psi_inv, rescale;  // host copies
     DevArray<u64> d_q, d_qinv, d_bred, d_psi, d_psi_inv, d_ninv, d_psi_w, d_psi_ws, d_psi_inv_w, d_psi_inv_ws, d_ninv_w, d_psi_wd;
+    DevArray<u64> d_psi_wf, d_psi_inv_wf, d_psi_inv_wd, d_ninv_f;  // FP64-only transforms
     // rescaleParams[j-1][i] and pHalfNegQi = q_i - ((q_j - 1)/2 mod q_i) (ring_scaling.go:82,:97), both triangular [j(j-1)/2 + i]
     DevArray<u64> d_rescale, d_phalfneg;
     RingTables T;

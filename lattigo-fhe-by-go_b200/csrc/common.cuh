@@ -21,6 +21,11 @@ struct RingTables {
     const u64* psi_inv_w;   // [nl][N]      nttPsiInv out of Montgomery form
     const u64* psi_inv_ws;  // [nl][N]      its Shoup constants (fast inverse NTT)
     const u64* ninv_w;   // [nl][2]         {N^-1 mod q in plain form, its Shoup constant}
+    // FP64-only transforms (moduli below 3*2^44, modarith.cuh): the same twiddles as doubles
+    const u64* psi_wf;      // [nl][N]      bits of (double)psi_w
+    const u64* psi_inv_wf;  // [nl][N]      bits of (double)psi_inv_w
+    const u64* psi_inv_wd;  // [nl][N]      bits of RD(psi_inv_ws) * 2^-64
+    const u64* ninv_f;      // [nl][2]      bits of {(double)ninv, RD(ninv / q)}
     u32 N;
     u32 logN;
     int nl;

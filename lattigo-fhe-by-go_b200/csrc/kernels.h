@@ -11,6 +11,7 @@ extern std::atomic<uint64_t> lg_g_launches;  // kernels launched by this library
 // (std::call_once), then only changed through lg_debug_set_switch -- no getenv on any launch path.  All default to 0.
 struct LgSwitches {
     std::atomic<int> literal_ntt{0};     // LATTIGPU_LITERAL_NTT: literal Butterfly/InvButterfly in every transform
+    std::atomic<int> no_d64_ntt{0};      // LATTIGPU_NO_D64_NTT: integer instead of FP64-only butterflies below 3*2^44
     std::atomic<int> ks_acc64{0};        // LATTIGPU_KS_ACC64: never take the 96-bit key-switch accumulators
     std::atomic<int> no_fp_modup{0};     // LATTIGPU_NO_FP_MODUP: integer-only basis extension
     std::atomic<int> no_lazy_modup{0};   // LATTIGPU_NO_LAZY_MODUP: canonical key-switch digits
@@ -73,6 +74,7 @@ struct NttArgs {
     // inverse only: per (batch, limb) flag, non-zero = some input word is above 2q, use the literal
     // butterflies for that limb (written by lg_launch_range_flags); nullptr = inputs known to be in range
     const u32* flags;
+    int no_d64;                      // set by the launchers from the "no_d64_ntt" switch
     NttTail tail;                    // forward only
     NttBcast bcast;                  // forward only
 };
@@ -101,6 +103,7 @@ struct KsFusedArgs {
     size_t acc_bs;
     int beta, alpha, nl;  // digit i owns the data limbs whose TABLE limb lies in [i*alpha, min((i+1)*alpha, nl))
     int acc64;            // 1 = never take the 96-bit accumulators (LATTIGPU_KS_ACC64=1: A/B and cross-check)
+    int no_d64;           // set by the launcher from the "no_d64_ntt" switch
 };
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st);
 

@@ -236,6 +236,53 @@ LG_DEV void butterfly_inv_f64(u64& X, u64& Y, u64 w, double wd, double cw, u64 n
     Y = shoup_f64(w, wd, cw, d, nq);
 }
 
+// ---- FP64-only butterflies (moduli below 3*2^44) ---------------------------------------------------------------
+// On B200 every pipe these kernels use (integer multiply, integer ALU, FP64) is fed by one dispatch port per SM
+// sub-partition that sustains about one warp instruction every two cycles: throughput follows the INSTRUCTION COUNT,
+// whatever the mix (profiles/r02_fp64_butterfly.txt: the 13-instruction butterfly above runs at 5.48 per clock per SM,
+// the 8-instruction one below at 7.13, any mix of the two in between).  So the shortest exact butterfly wins, and that
+// is one that never touches the integer pipes: values are kept as DOUBLES holding exact signed integers.
+//     h  = RN(w*y),  l = fma(w, y, -h)              the product as an exact two-word sum (an FMA's error term is exact)
+//     qh = RD(y*wd + 1.5*2^52) - 1.5*2^52           wd = RD(w/q) (deficit below 2^-52): qh = floor(y*w/q) + {-1, 0, +1}
+//     t  = fma(-qh, q, h) + l                       both steps exact: |h - qh*q| < 2^48;  t = w*y - qh*q in [-q, 2q)
+// for |y| < 2^51 (the magic-number floor needs |y*wd| < 2^51).  A Cooley-Tukey stage adds at most 2q to the magnitude:
+// 16 stages from an input below 2^49 stay below 2^49 + 32q < 2^51 for q < 3*2^44.  The values a kernel leaves in HBM
+// for the next phase are the raw doubles; integers are converted on the way in (1 LOP3 + 1 DADD) and out.
+#define LG_D64_MAGIC 6755399441055744.0  // 1.5 * 2^52
+LG_DEV double bits2d(u64 b) { return __longlong_as_double((long long)b); }
+LG_DEV u64 d2bits(double d) { return (u64)__double_as_longlong(d); }
+// integer v < 2^52 -> the double v - off, c = 2^52 + off (exactly representable)
+LG_DEV double u52_to_d(u64 v, double c) {
+    return __dadd_rn(__hiloint2double((int)((u32)(v >> 32) | 0x43300000u), (int)(u32)v), -c);
+}
+// double v (an integer) with 0 <= v + off < 2^52 -> the integer v + off, c = 2^52 + off
+LG_DEV u64 d_to_u52(double v, double c) { return d2bits(__dadd_rn(v, c)) & 0x000FFFFFFFFFFFFFull; }
+// w*y - qh*q in [-q, 2q); in [0, 2q) when y >= 0
+LG_DEV double d64_mul(double w, double wd, double y, double q) {
+    const double h = __dmul_rn(w, y);
+    const double l = __fma_rn(w, y, -h);
+    const double qh = __dadd_rn(__fma_rd(y, wd, LG_D64_MAGIC), -LG_D64_MAGIC);
+    return __dadd_rn(__fma_rn(-qh, q, h), l);
+}
+// v - floor~(v/q)*q in [-q, 2q) for |v| < 2^51 (qinvd = RD(1/q)); in [0, 2q) when v >= 0
+LG_DEV double d64_red(double v, double qinvd, double q) {
+    const double c = __dadd_rn(__fma_rd(v, qinvd, LG_D64_MAGIC), -LG_D64_MAGIC);
+    return __fma_rn(-c, q, v);
+}
+// X, Y hold the bit patterns of the doubles
+LG_DEV void butterfly_fwd_d64(u64& X, u64& Y, u64 wb, u64 wdb, double q) {
+    const double t = d64_mul(bits2d(wb), bits2d(wdb), bits2d(Y), q);
+    const double x = bits2d(X);
+    X = d2bits(__dadd_rn(x, t));
+    Y = d2bits(__dadd_rn(x, -t));
+}
+// Gentleman-Sande: the sum path doubles per stage (callers reduce every four stages), the product path ends in [-q, 2q)
+LG_DEV void butterfly_inv_d64(u64& X, u64& Y, u64 wb, u64 wdb, double q) {
+    const double x = bits2d(X), y = bits2d(Y);
+    X = d2bits(__dadd_rn(x, y));
+    Y = d2bits(d64_mul(bits2d(wb), bits2d(wdb), __dadd_rn(x, -y), q));
+}
+
 // InvButterfly, ring/ntt.go:43-50
 LG_DEV void butterfly_inv(u64& U, u64& V, u64 w, u64 q, u64 qinv, u64 twoq) {
     u64 x = U + V;

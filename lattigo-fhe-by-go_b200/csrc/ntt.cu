@@ -34,17 +34,22 @@ namespace {
 
 // butterfly flavours: forward LAZY = values in [0,8q), inverse LAZY = values in [0,4q)
 // forward M_F64 = M_FREE with the quotient taken on the FP64 pipe (moduli below 3*2^44)
-enum { M_LITERAL = 0, M_FREE = 1, M_LAZY = 2, M_F64 = 3 };
+// M_D64 = FP64-only butterflies on doubles (moduli below 3*2^44; modarith.cuh), both directions: the default for those
+// moduli, M_F64 / M_FREE remain behind the "no_d64_ntt" switch
+enum { M_LITERAL = 0, M_FREE = 1, M_LAZY = 2, M_F64 = 3, M_D64 = 4 };
 
-LG_DEV int fwd_mode(u64 q) {
-    return q < (3ull << 44) ? M_F64 : (q < (1ull << 56) ? M_FREE : (q < (1ull << 61) ? M_LAZY : M_LITERAL));
+LG_DEV int fwd_mode(u64 q, int no_d64) {
+    return q < (3ull << 44) ? (no_d64 ? M_F64 : M_D64) : (q < (1ull << 56) ? M_FREE : (q < (1ull << 61) ? M_LAZY : M_LITERAL));
 }
-LG_DEV int inv_mode(u64 q) { return q < (1ull << 46) ? M_FREE : (q < (1ull << 61) ? M_LAZY : M_LITERAL); }
+LG_DEV int inv_mode(u64 q, int no_d64) {
+    return (q < (3ull << 44) && !no_d64) ? M_D64 : (q < (1ull << 46) ? M_FREE : (q < (1ull << 61) ? M_LAZY : M_LITERAL));
+}
 
 struct TwConst {
     u64 q, qinv, twoq, fourq, nq;
-    const u64* tw;   // literal: nttPsi / nttPsiInv (Montgomery).  fast: the plain-domain table
-    const u64* tws;  // fast: Shoup constants (M_F64: the bits of the double table psi_wd)
+    const u64* tw;   // literal: nttPsi / nttPsiInv (Montgomery).  fast: the plain-domain table (M_D64: as doubles)
+    const u64* tws;  // fast: Shoup constants (M_F64, M_D64: the bits of the double table psi_wd / psi_inv_wd)
+    double qd, qinvd, q34;  // M_D64: q, RD(1/q) and 34*q as doubles
 };
 
 // 256-bit global access (sm_100: LDG.E.256 / STG.E.256); p must be 32-byte aligned
@@ -104,6 +109,8 @@ LG_DEV void fwd_stage(u64 (&x)[16], const TwConst& c, u32 twbase) {
                 butterfly_fwd_free(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, c.fourq);
             else if (MODE == M_F64)
                 butterfly_fwd_f64(x[r], x[r + (1 << U)], w[g], wd, cw, c.nq, c.fourq);
+            else if (MODE == M_D64)
+                butterfly_fwd_d64(x[r], x[r + (1 << U)], w[g], ws[g], c.qd);
             else
                 butterfly_fwd_8q(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, c.fourq);
         }
@@ -136,6 +143,8 @@ LG_DEV void inv_stage(u64 (&x)[16], const TwConst& c, u32 twbase, u32 stage) {
                 butterfly_inv(x[r], x[r + (1 << U)], w[g], c.q, c.qinv, c.twoq);
             else if (MODE == M_FREE)
                 butterfly_inv_free(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, m);
+            else if (MODE == M_D64)
+                butterfly_inv_d64(x[r], x[r + (1 << U)], w[g], ws[g], c.qd);
             else
                 butterfly_inv_4q(x[r], x[r + (1 << U)], w[g], ws[g], c.nq, c.fourq);
         }
@@ -175,6 +184,8 @@ LG_DEV void fwd_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp) {
                 butterfly_fwd_free(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
             else if (MODE == M_F64)
                 butterfly_fwd_f64(x[r], x[r + (1 << U)], w, wd, cw, c.nq, c.fourq);
+            else if (MODE == M_D64)
+                butterfly_fwd_d64(x[r], x[r + (1 << U)], w, ws, c.qd);
             else
                 butterfly_fwd_8q(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
         }
@@ -205,6 +216,8 @@ LG_DEV void inv_stage_sm(u64 (&x)[16], const TwConst& c, const u64* wp, u32 stag
                 butterfly_inv(x[r], x[r + (1 << U)], w, c.q, c.qinv, c.twoq);
             else if (MODE == M_FREE)
                 butterfly_inv_free(x[r], x[r + (1 << U)], w, ws, c.nq, m);
+            else if (MODE == M_D64)
+                butterfly_inv_d64(x[r], x[r + (1 << U)], w, ws, c.qd);
             else
                 butterfly_inv_4q(x[r], x[r + (1 << U)], w, ws, c.nq, c.fourq);
         }
@@ -274,11 +287,28 @@ LG_DEV TwConst tw_const(const RingTables& T, const LimbConst& lc, int tl) {
     } else if (MODE == M_F64) {
         c.tw = T.psi_w + off;
         c.tws = T.psi_wd + off;
+    } else if (MODE == M_D64) {
+        c.tw = (FWD ? T.psi_wf : T.psi_inv_wf) + off;
+        c.tws = (FWD ? T.psi_wd : T.psi_inv_wd) + off;
+        c.qd = __ull2double_rn(lc.q);  // exact: q < 2^46
+        c.qinvd = __ddiv_rd(1.0, c.qd);
+        c.q34 = 34.0 * c.qd;           // exact: an integer below 2^52
     } else {
         c.tw = (FWD ? T.psi_w : T.psi_inv_w) + off;
         c.tws = (FWD ? T.psi_ws : T.psi_inv_ws) + off;
     }
     return c;
+}
+
+// M_D64 helpers on the bit patterns held in x[]
+// signed lazy double (|v| < 34q) -> canonical integer
+LG_DEV u64 d64_canon(u64 xb, const TwConst& c) {
+    const double r = d64_red(__dadd_rn(bits2d(xb), c.q34), c.qinvd, c.qd);  // v + 34q >= 0: r in [0, 2q)
+    return cred(d_to_u52(r, 4503599627370496.0), c.q);
+}
+LG_DEV void d64_reduce_all(u64 (&x)[16], const TwConst& c) {  // -> [-q, 2q)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = d2bits(d64_red(bits2d(x[r]), c.qinvd, c.qd));
 }
 
 // ---- forward, strided phase: stages 1..L -----------------------------------
@@ -304,7 +334,8 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
     if (MODE != M_LITERAL) {
         // headroom of the lazy butterflies (canonical inputs never take the slow branch): M_FREE keeps
         // everything below 2^63, M_F64 below 2^50, M_LAZY below 2^(bits(q)+2) <= 8q
-        const u32 sh = MODE == M_FREE ? 63u : (MODE == M_F64 ? 50u : 66u - (u32)__clzll((long long)c.q));
+        // (M_D64: below 2^49, so that 16 stages stay below 2^49 + 32q < 2^51)
+        const u32 sh = MODE == M_FREE ? 63u : (MODE == M_F64 ? 50u : (MODE == M_D64 ? 49u : 66u - (u32)__clzll((long long)c.q)));
         u64 o = 0;
 #pragma unroll
         for (int r = 0; r < 16; ++r) o |= x[r];
@@ -313,6 +344,10 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
             for (int r = 0; r < 16; ++r)
                 if (x[r] >> sh) x[r] = bred_add(x[r], c.q, s.c.u0);
         }
+    }
+    if (MODE == M_D64) {  // integers -> doubles; the phase leaves raw doubles for the contiguous phase
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = d2bits(u52_to_d(x[r], 4503599627370496.0));
     }
     __syncthreads();
     fwd_stages_sm<3, 1, MODE>(x, c, tws_sm);
@@ -343,8 +378,10 @@ __global__ void __launch_bounds__(256, STRIDED_MINB) ntt_fwd_strided(const NttAr
     __shared__ __align__(16) u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
     const LimbSetup s = setup_limb(a);
     if (s.skip) return;
-    const int mode = LITERAL ? M_LITERAL : fwd_mode(s.c.q);
-    if (mode == M_F64)
+    const int mode = LITERAL ? M_LITERAL : fwd_mode(s.c.q, a.no_d64);
+    if (mode == M_D64)
+        fwd_strided_body<L, M_D64>(a, s, sm, tws_sm);
+    else if (mode == M_F64)
         fwd_strided_body<L, M_F64>(a, s, sm, tws_sm);
     else if (mode == M_FREE)
         fwd_strided_body<L, M_FREE>(a, s, sm, tws_sm);
@@ -491,7 +528,15 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
                 for (int h = 0; h < 4; ++h) {
                     u64 va[4], r[4];
                     ld256(va, ta + 4 * h);
-                    if (MODE == M_F64 && canon) {
+                    if (MODE == M_D64 && canon) {
+                        // va < q and |x| < 34q: va + (34q - x) is positive, below 2^52 and congruent
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            r[e] = mred(va[e] + d_to_u52(-bits2d(x[4 * h + e]), 4503599627370496.0 + c.q34), sj, c.q, c.qinv);
+                    } else if (MODE == M_D64) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) r[e] = mred(va[e] + (c.q - d64_canon(x[4 * h + e], c)), sj, c.q, c.qinv);
+                    } else if (MODE == M_F64 && canon) {
                         // va < q and x < 2^52 (FP64 transform): va + (kq - x) is positive, below 2^53 and congruent, so the
                         // one canonical word MRed + CRed returns is the reference's
 #pragma unroll
@@ -512,6 +557,13 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
                 continue;
             }
             // ring/ntt.go:83-85
+            if (MODE == M_D64) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    st256(dst + e0 + 4 * h, d64_canon(x[4 * h], c), d64_canon(x[4 * h + 1], c), d64_canon(x[4 * h + 2], c),
+                          d64_canon(x[4 * h + 3], c));
+                continue;
+            }
 #pragma unroll
             for (int h = 0; h < 4; ++h)
                 st256(dst + e0 + 4 * h, bred_add(x[4 * h], c.q, lc.u0), bred_add(x[4 * h + 1], c.q, lc.u0),
@@ -524,7 +576,12 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
                 x[2 * pp] = v.x;
                 x[2 * pp + 1] = v.y;
             }
+            if (MODE == M_D64) {  // in-range integers (<= 2q) -> doubles
+#pragma unroll
+                for (int r = 0; r < 16; ++r) x[r] = d2bits(u52_to_d(x[r], 4503599627370496.0));
+            }
             inv_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp, 0u);
+            if (MODE == M_D64) d64_reduce_all(x, c);  // sums of 16 inputs -> [-q, 2q) before the next four stages
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < 16; ++r) buf[16 * cc + (r ^ cc)] = x[r];
@@ -557,14 +614,16 @@ __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttAr
     const LimbConst lc = load_limb_const(a.T, tl);
     int mode;
     if (FWD) {
-        mode = LITERAL ? M_LITERAL : fwd_mode(lc.q);
+        mode = LITERAL ? M_LITERAL : fwd_mode(lc.q, a.no_d64);
     } else {
         bool flagged = LITERAL;  // one flagged entry makes the whole group literal (always exact)
         if (a.flags != nullptr)
             for (int i = 0; i < nb; ++i) flagged |= a.flags[(size_t)(b0 + i) * gridDim.z + j] != 0;
-        mode = flagged ? M_LITERAL : inv_mode(lc.q);
+        mode = flagged ? M_LITERAL : inv_mode(lc.q, a.no_d64);
     }
-    if (mode == M_F64)
+    if (mode == M_D64)
+        contig_pipe_body<FWD, M_D64, TAIL>(a, lc, tl, b0, nb, ks_smem);
+    else if (mode == M_F64)
         contig_pipe_body<FWD, FWD ? M_F64 : M_FREE, TAIL>(a, lc, tl, b0, nb, ks_smem);
     else if (mode == M_FREE)
         contig_pipe_body<FWD, M_FREE, TAIL>(a, lc, tl, b0, nb, ks_smem);
@@ -656,8 +715,8 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
     contig_fill_tw<MODE>(c, N, segbase, cc, twp, twseg);  // twiddles of the tile, once for all digits
 
     // floor(2^64/q) is the high Barrett word (modular_reduction.go:97-106); rounded down it is the Shoup double of w = 1
-    const double qd1 = (ACC == ACC_WIDE96) ? __ull2double_rd(lc.u0) * 5.421010862427522170037e-20 : 0.0;
-    const double cq1 = (ACC == ACC_WIDE96) ? shoup_cw(qd1) : 0.0;
+    const double qd1 = (ACC == ACC_WIDE96 && MODE != M_D64) ? __ull2double_rd(lc.u0) * 5.421010862427522170037e-20 : 0.0;
+    const double cq1 = (ACC == ACC_WIDE96 && MODE != M_D64) ? shoup_cw(qd1) : 0.0;
 
     const u64* key = a.evk + (size_t)tl * N + e0;
     u64 acc0[16], acc1[16];
@@ -714,7 +773,17 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
             ks_load_keys(kk0, kk1, key, a.evk_hs);  // in flight during the second register block
 #endif
             fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp);
-            if (ACC == ACC_WIDE96) {
+            if (MODE == M_D64) {  // doubles (|v| < 34q) -> the integers the multiply-accumulate takes
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    if (ACC == ACC_WIDE96)  // [0, 3q)
+                        x[r] = d_to_u52(d64_red(bits2d(x[r]), c.qinvd, c.qd), 4503599627370496.0 + c.qd);
+                    else if (ACC == ACC_LAZY64)  // (0, 68q), congruent
+                        x[r] = d_to_u52(bits2d(x[r]), 4503599627370496.0 + c.q34);
+                    else
+                        x[r] = d64_canon(x[r], c);
+                }
+            } else if (ACC == ACC_WIDE96) {
 #pragma unroll
                 for (int r = 0; r < 16; ++r) x[r] = reduce_f64(x[r], qd1, cq1, c.nq);
             } else if (ACC == ACC_EXACT) {
@@ -770,7 +839,7 @@ __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const
     extern __shared__ __align__(16) u64 ks_smem[];
     const int tl = a.map(blockIdx.z);
     const LimbConst lc = load_limb_const(a.T, tl);
-    const int mode = LITERAL ? M_LITERAL : fwd_mode(lc.q);
+    const int mode = LITERAL ? M_LITERAL : fwd_mode(lc.q, a.no_d64);
     // beta lazy terms below 2q fit 64 bits (a term is below 2q when the key word has at most bits(q) bits: its product
     // with a transform value below 2^63 (M_FREE), 8q (M_LAZY) or 2^52 (M_F64) then has a high word below q)
     const bool lazyacc = (2 * lc.q) <= (~0ull) / (u64)a.beta;
@@ -778,7 +847,14 @@ __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const
     // are watched -- below 2^32 a key word is harmless for any q)
     const int qbits = 64 - __clzll((long long)lc.q), kb = qbits < 32 ? 32 : qbits;
     u32 keyhi = 0;
-    if (mode == M_F64) {
+    if (mode == M_D64) {
+        const int sh = 96 - kb;
+        if (!a.acc64 && (sh >= 64 || ((3ull * (u64)a.beta * lc.q) >> sh) == 0))
+            keyhi = ks_fused_body<M_D64, ACC_WIDE96>(a, lc, tl, ks_smem);
+        else
+            keyhi = ks_fused_body<M_D64, ACC_LAZY64>(a, lc, tl, ks_smem);
+        if (__syncthreads_or((keyhi >> (kb - 32)) != 0)) ks_fused_body<M_D64, ACC_EXACT>(a, lc, tl, ks_smem);
+    } else if (mode == M_F64) {
         // beta products of a key word below 2^kb and a digit value below 3q fit 96 bits
         const int sh = 96 - kb;  // 50..64; a shift by 64 is not defined in C++: every product fits then
         if (!a.acc64 && (sh >= 64 || ((3ull * (u64)a.beta * lc.q) >> sh) == 0))
@@ -826,9 +902,11 @@ LG_DEV void inv_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
     }
     fill_strided_tw<L, MODE == M_LITERAL>(tws_sm, c);
     __syncthreads();
+    if (MODE == M_D64) d64_reduce_all(x, c);  // the contiguous phase left sums of 16 values: -> [-q, 2q)
     if (N2 > 0) {
         const u64* twg = tws_sm + (1 + g) * 32;
         inv_stages_sm<(N2 > 0 ? N2 - 1 : 0), 1, MODE>(x, c, twg, 8u);
+        if (MODE == M_D64) d64_reduce_all(x, c);
 #pragma unroll
         for (int r = 0; r < 16; ++r) sm[(16 * g + r) * W + col] = x[r];
         __syncthreads();
@@ -842,6 +920,15 @@ LG_DEV void inv_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
         const u64 ninv = a.T.ninv[s.tl];
 #pragma unroll
         for (int r = 0; r < 16; ++r) out[r * G * 256] = mred(x[r], ninv, c.q, c.qinv);
+    } else if (MODE == M_D64) {
+        // |v| <= 32q: reduced to [-q, 2q) and shifted to [0, 3q) (the multiplication needs |y| < 2^51 and, for a
+        // result in [0, 2q), y >= 0); the product with N^-1 then lands in [0, 2q)
+        const double nf = bits2d(a.T.ninv_f[2 * s.tl]), nd = bits2d(a.T.ninv_f[2 * s.tl + 1]);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const double y = __dadd_rn(d64_red(bits2d(x[r]), c.qinvd, c.qd), c.qd);
+            out[r * G * 256] = cred(d_to_u52(d64_mul(nf, nd, y, c.qd), 4503599627370496.0), c.q);
+        }
     } else {
         const u64 nw = a.T.ninv_w[2 * s.tl], nws = a.T.ninv_w[2 * s.tl + 1];
 #pragma unroll
@@ -855,8 +942,10 @@ __global__ void __launch_bounds__(256, STRIDED_MINB) ntt_inv_strided(const NttAr
     __shared__ __align__(16) u64 tws_sm[32 * ((1 << (L - 4)) + 1)];
     const LimbSetup s = setup_limb(a);
     if (s.skip) return;
-    const int mode = (LITERAL || inv_flagged(a)) ? M_LITERAL : inv_mode(s.c.q);
-    if (mode == M_FREE)
+    const int mode = (LITERAL || inv_flagged(a)) ? M_LITERAL : inv_mode(s.c.q, a.no_d64);
+    if (mode == M_D64)
+        inv_strided_body<L, M_D64>(a, s, sm, tws_sm);
+    else if (mode == M_FREE)
         inv_strided_body<L, M_FREE>(a, s, sm, tws_sm);
     else if (mode == M_LAZY)
         inv_strided_body<L, M_LAZY>(a, s, sm, tws_sm);
@@ -1001,16 +1090,18 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     const int L = (int)logN - 8;
     const bool literal = literal_ntt();
     const dim3 sgrid(batch, N / 4096, nlimbs);
-    NttArgs second = args;  // the second phase runs in place on the output
+    NttArgs first = args;
+    first.no_d64 = lg_switches().no_d64_ntt.load(std::memory_order_relaxed) ? 1 : 0;
+    NttArgs second = first;  // the second phase runs in place on the output
     second.in = args.out;
     second.in_bstride = args.out_bstride;
     second.in_ls = args.out_ls;
     second.bcast.enabled = 0;
     if (!inverse) {
-        launch_strided_any(L, true, literal, args, sgrid, st);
+        launch_strided_any(L, true, literal, first, sgrid, st);
         launch_contig_pipe(true, literal, second, nlimbs, batch, st);
     } else {
-        launch_contig_pipe(false, literal, args, nlimbs, batch, st);
+        launch_contig_pipe(false, literal, first, nlimbs, batch, st);
         launch_strided_any(L, false, literal, second, sgrid, st);
     }
     lg_g_launches += 2;
@@ -1021,7 +1112,9 @@ int lg_launch_ntt_fwd_strided(const NttArgs& args, int nlimbs, int batch, cudaSt
     if (nlimbs <= 0 || batch <= 0) return 0;
     const u32 logN = args.T.logN, N = args.T.N;
     if (logN < 12 || logN > 16) return 1;
-    launch_strided_any((int)logN - 8, true, literal_ntt(), args, dim3(batch, N / 4096, nlimbs), st);
+    NttArgs first = args;
+    first.no_d64 = lg_switches().no_d64_ntt.load(std::memory_order_relaxed) ? 1 : 0;
+    launch_strided_any((int)logN - 8, true, literal_ntt(), first, dim3(batch, N / 4096, nlimbs), st);
     lg_g_launches += 1;
     return 0;
 }
@@ -1041,6 +1134,7 @@ int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t
     const size_t smem = KS_SMEM_WORDS * sizeof(u64);
     KsFusedArgs k = a;
     k.acc64 = lg_switches().ks_acc64.load(std::memory_order_relaxed) ? 1 : 0;
+    k.no_d64 = lg_switches().no_d64_ntt.load(std::memory_order_relaxed) ? 1 : 0;
     if (literal_ntt()) {
         lg_ensure_dyn_smem<ks_fused_kernel<true>>(smem);
         ks_fused_kernel<true><<<grid, CONTIG_THREADS, smem, st>>>(k);

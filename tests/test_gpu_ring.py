@@ -459,6 +459,80 @@ def test_ntt_zero_and_sparse_inputs(lg, logN):
         assert np.array_equal(got[b], octx.invntt(np.ascontiguousarray(a[b]))), ("inv", b)
 
 
+def _prime_below(bound, two_n):
+    """largest NTT-friendly prime below `bound` (p = 1 mod 2N)"""
+    def is_prime(n):
+        if n < 2:
+            return False
+        for sp in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+            if n % sp == 0:
+                return n == sp
+        d, r = n - 1, 0
+        while d % 2 == 0:
+            d //= 2
+            r += 1
+        for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+            x = pow(a, d, n)
+            if x in (1, n - 1):
+                continue
+            for _ in range(r - 1):
+                x = x * x % n
+                if x == n - 1:
+                    break
+            else:
+                return False
+        return True
+
+    p = (bound - 1) // two_n * two_n + 1
+    while not is_prime(p):
+        p -= two_n
+    return p
+
+
+@pytest.mark.parametrize("logN", [12, 13, 14, 15, 16])
+@pytest.mark.parametrize("no_d64", [0, 1], ids=["d64", "int"])
+def test_ntt_parity_fp64_butterfly_moduli(lg, logN, no_d64):
+    """Moduli below 3*2^44 take the FP64-only butterflies (values kept as doubles, modarith.cuh) in both directions, or the
+    integer ones behind the "no_d64_ntt" switch.  Both must match the oracle on: uniform residues, arbitrary 64-bit words,
+    and the inputs that drive the lazy values to their extremes (all q-1; alternating 0 / q-1; all 2q for the inverse).
+    The largest admissible prime (just below 3*2^44) and its neighbour above (integer path) are included."""
+    N = 1 << logN
+    edge = _prime_below(3 << 44, 2 * N)
+    above = _prime_below((3 << 44) + (1 << 40), 2 * N)
+    assert edge < (3 << 44) <= above
+    moduli = orc.generate_ntt_primes(30, logN, 1) + orc.generate_ntt_primes(45, logN, 2) + [edge, above]
+    octx = orc.Context(N, moduli)
+    ctx = lg.ring.NewContextWithParams(N, moduli)
+    rng = np.random.default_rng(300 + logN)
+    nl = len(moduli)
+    a = np.zeros((5, nl, N), dtype=np.uint64)
+    for i, q in enumerate(moduli):
+        a[0, i] = rng.integers(0, q, size=N, dtype=np.uint64)
+        a[2, i] = q - 1
+        a[3, i, ::2] = q - 1
+        a[4, i] = 2 * q  # the inverse's in-range limit (values <= 2q)
+    a[1] = rng.integers(0, 1 << 64, size=(nl, N), dtype=np.uint64)
+    try:
+        lg.ring.debug_set_switch("no_d64_ntt", no_d64)
+        p = lg.ring.Poly.from_numpy(a)
+        out = lg.ring.Poly(N, nl, 5)
+        ctx.NTT(p, out)
+        got = out.numpy(squeeze=False)
+        for b in range(5):
+            assert np.array_equal(got[b], octx.ntt(np.ascontiguousarray(a[b]))), ("fwd", b)
+        ctx.InvNTT(p, out)
+        got = out.numpy(squeeze=False)
+        for b in range(5):
+            want = octx.invntt(np.ascontiguousarray(a[b]))
+            bad = [i for i in range(nl) if not np.array_equal(got[b, i], want[i])]
+            assert not bad, ("inv", b, bad, [int(v) for v in got[b, bad[0]][:4]], [int(v) for v in want[bad[0]][:4]], moduli[bad[0]])
+        ctx.InvNTT(out, out)  # in place on canonical data
+        ctx.NTT(out, out)
+        assert np.array_equal(out.numpy(squeeze=False), got)
+    finally:
+        lg.ring.debug_set_switch("no_d64_ntt", 0)
+
+
 @pytest.mark.parametrize("src", [[45] * 4, [45] * 3, [34, 34], [45], [46] * 3, [55] * 4, [55, 45, 45, 45], [55, 55], [49] * 3, [56]],
                          ids=["4x45", "3x45", "2x34", "1x45", "3x46", "4x55", "55+3x45", "2x55", "3x49", "1x56"])
 @pytest.mark.parametrize("dst_bits", [[60, 60, 55, 45, 34], [36, 59], [55, 45, 45, 34]], ids=["wide", "narrow", "ckks"])
