@@ -733,10 +733,135 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_config(args):
+    """bench.py --config C1|C2|C3|C5: the same JSON contract on another BASELINE.json configuration (bench_configs.py)"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import bench_configs
+    import lattigpu
+    from lattigpu import ring as gring
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    gring.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    builder, cid = bench_configs.CONFIGS[args.config]
+    cfg = builder(lattigpu, dev, 0x1A771C0 + cid + rank, hbm_peak, peak_src)
+    st = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = gring.launch_count()
+        e0.record(st)
+        for _ in range(steps):
+            fn()
+        e1.record(st)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = gring.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, launches = timed(cfg["step"], args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms / args.steps
+    units = cfg["units_per_step"]
+    value = world * units * 1e3 / ms_per_step
+    extra = {}
+    for name, fn in cfg.get("extra", {}).items():
+        ems, _ = timed(fn, args.steps, 3)
+        extra[name] = {"value": world * units * args.steps * 1e3 / ems, "unit": cfg.get("extra_unit", cfg["unit"])}
+
+    # e2e: inputs from pinned host memory, results back to pinned host memory, inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        ins, outs = cfg["e2e"]
+        h_in = [torch.empty(n, dtype=torch.int64).pin_memory() for _, n in ins]
+        h_out = [torch.empty(n, dtype=torch.int64).pin_memory() for _, n in outs]
+        for h, (t, n) in zip(h_in, ins):
+            h.copy_(t.reshape(-1)[:n])
+
+        def e2e_step():
+            for h, (t, n) in zip(h_in, ins):
+                t.reshape(-1)[:n].copy_(h, non_blocking=True)
+            cfg["step"]()
+            for h, (t, n) in zip(h_out, outs):
+                h.copy_(t.reshape(-1)[:n], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        nsteps = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * units * nsteps / dt, "unit": cfg["unit"], "h2d_bytes_per_step": 8 * sum(n for _, n in ins),
+               "d2h_bytes_per_step": 8 * sum(n for _, n in outs), "ms_per_step": 1e3 * dt / nsteps,
+               "note": "pinned host buffers -> device, the step through the C ABI, results -> pinned host buffers; host sync per step"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, sample = cfg["cpu"](cores)
+        cpu = {"value": v, "unit": cfg["unit"], "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": {"workload": cfg["workload"], "baseline_config": args.config, "units_per_gpu_per_step": units,
+                       "l2_policy": "inputs larger than L2, no flush", "parallelism": "batch-sharded x%d, no collective" % world},
+            "also": extra, "roofline": cfg["roofline"](1e3 * ms_per_step), "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "C4":
+        run_config(args)
     else:
         run_gpu(args)
 

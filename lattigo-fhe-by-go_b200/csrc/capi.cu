@@ -42,6 +42,7 @@ LgSwitches& lg_switches() {
         sw.no_tail_canon = flag("LATTIGPU_NO_TAIL_CANON", true);
         sw.no_fused_tail = flag("LATTIGPU_NO_FUSED_TAIL", true);
         if (const char* e = getenv("LATTIGPU_KS_SCRATCH_WORDS")) sw.ks_scratch_words = strtoull(e, nullptr, 10);
+        if (const char* e = getenv("LATTIGPU_NTT_L2_BYTES")) sw.ntt_l2_bytes = strtoull(e, nullptr, 10);
     });
     return sw;
 }
@@ -115,6 +116,7 @@ int lg_debug_set_switch(const char* name, uint64_t value) {
     else if (!strcmp(name, "no_tail_canon")) sw.no_tail_canon = v;
     else if (!strcmp(name, "no_fused_tail")) sw.no_fused_tail = v;
     else if (!strcmp(name, "ks_scratch_words")) sw.ks_scratch_words = value ? value : ((uint64_t)6 << 27);
+    else if (!strcmp(name, "ntt_l2_bytes")) sw.ntt_l2_bytes = value;
     else {
         lg_set_error("lg_debug_set_switch: unknown switch '%s'", name);
         return LG_ERR_ARG;

@@ -19,6 +19,11 @@ struct LgSwitches {
     std::atomic<int> no_tail_canon{0};   // LATTIGPU_NO_TAIL_CANON: reduce the transform before the ModDown tail
     std::atomic<int> no_fused_tail{0};   // LATTIGPU_NO_FUSED_TAIL: separate ModDown / rescale tail kernels
     std::atomic<uint64_t> ks_scratch_words{(uint64_t)6 << 27};  // LATTIGPU_KS_SCRATCH_WORDS: digit scratch budget (words)
+    // LATTIGPU_NTT_L2_BYTES: a two-phase transform runs over groups of batch entries whose intermediate (the first phase's
+    // output) would stay in L2 until the second phase reads it; 0 (default) = one launch pair over the whole batch.
+    // Measured (profiles/r02_ntt_l2_sweep.jsonl): the small grids cost more than the saved HBM pass -- 456 us for
+    // 1088 limb-NTTs unsplit against 608 us at 96 MiB and 1040 us at 12..32 MiB.
+    std::atomic<uint64_t> ntt_l2_bytes{0};
 };
 LgSwitches& lg_switches();
 
@@ -75,6 +80,7 @@ struct NttArgs {
     // butterflies for that limb (written by lg_launch_range_flags); nullptr = inputs known to be in range
     const u32* flags;
     int no_d64;                      // set by the launchers from the "no_d64_ntt" switch
+    int batch0;                      // index of the launch's first batch entry in the caller's batch (tail addressing)
     NttTail tail;                    // forward only
     NttBcast bcast;                  // forward only
 };

@@ -516,7 +516,7 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
             fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp);
             if (TAIL) {
                 // the caller's (x - NTT(y)) * s_j tail (+ add) on the canonical transform, straight from the registers
-                const int bi = b0 + i, set = bi >= a.tail.split ? 1 : 0;
+                const int bi = a.batch0 + b0 + i, set = bi >= a.tail.split ? 1 : 0;
                 const size_t bb = (size_t)(bi - (set ? a.tail.split : 0));
                 const u64* ta = a.tail.a[set] + bb * a.tail.a_bs[set] + (size_t)j * (a.tail.a_ls ? a.tail.a_ls : N) + e0;
                 u64* to = a.tail.out[set] + bb * a.tail.out_bs[set] + (size_t)j * (a.tail.out_ls ? a.tail.out_ls : N) + e0;
@@ -1090,21 +1090,40 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
     const int L = (int)logN - 8;
     const bool literal = literal_ntt();
     const dim3 sgrid(batch, N / 4096, nlimbs);
-    NttArgs first = args;
-    first.no_d64 = lg_switches().no_d64_ntt.load(std::memory_order_relaxed) ? 1 : 0;
-    NttArgs second = first;  // the second phase runs in place on the output
-    second.in = args.out;
-    second.in_bstride = args.out_bstride;
-    second.in_ls = args.out_ls;
-    second.bcast.enabled = 0;
-    if (!inverse) {
-        launch_strided_any(L, true, literal, first, sgrid, st);
-        launch_contig_pipe(true, literal, second, nlimbs, batch, st);
-    } else {
-        launch_contig_pipe(false, literal, first, nlimbs, batch, st);
-        launch_strided_any(L, false, literal, second, sgrid, st);
+    // Groups of batch entries whose first-phase output fits the L2 budget: the second phase then reads it from L2
+    // instead of HBM (the transform is bandwidth-bound once the butterflies run on the FP64 pipe).
+    int cb = batch;
+    const size_t l2_bytes = (size_t)lg_switches().ntt_l2_bytes.load(std::memory_order_relaxed);
+    if (l2_bytes && args.skip_alpha == 0) {
+        const size_t per = (size_t)nlimbs * N * sizeof(u64);
+        cb = (int)(l2_bytes / per);
+        if (cb < 1) cb = 1;
+        if (cb > batch) cb = batch;
     }
-    lg_g_launches += 2;
+    (void)sgrid;
+    for (int g0 = 0; g0 < batch; g0 += cb) {
+        const int nb = (batch - g0) < cb ? (batch - g0) : cb;
+        NttArgs first = args;
+        first.no_d64 = lg_switches().no_d64_ntt.load(std::memory_order_relaxed) ? 1 : 0;
+        first.in = args.in + (size_t)g0 * args.in_bstride;
+        first.out = args.out + (size_t)g0 * args.out_bstride;
+        first.batch0 = g0;
+        if (args.flags) first.flags = args.flags + (size_t)g0 * nlimbs;
+        NttArgs second = first;  // the second phase runs in place on the output
+        second.in = first.out;
+        second.in_bstride = args.out_bstride;
+        second.in_ls = args.out_ls;
+        second.bcast.enabled = 0;
+        const dim3 grid(nb, N / 4096, nlimbs);
+        if (!inverse) {
+            launch_strided_any(L, true, literal, first, grid, st);
+            launch_contig_pipe(true, literal, second, nlimbs, nb, st);
+        } else {
+            launch_contig_pipe(false, literal, first, nlimbs, nb, st);
+            launch_strided_any(L, false, literal, second, grid, st);
+        }
+        lg_g_launches += 2;
+    }
     return 0;
 }
 

@@ -8,11 +8,16 @@ COLS = [("gpu__time_duration.sum", "us", 1.0), ("dram__bytes_read.sum", "rdMB", 
         ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%", 1.0),
         ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%", 1.0),
         ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%", 1.0),
+        ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64%", 1.0),
+        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%", 1.0),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "shortsb", 1.0),
+        ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "dispat", 1.0),
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "barrier", 1.0),
         ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "longsb", 1.0),
         ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "mathpt", 1.0),
         ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "wait", 1.0),
         ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "notsel", 1.0),
-        ("sm__inst_executed.sum", "Minst", 1e-6)]
+        ("smsp__inst_executed.sum", "Minst", 1e-6)]
 
 
 def main(path):
