@@ -73,10 +73,11 @@ uint64_t lg_launch_count(void);
  * be changed through this call.  Names (value 0/1 unless noted): "literal_ntt" (literal Butterfly/InvButterfly of
  * ring/ntt.go:32-50 in every transform), "no_d64_ntt" (integer instead of FP64-only butterflies for moduli below
  * 3*2^44), "ks_acc64" (64-bit instead of 96-bit key-switch accumulators),
- * "no_fp_modup" / "no_lazy_modup" / "no_wide_modup" (basis-extension kernel choice), "no_tail_canon" /
+ * "no_fp_modup" / "no_lazy_modup" / "no_wide_modup" / "modup_cpt2" (basis-extension kernel choice), "no_tail_canon" /
  * "no_fused_tail" (ModDown / rescale tail placement), "ks_scratch_words" (value = digit scratch budget of the key
  * switch in 64-bit words, 0 restores the 6 GiB default), "ntt_l2_bytes" (value = bytes of first-phase output a group of
- * batch entries of a two-phase NTT may hold, 0 = default: no grouping).  Unknown names return LG_ERR_ARG. */
+ * batch entries of a two-phase NTT may hold, 0 = default: no grouping), "reverse_walk" (second NTT phases walk their
+ * grid backwards; default off).  Unknown names return LG_ERR_ARG. */
 int lg_debug_set_switch(const char* name, uint64_t value);
 
 /* ---- ring.Context -------------------------------------------------------- */

@@ -288,11 +288,15 @@ __global__ void __launch_bounds__(128) modup_wide_kernel(const ModUpArgs a) {
 // column sums and the Montgomery reduction of modup_fast_kernel.
 // LAZY: the result is left in [0, 2p) (no conditional subtraction) -- for the key-switch digits, whose only reader
 // is the forward NTT (exact for any input below its headroom).
-template <int NSRC, bool LAZY>
+// CPT coefficients per thread (256-bit access for CPT = 4): the per-target constants (interleaved so that one 128-bit
+// shared-memory load brings a (C, Cd) or (K', Kd) pair) and the loop overhead are paid once per CPT coefficients --
+// throughput follows the instruction count (profiles/r02_fp64_butterfly.txt): 29 instead of 41 per target coefficient.
+template <int NSRC, bool LAZY, int CPT>
 __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
-    constexpr int ROW = 4 * NSRC + 5;  // np, p, 1/p, C[NSRC], Cd[NSRC], K'[NSRC+1], Kd[NSRC+1]
-    constexpr int O_C = 3, O_CD = 3 + NSRC, O_K = 3 + 2 * NSRC, O_KD = 4 + 3 * NSRC;
-    __shared__ u64 tab[LG_MAX_LIMBS * ROW];
+    // row: {np, p}, {1/p, -}, {C_i, Cd_i} x NSRC, {K'_v, Kd_v} x (NSRC+1)
+    constexpr int ROW = 4 + 2 * NSRC + 2 * (NSRC + 1);
+    constexpr int O_C = 4, O_K = 4 + 2 * NSRC;
+    __shared__ __align__(16) u64 tab[LG_MAX_LIMBS * ROW];
     const ModUpTables& M = a.M;
     int ntg = 0;
     for (int k = 0; k < a.nruns; ++k) ntg += a.ndst[k];
@@ -310,48 +314,61 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
         row[0] = 0 - p;
         row[1] = p;
         row[2] = (u64)__double_as_longlong(__ddiv_rd(1.0, __ull2double_ru(p)));
+        row[3] = 0;
 #pragma unroll
         for (int i = 0; i < NSRC; ++i) {
             const u64 c = mred(M.qispj[(size_t)i * M.dst_total + tg], 1, p, pinv);  // out of Montgomery form
-            row[O_C + i] = c;
-            row[O_CD + i] = (u64)__double_as_longlong(__ull2double_rd(c));
+            row[O_C + 2 * i] = c;
+            row[O_C + 2 * i + 1] = (u64)__double_as_longlong(__ull2double_rd(c));
         }
 #pragma unroll
         for (int v = 0; v <= NSRC; ++v) {
             const u64 kv = M.qpjinv[(size_t)tg * (M.src_total + 1) + v];
-            row[O_K + v] = kv + 0x4330000000000000ull * p;  // + bits(2^52) * p: cancels the exponent field of t
-            row[O_KD + v] = (u64)__double_as_longlong(__ull2double_rd(kv));
+            row[O_K + 2 * v] = kv + 0x4330000000000000ull * p;  // + bits(2^52) * p: cancels the exponent field of t
+            row[O_K + 2 * v + 1] = (u64)__double_as_longlong(__ull2double_rd(kv));
         }
     }
     __syncthreads();
-    const u32 x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const u32 x = CPT * (blockIdx.x * blockDim.x + threadIdx.x);
     const int bt = blockIdx.y;
     if (x >= a.N) return;
-    u32 y0[NSRC][2], y1[NSRC][2];
-    double yd[NSRC][2];
-    u32 v[2];
+    u32 y0[NSRC][CPT], y1[NSRC][CPT];
+    double yd[NSRC][CPT];
+    u32 v[CPT];
     {
-        double vi0 = 0.0, vi1 = 0.0;
+        double vi[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) vi[e] = 0.0;
         const u64* in = a.in + bt * a.in_bs + x;
 #pragma unroll
         for (int i = 0; i < NSRC; ++i) {
             const u64* srcp = a.src[0] ? a.src[i] + bt * a.in_bs + x : in + (size_t)i * a.N;
-            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(srcp);
-            if (a.copy_out) *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x) = val;
+            u64 val[CPT];
+#pragma unroll
+            for (int h = 0; h < CPT / 2; ++h) {
+                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(srcp + 2 * h);
+                val[2 * h] = t.x;
+                val[2 * h + 1] = t.y;
+            }
+            if (a.copy_out) {
+#pragma unroll
+                for (int h = 0; h < CPT / 2; ++h)
+                    *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x + 2 * h) =
+                        make_ulonglong2(val[2 * h], val[2 * h + 1]);
+            }
             const u64 qi = __ldg(M.srcQ + i), qib = __ldg(M.qib + i), qinv = __ldg(M.srcQinv + i);
-            const u64 ya = mred(val.x, qib, qi, qinv), yb = mred(val.y, qib, qi, qinv);
             const double qd = __ull2double_rn(qi);
-            yd[i][0] = __ull2double_rn(ya);  // exact: below 2^48
-            yd[i][1] = __ull2double_rn(yb);
-            vi0 = __dadd_rn(vi0, __ddiv_rn(yd[i][0], qd));
-            vi1 = __dadd_rn(vi1, __ddiv_rn(yd[i][1], qd));
-            y0[i][0] = (u32)ya;
-            y1[i][0] = (u32)(ya >> 32);
-            y0[i][1] = (u32)yb;
-            y1[i][1] = (u32)(yb >> 32);
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) {
+                const u64 ye = mred(val[e], qib, qi, qinv);
+                yd[i][e] = __ull2double_rn(ye);  // exact: below 2^48
+                vi[e] = __dadd_rn(vi[e], __ddiv_rn(yd[i][e], qd));  // :363-375, sequential as in the reference
+                y0[i][e] = (u32)ye;
+                y1[i][e] = (u32)(ye >> 32);
+            }
         }
-        v[0] = (u32)__double2ull_rz(vi0);
-        v[1] = (u32)__double2ull_rz(vi1);
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) v[e] = (u32)__double2ull_rz(vi[e]);
     }
     int idx = 0;
 #pragma unroll 1
@@ -360,24 +377,27 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
 #pragma unroll 1
         for (int t = 0; t < a.ndst[k]; ++t, ++idx) {
             const u64* row = tab + idx * ROW;
-            const u64 np = row[0], pj = row[1];
+            const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(row);      // {np, p}
+            const u64 np = h0.x, pj = h0.y;
             const double pinvd = __longlong_as_double((long long)row[2]);
             u64 c[NSRC];
             double cd[NSRC];
 #pragma unroll
             for (int i = 0; i < NSRC; ++i) {
-                c[i] = row[O_C + i];
-                cd[i] = __longlong_as_double((long long)row[O_CD + i]);
+                const ulonglong2 pr = *reinterpret_cast<const ulonglong2*>(row + O_C + 2 * i);
+                c[i] = pr.x;
+                cd[i] = __longlong_as_double((long long)pr.y);
             }
-            u64 res[2];
+            u64 res[CPT];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < CPT; ++e) {
+                const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(row + O_K + 2 * v[e]);  // {K'_v, Kd_v}
                 double s = __dmul_rd(yd[0][e], cd[0]);
 #pragma unroll
                 for (int i = 1; i < NSRC; ++i) s = __fma_rd(yd[i][e], cd[i], s);
-                s = __dadd_rd(s, __longlong_as_double((long long)row[O_KD + v[e]]));
+                s = __dadd_rd(s, __longlong_as_double((long long)kk.y));
                 const u64 tb = (u64)__double_as_longlong(__fma_rd(s, pinvd, 4503599627370496.0));
-                u64 acc = row[O_K + v[e]];
+                u64 acc = kk.x;
                 u32 h = 0;
 #pragma unroll
                 for (int i = 0; i < NSRC; ++i) {
@@ -390,7 +410,9 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
                 h = mad_lo32((u32)(tb >> 32), (u32)np, h);
                 res[e] = LAZY ? acc + ((u64)h << 32) : cred(acc + ((u64)h << 32), pj);
             }
-            *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N) = make_ulonglong2(res[0], res[1]);
+#pragma unroll
+            for (int h = 0; h < CPT / 2; ++h)
+                *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N + 2 * h) = make_ulonglong2(res[2 * h], res[2 * h + 1]);
         }
     }
 }
@@ -536,22 +558,26 @@ int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
     const bool no_lazy = lg_switches().no_lazy_modup.load(std::memory_order_relaxed) != 0;
     const bool lazy = a.lazy_out && !no_lazy;
     if (a.fast == 2 && !no_fp && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
-        dim3 fgrid((a.N / 2 + 127) / 128, batch);
-        if (lazy) {
-            switch (a.nsrc) {
-                case 1: modup_fp_kernel<1, true><<<fgrid, 128, 0, st>>>(a); break;
-                case 2: modup_fp_kernel<2, true><<<fgrid, 128, 0, st>>>(a); break;
-                case 3: modup_fp_kernel<3, true><<<fgrid, 128, 0, st>>>(a); break;
-                default: modup_fp_kernel<4, true><<<fgrid, 128, 0, st>>>(a); break;
-            }
-        } else {
-            switch (a.nsrc) {
-                case 1: modup_fp_kernel<1, false><<<fgrid, 128, 0, st>>>(a); break;
-                case 2: modup_fp_kernel<2, false><<<fgrid, 128, 0, st>>>(a); break;
-                case 3: modup_fp_kernel<3, false><<<fgrid, 128, 0, st>>>(a); break;
-                default: modup_fp_kernel<4, false><<<fgrid, 128, 0, st>>>(a); break;
-            }
+        // four coefficients per thread when that still fills the GPU (two otherwise)
+        const bool four = !lg_switches().modup_cpt2.load(std::memory_order_relaxed) && a.N >= 4 &&
+                          (size_t)batch * (a.N / 4 / 128) >= 2 * 148;
+        const int cpt = four ? 4 : 2;
+        dim3 fgrid((a.N / cpt + 127) / 128, batch);
+#define LG_FP(NS)                                                                                  \
+    if (four) {                                                                                    \
+        if (lazy) modup_fp_kernel<NS, true, 4><<<fgrid, 128, 0, st>>>(a);                          \
+        else modup_fp_kernel<NS, false, 4><<<fgrid, 128, 0, st>>>(a);                              \
+    } else {                                                                                       \
+        if (lazy) modup_fp_kernel<NS, true, 2><<<fgrid, 128, 0, st>>>(a);                          \
+        else modup_fp_kernel<NS, false, 2><<<fgrid, 128, 0, st>>>(a);                              \
+    }
+        switch (a.nsrc) {
+            case 1: LG_FP(1) break;
+            case 2: LG_FP(2) break;
+            case 3: LG_FP(3) break;
+            default: LG_FP(4) break;
         }
+#undef LG_FP
         lg_g_launches += 1;
         return 0;
     }

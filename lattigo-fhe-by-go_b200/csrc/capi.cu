@@ -36,8 +36,10 @@ LgSwitches& lg_switches() {
         sw.literal_ntt = flag("LATTIGPU_LITERAL_NTT", false);
         sw.ks_acc64 = flag("LATTIGPU_KS_ACC64", false);
         sw.no_d64_ntt = flag("LATTIGPU_NO_D64_NTT", true);
+        sw.reverse_walk = flag("LATTIGPU_REVERSE_WALK", true);
         sw.no_fp_modup = flag("LATTIGPU_NO_FP_MODUP", true);
         sw.no_lazy_modup = flag("LATTIGPU_NO_LAZY_MODUP", true);
+        sw.modup_cpt2 = flag("LATTIGPU_MODUP_CPT2", true);
         sw.no_wide_modup = flag("LATTIGPU_NO_WIDE_MODUP", true);
         sw.no_tail_canon = flag("LATTIGPU_NO_TAIL_CANON", true);
         sw.no_fused_tail = flag("LATTIGPU_NO_FUSED_TAIL", true);
@@ -110,8 +112,10 @@ int lg_debug_set_switch(const char* name, uint64_t value) {
     if (!strcmp(name, "literal_ntt")) sw.literal_ntt = v;
     else if (!strcmp(name, "ks_acc64")) sw.ks_acc64 = v;
     else if (!strcmp(name, "no_d64_ntt")) sw.no_d64_ntt = v;
+    else if (!strcmp(name, "reverse_walk")) sw.reverse_walk = v;
     else if (!strcmp(name, "no_fp_modup")) sw.no_fp_modup = v;
     else if (!strcmp(name, "no_lazy_modup")) sw.no_lazy_modup = v;
+    else if (!strcmp(name, "modup_cpt2")) sw.modup_cpt2 = v;
     else if (!strcmp(name, "no_wide_modup")) sw.no_wide_modup = v;
     else if (!strcmp(name, "no_tail_canon")) sw.no_tail_canon = v;
     else if (!strcmp(name, "no_fused_tail")) sw.no_fused_tail = v;

@@ -11,9 +11,14 @@ extern std::atomic<uint64_t> lg_g_launches;  // kernels launched by this library
 // (std::call_once), then only changed through lg_debug_set_switch -- no getenv on any launch path.  All default to 0.
 struct LgSwitches {
     std::atomic<int> literal_ntt{0};     // LATTIGPU_LITERAL_NTT: literal Butterfly/InvButterfly in every transform
+    // LATTIGPU_REVERSE_WALK: second NTT phases and the fused digit loop walk their grids backwards, reading first what the
+    // previous launch wrote last.  Measured (profiles/r02_reverse_walk_ab.jsonl, ABAB): no gain (467 -> 474..499 us per
+    // 1088 limb-NTTs), so it is off.
+    std::atomic<int> reverse_walk{0};
     std::atomic<int> no_d64_ntt{0};      // LATTIGPU_NO_D64_NTT: integer instead of FP64-only butterflies below 3*2^44
     std::atomic<int> ks_acc64{0};        // LATTIGPU_KS_ACC64: never take the 96-bit key-switch accumulators
     std::atomic<int> no_fp_modup{0};     // LATTIGPU_NO_FP_MODUP: integer-only basis extension
+    std::atomic<int> modup_cpt2{0};      // LATTIGPU_MODUP_CPT2: two instead of four coefficients per thread in modup_fp_kernel
     std::atomic<int> no_lazy_modup{0};   // LATTIGPU_NO_LAZY_MODUP: canonical key-switch digits
     std::atomic<int> no_wide_modup{0};   // LATTIGPU_NO_WIDE_MODUP: generic kernel for 5..16 sources
     std::atomic<int> no_tail_canon{0};   // LATTIGPU_NO_TAIL_CANON: reduce the transform before the ModDown tail
@@ -81,6 +86,7 @@ struct NttArgs {
     const u32* flags;
     int no_d64;                      // set by the launchers from the "no_d64_ntt" switch
     int batch0;                      // index of the launch's first batch entry in the caller's batch (tail addressing)
+    int rev;                         // walk the grid backwards (second phases: read first what the first phase wrote last)
     NttTail tail;                    // forward only
     NttBcast bcast;                  // forward only
 };
@@ -110,6 +116,7 @@ struct KsFusedArgs {
     int beta, alpha, nl;  // digit i owns the data limbs whose TABLE limb lies in [i*alpha, min((i+1)*alpha, nl))
     int acc64;            // 1 = never take the 96-bit accumulators (LATTIGPU_KS_ACC64=1: A/B and cross-check)
     int no_d64;           // set by the launcher from the "no_d64_ntt" switch
+    int rev;              // walk the grid backwards (set by the launcher)
 };
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st);
 

@@ -248,6 +248,12 @@ LG_DEV void fill_strided_tw(u64* tws_sm, const TwConst& c) {
     }
 }
 
+// CTAs are dispatched in blockIdx order (x fastest, z slowest).  A launch that reads what the previous launch wrote can
+// walk its grid backwards (NttArgs::rev): the data written last -- still in L2 -- is then read first.
+LG_DEV int cta_x(const NttArgs& a) { return a.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x; }
+LG_DEV int cta_y(const NttArgs& a) { return a.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y; }
+LG_DEV int cta_z(const NttArgs& a) { return a.rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z; }
+
 struct LimbSetup {
     LimbConst c;
     const u64* in;
@@ -258,7 +264,7 @@ struct LimbSetup {
 
 LG_DEV LimbSetup setup_limb(const NttArgs& a) {
     LimbSetup s;
-    const int j = blockIdx.z, b = blockIdx.x;
+    const int j = cta_z(a), b = cta_x(a);
     s.tl = a.map(j);
     if (a.skip_alpha > 0) {
         const int dg = b / a.skip_div;
@@ -320,7 +326,7 @@ LG_DEV void fwd_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
     constexpr int N2 = L - 4;        // stages of the second register block
     const TwConst c = tw_const<true, MODE>(a.T, s.c, s.tl);
     const int t = threadIdx.x, col = t % W, g = t / W;
-    const u32 colg = blockIdx.y * W + col;
+    const u32 colg = cta_y(a) * W + col;
     u64 x[16];
     const u64* in = s.in + colg + g * 256;
 #pragma unroll
@@ -479,10 +485,10 @@ LG_DEV void prefetch_warp_tile_rows(u64* buf, const u64* __restrict__ src_tile) 
 template <bool FWD, int MODE, bool TAIL>
 LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int b0, int nb, u64* smem) {
     const u32 N = a.T.N;
-    const int j = blockIdx.z;
+    const int j = cta_z(a);
     const TwConst c = tw_const<FWD, MODE>(a.T, lc, tl);
     const u32 t = threadIdx.x, sg = t >> 4, cc = t & 15;
-    const u32 tile0 = blockIdx.y * CONTIG_TILE;
+    const u32 tile0 = cta_y(a) * CONTIG_TILE;
     const u32 segbase = tile0 + sg * 256u;
     const u32 e0 = segbase + 16 * cc, j0 = segbase + cc;
     u64* const tilebuf = smem;
@@ -602,8 +608,8 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
 template <bool FWD, bool LITERAL, bool TAIL = false>
 __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttArgs a, int batch, int bpc) {
     extern __shared__ __align__(16) u64 ks_smem[];
-    const int j = blockIdx.z;
-    const int b0 = blockIdx.x * bpc, nb = (batch - b0) < bpc ? (batch - b0) : bpc;
+    const int j = cta_z(a);
+    const int b0 = cta_x(a) * bpc, nb = (batch - b0) < bpc ? (batch - b0) : bpc;
     const int tl = a.map(j);
     if (a.skip_alpha > 0) {  // digit-batched launch: bpc divides skip_div, so a group never straddles two digits
         const int dg = b0 / a.skip_div;
@@ -697,11 +703,12 @@ LG_DEV void ks_load_keys(u64 (&k0)[16], u64 (&k1)[16], const u64* key, size_t hs
 template <int MODE, int ACC>
 LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64* smem) {
     const u32 N = a.T.N;
-    const int j = blockIdx.z, b = blockIdx.x;
+    const int j = a.rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    const int b = a.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
     const u64 q = lc.q, qinv = lc.qinv;
     const TwConst c = tw_const<true, MODE>(a.T, lc, tl);
     const u32 t = threadIdx.x, sg = t >> 4, cc = t & 15;
-    const u32 tile0 = blockIdx.y * CONTIG_TILE;      // first word of the CTA's tile within the limb
+    const u32 tile0 = (a.rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y) * CONTIG_TILE;  // first word of the CTA's tile within the limb
     const u32 segbase = tile0 + sg * 256u;
     const u32 e0 = segbase + 16 * cc;
     u64* const tilebuf = smem;                        // [2][2048]
@@ -837,7 +844,7 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
 template <bool LITERAL>
 __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const KsFusedArgs a) {
     extern __shared__ __align__(16) u64 ks_smem[];
-    const int tl = a.map(blockIdx.z);
+    const int tl = a.map(a.rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z);
     const LimbConst lc = load_limb_const(a.T, tl);
     const int mode = LITERAL ? M_LITERAL : fwd_mode(lc.q, a.no_d64);
     // beta lazy terms below 2q fit 64 bits (a term is below 2q when the key word has at most bits(q) bits: its product
@@ -878,7 +885,7 @@ __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const
 }
 
 LG_DEV bool inv_flagged(const NttArgs& a) {
-    return a.flags != nullptr && a.flags[(size_t)blockIdx.x * gridDim.z + blockIdx.z] != 0;
+    return a.flags != nullptr && a.flags[(size_t)cta_x(a) * gridDim.z + cta_z(a)] != 0;
 }
 
 // ---- inverse, strided phase: last L stages + MRed by N^-1 --------------------
@@ -889,7 +896,7 @@ LG_DEV void inv_strided_body(const NttArgs& a, const LimbSetup& s, u64* sm, u64*
     constexpr int N2 = L - 4;
     const TwConst c = tw_const<false, MODE>(a.T, s.c, s.tl);
     const int t = threadIdx.x, col = t % W, g = t / W;
-    const u32 colg = blockIdx.y * W + col;
+    const u32 colg = cta_y(a) * W + col;
     u64 x[16];
     if (N2 > 0) {
         const u64* in = s.in + colg + g * 16 * 256;
@@ -1114,6 +1121,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
         second.in_bstride = args.out_bstride;
         second.in_ls = args.out_ls;
         second.bcast.enabled = 0;
+        second.rev = lg_switches().reverse_walk.load(std::memory_order_relaxed) ? 1 : 0;
         const dim3 grid(nb, N / 4096, nlimbs);
         if (!inverse) {
             launch_strided_any(L, true, literal, first, grid, st);
@@ -1154,6 +1162,7 @@ int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t
     KsFusedArgs k = a;
     k.acc64 = lg_switches().ks_acc64.load(std::memory_order_relaxed) ? 1 : 0;
     k.no_d64 = lg_switches().no_d64_ntt.load(std::memory_order_relaxed) ? 1 : 0;
+    k.rev = lg_switches().reverse_walk.load(std::memory_order_relaxed) ? 1 : 0;  // the strided phase wrote the high limbs last
     if (literal_ntt()) {
         lg_ensure_dyn_smem<ks_fused_kernel<true>>(smem);
         ks_fused_kernel<true><<<grid, CONTIG_THREADS, smem, st>>>(k);

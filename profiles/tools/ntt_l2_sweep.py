@@ -59,6 +59,30 @@ def step():
     ev.Rescale(nQ, o, 1, stream=sp)
 
 
+if len(sys.argv) > 2 and sys.argv[1] == "ab":  # interleaved A/B of 0/1 switches: python ntt_l2_sweep.py ab <switch> [<switch> ...]
+    import statistics
+
+    for _ in range(3):
+        step()
+    for name in sys.argv[2:]:
+        acc = {0: {"fwd": [], "inv": [], "step": []}, 1: {"fwd": [], "inv": [], "step": []}}
+        for rnd in range(8):
+            for val in ((0, 1) if rnd % 2 == 0 else (1, 0)):
+                ring.debug_set_switch(name, val)
+                acc[val]["fwd"].append(timed(lambda: cQ.NTT(a[0], o[0], stream=sp), reps=5, warm=1))
+                acc[val]["inv"].append(timed(lambda: cQ.InvNTT(a[0], o[0], stream=sp), reps=5, warm=1))
+                acc[val]["step"].append(timed(step, reps=3, warm=1))
+        ring.debug_set_switch(name, 0)
+        print(json.dumps({"switch": name, "rounds": 8,
+                          "median_us": {str(v): {k: statistics.median(x) for k, x in acc[v].items()} for v in (0, 1)},
+                          "min_us": {str(v): {k: min(x) for k, x in acc[v].items()} for v in (0, 1)}}), flush=True)
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "rev":  # A/B of the backward grid walk of the second phases (ABAB)
+    for norev in (1, 0, 1, 0):
+        ring.debug_set_switch("reverse_walk", 1 - norev)
+        print(json.dumps({"no_reverse_walk": norev, "fwd_us": timed(lambda: cQ.NTT(a[0], o[0], stream=sp)),
+                          "inv_us": timed(lambda: cQ.InvNTT(a[0], o[0], stream=sp)), "step_us": timed(step, reps=8)}), flush=True)
+    sys.exit(0)
 for mib in [int(x) for x in sys.argv[1:]] or [0, 16, 24, 32, 48, 64, 96]:
     ring.debug_set_switch("ntt_l2_bytes", mib << 20)
     res = {"ntt_l2_MiB": mib, "fwd_us": timed(lambda: cQ.NTT(a[0], o[0], stream=sp)),
