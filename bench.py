@@ -137,7 +137,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 
@@ -320,6 +320,31 @@ def leg_party(args, dev, world, rank, timed_ms):
     return res
 
 # ----------------------------------------------------------------------------
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout under
+# NCCL_DEBUG=VERSION whatever NCCL_DEBUG_FILE says), so the process' fd 1 is pointed at stderr for the whole run and
+# the JSON line goes to a duplicate of the original stdout.
+# ----------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+# ----------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------
 class ClockSampler:
@@ -383,7 +408,7 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     gring.set_device(local_rank)
     if world > 1:
-        # stdout carries the one JSON line: NCCL's own messages (the version banner under NCCL_DEBUG=VERSION/INFO) go to stderr
+        capture_stdout()
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -728,7 +753,7 @@ def run_gpu(args):
             "rotate": rotate, "roofline": roofline, "roofline_op": roofline_op, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "parity_check": parity_check, "limb_sharded": legs["limb_sharded"], "party": legs["party"],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -751,6 +776,7 @@ def run_config(args):
     torch.cuda.set_device(local_rank)
     gring.set_device(local_rank)
     if world > 1:
+        capture_stdout()
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -851,7 +877,7 @@ def run_config(args):
             "also": extra, "roofline": cfg["roofline"](1e3 * ms_per_step), "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
