@@ -72,7 +72,8 @@ uint64_t lg_launch_count(void);
  * process from the environment variable LATTIGPU_<NAME IN UPPER CASE> (no getenv on any launch path) and can then only
  * be changed through this call.  Names (value 0/1 unless noted): "literal_ntt" (literal Butterfly/InvButterfly of
  * ring/ntt.go:32-50 in every transform), "no_d64_ntt" (integer instead of FP64-only butterflies for moduli below
- * 3*2^44), "ks_acc64" (64-bit instead of 96-bit key-switch accumulators),
+ * 3*2^44), "ks_acc64" (64-bit instead of 96-bit key-switch accumulators), "no_fp_mac" (integer instead of FP64 key-switch
+ * accumulators),
  * "no_fp_modup" / "no_lazy_modup" / "no_wide_modup" / "modup_cpt2" (basis-extension kernel choice), "no_tail_canon" /
  * "no_fused_tail" (ModDown / rescale tail placement), "ks_scratch_words" (value = digit scratch budget of the key
  * switch in 64-bit words, 0 restores the 6 GiB default), "ntt_l2_bytes" (value = bytes of first-phase output a group of
@@ -237,6 +238,9 @@ int lg_swk_wrap(void* device_ptr, uint64_t N, int beta, int nQP, lg_swk** out);
  * evakey[digit][half] as a non-owning ring.Poly handle over QP for lg_poly_write_to / lg_poly_decode */
 int lg_swk_alloc(uint64_t N, int beta, int nQP, lg_swk** out);
 int lg_swk_poly(const lg_swk* k, int digit, int half, lg_poly** out);
+/* A key is immutable once an evaluator has used it (derived device forms are built at first use).  Call this after
+ * writing to the key's memory by other means than a view obtained afterwards (lg_swk_poly invalidates by itself). */
+int lg_swk_invalidate(lg_swk* k);
 int lg_swk_beta(const lg_swk* k);
 int lg_swk_nlimbs(const lg_swk* k);
 uint64_t lg_swk_n(const lg_swk* k);

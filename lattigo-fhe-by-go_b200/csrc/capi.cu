@@ -35,6 +35,7 @@ LgSwitches& lg_switches() {
         };
         sw.literal_ntt = flag("LATTIGPU_LITERAL_NTT", false);
         sw.ks_acc64 = flag("LATTIGPU_KS_ACC64", false);
+        sw.no_fp_mac = flag("LATTIGPU_NO_FP_MAC", true);
         sw.no_d64_ntt = flag("LATTIGPU_NO_D64_NTT", true);
         sw.reverse_walk = flag("LATTIGPU_REVERSE_WALK", true);
         sw.no_fp_modup = flag("LATTIGPU_NO_FP_MODUP", true);
@@ -111,6 +112,7 @@ int lg_debug_set_switch(const char* name, uint64_t value) {
     const int v = value ? 1 : 0;
     if (!strcmp(name, "literal_ntt")) sw.literal_ntt = v;
     else if (!strcmp(name, "ks_acc64")) sw.ks_acc64 = v;
+    else if (!strcmp(name, "no_fp_mac")) sw.no_fp_mac = v;
     else if (!strcmp(name, "no_d64_ntt")) sw.no_d64_ntt = v;
     else if (!strcmp(name, "reverse_walk")) sw.reverse_walk = v;
     else if (!strcmp(name, "no_fp_modup")) sw.no_fp_modup = v;

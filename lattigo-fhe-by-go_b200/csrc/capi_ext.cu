@@ -496,6 +496,11 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
             memset(&k, 0, sizeof(k));
             k.T = QP->T;
             k.map = qp_map;
+            if (!lg_switches().no_fp_mac.load(std::memory_order_relaxed) && evk->nQP == QP->nl) {
+                LG_TRY(lgi_swk_prepare(evk, QP, st));
+                k.evk_f = evk->d_f;
+                k.key_bad = evk->d_bad;
+            }
             k.D = D.d;
             k.d_ds = d_ds;
             k.d_bs = d_bs;
@@ -584,6 +589,20 @@ static int ckks_switch_keys(lg_ckks_eval* e, int level, int batch, const u64* cx
     // the accumulators are canonical, so their inverse transforms need no range check
     return lgi_moddown_pair_ntt(e->ext.get(), level, batch, acc0, acc1, d_bs, nl, out0, out0_bs, add0, out1, out1_bs, add1, true,
                                 st, true);
+}
+
+int lgi_swk_prepare(const lg_swk* k, const lg_ring* QP, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(k->mu);
+    if (k->prepared) return LG_OK;
+    const size_t words = (size_t)k->beta * 2 * k->nQP * k->N;
+    if (!k->d_f) LG_CUDA_CHECK(cudaMalloc((void**)&k->d_f, words * sizeof(u64)));
+    if (!k->d_bad) LG_CUDA_CHECK(cudaMalloc((void**)&k->d_bad, (size_t)k->beta * 2 * k->nQP * sizeof(u32)));
+    LG_CUDA_CHECK(cudaMemsetAsync(k->d_bad, 0, (size_t)k->beta * 2 * k->nQP * sizeof(u32), st));
+    lg_launch_swk_prepare(QP->T, k->d, k->d_f, k->d_bad, k->beta, k->nQP, st);
+    LG_LAUNCH_CHECK();
+    LG_CUDA_CHECK(cudaStreamSynchronize(st));  // once per key: other streams may use it right away
+    k->prepared = true;
+    return LG_OK;
 }
 
 int lgi_concat_ring(const lg_ring* Q, const lg_ring* P, std::unique_ptr<lg_ring>& out) {
@@ -680,8 +699,18 @@ int lg_swk_alloc(uint64_t N, int beta, int nQP, lg_swk** out) {
     return LG_OK;
 }
 // evakey[digit][half] as a non-owning polynomial handle over QP (the key must outlive it)
+int lg_swk_invalidate(lg_swk* k) {
+    LG_REQUIRE(k, "SwitchingKey: null argument");
+    std::lock_guard<std::mutex> lock(k->mu);
+    k->prepared = false;
+    return LG_OK;
+}
 int lg_swk_poly(const lg_swk* k, int digit, int half, lg_poly** out) {
     LG_REQUIRE(k && out, "SwitchingKey: null argument");
+    {
+        std::lock_guard<std::mutex> lock(k->mu);
+        k->prepared = false;  // a view exists to fill the key: its derived forms are rebuilt at the next use
+    }
     LG_REQUIRE(digit >= 0 && digit < k->beta && (half == 0 || half == 1), "SwitchingKey: evakey[%d][%d] out of range", digit, half);
     LG_ON_DEVICE(k->device);
     return lg_poly_wrap((void*)k->key(digit, half), k->N, k->nQP, 1, out);

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "../../include/lattigpu.h"
@@ -183,7 +184,20 @@ struct lg_swk {
     int beta = 0, nQP = 0;
     bool owns = false;
     const u64* key(int digit, int half) const { return d + ((size_t)(digit * 2 + half) * nQP) * N; }
+    // FP64 form for the limbs whose moduli take the FP64-only transforms (ntt.cu, ACC_FP): the key words out of Montgomery
+    // form as doubles, same layout, and one flag per (digit, half, limb) raised when a word of that limb is not canonical
+    // (such limbs keep the integer accumulators).  Built by lgi_swk_prepare on first use: a key is immutable once an
+    // evaluator has used it -- lg_swk_invalidate after writing to it (lg_swk_poly invalidates: views exist to fill keys).
+    mutable u64* d_f = nullptr;
+    mutable u32* d_bad = nullptr;
+    mutable bool prepared = false;
+    mutable std::mutex mu;
+    ~lg_swk() {
+        if (d_f) cudaFree(d_f);
+        if (d_bad) cudaFree(d_bad);
+    }
 };
+int lgi_swk_prepare(const lg_swk* k, const lg_ring* QP, cudaStream_t st);
 
 // RotateHoisted precomputation: the NTT-domain digits of value[1] (ckks/evaluator.go:1258-1273)
 struct lg_hoisted {

@@ -356,6 +356,11 @@ int switch_keys_resident(lg_ckks_eval* e, lg_comm* c, int level, int batch, cons
         memset(&k, 0, sizeof(k));
         k.T = QP->T;
         k.map = o.qp_map();
+        if (!lg_switches().no_fp_mac.load(std::memory_order_relaxed)) {
+            LG_TRY(lgi_swk_prepare(evk, QP, st));
+            k.evk_f = evk->d_f;
+            k.key_bad = evk->d_bad;
+        }
         k.D = D.d;
         k.d_ds = d_ds;
         k.d_bs = d_bs;

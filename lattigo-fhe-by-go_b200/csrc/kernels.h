@@ -17,6 +17,7 @@ struct LgSwitches {
     std::atomic<int> reverse_walk{0};
     std::atomic<int> no_d64_ntt{0};      // LATTIGPU_NO_D64_NTT: integer instead of FP64-only butterflies below 3*2^44
     std::atomic<int> ks_acc64{0};        // LATTIGPU_KS_ACC64: never take the 96-bit key-switch accumulators
+    std::atomic<int> no_fp_mac{0};       // LATTIGPU_NO_FP_MAC: integer key-switch accumulators on the FP64-class limbs too
     std::atomic<int> no_fp_modup{0};     // LATTIGPU_NO_FP_MODUP: integer-only basis extension
     std::atomic<int> modup_cpt2{0};      // LATTIGPU_MODUP_CPT2: two instead of four coefficients per thread in modup_fp_kernel
     std::atomic<int> no_lazy_modup{0};   // LATTIGPU_NO_LAZY_MODUP: canonical key-switch digits
@@ -110,6 +111,8 @@ struct KsFusedArgs {
     size_t cx_bs, cx_ls;  // cx_ls = 0: N
     const u64* evk;     // evk[i][h], table limb tl at evk + i*evk_ds + h*evk_hs + tl*N (shared by the batch)
     size_t evk_ds, evk_hs;
+    const u64* evk_f;   // the same key out of Montgomery form as doubles (FP64-class limbs; lg_launch_swk_prepare), or nullptr
+    const u32* key_bad; // per (digit, half, table limb): a word of that key limb is not canonical -> integer accumulators
     u64* acc0;          // outputs, limb j of batch b at acc + b*acc_bs + j*N, canonical
     u64* acc1;
     size_t acc_bs;
@@ -119,6 +122,8 @@ struct KsFusedArgs {
     int rev;              // walk the grid backwards (set by the launcher)
 };
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st);
+// keyf = double(InvMForm(key)) for the limbs with q < 3*2^44, bad[(digit*2+half)*nQP + tl] |= 1 when a word >= q
+int lg_launch_swk_prepare(const RingTables& T, const u64* key, u64* keyf, u32* bad, int beta, int nQP, cudaStream_t st);
 
 // ---- K3a: coefficient-wise ops (ring/ring.go) --------------------------------
 enum EwOp {

@@ -138,7 +138,32 @@ __global__ void __launch_bounds__(256) ks_hoisted_kernel(const KsHoistArgs a) {
         ks_hoisted_body<false>(a, k, tl);
 }
 
+// FP64 form of a switching key (ntt.cu ACC_FP): plain key words as doubles for the FP64-class limbs
+__global__ void __launch_bounds__(256) swk_prepare_kernel(RingTables T, const u64* key, u64* keyf, u32* bad, int nQP) {
+    const int tl = blockIdx.y, dh = blockIdx.z;
+    const u64 q = T.q[tl];
+    if (q >= (3ull << 44)) return;
+    const u64 qinv = T.qinv[tl];
+    const size_t off = ((size_t)dh * nQP + tl) * T.N;
+    int isbad = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+        const u64 w = key[off + i];
+        isbad |= w >= q;
+        keyf[off + i] = (u64)__double_as_longlong(__ull2double_rn(mred(w, 1, q, qinv)));  // exact: below 2^46
+    }
+    if (__syncthreads_or(isbad) && threadIdx.x == 0) atomicOr(bad + (size_t)dh * nQP + tl, 1u);
+}
+
 }  // namespace
+
+int lg_launch_swk_prepare(const RingTables& T, const u64* key, u64* keyf, u32* bad, int beta, int nQP, cudaStream_t st) {
+    if (beta <= 0 || nQP <= 0) return 0;
+    u32 bx = (T.N + 255) / 256;
+    if (bx > 16) bx = 16;
+    swk_prepare_kernel<<<dim3(bx, nQP, 2 * beta), 256, 0, st>>>(T, key, keyf, bad, nQP);
+    lg_g_launches += 1;
+    return 0;
+}
 
 int lg_launch_ks_hoisted(const KsHoistArgs& a, int nlimbs, int batch, cudaStream_t st) {
     if (nlimbs <= 0 || batch <= 0) return 0;

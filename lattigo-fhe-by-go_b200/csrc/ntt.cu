@@ -651,7 +651,11 @@ __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttAr
 // ACC_EXACT is the always-valid form: the digit value is made canonical first (as the reference's c2QiQ / c2QiP are) and
 // every term is a full MRed + CRed, exact for ANY 64-bit key word.  The two lazy forms assume key words of at most
 // bits(q) bits; they watch the high halves of the key words and the CTA repeats its tile with ACC_EXACT otherwise.
-enum { ACC_EXACT = 0, ACC_LAZY64 = 1, ACC_WIDE96 = 2 };
+// ACC_FP (M_D64 limbs only): the multiply-accumulate on the FP64 pipe as well -- the key limb out of Montgomery form as
+// doubles (lg_launch_swk_prepare), every term k*x reduced to [-q, 2q) by d64_mul (the digit value is already a double
+// below 34q: no conversion), the accumulators two doubles per coefficient (64 registers instead of 96).  Sum of beta
+// terms below 2q: exact.  8 instructions per term instead of 12.5; limbs with a non-canonical key word stay integer.
+enum { ACC_EXACT = 0, ACC_LAZY64 = 1, ACC_WIDE96 = 2, ACC_FP = 3 };
 
 // (a2 : A) += k * x, caller guarantees the running sum stays below 2^96
 LG_DEV void mac96(u64& A, u32& a2, u64 k, u64 x) {
@@ -725,8 +729,8 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
     const double qd1 = (ACC == ACC_WIDE96 && MODE != M_D64) ? __ull2double_rd(lc.u0) * 5.421010862427522170037e-20 : 0.0;
     const double cq1 = (ACC == ACC_WIDE96 && MODE != M_D64) ? shoup_cw(qd1) : 0.0;
 
-    const u64* key = a.evk + (size_t)tl * N + e0;
-    u64 acc0[16], acc1[16];
+    const u64* key = (ACC == ACC_FP ? a.evk_f : a.evk) + (size_t)tl * N + e0;
+    u64 acc0[16], acc1[16];  // ACC_FP: bit patterns of doubles (+0.0 = 0)
     u32 top0[16], top1[16], keyhi = 0;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -761,9 +765,13 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
 #pragma unroll
                 for (int e = 0; e < 4; ++e) x[4 * h + e] = v[e];
             }
-            if (ACC == ACC_WIDE96 || ACC == ACC_EXACT) {  // caller data, any 64-bit word: canonical
+            if (ACC == ACC_WIDE96 || ACC == ACC_EXACT || ACC == ACC_FP) {  // caller data, any 64-bit word: canonical
 #pragma unroll
                 for (int r = 0; r < 16; ++r) x[r] = bred_add(x[r], q, lc.u0);
+            }
+            if (ACC == ACC_FP) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) x[r] = d2bits(u52_to_d(x[r], 4503599627370496.0));
             }
         } else {
 #pragma unroll
@@ -787,7 +795,7 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
                         x[r] = d_to_u52(d64_red(bits2d(x[r]), c.qinvd, c.qd), 4503599627370496.0 + c.qd);
                     else if (ACC == ACC_LAZY64)  // (0, 68q), congruent
                         x[r] = d_to_u52(bits2d(x[r]), 4503599627370496.0 + c.q34);
-                    else
+                    else if (ACC == ACC_EXACT)
                         x[r] = d64_canon(x[r], c);
                 }
             } else if (ACC == ACC_WIDE96) {
@@ -804,7 +812,11 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
 #endif
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-            if (ACC == ACC_WIDE96) {
+            if (ACC == ACC_FP) {
+                const double xd = bits2d(x[r]), k0 = bits2d(kk0[r]), k1 = bits2d(kk1[r]);
+                acc0[r] = d2bits(__dadd_rn(bits2d(acc0[r]), d64_mul(k0, __dmul_rd(k0, c.qinvd), xd, c.qd)));
+                acc1[r] = d2bits(__dadd_rn(bits2d(acc1[r]), d64_mul(k1, __dmul_rd(k1, c.qinvd), xd, c.qd)));
+            } else if (ACC == ACC_WIDE96) {
                 keyhi |= (u32)(kk0[r] >> 32) | (u32)(kk1[r] >> 32);
                 mac96(acc0[r], top0[r], kk0[r], x[r]);
                 mac96(acc1[r], top1[r], kk1[r], x[r]);
@@ -820,7 +832,13 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
     }
     u64* o0 = a.acc0 + (size_t)b * a.acc_bs + (size_t)j * N + e0;
     u64* o1 = a.acc1 + (size_t)b * a.acc_bs + (size_t)j * N + e0;
-    if (ACC == ACC_WIDE96) {
+    if (ACC == ACC_FP) {  // |sum| < 18q
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            acc0[r] = d64_canon(acc0[r], c);
+            acc1[r] = d64_canon(acc1[r], c);
+        }
+    } else if (ACC == ACC_WIDE96) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             acc0[r] = mred96(acc0[r], top0[r], q, qinv);
@@ -854,7 +872,16 @@ __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const
     // are watched -- below 2^32 a key word is harmless for any q)
     const int qbits = 64 - __clzll((long long)lc.q), kb = qbits < 32 ? 32 : qbits;
     u32 keyhi = 0;
-    if (mode == M_D64) {
+    bool fpmac = mode == M_D64 && a.evk_f != nullptr && !a.acc64 && a.beta <= 32;
+    if (fpmac) {  // every key limb of this table limb canonical?
+        const int nqp = (int)(a.evk_hs / a.T.N);
+        u32 bad = 0;
+        for (int i = 0; i < 2 * a.beta; ++i) bad |= a.key_bad[(size_t)i * nqp + tl];
+        fpmac = bad == 0;
+    }
+    if (fpmac) {
+        ks_fused_body<M_D64, ACC_FP>(a, lc, tl, ks_smem);
+    } else if (mode == M_D64) {
         const int sh = 96 - kb;
         if (!a.acc64 && (sh >= 64 || ((3ull * (u64)a.beta * lc.q) >> sh) == 0))
             keyhi = ks_fused_body<M_D64, ACC_WIDE96>(a, lc, tl, ks_smem);

@@ -154,6 +154,7 @@ SIGNATURES = {
     "lg_swk_create": (ci, [u64, ci, ci, p64, C.POINTER(vp)]),
     "lg_swk_alloc": (ci, [u64, ci, ci, C.POINTER(vp)]),
     "lg_swk_poly": (ci, [vp, ci, ci, C.POINTER(vp)]),
+    "lg_swk_invalidate": (ci, [vp]),
     "lg_swk_beta": (ci, [vp]),
     "lg_swk_nlimbs": (ci, [vp]),
     "lg_swk_n": (u64, [vp]),
