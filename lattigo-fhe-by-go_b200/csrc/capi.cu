@@ -36,6 +36,7 @@ LgSwitches& lg_switches() {
         sw.literal_ntt = flag("LATTIGPU_LITERAL_NTT", false);
         sw.ks_acc64 = flag("LATTIGPU_KS_ACC64", false);
         sw.no_fp_mac = flag("LATTIGPU_NO_FP_MAC", true);
+        sw.no_ks_tma = flag("LATTIGPU_NO_KS_TMA", true);
         sw.no_d64_ntt = flag("LATTIGPU_NO_D64_NTT", true);
         sw.reverse_walk = flag("LATTIGPU_REVERSE_WALK", true);
         sw.no_fp_modup = flag("LATTIGPU_NO_FP_MODUP", true);
@@ -44,6 +45,8 @@ LgSwitches& lg_switches() {
         sw.no_wide_modup = flag("LATTIGPU_NO_WIDE_MODUP", true);
         sw.no_tail_canon = flag("LATTIGPU_NO_TAIL_CANON", true);
         sw.no_fused_tail = flag("LATTIGPU_NO_FUSED_TAIL", true);
+        if (const char* e = getenv("LATTIGPU_KS_KEY_PF")) sw.ks_key_pf = atoi(e);
+        if (const char* e = getenv("LATTIGPU_TAIL_PF")) sw.tail_pf = atoi(e);
         if (const char* e = getenv("LATTIGPU_KS_SCRATCH_WORDS")) sw.ks_scratch_words = strtoull(e, nullptr, 10);
         if (const char* e = getenv("LATTIGPU_NTT_L2_BYTES")) sw.ntt_l2_bytes = strtoull(e, nullptr, 10);
     });
@@ -113,6 +116,7 @@ int lg_debug_set_switch(const char* name, uint64_t value) {
     if (!strcmp(name, "literal_ntt")) sw.literal_ntt = v;
     else if (!strcmp(name, "ks_acc64")) sw.ks_acc64 = v;
     else if (!strcmp(name, "no_fp_mac")) sw.no_fp_mac = v;
+    else if (!strcmp(name, "no_ks_tma")) sw.no_ks_tma = v;
     else if (!strcmp(name, "no_d64_ntt")) sw.no_d64_ntt = v;
     else if (!strcmp(name, "reverse_walk")) sw.reverse_walk = v;
     else if (!strcmp(name, "no_fp_modup")) sw.no_fp_modup = v;
@@ -121,6 +125,8 @@ int lg_debug_set_switch(const char* name, uint64_t value) {
     else if (!strcmp(name, "no_wide_modup")) sw.no_wide_modup = v;
     else if (!strcmp(name, "no_tail_canon")) sw.no_tail_canon = v;
     else if (!strcmp(name, "no_fused_tail")) sw.no_fused_tail = v;
+    else if (!strcmp(name, "ks_key_pf")) sw.ks_key_pf = (int)value;
+    else if (!strcmp(name, "tail_pf")) sw.tail_pf = (int)value;
     else if (!strcmp(name, "ks_scratch_words")) sw.ks_scratch_words = value ? value : ((uint64_t)6 << 27);
     else if (!strcmp(name, "ntt_l2_bytes")) sw.ntt_l2_bytes = value;
     else {

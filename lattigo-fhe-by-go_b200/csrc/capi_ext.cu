@@ -500,6 +500,10 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
                 LG_TRY(lgi_swk_prepare(evk, QP, st));
                 k.evk_f = evk->d_f;
                 k.key_bad = evk->d_bad;
+                if (evk->has_map) {
+                    k.h_keymap = evk->keymap;
+                    k.h_fp_ok = evk->fp_ok.data();
+                }
             }
             k.D = D.d;
             k.d_ds = d_ds;
@@ -601,6 +605,16 @@ int lgi_swk_prepare(const lg_swk* k, const lg_ring* QP, cudaStream_t st) {
     lg_launch_swk_prepare(QP->T, k->d, k->d_f, k->d_bad, k->beta, k->nQP, st);
     LG_LAUNCH_CHECK();
     LG_CUDA_CHECK(cudaStreamSynchronize(st));  // once per key: other streams may use it right away
+    // host side: which limbs the TMA digit loop may take, and the descriptor of d_f it loads key tiles through
+    std::vector<u32> bad((size_t)k->beta * 2 * k->nQP);
+    LG_CUDA_CHECK(cudaMemcpy(bad.data(), k->d_bad, bad.size() * sizeof(u32), cudaMemcpyDeviceToHost));
+    k->fp_ok.assign(k->nQP, 0);
+    for (int tl = 0; tl < k->nQP && tl < (int)QP->q.size(); ++tl) {
+        u32 b = QP->q[tl] >= (3ull << 44);
+        for (int dh = 0; dh < 2 * k->beta; ++dh) b |= bad[(size_t)dh * k->nQP + tl];
+        k->fp_ok[tl] = b ? 0 : 1;
+    }
+    k->has_map = (words % 16 == 0) && lg_encode_key_tensor_map(k->keymap, k->d_f, words) == 0;
     k->prepared = true;
     return LG_OK;
 }

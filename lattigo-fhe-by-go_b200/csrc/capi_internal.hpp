@@ -191,6 +191,11 @@ struct lg_swk {
     mutable u64* d_f = nullptr;
     mutable u32* d_bad = nullptr;
     mutable bool prepared = false;
+    // host side of the same: fp_ok[tl] = table limb tl may take ks_fused_tma_kernel (FP64-class modulus and no flag raised
+    // for any (digit, half)), and the TMA descriptor of d_f (128 opaque bytes, a CUtensorMap; has_map = it could be encoded)
+    mutable std::vector<unsigned char> fp_ok;
+    alignas(64) mutable unsigned char keymap[128];
+    mutable bool has_map = false;
     mutable std::mutex mu;
     ~lg_swk() {
         if (d_f) cudaFree(d_f);

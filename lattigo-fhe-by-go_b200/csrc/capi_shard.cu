@@ -360,6 +360,10 @@ int switch_keys_resident(lg_ckks_eval* e, lg_comm* c, int level, int batch, cons
             LG_TRY(lgi_swk_prepare(evk, QP, st));
             k.evk_f = evk->d_f;
             k.key_bad = evk->d_bad;
+            if (evk->has_map) {
+                k.h_keymap = evk->keymap;
+                k.h_fp_ok = evk->fp_ok.data();
+            }
         }
         k.D = D.d;
         k.d_ds = d_ds;

@@ -30,6 +30,14 @@ struct LgSwitches {
     // Measured (profiles/r02_ntt_l2_sweep.jsonl): the small grids cost more than the saved HBM pass -- 456 us for
     // 1088 limb-NTTs unsplit against 608 us at 96 MiB and 1040 us at 12..32 MiB.
     std::atomic<uint64_t> ntt_l2_bytes{0};
+    // LATTIGPU_KS_KEY_PF / LATTIGPU_TAIL_PF: software prefetch (prefetch.global.L1, one instruction per 128-byte line) of the
+    // key lines of the current digit in the fused digit loop, and of the ModDown / rescale tail operands in the last NTT
+    // phase, issued before the second register block; 0 = off (A/B).
+    std::atomic<int> ks_key_pf{0};
+    // LATTIGPU_NO_KS_TMA: every limb of the fused digit loop on ks_fused_kernel (keys through registers); default: the
+    // FP64-class limbs on ks_fused_tma_kernel (two batch entries per CTA, key tiles through shared memory by TMA)
+    std::atomic<int> no_ks_tma{0};
+    std::atomic<int> tail_pf{0};
 };
 LgSwitches& lg_switches();
 
@@ -88,6 +96,7 @@ struct NttArgs {
     int no_d64;                      // set by the launchers from the "no_d64_ntt" switch
     int batch0;                      // index of the launch's first batch entry in the caller's batch (tail addressing)
     int rev;                         // walk the grid backwards (second phases: read first what the first phase wrote last)
+    int pf;                          // prefetch the tail operands into L1 (set by the launcher from the "tail_pf" switch)
     NttTail tail;                    // forward only
     NttBcast bcast;                  // forward only
 };
@@ -120,8 +129,20 @@ struct KsFusedArgs {
     int acc64;            // 1 = never take the 96-bit accumulators (LATTIGPU_KS_ACC64=1: A/B and cross-check)
     int no_d64;           // set by the launcher from the "no_d64_ntt" switch
     int rev;              // walk the grid backwards (set by the launcher)
+    int pf;               // prefetch the key lines into L1 (set by the launcher from the "ks_key_pf" switch)
+    // blockIdx.z -> data limb (set by the launcher when it splits the limbs between ks_fused_kernel and ks_fused_tma_kernel)
+    int use_zl;
+    unsigned char zl[LG_MAX_LIMBS];
+    // host-side, read by the launcher only (both or neither): the TMA descriptor of evk_f (a CUtensorMap: rows of 16 words,
+    // 128-byte swizzle) and, per table limb, whether ks_fused_tma_kernel may take it (FP64-class modulus, every key word
+    // canonical); lgi_swk_prepare builds both
+    const void* h_keymap;
+    const unsigned char* h_fp_ok;
 };
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st);
+// CUtensorMap (128 bytes at `map`) of a key in FP64 form: `words` u64 at `keyf` seen as rows of 16 words, boxes of 128 rows
+// (one 2048-word tile), 128-byte swizzle.  0 = ok (needs a driver with cuTensorMapEncodeTiled)
+int lg_encode_key_tensor_map(void* map, const u64* keyf, size_t words);
 // keyf = double(InvMForm(key)) for the limbs with q < 3*2^44, bad[(digit*2+half)*nQP + tl] |= 1 when a word >= q
 int lg_launch_swk_prepare(const RingTables& T, const u64* key, u64* keyf, u32* bad, int beta, int nQP, cudaStream_t st);
 

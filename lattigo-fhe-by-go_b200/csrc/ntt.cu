@@ -25,6 +25,7 @@
 //                       consecutive words that move with 256-bit loads/stores.
 //   Twiddle index for the butterfly on (j, j+2^s): (N >> (s+1)) + (j >> (s+1))
 //   in both directions (ring/ntt.go:74 and :120).
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -59,6 +60,8 @@ LG_DEV void ld256(u64 (&v)[4], const u64* p) {
 LG_DEV void ld256_nc(u64 (&v)[4], const u64* p) {
     asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
 }
+LG_DEV void prefetch_l1(const u64* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+LG_DEV void prefetch_l2(const u64* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 LG_DEV void st256(u64* p, u64 a, u64 b, u64 c, u64 d) {
     asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
@@ -519,6 +522,16 @@ LG_DEV void contig_pipe_body(const NttArgs& a, const LimbConst& lc, int tl, int 
             for (int r = 0; r < 16; ++r) x[r] = buf[16 * cc + (r ^ cc)];
             __syncwarp();
             if (i + 1 < nb) prefetch_warp_tile(tilebuf, src + (size_t)(i + 1) * a.in_bstride);
+            if (TAIL && a.pf) {  // the thread's 16 words of a[] (and of out[] when it is added to) = one 128-byte line each
+                const int bi = a.batch0 + b0 + i, set = bi >= a.tail.split ? 1 : 0;
+                const size_t bb = (size_t)(bi - (set ? a.tail.split : 0));
+                const u64* ta = a.tail.a[set] + bb * a.tail.a_bs[set] + (size_t)j * (a.tail.a_ls ? a.tail.a_ls : N) + e0;
+                if (a.pf == 2) prefetch_l2(ta); else prefetch_l1(ta);
+                if (a.tail.add[set]) {
+                    const u64* to = a.tail.out[set] + bb * a.tail.out_bs[set] + (size_t)j * (a.tail.out_ls ? a.tail.out_ls : N) + e0;
+                    if (a.pf == 2) prefetch_l2(to); else prefetch_l1(to);
+                }
+            }
             fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp);
             if (TAIL) {
                 // the caller's (x - NTT(y)) * s_j tail (+ add) on the canonical transform, straight from the registers
@@ -703,11 +716,17 @@ LG_DEV void ks_load_keys(u64 (&k0)[16], u64 (&k1)[16], const u64* key, size_t hs
     }
 }
 
+// data limb of this CTA: blockIdx.z, through the launcher's list when the limbs are split between two kernels
+LG_DEV int ks_data_limb(const KsFusedArgs& a) {
+    const int z = a.rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    return a.use_zl ? (int)a.zl[z] : z;
+}
+
 // ACC_LAZY64: beta * 2q fits 64 bits, so the products are accumulated unreduced (MRedConstant, in (0,2q)).
 template <int MODE, int ACC>
 LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64* smem) {
     const u32 N = a.T.N;
-    const int j = a.rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    const int j = ks_data_limb(a);
     const int b = a.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
     const u64 q = lc.q, qinv = lc.qinv;
     const TwConst c = tw_const<true, MODE>(a.T, lc, tl);
@@ -753,6 +772,10 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
         u64 kk0[16], kk1[16];
         ks_load_keys(kk0, kk1, key, a.evk_hs);
 #endif
+        if (a.pf == 2) {  // at the top of the iteration instead
+            prefetch_l1(key);
+            prefetch_l1(key + a.evk_hs);
+        }
         if (i == own_i) {  // ckks/evaluator.go:1579-1584, bfv/evaluator.go:776-780
 #if KS_KEYPREFETCH == 1
             ks_load_keys(kk0, kk1, key, a.evk_hs);
@@ -787,6 +810,10 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
 #if KS_KEYPREFETCH == 1
             ks_load_keys(kk0, kk1, key, a.evk_hs);  // in flight during the second register block
 #endif
+            if (a.pf == 1) {  // the thread's 16 words of evk[i][0] and evk[i][1]: one 128-byte line each
+                prefetch_l1(key);
+                prefetch_l1(key + a.evk_hs);
+            }
             fwd_stages_sm<3, CONTIG_THREADS, MODE>(x, c, twp);
             if (MODE == M_D64) {  // doubles (|v| < 34q) -> the integers the multiply-accumulate takes
 #pragma unroll
@@ -862,7 +889,7 @@ LG_DEV u32 ks_fused_body(const KsFusedArgs& a, const LimbConst& lc, int tl, u64*
 template <bool LITERAL>
 __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const KsFusedArgs a) {
     extern __shared__ __align__(16) u64 ks_smem[];
-    const int tl = a.map(a.rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z);
+    const int tl = a.map(ks_data_limb(a));
     const LimbConst lc = load_limb_const(a.T, tl);
     const int mode = LITERAL ? M_LITERAL : fwd_mode(lc.q, a.no_d64);
     // beta lazy terms below 2q fit 64 bits (a term is below 2q when the key word has at most bits(q) bits: its product
@@ -908,6 +935,188 @@ __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const
         }
     } else {
         ks_fused_body<M_LITERAL, ACC_EXACT>(a, lc, tl, ks_smem);
+    }
+}
+
+// ---- fused digit loop, FP64-class limbs: two batch entries per CTA, key tiles by TMA ---------------------------------
+// ks_fused_kernel keeps the 32 key words of a digit in 64 registers (168 in all: 3 CTAs of 4 warps per SM) and waits for
+// them where the multiply-accumulate starts (ncu: 15 % of its stall samples sit on the first instruction that reads a key
+// word; software prefetch into L1 does not help, profiles/README.md).  This kernel is the ACC_FP path rebuilt around a
+// shared-memory key tile:
+//   * a 256-thread CTA takes the same (limb, tile) of TWO batch entries (threads 0..127 and 128..255): the tile's twiddles
+//     (32 KiB) and the digit's key tile (2 x 16 KiB) are staged once for both, so their L2 -> SM traffic halves;
+//   * the key tile of digit i arrives by TMA (cp.async.bulk.tensor.2d through a CUtensorMap of the key seen as rows of
+//     16 words, 128-byte swizzle: thread t then reads its 16 consecutive words -- row t of the box -- with eight
+//     conflict-free 128-bit loads) while the digit's transform runs; completion on an mbarrier (complete_tx), the buffer
+//     is handed back through a second mbarrier on which every warp arrives after its multiply-accumulate;
+//   * each warp fetches its 4 KiB of the next digit tile with one cp.async.bulk (instead of 256 cp.async of 16 bytes)
+//     onto its own mbarrier; single tile buffer per entry, re-filled as soon as the exchange has left it;
+//   * no key registers: 128 registers, 2 CTAs (16 warps) per SM instead of 12 warps.
+// shared memory from a 1024-byte aligned base: key tile 32 KiB | digit tiles 2 x 16 KiB | private twiddles 30 KiB |
+// segment twiddles 2 KiB | mbarriers
+#define KSF_GROUPS 2
+#define KSF_THREADS (KSF_GROUPS * CONTIG_THREADS)
+#define KSF_OFF_TILE 32768u
+#define KSF_OFF_TWP (KSF_OFF_TILE + KSF_GROUPS * 16384u)
+#define KSF_OFF_TWSEG (KSF_OFF_TWP + 30u * CONTIG_THREADS * 8u)
+#define KSF_OFF_BAR (KSF_OFF_TWSEG + 8u * 32u * 8u)
+#define KSF_SMEM_BYTES (KSF_OFF_BAR + 128u + 1024u)
+
+LG_DEV void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+LG_DEV void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+LG_DEV void mbar_arrive(u32 bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+LG_DEV bool mbar_try_wait(u32 bar, u32 parity) {
+    u32 ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// bounded: a transfer that never completes traps instead of hanging the device
+LG_DEV void mbar_wait(u32 bar, u32 parity) {
+    u32 n = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++n > (1u << 26)) __trap();
+}
+LG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+LG_DEV void tma_load_rows(u32 dst, const CUtensorMap* map, int row, u32 bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(0), "r"(row), "r"(bar)
+                 : "memory");
+}
+LG_DEV void bulk_load(u32 dst, const u64* src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFusedArgs a, const __grid_constant__ CUtensorMap kmap) {
+    extern __shared__ __align__(16) u64 ks_smem[];
+    const u32 raw = (u32)__cvta_generic_to_shared(ks_smem);
+    const u32 sbase = (raw + 1023u) & ~1023u;  // the swizzled key boxes want 1024-byte alignment
+    u64* const base = ks_smem + ((sbase - raw) >> 3);
+    const u32 N = a.T.N;
+    const int j = ks_data_limb(a);
+    const int tl = a.map(j);
+    const LimbConst lc = load_limb_const(a.T, tl);
+    const TwConst c = tw_const<true, M_D64>(a.T, lc, tl);
+    const u32 t = threadIdx.x, g = t >> 7, tt = t & 127u, warp = t >> 5, lane = t & 31u;
+    const u32 sg = tt >> 4, cc = tt & 15u;
+    const int batch = a.use_zl >> 8;  // the launcher packs the batch size above the flag
+    int b = (int)blockIdx.x * KSF_GROUPS + (int)g;
+    const bool active = b < batch;
+    if (!active) b = batch - 1;  // an odd batch: the second half of the last CTA repeats the last entry and does not store
+    const u32 tile0 = blockIdx.y * CONTIG_TILE;
+    const u32 segbase = tile0 + sg * 256u;
+    const u32 e0 = segbase + 16 * cc;
+    u64* const tilebuf = base + (KSF_OFF_TILE >> 3) + g * 2048u;
+    u64* const buf = tilebuf + sg * 256;
+    u64* const twp = base + (KSF_OFF_TWP >> 3) + 2 * tt;
+    u64* const twseg = base + (KSF_OFF_TWSEG >> 3) + sg * 32;
+    const u32 kbar_full = sbase + KSF_OFF_BAR, kbar_empty = kbar_full + 8, tbar = kbar_full + 16 + 8 * warp;
+    const u32 warp_tile = sbase + KSF_OFF_TILE + g * 16384u + (warp & 3u) * 4096u;  // the warp's two segments
+
+    const u64* din = a.D + (size_t)b * a.d_bs + (size_t)j * N + tile0 + (warp & 3u) * 512u;
+    const int own_i = (tl < a.nl) ? tl / a.alpha : -1;
+    const size_t key_row0 = ((size_t)tl * N + tile0) >> 4;  // row of the tile's first word within evk_f[0][0]
+    const u32 ds_rows = (u32)(a.evk_ds >> 4), hs_rows = (u32)(a.evk_hs >> 4);
+
+    if (t == 0) {
+        mbar_init(kbar_full, 1);
+        mbar_init(kbar_empty, KSF_THREADS / 32);
+        for (int w = 0; w < KSF_THREADS / 32; ++w) mbar_init(kbar_full + 16 + 8 * w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (g == 0) contig_fill_tw<M_D64>(c, N, segbase, cc, twp, twseg);  // twiddles of the tile, once for both entries and all digits
+    __syncthreads();
+    if (t == 0) {
+        mbar_expect_tx(kbar_full, 32768u);
+        tma_load_rows(sbase, &kmap, (int)key_row0, kbar_full);
+        tma_load_rows(sbase + 16384u, &kmap, (int)(key_row0 + hs_rows), kbar_full);
+    }
+    if (lane == 0 && own_i != 0) {
+        mbar_expect_tx(tbar, 4096u);
+        bulk_load(warp_tile, din, 4096u, tbar);
+    }
+    u32 tphase = 0;
+    double acc0[16], acc1[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc0[r] = acc1[r] = 0.0;
+    // the thread's row of the key boxes: 16-byte chunk p of row tt sits at chunk p ^ (tt & 7)
+    const u64* const krow = base + tt * 16u;
+    const u32 ksw = tt & 7u;
+#pragma unroll 1
+    for (int i = 0; i < a.beta; ++i) {
+        u64 x[16];
+        if (i == own_i) {  // ckks/evaluator.go:1579-1584, bfv/evaluator.go:776-780
+            const u64* cx = a.cx + (size_t)b * a.cx_bs + (size_t)j * (a.cx_ls ? a.cx_ls : N) + e0;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                u64 v[4];
+                ld256(v, cx + 4 * h);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[4 * h + e] = d2bits(u52_to_d(bred_add(v[e], lc.q, lc.u0), 4503599627370496.0));
+            }
+            if (i + 1 < a.beta && lane == 0) {  // the next digit's tile (nothing was in flight for this one)
+                mbar_expect_tx(tbar, 4096u);
+                bulk_load(warp_tile, din + (size_t)(i + 1) * a.d_ds, 4096u, tbar);
+            }
+        } else {
+            mbar_wait(tbar, tphase);
+            tphase ^= 1u;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = buf[cc + 16 * r];
+            fwd_stages_sm<3, 1, M_D64>(x, c, twseg);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) buf[16 * r + (cc ^ r)] = x[r];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = buf[16 * cc + (r ^ cc)];
+            __syncwarp();
+            if (i + 1 < a.beta && i + 1 != own_i && lane == 0) {  // the buffer is free: fetch the next digit's tile
+                fence_proxy_async();
+                mbar_expect_tx(tbar, 4096u);
+                bulk_load(warp_tile, din + (size_t)(i + 1) * a.d_ds, 4096u, tbar);
+            }
+            fwd_stages_sm<3, CONTIG_THREADS, M_D64>(x, c, twp);
+        }
+        mbar_wait(kbar_full, (u32)i & 1u);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(krow + 2u * (p ^ ksw));
+            const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(krow + 2048u + 2u * (p ^ ksw));
+            const double xa = bits2d(x[2 * p]), xb = bits2d(x[2 * p + 1]);
+            const double k0a = bits2d(k0.x), k0b = bits2d(k0.y), k1a = bits2d(k1.x), k1b = bits2d(k1.y);
+            acc0[2 * p] = __dadd_rn(acc0[2 * p], d64_mul(k0a, __dmul_rd(k0a, c.qinvd), xa, c.qd));
+            acc1[2 * p] = __dadd_rn(acc1[2 * p], d64_mul(k1a, __dmul_rd(k1a, c.qinvd), xa, c.qd));
+            acc0[2 * p + 1] = __dadd_rn(acc0[2 * p + 1], d64_mul(k0b, __dmul_rd(k0b, c.qinvd), xb, c.qd));
+            acc1[2 * p + 1] = __dadd_rn(acc1[2 * p + 1], d64_mul(k1b, __dmul_rd(k1b, c.qinvd), xb, c.qd));
+        }
+        // hand the key buffer back; thread 0 re-fills it with the next digit's tile once every warp has done so
+        __syncwarp();
+        if (lane == 0) mbar_arrive(kbar_empty);
+        if (t == 0 && i + 1 < a.beta) {
+            mbar_wait(kbar_empty, (u32)i & 1u);
+            fence_proxy_async();
+            mbar_expect_tx(kbar_full, 32768u);
+            const int row = (int)(key_row0 + (size_t)(i + 1) * ds_rows);
+            tma_load_rows(sbase, &kmap, row, kbar_full);
+            tma_load_rows(sbase + 16384u, &kmap, row + (int)hs_rows, kbar_full);
+        }
+    }
+    if (!active) return;
+    u64* o0 = a.acc0 + (size_t)b * a.acc_bs + (size_t)j * N + e0;
+    u64* o1 = a.acc1 + (size_t)b * a.acc_bs + (size_t)j * N + e0;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {  // |sum| < 18q
+        st256(o0 + 4 * h, d64_canon(d2bits(acc0[4 * h]), c), d64_canon(d2bits(acc0[4 * h + 1]), c), d64_canon(d2bits(acc0[4 * h + 2]), c),
+              d64_canon(d2bits(acc0[4 * h + 3]), c));
+        st256(o1 + 4 * h, d64_canon(d2bits(acc1[4 * h]), c), d64_canon(d2bits(acc1[4 * h + 1]), c), d64_canon(d2bits(acc1[4 * h + 2]), c),
+              d64_canon(d2bits(acc1[4 * h + 3]), c));
     }
 }
 
@@ -1149,6 +1358,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
         second.in_ls = args.out_ls;
         second.bcast.enabled = 0;
         second.rev = lg_switches().reverse_walk.load(std::memory_order_relaxed) ? 1 : 0;
+        second.pf = lg_switches().tail_pf.load(std::memory_order_relaxed);
         const dim3 grid(nb, N / 4096, nlimbs);
         if (!inverse) {
             launch_strided_any(L, true, literal, first, grid, st);
@@ -1181,16 +1391,72 @@ int lg_launch_range_flags(const NttArgs& args, int nlimbs, int batch, u32* flags
     return 0;
 }
 
+int lg_encode_key_tensor_map(void* map, const u64* keyf, size_t words) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            fn = nullptr;
+        }
+        return (EncodeFn)fn;
+    }();
+    if (!encode || words % 16 != 0 || (words >> 4) > 0x7fffffffull || ((uintptr_t)keyf & 15) != 0) return 1;
+    const cuuint64_t gdim[2] = {16, (cuuint64_t)(words >> 4)};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {16, 128};
+    const cuuint32_t estride[2] = {1, 1};
+    CUtensorMap m;
+    if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)keyf, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    memcpy(map, &m, sizeof(m));
+    return 0;
+}
+
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st) {
     if (nlimbs <= 0 || batch <= 0) return 0;
-    if (a.T.logN < 12 || a.T.logN > 16 || a.beta < 1) return 1;
-    const dim3 grid(batch, a.T.N / CONTIG_TILE, nlimbs);
+    if (a.T.logN < 12 || a.T.logN > 16 || a.beta < 1 || nlimbs > LG_MAX_LIMBS) return 1;
+    const u32 tiles = a.T.N / CONTIG_TILE;
     const size_t smem = KS_SMEM_WORDS * sizeof(u64);
     KsFusedArgs k = a;
     k.acc64 = lg_switches().ks_acc64.load(std::memory_order_relaxed) ? 1 : 0;
     k.no_d64 = lg_switches().no_d64_ntt.load(std::memory_order_relaxed) ? 1 : 0;
+    k.pf = lg_switches().ks_key_pf.load(std::memory_order_relaxed);
     k.rev = lg_switches().reverse_walk.load(std::memory_order_relaxed) ? 1 : 0;  // the strided phase wrote the high limbs last
-    if (literal_ntt()) {
+    k.use_zl = 0;
+    const bool literal = literal_ntt();
+    // FP64-class limbs whose key words are all canonical go to the TMA kernel, the others stay on ks_fused_kernel
+    int nfp = 0, nint = 0;
+    unsigned char zfp[LG_MAX_LIMBS], zint[LG_MAX_LIMBS];
+    const bool tma = a.h_keymap && a.h_fp_ok && a.evk_f && !literal && !k.acc64 && !k.no_d64 && a.beta <= 32 && batch < (1 << 20) &&
+                     (a.evk_ds % 16 == 0) && (a.evk_hs % 16 == 0) && !lg_switches().no_ks_tma.load(std::memory_order_relaxed);
+    for (int j = 0; j < nlimbs; ++j) {
+        if (tma && a.h_fp_ok[a.map(j)])
+            zfp[nfp++] = (unsigned char)j;
+        else
+            zint[nint++] = (unsigned char)j;
+    }
+    if (nfp > 0) {
+        KsFusedArgs f = k;
+        f.rev = 0;
+        f.use_zl = 1 | (batch << 8);
+        memcpy(f.zl, zfp, sizeof(f.zl));
+        CUtensorMap kmap;
+        memcpy(&kmap, a.h_keymap, sizeof(kmap));
+        lg_ensure_dyn_smem<ks_fused_tma_kernel>(KSF_SMEM_BYTES);
+        ks_fused_tma_kernel<<<dim3((batch + KSF_GROUPS - 1) / KSF_GROUPS, tiles, nfp), KSF_THREADS, KSF_SMEM_BYTES, st>>>(f, kmap);
+        lg_g_launches += 1;
+        if (nint == 0) return 0;
+        k.use_zl = 1;
+        memcpy(k.zl, zint, sizeof(k.zl));
+    }
+    const dim3 grid(batch, tiles, nint);
+    if (literal) {
         lg_ensure_dyn_smem<ks_fused_kernel<true>>(smem);
         ks_fused_kernel<true><<<grid, CONTIG_THREADS, smem, st>>>(k);
     } else {

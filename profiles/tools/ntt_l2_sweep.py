@@ -64,18 +64,20 @@ if len(sys.argv) > 2 and sys.argv[1] == "ab":  # interleaved A/B of 0/1 switches
 
     for _ in range(3):
         step()
-    for name in sys.argv[2:]:
-        acc = {0: {"fwd": [], "inv": [], "step": []}, 1: {"fwd": [], "inv": [], "step": []}}
+    for spec in sys.argv[2:]:  # <switch> (values 0 and 1) or <switch>:<a>:<b>
+        name, *vals = spec.split(":")
+        va, vb = (int(vals[0]), int(vals[1])) if vals else (0, 1)
+        acc = {va: {"fwd": [], "inv": [], "step": []}, vb: {"fwd": [], "inv": [], "step": []}}
         for rnd in range(8):
-            for val in ((0, 1) if rnd % 2 == 0 else (1, 0)):
+            for val in ((va, vb) if rnd % 2 == 0 else (vb, va)):
                 ring.debug_set_switch(name, val)
                 acc[val]["fwd"].append(timed(lambda: cQ.NTT(a[0], o[0], stream=sp), reps=5, warm=1))
                 acc[val]["inv"].append(timed(lambda: cQ.InvNTT(a[0], o[0], stream=sp), reps=5, warm=1))
                 acc[val]["step"].append(timed(step, reps=3, warm=1))
-        ring.debug_set_switch(name, 0)
-        print(json.dumps({"switch": name, "rounds": 8,
-                          "median_us": {str(v): {k: statistics.median(x) for k, x in acc[v].items()} for v in (0, 1)},
-                          "min_us": {str(v): {k: min(x) for k, x in acc[v].items()} for v in (0, 1)}}), flush=True)
+        ring.debug_set_switch(name, vb if vals else 0)
+        print(json.dumps({"switch": spec, "rounds": 8,
+                          "median_us": {str(v): {k: statistics.median(x) for k, x in acc[v].items()} for v in (va, vb)},
+                          "min_us": {str(v): {k: min(x) for k, x in acc[v].items()} for v in (va, vb)}}), flush=True)
     sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "rev":  # A/B of the backward grid walk of the second phases (ABAB)
     for norev in (1, 0, 1, 0):
