@@ -140,7 +140,7 @@ struct KsFusedArgs {
     const unsigned char* h_fp_ok;
 };
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st);
-// CUtensorMap (128 bytes at `map`) of a key in FP64 form: `words` u64 at `keyf` seen as rows of 16 words, boxes of 128 rows
+// CUtensorMap (128 bytes at `map`) of a key in FP64 form: `words` u64 at `keyf` seen as rows of 16 words, boxes of 32 rows
 // (one 2048-word tile), 128-byte swizzle.  0 = ok (needs a driver with cuTensorMapEncodeTiled)
 int lg_encode_key_tensor_map(void* map, const u64* keyf, size_t words);
 // keyf = double(InvMForm(key)) for the limbs with q < 3*2^44, bad[(digit*2+half)*nQP + tl] |= 1 when a word >= q

@@ -946,9 +946,9 @@ __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const
 //   * a 256-thread CTA takes the same (limb, tile) of TWO batch entries (threads 0..127 and 128..255): the tile's twiddles
 //     (32 KiB) and the digit's key tile (2 x 16 KiB) are staged once for both, so their L2 -> SM traffic halves;
 //   * the key tile of digit i arrives by TMA (cp.async.bulk.tensor.2d through a CUtensorMap of the key seen as rows of
-//     16 words, 128-byte swizzle: thread t then reads its 16 consecutive words -- row t of the box -- with eight
-//     conflict-free 128-bit loads) while the digit's transform runs; completion on an mbarrier (complete_tx), the buffer
-//     is handed back through a second mbarrier on which every warp arrives after its multiply-accumulate;
+//     16 words, 128-byte swizzle: thread t then reads its 16 consecutive words -- row t of the tile -- with eight
+//     conflict-free 128-bit loads) while the digit's transform runs, in boxes of 32 rows: the two warps that read the same
+//     rows (warp w of either entry) own a full / empty mbarrier pair, so no warp waits for more than its partner;
 //   * each warp fetches its 4 KiB of the next digit tile with one cp.async.bulk (instead of 256 cp.async of 16 bytes)
 //     onto its own mbarrier; single tile buffer per entry, re-filled as soon as the exchange has left it;
 //   * no key registers: 128 registers, 2 CTAs (16 warps) per SM instead of 12 warps.
@@ -975,10 +975,19 @@ LG_DEV bool mbar_try_wait(u32 bar, u32 parity) {
                  : "memory");
     return ok != 0;
 }
+// with a suspend-time hint (ns): the thread may sleep in the instruction instead of spinning through the loop around it
+LG_DEV bool mbar_try_wait_hint(u32 bar, u32 parity, u32 ns) {
+    u32 ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity), "r"(ns)
+                 : "memory");
+    return ok != 0;
+}
 // bounded: a transfer that never completes traps instead of hanging the device
-LG_DEV void mbar_wait(u32 bar, u32 parity) {
+LG_DEV void mbar_wait(u32 bar, u32 parity, bool hint = false) {
     u32 n = 0;
-    while (!mbar_try_wait(bar, parity))
+    while (!(hint ? mbar_try_wait_hint(bar, parity, 2000u) : mbar_try_wait(bar, parity)))
         if (++n > (1u << 26)) __trap();
 }
 LG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -1016,7 +1025,13 @@ __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFu
     u64* const buf = tilebuf + sg * 256;
     u64* const twp = base + (KSF_OFF_TWP >> 3) + 2 * tt;
     u64* const twseg = base + (KSF_OFF_TWSEG >> 3) + sg * 32;
-    const u32 kbar_full = sbase + KSF_OFF_BAR, kbar_empty = kbar_full + 8, tbar = kbar_full + 16 + 8 * warp;
+    // key hand-off per warp pair (warp wq of either entry reads rows 32wq .. 32wq+31 of both boxes): full / empty barriers
+    // a.pf (the "ks_key_pf" switch, A/B): bit 0 = suspend-time hint on the key wait, bit 1 = one full / empty pair for the
+    // whole CTA (every warp waits for the slowest) instead of one per warp pair
+    const bool hint = (a.pf & 1) != 0, cta_wide = (a.pf & 2) != 0;
+    const u32 wq = cta_wide ? 0u : (warp & 3u);
+    const u32 bars = sbase + KSF_OFF_BAR, kbar_full = bars + 8 * wq, kbar_empty = bars + 32 + 8 * wq, tbar = bars + 64 + 8 * warp;
+    const u32 kdst = sbase + wq * 4096u;  // the pair's rows of the evk[i][0] box; evk[i][1] 16 KiB further
     const u32 warp_tile = sbase + KSF_OFF_TILE + g * 16384u + (warp & 3u) * 4096u;  // the warp's two segments
 
     const u64* din = a.D + (size_t)b * a.d_bs + (size_t)j * N + tile0 + (warp & 3u) * 512u;
@@ -1025,17 +1040,24 @@ __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFu
     const u32 ds_rows = (u32)(a.evk_ds >> 4), hs_rows = (u32)(a.evk_hs >> 4);
 
     if (t == 0) {
-        mbar_init(kbar_full, 1);
-        mbar_init(kbar_empty, KSF_THREADS / 32);
-        for (int w = 0; w < KSF_THREADS / 32; ++w) mbar_init(kbar_full + 16 + 8 * w, 1);
+        for (int w = 0; w < 4; ++w) {
+            mbar_init(bars + 8 * w, 1);
+            mbar_init(bars + 32 + 8 * w, cta_wide ? KSF_THREADS / 32 : KSF_GROUPS);
+        }
+        for (int w = 0; w < KSF_THREADS / 32; ++w) mbar_init(bars + 64 + 8 * w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (g == 0) contig_fill_tw<M_D64>(c, N, segbase, cc, twp, twseg);  // twiddles of the tile, once for both entries and all digits
     __syncthreads();
-    if (t == 0) {
-        mbar_expect_tx(kbar_full, 32768u);
-        tma_load_rows(sbase, &kmap, (int)key_row0, kbar_full);
-        tma_load_rows(sbase + 16384u, &kmap, (int)(key_row0 + hs_rows), kbar_full);
+    const int krow0 = (int)key_row0 + 32 * (int)wq;
+    const int nbox = cta_wide ? 4 : 1;                                        // boxes of 32 rows per half
+    const bool mover = cta_wide ? (t == 0) : (g == 0 && lane == 0);           // the first entry's warp of each pair moves its rows
+    if (mover) {
+        mbar_expect_tx(kbar_full, 8192u * nbox);
+        for (int bx = 0; bx < nbox; ++bx) {
+            tma_load_rows(kdst + 4096u * bx, &kmap, krow0 + 32 * bx, kbar_full);
+            tma_load_rows(kdst + 4096u * bx + 16384u, &kmap, krow0 + 32 * bx + (int)hs_rows, kbar_full);
+        }
     }
     if (lane == 0 && own_i != 0) {
         mbar_expect_tx(tbar, 4096u);
@@ -1084,7 +1106,7 @@ __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFu
             }
             fwd_stages_sm<3, CONTIG_THREADS, M_D64>(x, c, twp);
         }
-        mbar_wait(kbar_full, (u32)i & 1u);
+        mbar_wait(kbar_full, (u32)i & 1u, hint);
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
             const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(krow + 2u * (p ^ ksw));
@@ -1096,16 +1118,20 @@ __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFu
             acc0[2 * p + 1] = __dadd_rn(acc0[2 * p + 1], d64_mul(k0b, __dmul_rd(k0b, c.qinvd), xb, c.qd));
             acc1[2 * p + 1] = __dadd_rn(acc1[2 * p + 1], d64_mul(k1b, __dmul_rd(k1b, c.qinvd), xb, c.qd));
         }
-        // hand the key buffer back; thread 0 re-fills it with the next digit's tile once every warp has done so
+        // hand the pair's key rows back; the first entry's warp re-fills them with the next digit's once both have done so
         __syncwarp();
-        if (lane == 0) mbar_arrive(kbar_empty);
-        if (t == 0 && i + 1 < a.beta) {
-            mbar_wait(kbar_empty, (u32)i & 1u);
-            fence_proxy_async();
-            mbar_expect_tx(kbar_full, 32768u);
-            const int row = (int)(key_row0 + (size_t)(i + 1) * ds_rows);
-            tma_load_rows(sbase, &kmap, row, kbar_full);
-            tma_load_rows(sbase + 16384u, &kmap, row + (int)hs_rows, kbar_full);
+        if (lane == 0) {
+            mbar_arrive(kbar_empty);
+            if (mover && i + 1 < a.beta) {
+                mbar_wait(kbar_empty, (u32)i & 1u);
+                fence_proxy_async();
+                mbar_expect_tx(kbar_full, 8192u * nbox);
+                const int row = krow0 + (i + 1) * (int)ds_rows;
+                for (int bx = 0; bx < nbox; ++bx) {
+                    tma_load_rows(kdst + 4096u * bx, &kmap, row + 32 * bx, kbar_full);
+                    tma_load_rows(kdst + 4096u * bx + 16384u, &kmap, row + 32 * bx + (int)hs_rows, kbar_full);
+                }
+            }
         }
     }
     if (!active) return;
@@ -1407,7 +1433,7 @@ int lg_encode_key_tensor_map(void* map, const u64* keyf, size_t words) {
     if (!encode || words % 16 != 0 || (words >> 4) > 0x7fffffffull || ((uintptr_t)keyf & 15) != 0) return 1;
     const cuuint64_t gdim[2] = {16, (cuuint64_t)(words >> 4)};
     const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {16, 128};
+    const cuuint32_t box[2] = {16, 32};  // a warp pair's 32 rows of a 2048-word tile
     const cuuint32_t estride[2] = {1, 1};
     CUtensorMap m;
     if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)keyf, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,

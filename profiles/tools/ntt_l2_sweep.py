@@ -68,16 +68,21 @@ if len(sys.argv) > 2 and sys.argv[1] == "ab":  # interleaved A/B of 0/1 switches
         name, *vals = spec.split(":")
         va, vb = (int(vals[0]), int(vals[1])) if vals else (0, 1)
         acc = {va: {"fwd": [], "inv": [], "step": []}, vb: {"fwd": [], "inv": [], "step": []}}
-        for rnd in range(8):
+        rounds = int(os.environ.get("AB_ROUNDS", "8"))
+        step_only = os.environ.get("AB_STEP_ONLY", "0") == "1"
+        for rnd in range(rounds):
             for val in ((va, vb) if rnd % 2 == 0 else (vb, va)):
                 ring.debug_set_switch(name, val)
-                acc[val]["fwd"].append(timed(lambda: cQ.NTT(a[0], o[0], stream=sp), reps=5, warm=1))
-                acc[val]["inv"].append(timed(lambda: cQ.InvNTT(a[0], o[0], stream=sp), reps=5, warm=1))
-                acc[val]["step"].append(timed(step, reps=3, warm=1))
+                if not step_only:
+                    acc[val]["fwd"].append(timed(lambda: cQ.NTT(a[0], o[0], stream=sp), reps=5, warm=1))
+                    acc[val]["inv"].append(timed(lambda: cQ.InvNTT(a[0], o[0], stream=sp), reps=5, warm=1))
+                acc[val]["step"].append(timed(step, reps=5 if step_only else 3, warm=1))
         ring.debug_set_switch(name, vb if vals else 0)
-        print(json.dumps({"switch": spec, "rounds": 8,
-                          "median_us": {str(v): {k: statistics.median(x) for k, x in acc[v].items()} for v in (va, vb)},
-                          "min_us": {str(v): {k: min(x) for k, x in acc[v].items()} for v in (va, vb)}}), flush=True)
+        diffs = [y / x - 1.0 for x, y in zip(acc[va]["step"], acc[vb]["step"])]  # per round: step(vb) / step(va) - 1
+        print(json.dumps({"switch": spec, "rounds": rounds,
+                          "median_us": {str(v): {k: statistics.median(x) for k, x in acc[v].items() if x} for v in (va, vb)},
+                          "min_us": {str(v): {k: min(x) for k, x in acc[v].items() if x} for v in (va, vb)},
+                          "step_rel_median": statistics.median(diffs), "step_rel_quartiles": statistics.quantiles(diffs, n=4)}), flush=True)
     sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "rev":  # A/B of the backward grid walk of the second phases (ABAB)
     for norev in (1, 0, 1, 0):
