@@ -59,6 +59,16 @@ def step():
     ev.Rescale(nQ, o, 1, stream=sp)
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "time":  # one library (LATTIGPU_LIB): median / min step and transform times
+    import statistics
+
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+    st = [timed(step, reps=5, warm=1) for _ in range(n)]
+    fw = [timed(lambda: cQ.NTT(a[0], o[0], stream=sp), reps=5, warm=1) for _ in range(n)]
+    iv = [timed(lambda: cQ.InvNTT(a[0], o[0], stream=sp), reps=5, warm=1) for _ in range(n)]
+    print(json.dumps({"lib": os.environ.get("LATTIGPU_LIB", "default"), "step_us": statistics.median(st), "step_min_us": min(st),
+                      "fwd_us": statistics.median(fw), "inv_us": statistics.median(iv)}), flush=True)
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[1] == "ab":  # interleaved A/B of 0/1 switches: python ntt_l2_sweep.py ab <switch> [<switch> ...]
     import statistics
 
