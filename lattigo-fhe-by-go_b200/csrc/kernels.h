@@ -37,6 +37,10 @@ struct LgSwitches {
     // LATTIGPU_NO_KS_TMA: every limb of the fused digit loop on ks_fused_kernel (keys through registers); default: the
     // FP64-class limbs on ks_fused_tma_kernel (two batch entries per CTA, key tiles through shared memory by TMA)
     std::atomic<int> no_ks_tma{0};
+    // LATTIGPU_TILE_FASTEST=0: the strided NTT phases walk the batch entries fastest; default 1: the tiles of a limb fastest
+    // (adjacent 128-byte columns in flight together).  Measured (profiles/r02_tile_fastest_ab.jsonl, 16 interleaved rounds):
+    // forward / inverse limb-NTT -1.3 % / -1.1 %, step -0.5 %.
+    std::atomic<int> tile_fastest{1};
     std::atomic<int> tail_pf{0};
 };
 LgSwitches& lg_switches();
@@ -96,6 +100,7 @@ struct NttArgs {
     int no_d64;                      // set by the launchers from the "no_d64_ntt" switch
     int batch0;                      // index of the launch's first batch entry in the caller's batch (tail addressing)
     int rev;                         // walk the grid backwards (second phases: read first what the first phase wrote last)
+    int tfast;                       // strided phases: tile index fastest (set by the launcher from the "tile_fastest" switch)
     int pf;                          // prefetch the tail operands into L1 (set by the launcher from the "tail_pf" switch)
     NttTail tail;                    // forward only
     NttBcast bcast;                  // forward only

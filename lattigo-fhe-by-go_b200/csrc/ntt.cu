@@ -253,8 +253,17 @@ LG_DEV void fill_strided_tw(u64* tws_sm, const TwConst& c) {
 
 // CTAs are dispatched in blockIdx order (x fastest, z slowest).  A launch that reads what the previous launch wrote can
 // walk its grid backwards (NttArgs::rev): the data written last -- still in L2 -- is then read first.
-LG_DEV int cta_x(const NttArgs& a) { return a.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x; }
-LG_DEV int cta_y(const NttArgs& a) { return a.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y; }
+// NttArgs::tfast (strided phases): the tile index is the fastest grid dimension instead of the batch index, so the CTAs
+// in flight together read and write ADJACENT 128-byte columns of the same rows (whole 2 KiB rows of the limb): DRAM page
+// locality for a launch that is HBM-bound.
+LG_DEV int cta_x(const NttArgs& a) {  // batch index
+    if (a.tfast) return a.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    return a.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+}
+LG_DEV int cta_y(const NttArgs& a) {  // tile index
+    if (a.tfast) return a.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    return a.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+}
 LG_DEV int cta_z(const NttArgs& a) { return a.rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z; }
 
 struct LimbSetup {
@@ -1296,7 +1305,10 @@ void launch_strided(bool fwd, bool literal, const NttArgs& a, dim3 grid, cudaStr
     }
 }
 
-void launch_strided_any(int L, bool fwd, bool literal, const NttArgs& a, dim3 grid, cudaStream_t st) {
+void launch_strided_any(int L, bool fwd, bool literal, const NttArgs& a0, dim3 grid, cudaStream_t st) {
+    NttArgs a = a0;
+    a.tfast = (lg_switches().tile_fastest.load(std::memory_order_relaxed) && grid.x <= 65535u) ? 1 : 0;
+    if (a.tfast) grid = dim3(grid.y, grid.x, grid.z);
     switch (L) {
         case 4: launch_strided<4>(fwd, literal, a, grid, st); break;
         case 5: launch_strided<5>(fwd, literal, a, grid, st); break;
