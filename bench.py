@@ -552,7 +552,9 @@ def run_gpu(args):
     # INT-side ceiling: register-resident butterfly rates measured on this GPU (profiles/microbench/
     # fast_butterfly.cu, profiles/r01_butterfly_peaks.txt): FP64-quotient butterfly for moduli below 3*2^44,
     # the 16-instruction Shoup butterfly below 2^56, the [0,8q) butterfly above
-    peak_bf = {"f64": 1.584e12, "free": 1.151e12, "lazy": 0.950e12}
+    # (round 2: the limbs below 3*2^44 run the 8-instruction FP64-only butterfly, 2.074e12/s register-resident,
+    # profiles/r02_fp64_butterfly.txt -- the ceiling moves up with the shorter instruction sequence)
+    peak_bf = {"f64": 2.074e12, "free": 1.151e12, "lazy": 0.950e12}
     mix = {"f64": sum(1 for q in Q if q < (3 << 44)), "free": sum(1 for q in Q if (3 << 44) <= q < (1 << 56)),
            "lazy": sum(1 for q in Q if q >= (1 << 56))}
     bf_per_limb = (N // 2) * p["LogN"]
@@ -566,11 +568,14 @@ def run_gpu(args):
         "bound": "int", "kernel": "ntt_fwd (strided phase + pipelined contiguous phase, one batched limb-NTT launch pair)",
         "achieved": bf_rate / 1e9, "peak": bf_peak / 1e9, "unit": "Gbutterfly/s", "frac": bf_rate / bf_peak,
         "traffic": traffic, "limb_mix": mix,
-        "peak_source": "profiles/r01_butterfly_peaks.txt (register-resident butterfly microbenchmark on B200, weighted by "
-                       "the limb mix); tensor cores unused: exact 64-bit modular integer arithmetic",
+        "peak_source": "profiles/r02_fp64_butterfly.txt + profiles/r01_butterfly_peaks.txt (register-resident butterfly "
+                       "microbenchmarks on B200 of the instruction sequences shipped, weighted by the limb mix); tensor "
+                       "cores unused: exact 64-bit modular integer arithmetic",
         "algorithmic_bytes_per_launch": alg_bytes, "limb_ntts_per_launch": nlimbs_launch, "launch_us": fwd_us,
         "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
-                "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None},
+                "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+                # the two-phase transform passes through HBM twice: on the DRAM bytes ncu saw it runs at this fraction of peak
+                "dram_frac": (traffic / (fwd_us * 1e-6) / 1e9 / hbm_peak) if traffic else None},
     }
 
     # ---- op-level roofline, SURVEY.md 8(d): max(INT work / INT peak, compulsory bytes / HBM peak) over the measured

@@ -50,6 +50,7 @@ LgSwitches& lg_switches() {
         if (const char* e = getenv("LATTIGPU_TAIL_PF")) sw.tail_pf = atoi(e);
         if (const char* e = getenv("LATTIGPU_KS_SCRATCH_WORDS")) sw.ks_scratch_words = strtoull(e, nullptr, 10);
         if (const char* e = getenv("LATTIGPU_NTT_L2_BYTES")) sw.ntt_l2_bytes = strtoull(e, nullptr, 10);
+        if (const char* e = getenv("LATTIGPU_NTT_L2_STREAMS")) sw.ntt_l2_streams = atoi(e);
     });
     return sw;
 }
@@ -131,6 +132,7 @@ int lg_debug_set_switch(const char* name, uint64_t value) {
     else if (!strcmp(name, "tail_pf")) sw.tail_pf = (int)value;
     else if (!strcmp(name, "ks_scratch_words")) sw.ks_scratch_words = value ? value : ((uint64_t)6 << 27);
     else if (!strcmp(name, "ntt_l2_bytes")) sw.ntt_l2_bytes = value;
+    else if (!strcmp(name, "ntt_l2_streams")) sw.ntt_l2_streams = (int)value;
     else {
         lg_set_error("lg_debug_set_switch: unknown switch '%s'", name);
         return LG_ERR_ARG;

@@ -30,6 +30,7 @@ struct LgSwitches {
     // Measured (profiles/r02_ntt_l2_sweep.jsonl): the small grids cost more than the saved HBM pass -- 456 us for
     // 1088 limb-NTTs unsplit against 608 us at 96 MiB and 1040 us at 12..32 MiB.
     std::atomic<uint64_t> ntt_l2_bytes{0};
+    std::atomic<int> ntt_l2_streams{0};  // LATTIGPU_NTT_L2_STREAMS: the groups alternate between two auxiliary streams
     // LATTIGPU_KS_KEY_PF / LATTIGPU_TAIL_PF: software prefetch (prefetch.global.L1, one instruction per 128-byte line) of the
     // key lines of the current digit in the fused digit loop, and of the ModDown / rescale tail operands in the last NTT
     // phase, issued before the second register block; 0 = off (A/B).

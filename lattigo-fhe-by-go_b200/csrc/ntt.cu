@@ -1351,6 +1351,32 @@ void launch_contig_pipe(bool fwd, bool literal, const NttArgs& a, int nlimbs, in
 
 bool literal_ntt() { return lg_switches().literal_ntt.load(std::memory_order_relaxed) != 0; }
 
+// auxiliary streams of the L2-grouped transform, one set per (host thread, device)
+struct NttAux {
+    cudaStream_t s[2];
+    cudaEvent_t fork, join[2];
+};
+NttAux* ntt_aux() {
+    thread_local NttAux* per_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!per_dev[dev]) {
+        NttAux* a = new NttAux;
+        bool ok = cudaEventCreateWithFlags(&a->fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; ++k)
+            ok = cudaStreamCreateWithFlags(&a->s[k], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&a->join[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            delete a;
+            return nullptr;
+        }
+        per_dev[dev] = a;
+    }
+    return per_dev[dev];
+}
+
 }  // namespace
 
 int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cudaStream_t st) {
@@ -1382,7 +1408,66 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
         if (cb > batch) cb = batch;
     }
     (void)sgrid;
-    for (int g0 = 0; g0 < batch; g0 += cb) {
+    // "ntt_l2_streams" = 2: groups of LIMBS over the whole batch instead (plain transforms only) -- the contiguous phase
+    // keeps its eight batch entries per CTA and a group touches the twiddles of its own limbs alone
+    if (l2_bytes && lg_switches().ntt_l2_streams.load(std::memory_order_relaxed) == 2 && !args.tail.enabled && !args.bcast.enabled &&
+        !args.flags && args.skip_alpha == 0 && args.skip0 >= args.skip1) {
+        int cl = (int)(l2_bytes / ((size_t)batch * N * sizeof(u64)));
+        if (cl < 1) cl = 1;
+        if (cl < nlimbs) {
+            NttAux* aux = ntt_aux();
+            if (aux) {
+                cudaEventRecord(aux->fork, st);
+                for (int k = 0; k < 2; ++k) cudaStreamWaitEvent(aux->s[k], aux->fork, 0);
+            }
+            int gi = 0;
+            for (int j0 = 0; j0 < nlimbs; j0 += cl, ++gi) {
+                cudaStream_t gs = aux ? aux->s[gi & 1] : st;
+                const int nj = (nlimbs - j0) < cl ? (nlimbs - j0) : cl;
+                NttArgs first = args;
+                first.no_d64 = lg_switches().no_d64_ntt.load(std::memory_order_relaxed) ? 1 : 0;
+                first.in = args.in + (size_t)j0 * (args.in_ls ? args.in_ls : N);
+                first.out = args.out + (size_t)j0 * (args.out_ls ? args.out_ls : N);
+                const LimbMap m = args.map;
+                first.map.n0 = m.n0 > j0 ? m.n0 - j0 : 0;
+                first.map.l0 = m.l0 + j0 * m.st;
+                first.map.l1 = j0 > m.n0 ? m.l1 + (j0 - m.n0) * m.st : m.l1;
+                NttArgs second = first;
+                second.in = first.out;
+                second.in_bstride = args.out_bstride;
+                second.in_ls = args.out_ls;
+                second.rev = 0;
+                second.pf = 0;
+                const dim3 grid(batch, N / 4096, nj);
+                if (!inverse) {
+                    launch_strided_any(L, true, literal, first, grid, gs);
+                    launch_contig_pipe(true, literal, second, nj, batch, gs);
+                } else {
+                    launch_contig_pipe(false, literal, first, nj, batch, gs);
+                    launch_strided_any(L, false, literal, second, grid, gs);
+                }
+                lg_g_launches += 2;
+            }
+            if (aux) {
+                for (int k = 0; k < 2; ++k) {
+                    cudaEventRecord(aux->join[k], aux->s[k]);
+                    cudaStreamWaitEvent(st, aux->join[k], 0);
+                }
+            }
+            return 0;
+        }
+    }
+    // With L2-sized groups the launch pairs of consecutive groups go to two auxiliary streams in turn, so that the tail of
+    // one group's kernels overlaps the next group's (the groups are independent); `st` forks into them and joins them.
+    const bool fork = cb < batch && lg_switches().ntt_l2_streams.load(std::memory_order_relaxed) != 0;
+    NttAux* aux = fork ? ntt_aux() : nullptr;
+    if (aux) {
+        cudaEventRecord(aux->fork, st);
+        for (int k = 0; k < 2; ++k) cudaStreamWaitEvent(aux->s[k], aux->fork, 0);
+    }
+    int gi = 0;
+    for (int g0 = 0; g0 < batch; g0 += cb, ++gi) {
+        cudaStream_t gs = aux ? aux->s[gi & 1] : st;
         const int nb = (batch - g0) < cb ? (batch - g0) : cb;
         NttArgs first = args;
         first.no_d64 = lg_switches().no_d64_ntt.load(std::memory_order_relaxed) ? 1 : 0;
@@ -1399,13 +1484,19 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
         second.pf = lg_switches().tail_pf.load(std::memory_order_relaxed);
         const dim3 grid(nb, N / 4096, nlimbs);
         if (!inverse) {
-            launch_strided_any(L, true, literal, first, grid, st);
-            launch_contig_pipe(true, literal, second, nlimbs, nb, st);
+            launch_strided_any(L, true, literal, first, grid, gs);
+            launch_contig_pipe(true, literal, second, nlimbs, nb, gs);
         } else {
-            launch_contig_pipe(false, literal, first, nlimbs, nb, st);
-            launch_strided_any(L, false, literal, second, grid, st);
+            launch_contig_pipe(false, literal, first, nlimbs, nb, gs);
+            launch_strided_any(L, false, literal, second, grid, gs);
         }
         lg_g_launches += 2;
+    }
+    if (aux) {
+        for (int k = 0; k < 2; ++k) {
+            cudaEventRecord(aux->join[k], aux->s[k]);
+            cudaStreamWaitEvent(st, aux->join[k], 0);
+        }
     }
     return 0;
 }
