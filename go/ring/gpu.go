@@ -303,6 +303,47 @@ func (g *GPUContext) BitReverse(p1, p2 *GPUPoly) {
 	must(C.lg_ring_bitreverse(g.h, g.all(), p1.h, p2.h, g.st()))
 }
 
+// MulPoly, MulPolyMontgomery: ring.go:358-380; MulPolyNaive, MulPolyNaiveMontgomery: ring.go:383-437
+func (g *GPUContext) MulPoly(p1, p2, p3 *GPUPoly) {
+	must(C.lg_ring_mul_poly(g.h, p1.h, p2.h, p3.h, 0, g.st()))
+}
+func (g *GPUContext) MulPolyMontgomery(p1, p2, p3 *GPUPoly) {
+	must(C.lg_ring_mul_poly(g.h, p1.h, p2.h, p3.h, 1, g.st()))
+}
+func (g *GPUContext) MulPolyNaive(p1, p2, p3 *GPUPoly) {
+	must(C.lg_ring_mul_poly_naive(g.h, p1.h, p2.h, p3.h, 0, g.st()))
+}
+func (g *GPUContext) MulPolyNaiveMontgomery(p1, p2, p3 *GPUPoly) {
+	must(C.lg_ring_mul_poly_naive(g.h, p1.h, p2.h, p3.h, 1, g.st()))
+}
+
+// Exp: ring.go:441-464 (p1 is left in the NTT domain and p2 ends as InvNTT(p1), as the reference's last line does)
+func (g *GPUContext) Exp(p1 *GPUPoly, e uint64, p2 *GPUPoly) {
+	must(C.lg_ring_exp(g.h, p1.h, C.uint64_t(e), p2.h, g.st()))
+}
+
+// Shift: ring.go:575-580
+func (g *GPUContext) Shift(p1 *GPUPoly, n uint64, p2 *GPUPoly) {
+	must(C.lg_ring_shift(g.h, p1.h, C.uint64_t(n), p2.h, g.st()))
+}
+
+// Rotate: ring.go:775-800 (the reference writes p1's coefficients; p2 is never touched)
+func (g *GPUContext) Rotate(p1 *GPUPoly, n uint64, p2 *GPUPoly) {
+	must(C.lg_ring_rotate(g.h, p1.h, C.uint64_t(n), g.st()))
+}
+
+// Equal, EqualLvl: ring_context.go:424-467 (both operands are reduced in place; the call synchronises the stream)
+func (g *GPUContext) Equal(p1, p2 *GPUPoly) bool {
+	var eq C.int
+	must(C.lg_ring_equal(g.h, g.all(), p1.h, p2.h, &eq, g.st()))
+	return eq != 0
+}
+func (g *GPUContext) EqualLvl(level uint64, p1, p2 *GPUPoly) bool {
+	var eq C.int
+	must(C.lg_ring_equal(g.h, C.int(level+1), p1.h, p2.h, &eq, g.st()))
+	return eq != 0
+}
+
 // Mod, AND, OR, XOR: ring.go:146-184
 func (g *GPUContext) Mod(p1 *GPUPoly, m uint64, p2 *GPUPoly) {
 	must(C.lg_ring_mod(g.h, g.all(), p1.h, C.uint64_t(m), p2.h, g.st()))

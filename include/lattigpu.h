@@ -185,6 +185,19 @@ int lg_ring_mult_by_monomial(const lg_ring* r, int nl, const lg_poly* p1, uint64
 int lg_ring_mul_by_vector_montgomery(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* vec, lg_poly* p2, lg_stream_t s);               /* :726-734 */
 int lg_ring_mul_by_vector_montgomery_and_add_nomod(const lg_ring* r, int nl, const lg_poly* p1, const lg_poly* vec, lg_poly* p2, lg_stream_t s); /* :737-745 */
 int lg_ring_bitreverse(const lg_ring* r, int nl, const lg_poly* p1, lg_poly* p2, lg_stream_t s);                          /* :749-772 (p1 != p2) */
+/* The rest of ring.Context's method set (not on the evaluator path; csrc/ringext.cu).  All of them act on every limb of the
+ * context, as the reference's do.  MulPoly :358-367 / MulPolyMontgomery :371-380 (montgomery != 0): p3 = InvNTT(MulCoeffs(NTT(p1),
+ * NTT(p2))).  MulPolyNaive :383-410 / MulPolyNaiveMontgomery :413-437 (montgomery != 0): the N^2 negacyclic convolution.
+ * Exp :441-464 keeps the reference's ending (p1 is left in the NTT domain, p2 = InvNTT(p1)).  Shift :575-580: p2[k] =
+ * p1[(k + n) mod N], LG_ERR_ARG where Go's slice expression panics (n > N).  Rotate :775-800 multiplies coefficient j >= 1 of
+ * p1 by root^j IN p1 (the reference never writes p2).  Equal :424-446 / EqualLvl :449-467 (nl = level + 1) reduce both
+ * operands in place and synchronise the stream: *equal = 1 when every word agrees. */
+int lg_ring_mul_poly(const lg_ring* r, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, int montgomery, lg_stream_t s);
+int lg_ring_mul_poly_naive(const lg_ring* r, const lg_poly* p1, const lg_poly* p2, lg_poly* p3, int montgomery, lg_stream_t s);
+int lg_ring_exp(const lg_ring* r, lg_poly* p1, uint64_t e, lg_poly* p2, lg_stream_t s);
+int lg_ring_shift(const lg_ring* r, const lg_poly* p1, uint64_t n, lg_poly* p2, lg_stream_t s);
+int lg_ring_rotate(const lg_ring* r, lg_poly* p1, uint64_t n, lg_stream_t s);
+int lg_ring_equal(const lg_ring* r, int nl, lg_poly* p1, lg_poly* p2, int* equal, lg_stream_t s);
 
 /* ---- Galois automorphisms, ring/ring_galois.go ----------------------------- */
 int lg_galois_create(uint64_t gen, uint64_t power, uint64_t N, lg_galois** out);           /* PermuteNTTIndex :29-50 */

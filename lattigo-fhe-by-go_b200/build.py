@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "liblattigpu.so")
-SOURCES = ["capi.cu", "capi_ext.cu", "capi_bfv.cu", "capi_shard.cu", "ntt.cu", "elementwise.cu", "permute.cu", "basisext.cu", "keyswitch.cu", "crp.cu", "scaler.cu"]
+SOURCES = ["capi.cu", "ringext.cu", "capi_ext.cu", "capi_bfv.cu", "capi_shard.cu", "ntt.cu", "elementwise.cu", "permute.cu", "basisext.cu", "keyswitch.cu", "crp.cu", "scaler.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2", "--fmad=false",

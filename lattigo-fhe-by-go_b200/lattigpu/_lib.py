@@ -119,6 +119,12 @@ SIGNATURES = {
     "lg_ring_mul_by_vector_montgomery": (ci, [_R, ci, _P, _P, _P, vp]),
     "lg_ring_mul_by_vector_montgomery_and_add_nomod": (ci, [_R, ci, _P, _P, _P, vp]),
     "lg_ring_bitreverse": (ci, _OP2),
+    "lg_ring_mul_poly": (ci, [_R, _P, _P, _P, ci, vp]),
+    "lg_ring_mul_poly_naive": (ci, [_R, _P, _P, _P, ci, vp]),
+    "lg_ring_exp": (ci, [_R, _P, u64, _P, vp]),
+    "lg_ring_shift": (ci, [_R, _P, u64, _P, vp]),
+    "lg_ring_rotate": (ci, [_R, _P, u64, vp]),
+    "lg_ring_equal": (ci, [_R, ci, _P, _P, C.POINTER(ci), vp]),
     "lg_galois_create": (ci, [u64, u64, u64, C.POINTER(vp)]),
     "lg_galois_create_from_index": (ci, [p64, u64, C.POINTER(vp)]),
     "lg_galois_get_index": (ci, [vp, p64]),

@@ -261,6 +261,39 @@ class Context:
     InvMForm, _ = _op2("lg_ring_invmform")
     BitReverse, _ = _op2("lg_ring_bitreverse")
 
+    # ring/ring.go:357-437, :439-464, :574-580, :772-800; ring/ring_context.go:423-467 (csrc/ringext.cu)
+    def MulPoly(self, p1, p2, p3, stream=None):
+        check(lib().lg_ring_mul_poly(self.h, p1.h, p2.h, p3.h, 0, _s(stream)))
+
+    def MulPolyMontgomery(self, p1, p2, p3, stream=None):
+        check(lib().lg_ring_mul_poly(self.h, p1.h, p2.h, p3.h, 1, _s(stream)))
+
+    def MulPolyNaive(self, p1, p2, p3, stream=None):
+        check(lib().lg_ring_mul_poly_naive(self.h, p1.h, p2.h, p3.h, 0, _s(stream)))
+
+    def MulPolyNaiveMontgomery(self, p1, p2, p3, stream=None):
+        check(lib().lg_ring_mul_poly_naive(self.h, p1.h, p2.h, p3.h, 1, _s(stream)))
+
+    def Exp(self, p1, e, p2, stream=None):
+        check(lib().lg_ring_exp(self.h, p1.h, u64(e), p2.h, _s(stream)))
+
+    def Shift(self, p1, n, p2, stream=None):
+        check(lib().lg_ring_shift(self.h, p1.h, u64(n), p2.h, _s(stream)))
+
+    def Rotate(self, p1, n, p2=None, stream=None):
+        """p2 is accepted and ignored, as the reference never writes it (ring.go:791)"""
+        check(lib().lg_ring_rotate(self.h, p1.h, u64(n), _s(stream)))
+
+    def Equal(self, p1, p2, stream=None):
+        return self.EqualLvl(self.nl - 1, p1, p2, stream)
+
+    def EqualLvl(self, level, p1, p2, stream=None):
+        import ctypes
+
+        eq = ctypes.c_int(0)
+        check(lib().lg_ring_equal(self.h, level + 1, p1.h, p2.h, ctypes.byref(eq), _s(stream)))
+        return bool(eq.value)
+
     def _word(self, name, p1, m, p2, stream=None):
         check(getattr(lib(), name)(self.h, self.nl, p1.h, u64(m), p2.h, _s(stream)))
 

@@ -267,6 +267,104 @@ class Context:
         return q[:-1].copy()
 
 
+def _mred1(x, y, q, qinv):
+    """MRed, modular_reduction.go:70-79, on Python integers"""
+    M = (1 << 64) - 1
+    t = x * y
+    h = ((((t & M) * qinv) & M) * q) >> 64
+    r = ((t >> 64) - h + q) & M
+    return r - q if r >= q else r
+
+
+def _go_mask(N):
+    """(1 << N) - 1 on uint64 as Go evaluates it: a shift by 64 or more gives 0"""
+    return (1 << 64) - 1 if N >= 64 else (1 << N) - 1
+
+
+def mul_poly(ctx, p1, p2, montgomery=False):
+    """MulPoly ring/ring.go:358-367, MulPolyMontgomery :371-380"""
+    a, b = ctx.ntt(p1), ctx.ntt(p2)
+    p3 = ctx.op3("mulcoeffs_montgomery" if montgomery else "mulcoeffs", a, b)
+    return ctx.invntt(p3)
+
+
+def mul_poly_naive(ctx, p1, p2, montgomery=False):
+    """MulPolyNaive ring/ring.go:383-410 (p1 to Montgomery form first), MulPolyNaiveMontgomery :413-437; small N only"""
+    N = ctx.N
+    c1 = p1.copy() if montgomery else ctx.op2("mform_poly", p1)
+    out = np.zeros_like(p1)
+    for x, q in enumerate(ctx.moduli):
+        qinv = int(ctx.mred[x])
+        a, b = c1[x].tolist(), p2[x].tolist()
+        r = [0] * N
+        for i in range(N):
+            for j in range(i):
+                v = r[j] + (q - _mred1(a[i], b[N - i + j], q, qinv))
+                r[j] = v - q if v >= q else v
+            for j in range(i, N):
+                v = r[j] + _mred1(a[i], b[j - i], q, qinv)
+                r[j] = v - q if v >= q else v
+        out[x] = np.array(r, dtype=np.uint64)
+    return out
+
+
+def ring_exp(ctx, p1, e):
+    """Exp ring/ring.go:441-464; returns (p1 after the call, p2)"""
+    p1 = ctx.ntt(p1)
+    tmp = ctx.op3("add", ctx.new_poly(), p1)
+    p2 = np.ones_like(p1)
+    i = int(e)
+    while i > 0:
+        if i & 1:
+            p2 = ctx.op3("mulcoeffs", p2, tmp)
+        tmp = ctx.op3("mulcoeffs", tmp, p1)
+        i >>= 1
+    p2 = ctx.invntt(p2)
+    p2 = ctx.invntt(p1)  # :463 overwrites the power
+    return p1, p2
+
+
+def ring_shift(ctx, p1, n):
+    """Shift ring/ring.go:575-580: append(p1[n:], p1[:n]...)"""
+    k = int(n) & _go_mask(ctx.N)
+    if k > ctx.N:
+        raise IndexError("slice bounds out of range")
+    return np.concatenate([p1[:, k:], p1[:, :k]], axis=1)
+
+
+def ring_rotate(ctx, p1, n):
+    """Rotate ring/ring.go:775-800: written into p1 (p2 is never touched); returns p1 after the call; small N only"""
+    n = int(n) & _go_mask(ctx.N)
+    out = p1.copy()
+    for i, q in enumerate(ctx.moduli):
+        qinv = int(ctx.mred[i])
+        psi = int(ctx.psi_mont[i])
+        root = _mred1(psi, psi, q, qinv)
+        res, x, e = (1 << 64) % q, root, n  # modexpMontgomery, ring/utils.go:39-50
+        while e > 0:
+            if e & 1:
+                res = _mred1(res, x, q, qinv)
+            x = _mred1(x, x, q, qinv)
+            e >>= 1
+        root = res
+        gal = (1 << 64) % q
+        row = out[i].tolist()
+        for j in range(1, ctx.N):
+            gal = _mred1(gal, root, q, qinv)
+            row[j] = _mred1(row[j], gal, q, qinv)
+        out[i] = np.array(row, dtype=np.uint64)
+    return out
+
+
+def ring_equal(ctx, p1, p2, level=None):
+    """Equal / EqualLvl ring/ring_context.go:424-467: returns (equal, p1 reduced, p2 reduced)"""
+    nl = ctx.nl if level is None else level + 1
+    a, b = p1.copy(), p2.copy()
+    a[:nl] = ctx.op2("reduce", p1[:nl].copy(), nl=nl)
+    b[:nl] = ctx.op2("reduce", p2[:nl].copy(), nl=nl)
+    return bool(np.array_equal(a[:nl], b[:nl])), a, b
+
+
 def permute_ntt_index(gen, power, N):
     idx = np.zeros(N, dtype=np.uint64)
     lib().orc_permute_ntt_index(gen, power, N, ptr(idx))

@@ -105,6 +105,49 @@ def test_mulpoly_vs_naive(N):
         assert [int(v) for v in c2[i]] == want
 
 
+def test_ring_method_set_extras():
+    """the oracle's MulPoly*, Shift, Rotate, Exp, Equal restatements against the reference's own property tests
+    (ring/ring_test.go:422-450 GaloisShift, :503-548 MulPoly) and plain integer arithmetic"""
+    N, moduli = 64, QI60[:2]
+    rng = random.Random(5)
+    ctx = orc.Context(N, moduli)
+    a = np.array([[rng.randrange(q) for _ in range(N)] for q in moduli], dtype=np.uint64)
+    b = np.array([[rng.randrange(q) for _ in range(N)] for q in moduli], dtype=np.uint64)
+    want = orc.mul_poly_naive(ctx, a, b)
+    assert np.array_equal(orc.mul_poly(ctx, a, b), want)
+    am, bm = ctx.op2("mform_poly", a), ctx.op2("mform_poly", b)
+    assert np.array_equal(ctx.op2("invmform_poly", orc.mul_poly(ctx, am, bm, montgomery=True)), want)
+    assert np.array_equal(orc.mul_poly_naive(ctx, am, b, montgomery=True), want)
+    for i, q in enumerate(moduli):  # and the schoolbook negacyclic product on integers
+        ref = [0] * N
+        for x in range(N):
+            for y in range(N):
+                v = int(a[i, x]) * int(b[i, y])
+                k = x + y
+                ref[k % N] = (ref[k % N] + (v if k < N else -v)) % q
+        assert [int(v) for v in want[i]] == ref
+    # GaloisShift: BitReverse, InvNTT, Rotate(1), NTT, BitReverse, Reduce == Shift(1)
+    br = [int(format(j, "0%db" % (N.bit_length() - 1))[::-1], 2) for j in range(N)]
+    t = ctx.invntt(np.ascontiguousarray(a[:, br]))
+    t = orc.ring_rotate(ctx, t, 1)
+    t = ctx.ntt(t)
+    t = ctx.op2("reduce", np.ascontiguousarray(t[:, br]))
+    assert np.array_equal(t, orc.ring_shift(ctx, a, 1))
+    assert np.array_equal(orc.ring_shift(ctx, a, N), a)
+    with pytest.raises(IndexError):
+        orc.ring_shift(ctx, a, N + 1)
+    # Exp ends with InvNTT(NTT(p1)) in p2 (ring.go:463)
+    p1, p2 = orc.ring_exp(ctx, a, 3)
+    assert np.array_equal(p1, ctx.ntt(a)) and np.array_equal(p2, a)
+    # Equal compares residues
+    qcol = np.array(moduli, dtype=np.uint64)[:, None]
+    eq, ra, rb = orc.ring_equal(ctx, a, a + qcol)
+    assert eq and np.array_equal(ra, a) and np.array_equal(rb, a)
+    c = a.copy()
+    c[1, 0] ^= np.uint64(1)
+    assert not orc.ring_equal(ctx, a, c)[0] and orc.ring_equal(ctx, a, c, level=0)[0]
+
+
 @pytest.mark.parametrize("srcdst", [(QI60, PI60), (QI60[:2], QI60[:2]), (PI60[:3], QI60)])
 def test_extend_basis_vs_crt(srcdst):
     # ring/ring_test.go:550-585 (ModUpSplitQP equals reduction of the big integer)
