@@ -1562,7 +1562,8 @@ int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t
     // FP64-class limbs whose key words are all canonical go to the TMA kernel, the others stay on ks_fused_kernel
     int nfp = 0, nint = 0;
     unsigned char zfp[LG_MAX_LIMBS], zint[LG_MAX_LIMBS];
-    const bool tma = a.h_keymap && a.h_fp_ok && a.evk_f && !literal && !k.acc64 && !k.no_d64 && a.beta <= 32 && batch < (1 << 20) &&
+    // (a single entry would leave half of every CTA idle: it stays on ks_fused_kernel)
+    const bool tma = a.h_keymap && a.h_fp_ok && a.evk_f && !literal && !k.acc64 && !k.no_d64 && a.beta <= 32 && batch >= 2 && batch < (1 << 20) &&
                      (a.evk_ds % 16 == 0) && (a.evk_hs % 16 == 0) && !lg_switches().no_ks_tma.load(std::memory_order_relaxed);
     for (int j = 0; j < nlimbs; ++j) {
         if (tma && a.h_fp_ok[a.map(j)])

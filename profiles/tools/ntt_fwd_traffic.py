@@ -1,5 +1,5 @@
 """DRAM bytes of the forward NTT launch pair (strided + pipelined contiguous phase) from an
-`ncu --set full --page raw --csv` export -> profiles/r01_ncu_ntt_fwd.json, read by bench.py for roofline.traffic.
+`ncu --set full --page raw --csv` export -> profiles/r0N_ncu_ntt_fwd.json, read by bench.py for roofline.traffic.
 Usage: python profiles/tools/ntt_fwd_traffic.py raw.csv N limbs batch out.json"""
 import csv
 import json
@@ -21,7 +21,7 @@ def main(path, N, limbs, batch, out):
         name = d[ix["Kernel Name"]]
         grid = d[ix["Grid Size"]].replace(" ", "")
         g = [int(x) for x in grid.strip("()").split(",")]
-        if "ntt_fwd_strided" in name and g[0] == batch and g[2] == limbs:
+        if "ntt_fwd_strided" in name and batch in (g[0], g[1]) and g[2] == limbs:  # (batch, tiles, limbs) or tiles fastest
             found["strided"] = d
         if "ntt_contig_pipe<(bool)1" in name.replace(" ", "") or "ntt_contig_pipe<1" in name.replace(" ", ""):
             if g[2] == limbs and g[1] == N // 2048:
