@@ -961,12 +961,23 @@ __global__ void __launch_bounds__(CONTIG_THREADS, KS_MINB) ks_fused_kernel(const
 //   * each warp fetches its 4 KiB of the next digit tile with one cp.async.bulk (instead of 256 cp.async of 16 bytes)
 //     onto its own mbarrier; single tile buffer per entry, re-filled as soon as the exchange has left it;
 //   * no key registers: 128 registers, 2 CTAs (16 warps) per SM instead of 12 warps.
-// shared memory from a 1024-byte aligned base: key tile 32 KiB | digit tiles 2 x 16 KiB | private twiddles 30 KiB |
+// shared memory from a 1024-byte aligned base: key tile 32 KiB | digit tiles 2 x 17 KiB (padded rows) | private twiddles 30 KiB |
 // segment twiddles 2 KiB | mbarriers
 #define KSF_GROUPS 2
 #define KSF_THREADS (KSF_GROUPS * CONTIG_THREADS)
+// A segment's 256 words sit in KSF_SEG words: the tile arrives in natural order (the first register block reads cc + 16r),
+// the exchange between the register blocks writes word 16r + cc to KSF_ROW*r + cc and reads KSF_ROW*cc + r.  Rows padded to
+// 17 words are conflict-free both ways for 64-bit accesses and every address is the thread's base plus a compile-time offset
+// (an XOR swizzle costs about 50 address instructions per exchange): step -0.9 % in an ABAB of two libraries.  This kernel's
+// shared memory takes the largest carve-out either way, which is what made the same padding lose in the plain transforms.
+// Rows of 18 words with eight 128-bit loads on the read side (KSF_ROW 18) measured slower than 17 (profiles/README.md).
+#ifndef KSF_ROW
+#define KSF_ROW 17u
+#endif
+#define KSF_SEG (16u * KSF_ROW)
+#define KSF_TILE (8u * KSF_SEG)
 #define KSF_OFF_TILE 32768u
-#define KSF_OFF_TWP (KSF_OFF_TILE + KSF_GROUPS * 16384u)
+#define KSF_OFF_TWP (KSF_OFF_TILE + KSF_GROUPS * KSF_TILE * 8u)
 #define KSF_OFF_TWSEG (KSF_OFF_TWP + 30u * CONTIG_THREADS * 8u)
 #define KSF_OFF_BAR (KSF_OFF_TWSEG + 8u * 32u * 8u)
 #define KSF_SMEM_BYTES (KSF_OFF_BAR + 128u + 1024u)
@@ -1005,10 +1016,15 @@ LG_DEV void tma_load_rows(u32 dst, const CUtensorMap* map, int row, u32 bar) {
                  "l"(map), "r"(0), "r"(row), "r"(bar)
                  : "memory");
 }
-LG_DEV void bulk_load(u32 dst, const u64* src, u32 bytes, u32 bar) {
+LG_DEV void bulk_load1(u32 dst, const u64* src, u32 bytes, u32 bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
                  : "memory");
+}
+// a warp's two segments (512 consecutive words) into their padded places: two copies of 2 KiB on one barrier
+LG_DEV void bulk_load(u32 dst, const u64* src, u32 bytes, u32 bar) {
+    bulk_load1(dst, src, bytes / 2, bar);
+    bulk_load1(dst + KSF_SEG * 8u, src + 256, bytes / 2, bar);
 }
 
 __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFusedArgs a, const __grid_constant__ CUtensorMap kmap) {
@@ -1030,8 +1046,8 @@ __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFu
     const u32 tile0 = blockIdx.y * CONTIG_TILE;
     const u32 segbase = tile0 + sg * 256u;
     const u32 e0 = segbase + 16 * cc;
-    u64* const tilebuf = base + (KSF_OFF_TILE >> 3) + g * 2048u;
-    u64* const buf = tilebuf + sg * 256;
+    u64* const tilebuf = base + (KSF_OFF_TILE >> 3) + g * KSF_TILE;
+    u64* const buf = tilebuf + sg * KSF_SEG;
     u64* const twp = base + (KSF_OFF_TWP >> 3) + 2 * tt;
     u64* const twseg = base + (KSF_OFF_TWSEG >> 3) + sg * 32;
     // key hand-off per warp pair (warp wq of either entry reads rows 32wq .. 32wq+31 of both boxes): full / empty barriers
@@ -1041,7 +1057,7 @@ __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFu
     const u32 wq = cta_wide ? 0u : (warp & 3u);
     const u32 bars = sbase + KSF_OFF_BAR, kbar_full = bars + 8 * wq, kbar_empty = bars + 32 + 8 * wq, tbar = bars + 64 + 8 * warp;
     const u32 kdst = sbase + wq * 4096u;  // the pair's rows of the evk[i][0] box; evk[i][1] 16 KiB further
-    const u32 warp_tile = sbase + KSF_OFF_TILE + g * 16384u + (warp & 3u) * 4096u;  // the warp's two segments
+    const u32 warp_tile = sbase + KSF_OFF_TILE + (g * KSF_TILE + (warp & 3u) * 2u * KSF_SEG) * 8u;  // the warp's two segments
 
     const u64* din = a.D + (size_t)b * a.d_bs + (size_t)j * N + tile0 + (warp & 3u) * 512u;
     const int own_i = (tl < a.nl) ? tl / a.alpha : -1;
@@ -1103,10 +1119,20 @@ __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFu
             fwd_stages_sm<3, 1, M_D64>(x, c, twseg);
             __syncwarp();
 #pragma unroll
-            for (int r = 0; r < 16; ++r) buf[16 * r + (cc ^ r)] = x[r];
+            for (int r = 0; r < 16; ++r) buf[KSF_ROW * r + cc] = x[r];
             __syncwarp();
+            if (KSF_ROW % 2 == 0) {
+                const ulonglong2* row = reinterpret_cast<const ulonglong2*>(buf + KSF_ROW * cc);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) x[r] = buf[16 * cc + (r ^ cc)];
+                for (int h = 0; h < 8; ++h) {
+                    const ulonglong2 v = row[h];
+                    x[2 * h] = v.x;
+                    x[2 * h + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) x[r] = buf[KSF_ROW * cc + r];
+            }
             __syncwarp();
             if (i + 1 < a.beta && i + 1 != own_i && lane == 0) {  // the buffer is free: fetch the next digit's tile
                 fence_proxy_async();
