@@ -124,6 +124,41 @@ def test_switch_keys_unreduced_key_words(lg, params, keykind):
         lg.ring.debug_set_switch("ks_acc64", 0)
 
 
+@pytest.mark.parametrize("batch", [1, 2, 3, 5])
+def test_digit_loop_kernels_agree(lg, batch):
+    """The fused digit loop runs as two launches: ks_fused_tma_kernel (two batch entries per CTA, key tiles by TMA) on the
+    FP64-class limbs whose key words are canonical, ks_fused_kernel on the rest.  Both must give the oracle's words for odd
+    and even batches (an odd batch leaves half of the last CTA idle, a single entry stays on ks_fused_kernel), with the
+    "no_ks_tma" switch forcing the old kernel everywhere, and with a key whose one non-canonical word moves exactly one limb
+    from one kernel to the other."""
+    s = Setup(lg, ALPHA4)
+    rng = np.random.default_rng(31 + batch)
+    evk = s.evk(rng)
+    evk_bad = evk.copy()
+    evk_bad[2, 1, 3, 7] = np.uint64((1 << 64) - 5)  # limb 3 (45-bit): not canonical -> integer accumulators for that limb
+    cx = s.ct(rng, "reduced", batch)[:, 0]
+    pcx = lg.ring.Poly.from_numpy(np.ascontiguousarray(cx))
+    try:
+        for key in (evk, evk_bad):
+            results = []
+            for off in (0, 1):
+                lg.ring.debug_set_switch("no_ks_tma", off)
+                dk = lg.ckks.SwitchingKey(key)
+                for level in (s.nQ - 1, s.nQ - 3):
+                    p0, p1 = lg.ring.Poly(s.N, s.nQ, batch), lg.ring.Poly(s.N, s.nQ, batch)
+                    s.ev.switchKeysInPlace(level, pcx, dk, p0, p1)
+                    results.append((p0.numpy(nl=level + 1, squeeze=False), p1.numpy(nl=level + 1, squeeze=False)))
+            half = len(results) // 2
+            for (a0, a1), (b0, b1) in zip(results[:half], results[half:]):
+                assert np.array_equal(a0, b0) and np.array_equal(a1, b1)
+            for k, level in enumerate((s.nQ - 1, s.nQ - 3)):
+                for b in range(batch):
+                    w0, w1 = s.oev.switch_keys_in_place(level, np.ascontiguousarray(cx[b]), key)
+                    assert np.array_equal(results[k][0][b], w0) and np.array_equal(results[k][1][b], w1), (level, b)
+    finally:
+        lg.ring.debug_set_switch("no_ks_tma", 0)
+
+
 @pytest.mark.parametrize("params", [PN12, PN13, SMALL3, PN14], ids=["PN12", "PN13", "alpha3", "PN14"])
 @pytest.mark.parametrize("kind", ["reduced", "words"])
 def test_mul_relin_rescale(lg, params, kind):
