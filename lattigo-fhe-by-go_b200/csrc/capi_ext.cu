@@ -989,6 +989,12 @@ int lg_ckks_switch_key_hoisted(lg_ckks_eval* e, const lg_hoisted* h, const lg_po
     ka.evk = k->key(0, 0);
     ka.evk_ds = (size_t)(k->key(1, 0) - k->key(0, 0));
     ka.evk_hs = (size_t)(k->key(0, 1) - k->key(0, 0));
+    if (!lg_switches().no_fp_mac.load(std::memory_order_relaxed) && k->nQP == QP->nl) {
+        LG_TRY(lgi_swk_prepare(k, QP, st));
+        ka.evk_f = k->d_f;
+        ka.key_bad = k->d_bad;
+        ka.nqp = k->nQP;
+    }
     ka.acc0 = acc0;
     ka.acc1 = acc1;
     ka.acc_bs = h->d_bs;

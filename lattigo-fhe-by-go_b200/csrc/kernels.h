@@ -311,6 +311,9 @@ struct KsHoistArgs {
     const u32* index;   // permuteNTT index table (N entries)
     const u64* evk;
     size_t evk_ds, evk_hs;
+    const u64* evk_f;   // FP64 form of the key (lg_launch_swk_prepare) and its per-(digit, half, limb) flags, or nullptr
+    const u32* key_bad;
+    int nqp;            // limbs per key polynomial (rows of key_bad)
     u64* acc0;
     u64* acc1;
     size_t acc_bs;

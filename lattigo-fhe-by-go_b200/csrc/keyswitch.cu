@@ -129,9 +129,66 @@ __device__ __forceinline__ void ks_hoisted_body(const KsHoistArgs& a, const Limb
                  : "memory");
 }
 
+// The same on the FP64 pipe for moduli below 3*2^44 whose key limb is canonical (ntt.cu ACC_FP: the key out of Montgomery
+// form as doubles, every term k*x brought to [0, 2q) by d64_mul, two double accumulators per coefficient, one canonical
+// reduction at the end): 8 instead of about 29 instructions per term.  The digit values are canonical transforms (below q)
+// except on the digit's own limbs, which are the caller's NTT-domain words: a thread that meets a word of 2^51 or more
+// returns false and its four coefficients are redone on the integer path.  (Loading digit i+1 while digit i is accumulated --
+// a register double buffer -- measured slower: 5990 against 6360 hoisted rotations/s, profiles/README.md.)
+__device__ __forceinline__ bool ks_hoisted_body_fp(const KsHoistArgs& a, const LimbConst& k, int tl) {
+    const int j = blockIdx.z, bt = blockIdx.x;
+    const u32 N = a.T.N;
+    const u32 e0 = 4 * (blockIdx.y * blockDim.x + threadIdx.x);
+    if (e0 >= N) return true;
+    const uint4 ix = *reinterpret_cast<const uint4*>(a.index + e0);
+    const u32 idx[4] = {ix.x, ix.y, ix.z, ix.w};
+    const u64* d = a.D + (size_t)bt * a.d_bs + (size_t)j * N;
+    const u64* key = a.evk_f + (size_t)tl * N + e0;
+    const double qd = __ull2double_rn(k.q), qinvd = __ddiv_rd(1.0, qd);
+    double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
+    u64 wide = 0;
+#pragma unroll 1
+    for (int i = 0; i < a.beta; ++i, d += a.d_ds, key += a.evk_ds) {
+        u64 x[4], k0[4], k1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = d[idx[e]];
+        asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(k0[0]), "=l"(k0[1]), "=l"(k0[2]), "=l"(k0[3]) : "l"(key));
+        asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(k1[0]), "=l"(k1[1]), "=l"(k1[2]), "=l"(k1[3])
+                     : "l"(key + a.evk_hs));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            wide |= x[e];
+            const double xd = u52_to_d(x[e] & 0x000FFFFFFFFFFFFFull, 4503599627370496.0);
+            const double ka = bits2d(k0[e]), kb = bits2d(k1[e]);
+            acc0[e] = __dadd_rn(acc0[e], d64_mul(ka, __dmul_rd(ka, qinvd), xd, qd));
+            acc1[e] = __dadd_rn(acc1[e], d64_mul(kb, __dmul_rd(kb, qinvd), xd, qd));
+        }
+    }
+    if (wide >> 51) return false;
+    const double q34 = 34.0 * qd;
+    u64 r0[4], r1[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {  // 0 <= sum < 2q*beta <= 64q: brought to [0, 2q) and then below q
+        r0[e] = cred(d_to_u52(d64_red(acc0[e], qinvd, qd), 4503599627370496.0), k.q);
+        r1[e] = cred(d_to_u52(d64_red(acc1[e], qinvd, qd), 4503599627370496.0), k.q);
+    }
+    (void)q34;
+    u64* o0 = a.acc0 + (size_t)bt * a.acc_bs + (size_t)j * N + e0;
+    u64* o1 = a.acc1 + (size_t)bt * a.acc_bs + (size_t)j * N + e0;
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(o0), "l"(r0[0]), "l"(r0[1]), "l"(r0[2]), "l"(r0[3]) : "memory");
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(o1), "l"(r1[0]), "l"(r1[1]), "l"(r1[2]), "l"(r1[3]) : "memory");
+    return true;
+}
+
 __global__ void __launch_bounds__(256) ks_hoisted_kernel(const KsHoistArgs a) {
     const int tl = a.map(blockIdx.z);
     const LimbConst k = load_limb_const(a.T, tl);
+    if (a.evk_f != nullptr && k.q < (3ull << 44) && a.beta <= 32) {
+        u32 bad = 0;
+        for (int i = 0; i < 2 * a.beta; ++i) bad |= a.key_bad[(size_t)i * a.nqp + tl];
+        if (bad == 0 && ks_hoisted_body_fp(a, k, tl)) return;
+    }
     if ((2 * k.q) <= (~0ull) / (u64)a.beta)
         ks_hoisted_body<true>(a, k, tl);
     else
