@@ -423,11 +423,14 @@ __global__ void __launch_bounds__(128) modup_fp_kernel(const ModUpArgs a) {
 // themselves rounded down) -- so that r1 = S + K_v - qh1*p lies in [0, (2^SH + 8 * 2^-52 * sum_i q_i + 2) * p) (eight downward roundings), which
 // the host checks to be below 2^64 for every target before choosing this kernel.  A second quotient on r1 (converted
 // rounding down) leaves [0, 2p) and one conditional subtraction.  Everything integer is mod 2^64 as in modup_fp_kernel.
-template <int NSRC, bool LAZY>
+// CPT coefficients per thread (256-bit access for CPT = 4) and the per-target constants as 128-bit shared-memory pairs, as in
+// modup_fp_kernel: the constant loads and the loop overhead are paid once per CPT coefficients.
+template <int NSRC, bool LAZY, int CPT>
 __global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
-    constexpr int ROW = 3 * NSRC + 6;  // np << SH, p, 1/p, bits(2^52) * p, np, C[NSRC], Cd[NSRC], K'[NSRC+1]
-    constexpr int O_C = 5, O_CD = 5 + NSRC, O_K = 5 + 2 * NSRC;
-    __shared__ u64 tab[LG_MAX_LIMBS * ROW];
+    // row: {np << SH, p}, {1/p, bits(2^52) * p}, {np, -}, {C_i, Cd_i} x NSRC, K'[NSRC+1] (+ pad to an even count)
+    constexpr int O_C = 6, O_K = 6 + 2 * NSRC;
+    constexpr int ROW = (O_K + NSRC + 1 + 1) & ~1;
+    __shared__ __align__(16) u64 tab[LG_MAX_LIMBS * ROW];
     const ModUpTables& M = a.M;
     const int sh = a.fp_shift;
     const u64 magic_bits = (u64)(0x433 + sh) << 52;  // 2^(52+sh)
@@ -449,11 +452,12 @@ __global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
         row[2] = (u64)__double_as_longlong(__ddiv_rd(1.0, __ull2double_ru(p)));
         row[3] = 0x4330000000000000ull * p;
         row[4] = 0 - p;
+        row[5] = 0;
 #pragma unroll
         for (int i = 0; i < NSRC; ++i) {
             const u64 c = mred(M.qispj[(size_t)i * M.dst_total + tg], 1, p, pinv);  // out of Montgomery form
-            row[O_C + i] = c;
-            row[O_CD + i] = (u64)__double_as_longlong(__ull2double_rd(c));
+            row[O_C + 2 * i] = c;
+            row[O_C + 2 * i + 1] = (u64)__double_as_longlong(__ull2double_rd(c));
         }
 #pragma unroll
         for (int v = 0; v <= NSRC; ++v)
@@ -461,34 +465,46 @@ __global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
     }
     __syncthreads();
     const double magic = __longlong_as_double((long long)magic_bits);
-    const u32 x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const u32 x = CPT * (blockIdx.x * blockDim.x + threadIdx.x);
     const int bt = blockIdx.y;
     if (x >= a.N) return;
-    u32 y0[NSRC][2], y1[NSRC][2];
-    double yd[NSRC][2];
-    u32 v[2];
+    u32 y0[NSRC][CPT], y1[NSRC][CPT];
+    double yd[NSRC][CPT];
+    u32 v[CPT];
     {
-        double vi0 = 0.0, vi1 = 0.0;
+        double vi[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) vi[e] = 0.0;
         const u64* in = a.in + bt * a.in_bs + x;
 #pragma unroll
         for (int i = 0; i < NSRC; ++i) {
             const u64* srcp = a.src[0] ? a.src[i] + bt * a.in_bs + x : in + (size_t)i * a.N;
-            const ulonglong2 val = *reinterpret_cast<const ulonglong2*>(srcp);
-            if (a.copy_out) *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x) = val;
+            u64 val[CPT];
+#pragma unroll
+            for (int h = 0; h < CPT / 2; ++h) {
+                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(srcp + 2 * h);
+                val[2 * h] = t.x;
+                val[2 * h + 1] = t.y;
+            }
+            if (a.copy_out) {
+#pragma unroll
+                for (int h = 0; h < CPT / 2; ++h)
+                    *reinterpret_cast<ulonglong2*>(a.copy_out + bt * a.copy_bs + (size_t)i * a.N + x + 2 * h) =
+                        make_ulonglong2(val[2 * h], val[2 * h + 1]);
+            }
             const u64 qi = __ldg(M.srcQ + i), qib = __ldg(M.qib + i), qinv = __ldg(M.srcQinv + i);
-            const u64 ya = mred(val.x, qib, qi, qinv), yb = mred(val.y, qib, qi, qinv);
             const double qd = __ull2double_rn(qi);
-            vi0 = __dadd_rn(vi0, __ddiv_rn(__ull2double_rn(ya), qd));
-            vi1 = __dadd_rn(vi1, __ddiv_rn(__ull2double_rn(yb), qd));
-            yd[i][0] = __ull2double_rd(ya);
-            yd[i][1] = __ull2double_rd(yb);
-            y0[i][0] = (u32)ya;
-            y1[i][0] = (u32)(ya >> 32);
-            y0[i][1] = (u32)yb;
-            y1[i][1] = (u32)(yb >> 32);
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) {
+                const u64 ye = mred(val[e], qib, qi, qinv);
+                vi[e] = __dadd_rn(vi[e], __ddiv_rn(__ull2double_rn(ye), qd));  // :363-375, sequential as in the reference
+                yd[i][e] = __ull2double_rd(ye);
+                y0[i][e] = (u32)ye;
+                y1[i][e] = (u32)(ye >> 32);
+            }
         }
-        v[0] = (u32)__double2ull_rz(vi0);
-        v[1] = (u32)__double2ull_rz(vi1);
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) v[e] = (u32)__double2ull_rz(vi[e]);
     }
     int idx = 0;
 #pragma unroll 1
@@ -497,18 +513,21 @@ __global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
 #pragma unroll 1
         for (int t = 0; t < a.ndst[k]; ++t, ++idx) {
             const u64* row = tab + idx * ROW;
-            const u64 npsh = row[0], pj = row[1], c52 = row[3], np = row[4];
-            const double pinvd = __longlong_as_double((long long)row[2]);
+            const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(row);      // {np << SH, p}
+            const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(row + 2);  // {1/p, bits(2^52) * p}
+            const u64 npsh = h0.x, pj = h0.y, c52 = h1.y, np = row[4];
+            const double pinvd = __longlong_as_double((long long)h1.x);
             u64 c[NSRC];
             double cd[NSRC];
 #pragma unroll
             for (int i = 0; i < NSRC; ++i) {
-                c[i] = row[O_C + i];
-                cd[i] = __longlong_as_double((long long)row[O_CD + i]);
+                const ulonglong2 pr = *reinterpret_cast<const ulonglong2*>(row + O_C + 2 * i);
+                c[i] = pr.x;
+                cd[i] = __longlong_as_double((long long)pr.y);
             }
-            u64 res[2];
+            u64 res[CPT];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < CPT; ++e) {
                 double s = __dmul_rd(yd[0][e], cd[0]);
 #pragma unroll
                 for (int i = 1; i < NSRC; ++i) s = __fma_rd(yd[i][e], cd[i], s);
@@ -531,7 +550,9 @@ __global__ void __launch_bounds__(128) modup_fp2_kernel(const ModUpArgs a) {
                 r2 += (u64)h2 << 32;
                 res[e] = LAZY ? r2 : cred(r2, pj);
             }
-            *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N) = make_ulonglong2(res[0], res[1]);
+#pragma unroll
+            for (int h = 0; h < CPT / 2; ++h)
+                *reinterpret_cast<ulonglong2*>(out + (size_t)t * a.N + 2 * h) = make_ulonglong2(res[2 * h], res[2 * h + 1]);
         }
     }
 }
@@ -558,8 +579,9 @@ int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
     const bool no_lazy = lg_switches().no_lazy_modup.load(std::memory_order_relaxed) != 0;
     const bool lazy = a.lazy_out && !no_lazy;
     if (a.fast == 2 && !no_fp && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
-        // four coefficients per thread when that still fills the GPU (two otherwise)
-        const bool four = !lg_switches().modup_cpt2.load(std::memory_order_relaxed) && a.N >= 4 &&
+        // four coefficients per thread when that still fills the GPU (two otherwise, and for one or two sources: that
+        // variant is bound by its HBM writes, 4.8 TB/s, and loses with the lower occupancy -- 166 against 120 us per digit)
+        const bool four = !lg_switches().modup_cpt2.load(std::memory_order_relaxed) && a.N >= 4 && a.nsrc >= 3 &&
                           (size_t)batch * (a.N / 4 / 128) >= 2 * 148;
         const int cpt = four ? 4 : 2;
         dim3 fgrid((a.N / cpt + 127) / 128, batch);
@@ -582,22 +604,25 @@ int lg_launch_modup(const ModUpArgs& a, int batch, cudaStream_t st) {
         return 0;
     }
     if (a.fast == 3 && !no_fp && a.nsrc >= 1 && a.nsrc <= 4 && a.N >= 2) {
-        dim3 fgrid((a.N / 2 + 127) / 128, batch);
-        if (lazy) {
-            switch (a.nsrc) {
-                case 1: modup_fp2_kernel<1, true><<<fgrid, 128, 0, st>>>(a); break;
-                case 2: modup_fp2_kernel<2, true><<<fgrid, 128, 0, st>>>(a); break;
-                case 3: modup_fp2_kernel<3, true><<<fgrid, 128, 0, st>>>(a); break;
-                default: modup_fp2_kernel<4, true><<<fgrid, 128, 0, st>>>(a); break;
-            }
-        } else {
-            switch (a.nsrc) {
-                case 1: modup_fp2_kernel<1, false><<<fgrid, 128, 0, st>>>(a); break;
-                case 2: modup_fp2_kernel<2, false><<<fgrid, 128, 0, st>>>(a); break;
-                case 3: modup_fp2_kernel<3, false><<<fgrid, 128, 0, st>>>(a); break;
-                default: modup_fp2_kernel<4, false><<<fgrid, 128, 0, st>>>(a); break;
-            }
+        const bool four = !lg_switches().modup_cpt2.load(std::memory_order_relaxed) && a.N >= 4 &&
+                          (size_t)batch * (a.N / 4 / 128) >= 2 * 148;
+        const int cpt = four ? 4 : 2;
+        dim3 fgrid((a.N / cpt + 127) / 128, batch);
+#define LG_FP2(NS)                                                                                 \
+    if (four) {                                                                                    \
+        if (lazy) modup_fp2_kernel<NS, true, 4><<<fgrid, 128, 0, st>>>(a);                         \
+        else modup_fp2_kernel<NS, false, 4><<<fgrid, 128, 0, st>>>(a);                             \
+    } else {                                                                                       \
+        if (lazy) modup_fp2_kernel<NS, true, 2><<<fgrid, 128, 0, st>>>(a);                         \
+        else modup_fp2_kernel<NS, false, 2><<<fgrid, 128, 0, st>>>(a);                             \
+    }
+        switch (a.nsrc) {
+            case 1: LG_FP2(1) break;
+            case 2: LG_FP2(2) break;
+            case 3: LG_FP2(3) break;
+            default: LG_FP2(4) break;
         }
+#undef LG_FP2
         lg_g_launches += 1;
         return 0;
     }
