@@ -471,12 +471,23 @@ int lgi_keyswitch_digits(const lg_ring* QP, const lg_ring* Q, LimbMap qp_map, co
         for (int b0 = 0; b0 < batch; b0 += chunk) {
             const int cb = (batch - b0) < chunk ? (batch - b0) : chunk;
             const size_t d_ds = (size_t)cb * d_bs;
+            // The basis extensions of the digits are independent; for a few ciphertexts each is a fraction of a wave, so
+            // they go to auxiliary streams in turn and overlap (forked from and joined to `st`).
+            LgAux* aux = (cb * (N / 2 / 128) < 2 * 148 && beta > 1 && !lg_switches().no_aux_streams.load(std::memory_order_relaxed))
+                             ? lg_aux_streams()
+                             : nullptr;
+            if (aux) lg_aux_fork(aux, st, LG_AUX_STREAMS);
             for (int i = 0; i < beta; ++i) {
                 u64* Di = D.d + (size_t)i * d_ds;
                 // the digits are read by the forward NTT alone: no conditional subtraction needed
-                LG_TRY(lgi_decompose(dec, level, i, cb, coef + (size_t)b0 * coef_bs, coef_bs, Di, d_bs, Di + (size_t)nl * N,
-                                     d_bs, st, true));
+                const int rc = lgi_decompose(dec, level, i, cb, coef + (size_t)b0 * coef_bs, coef_bs, Di, d_bs, Di + (size_t)nl * N,
+                                             d_bs, aux ? aux->s[i % LG_AUX_STREAMS] : st, true);
+                if (rc != LG_OK) {
+                    if (aux) lg_aux_join(aux, st, LG_AUX_STREAMS);
+                    return rc;
+                }
             }
+            if (aux) lg_aux_join(aux, st, LG_AUX_STREAMS);
             NttArgs a;
             memset(&a, 0, sizeof(a));
             a.T = QP->T;

@@ -38,6 +38,8 @@ struct LgSwitches {
     // LATTIGPU_NO_KS_TMA: every limb of the fused digit loop on ks_fused_kernel (keys through registers); default: the
     // FP64-class limbs on ks_fused_tma_kernel (two batch entries per CTA, key tiles through shared memory by TMA)
     std::atomic<int> no_ks_tma{0};
+    // LATTIGPU_NO_AUX_STREAMS: the per-digit basis extensions of a small batch stay on the caller's stream
+    std::atomic<int> no_aux_streams{0};
     // LATTIGPU_TILE_FASTEST=0: the strided NTT phases walk the batch entries fastest; default 1: the tiles of a limb fastest
     // (adjacent 128-byte columns in flight together).  Measured (profiles/r02_tile_fastest_ab.jsonl, 16 interleaved rounds):
     // forward / inverse limb-NTT -1.3 % / -1.1 %, step -0.5 %.
@@ -59,6 +61,17 @@ inline void lg_ensure_dyn_smem(size_t bytes) {
 }
 
 #define LG_MAX_LIMBS 64
+
+// Auxiliary streams for independent launches inside one call (ntt.cu): forked from the caller's stream and joined back to it
+// with events, so the call stays ordered on the caller's stream (and capturable).
+#define LG_AUX_STREAMS 4
+struct LgAux {
+    cudaStream_t s[LG_AUX_STREAMS];
+    cudaEvent_t fork, join[LG_AUX_STREAMS];
+};
+LgAux* lg_aux_streams();  // nullptr when they cannot be created
+void lg_aux_fork(LgAux* a, cudaStream_t st, int n);
+void lg_aux_join(LgAux* a, cudaStream_t st, int n);
 
 // ---- K1: NTT ----------------------------------------------------------------
 // Epilogue of the forward transform's last phase (logN >= 12): instead of storing NTT(x) the kernel stores

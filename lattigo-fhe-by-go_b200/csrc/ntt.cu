@@ -1377,20 +1377,18 @@ void launch_contig_pipe(bool fwd, bool literal, const NttArgs& a, int nlimbs, in
 
 bool literal_ntt() { return lg_switches().literal_ntt.load(std::memory_order_relaxed) != 0; }
 
-// auxiliary streams of the L2-grouped transform, one set per (host thread, device)
-struct NttAux {
-    cudaStream_t s[2];
-    cudaEvent_t fork, join[2];
-};
-NttAux* ntt_aux() {
-    thread_local NttAux* per_dev[64] = {};
+}  // namespace
+
+// auxiliary streams, one set per (host thread, device): forked from and joined to the caller's stream with events
+LgAux* lg_aux_streams() {
+    thread_local LgAux* per_dev[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return nullptr;
     if (!per_dev[dev]) {
-        NttAux* a = new NttAux;
+        LgAux* a = new LgAux;
         bool ok = cudaEventCreateWithFlags(&a->fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int k = 0; k < 2 && ok; ++k)
+        for (int k = 0; k < LG_AUX_STREAMS && ok; ++k)
             ok = cudaStreamCreateWithFlags(&a->s[k], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&a->join[k], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) {
@@ -1402,7 +1400,20 @@ NttAux* ntt_aux() {
     }
     return per_dev[dev];
 }
+void lg_aux_fork(LgAux* a, cudaStream_t st, int n) {
+    cudaEventRecord(a->fork, st);
+    for (int k = 0; k < n; ++k) cudaStreamWaitEvent(a->s[k], a->fork, 0);
+}
+void lg_aux_join(LgAux* a, cudaStream_t st, int n) {
+    for (int k = 0; k < n; ++k) {
+        cudaEventRecord(a->join[k], a->s[k]);
+        cudaStreamWaitEvent(st, a->join[k], 0);
+    }
+}
 
+namespace {
+typedef LgAux NttAux;
+NttAux* ntt_aux() { return lg_aux_streams(); }
 }  // namespace
 
 int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cudaStream_t st) {
