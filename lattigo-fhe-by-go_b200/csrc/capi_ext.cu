@@ -369,6 +369,21 @@ int lgi_decompose(const lg_decomposer* d, int level, int crt, int batch, const u
     a.out_bs[1] = outP_bs;
     a.ndst[1] = d->nP;
     a.tgt0[1] = d->nQ;
+    if (lazy_out) {
+        // key-switch callers take the digit's own limbs from the NTT-domain input (ckks/evaluator.go:1579-1584): those
+        // targets are never read, so they are not computed -- the Q run splits around [p0idxst, p0idxed)
+        const int own1 = p0idxed < level + 1 ? p0idxed : level + 1;
+        a.nruns = 3;
+        a.ndst[0] = p0idxst;
+        a.out[2] = a.out[1];
+        a.out_bs[2] = a.out_bs[1];
+        a.ndst[2] = a.ndst[1];
+        a.tgt0[2] = a.tgt0[1];
+        a.out[1] = outQ + (size_t)own1 * N;
+        a.out_bs[1] = outQ_bs;
+        a.ndst[1] = level + 1 - own1;
+        a.tgt0[1] = own1;
+    }
     a.copy_out = nullptr;
     a.fast = m.fast_level(a.nsrc, &a.fp_shift);
     a.lazy_out = lazy_out ? 1 : 0;
