@@ -338,8 +338,20 @@ int switch_keys_resident(lg_ckks_eval* e, lg_comm* c, int level, int batch, cons
     if (no > 0) {
         LG_TRY(D.alloc((size_t)beta * batch * d_bs));
         const size_t d_ds = (size_t)batch * d_bs;
-        for (int i = 0; i < beta; ++i)
-            LG_TRY(decompose_own(c, e->dec.get(), o, level, i, batch, c2_off, D.d + (size_t)i * d_ds, d_bs, st));
+        // independent per-digit basis extensions: for a few ciphertexts they overlap on auxiliary streams (capi_ext.cu)
+        LgAux* aux = ((size_t)batch * (N / 2 / 128) < 2 * 148 && beta > 1 && !lg_switches().no_aux_streams.load(std::memory_order_relaxed))
+                         ? lg_aux_streams()
+                         : nullptr;
+        if (aux) lg_aux_fork(aux, st, LG_AUX_STREAMS);
+        for (int i = 0; i < beta; ++i) {
+            const int rc = decompose_own(c, e->dec.get(), o, level, i, batch, c2_off, D.d + (size_t)i * d_ds, d_bs,
+                                         aux ? aux->s[i % LG_AUX_STREAMS] : st);
+            if (rc != LG_OK) {
+                if (aux) lg_aux_join(aux, st, LG_AUX_STREAMS);
+                return rc;
+            }
+        }
+        if (aux) lg_aux_join(aux, st, LG_AUX_STREAMS);
         NttArgs a;
         memset(&a, 0, sizeof(a));
         a.T = QP->T;
