@@ -38,6 +38,7 @@ LgSwitches& lg_switches() {
         sw.no_fp_mac = flag("LATTIGPU_NO_FP_MAC", true);
         sw.no_ks_tma = flag("LATTIGPU_NO_KS_TMA", true);
         sw.no_aux_streams = flag("LATTIGPU_NO_AUX_STREAMS", true);
+        sw.no_strided_tma = flag("LATTIGPU_NO_STRIDED_TMA", true);
         if (const char* e = getenv("LATTIGPU_TILE_FASTEST")) sw.tile_fastest = atoi(e) ? 1 : 0;
         sw.no_d64_ntt = flag("LATTIGPU_NO_D64_NTT", true);
         sw.reverse_walk = flag("LATTIGPU_REVERSE_WALK", true);
@@ -121,6 +122,7 @@ int lg_debug_set_switch(const char* name, uint64_t value) {
     else if (!strcmp(name, "no_fp_mac")) sw.no_fp_mac = v;
     else if (!strcmp(name, "no_ks_tma")) sw.no_ks_tma = v;
     else if (!strcmp(name, "no_aux_streams")) sw.no_aux_streams = v;
+    else if (!strcmp(name, "no_strided_tma")) sw.no_strided_tma = v;
     else if (!strcmp(name, "tile_fastest")) sw.tile_fastest = v;
     else if (!strcmp(name, "no_d64_ntt")) sw.no_d64_ntt = v;
     else if (!strcmp(name, "reverse_walk")) sw.reverse_walk = v;

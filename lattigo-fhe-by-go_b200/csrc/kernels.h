@@ -40,6 +40,9 @@ struct LgSwitches {
     std::atomic<int> no_ks_tma{0};
     // LATTIGPU_NO_AUX_STREAMS: the per-digit basis extensions of a small batch stay on the caller's stream
     std::atomic<int> no_aux_streams{0};
+    // LATTIGPU_NO_STRIDED_TMA: the forward strided NTT phase with per-thread loads and stores (ntt_fwd_strided) instead of
+    // the TMA-fed ring (ntt_fwd_strided_tma)
+    std::atomic<int> no_strided_tma{0};
     // LATTIGPU_TILE_FASTEST=0: the strided NTT phases walk the batch entries fastest; default 1: the tiles of a limb fastest
     // (adjacent 128-byte columns in flight together).  Measured (profiles/r02_tile_fastest_ab.jsonl, 16 interleaved rounds):
     // forward / inverse limb-NTT -1.3 % / -1.1 %, step -0.5 %.

@@ -1181,6 +1181,160 @@ __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFu
     }
 }
 
+// ---- forward strided phase fed by TMA ----------------------------------------------------------------------------
+// ntt_fwd_strided issues its 16 loads per thread in one burst, computes, then stores: a CTA has nothing in flight for most
+// of its life, and the digit launch of a key switch (10.4 GB) runs at 4.8 TB/s although its access pattern alone reaches
+// 6.3 TB/s (profiles/r02_strided_copy.txt).  Here the tile -- all 2^L rows of W adjacent columns = a 2-D box of the limb seen
+// as rows of 256 words -- moves by TMA in both directions: a CTA takes the same (limb, tile) of up to `bpc` batch entries,
+// loads run two entries ahead into a ring of three 32 KiB buffers (cp.async.bulk.tensor.2d + mbarrier), the register blocks
+// work IN PLACE on the buffer (the exchange between them uses the slots the values were read from), and the result leaves with
+// a TMA store (bulk_group) while the next entry is transformed.  No thread issues a global load or store; twiddles are staged
+// once per CTA.  256 threads, up to 128 registers, 2 CTAs/SM.
+#define STMA_STAGES 3
+#define STMA_SMEM_BYTES(L) (STMA_STAGES * 32768u + 32u * ((1u << ((L) - 4)) + 1u) * 8u + 64u + 128u)
+
+LG_DEV void tma_load_box(u32 dst, const CUtensorMap* map, int col, int row, u32 bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(col), "r"(row), "r"(bar)
+                 : "memory");
+}
+LG_DEV void tma_store_box(const CUtensorMap* map, int col, int row, u32 src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col), "r"(row), "r"(src)
+                 : "memory");
+}
+LG_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N_>
+LG_DEV void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_) : "memory");
+}
+
+// the two register blocks of the strided phase on a tile held in shared memory as [2^L rows][W columns], in place
+template <int L, int MODE>
+LG_DEV void fwd_strided_tile(const NttArgs& a, const LimbConst& lc, int tl, u64* tile, const u64* tws_sm) {
+    constexpr int G = 1 << (L - 4);  // threads per column
+    constexpr int W = 256 / G;       // columns per CTA
+    constexpr int N2 = L - 4;        // stages of the second register block
+    const TwConst c = tw_const<true, MODE>(a.T, lc, tl);
+    const int t = threadIdx.x, col = t % W, g = t / W;
+    u64 x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = tile[(g + r * G) * W + col];
+    if (a.bcast.enabled && a.bcast.add != nullptr) {  // ring_scaling.go:99-103: + (q_j - pHalf mod q_j), unreduced
+        const u64 add = __ldg(a.bcast.add + tl);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] += add;
+    }
+    if (MODE != M_LITERAL) {  // headroom of the lazy butterflies, as in fwd_strided_body
+        const u32 sh = MODE == M_FREE ? 63u : (MODE == M_F64 ? 50u : (MODE == M_D64 ? 49u : 66u - (u32)__clzll((long long)c.q)));
+        u64 o = 0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) o |= x[r];
+        if (o >> sh) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (x[r] >> sh) x[r] = bred_add(x[r], c.q, lc.u0);
+        }
+    }
+    if (MODE == M_D64) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = d2bits(u52_to_d(x[r], 4503599627370496.0));
+    }
+    fwd_stages_sm<3, 1, MODE>(x, c, tws_sm);
+    if (N2 > 0) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) tile[(g + r * G) * W + col] = x[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = tile[(16 * g + r) * W + col];
+        const u64* twg = tws_sm + (1 + g) * 32;
+        fwd_stages_sm<(N2 > 0 ? N2 - 1 : 0), 1, MODE>(x, c, twg);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) tile[(16 * g + r) * W + col] = x[r];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) tile[(g + r * G) * W + col] = x[r];
+    }
+}
+
+template <int L, bool LITERAL>
+__global__ void __launch_bounds__(256, 2) ntt_fwd_strided_tma(const NttArgs a, const __grid_constant__ CUtensorMap in_map,
+                                                               const __grid_constant__ CUtensorMap out_map, int batch, int bpc) {
+    extern __shared__ __align__(16) u64 ks_smem[];
+    constexpr int W = 256 >> (L - 4);
+    const u32 raw = (u32)__cvta_generic_to_shared(ks_smem);
+    const u32 sbase = (raw + 127u) & ~127u;
+    u64* const base = ks_smem + ((sbase - raw) >> 3);
+    u64* const tws_sm = base + STMA_STAGES * 4096;
+    const u32 bars = sbase + STMA_STAGES * 32768u + 32u * ((1u << (L - 4)) + 1u) * 8u;
+    const int j = (int)blockIdx.z, tile_x = (int)blockIdx.x;
+    const int b0 = (int)blockIdx.y * bpc, nb = (batch - b0) < bpc ? (batch - b0) : bpc;
+    const int tl = a.map(j);
+    if (a.skip_alpha > 0) {  // digit-batched launch: bpc divides skip_div, so a group never straddles two digits
+        const int dg = b0 / a.skip_div;
+        if (tl < a.skip_nl && tl >= dg * a.skip_alpha && tl < (dg + 1) * a.skip_alpha) return;
+    } else if (j >= a.skip0 && j < a.skip1) {
+        return;
+    }
+    const LimbConst lc = load_limb_const(a.T, tl);
+    const int mode = LITERAL ? M_LITERAL : fwd_mode(lc.q, a.no_d64);
+    const u32 t = threadIdx.x;
+    // rows of 256 words: limb j of entry b starts at row (b*bstride + j*ls) / 256
+    const size_t in_ls = a.bcast.enabled ? 0 : (a.in_ls ? a.in_ls : a.T.N), out_ls = a.out_ls ? a.out_ls : a.T.N;
+    const int col0 = tile_x * W;
+    auto in_row = [&](int i) { return (int)(((size_t)(b0 + i) * a.in_bstride + (size_t)j * in_ls) >> 8); };
+    auto out_row = [&](int i) { return (int)(((size_t)(b0 + i) * a.out_bstride + (size_t)j * out_ls) >> 8); };
+    if (t == 0) {
+        for (int s = 0; s < STMA_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const TwConst c = LITERAL ? tw_const<true, M_LITERAL>(a.T, lc, tl)
+                                  : (mode == M_D64 ? tw_const<true, M_D64>(a.T, lc, tl)
+                                                   : (mode == M_F64 ? tw_const<true, M_F64>(a.T, lc, tl) : tw_const<true, M_FREE>(a.T, lc, tl)));
+        if (LITERAL || mode == M_LITERAL)
+            fill_strided_tw<L, true>(tws_sm, tw_const<true, M_LITERAL>(a.T, lc, tl));
+        else
+            fill_strided_tw<L, false>(tws_sm, c);
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int i = 0; i < 2 && i < nb; ++i) {
+            mbar_expect_tx(bars + 8 * i, 32768u);
+            tma_load_box(sbase + 32768u * i, &in_map, col0, in_row(i), bars + 8 * i);
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < nb; ++i) {
+        const int s = i % STMA_STAGES;
+        if (t == 0 && i + 2 < nb) {
+            // the buffer of entry i+2 held entry i-1: its store must have finished reading shared memory
+            bulk_wait_read<0>();
+            const int s2 = (i + 2) % STMA_STAGES;
+            mbar_expect_tx(bars + 8 * s2, 32768u);
+            tma_load_box(sbase + 32768u * s2, &in_map, col0, in_row(i + 2), bars + 8 * s2);
+        }
+        mbar_wait(bars + 8 * s, (u32)(i / STMA_STAGES) & 1u);
+        u64* tile = base + s * 4096;
+        if (mode == M_D64)
+            fwd_strided_tile<L, M_D64>(a, lc, tl, tile, tws_sm);
+        else if (mode == M_F64)
+            fwd_strided_tile<L, M_F64>(a, lc, tl, tile, tws_sm);
+        else if (mode == M_FREE)
+            fwd_strided_tile<L, M_FREE>(a, lc, tl, tile, tws_sm);
+        else if (mode == M_LAZY)
+            fwd_strided_tile<L, M_LAZY>(a, lc, tl, tile, tws_sm);
+        else
+            fwd_strided_tile<L, M_LITERAL>(a, lc, tl, tile, tws_sm);
+        fence_proxy_async();  // every thread's writes to the tile, before the async-proxy store reads them
+        __syncthreads();
+        if (t == 0) {
+            tma_store_box(&out_map, col0, out_row(i), sbase + 32768u * s);
+            bulk_commit();
+        }
+    }
+    if (t == 0) bulk_wait_read<0>();  // shared memory stays valid until the last store has read it
+}
+
 LG_DEV bool inv_flagged(const NttArgs& a) {
     return a.flags != nullptr && a.flags[(size_t)cta_x(a) * gridDim.z + cta_z(a)] != 0;
 }
@@ -1331,8 +1485,81 @@ void launch_strided(bool fwd, bool literal, const NttArgs& a, dim3 grid, cudaStr
     }
 }
 
+// CUtensorMap of a buffer of 64-bit words seen as `rows` rows of `cols` words (row pitch = cols words), boxes of box_cols x
+// box_rows; 0 = ok (needs a driver with cuTensorMapEncodeTiled)
+static int encode_words_2d(void* map, const u64* ptr, size_t cols, size_t rows, unsigned box_cols, unsigned box_rows, bool swizzle128) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            fn = nullptr;
+        }
+        return (EncodeFn)fn;
+    }();
+    if (!encode || rows == 0 || rows > 0x7fffffffull || ((uintptr_t)ptr & 15) != 0) return 1;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * 8};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estride[2] = {1, 1};
+    CUtensorMap m;
+    if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)ptr, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    memcpy(map, &m, sizeof(m));
+    return 0;
+}
+
+// forward strided phase by TMA (ntt_fwd_strided_tma): false = not applicable, the caller launches ntt_fwd_strided
+template <int L>
+static bool launch_strided_tma(bool literal, const NttArgs& a, int batch, int nlimbs, cudaStream_t st) {
+    const u32 N = a.T.N;
+    const size_t in_ls = a.bcast.enabled ? 0 : (a.in_ls ? a.in_ls : N), out_ls = a.out_ls ? a.out_ls : N;
+    if ((a.in_bstride | a.out_bstride | in_ls | out_ls) & 255) return false;
+    if (batch > 1 && (a.in_bstride == 0 || a.out_bstride == 0)) return false;
+    const size_t rows_in = ((size_t)(batch - 1) * a.in_bstride + (size_t)(nlimbs - 1) * in_ls + N) >> 8;
+    const size_t rows_out = ((size_t)(batch - 1) * a.out_bstride + (size_t)(nlimbs - 1) * out_ls + N) >> 8;
+    constexpr unsigned W = 256u >> (L - 4), R = 1u << L;
+    CUtensorMap in_map, out_map;
+    if (encode_words_2d(&in_map, a.in, 256, rows_in, W, R, false) != 0) return false;
+    if (encode_words_2d(&out_map, a.out, 256, rows_out, W, R, false) != 0) return false;
+    int bpc = batch < 8 ? batch : 8;
+    const long tiles = N / 4096;
+    while (bpc > 2 && tiles * nlimbs * ((batch + bpc - 1) / bpc) < 2L * 148 * 2) bpc = (bpc + 1) / 2;
+    if (a.skip_alpha > 0)
+        while (a.skip_div % bpc) --bpc;
+    const int groups = (batch + bpc - 1) / bpc;
+    if (groups > 65535) return false;
+    const dim3 grid((unsigned)tiles, (unsigned)groups, (unsigned)nlimbs);
+    const size_t smem = STMA_SMEM_BYTES(L);
+    if (literal) {
+        lg_ensure_dyn_smem<ntt_fwd_strided_tma<L, true>>(smem);
+        ntt_fwd_strided_tma<L, true><<<grid, 256, smem, st>>>(a, in_map, out_map, batch, bpc);
+    } else {
+        lg_ensure_dyn_smem<ntt_fwd_strided_tma<L, false>>(smem);
+        ntt_fwd_strided_tma<L, false><<<grid, 256, smem, st>>>(a, in_map, out_map, batch, bpc);
+    }
+    return true;
+}
+
 void launch_strided_any(int L, bool fwd, bool literal, const NttArgs& a0, dim3 grid, cudaStream_t st) {
     NttArgs a = a0;
+    if (fwd && grid.x >= 2 && !lg_switches().no_strided_tma.load(std::memory_order_relaxed)) {  // grid = (batch, tiles, limbs)
+        bool done = false;
+        switch (L) {
+            case 4: done = launch_strided_tma<4>(literal, a, (int)grid.x, (int)grid.z, st); break;
+            case 5: done = launch_strided_tma<5>(literal, a, (int)grid.x, (int)grid.z, st); break;
+            case 6: done = launch_strided_tma<6>(literal, a, (int)grid.x, (int)grid.z, st); break;
+            case 7: done = launch_strided_tma<7>(literal, a, (int)grid.x, (int)grid.z, st); break;
+            default: done = launch_strided_tma<8>(literal, a, (int)grid.x, (int)grid.z, st); break;
+        }
+        if (done) return;
+    }
     a.tfast = (lg_switches().tile_fastest.load(std::memory_order_relaxed) && grid.x <= 65535u) ? 1 : 0;
     if (a.tfast) grid = dim3(grid.y, grid.x, grid.z);
     switch (L) {
@@ -1558,30 +1785,8 @@ int lg_launch_range_flags(const NttArgs& args, int nlimbs, int batch, u32* flags
 }
 
 int lg_encode_key_tensor_map(void* map, const u64* keyf, size_t words) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = [] {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            fn = nullptr;
-        }
-        return (EncodeFn)fn;
-    }();
-    if (!encode || words % 16 != 0 || (words >> 4) > 0x7fffffffull || ((uintptr_t)keyf & 15) != 0) return 1;
-    const cuuint64_t gdim[2] = {16, (cuuint64_t)(words >> 4)};
-    const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {16, 32};  // a warp pair's 32 rows of a 2048-word tile
-    const cuuint32_t estride[2] = {1, 1};
-    CUtensorMap m;
-    if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)keyf, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return 1;
-    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
-    memcpy(map, &m, sizeof(m));
-    return 0;
+    if (words % 16 != 0) return 1;
+    return encode_words_2d(map, keyf, 16, words >> 4, 16, 32, true);  // a warp pair's 32 rows of a 2048-word tile
 }
 
 int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t st) {
