@@ -111,8 +111,8 @@ struct NttArgs {
     // of that entry are the digit's own ones: data limbs whose TABLE limb tl lies in
     // [digit*skip_alpha, min((digit+1)*skip_alpha, skip_nl))
     int skip_alpha, skip_div, skip_nl;
-    // inverse only: per (batch, limb) flag, non-zero = some input word is above 2q, use the literal
-    // butterflies for that limb (written by lg_launch_range_flags); nullptr = inputs known to be in range
+    // inverse only: per data limb flag, non-zero = some input word of that limb (in any batch entry) is above 2q, use the
+    // literal butterflies for that limb (written by lg_launch_range_flags); nullptr = inputs known to be in range
     const u32* flags;
     int no_d64;                      // set by the launchers from the "no_d64_ntt" switch
     int batch0;                      // index of the launch's first batch entry in the caller's batch (tail addressing)
@@ -126,7 +126,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
 // forward transform, strided phase only, in place or out of place (logN >= 12); the contiguous phase is
 // then run by lg_launch_ks_fused
 int lg_launch_ntt_fwd_strided(const NttArgs& args, int nlimbs, int batch, cudaStream_t st);
-// flags[b*nlimbs + j] = any word of limb j of batch entry b is > 2q
+// flags[j] = any word of data limb j (over the whole batch) is > 2q
 int lg_launch_range_flags(const NttArgs& args, int nlimbs, int batch, u32* flags, cudaStream_t st);
 
 // Key-switch digit loop fused with the contiguous NTT phase (ckks/evaluator.go:1511-1552,

@@ -645,8 +645,7 @@ __global__ void __launch_bounds__(CONTIG_THREADS, 4) ntt_contig_pipe(const NttAr
         mode = LITERAL ? M_LITERAL : fwd_mode(lc.q, a.no_d64);
     } else {
         bool flagged = LITERAL;  // one flagged entry makes the whole group literal (always exact)
-        if (a.flags != nullptr)
-            for (int i = 0; i < nb; ++i) flagged |= a.flags[(size_t)(b0 + i) * gridDim.z + j] != 0;
+        if (a.flags != nullptr) flagged |= a.flags[j] != 0;
         mode = flagged ? M_LITERAL : inv_mode(lc.q, a.no_d64);
     }
     if (mode == M_D64)
@@ -1190,7 +1189,12 @@ __global__ void __launch_bounds__(KSF_THREADS, 2) ks_fused_tma_kernel(const KsFu
 // work IN PLACE on the buffer (the exchange between them uses the slots the values were read from), and the result leaves with
 // a TMA store (bulk_group) while the next entry is transformed.  No thread issues a global load or store; twiddles are staged
 // once per CTA.  256 threads, up to 128 registers, 2 CTAs/SM.
+#ifndef STMA_STAGES
 #define STMA_STAGES 3
+#endif
+#ifndef STMA_MINB
+#define STMA_MINB 2
+#endif
 #define STMA_SMEM_BYTES(L) (STMA_STAGES * 32768u + 32u * ((1u << ((L) - 4)) + 1u) * 8u + 64u + 128u)
 
 LG_DEV void tma_load_box(u32 dst, const CUtensorMap* map, int col, int row, u32 bar) {
@@ -1257,7 +1261,7 @@ LG_DEV void fwd_strided_tile(const NttArgs& a, const LimbConst& lc, int tl, u64*
 }
 
 template <int L, bool LITERAL>
-__global__ void __launch_bounds__(256, 2) ntt_fwd_strided_tma(const NttArgs a, const __grid_constant__ CUtensorMap in_map,
+__global__ void __launch_bounds__(256, STMA_MINB) ntt_fwd_strided_tma(const NttArgs a, const __grid_constant__ CUtensorMap in_map,
                                                                const __grid_constant__ CUtensorMap out_map, int batch, int bpc) {
     extern __shared__ __align__(16) u64 ks_smem[];
     constexpr int W = 256 >> (L - 4);
@@ -1298,7 +1302,7 @@ __global__ void __launch_bounds__(256, 2) ntt_fwd_strided_tma(const NttArgs a, c
     }
     __syncthreads();
     if (t == 0) {
-        for (int i = 0; i < 2 && i < nb; ++i) {
+        for (int i = 0; i < STMA_STAGES - 1 && i < nb; ++i) {
             mbar_expect_tx(bars + 8 * i, 32768u);
             tma_load_box(sbase + 32768u * i, &in_map, col0, in_row(i), bars + 8 * i);
         }
@@ -1306,12 +1310,12 @@ __global__ void __launch_bounds__(256, 2) ntt_fwd_strided_tma(const NttArgs a, c
 #pragma unroll 1
     for (int i = 0; i < nb; ++i) {
         const int s = i % STMA_STAGES;
-        if (t == 0 && i + 2 < nb) {
-            // the buffer of entry i+2 held entry i-1: its store must have finished reading shared memory
+        if (t == 0 && i + STMA_STAGES - 1 < nb) {
+            // the buffer of entry i+STAGES-1 held entry i-1: its store must have finished reading shared memory
             bulk_wait_read<0>();
-            const int s2 = (i + 2) % STMA_STAGES;
+            const int s2 = (i + STMA_STAGES - 1) % STMA_STAGES;
             mbar_expect_tx(bars + 8 * s2, 32768u);
-            tma_load_box(sbase + 32768u * s2, &in_map, col0, in_row(i + 2), bars + 8 * s2);
+            tma_load_box(sbase + 32768u * s2, &in_map, col0, in_row(i + STMA_STAGES - 1), bars + 8 * s2);
         }
         mbar_wait(bars + 8 * s, (u32)(i / STMA_STAGES) & 1u);
         u64* tile = base + s * 4096;
@@ -1336,7 +1340,7 @@ __global__ void __launch_bounds__(256, 2) ntt_fwd_strided_tma(const NttArgs a, c
 }
 
 LG_DEV bool inv_flagged(const NttArgs& a) {
-    return a.flags != nullptr && a.flags[(size_t)cta_x(a) * gridDim.z + cta_z(a)] != 0;
+    return a.flags != nullptr && a.flags[cta_z(a)] != 0;
 }
 
 // ---- inverse, strided phase: last L stages + MRed by N^-1 --------------------
@@ -1411,8 +1415,10 @@ __global__ void __launch_bounds__(256, STRIDED_MINB) ntt_inv_strided(const NttAr
         inv_strided_body<L, M_LITERAL>(a, s, sm, tws_sm);
 }
 
-// flags[b*nlimbs + j] != 0 when some word of the limb exceeds 2q (the inverse then has to be literal);
-// flags are zeroed by the launcher, every CTA scans up to 4096 words
+// flags[j] != 0 when some word of data limb j, in ANY batch entry, exceeds 2q: the inverse transform of that limb is then
+// literal for the whole batch.  One decision per limb keeps the two phases consistent -- they exchange raw doubles
+// (FP64-only butterflies) or integers (literal) through HBM, and their CTAs group the batch entries differently.
+// The flags are zeroed by the launcher, every CTA scans up to 4096 words.
 __global__ void __launch_bounds__(256) range_flags_kernel(const NttArgs a, u32* flags) {
     const int j = blockIdx.z, b = blockIdx.x;
     const u64 twoq = 2 * a.T.q[a.map(j)];
@@ -1424,7 +1430,7 @@ __global__ void __launch_bounds__(256) range_flags_kernel(const NttArgs a, u32* 
         bad |= (v.x > twoq) | (v.y > twoq);
     }
     bad = __syncthreads_or(bad);
-    if (bad && threadIdx.x == 0) atomicOr(flags + (size_t)b * gridDim.z + j, 1u);
+    if (bad && threadIdx.x == 0) atomicOr(flags + j, 1u);
 }
 
 // ---- small rings (logN <= 11): one CTA per limb, radix-2 in shared memory ----
@@ -1515,7 +1521,10 @@ static int encode_words_2d(void* map, const u64* ptr, size_t cols, size_t rows, 
     return 0;
 }
 
-// forward strided phase by TMA (ntt_fwd_strided_tma): false = not applicable, the caller launches ntt_fwd_strided
+// forward strided phase by TMA (ntt_fwd_strided_tma): false = not applicable, the caller launches ntt_fwd_strided.  (The
+// same ring for the inverse strided phase measured slower, 620 against 610 us per 1088 limb-NTTs: with its N^-1 product that
+// phase is bound by the FP64 pipe, 70 % busy, and loses more with 16 instead of 32 warps per SM than the asynchronous
+// copies give back.)
 template <int L>
 static bool launch_strided_tma(bool literal, const NttArgs& a, int batch, int nlimbs, cudaStream_t st) {
     const u32 N = a.T.N;
@@ -1738,7 +1747,7 @@ int lg_launch_ntt(const NttArgs& args, int nlimbs, int batch, bool inverse, cuda
         first.in = args.in + (size_t)g0 * args.in_bstride;
         first.out = args.out + (size_t)g0 * args.out_bstride;
         first.batch0 = g0;
-        if (args.flags) first.flags = args.flags + (size_t)g0 * nlimbs;
+        first.flags = args.flags;  // per limb, whatever the batch group
         NttArgs second = first;  // the second phase runs in place on the output
         second.in = first.out;
         second.in_bstride = args.out_bstride;
@@ -1778,7 +1787,7 @@ int lg_launch_ntt_fwd_strided(const NttArgs& args, int nlimbs, int batch, cudaSt
 
 int lg_launch_range_flags(const NttArgs& args, int nlimbs, int batch, u32* flags, cudaStream_t st) {
     if (nlimbs <= 0 || batch <= 0) return 0;
-    cudaMemsetAsync(flags, 0, (size_t)batch * nlimbs * sizeof(u32), st);
+    cudaMemsetAsync(flags, 0, (size_t)nlimbs * sizeof(u32), st);
     range_flags_kernel<<<dim3(batch, (args.T.N + 4095) / 4096, nlimbs), 256, 0, st>>>(args, flags);
     lg_g_launches += 1;
     return 0;

@@ -128,6 +128,33 @@ def test_ntt_parity(lg, logN, kind):
         assert np.array_equal(q.numpy(), x)
 
 
+@pytest.mark.parametrize("logN", [12, 16])
+def test_invntt_mixed_batch(lg, logN):
+    """A batch whose entries differ in kind: in-range words in some entries, arbitrary 64-bit words in others, for moduli
+    of every butterfly class.  The inverse transform's two phases exchange raw doubles (FP64-only butterflies) or integers
+    (literal butterflies, taken when a word exceeds 2q) through HBM, so they must take the same decision per limb whatever
+    their CTAs' grouping of the batch entries."""
+    N = 1 << logN
+    moduli = orc.generate_ntt_primes(45, logN, 2) + orc.generate_ntt_primes(55, logN, 1) + orc.generate_ntt_primes(60, logN, 1)
+    rng = np.random.default_rng(41 + logN)
+    o = orc.Context(N, moduli)
+    ctx = lg.ring.NewContextWithParams(N, moduli)
+    batch = 5
+    a = uniform(rng, moduli, N, batch)
+    a[1] = words(rng, len(moduli), N)          # every limb of entry 1 out of range
+    a[3, 0] = words(rng, 1, N)[0]              # one limb of entry 3
+    a[4, 2, 7] = np.uint64((1 << 64) - 1)      # a single word
+    pa, pb = lg.ring.Poly.from_numpy(a), lg.ring.Poly(N, len(moduli), batch)
+    ctx.InvNTT(pa, pb)
+    got = pb.numpy(squeeze=False)
+    for b in range(batch):
+        assert np.array_equal(got[b], o.invntt(np.ascontiguousarray(a[b]))), b
+    ctx.NTT(pa, pb)
+    got = pb.numpy(squeeze=False)
+    for b in range(batch):
+        assert np.array_equal(got[b], o.ntt(np.ascontiguousarray(a[b]))), b
+
+
 def test_ntt_from_go_tables_and_single_limb(lg):
     """tables supplied by the host language (lg_ring_create_from_tables) and the free
     functions ring.NTT / ring.InvNTT on one limb (ntt.go:53, :89)"""
