@@ -565,7 +565,7 @@ def run_gpu(args):
     bf_rate = butterflies / (fwd_us * 1e-6)
     bf_peak = butterflies / (int_floor_us * 1e-6)
     roofline = {
-        "bound": "int", "kernel": "ntt_fwd (strided phase + pipelined contiguous phase, one batched limb-NTT launch pair)",
+        "bound": "int", "kernel": "ntt_fwd (TMA-fed strided phase + pipelined contiguous phase, one batched limb-NTT launch pair)",
         "achieved": bf_rate / 1e9, "peak": bf_peak / 1e9, "unit": "Gbutterfly/s", "frac": bf_rate / bf_peak,
         "traffic": traffic, "limb_mix": mix,
         "peak_source": "profiles/r02_fp64_butterfly.txt + profiles/r01_butterfly_peaks.txt (register-resident butterfly "

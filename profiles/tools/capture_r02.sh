@@ -24,7 +24,7 @@ timeout 300 ncu --set full --clock-control none -k regex:ntt_fwd_strided\|ntt_co
 ncu -i gpurun_out/nttfwd_$V.ncu-rep --page raw --csv > gpurun_out/nttfwd_${V}_raw.csv 2>/dev/null
 python profiles/tools/ntt_fwd_traffic.py gpurun_out/nttfwd_${V}_raw.csv 65536 34 32 gpurun_out/r02_ncu_ntt_fwd.json; cat gpurun_out/r02_ncu_ntt_fwd.json
 rm -f gpurun_out/nttfwd_$V.ncu-rep
-for sel in ks_fused_tma_kernel:0 ks_fused_kernel:0 ntt_fwd_strided:0 ntt_contig_pipe:0 ntt_contig_pipe:1 ntt_contig_pipe:2 ntt_contig_pipe:3 modup_fp_kernel:0 ntt_inv_strided:0; do
+for sel in ks_fused_tma_kernel:0 ks_fused_kernel:0 ntt_fwd_strided_tma:0 ntt_contig_pipe:0 ntt_contig_pipe:1 ntt_contig_pipe:2 ntt_contig_pipe:3 modup_fp_kernel:0 ntt_inv_strided:0; do
   kn=${sel%%:*}; sk=${sel##*:}
   ncu -i gpurun_out/step_full_$V.ncu-rep --page source --csv --print-source sass -k regex:$kn --launch-skip $sk --launch-count 1 \
     > gpurun_out/src_${kn}_${sk}_$V.csv 2>/dev/null

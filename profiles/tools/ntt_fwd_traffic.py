@@ -21,7 +21,7 @@ def main(path, N, limbs, batch, out):
         name = d[ix["Kernel Name"]]
         grid = d[ix["Grid Size"]].replace(" ", "")
         g = [int(x) for x in grid.strip("()").split(",")]
-        if "ntt_fwd_strided" in name and batch in (g[0], g[1]) and g[2] == limbs:  # (batch, tiles, limbs) or tiles fastest
+        if "ntt_fwd_strided" in name and g[2] == limbs:  # ntt_fwd_strided (batch, tiles, limbs) / _tma (tiles, batch groups, limbs)
             found["strided"] = d
         if "ntt_contig_pipe<(bool)1" in name.replace(" ", "") or "ntt_contig_pipe<1" in name.replace(" ", ""):
             if g[2] == limbs and g[1] == N // 2048:
