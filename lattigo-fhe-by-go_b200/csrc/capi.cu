@@ -272,6 +272,9 @@ int lgi_ring_build_device(lg_ring* r) {
     r->T.N = (u32)r->N;
     r->T.logN = r->logN;
     r->T.nl = r->nl;
+    r->T.d64_mask = 0;
+    for (int i = 0; i < r->nl && i < 64; ++i)
+        if (r->q[i] < (3ull << 44)) r->T.d64_mask |= 1ull << i;
     return LG_OK;
 }
 

@@ -29,6 +29,7 @@ struct RingTables {
     u32 N;
     u32 logN;
     int nl;
+    u64 d64_mask;  // bit tl set: table limb tl is below 3*2^44 (FP64-only transforms); host-side launch heuristics read it
 };
 
 // Maps the j-th data limb of a launch to a table limb: the first n0 data limbs

@@ -1531,6 +1531,17 @@ static bool launch_strided_tma(bool literal, const NttArgs& a, int batch, int nl
     const size_t in_ls = a.bcast.enabled ? 0 : (a.in_ls ? a.in_ls : N), out_ls = a.out_ls ? a.out_ls : N;
     if ((a.in_bstride | a.out_bstride | in_ls | out_ls) & 255) return false;
     if (batch > 1 && (a.in_bstride == 0 || a.out_bstride == 0)) return false;
+    // The ring pays where the phase is HBM-bound: limbs on the 8-instruction FP64 butterflies, and enough work for two
+    // waves of CTAs that still pipeline four entries each.  Integer-butterfly limbs (60-bit rings: C1 3.43 -> 3.36 M NTT/s
+    // with the ring) and small batches (C5, 8 parties: 13.6 -> 12.7 k rounds/s) are bound by issue slots and by grid size and
+    // keep the per-thread-load kernel with its 32 warps per SM.
+    int fp = 0;
+    for (int j = 0; j < nlimbs; ++j) {
+        const int tl = a.map(j);
+        fp += (tl >= 0 && tl < 64) ? (int)((a.T.d64_mask >> tl) & 1) : 0;
+    }
+    if (a.no_d64 || 2 * fp < nlimbs) return false;
+    if ((long)(N / 4096) * nlimbs * ((batch + 3) / 4) < 2L * 148 * 2) return false;
     const size_t rows_in = ((size_t)(batch - 1) * a.in_bstride + (size_t)(nlimbs - 1) * in_ls + N) >> 8;
     const size_t rows_out = ((size_t)(batch - 1) * a.out_bstride + (size_t)(nlimbs - 1) * out_ls + N) >> 8;
     constexpr unsigned W = 256u >> (L - 4), R = 1u << L;
