@@ -1833,6 +1833,14 @@ int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t
         else
             zint[nint++] = (unsigned char)j;
     }
+    // The two launches write disjoint limbs: when both exist the integer one goes to an auxiliary stream, forked from `st`
+    // before the TMA launch and joined after, so that its CTAs fill the SMs as the TMA kernel drains (and the other way round).
+    LgAux* aux = (nfp > 0 && nint > 0 && !lg_switches().no_aux_streams.load(std::memory_order_relaxed)) ? lg_aux_streams() : nullptr;
+    cudaStream_t ks = st;
+    if (aux) {
+        lg_aux_fork(aux, st, 1);
+        ks = aux->s[0];
+    }
     if (nfp > 0) {
         KsFusedArgs f = k;
         f.rev = 0;
@@ -1850,11 +1858,12 @@ int lg_launch_ks_fused(const KsFusedArgs& a, int nlimbs, int batch, cudaStream_t
     const dim3 grid(batch, tiles, nint);
     if (literal) {
         lg_ensure_dyn_smem<ks_fused_kernel<true>>(smem);
-        ks_fused_kernel<true><<<grid, CONTIG_THREADS, smem, st>>>(k);
+        ks_fused_kernel<true><<<grid, CONTIG_THREADS, smem, ks>>>(k);
     } else {
         lg_ensure_dyn_smem<ks_fused_kernel<false>>(smem);
-        ks_fused_kernel<false><<<grid, CONTIG_THREADS, smem, st>>>(k);
+        ks_fused_kernel<false><<<grid, CONTIG_THREADS, smem, ks>>>(k);
     }
     lg_g_launches += 1;
+    if (aux) lg_aux_join(aux, st, 1);
     return 0;
 }
