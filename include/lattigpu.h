@@ -78,7 +78,14 @@ uint64_t lg_launch_count(void);
  * "no_fused_tail" (ModDown / rescale tail placement), "ks_scratch_words" (value = digit scratch budget of the key
  * switch in 64-bit words, 0 restores the 6 GiB default), "ntt_l2_bytes" (value = bytes of first-phase output a group of
  * batch entries of a two-phase NTT may hold, 0 = default: no grouping), "reverse_walk" (second NTT phases walk their
- * grid backwards; default off).  Unknown names return LG_ERR_ARG. */
+ * grid backwards; default off), "ntt_l2_streams" (1 / 2: the groups of "ntt_l2_bytes" alternate between two auxiliary
+ * streams, by batch entries / by limbs), "tile_fastest" (default 1: strided NTT phases walk the tiles of a limb fastest),
+ * "no_strided_tma" (forward strided NTT phase with per-thread loads instead of the TMA ring), "no_ks_tma" (every limb of
+ * the fused digit loop on the register-key kernel instead of the TMA kernel), "ks_key_pf" (on the TMA digit loop: bit 0 =
+ * suspend-time hint on the key wait, bit 1 = one key hand-off per CTA instead of one per warp pair; on the register-key
+ * kernel: 1 / 2 = L1 prefetch of the key lines before the second register block / at the top of the iteration), "tail_pf"
+ * (1 / 2 = L1 / L2 prefetch of the ModDown-tail operands), "no_aux_streams" (independent launches of one call stay on the
+ * caller's stream instead of auxiliary streams forked from and joined to it).  Unknown names return LG_ERR_ARG. */
 int lg_debug_set_switch(const char* name, uint64_t value);
 
 /* ---- ring.Context -------------------------------------------------------- */

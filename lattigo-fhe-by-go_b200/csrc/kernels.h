@@ -31,14 +31,16 @@ struct LgSwitches {
     // 1088 limb-NTTs unsplit against 608 us at 96 MiB and 1040 us at 12..32 MiB.
     std::atomic<uint64_t> ntt_l2_bytes{0};
     std::atomic<int> ntt_l2_streams{0};  // LATTIGPU_NTT_L2_STREAMS: the groups alternate between two auxiliary streams
-    // LATTIGPU_KS_KEY_PF / LATTIGPU_TAIL_PF: software prefetch (prefetch.global.L1, one instruction per 128-byte line) of the
-    // key lines of the current digit in the fused digit loop, and of the ModDown / rescale tail operands in the last NTT
-    // phase, issued before the second register block; 0 = off (A/B).
+    // LATTIGPU_KS_KEY_PF / LATTIGPU_TAIL_PF (A/B, 0 = off; lattigpu.h lists the values): software prefetch
+    // (prefetch.global.L1, one instruction per 128-byte line) of the key lines of the current digit in ks_fused_kernel and of
+    // the ModDown / rescale tail operands in the last NTT phase -- measured, no gain (profiles/r02_prefetch_ab.jsonl); on
+    // ks_fused_tma_kernel "ks_key_pf" selects the hand-off variants instead (suspend-time hint, one hand-off per CTA).
     std::atomic<int> ks_key_pf{0};
     // LATTIGPU_NO_KS_TMA: every limb of the fused digit loop on ks_fused_kernel (keys through registers); default: the
     // FP64-class limbs on ks_fused_tma_kernel (two batch entries per CTA, key tiles through shared memory by TMA)
     std::atomic<int> no_ks_tma{0};
-    // LATTIGPU_NO_AUX_STREAMS: the per-digit basis extensions of a small batch stay on the caller's stream
+    // LATTIGPU_NO_AUX_STREAMS: independent launches of one call stay on the caller's stream (the per-digit basis extensions
+    // of a single ciphertext, the integer launch of the fused digit loop beside the TMA one)
     std::atomic<int> no_aux_streams{0};
     // LATTIGPU_NO_STRIDED_TMA: the forward strided NTT phase with per-thread loads and stores (ntt_fwd_strided) instead of
     // the TMA-fed ring (ntt_fwd_strided_tma)
@@ -151,7 +153,7 @@ struct KsFusedArgs {
     int acc64;            // 1 = never take the 96-bit accumulators (LATTIGPU_KS_ACC64=1: A/B and cross-check)
     int no_d64;           // set by the launcher from the "no_d64_ntt" switch
     int rev;              // walk the grid backwards (set by the launcher)
-    int pf;               // prefetch the key lines into L1 (set by the launcher from the "ks_key_pf" switch)
+    int pf;               // the "ks_key_pf" switch (set by the launcher): key-line prefetch / TMA hand-off variants, see lattigpu.h
     // blockIdx.z -> data limb (set by the launcher when it splits the limbs between ks_fused_kernel and ks_fused_tma_kernel)
     int use_zl;
     unsigned char zl[LG_MAX_LIMBS];

@@ -12,14 +12,15 @@
 // canonical kernels) or run lg_launch_range_flags first, and flagged limbs take the literal InvButterfly.
 // Moduli >= 2^61 and LATTIGPU_LITERAL_NTT=1 use the literal butterflies throughout (A/B and cross-check).
 //
-// Schedule (N = 2^logN, one limb = N words, grid = batch x tiles x limbs -- batch fastest, so the CTAs that
-// share a limb's twiddles and key tile run together and hit L2):
+// Schedule (N = 2^logN, one limb = N words; the CTAs that share a limb's twiddles and key tile run together and hit L2:
+// limbs are the slowest grid dimension; the contiguous phases walk the batch fastest, the strided phases the tiles):
 //   logN <= 11 : one CTA per limb, radix-2 stages in shared memory.
 //   logN >= 12 : two phases of register-resident radix-16 blocks (16 coefficients per thread, 4 stages,
 //                8 independent butterflies per stage)
 //     "strided" phase : the top L = logN-8 stages; a 256-thread CTA owns all 2^L rows of
 //                       W = 4096/2^L adjacent columns (coalesced 8*W-byte rows) and re-distributes
-//                       through shared memory once,
+//                       through shared memory once; forward and HBM-bound: the tile moves by TMA through a ring of
+//                       three buffers (ntt_fwd_strided_tma),
 //     "contig"  phase : the low 8 stages on contiguous 256-word segments; 16 threads own a segment, so
 //                       the exchange is warp-synchronous (no CTA barrier) and every thread ends with 16
 //                       consecutive words that move with 256-bit loads/stores.
