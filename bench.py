@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rotate", action="store_true")
     ap.add_argument("--hoisted-rotations", type=int, default=8, help="rotations per RotateHoisted call")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the batch is cut into for the pipelined e2e path")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks the batch is cut into for the pipelined e2e path")
     ap.add_argument("--params", type=int, default=PARAMS_ID, help="index into ckks.DefaultParams (default PN16QP1761)")
     ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"],
                     help="BASELINE.json configuration (default C4 = the headline; the others print the same JSON contract)")
